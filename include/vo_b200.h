@@ -1,0 +1,207 @@
+/*
+ * vo_b200.h -- C ABI of the B200-native hot path of visual_odometry_ros.
+ *
+ * The reference has no FFI layer: its boundary is the public C++ surface of
+ *   core/visual_odometry/feature_tracker.h:44-104          (FeatureTracker)
+ *   core/visual_odometry/motion_estimator.h:107-147        (MotionEstimator)
+ *   core/visual_odometry/ba_solver/sparse_bundle_adjustment.h:105-130
+ *   core/util/triangulate_3d.h:16-30                       (mapping::triangulateDLT)
+ *   standalone/motion_estimator/motion_estimator.h:22-35
+ *   standalone/depth_filter/depth_filter.h:13-21
+ * The C++ shim classes in visual_odometry_ros_b200/host/ keep those signatures and
+ * call ONLY the functions below.  Plain pointers and sizes, no torch / Eigen / cv types.
+ *
+ * Conventions
+ *  - every function returns an int status: VO_OK (0) or a negative VO_ERR_* code; the
+ *    shim maps codes back to the reference's std::runtime_error texts.
+ *  - pointers are HOST pointers unless the parameter name ends in `_d` (device pointer)
+ *    or the function name ends in `_d` (all array arguments are device pointers; the
+ *    call is asynchronous on the context's stream and does not synchronise).
+ *  - 2-D points are interleaved float32 (x, y) == cv::Point2f (define_type.h:16);
+ *    3-D points interleaved float32 (x, y, z) == Eigen::Vector3f (define_type.h:17);
+ *    poses are 4x4 float32 ROW-major here (the shim transposes Eigen's column-major
+ *    PoseSE3, define_type.h:42); masks are one uint8 per element (the shim unpacks
+ *    std::vector<bool>, define_type.h:36).
+ *  - one vo_ctx == one GPU + one CUDA stream + a set of image slots holding
+ *    device-resident pyramids.  There is NO CPU fallback: without a CUDA device
+ *    vo_ctx_create fails with VO_ERR_NO_DEVICE.
+ */
+#ifndef VO_B200_H_
+#define VO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VO_API __attribute__((visibility("default")))
+#else
+#define VO_API
+#endif
+
+#define VO_OK                 0
+#define VO_ERR_INVALID_ARG   -1
+#define VO_ERR_CUDA          -2
+#define VO_ERR_SIZE_MISMATCH -3  /* reference: "X.size() != pts1.size()" etc. */
+#define VO_ERR_NAN           -4  /* reference: NaN runtime_errors */
+#define VO_ERR_MODE          -5  /* reference: stereo/mono mode misuse */
+#define VO_ERR_NO_DEVICE     -6
+#define VO_ERR_LARGE_UPDATE  -7  /* reference: LBA "large update!" (sparse_bundle_adjustment.cpp:731) */
+
+/* cv::OPTFLOW_USE_INITIAL_FLOW (feature_tracker.cpp:71,110,119,188) */
+#define VO_KLT_USE_INITIAL_FLOW 4
+
+typedef struct vo_ctx vo_ctx;
+
+VO_API const char *vo_status_string(int status);
+/* Last CUDA / argument error text recorded on this context (never NULL). */
+VO_API const char *vo_last_error(const vo_ctx *ctx);
+/* Library build info: "vo_b200 <version> sm_100a nvcc <ver>". */
+VO_API const char *vo_build_info(void);
+
+/* ------------------------------------------------------------------ context */
+/* device: CUDA ordinal. n_slots image slots, each sized for max_w x max_h u8 images
+ * (pyramid + Scharr derivative pyramid, all levels).  max_feat: capacity of the
+ * internal staging used by the host-pointer entry points.  stream: a cudaStream_t to
+ * launch on (e.g. torch's current stream) or NULL to let the context own one. */
+VO_API int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int max_feat,
+                  void *stream, vo_ctx **out);
+VO_API int vo_ctx_destroy(vo_ctx *ctx);
+VO_API int vo_ctx_synchronize(vo_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench `gpu_launches`). */
+VO_API long long vo_ctx_launch_count(const vo_ctx *ctx);
+
+/* ------------------------------------------------------------------ images / pyramids
+ * Replaces the per-call cv::buildOpticalFlowPyramid inside cv::calcOpticalFlowPyrLK
+ * (feature_tracker.cpp:29 ...) -- pyramids are built once per image, on device. */
+/* Async H2D of a CV_8UC1 image (row pitch `step` bytes) into slot; marks pyramid stale. */
+VO_API int vo_upload_image(vo_ctx *ctx, int slot, const uint8_t *data, int w, int h, size_t step);
+/* Same, source already on the device. */
+VO_API int vo_set_image_d(vo_ctx *ctx, int slot, const uint8_t *data_d, int w, int h, size_t step);
+/* Build pyramid levels 0..n_levels-1 (+ Scharr derivative if with_deriv) for a batch of
+ * slots now (otherwise built lazily by the first tracking call that needs them). */
+VO_API int vo_build_pyramids(vo_ctx *ctx, const int *slots, int n_slots, int n_levels, int with_deriv);
+/* Effective maxLevel after OpenCV's clamp (next level w or h <= win -> stop). */
+VO_API int vo_effective_max_level(int w, int h, int win, int max_level);
+/* Debug/parity read-back of one level: img (w_l*h_l u8) and/or deriv (w_l*h_l*2 int16). */
+VO_API int vo_read_pyramid_level(vo_ctx *ctx, int slot, int level, uint8_t *img, int16_t *deriv,
+                          int *w_l, int *h_l);
+
+/* ------------------------------------------------------------------ raw pyramidal LK
+ * == cv::calcOpticalFlowPyrLK(img[slot0], img[slot1], pts0, pts1, status, err,
+ *        Size(win,win), max_level, TermCriteria(COUNT+EPS,30,0.01), flags, 1e-4)
+ * err is written 0 where status==0 (OpenCV leaves it undefined there). */
+VO_API int vo_klt_track(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n, int win,
+                 int max_level, int flags, float *pts1_inout, uint8_t *status, float *err);
+/* Batched, device-resident: n_pairs independent image pairs, n features each.
+ * slots0/slots1 are HOST arrays of slot ids; *_d arrays are [n_pairs][n] row-major.
+ * counters_d (nullable): int64[2*VO_MAX_LEVELS] = per level {windows templated,
+ * LK iterations executed}, accumulated (used for the algorithmic-bytes model). */
+#define VO_MAX_LEVELS 8
+VO_API int vo_klt_track_batch_d(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1,
+                         const float *pts0_d, int n, int win, int max_level, int flags,
+                         float *pts1_inout_d, uint8_t *status_d, float *err_d,
+                         long long *counters_d);
+
+/* ------------------------------------------------------------------ FeatureTracker methods
+ * (feature_tracker.cpp:13-206).  mask_inout: pre-existing entries are ANDed in, exactly as
+ * `mask_valid.resize(n, true)` keeps them (Appendix B #7); pass all-1 for a fresh mask. */
+VO_API int vo_ft_track(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n, int window_size,
+                int max_pyr_lvl, float thres_err, float *pts_track, uint8_t *mask_inout);
+VO_API int vo_ft_track_with_prior(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n,
+                           int window_size, int max_pyr_lvl, float thres_err,
+                           float *pts_track_inout, uint8_t *mask_inout);
+VO_API int vo_ft_track_bidirection(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n,
+                            int window_size, int max_pyr_lvl, float thres_err,
+                            float thres_bidirection, float *pts_track, uint8_t *mask_inout);
+VO_API int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int slot1, const float *pts0,
+                                       int n, int window_size, int max_pyr_lvl, float thres_err,
+                                       float thres_bidirection, float *pts_track_inout,
+                                       uint8_t *mask_inout);
+/* FeatureTracker::calcPrior (feature_tracker.cpp:208-234). Tw1: 4x4 row-major; K: fx,fy,cx,cy. */
+VO_API int vo_ft_calc_prior(vo_ctx *ctx, const float *pts0, const float *Xw, int n, const float *Tw1,
+                     const float *K4, float *pts1_prior);
+/* FeatureTracker::trackWithScale (feature_tracker.cpp:236-504). The float image and its
+ * 3x3 Sobel derivatives (stereo_vo.cpp:551-552) are computed on device from slot0. */
+VO_API int vo_ft_track_with_scale(vo_ctx *ctx, int slot0, int slot1, const float *pts0,
+                           const float *scale_est, int n, float *pts_track_inout,
+                           uint8_t *mask_inout);
+
+/* ------------------------------------------------------------------ pose-only Gauss-Newton
+ * MotionEstimator::poseOnlyBundleAdjustment (core motion_estimator.cpp:665-861 ==
+ * standalone motion_estimator.cpp:4-193) and _Stereo (core :863-1088 == standalone :195-411).
+ * R01/t01/T01 are in-out (row-major). Returns VO_OK and *success=0 when the result is NaN
+ * (reference returns false and leaves the pose untouched). iters_out nullable. */
+VO_API int vo_pose_gn_mono(vo_ctx *ctx, const float *X, const float *pts1, int n, float fx, float fy,
+                    float cx, float cy, int thres_reproj_outlier, float *R01_inout,
+                    float *t01_inout, uint8_t *mask_inlier, int *success, int *iters_out);
+VO_API int vo_pose_gn_stereo(vo_ctx *ctx, const float *X, const float *pts_l1, const float *pts_r1, int n,
+                      const float *K_l4, const float *K_r4, const float *T_lr,
+                      float thres_reproj_outlier, float *T01_inout, uint8_t *mask_inlier,
+                      int *success, int *iters_out);
+/* Batched device-resident variant: n_prob independent problems, problem p owns points
+ * [offsets[p], offsets[p+1]).  T01_inout_d: [n_prob][16]. One CTA per problem. */
+VO_API int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, const float *X_d,
+                              const float *pts_l1_d, const float *pts_r1_d, const float *K_l4,
+                              const float *K_r4, const float *T_lr, float thres_reproj_outlier,
+                              float *T01_inout_d, uint8_t *mask_inlier_d, int *success_d,
+                              int *iters_d);
+
+/* ------------------------------------------------------------------ triangulation
+ * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */
+VO_API int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,
+                       const float *t10, const float *K0_4, const float *K1_4, float *X0, float *X1);
+
+/* ------------------------------------------------------------------ depth filter
+ * DepthFilter::updateNormalDistribution (standalone/depth_filter/depth_filter.cpp:3-13). */
+VO_API int vo_depth_filter_normal(vo_ctx *ctx, const double *x_prev, const double *cov_prev,
+                           const double *x_curr, const double *cov_curr, int n, double *x_upd,
+                           double *cov_upd);
+/* DepthFilter::updateStudentTDistribution (depth_filter.cpp:15-46; the reference body does
+ * not compile -- semantics defined in DESIGN.md "D2").  a/b/x_min/x_max are in-out. */
+VO_API int vo_depth_filter_student_t(vo_ctx *ctx, const double *x_prev, const double *cov_prev,
+                              double *a_inout, double *b_inout, double *x_min_inout,
+                              double *x_max_inout, const double *x_curr, const double *cov_curr,
+                              int n, double *x_upd, double *cov_upd);
+
+/* ------------------------------------------------------------------ compaction
+ * Stable mask compaction == LandmarkTracking(src, mask) (landmark.cpp:194-231, 291-332):
+ * index_out[k] = index of the k-th set mask entry; *n_out = number kept. */
+VO_API int vo_compact(vo_ctx *ctx, const uint8_t *mask, int n, int *index_out, int *n_out);
+
+/* ------------------------------------------------------------------ local bundle adjustment
+ * SparseBundleAdjustmentSolver::solveForFiniteIterations
+ * (ba_solver/sparse_bundle_adjustment.cpp:150-768) on the problem SparseBAParameters packs
+ * (ba_solver/sparse_ba_parameters.h:292-465): poses/points already in the reference
+ * keyframe's frame and divided by the pose scale. FP64 throughout. */
+typedef struct vo_lba_problem {
+    int n_frames;            /* left keyframes in the window (fixed + optimisable) */
+    int n_opt;               /* optimisable left keyframes */
+    int n_points;            /* M */
+    int n_obs;               /* total observations */
+    const double *poses;     /* [n_frames][16] row-major T_jw (ref frame, scaled) */
+    const int *opt_index;    /* [n_frames] index into the optimised block, or -1 if fixed */
+    const double *points;    /* [n_points][3] */
+    const int *obs_ptr;      /* [n_points+1] CSR offsets, observation order == reference order */
+    const int *obs_frame;    /* [n_obs] left-keyframe index the observation belongs to */
+    const uint8_t *obs_right;/* [n_obs] 1 if observed in the right image */
+    const double *obs_px;    /* [n_obs][2] */
+    double K_l[4], K_r[4];   /* fx, fy, cx, cy */
+    double T_lr[16];         /* row-major, translation already scaled; identity in mono */
+    int is_stereo;
+    double huber;            /* 0.5 (motion_estimator.cpp:1232) */
+    double lambda;           /* 1e-5 (sparse_bundle_adjustment.cpp:185) */
+    int max_iter;            /* 10 (motion_estimator.cpp:1226) */
+} vo_lba_problem;
+/* poses_out [n_frames][16], points_out [n_points][3]; avg_err_out[max_iter] per-iteration
+ * sqrt(err/n_obs) (sparse_bundle_adjustment.cpp:606). *success = last avg_err <= 1 px. */
+VO_API int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *prob, double *poses_out, double *points_out,
+                 double *avg_err_out, int *success);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VO_B200_H_ */

@@ -1,0 +1,209 @@
+"""ctypes binding of ``libvo_b200.so`` (the C ABI in ``include/vo_b200.h``).
+
+This is the only way Python reaches the CUDA path; there is no CPU fallback.  If the
+shared library is missing, importing the symbols raises ``VoLibraryMissing`` loudly.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvo_b200.so")
+
+VO_OK = 0
+VO_ERR_INVALID_ARG = -1
+VO_ERR_CUDA = -2
+VO_ERR_SIZE_MISMATCH = -3
+VO_ERR_NAN = -4
+VO_ERR_MODE = -5
+VO_ERR_NO_DEVICE = -6
+VO_ERR_LARGE_UPDATE = -7
+VO_KLT_USE_INITIAL_FLOW = 4
+VO_MAX_LEVELS = 8
+
+
+class VoLibraryMissing(RuntimeError):
+    pass
+
+
+class VoError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"vo_b200 status {status}: {text}")
+        self.status = status
+
+
+_lib = None
+
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_f32_p = ctypes.POINTER(ctypes.c_float)
+c_f64_p = ctypes.POINTER(ctypes.c_double)
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+c_i16_p = ctypes.POINTER(ctypes.c_int16)
+c_i64_p = ctypes.POINTER(ctypes.c_longlong)
+vp = ctypes.c_void_p
+
+
+class LbaProblem(ctypes.Structure):
+    _fields_ = [
+        ("n_frames", ctypes.c_int), ("n_opt", ctypes.c_int), ("n_points", ctypes.c_int), ("n_obs", ctypes.c_int),
+        ("poses", c_f64_p), ("opt_index", c_int_p), ("points", c_f64_p), ("obs_ptr", c_int_p),
+        ("obs_frame", c_int_p), ("obs_right", c_u8_p), ("obs_px", c_f64_p),
+        ("K_l", ctypes.c_double * 4), ("K_r", ctypes.c_double * 4), ("T_lr", ctypes.c_double * 16),
+        ("is_stereo", ctypes.c_int), ("huber", ctypes.c_double), ("lambda_", ctypes.c_double),
+        ("max_iter", ctypes.c_int),
+    ]
+
+
+def lib():
+    """Load libvo_b200.so (built by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VoLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.vo_status_string.restype = ctypes.c_char_p
+    L.vo_last_error.restype = ctypes.c_char_p
+    L.vo_last_error.argtypes = [vp]
+    L.vo_build_info.restype = ctypes.c_char_p
+    L.vo_ctx_launch_count.restype = ctypes.c_longlong
+    L.vo_ctx_launch_count.argtypes = [vp]
+    L.vo_ctx_create.argtypes = [ctypes.c_int] * 5 + [vp, ctypes.POINTER(vp)]
+    L.vo_ctx_destroy.argtypes = [vp]
+    L.vo_ctx_synchronize.argtypes = [vp]
+    L.vo_upload_image.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+    L.vo_set_image_d.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+    L.vo_build_pyramids.argtypes = [vp, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.vo_read_pyramid_level.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, c_int_p, c_int_p]
+    L.vo_klt_track.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_int, vp, vp, vp]
+    L.vo_klt_track_batch_d.argtypes = [vp, ctypes.c_int, c_int_p, c_int_p, vp, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    ft = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float]
+    L.vo_ft_track.argtypes = ft + [vp, vp]
+    L.vo_ft_track_with_prior.argtypes = ft + [vp, vp]
+    L.vo_ft_track_bidirection.argtypes = ft + [ctypes.c_float, vp, vp]
+    L.vo_ft_track_bidirection_with_prior.argtypes = ft + [ctypes.c_float, vp, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(vp) if a is not None else None
+
+
+def check(ctx_handle, rc):
+    if rc != VO_OK:
+        L = lib()
+        txt = L.vo_status_string(rc).decode()
+        if ctx_handle:
+            txt += ": " + L.vo_last_error(ctx_handle).decode()
+        raise VoError(rc, txt)
+
+
+class Context:
+    """One GPU + one stream + ``n_slots`` device-resident image pyramids (``vo_ctx``)."""
+
+    def __init__(self, device=0, max_w=1241, max_h=376, n_slots=4, max_feat=4096, stream=None):
+        L = lib()
+        h = vp()
+        rc = L.vo_ctx_create(device, max_w, max_h, n_slots, max_feat, vp(stream) if stream else None,
+                             ctypes.byref(h))
+        if rc != VO_OK:
+            raise VoError(rc, L.vo_status_string(rc).decode())
+        self.h = h
+        self.L = L
+        self.n_slots = n_slots
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vo_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self.h, self.L.vo_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.vo_ctx_launch_count(self.h))
+
+    # ---------------------------------------------------------------- images
+    def upload_image(self, slot, img):
+        img = np.asarray(img)
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        self._keep = img  # keep alive until the async copy is consumed
+        check(self.h, self.L.vo_upload_image(self.h, slot, _ptr(img), img.shape[1], img.shape[0], img.strides[0]))
+
+    def set_image_d(self, slot, dev_ptr, w, h, step):
+        check(self.h, self.L.vo_set_image_d(self.h, slot, vp(dev_ptr), w, h, step))
+
+    def build_pyramids(self, slots, n_levels, with_deriv=True):
+        ids = np.ascontiguousarray(slots, np.int32)
+        check(self.h, self.L.vo_build_pyramids(self.h, ids.ctypes.data_as(c_int_p), len(ids), n_levels,
+                                               1 if with_deriv else 0))
+
+    def read_pyramid_level(self, slot, level, want_deriv=True):
+        w, h = ctypes.c_int(), ctypes.c_int()
+        check(self.h, self.L.vo_read_pyramid_level(self.h, slot, level, None, None, ctypes.byref(w), ctypes.byref(h)))
+        img = np.empty((h.value, w.value), np.uint8)
+        der = np.empty((h.value, w.value, 2), np.int16) if want_deriv else None
+        check(self.h, self.L.vo_read_pyramid_level(self.h, slot, level, _ptr(img), _ptr(der), ctypes.byref(w),
+                                                   ctypes.byref(h)))
+        return img, der
+
+    # ---------------------------------------------------------------- raw LK
+    def klt_track(self, slot0, slot1, pts0, win, max_level, flags=0, prior=None):
+        pts0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        n = len(pts0)
+        p1 = (np.ascontiguousarray(prior, np.float32).reshape(-1, 2).copy()
+              if flags & VO_KLT_USE_INITIAL_FLOW else np.zeros_like(pts0))
+        st = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        check(self.h, self.L.vo_klt_track(self.h, slot0, slot1, _ptr(pts0), n, win, max_level, flags, _ptr(p1),
+                                          _ptr(st), _ptr(err)))
+        return p1, st, err
+
+    def klt_track_batch_d(self, slots0, slots1, pts0_d, n, win, max_level, flags, pts1_d, status_d, err_d,
+                          counters_d=None):
+        s0 = np.ascontiguousarray(slots0, np.int32)
+        s1 = np.ascontiguousarray(slots1, np.int32)
+        check(self.h, self.L.vo_klt_track_batch_d(
+            self.h, len(s0), s0.ctypes.data_as(c_int_p), s1.ctypes.data_as(c_int_p), vp(pts0_d), n, win, max_level,
+            flags, vp(pts1_d), vp(status_d) if status_d else None, vp(err_d) if err_d else None,
+            vp(counters_d) if counters_d else None))
+
+    # ---------------------------------------------------------------- FeatureTracker methods
+    def _ft(self, fn, slot0, slot1, pts0, win, lvl, thres_err, extra, pts_track, mask):
+        pts0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        n = len(pts0)
+        pt = (np.ascontiguousarray(pts_track, np.float32).reshape(-1, 2).copy() if pts_track is not None
+              else np.zeros_like(pts0))
+        m = np.ones(n, np.uint8) if mask is None else np.ascontiguousarray(mask).astype(np.uint8).copy()
+        if len(pt) != n or len(m) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "pts_track.size() != pts0.size()")
+        args = [self.h, slot0, slot1, _ptr(pts0), n, win, lvl, thres_err] + extra + [_ptr(pt), _ptr(m)]
+        check(self.h, fn(*args))
+        return pt, m.astype(bool)
+
+    def ft_track(self, slot0, slot1, pts0, win, lvl, thres_err, mask=None):
+        return self._ft(self.L.vo_ft_track, slot0, slot1, pts0, win, lvl, thres_err, [], None, mask)
+
+    def ft_track_with_prior(self, slot0, slot1, pts0, prior, win, lvl, thres_err, mask=None):
+        return self._ft(self.L.vo_ft_track_with_prior, slot0, slot1, pts0, win, lvl, thres_err, [], prior, mask)
+
+    def ft_track_bidirection(self, slot0, slot1, pts0, win, lvl, thres_err, thres_bi, mask=None):
+        return self._ft(self.L.vo_ft_track_bidirection, slot0, slot1, pts0, win, lvl, thres_err,
+                        [ctypes.c_float(thres_bi)], None, mask)
+
+    def ft_track_bidirection_with_prior(self, slot0, slot1, pts0, prior, win, lvl, thres_err, thres_bi, mask=None):
+        return self._ft(self.L.vo_ft_track_bidirection_with_prior, slot0, slot1, pts0, win, lvl, thres_err,
+                        [ctypes.c_float(thres_bi)], prior, mask)

@@ -1,0 +1,376 @@
+// api.cu -- context management and the image / KLT part of the C ABI (include/vo_b200.h).
+#include "vo_internal.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#ifndef VO_VERSION
+#define VO_VERSION "0.1.0"
+#endif
+#define VO_STR2(x) #x
+#define VO_STR(x) VO_STR2(x)
+
+extern "C" const char *vo_status_string(int status)
+{
+    switch (status) {
+    case VO_OK: return "ok";
+    case VO_ERR_INVALID_ARG: return "invalid argument";
+    case VO_ERR_CUDA: return "CUDA error";
+    case VO_ERR_SIZE_MISMATCH: return "size mismatch";
+    case VO_ERR_NAN: return "NaN encountered";
+    case VO_ERR_MODE: return "stereo/mono mode misuse";
+    case VO_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case VO_ERR_LARGE_UPDATE: return "large update!";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *vo_last_error(const vo_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" const char *vo_build_info(void)
+{
+    return "vo_b200 " VO_VERSION " sm_100a nvcc " VO_STR(__CUDACC_VER_MAJOR__) "." VO_STR(__CUDACC_VER_MINOR__);
+}
+
+extern "C" int vo_effective_max_level(int w, int h, int win, int max_level)
+{
+    // cv::buildOpticalFlowPyramid: stop when the next level's width or height <= window
+    for (int level = 0; level < max_level; ++level) {
+        w = (w + 1) / 2;
+        h = (h + 1) / 2;
+        if (w <= win || h <= win) return level;
+    }
+    return max_level;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int max_feat, void *stream, vo_ctx **out)
+{
+    if (!out) return VO_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (max_w < 1 || max_h < 1 || n_slots < 0 || max_feat < 0) return VO_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return VO_ERR_NO_DEVICE;
+    }
+    vo_ctx *ctx = new (std::nothrow) vo_ctx();
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return VO_ERR_CUDA; }
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VO_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    ctx->max_w = max_w; ctx->max_h = max_h; ctx->n_slots = n_slots; ctx->max_feat = max_feat;
+
+    // level geometry for the maximum image; levels stop once a side would drop below 8 px
+    int lw[VO_MAX_LEVELS], lh[VO_MAX_LEVELS], nl = 0;
+    for (int w = max_w, h = max_h; nl < VO_MAX_LEVELS; ++nl) {
+        lw[nl] = w; lh[nl] = h;
+        const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw < 8 || nh < 8) { ++nl; break; }
+        w = nw; h = nh;
+    }
+    ctx->max_levels = nl;
+    size_t img_bytes = 0, der_bytes = 0;
+    for (int l = 0; l < nl; ++l) {
+        const size_t pitch = align_up((size_t)lw[l] + 2 * VO_PAD, 128);
+        const size_t rows = (size_t)lh[l] + 2 * VO_PAD;
+        img_bytes += align_up(pitch * rows, 256);
+        der_bytes += align_up(pitch * rows * sizeof(short2), 256);
+    }
+    ctx->slots.resize(n_slots);
+    for (int s = 0; s < n_slots; ++s) {
+        Slot &S = ctx->slots[s];
+        S.bytes = img_bytes + der_bytes;
+        if (cudaMalloc((void **)&S.base, S.bytes) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+        if (cudaMemsetAsync(S.base, 0, S.bytes, ctx->stream) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+        memset(&S.desc, 0, sizeof(S.desc));
+    }
+    if (n_slots > 0 && cudaMalloc((void **)&ctx->d_slots, sizeof(SlotDesc) * n_slots) != cudaSuccess) {
+        vo_ctx_destroy(ctx);
+        return VO_ERR_CUDA;
+    }
+    if (vo_stage_reserve(ctx, (size_t)(max_feat > 0 ? max_feat : 1) * 64) != VO_OK) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+    *out = ctx;
+    return VO_OK;
+}
+
+extern "C" int vo_ctx_destroy(vo_ctx *ctx)
+{
+    if (!ctx) return VO_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &S : ctx->slots) if (S.base) cudaFree(S.base);
+    if (ctx->d_slots) cudaFree(ctx->d_slots);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    for (int i = 0; i < 4; ++i) if (ctx->d_f32[i]) cudaFree(ctx->d_f32[i]);
+    if (ctx->d_lba) cudaFree(ctx->d_lba);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VO_OK;
+}
+
+extern "C" int vo_ctx_synchronize(vo_ctx *ctx)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+extern "C" long long vo_ctx_launch_count(const vo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vo_stage_reserve(vo_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->stage_bytes) return VO_OK;
+    bytes = align_up(bytes, 4096);
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->h_stage = nullptr; ctx->d_stage = nullptr; ctx->stage_bytes = 0;
+    VO_CUDA(cudaMallocHost((void **)&ctx->h_stage, bytes));
+    VO_CUDA(cudaMalloc((void **)&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+    return VO_OK;
+}
+
+// (Re)derive the level descriptors of a slot for a w x h image and push them to the device.
+static int slot_set_geometry(vo_ctx *ctx, int slot, int w, int h)
+{
+    Slot &S = ctx->slots[slot];
+    if (S.w == w && S.h == h) return VO_OK;
+    // image size changed: the zero ring of the derivative planes must be restored
+    VO_CUDA(cudaMemsetAsync(S.base, 0, S.bytes, ctx->stream));
+    size_t img_off = 0;
+    // image planes first, then derivative planes (each plane 256-B aligned)
+    int lw = w, lh = h;
+    size_t offs_img[VO_MAX_LEVELS], offs_der[VO_MAX_LEVELS];
+    int pitches[VO_MAX_LEVELS], ws[VO_MAX_LEVELS], hs[VO_MAX_LEVELS];
+    int nl = 0;
+    for (; nl < ctx->max_levels; ++nl) {
+        const size_t pitch = align_up((size_t)lw + 2 * VO_PAD, 128);
+        offs_img[nl] = img_off;
+        pitches[nl] = (int)pitch; ws[nl] = lw; hs[nl] = lh;
+        img_off += align_up(pitch * ((size_t)lh + 2 * VO_PAD), 256);
+        const int nw = (lw + 1) / 2, nh = (lh + 1) / 2;
+        if (nw < 8 || nh < 8) { ++nl; break; }
+        lw = nw; lh = nh;
+    }
+    size_t der_off = img_off;
+    for (int l = 0; l < nl; ++l) {
+        offs_der[l] = der_off;
+        der_off += align_up((size_t)pitches[l] * ((size_t)hs[l] + 2 * VO_PAD) * sizeof(short2), 256);
+    }
+    VO_REQUIRE(der_off <= S.bytes, VO_ERR_INVALID_ARG, "image larger than the context's max_w x max_h");
+    memset(&S.desc, 0, sizeof(S.desc));
+    for (int l = 0; l < nl; ++l) {
+        LevelDesc &L = S.desc.lv[l];
+        L.w = ws[l]; L.h = hs[l]; L.pitch = pitches[l];
+        L.img = S.base + offs_img[l] + (size_t)VO_PAD * pitches[l] + VO_PAD;
+        L.deriv = reinterpret_cast<short2 *>(S.base + offs_der[l]) + (size_t)VO_PAD * pitches[l] + VO_PAD;
+    }
+    S.w = w; S.h = h;
+    VO_CUDA(cudaMemcpyAsync(ctx->d_slots + slot, &S.desc, sizeof(SlotDesc), cudaMemcpyHostToDevice, ctx->stream));
+    // the descriptor lives in pageable host memory inside the vector: make the copy complete
+    // before anybody can move/modify it
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+static int set_image_common(vo_ctx *ctx, int slot, const uint8_t *data, int w, int h, size_t step, cudaMemcpyKind kind)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(slot >= 0 && slot < ctx->n_slots, VO_ERR_INVALID_ARG, "slot id out of range");
+    VO_REQUIRE(data && w >= 8 && h >= 8 && step >= (size_t)w, VO_ERR_INVALID_ARG, "bad image arguments");
+    VO_REQUIRE(w <= ctx->max_w + 0 && h <= ctx->max_h + 0, VO_ERR_INVALID_ARG, "image larger than the context's max_w x max_h");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    int rc = slot_set_geometry(ctx, slot, w, h);
+    if (rc) return rc;
+    Slot &S = ctx->slots[slot];
+    const LevelDesc &L0 = S.desc.lv[0];
+    VO_CUDA(cudaMemcpy2DAsync(L0.img, L0.pitch, data, step, w, h, kind, ctx->stream));
+    S.levels_built = 0; S.deriv_built = 0; S.border0 = false;
+    return VO_OK;
+}
+
+extern "C" int vo_upload_image(vo_ctx *ctx, int slot, const uint8_t *data, int w, int h, size_t step)
+{
+    return set_image_common(ctx, slot, data, w, h, step, cudaMemcpyHostToDevice);
+}
+
+extern "C" int vo_set_image_d(vo_ctx *ctx, int slot, const uint8_t *data_d, int w, int h, size_t step)
+{
+    return set_image_common(ctx, slot, data_d, w, h, step, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int vo_build_pyramids(vo_ctx *ctx, const int *slots, int n_slots, int n_levels, int with_deriv)
+{
+    if (!ctx || !slots) return VO_ERR_INVALID_ARG;
+    VO_CUDA(cudaSetDevice(ctx->device));
+    if (n_levels > ctx->max_levels) n_levels = ctx->max_levels;
+    return vo_ensure_pyramids(ctx, slots, n_slots, n_levels, with_deriv);
+}
+
+extern "C" int vo_read_pyramid_level(vo_ctx *ctx, int slot, int level, uint8_t *img, int16_t *deriv, int *w_l, int *h_l)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(slot >= 0 && slot < ctx->n_slots, VO_ERR_INVALID_ARG, "slot id out of range");
+    const Slot &S = ctx->slots[slot];
+    VO_REQUIRE(level >= 0 && level < S.levels_built, VO_ERR_INVALID_ARG, "level not built");
+    const LevelDesc &L = S.desc.lv[level];
+    if (w_l) *w_l = L.w;
+    if (h_l) *h_l = L.h;
+    if (img) VO_CUDA(cudaMemcpy2DAsync(img, L.w, L.img, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
+    if (deriv) {
+        VO_REQUIRE(level < S.deriv_built, VO_ERR_INVALID_ARG, "derivative level not built");
+        VO_CUDA(cudaMemcpy2DAsync(deriv, (size_t)L.w * 4, L.deriv, (size_t)L.pitch * 4, (size_t)L.w * 4, L.h,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------ KLT
+extern "C" int vo_klt_track_batch_d(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1, const float *pts0_d,
+                                    int n, int win, int max_level, int flags, float *pts1_inout_d, uint8_t *status_d,
+                                    float *err_d, long long *counters_d)
+{
+    if (!ctx || !slots0 || !slots1) return VO_ERR_INVALID_ARG;
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_klt_launch(ctx, n_pairs, slots0, slots1, pts0_d, n, win, max_level, flags, pts1_inout_d, status_d, err_d,
+                         counters_d, nullptr);
+}
+
+// Staging layout for the host-pointer entry points (one H2D + one D2H per call):
+//   [pts0 n*8][pts1 n*8][ptsb n*8][err n*4][errb n*4][status n][statusb n][mask n]
+struct KltStage {
+    size_t o_pts0, o_pts1, o_ptsb, o_err, o_errb, o_st, o_stb, o_mask, total;
+    explicit KltStage(int n)
+    {
+        size_t o = 0;
+        o_pts0 = o; o += (size_t)n * 8;
+        o_pts1 = o; o += (size_t)n * 8;
+        o_ptsb = o; o += (size_t)n * 8;
+        o_err = o; o += (size_t)n * 4;
+        o_errb = o; o += (size_t)n * 4;
+        o_st = o; o += align_up(n, 16);
+        o_stb = o; o += align_up(n, 16);
+        o_mask = o; o += align_up(n, 16);
+        total = align_up(o, 256);
+    }
+};
+
+extern "C" int vo_klt_track(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n, int win, int max_level,
+                            int flags, float *pts1_inout, uint8_t *status, float *err)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(pts0 && pts1_inout && status && err, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    KltStage L(n);
+    int rc = vo_stage_reserve(ctx, L.total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h + L.o_pts0, pts0, (size_t)n * 8);
+    size_t up = (size_t)n * 8;
+    if (flags & VO_KLT_USE_INITIAL_FLOW) { memcpy(h + L.o_pts1, pts1_inout, (size_t)n * 8); up = (size_t)n * 16; }
+    VO_CUDA(cudaMemcpyAsync(d, h, up, cudaMemcpyHostToDevice, ctx->stream));
+    rc = vo_klt_launch(ctx, 1, &slot0, &slot1, (const float *)(d + L.o_pts0), n, win, max_level, flags,
+                       (float *)(d + L.o_pts1), d + L.o_st, (float *)(d + L.o_err), nullptr, nullptr);
+    if (rc) return rc;
+    VO_CUDA(cudaMemcpyAsync(h + L.o_pts1, d + L.o_pts1, L.o_stb - L.o_pts1, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(pts1_inout, h + L.o_pts1, (size_t)n * 8);
+    memcpy(err, h + L.o_err, (size_t)n * 4);
+    memcpy(status, h + L.o_st, (size_t)n);
+    return VO_OK;
+}
+
+// FeatureTracker front-ends. mode: 1 track, 2 trackWithPrior, 3 trackBidirection, 4 trackBidirectionWithPrior
+static int ft_common(vo_ctx *ctx, int mode, int slot0, int slot1, const float *pts0, int n, int win, int max_lvl,
+                     float thres_err, float thres_bi, float *pts_track, uint8_t *mask)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(pts0 && pts_track && mask, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    KltStage L(n);
+    int rc = vo_stage_reserve(ctx, L.total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    const bool prior = (mode == 2 || mode == 4);
+    memcpy(h + L.o_pts0, pts0, (size_t)n * 8);
+    if (prior) memcpy(h + L.o_pts1, pts_track, (size_t)n * 8);
+    memcpy(h + L.o_mask, mask, (size_t)n);
+    VO_CUDA(cudaMemcpyAsync(d, h, prior ? (size_t)n * 16 : (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(d + L.o_mask, h + L.o_mask, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    const float *d_pts0 = (const float *)(d + L.o_pts0);
+    float *d_pts1 = (float *)(d + L.o_pts1);
+    KltPost post{};
+    post.thres_err = thres_err;
+    post.mask = d + L.o_mask;
+    if (mode == 1 || mode == 2) {
+        post.mode = mode;
+        rc = vo_klt_launch(ctx, 1, &slot0, &slot1, d_pts0, n, win, max_lvl, prior ? VO_KLT_USE_INITIAL_FLOW : 0, d_pts1,
+                           d + L.o_st, (float *)(d + L.o_err), nullptr, &post);
+        if (rc) return rc;
+    } else {
+        // forward pass (no mask yet), then backward pass seeded with pts0 whose epilogue fuses
+        // the bidirectional validity test (feature_tracker.cpp:57-83 / :105-149)
+        post.mode = 3;
+        rc = vo_klt_launch(ctx, 1, &slot0, &slot1, d_pts0, n, win, max_lvl, prior ? VO_KLT_USE_INITIAL_FLOW : 0, d_pts1,
+                           d + L.o_st, (float *)(d + L.o_err), nullptr, &post);
+        if (rc) return rc;
+        VO_CUDA(cudaMemcpyAsync(d + L.o_ptsb, d + L.o_pts0, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        post.mode = 4;
+        post.border = (mode == 3) ? 3 : 0;
+        post.thres_bi2 = (mode == 3) ? thres_bi * thres_bi : (thres_bi * thres_bi) * 5;
+        post.ref_pts = d_pts0;
+        post.fwd_pts = d_pts1;
+        post.fwd_status = d + L.o_st;
+        post.fwd_err = (const float *)(d + L.o_err);
+        const int back_lvl = (mode == 3) ? max_lvl - 1 : max_lvl;
+        rc = vo_klt_launch(ctx, 1, &slot1, &slot0, d_pts1, n, win, back_lvl < 0 ? 0 : back_lvl, VO_KLT_USE_INITIAL_FLOW,
+                           (float *)(d + L.o_ptsb), d + L.o_stb, (float *)(d + L.o_errb), nullptr, &post);
+        if (rc) return rc;
+    }
+    VO_CUDA(cudaMemcpyAsync(h + L.o_pts1, d + L.o_pts1, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(h + L.o_mask, d + L.o_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(pts_track, h + L.o_pts1, (size_t)n * 8);
+    memcpy(mask, h + L.o_mask, (size_t)n);
+    return VO_OK;
+}
+
+extern "C" int vo_ft_track(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n, int window_size, int max_pyr_lvl,
+                           float thres_err, float *pts_track, uint8_t *mask_inout)
+{
+    return ft_common(ctx, 1, slot0, slot1, pts0, n, window_size, max_pyr_lvl, thres_err, 0.f, pts_track, mask_inout);
+}
+extern "C" int vo_ft_track_with_prior(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n, int window_size,
+                                      int max_pyr_lvl, float thres_err, float *pts_track_inout, uint8_t *mask_inout)
+{
+    return ft_common(ctx, 2, slot0, slot1, pts0, n, window_size, max_pyr_lvl, thres_err, 0.f, pts_track_inout, mask_inout);
+}
+extern "C" int vo_ft_track_bidirection(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n, int window_size,
+                                       int max_pyr_lvl, float thres_err, float thres_bidirection, float *pts_track,
+                                       uint8_t *mask_inout)
+{
+    return ft_common(ctx, 3, slot0, slot1, pts0, n, window_size, max_pyr_lvl, thres_err, thres_bidirection, pts_track,
+                     mask_inout);
+}
+extern "C" int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int slot1, const float *pts0, int n,
+                                                  int window_size, int max_pyr_lvl, float thres_err,
+                                                  float thres_bidirection, float *pts_track_inout, uint8_t *mask_inout)
+{
+    return ft_common(ctx, 4, slot0, slot1, pts0, n, window_size, max_pyr_lvl, thres_err, thres_bidirection,
+                     pts_track_inout, mask_inout);
+}

@@ -1,0 +1,299 @@
+// klt.cu -- K-klt: pyramidal Lucas-Kanade, one warp per feature, all levels in one launch.
+//
+// Device restatement of what cv::calcOpticalFlowPyrLK does for the reference's
+// FeatureTracker (core/visual_odometry/feature_tracker.cpp:29,60,69,108,117,186):
+// OpenCV's LKTrackerInvoker semantics are reproduced exactly in the integer domain
+// (W_BITS=14 fixed-point bilinear weights, cvRound = round-half-even, int16 template with
+// 5 fractional bits, status/err only at level 0, epsilon/oscillation stopping rules).
+// The 2x2 normal-equation sums are accumulated EXACTLY: per-lane int32 partials are
+// reduced with redux.sync (two 16-bit halves -> int64), then rounded once to float --
+// OpenCV's float accumulators differ from this only by their summation-order rounding.
+//
+// Work decomposition: one warp per (pair, feature); lane L owns window pixels
+// idx = L + 32*k (k < NPX).  The template (I, Ix, Iy) lives in registers for the whole
+// level; every iteration gathers the 2x2 bilinear neighbourhood of the next image from
+// L1/L2 (the padded pyramids make the gathers branch-free), so a level costs
+// (w+1)^2 * (1 + 4 + k) algorithmic bytes, which is the figure bench.py reports against.
+#include "vo_internal.cuh"
+
+#include <cfloat>
+
+#define W_BITS 14
+
+struct KltArgs {
+    const SlotDesc *slots;
+    IdList s0, s1;
+    const float2 *pts0;
+    float2 *pts1;
+    uint8_t *status;
+    float *err;
+    unsigned long long *counters;   // [2*VO_MAX_LEVELS] or null
+    int n;
+    int win;
+    int top_level;      // effective maxLevel
+    int flags;
+    int max_count;
+    float min_eig;
+    double eps2;
+    KltPost post;
+};
+
+__device__ __forceinline__ long long warp_sum_exact(int v)
+{
+    // exact 32-lane sum of int32 partials without overflow: split in 16-bit halves
+    const int hi = v >> 16;
+    const int lo = v & 0xffff;
+    const int shi = __reduce_add_sync(0xffffffffu, hi);
+    const int slo = __reduce_add_sync(0xffffffffu, lo);
+    return ((long long)shi << 16) + (long long)slo;
+}
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11)
+{
+    const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
+    iw00 = __float2int_rn(__fmul_rn(__fmul_rn(oma, omb), (float)(1 << W_BITS)));
+    iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, omb), (float)(1 << W_BITS)));
+    iw10 = __float2int_rn(__fmul_rn(__fmul_rn(oma, b), (float)(1 << W_BITS)));
+    iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+}
+
+template <int NPX>
+__global__ void __launch_bounds__(128)
+k_klt(const KltArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int pair = blockIdx.y;
+    if (f >= a.n) return;
+    const size_t gi = (size_t)pair * a.n + f;
+    const SlotDesc &S0 = a.slots[a.s0.id[pair]];
+    const SlotDesc &S1 = a.slots[a.s1.id[pair]];
+    const int win = a.win;
+    const int npix = win * win;
+    const float halfWin = (float)(win - 1) * 0.5f;
+
+    // per-lane pixel coordinates inside the window (level independent)
+    int px[NPX], py[NPX];
+#pragma unroll
+    for (int k = 0; k < NPX; ++k) {
+        const int idx = lane + 32 * k;
+        const int y = idx / win;
+        py[k] = y;
+        px[k] = idx - y * win;
+    }
+
+    const float2 p0 = a.pts0[gi];
+    float2 stored = (a.flags & VO_KLT_USE_INITIAL_FLOW) ? a.pts1[gi] : p0;  // == nextPts[ptidx]
+    int status = 1;
+    float errv = 0.f;
+
+    for (int level = a.top_level; level >= 0; --level) {
+        const LevelDesc I = S0.lv[level];
+        const LevelDesc J = S1.lv[level];
+        const float sc = 1.f / (float)(1 << level);     // exact power of two
+        float prevx = __fmul_rn(p0.x, sc), prevy = __fmul_rn(p0.y, sc);
+        if (level == a.top_level) {
+            if (a.flags & VO_KLT_USE_INITIAL_FLOW) { stored.x = __fmul_rn(stored.x, sc); stored.y = __fmul_rn(stored.y, sc); }
+            else { stored.x = prevx; stored.y = prevy; }
+        } else {
+            stored.x = __fmul_rn(stored.x, 2.f); stored.y = __fmul_rn(stored.y, 2.f);
+        }
+        float nextx = stored.x, nexty = stored.y;
+
+        prevx = __fsub_rn(prevx, halfWin); prevy = __fsub_rn(prevy, halfWin);
+        const int ipx = __float2int_rd(prevx), ipy = __float2int_rd(prevy);
+        if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+            if (level == 0) { status = 0; errv = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(__fsub_rn(prevx, (float)ipx), __fsub_rn(prevy, (float)ipy), iw00, iw01, iw10, iw11);
+
+        // ---- template: I (5 frac bits), Ix, Iy as int16-range ints in registers; exact A sums
+        int Iv[NPX], Ix[NPX], Iy[NPX];
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+        {
+            const uint8_t *ib = I.img + (ptrdiff_t)ipy * I.pitch + ipx;
+            const short2 *db = I.deriv + (ptrdiff_t)ipy * I.pitch + ipx;
+#pragma unroll
+            for (int k = 0; k < NPX; ++k) {
+                const bool ok = (lane + 32 * k) < npix;
+                const int o = ok ? py[k] * I.pitch + px[k] : 0;
+                const int s00 = __ldg(ib + o), s01 = __ldg(ib + o + 1);
+                const int s10 = __ldg(ib + o + I.pitch), s11 = __ldg(ib + o + I.pitch + 1);
+                const short2 d00 = __ldg(db + o), d01 = __ldg(db + o + 1);
+                const short2 d10 = __ldg(db + o + I.pitch), d11 = __ldg(db + o + I.pitch + 1);
+                int iv = (s00 * iw00 + s01 * iw01 + s10 * iw10 + s11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                int ix = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+                int iy = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+                if (!ok) { iv = 0; ix = 0; iy = 0; }
+                Iv[k] = iv; Ix[k] = ix; Iy[k] = iy;
+                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+            }
+        }
+        const float FLT_SCALE = 1.f / (float)(1 << 20);
+        const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
+        const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
+        const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dif = __fsub_rn(A11, A22);
+        const float minEig = __fdiv_rn(
+            __fsub_rn(__fadd_rn(A22, A11),
+                      __fsqrt_rn(__fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+            (float)(2 * win * win));
+        if (a.counters && lane == 0) atomicAdd(a.counters + 2 * level, 1ull);
+        if (minEig < a.min_eig || D < FLT_EPSILON) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+
+        nextx = __fsub_rn(nextx, halfWin); nexty = __fsub_rn(nexty, halfWin);
+        float pdx = 0.f, pdy = 0.f;
+        int j = 0;
+        for (; j < a.max_count; ++j) {
+            const int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
+            if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            bilinear_weights(__fsub_rn(nextx, (float)inx), __fsub_rn(nexty, (float)iny), iw00, iw01, iw10, iw11);
+            const uint8_t *jb = J.img + (ptrdiff_t)iny * J.pitch + inx;
+            int sb1 = 0, sb2 = 0;
+#pragma unroll
+            for (int k = 0; k < NPX; ++k) {
+                const int o = (lane + 32 * k) < npix ? py[k] * J.pitch + px[k] : 0;
+                const int s00 = __ldg(jb + o), s01 = __ldg(jb + o + 1);
+                const int s10 = __ldg(jb + o + J.pitch), s11 = __ldg(jb + o + J.pitch + 1);
+                const int diff = ((s00 * iw00 + s01 * iw01 + s10 * iw10 + s11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - Iv[k];
+                sb1 += diff * Ix[k];   // Ix = Iy = 0 on padding lanes
+                sb2 += diff * Iy[k];
+            }
+            const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
+            const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nextx = __fadd_rn(nextx, dx); nexty = __fadd_rn(nexty, dy);
+            stored.x = __fadd_rn(nextx, halfWin); stored.y = __fadd_rn(nexty, halfWin);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= a.eps2) { ++j; break; }
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                stored.x = __fsub_rn(stored.x, __fmul_rn(dx, 0.5f));
+                stored.y = __fsub_rn(stored.y, __fmul_rn(dy, 0.5f));
+                ++j;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (a.counters && lane == 0) atomicAdd(a.counters + 2 * level + 1, (unsigned long long)j);
+
+        if (status && level == 0) {
+            const float npx = __fsub_rn(stored.x, halfWin), npy = __fsub_rn(stored.y, halfWin);
+            const int inx = __float2int_rd(npx), iny = __float2int_rd(npy);
+            if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) {
+                status = 0;
+            } else {
+                bilinear_weights(__fsub_rn(npx, (float)inx), __fsub_rn(npy, (float)iny), iw00, iw01, iw10, iw11);
+                const uint8_t *jb = J.img + (ptrdiff_t)iny * J.pitch + inx;
+                int sabs = 0;
+#pragma unroll
+                for (int k = 0; k < NPX; ++k) {
+                    const bool ok = (lane + 32 * k) < npix;
+                    const int o = ok ? py[k] * J.pitch + px[k] : 0;
+                    const int s00 = __ldg(jb + o), s01 = __ldg(jb + o + 1);
+                    const int s10 = __ldg(jb + o + J.pitch), s11 = __ldg(jb + o + J.pitch + 1);
+                    const int diff = ((s00 * iw00 + s01 * iw01 + s10 * iw10 + s11 * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - Iv[k];
+                    sabs += ok ? abs(diff) : 0;
+                }
+                const int tot = __reduce_add_sync(0xffffffffu, sabs);   // <= 961*8160 < 2^31
+                errv = __fdiv_rn(__fmul_rn((float)tot, 1.f), (float)(32 * win * win));
+            }
+        }
+    }
+
+    if (lane == 0) {
+        a.pts1[gi] = stored;
+        if (!status) errv = 0.f;
+        if (a.status) a.status[gi] = (uint8_t)status;
+        if (a.err) a.err[gi] = errv;
+        // ---- fused FeatureTracker post-filters
+        const KltPost &P = a.post;
+        if (P.mode == 1) {          // track(): feature_tracker.cpp:33-34
+            P.mask[gi] = P.mask[gi] && status && errv <= P.thres_err;
+        } else if (P.mode == 2) {   // trackWithPrior(): feature_tracker.cpp:191-197
+            const float w = (float)S0.lv[0].w, h = (float)S0.lv[0].h;
+            P.mask[gi] = P.mask[gi] && status && stored.x > 0.f && stored.x < w && stored.y > 0.f && stored.y < h &&
+                         errv <= P.thres_err;
+        } else if (P.mode == 4) {   // backward pass of trackBidirection(+WithPrior): :74-83 / :130-149
+            const float w = (float)S0.lv[0].w, h = (float)S0.lv[0].h;
+            const float2 ref = reinterpret_cast<const float2 *>(P.ref_pts)[gi];
+            const float2 fw = reinterpret_cast<const float2 *>(P.fwd_pts)[gi];
+            const float ddx = __fsub_rn(stored.x, ref.x), ddy = __fsub_rn(stored.y, ref.y);
+            const float dist2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+            const float bd = (float)P.border;
+            const bool inimg = fw.x > bd && fw.x < w - bd && fw.y > bd && fw.y < h - bd;
+            const bool fs = P.fwd_status[gi] != 0;
+            P.mask[gi] = P.mask[gi] && inimg && fs && status && P.fwd_err[gi] <= P.thres_err && errv <= P.thres_err &&
+                         dist2 <= P.thres_bi2;
+        }
+    }
+}
+
+int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1, const float *pts0_d,
+                  int n, int win, int max_level, int flags, float *pts1_d, uint8_t *status_d,
+                  float *err_d, long long *counters_d, const KltPost *post)
+{
+    VO_REQUIRE(n >= 0 && n_pairs >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0 || n_pairs == 0) return VO_OK;
+    VO_REQUIRE(win >= 3 && win <= VO_MAX_WIN, VO_ERR_INVALID_ARG, "window size must be in [3, 31]");
+    VO_REQUIRE(max_level >= 0, VO_ERR_INVALID_ARG, "max_level < 0");
+    for (int i = 0; i < n_pairs; ++i) {
+        VO_REQUIRE(slots0[i] >= 0 && slots0[i] < ctx->n_slots && slots1[i] >= 0 && slots1[i] < ctx->n_slots,
+                   VO_ERR_INVALID_ARG, "slot id out of range");
+        VO_REQUIRE(ctx->slots[slots0[i]].w > 0 && ctx->slots[slots1[i]].w > 0, VO_ERR_INVALID_ARG, "slot has no image");
+        VO_REQUIRE(ctx->slots[slots0[i]].w == ctx->slots[slots1[i]].w && ctx->slots[slots0[i]].h == ctx->slots[slots1[i]].h,
+                   VO_ERR_SIZE_MISMATCH, "image pair sizes differ");
+    }
+    const Slot &A = ctx->slots[slots0[0]];
+    int eff = vo_effective_max_level(A.w, A.h, win, max_level);
+    if (eff > ctx->max_levels - 1) eff = ctx->max_levels - 1;
+    int rc = vo_ensure_pyramids(ctx, slots0, n_pairs, eff + 1, 1);
+    if (rc) return rc;
+    rc = vo_ensure_pyramids(ctx, slots1, n_pairs, eff + 1, 0);
+    if (rc) return rc;
+
+    const int npx = vo_div_up(win * win, 32);
+    for (int c0 = 0; c0 < n_pairs; c0 += VO_IDLIST_MAX) {
+        const int nb = n_pairs - c0 < VO_IDLIST_MAX ? n_pairs - c0 : VO_IDLIST_MAX;
+        KltArgs a;
+        a.slots = ctx->d_slots;
+        for (int i = 0; i < nb; ++i) { a.s0.id[i] = slots0[c0 + i]; a.s1.id[i] = slots1[c0 + i]; }
+        const size_t off = (size_t)c0 * n;
+        a.pts0 = reinterpret_cast<const float2 *>(pts0_d) + off;
+        a.pts1 = reinterpret_cast<float2 *>(pts1_d) + off;
+        a.status = status_d ? status_d + off : nullptr;
+        a.err = err_d ? err_d + off : nullptr;
+        a.counters = reinterpret_cast<unsigned long long *>(counters_d);
+        a.n = n; a.win = win; a.top_level = eff; a.flags = flags;
+        a.max_count = 30; a.min_eig = 1e-4f; a.eps2 = 0.01 * 0.01;
+        if (post) {
+            a.post = *post;
+            if (a.post.ref_pts) a.post.ref_pts += 2 * off;
+            if (a.post.fwd_pts) a.post.fwd_pts += 2 * off;
+            if (a.post.fwd_status) a.post.fwd_status += off;
+            if (a.post.fwd_err) a.post.fwd_err += off;
+            if (a.post.mask) a.post.mask += off;
+        } else {
+            a.post = KltPost{};
+        }
+        dim3 grd(vo_div_up(n, 4), nb);
+        if (npx <= 6) k_klt<6><<<grd, 128, 0, ctx->stream>>>(a);
+        else if (npx <= 8) k_klt<8><<<grd, 128, 0, ctx->stream>>>(a);
+        else if (npx <= 10) k_klt<10><<<grd, 128, 0, ctx->stream>>>(a);
+        else if (npx <= 14) k_klt<14><<<grd, 128, 0, ctx->stream>>>(a);
+        else if (npx <= 20) k_klt<20><<<grd, 128, 0, ctx->stream>>>(a);
+        else k_klt<31><<<grd, 128, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}

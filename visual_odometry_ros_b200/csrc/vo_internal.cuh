@@ -1,0 +1,109 @@
+// vo_internal.cuh -- shared device/host structures of libvo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vo_b200.h"
+
+#define VO_PAD 32           // reflect-101 border (px) kept around every pyramid level (>= win+1)
+#define VO_MAX_WIN 31
+
+// One pyramid level in HBM.  `img` points at pixel (0,0) of a padded, reflect-101-bordered
+// u8 plane (row pitch `pitch` bytes, 128-B aligned, VO_PAD px of border on every side, so
+// img[y*pitch + x] is valid for -VO_PAD <= x < w+VO_PAD, same for y).  `deriv` is the Scharr
+// derivative plane (short2 = {Ix, Iy}) with the same pitch in ELEMENTS and a zero border --
+// the layout cv::calcOpticalFlowPyrLK builds on the CPU (reflect-101 image ring, constant-0
+// derivative ring), but resident and built once per image.
+struct LevelDesc {
+    uint8_t *img;
+    short2 *deriv;
+    int w, h;
+    int pitch;
+    int _pad;
+};
+
+// Slot ids of one batched launch travel by value in the kernel parameters (no staging copy).
+#define VO_IDLIST_MAX 64
+struct IdList {
+    int id[VO_IDLIST_MAX];
+};
+
+struct SlotDesc {
+    LevelDesc lv[VO_MAX_LEVELS];
+};
+
+struct Slot {
+    SlotDesc desc;            // host copy of the device descriptor
+    uint8_t *base = nullptr;  // one allocation: all image planes then all deriv planes
+    size_t bytes = 0;
+    int w = 0, h = 0;         // current image size (level 0)
+    int levels_built = 0;     // pyramid levels valid (0 = only level 0 pixels uploaded)
+    int deriv_built = 0;      // derivative levels valid
+    bool border0 = false;     // level-0 border filled
+};
+
+struct vo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int max_w = 0, max_h = 0, n_slots = 0, max_feat = 0;
+    std::vector<Slot> slots;
+    SlotDesc *d_slots = nullptr;   // device mirror of all slot descriptors
+    int max_levels = 0;            // levels allocated per slot
+    // pinned + device staging for the host-pointer entry points
+    uint8_t *h_stage = nullptr;
+    uint8_t *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    long long launches = 0;
+    std::string last_error;
+    // trackWithScale scratch (float image + Sobel derivatives), lazily allocated
+    float *d_f32[4] = {nullptr, nullptr, nullptr, nullptr};
+    int f32_slot[2] = {-1, -1};
+    // LBA scratch
+    void *d_lba = nullptr;
+    size_t lba_bytes = 0;
+};
+
+#define VO_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);     \
+            return VO_ERR_CUDA;                                                        \
+        }                                                                              \
+    } while (0)
+
+#define VO_REQUIRE(cond, code, msg)                                                    \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            if (ctx) ctx->last_error = (msg);                                          \
+            return (code);                                                             \
+        }                                                                              \
+    } while (0)
+
+// Grow-only device+pinned staging; returns VO_OK or error.
+int vo_stage_reserve(vo_ctx *ctx, size_t bytes);
+
+// pyramid.cu
+int vo_ensure_pyramids(vo_ctx *ctx, const int *slots, int n, int n_levels, int with_deriv);
+
+// klt.cu
+struct KltPost {           // fused FeatureTracker post-filter (feature_tracker.cpp:33-34 etc.)
+    int mode;              // 0 none, 1 track, 2 with_prior, 3 bidir-forward (no mask), 4 bidir-backward
+    float thres_err;
+    float thres_bi2;       // already squared (and x5 for the with-prior variant)
+    int border;            // 3 for trackBidirection, 0 for the *WithPrior variants
+    int strict_border;     // unused
+    const float *ref_pts;      // bidir-backward: pts0 to compare the back-track with
+    const float *fwd_pts;      // bidir-backward: forward-tracked points (border test)
+    const uint8_t *fwd_status; // bidir-backward
+    const float *fwd_err;
+    uint8_t *mask;             // in-out (ANDed)
+};
+int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1, const float *pts0_d,
+                  int n, int win, int max_level, int flags, float *pts1_d, uint8_t *status_d,
+                  float *err_d, long long *counters_d, const KltPost *post);
+
+static inline int vo_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -1,0 +1,126 @@
+"""Deterministic synthetic inputs for the BASELINE.json configs.
+
+Pure numpy (+ cv2 for resampling); shared by tests/ and bench.py.  Nothing here is
+on the product path -- it only manufactures inputs.
+
+Intrinsics are KITTI-00 (``config/stereo/kitti_00_stereo.yaml:11-48`` of the reference).
+"""
+import numpy as np
+
+KITTI_W, KITTI_H = 1241, 376
+FX = FY = 718.856
+CX, CY = 607.1928, 185.2157
+BASELINE_M = 0.5371657189
+
+
+def kitti_K():
+    return np.array([FX, FY, CX, CY], np.float32)
+
+
+def kitti_T_lr():
+    T = np.eye(4, dtype=np.float32)
+    T[0, 3] = BASELINE_M
+    return T
+
+
+def textured_image(rng, w=KITTI_W, h=KITTI_H, noise_sigma=2.0):
+    """Band-limited random texture: 3 octaves of bicubic-upsampled uniform noise."""
+    import cv2
+    acc = np.zeros((h, w), np.float32)
+    for octave, amp in ((8, 1.0), (16, 0.7), (32, 0.5), (64, 0.35)):
+        gh, gw = max(2, h // (128 // octave * 2)), max(2, w // (128 // octave * 2))
+        g = rng.uniform(-1, 1, (gh, gw)).astype(np.float32)
+        acc += amp * cv2.resize(g, (w, h), interpolation=cv2.INTER_CUBIC)
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    img = acc * 255.0 + rng.normal(0, noise_sigma, (h, w)).astype(np.float32)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def warp_translate_field(img, dx, dy):
+    """out(x, y) = img(x - dx(x,y), y - dy(x,y)) bilinear; dx/dy scalars or HxW fields."""
+    import cv2
+    h, w = img.shape
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    mapx = (xs - dx).astype(np.float32)
+    mapy = (ys - dy).astype(np.float32)
+    return cv2.remap(img, mapx, mapy, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+
+
+def disparity_plane(w=KITTI_W, h=KITTI_H, d_top=5.0, d_bottom=60.0):
+    """Ground-plane-like inverse-depth field: disparity grows towards the image bottom."""
+    ys = np.linspace(0, 1, h, dtype=np.float32)[:, None]
+    xs = np.linspace(-1, 1, w, dtype=np.float32)[None, :]
+    return (d_top + (d_bottom - d_top) * ys ** 1.5 + 1.5 * xs).astype(np.float32)
+
+
+def grid_features(rng, n=2000, w=KITTI_W, h=KITTI_H, border=24, nx=50, ny=40):
+    """n features on a jittered nx x ny grid, >= border px from the image edge."""
+    gx = np.linspace(border + 4, w - border - 4, nx, dtype=np.float32)
+    gy = np.linspace(border + 4, h - border - 4, ny, dtype=np.float32)
+    xs, ys = np.meshgrid(gx, gy)
+    pts = np.stack([xs.ravel(), ys.ravel()], 1)
+    pts = pts + rng.uniform(-3, 3, pts.shape).astype(np.float32)
+    pts[:, 0] = np.clip(pts[:, 0], border, w - border)
+    pts[:, 1] = np.clip(pts[:, 1], border, h - border)
+    idx = rng.permutation(len(pts))[:n]
+    idx.sort()
+    return np.ascontiguousarray(pts[idx], np.float32)
+
+
+def klt_stereo_case(seed=2002, n=2000, w=KITTI_W, h=KITTI_H):
+    """BASELINE config 2: (left, right, next_left, pts0, disparity field, temporal flow)."""
+    rng = np.random.default_rng(seed)
+    left = textured_image(rng, w, h)
+    disp = disparity_plane(w, h)
+    # right image: a scene point at left x appears at x - d in the right image.
+    right = warp_translate_field(left, -disp, 0.0)
+    right = np.clip(right.astype(np.float32) + rng.normal(0, 1.0, right.shape), 0, 255).astype(np.uint8)
+    # next-left: forward-motion-like radial flow around the principal point, <= ~6 px
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    fx_ = 0.012 * (xs - CX) * (disp / 30.0) + 1.3
+    fy_ = 0.012 * (ys - CY) * (disp / 30.0) - 0.7
+    nxt = warp_translate_field(left, fx_, fy_)
+    nxt = np.clip(nxt.astype(np.float32) + rng.normal(0, 1.0, nxt.shape), 0, 255).astype(np.uint8)
+    pts0 = grid_features(rng, n, w, h)
+    return dict(left=left, right=right, next_left=nxt, pts0=pts0, disp=disp, flow=(fx_, fy_))
+
+
+# ------------------------------------------------------------------ pose GN scene (config 1)
+def so3_exp(w):
+    w = np.asarray(w, np.float64)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+
+
+def pose_scene(seed=1001, n=500, noise_px=0.3, outlier_frac=0.10,
+               rotvec=(0.002, -0.012, 0.001), t=(0.02, -0.01, 0.85)):
+    """BASELINE config 1: 500-point pinhole scene, stereo observations, 10 % gross outliers.
+
+    Returns X (prev-left frame), pts_l1, pts_r1 (current left/right pixels), T01_true
+    (pose of current-left in prev-left: X_prev = T01 * X_cur).
+    """
+    rng = np.random.default_rng(seed)
+    X = np.stack([rng.uniform(-12, 12, n), rng.uniform(-3, 2, n), rng.uniform(4, 50, n)], 1)
+    R01 = so3_exp(rotvec)
+    t01 = np.asarray(t, np.float64)
+    T01 = np.eye(4)
+    T01[:3, :3] = R01
+    T01[:3, 3] = t01
+    R10 = R01.T
+    t10 = -R01.T @ t01
+    Xl = X @ R10.T + t10
+    Xr = Xl.copy()
+    Xr[:, 0] -= BASELINE_M  # T_rl = inv(T_lr): x_r = x_l - b
+    pl = np.stack([FX * Xl[:, 0] / Xl[:, 2] + CX, FY * Xl[:, 1] / Xl[:, 2] + CY], 1)
+    pr = np.stack([FX * Xr[:, 0] / Xr[:, 2] + CX, FY * Xr[:, 1] / Xr[:, 2] + CY], 1)
+    pl += rng.normal(0, noise_px, pl.shape)
+    pr += rng.normal(0, noise_px, pr.shape)
+    n_out = int(round(outlier_frac * n))
+    idx = rng.choice(n, n_out, replace=False)
+    sign = rng.choice([-1.0, 1.0], (n_out, 2))
+    pl[idx] += sign * rng.uniform(5, 30, (n_out, 2))
+    return dict(X=X.astype(np.float32), pts_l1=pl.astype(np.float32), pts_r1=pr.astype(np.float32),
+                T01_true=T01, outlier_idx=np.sort(idx))
