@@ -134,10 +134,13 @@ VO_API int vo_ft_track_with_scale(vo_ctx *ctx, int slot0, int slot1, const float
  * MotionEstimator::poseOnlyBundleAdjustment (core motion_estimator.cpp:665-861 ==
  * standalone motion_estimator.cpp:4-193) and _Stereo (core :863-1088 == standalone :195-411).
  * R01/t01/T01 are in-out (row-major). Returns VO_OK and *success=0 when the result is NaN
- * (reference returns false and leaves the pose untouched). iters_out nullable. */
+ * (reference returns false and leaves the pose untouched). iters_out nullable.
+ * standalone_variant: 0 = core error accounting (weighted y row adds w*ry^2, core :799),
+ * 1 = standalone (adds ry^2, standalone :135); only the stopping test can differ. */
 VO_API int vo_pose_gn_mono(vo_ctx *ctx, const float *X, const float *pts1, int n, float fx, float fy,
-                    float cx, float cy, int thres_reproj_outlier, float *R01_inout,
-                    float *t01_inout, uint8_t *mask_inlier, int *success, int *iters_out);
+                    float cx, float cy, int thres_reproj_outlier, int standalone_variant,
+                    float *R01_inout, float *t01_inout, uint8_t *mask_inlier, int *success,
+                    int *iters_out);
 VO_API int vo_pose_gn_stereo(vo_ctx *ctx, const float *X, const float *pts_l1, const float *pts_r1, int n,
                       const float *K_l4, const float *K_r4, const float *T_lr,
                       float thres_reproj_outlier, float *T01_inout, uint8_t *mask_inlier,

@@ -87,6 +87,11 @@ def lib():
     L.vo_ft_track_with_prior.argtypes = ft + [vp, vp]
     L.vo_ft_track_bidirection.argtypes = ft + [ctypes.c_float, vp, vp]
     L.vo_ft_track_bidirection_with_prior.argtypes = ft + [ctypes.c_float, vp, vp]
+    f32 = ctypes.c_float
+    L.vo_pose_gn_mono.argtypes = [vp, vp, vp, ctypes.c_int, f32, f32, f32, f32, ctypes.c_int, ctypes.c_int, vp, vp, vp,
+                                  c_int_p, c_int_p]
+    L.vo_pose_gn_stereo.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, f32, vp, vp, c_int_p, c_int_p]
+    L.vo_pose_gn_stereo_batch_d.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -207,3 +212,49 @@ class Context:
     def ft_track_bidirection_with_prior(self, slot0, slot1, pts0, prior, win, lvl, thres_err, thres_bi, mask=None):
         return self._ft(self.L.vo_ft_track_bidirection_with_prior, slot0, slot1, pts0, win, lvl, thres_err,
                         [ctypes.c_float(thres_bi)], prior, mask)
+
+    # ---------------------------------------------------------------- pose-only Gauss-Newton
+    def pose_gn_stereo(self, X, pts_l1, pts_r1, K_l, K_r, T_lr, thres, T01_init):
+        """MotionEstimator::poseOnlyBundleAdjustment_Stereo -> (success, T01, mask, iters)."""
+        X = np.ascontiguousarray(X, np.float32).reshape(-1, 3)
+        pl = np.ascontiguousarray(pts_l1, np.float32).reshape(-1, 2)
+        pr = np.ascontiguousarray(pts_r1, np.float32).reshape(-1, 2)
+        n = len(X)
+        if len(pl) != n or len(pr) != n:
+            # reference text: motion_estimator.cpp:873
+            raise VoError(VO_ERR_SIZE_MISMATCH,
+                          "In 'poseOnlyStereoBundleAdjustment()': X.size() != pts_l1.size() || X.size() != pts_r1.size().")
+        Kl = np.ascontiguousarray(K_l, np.float32)
+        Kr = np.ascontiguousarray(K_r, np.float32)
+        Tlr = np.ascontiguousarray(T_lr, np.float32)
+        T01 = np.ascontiguousarray(T01_init, np.float32).copy()
+        mask = np.ones(n, np.uint8)
+        ok, it = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.h, self.L.vo_pose_gn_stereo(self.h, _ptr(X), _ptr(pl), _ptr(pr), n, _ptr(Kl), _ptr(Kr), _ptr(Tlr),
+                                               thres, _ptr(T01), _ptr(mask), ctypes.byref(ok), ctypes.byref(it)))
+        return bool(ok.value), T01, mask.astype(bool), it.value
+
+    def pose_gn_mono(self, X, pts1, K, thres, R01_init, t01_init, standalone_variant=0):
+        """MotionEstimator::poseOnlyBundleAdjustment -> (success, R01, t01, mask, iters)."""
+        X = np.ascontiguousarray(X, np.float32).reshape(-1, 3)
+        p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        n = len(X)
+        if len(p1) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "In 'poseOnlyBundleAdjustment()': X.size() != pts1.size().")
+        R = np.ascontiguousarray(R01_init, np.float32).copy()
+        t = np.ascontiguousarray(t01_init, np.float32).copy()
+        mask = np.ones(n, np.uint8)
+        ok, it = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.h, self.L.vo_pose_gn_mono(self.h, _ptr(X), _ptr(p1), n, float(K[0]), float(K[1]), float(K[2]),
+                                             float(K[3]), int(thres), int(standalone_variant), _ptr(R), _ptr(t),
+                                             _ptr(mask), ctypes.byref(ok), ctypes.byref(it)))
+        return bool(ok.value), R, t, mask.astype(bool), it.value
+
+    def pose_gn_stereo_batch_d(self, n_prob, offsets_d, X_d, pl_d, pr_d, K_l, K_r, T_lr, thres, T01_d, mask_d,
+                               success_d=None, iters_d=None):
+        Kl = np.ascontiguousarray(K_l, np.float32)
+        Kr = np.ascontiguousarray(K_r, np.float32)
+        Tlr = np.ascontiguousarray(T_lr, np.float32)
+        check(self.h, self.L.vo_pose_gn_stereo_batch_d(
+            self.h, n_prob, vp(offsets_d), vp(X_d), vp(pl_d), vp(pr_d), _ptr(Kl), _ptr(Kr), _ptr(Tlr), thres,
+            vp(T01_d), vp(mask_d), vp(success_d) if success_d else None, vp(iters_d) if iters_d else None))

@@ -1,0 +1,436 @@
+// pose_gn.cu -- K-pose: Huber 3D-2D pose-only Gauss-Newton, whole iteration loop on device.
+//
+// Replaces MotionEstimator::poseOnlyBundleAdjustment (core/visual_odometry/motion_estimator.cpp:665-861,
+// standalone/motion_estimator/motion_estimator.cpp:4-193) and ..._Stereo (core :863-1088,
+// standalone :195-411).  One CTA per problem; every thread evaluates the residual / Jacobian rows
+// of its points in FP32 with the reference's operation order (this file is compiled with
+// -fmad=false so no multiply-add is fused), accumulates the 21 upper-triangular JtWJ entries,
+// the 6 entries of -JtWr and the error in FP64 registers, reduces warp-level by shuffles then
+// block-level through shared memory, and thread 0 rounds the sums to FP32 and performs the
+// reference's damped 6x6 pivoted LDLT solve, se3Exp update and stopping test.  No host
+// round trip inside the <=100-iteration loop.  Reference quirks kept: Huber gate '>=' on the
+// (mean-)L1 residual, masks rewritten each iteration with outliers still weighted in
+// (motion_estimator.cpp:955-967), the right-camera Jacobian reusing the left closed form
+// (:1008-1031), int outlier threshold in mono (motion_estimator.h:117), err without sqrt in mono.
+#include "vo_internal.cuh"
+
+#include <cstring>
+
+#define POSE_THREADS 256
+#define POSE_MAX_ITER 100
+#define NACC 28   // 21 (upper JtWJ) + 6 (mJtWr) + 1 (err)
+
+struct PoseArgs {
+    const int *offsets;   // [n_prob+1] device, or null (single problem of n points)
+    int n_single;
+    const float *X, *pl, *pr;
+    float Kl[4], Kr[4];
+    float T_rl[16];       // row-major
+    float thres;
+    int mono;             // 1: mono (2 rows / point)
+    int variant;          // mono: 0 core, 1 standalone error accounting
+    float *T01;           // [n_prob][16] in-out (mono: packed as 4x4 too)
+    uint8_t *mask;
+    int *success;
+    int *iters;
+};
+
+__device__ __forceinline__ void inv_se3(const float *T, float *O)
+{
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) O[i * 4 + j] = T[j * 4 + i];
+        float s = 0.f;
+        for (int k = 0; k < 3; ++k) s += T[k * 4 + i] * T[k * 4 + 3];
+        O[i * 4 + 3] = -s;
+    }
+    O[12] = 0.f; O[13] = 0.f; O[14] = 0.f; O[15] = 1.f;
+}
+
+__device__ void inverse4(const float *m, float *out)
+{
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const float id = 1.0f / det;
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * id;
+}
+
+// geometry::se3Exp_f (core/util/geometry_library.cpp:386-440): sin/cos evaluated in double on
+// the float angle, coefficients rounded to float, small-angle branch below 1e-7.
+__device__ void se3exp_f(const float *xi, float *T)
+{
+    const float v0 = xi[0], v1 = xi[1], v2 = xi[2], w0 = xi[3], w1 = xi[4], w2 = xi[5];
+    const float theta = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+    const float wx[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+    float wx2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float s = 0.f;
+            for (int k = 0; k < 3; ++k) s += wx[i * 3 + k] * wx[k * 3 + j];
+            wx2[i * 3 + j] = s;
+        }
+    float a, b, c;
+    if (theta < 1e-7) {
+        a = 1.f; b = 0.5f; c = 0.33333333333333333333333333f;
+    } else {
+        const double th = (double)theta;
+        a = (float)(sin(th) / th);
+        b = (float)((1 - cos(th)) / (double)(theta * theta));
+        c = (float)((th - sin(th)) / (double)(theta * theta * theta));
+    }
+    float V[9];
+    for (int i = 0; i < 9; ++i) {
+        const float id = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+        const int r = i / 3, cc = i - 3 * r;
+        T[r * 4 + cc] = (id + a * wx[i]) + b * wx2[i];
+        V[i] = (id + b * wx[i]) + c * wx2[i];
+    }
+    for (int i = 0; i < 3; ++i) T[i * 4 + 3] = (V[i * 3 + 0] * v0 + V[i * 3 + 1] * v1) + V[i * 3 + 2] * v2;
+    T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+}
+
+// Eigen::LDLT<Matrix<float,6,6>,Lower> (diagonal pivoting, unblocked) + solve.
+__device__ void ldlt6_solve(float *m /*6x6 row-major sym, destroyed*/, const float *b, float *x)
+{
+    const int n = 6;
+    int tr[6];
+#define M(i, j) m[(i) * 6 + (j)]
+    for (int k = 0; k < n; ++k) {
+        int big = k;
+        float bv = fabsf(M(k, k));
+        for (int i = k + 1; i < n; ++i)
+            if (fabsf(M(i, i)) > bv) { bv = fabsf(M(i, i)); big = i; }
+        tr[k] = big;
+        if (big != k) {
+            const int s = n - big - 1;
+            for (int j = 0; j < k; ++j) { const float t = M(k, j); M(k, j) = M(big, j); M(big, j) = t; }
+            for (int i = 0; i < s; ++i) { const float t = M(big + 1 + i, k); M(big + 1 + i, k) = M(big + 1 + i, big); M(big + 1 + i, big) = t; }
+            { const float t = M(k, k); M(k, k) = M(big, big); M(big, big) = t; }
+            for (int i = k + 1; i < big; ++i) { const float t = M(i, k); M(i, k) = M(big, i); M(big, i) = t; }
+        }
+        const int rs = n - k - 1;
+        if (k > 0) {
+            float temp[6];
+            for (int j = 0; j < k; ++j) temp[j] = M(j, j) * M(k, j);
+            float s = 0.f;
+            for (int j = 0; j < k; ++j) s += M(k, j) * temp[j];
+            M(k, k) -= s;
+            for (int i = 0; i < rs; ++i) {
+                float s2 = 0.f;
+                for (int j = 0; j < k; ++j) s2 += M(k + 1 + i, j) * temp[j];
+                M(k + 1 + i, k) -= s2;
+            }
+        }
+        const float akk = M(k, k);
+        if (rs > 0 && fabsf(akk) > 0.f)
+            for (int i = 0; i < rs; ++i) M(k + 1 + i, k) /= akk;
+    }
+    float y[6];
+    for (int i = 0; i < n; ++i) y[i] = b[i];
+    for (int k = 0; k < n; ++k) if (tr[k] != k) { const float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+    for (int i = 0; i < n; ++i) { float s = y[i]; for (int j = 0; j < i; ++j) s -= M(i, j) * y[j]; y[i] = s; }
+    const float tol = 1.0f / 3.402823466e+38f;
+    for (int i = 0; i < n; ++i) y[i] = fabsf(M(i, i)) > tol ? y[i] / M(i, i) : 0.f;
+    for (int i = n - 1; i >= 0; --i) { float s = y[i]; for (int j = i + 1; j < n; ++j) s -= M(j, i) * y[j]; y[i] = s; }
+    for (int k = n - 1; k >= 0; --k) if (tr[k] != k) { const float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+    for (int i = 0; i < n; ++i) x[i] = y[i];
+#undef M
+}
+
+// One residual row: weighted rank-1 update with the row's structural zero (calcJtWJ_x / _y).
+// ZERO is the index of the zero Jacobian entry (1 for an x row, 0 for a y row).
+template <int ZERO>
+__device__ __forceinline__ void acc_row(double *acc, const float *Jt, float w, float r, bool weighted)
+{
+    float wJ[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) wJ[i] = weighted ? w * Jt[i] : Jt[i];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j, ++idx)
+            if (i != ZERO && j != ZERO) acc[idx] += (double)(wJ[i] * Jt[j]);
+    const float wr = weighted ? w * r : r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (i != ZERO) acc[21 + i] -= (double)(wr * Jt[i]);
+}
+
+__global__ void __launch_bounds__(POSE_THREADS)
+k_pose_gn(const PoseArgs a)
+{
+    __shared__ double s_part[POSE_THREADS / 32][NACC];
+    __shared__ float s_T10[16];
+    __shared__ int s_stop;
+    __shared__ float s_err_prev;
+
+    const int prob = blockIdx.x;
+    const int beg = a.offsets ? a.offsets[prob] : 0;
+    const int n = a.offsets ? a.offsets[prob + 1] - beg : a.n_single;
+    const float *X = a.X + 3 * (size_t)beg;
+    const float *pl = a.pl + 2 * (size_t)beg;
+    const float *pr = a.mono ? nullptr : a.pr + 2 * (size_t)beg;
+    uint8_t *mask = a.mask + beg;
+    float *T01 = a.T01 + 16 * (size_t)prob;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) {
+        float T[16];
+        for (int i = 0; i < 16; ++i) T[i] = T01[i];
+        float Ti[16];
+        if (a.mono) inverse4(T, Ti);       // Matrix4f::inverse() (motion_estimator.cpp:700)
+        else inv_se3(T, Ti);               // explicit R^T, -R^T t (:903-904)
+        for (int i = 0; i < 16; ++i) s_T10[i] = Ti[i];
+        s_stop = 0;
+        s_err_prev = 1e10f;
+    }
+    __syncthreads();
+
+    const float fx_l = a.Kl[0], fy_l = a.Kl[1], cx_l = a.Kl[2], cy_l = a.Kl[3];
+    const float fx_r = a.Kr[0], fy_r = a.Kr[1], cx_r = a.Kr[2], cy_r = a.Kr[3];
+    const float THRES_HUBER = 0.5f;
+    int iter = 0;
+    for (; iter < POSE_MAX_ITER; ++iter) {
+        float T10[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T10[i] = s_T10[i];
+        double acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+        for (int i = tid; i < n; i += POSE_THREADS) {
+            const float x0 = X[3 * i], x1 = X[3 * i + 1], x2 = X[3 * i + 2];
+            float Xl[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Xl[r] = ((T10[r * 4 + 0] * x0 + T10[r * 4 + 1] * x1) + T10[r * 4 + 2] * x2) + T10[r * 4 + 3];
+            const float iz_l = 1.0f / Xl[2], xiz_l = Xl[0] * iz_l, yiz_l = Xl[1] * iz_l;
+            const float fxxiz_l = fx_l * xiz_l, fyyiz_l = fy_l * yiz_l;
+            const float rx_l = (fxxiz_l + cx_l) - pl[2 * i], ry_l = (fyyiz_l + cy_l) - pl[2 * i + 1];
+            float Jt[6];
+            if (a.mono) {
+                float weight = 1.0f;
+                bool fw = false;
+                const float absrxry = fabsf(rx_l) + fabsf(ry_l);
+                if (absrxry >= THRES_HUBER) { weight = THRES_HUBER / absrxry; fw = true; }
+                mask[i] = (absrxry >= a.thres) ? 0 : 1;
+                Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
+                Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
+                acc_row<1>(acc, Jt, weight, rx_l, fw);
+                acc[27] += (double)(rx_l * rx_l);
+                Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
+                Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
+                acc_row<0>(acc, Jt, weight, ry_l, fw);
+                if (fw && a.variant == 0) acc[27] += (double)((weight * ry_l) * ry_l);
+                else acc[27] += (double)(ry_l * ry_l);
+            } else {
+                float Xr[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    Xr[r] = ((a.T_rl[r * 4 + 0] * Xl[0] + a.T_rl[r * 4 + 1] * Xl[1]) + a.T_rl[r * 4 + 2] * Xl[2]) + a.T_rl[r * 4 + 3];
+                const float iz_r = 1.0f / Xr[2], xiz_r = Xr[0] * iz_r, yiz_r = Xr[1] * iz_r;
+                const float fxxiz_r = fx_r * xiz_r, fyyiz_r = fy_r * yiz_r;
+                const float rx_r = (fxxiz_r + cx_r) - pr[2 * i], ry_r = (fyyiz_r + cy_r) - pr[2 * i + 1];
+                float weight = 1.0f;
+                float absrxry = fabsf(rx_l) + fabsf(ry_l) + fabsf(rx_r) + fabsf(ry_r);
+                absrxry *= 0.5f;
+                if (absrxry >= THRES_HUBER) weight = THRES_HUBER / absrxry;
+                mask[i] = (absrxry >= a.thres) ? 0 : 1;
+                Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
+                Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
+                acc_row<1>(acc, Jt, weight, rx_l, true); acc[27] += (double)(rx_l * rx_l);
+                Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
+                Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
+                acc_row<0>(acc, Jt, weight, ry_l, true); acc[27] += (double)(ry_l * ry_l);
+                Jt[0] = fx_r * iz_r; Jt[1] = 0.f; Jt[2] = -fxxiz_r * iz_r; Jt[3] = -fxxiz_r * yiz_r;
+                Jt[4] = fx_r * (1.0f + xiz_r * xiz_r); Jt[5] = -fx_r * yiz_r;
+                acc_row<1>(acc, Jt, weight, rx_r, true); acc[27] += (double)(rx_r * rx_r);
+                Jt[0] = 0.f; Jt[1] = fy_r * iz_r; Jt[2] = -fyyiz_r * iz_r; Jt[3] = -fy_r * (1.0f + yiz_r * yiz_r);
+                Jt[4] = fyyiz_r * xiz_r; Jt[5] = fy_r * xiz_r;
+                acc_row<0>(acc, Jt, weight, ry_r, true); acc[27] += (double)(ry_r * ry_r);
+            }
+        }
+        // warp-level then block-level reduction of the 28 FP64 partials
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) s_part[wid][k] = v;
+        }
+        __syncthreads();
+        if (tid < NACC) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < POSE_THREADS / 32; ++w) v += s_part[w][tid];
+            s_part[0][tid] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float H[36], g[6];
+            int idx = 0;
+            for (int i = 0; i < 6; ++i)
+                for (int j = i; j < 6; ++j, ++idx) { const float v = (float)s_part[0][idx]; H[i * 6 + j] = v; H[j * 6 + i] = v; }
+            for (int i = 0; i < 6; ++i) g[i] = (float)s_part[0][21 + i];
+            float err_curr = (float)s_part[0][27];
+            const float inv_npts = 1.0f / (float)n;
+            err_curr *= (inv_npts * 0.5f);
+            if (!a.mono) err_curr = sqrtf(err_curr);
+            const float delta_err = fabsf(err_curr - s_err_prev);
+            for (int i = 0; i < 6; ++i) H[i * 6 + i] *= (1.0f + 0.00001f);
+            float dxi[6], dT[16], Tn[16];
+            ldlt6_solve(H, g, dxi);
+            se3exp_f(dxi, dT);
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    float s = 0.f;
+                    for (int k = 0; k < 4; ++k) s += dT[i * 4 + k] * s_T10[k * 4 + j];
+                    Tn[i * 4 + j] = s;
+                }
+            for (int i = 0; i < 16; ++i) s_T10[i] = Tn[i];
+            s_err_prev = err_curr;
+            float nrm = 0.f;
+            for (int i = 0; i < 6; ++i) nrm += dxi[i] * dxi[i];
+            nrm = sqrtf(nrm);
+            s_stop = (nrm < 1e-6f || delta_err < 1e-7f) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_stop) { ++iter; break; }
+    }
+    if (tid == 0) {
+        float nrm2 = 0.f;
+        for (int i = 0; i < 16; ++i) nrm2 += s_T10[i] * s_T10[i];
+        const bool ok = !isnan(nrm2);
+        if (ok) {
+            float T10[16], Ti[16];
+            for (int i = 0; i < 16; ++i) T10[i] = s_T10[i];
+            inv_se3(T10, Ti);
+            for (int i = 0; i < 16; ++i) T01[i] = Ti[i];
+        }
+        if (a.success) a.success[prob] = ok ? 1 : 0;
+        if (a.iters) a.iters[prob] = iter;
+    }
+}
+
+static void host_inv_se3(const float *T, float *O)
+{
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) O[i * 4 + j] = T[j * 4 + i];
+        float s = 0.f;
+        for (int k = 0; k < 3; ++k) s += T[k * 4 + i] * T[k * 4 + 3];
+        O[i * 4 + 3] = -s;
+    }
+    O[12] = O[13] = O[14] = 0.f; O[15] = 1.f;
+}
+
+static int pose_launch(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const float *X_d, const float *pl_d,
+                       const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres, int mono,
+                       int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d)
+{
+    PoseArgs a;
+    a.offsets = offsets_d; a.n_single = n_single;
+    a.X = X_d; a.pl = pl_d; a.pr = pr_d;
+    for (int i = 0; i < 4; ++i) { a.Kl[i] = Kl[i]; a.Kr[i] = Kr ? Kr[i] : Kl[i]; }
+    if (T_lr) host_inv_se3(T_lr, a.T_rl);
+    else { for (int i = 0; i < 16; ++i) a.T_rl[i] = (i % 5 == 0) ? 1.f : 0.f; }
+    a.thres = thres; a.mono = mono; a.variant = variant;
+    a.T01 = T01_d; a.mask = mask_d; a.success = success_d; a.iters = iters_d;
+    k_pose_gn<<<n_prob, POSE_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
+extern "C" int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, const float *X_d,
+                                         const float *pts_l1_d, const float *pts_r1_d, const float *K_l4,
+                                         const float *K_r4, const float *T_lr, float thres_reproj_outlier,
+                                         float *T01_inout_d, uint8_t *mask_inlier_d, int *success_d, int *iters_d)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n_prob >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n_prob == 0) return VO_OK;
+    VO_REQUIRE(offsets_d && X_d && pts_l1_d && pts_r1_d && K_l4 && K_r4 && T_lr && T01_inout_d && mask_inlier_d,
+               VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return pose_launch(ctx, n_prob, offsets_d, 0, X_d, pts_l1_d, pts_r1_d, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0,
+                       T01_inout_d, mask_inlier_d, success_d, iters_d);
+}
+
+// Host-pointer single-problem entry points: one H2D, one launch, one D2H.
+static int pose_host(vo_ctx *ctx, const float *X, const float *pl, const float *pr, int n, const float *Kl,
+                     const float *Kr, const float *T_lr, float thres, int mono, int variant, float *T01_inout,
+                     uint8_t *mask, int *success, int *iters_out)
+{
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t oX = 0, oPl = oX + (size_t)n * 12, oPr = oPl + (size_t)n * 8, oT = oPr + (size_t)n * 8;
+    const size_t oFlags = oT + 64, oMask = oFlags + 16, total = oMask + (size_t)n + 64;
+    int rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h + oX, X, (size_t)n * 12);
+    memcpy(h + oPl, pl, (size_t)n * 8);
+    if (pr) memcpy(h + oPr, pr, (size_t)n * 8);
+    memcpy(h + oT, T01_inout, 64);
+    VO_CUDA(cudaMemcpyAsync(d, h, oFlags, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pose_launch(ctx, 1, nullptr, n, (const float *)(d + oX), (const float *)(d + oPl), (const float *)(d + oPr), Kl, Kr,
+                     T_lr, thres, mono, variant, (float *)(d + oT), d + oMask, (int *)(d + oFlags), (int *)(d + oFlags + 4));
+    if (rc) return rc;
+    VO_CUDA(cudaMemcpyAsync(h + oT, d + oT, total - oT, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int ok = *(int *)(h + oFlags);
+    if (ok) memcpy(T01_inout, h + oT, 64);
+    memcpy(mask, h + oMask, (size_t)n);
+    if (success) *success = ok;
+    if (iters_out) *iters_out = *(int *)(h + oFlags + 4);
+    return VO_OK;
+}
+
+extern "C" int vo_pose_gn_stereo(vo_ctx *ctx, const float *X, const float *pts_l1, const float *pts_r1, int n,
+                                 const float *K_l4, const float *K_r4, const float *T_lr, float thres_reproj_outlier,
+                                 float *T01_inout, uint8_t *mask_inlier, int *success, int *iters_out)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    VO_REQUIRE(K_l4 && K_r4 && T_lr && T01_inout, VO_ERR_INVALID_ARG, "null pointer");
+    if (n == 0) { if (success) *success = 1; if (iters_out) *iters_out = 1; return VO_OK; }
+    VO_REQUIRE(X && pts_l1 && pts_r1 && mask_inlier, VO_ERR_INVALID_ARG, "null pointer");
+    return pose_host(ctx, X, pts_l1, pts_r1, n, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0, T01_inout, mask_inlier,
+                     success, iters_out);
+}
+
+extern "C" int vo_pose_gn_mono(vo_ctx *ctx, const float *X, const float *pts1, int n, float fx, float fy, float cx,
+                               float cy, int thres_reproj_outlier, int standalone_variant, float *R01_inout,
+                               float *t01_inout, uint8_t *mask_inlier, int *success, int *iters_out)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    VO_REQUIRE(R01_inout && t01_inout, VO_ERR_INVALID_ARG, "null pointer");
+    if (n == 0) { if (success) *success = 1; if (iters_out) *iters_out = 1; return VO_OK; }
+    VO_REQUIRE(X && pts1 && mask_inlier, VO_ERR_INVALID_ARG, "null pointer");
+    float T[16] = {0};
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T[i * 4 + j] = R01_inout[i * 3 + j]; T[i * 4 + 3] = t01_inout[i]; }
+    T[15] = 1.f;
+    const float K[4] = {fx, fy, cx, cy};
+    int ok = 0;
+    int rc = pose_host(ctx, X, pts1, nullptr, n, K, K, nullptr, (float)thres_reproj_outlier, 1, standalone_variant ? 1 : 0, T, mask_inlier, &ok,
+                       iters_out);
+    if (rc) return rc;
+    if (ok) for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R01_inout[i * 3 + j] = T[i * 4 + j]; t01_inout[i] = T[i * 4 + 3]; }
+    if (success) *success = ok;
+    return VO_OK;
+}
