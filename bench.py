@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- KLT features/s (+ pose-GN solves/s, ms/frame) at 1241x376 stereo on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[1], batched as configs[4] prescribes): P independent
+KITTI-size stereo pairs per GPU and step; one step == FeatureTracker::track on every pair ==
+(4-level pyramid of both images + Scharr derivative pyramid of the first + pyramidal LK of
+2000 features, 21x21 window), i.e. exactly what one cv::calcOpticalFlowPyrLK call does in the
+reference (core/visual_odometry/feature_tracker.cpp:29).  `value` = features tracked per second,
+whole job, with the images already resident in HBM (slot level 0); `e2e` = the same through the
+host-buffer C-ABI call vo_ft_track_batch (pinned host images + points in, points + masks out,
+all copies inside the timed region).
+
+`--impl reference` times the reference's own CPU implementation of the same step
+(cv2.calcOpticalFlowPyrLK 4.13 -- the library call the reference makes -- with all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, NFEAT, WIN, MAXLVL, THRES_ERR = 1241, 376, 2000, 21, 3, 80.0
+METRIC = "KLT features/s at 1241x376 stereo (2000 features, 4-level pyramid, 21x21 window)"
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_pairs(P, seed):
+    """P distinct synthetic stereo pairs + feature sets (cheap variations of a few base pairs)."""
+    from visual_odometry_ros_b200 import synth
+    nbase = min(P, 4)
+    bases = [synth.klt_stereo_case(seed=seed + 17 * k, n=NFEAT) for k in range(nbase)]
+    rng = np.random.default_rng(seed)
+    lefts, rights, pts = [], [], []
+    for i in range(P):
+        b = bases[i % nbase]
+        sh = int(rng.integers(0, W)) if i >= nbase else 0
+        lefts.append(np.ascontiguousarray(np.roll(b["left"], sh, axis=1)))
+        rights.append(np.ascontiguousarray(np.roll(b["right"], sh, axis=1)))
+        pts.append(synth.grid_features(rng, NFEAT, W, H))
+    return lefts, rights, np.stack(pts).astype(np.float32)
+
+
+def cpu_reference_rate(left, right, pts0, threads, budget_s):
+    """cv2.calcOpticalFlowPyrLK (the reference's library call) on one pair, repeated."""
+    import cv2
+    from oracle import klt as oklt
+    cv2.setNumThreads(threads)
+    oklt.track(oklt.lk_cv2, left, right, pts0, WIN, MAXLVL, THRES_ERR)  # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        oklt.track(oklt.lk_cv2, left, right, pts0, WIN, MAXLVL, THRES_ERR)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or reps >= 2000:
+            break
+    return reps * len(pts0) / dt, reps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lefts, rights, pts = make_pairs(1, 2002)
+    cores = os.cpu_count() or 1
+    import cv2
+    from oracle import klt as oklt
+    cv2.setNumThreads(cores)
+    for _ in range(max(args.warmup, 1)):
+        oklt.track(oklt.lk_cv2, lefts[0], rights[0], pts[0], WIN, MAXLVL, THRES_ERR)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oklt.track(oklt.lk_cv2, lefts[0], rights[0], pts[0], WIN, MAXLVL, THRES_ERR)
+    dt = time.perf_counter() - t0
+    val = args.steps * NFEAT / dt
+    sample = (f"{args.steps} steps x 1 stereo pair x {NFEAT} features: cv2.calcOpticalFlowPyrLK 4.13 "
+              f"(+ track() post-filter), {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "features/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16 fixed-point + f32", "data": "synthetic",
+        "config": {"workload": "cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21 (one pair per step)"},
+        "cpu_baseline": {"value": val, "unit": "features/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=128, help="independent stereo pairs per GPU per step")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
+    ap.add_argument("--skip-extras", action="store_true", help="skip pose-GN / single-frame side measurements")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from visual_odometry_ros_b200 import capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    P, n, K, Wm = args.pairs, NFEAT, args.steps, args.warmup
+    lefts, rights, pts0_h = make_pairs(P, 2002 + 1000 * rank)
+    # an explicit non-default stream shared by torch (events, tensors) and the context (kernels):
+    # the legacy default stream's handle is 0, which vo_ctx_create reads as "own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = capi.Context(device=local, max_w=W, max_h=H, n_slots=2 * P, max_feat=P * n, stream=stream.cuda_stream)
+    slots0 = np.arange(P, dtype=np.int32)
+    slots1 = np.arange(P, 2 * P, dtype=np.int32)
+    all_slots = np.arange(2 * P, dtype=np.int32)
+
+    # pinned host copies (e2e path) and HBM-resident slots (value path)
+    host_imgs = torch.empty((2 * P, H, W), dtype=torch.uint8).pin_memory()
+    for i in range(P):
+        host_imgs[i] = torch.from_numpy(lefts[i])
+        host_imgs[P + i] = torch.from_numpy(rights[i])
+    host_np = host_imgs.numpy()
+    for s in range(2 * P):
+        ctx.upload_image(s, host_np[s])
+    ctx.synchronize()
+
+    pts0_d = torch.from_numpy(pts0_h).to(dev)
+    pts1_d = torch.zeros_like(pts0_d)
+    status_d = torch.zeros((P, n), dtype=torch.uint8, device=dev)
+    err_d = torch.zeros((P, n), dtype=torch.float32, device=dev)
+    counters_d = torch.zeros(2 * capi.VO_MAX_LEVELS, dtype=torch.int64, device=dev)
+    nlev = MAXLVL + 1
+
+    def step(ev=None, counters=None):
+        ctx.invalidate_pyramids(all_slots)
+        if ev:
+            ev[0].record(stream)
+        ctx.build_pyramids(slots0, nlev, True)
+        ctx.build_pyramids(slots1, nlev, False)
+        if ev:
+            ev[1].record(stream)
+        ctx.klt_track_batch_d(slots0, slots1, pts0_d.data_ptr(), n, WIN, MAXLVL, 0, pts1_d.data_ptr(),
+                              status_d.data_ptr(), err_d.data_ptr(), counters.data_ptr() if counters is not None else None)
+        if ev:
+            ev[2].record(stream)
+
+    # algorithmic bytes of one step's LK work, from the kernel's own counters (untimed step)
+    step(counters=counters_d)
+    torch.cuda.synchronize()
+    cnt = counters_d.cpu().numpy().reshape(-1, 2)
+    n_templ, n_iter = int(cnt[:, 0].sum()), int(cnt[:, 1].sum())
+    klt_bytes_per_step = (WIN + 1) ** 2 * (5 * n_templ + n_iter)
+    tracked = int(status_d.sum().item())
+
+    for _ in range(Wm):
+        step()
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local)
+    launches0 = ctx.launch_count
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        clocks.start()
+    e0.record(stream)
+    for k in range(K):
+        step(ev=evs[k])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    launches = ctx.launch_count - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = world * P * n / (ms_step * 1e-3)
+    pyr_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    klt_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    klt_launches_per_step = (P + 63) // 64
+    peak, peak_src = load_peak()
+    achieved = klt_bytes_per_step / (klt_ms * 1e-3) / 1e9
+
+    # ---------------------------------------------------------------- e2e (host buffers through the C ABI)
+    ptrs0 = [host_np[i].ctypes.data for i in range(P)]
+    ptrs1 = [host_np[P + i].ctypes.data for i in range(P)]
+    Ke = max(3, min(K, 10))
+
+    def e2e_step():
+        return ctx.ft_track_batch(slots0, slots1, ptrs0, ptrs1, W, H, W, pts0_h, WIN, MAXLVL, THRES_ERR)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(Ke):
+        pt_e, m_e = e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall)) / Ke
+    e2e_val = world * P * n / (e2e_ms * 1e-3)
+    h2d = 2 * P * W * H + P * n * 8 + P * n
+    d2h = P * n * 8 + P * n
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "features/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int16 fixed-point + f32", "data": "synthetic",
+        "config": {"workload": f"cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21; {P} independent pairs "
+                               f"per GPU per step (cfg5 batching); step = pyramids(both) + Scharr + LK",
+                   "pairs_per_gpu": P, "features_per_pair": n, "window": WIN, "levels": nlev,
+                   "l2_policy": "inputs larger than L2" if 2 * P * W * H > 126e6 else
+                                "working set (pyramids+derivatives) larger than L2",
+                   "tracked_ok": tracked},
+        "e2e": {"value": e2e_val, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": Ke, "api": "vo_ft_track_batch (host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_klt<14>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": klt_bytes_per_step / klt_launches_per_step,
+                     "launch_ms": klt_ms / klt_launches_per_step, "launches_per_step": klt_launches_per_step,
+                     "lk_templates": n_templ, "lk_iterations": n_iter},
+        "kernel_ms_per_step": {"pyramids+scharr": pyr_ms, "klt": klt_ms},
+        "clocks": clk,
+    }
+
+    if rank == 0 and world == 1 and not args.skip_extras:
+        out.update(side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, capi))
+    if rank == 0 and world == 1:
+        cores = os.cpu_count() or 1
+        v_all, reps, dt = cpu_reference_rate(lefts[0], rights[0], pts0_h[0], cores, args.cpu_budget)
+        v_one, reps1, dt1 = cpu_reference_rate(lefts[0], rights[0], pts0_h[0], 1, min(4.0, args.cpu_budget))
+        out["cpu_baseline"] = {
+            "value": v_all, "unit": "features/s", "cores": cores, "kind": "reference",
+            "sample": f"{reps} x (1 stereo pair, {n} features) in {dt:.1f} s: cv2.calcOpticalFlowPyrLK 4.13 "
+                      f"(the library call the reference makes, feature_tracker.cpp:29) + track() post-filter",
+            "single_thread_value": v_one}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, capi):
+    """pose-GN solves/s (batched) and single-frame ms (KLT temporal + KLT stereo + pose GN)."""
+    from oracle import pose as opose
+    res = {}
+    # ---- batched pose GN: 4096 problems x 500 points (cfg1 scene, per-problem noise)
+    nprob, npts = 4096, 500
+    s = synth.pose_scene(seed=1001, n=npts)
+    rng = np.random.default_rng(5)
+    X = np.tile(s["X"][None], (nprob, 1, 1)).astype(np.float32)
+    pl = (s["pts_l1"][None] + rng.normal(0, 0.05, (nprob, npts, 2))).astype(np.float32)
+    pr = (s["pts_r1"][None] + rng.normal(0, 0.05, (nprob, npts, 2))).astype(np.float32)
+    X_d, pl_d, pr_d = (torch.from_numpy(a).to(dev) for a in (X, pl, pr))
+    off_d = torch.arange(0, (nprob + 1) * npts, npts, dtype=torch.int32, device=dev)
+    T_d = torch.eye(4, device=dev).repeat(nprob, 1, 1).contiguous()
+    mask_d = torch.zeros(nprob * npts, dtype=torch.uint8, device=dev)
+    it_d = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    ok_d = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    K4, Tlr = synth.kitti_K(), synth.kitti_T_lr()
+    eye = torch.eye(4, device=dev).repeat(nprob, 1, 1).contiguous()
+
+    def solve():
+        T_d.copy_(eye)
+        ctx.pose_gn_stereo_batch_d(nprob, off_d.data_ptr(), X_d.data_ptr(), pl_d.data_ptr(), pr_d.data_ptr(), K4, K4,
+                                   Tlr, 3.0, T_d.data_ptr(), mask_d.data_ptr(), ok_d.data_ptr(), it_d.data_ptr())
+    for _ in range(3):
+        solve()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    a.record(stream)
+    for _ in range(reps):
+        solve()
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    t0 = time.perf_counter()
+    creps = 0
+    while time.perf_counter() - t0 < 2.0:
+        opose.pose_gn_stereo(X[creps % nprob], pl[creps % nprob], pr[creps % nprob], K4, K4, Tlr, 3.0, np.eye(4))
+        creps += 1
+    cpu_rate = creps / (time.perf_counter() - t0)
+    res["pose_gn"] = {"solves_per_s": nprob / (ms * 1e-3), "batch": nprob, "points": npts, "ms_per_batch": ms,
+                      "mean_iters": float(it_d.float().mean().item()),
+                      "cpu_port_solves_per_s_1core": cpu_rate}
+    # ---- single frame through the host C ABI: upload 2 new images, track L0->L1 and L1->R1, pose GN
+    nxt = synth.klt_stereo_case(seed=2002, n=NFEAT)
+    L0, L1, R1 = nxt["left"], nxt["next_left"], nxt["right"]
+    p0 = nxt["pts0"]
+    sc = synth.pose_scene(seed=1001, n=NFEAT)
+
+    ctx.upload_image(0, L0)   # previous left: pyramid + derivative stay cached from the previous frame
+
+    def frame():
+        ctx.upload_image(1, L1)
+        ctx.upload_image(2, R1)
+        pt, m = ctx.ft_track_with_prior(0, 1, p0, p0, WIN, MAXLVL, THRES_ERR)
+        pt2, m2 = ctx.ft_track_with_prior(1, 2, pt, pt, WIN, MAXLVL, THRES_ERR)
+        return ctx.pose_gn_stereo(sc["X"], sc["pts_l1"], sc["pts_r1"], K4, K4, Tlr, 3.0, np.eye(4))
+    for _ in range(5):
+        frame()
+    t0 = time.perf_counter()
+    reps = 50
+    for _ in range(reps):
+        frame()
+    ms_frame = (time.perf_counter() - t0) * 1e3 / reps
+    res["single_frame"] = {"ms_per_frame": ms_frame,
+                           "what": "host C ABI: 2 image uploads + 2x trackWithPrior(2000 feat) + stereo pose GN "
+                                   "(2000 pts), wall clock incl. all copies and syncs"}
+    return res
+
+
+if __name__ == "__main__":
+    main()

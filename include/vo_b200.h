@@ -84,6 +84,9 @@ VO_API int vo_set_image_d(vo_ctx *ctx, int slot, const uint8_t *data_d, int w, i
 /* Build pyramid levels 0..n_levels-1 (+ Scharr derivative if with_deriv) for a batch of
  * slots now (otherwise built lazily by the first tracking call that needs them). */
 VO_API int vo_build_pyramids(vo_ctx *ctx, const int *slots, int n_slots, int n_levels, int with_deriv);
+/* Mark the derived pyramid levels / derivatives of these slots stale (level-0 pixels stay):
+ * the next tracking call rebuilds them, as the reference does on every call. */
+VO_API int vo_invalidate_pyramids(vo_ctx *ctx, const int *slots, int n_slots);
 /* Effective maxLevel after OpenCV's clamp (next level w or h <= win -> stop). */
 VO_API int vo_effective_max_level(int w, int h, int win, int max_level);
 /* Debug/parity read-back of one level: img (w_l*h_l u8) and/or deriv (w_l*h_l*2 int16). */
@@ -121,6 +124,15 @@ VO_API int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int slot1,
                                        int n, int window_size, int max_pyr_lvl, float thres_err,
                                        float thres_bidirection, float *pts_track_inout,
                                        uint8_t *mask_inout);
+/* Batched FeatureTracker::track over n_pairs independent image pairs with HOST buffers:
+ * imgs0/imgs1 are arrays of n_pairs host image pointers (CV_8UC1, w x h, row pitch `step`;
+ * pinned memory makes the copies asynchronous; a NULL entry keeps the slot's current image),
+ * pts0 / pts_track / mask_inout are [n_pairs][n].  One H2D per image, batched kernels, one
+ * D2H of the results, one synchronisation. with_prior != 0 selects trackWithPrior. */
+VO_API int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1,
+                      const uint8_t *const *imgs0, const uint8_t *const *imgs1, int w, int h,
+                      size_t step, const float *pts0, int n, int window_size, int max_pyr_lvl,
+                      float thres_err, int with_prior, float *pts_track_inout, uint8_t *mask_inout);
 /* FeatureTracker::calcPrior (feature_tracker.cpp:208-234). Tw1: 4x4 row-major; K: fx,fy,cx,cy. */
 VO_API int vo_ft_calc_prior(vo_ctx *ctx, const float *pts0, const float *Xw, int n, const float *Tw1,
                      const float *K4, float *pts1_prior);

@@ -87,6 +87,10 @@ def lib():
     L.vo_ft_track_with_prior.argtypes = ft + [vp, vp]
     L.vo_ft_track_bidirection.argtypes = ft + [ctypes.c_float, vp, vp]
     L.vo_ft_track_bidirection_with_prior.argtypes = ft + [ctypes.c_float, vp, vp]
+    L.vo_invalidate_pyramids.argtypes = [vp, c_int_p, ctypes.c_int]
+    L.vo_ft_track_batch.argtypes = [vp, ctypes.c_int, c_int_p, c_int_p, vp, vp, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_size_t, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                    ctypes.c_int, vp, vp]
     f32 = ctypes.c_float
     L.vo_pose_gn_mono.argtypes = [vp, vp, vp, ctypes.c_int, f32, f32, f32, f32, ctypes.c_int, ctypes.c_int, vp, vp, vp,
                                   c_int_p, c_int_p]
@@ -155,6 +159,29 @@ class Context:
         ids = np.ascontiguousarray(slots, np.int32)
         check(self.h, self.L.vo_build_pyramids(self.h, ids.ctypes.data_as(c_int_p), len(ids), n_levels,
                                                1 if with_deriv else 0))
+
+    def invalidate_pyramids(self, slots):
+        ids = np.ascontiguousarray(slots, np.int32)
+        check(self.h, self.L.vo_invalidate_pyramids(self.h, ids.ctypes.data_as(c_int_p), len(ids)))
+
+    def ft_track_batch(self, slots0, slots1, img_ptrs0, img_ptrs1, w, h, step, pts0, win, lvl, thres_err,
+                       pts_track=None, mask=None, with_prior=False):
+        """Batched FeatureTracker::track(WithPrior) with host buffers. img_ptrs*: lists of host addresses
+        (ints; 0 keeps the slot's image). pts0: [n_pairs, n, 2] float32. Returns (pts_track, mask)."""
+        s0 = np.ascontiguousarray(slots0, np.int32)
+        s1 = np.ascontiguousarray(slots1, np.int32)
+        npairs = len(s0)
+        pts0 = np.ascontiguousarray(pts0, np.float32).reshape(npairs, -1, 2)
+        n = pts0.shape[1]
+        pt = (np.ascontiguousarray(pts_track, np.float32).reshape(npairs, n, 2) if pts_track is not None
+              else np.zeros_like(pts0))
+        m = np.ones((npairs, n), np.uint8) if mask is None else np.ascontiguousarray(mask, np.uint8).reshape(npairs, n)
+        a0 = (vp * npairs)(*[vp(int(p)) if p else None for p in img_ptrs0]) if img_ptrs0 is not None else None
+        a1 = (vp * npairs)(*[vp(int(p)) if p else None for p in img_ptrs1]) if img_ptrs1 is not None else None
+        check(self.h, self.L.vo_ft_track_batch(self.h, npairs, s0.ctypes.data_as(c_int_p), s1.ctypes.data_as(c_int_p),
+                                               a0, a1, w, h, step, _ptr(pts0), n, win, lvl, thres_err,
+                                               1 if with_prior else 0, _ptr(pt), _ptr(m)))
+        return pt, m
 
     def read_pyramid_level(self, slot, level, want_deriv=True):
         w, h = ctypes.c_int(), ctypes.c_int()

@@ -95,6 +95,11 @@ extern "C" int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int 
         vo_ctx_destroy(ctx);
         return VO_ERR_CUDA;
     }
+    ctx->raw_stride = (size_t)max_w * max_h;   // dense: consecutive slots are adjacent -> mergeable DMA
+    if (n_slots > 0 && cudaMalloc((void **)&ctx->raw_base, ctx->raw_stride * n_slots + 256) != cudaSuccess) {
+        vo_ctx_destroy(ctx);
+        return VO_ERR_CUDA;
+    }
     if (vo_stage_reserve(ctx, (size_t)(max_feat > 0 ? max_feat : 1) * 64) != VO_OK) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
     *out = ctx;
@@ -108,6 +113,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &S : ctx->slots) if (S.base) cudaFree(S.base);
     if (ctx->d_slots) cudaFree(ctx->d_slots);
+    if (ctx->raw_base) cudaFree(ctx->raw_base);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     for (int i = 0; i < 4; ++i) if (ctx->d_f32[i]) cudaFree(ctx->d_f32[i]);
@@ -175,6 +181,7 @@ static int slot_set_geometry(vo_ctx *ctx, int slot, int w, int h)
         L.img = S.base + offs_img[l] + (size_t)VO_PAD * pitches[l] + VO_PAD;
         L.deriv = reinterpret_cast<short2 *>(S.base + offs_der[l]) + (size_t)VO_PAD * pitches[l] + VO_PAD;
     }
+    S.desc.raw = ctx->raw_base + (size_t)slot * ctx->raw_stride;
     S.w = w; S.h = h;
     VO_CUDA(cudaMemcpyAsync(ctx->d_slots + slot, &S.desc, sizeof(SlotDesc), cudaMemcpyHostToDevice, ctx->stream));
     // the descriptor lives in pageable host memory inside the vector: make the copy complete
@@ -193,9 +200,12 @@ static int set_image_common(vo_ctx *ctx, int slot, const uint8_t *data, int w, i
     int rc = slot_set_geometry(ctx, slot, w, h);
     if (rc) return rc;
     Slot &S = ctx->slots[slot];
-    const LevelDesc &L0 = S.desc.lv[0];
-    VO_CUDA(cudaMemcpy2DAsync(L0.img, L0.pitch, data, step, w, h, kind, ctx->stream));
-    S.levels_built = 0; S.deriv_built = 0; S.border0 = false;
+    // DMA into the dense raw staging area (one contiguous copy when the source is dense);
+    // the ingest kernel moves it into the padded level-0 plane when the pyramid is built.
+    uint8_t *raw = ctx->raw_base + (size_t)slot * ctx->raw_stride;
+    if (step == (size_t)w) VO_CUDA(cudaMemcpyAsync(raw, data, (size_t)w * h, kind, ctx->stream));
+    else VO_CUDA(cudaMemcpy2DAsync(raw, w, data, step, w, h, kind, ctx->stream));
+    S.levels_built = 0; S.deriv_built = 0; S.border0 = false; S.raw_pending = true;
     return VO_OK;
 }
 
@@ -215,6 +225,17 @@ extern "C" int vo_build_pyramids(vo_ctx *ctx, const int *slots, int n_slots, int
     VO_CUDA(cudaSetDevice(ctx->device));
     if (n_levels > ctx->max_levels) n_levels = ctx->max_levels;
     return vo_ensure_pyramids(ctx, slots, n_slots, n_levels, with_deriv);
+}
+
+extern "C" int vo_invalidate_pyramids(vo_ctx *ctx, const int *slots, int n_slots)
+{
+    if (!ctx || !slots) return VO_ERR_INVALID_ARG;
+    for (int i = 0; i < n_slots; ++i) {
+        VO_REQUIRE(slots[i] >= 0 && slots[i] < ctx->n_slots, VO_ERR_INVALID_ARG, "slot id out of range");
+        Slot &S = ctx->slots[slots[i]];
+        S.levels_built = 0; S.deriv_built = 0; S.border0 = false;
+    }
+    return VO_OK;
 }
 
 extern "C" int vo_read_pyramid_level(vo_ctx *ctx, int slot, int level, uint8_t *img, int16_t *deriv, int *w_l, int *h_l)
@@ -373,4 +394,79 @@ extern "C" int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int sl
 {
     return ft_common(ctx, 4, slot0, slot1, pts0, n, window_size, max_pyr_lvl, thres_err, thres_bidirection,
                      pts_track_inout, mask_inout);
+}
+
+// Upload a list of images; consecutive slots fed from consecutive dense host images are merged
+// into ONE contiguous DMA (the raw staging areas of consecutive slots are adjacent when the
+// image fills max_w x max_h), which is what reaches full PCIe bandwidth.
+static int upload_many(vo_ctx *ctx, int n, const int *slots, const uint8_t *const *imgs, int w, int h, size_t step)
+{
+    if (!imgs) return VO_OK;
+    const size_t img_bytes = (size_t)w * h;
+    const bool mergeable = (step == (size_t)w) && (img_bytes == ctx->raw_stride);
+    int i = 0;
+    while (i < n) {
+        if (!imgs[i]) { ++i; continue; }
+        int j = i + 1;
+        while (mergeable && j < n && imgs[j] == imgs[j - 1] + img_bytes && slots[j] == slots[j - 1] + 1) ++j;
+        if (j - i > 1) {
+            for (int k = i; k < j; ++k) {
+                VO_REQUIRE(slots[k] >= 0 && slots[k] < ctx->n_slots, VO_ERR_INVALID_ARG, "slot id out of range");
+                int rc = slot_set_geometry(ctx, slots[k], w, h);
+                if (rc) return rc;
+                Slot &S = ctx->slots[slots[k]];
+                S.levels_built = 0; S.deriv_built = 0; S.border0 = false; S.raw_pending = true;
+            }
+            VO_CUDA(cudaMemcpyAsync(ctx->raw_base + (size_t)slots[i] * ctx->raw_stride, imgs[i], img_bytes * (j - i),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            int rc = vo_upload_image(ctx, slots[i], imgs[i], w, h, step);
+            if (rc) return rc;
+        }
+        i = j;
+    }
+    return VO_OK;
+}
+
+extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1,
+                                 const uint8_t *const *imgs0, const uint8_t *const *imgs1, int w, int h, size_t step,
+                                 const float *pts0, int n, int window_size, int max_pyr_lvl, float thres_err,
+                                 int with_prior, float *pts_track_inout, uint8_t *mask_inout)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0 && n_pairs >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0 || n_pairs == 0) return VO_OK;
+    VO_REQUIRE(slots0 && slots1 && pts0 && pts_track_inout && mask_inout, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    rc = upload_many(ctx, n_pairs, slots0, imgs0, w, h, step);
+    if (rc) return rc;
+    rc = upload_many(ctx, n_pairs, slots1, imgs1, w, h, step);
+    if (rc) return rc;
+    const size_t N = (size_t)n_pairs * n;
+    // staging: [pts0 N*8][pts1 N*8][err N*4][status N][mask N]
+    const size_t o_p0 = 0, o_p1 = o_p0 + N * 8, o_err = o_p1 + N * 8, o_st = o_err + N * 4, o_mask = o_st + align_up(N, 16);
+    const size_t total = o_mask + align_up(N, 16);
+    rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *hs = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(hs + o_p0, pts0, N * 8);
+    if (with_prior) memcpy(hs + o_p1, pts_track_inout, N * 8);
+    memcpy(hs + o_mask, mask_inout, N);
+    VO_CUDA(cudaMemcpyAsync(d, hs, with_prior ? N * 16 : N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(d + o_mask, hs + o_mask, N, cudaMemcpyHostToDevice, ctx->stream));
+    KltPost post{};
+    post.mode = with_prior ? 2 : 1;
+    post.thres_err = thres_err;
+    post.mask = d + o_mask;
+    rc = vo_klt_launch(ctx, n_pairs, slots0, slots1, (const float *)(d + o_p0), n, window_size, max_pyr_lvl,
+                       with_prior ? VO_KLT_USE_INITIAL_FLOW : 0, (float *)(d + o_p1), d + o_st, (float *)(d + o_err),
+                       nullptr, &post);
+    if (rc) return rc;
+    VO_CUDA(cudaMemcpyAsync(hs + o_p1, d + o_p1, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(hs + o_mask, d + o_mask, N, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(pts_track_inout, hs + o_p1, N * 8);
+    memcpy(mask_inout, hs + o_mask, N);
+    return VO_OK;
 }

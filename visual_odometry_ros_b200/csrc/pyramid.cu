@@ -19,6 +19,37 @@ __device__ __forceinline__ int reflect101(int p, int len)
 }
 
 // ---------------------------------------------------------------------------------------
+// ingest: dense raw upload (w x h, pitch w) -> interior of the padded level-0 plane.
+// 16 output bytes per thread; the raw side is read with byte-granular alignment handling
+// because w (1241) is odd, the padded side is written as aligned 128-bit words.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ingest(const SlotDesc *__restrict__ slots, const IdList ids)
+{
+    const SlotDesc &S = slots[ids.id[blockIdx.z]];
+    const LevelDesc L = S.lv[0];
+    const int y = blockIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x0 >= L.w) return;
+    const uint8_t *src = S.raw + (size_t)y * L.w + x0;
+    uint8_t *dst = L.img + (size_t)y * L.pitch + x0;
+    if (x0 + 16 <= L.w) {
+        // gather 16 bytes from an arbitrarily aligned address: 5 aligned words + funnel shifts
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ad & ~(uintptr_t)3);
+        const int sh = (int)(ad & 3) * 8;
+        const uint32_t a = __ldg(wp), b = __ldg(wp + 1), c = __ldg(wp + 2), d = __ldg(wp + 3);
+        const uint32_t e = sh ? __ldg(wp + 4) : 0u;
+        uint4 v;
+        v.x = __funnelshift_r(a, b, sh); v.y = __funnelshift_r(b, c, sh);
+        v.z = __funnelshift_r(c, d, sh); v.w = __funnelshift_r(d, e, sh);
+        *reinterpret_cast<uint4 *>(dst) = v;
+    } else {
+        for (int k = 0; x0 + k < L.w; ++k) dst[k] = src[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // pyrDown: one thread -> 4 output columns x 2 output rows.
 // ---------------------------------------------------------------------------------------
 #define PD_RPT 2
@@ -228,6 +259,18 @@ int vo_ensure_pyramids(vo_ctx *ctx, const int *slot_ids, int n, int n_levels, in
     }
     if (todo.empty()) return VO_OK;
     const int nb_total = (int)todo.size();
+    {   // slots whose pixels are still in the raw staging area
+        std::vector<int> pend;
+        for (int s : todo) if (ctx->slots[s].raw_pending) pend.push_back(s);
+        for (size_t c0 = 0; c0 < pend.size(); c0 += VO_IDLIST_MAX) {
+            const int nb = (int)(pend.size() - c0 < VO_IDLIST_MAX ? pend.size() - c0 : VO_IDLIST_MAX);
+            IdList ids;
+            for (int i = 0; i < nb; ++i) ids.id[i] = pend[c0 + i];
+            k_ingest<<<dim3(vo_div_up(vo_div_up(w, 16), 128), h, nb), 128, 0, ctx->stream>>>(ctx->d_slots, ids);
+            ctx->launches++;
+        }
+        for (int s : pend) ctx->slots[s].raw_pending = false;
+    }
     const Slot &S0 = ctx->slots[todo[0]];
     if (min_levels < 1) min_levels = 1;
     for (int c0 = 0; c0 < nb_total; c0 += VO_IDLIST_MAX) {

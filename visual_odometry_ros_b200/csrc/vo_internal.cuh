@@ -32,6 +32,7 @@ struct IdList {
 
 struct SlotDesc {
     LevelDesc lv[VO_MAX_LEVELS];
+    const uint8_t *raw;   // densely packed w x h upload target (DMA lands here at full PCIe rate)
 };
 
 struct Slot {
@@ -42,6 +43,7 @@ struct Slot {
     int levels_built = 0;     // pyramid levels valid (0 = only level 0 pixels uploaded)
     int deriv_built = 0;      // derivative levels valid
     bool border0 = false;     // level-0 border filled
+    bool raw_pending = false; // pixels sit in the raw staging area, not yet ingested into level 0
 };
 
 struct vo_ctx {
@@ -51,6 +53,8 @@ struct vo_ctx {
     int max_w = 0, max_h = 0, n_slots = 0, max_feat = 0;
     std::vector<Slot> slots;
     SlotDesc *d_slots = nullptr;   // device mirror of all slot descriptors
+    uint8_t *raw_base = nullptr;   // n_slots x raw_stride bytes: contiguous upload staging
+    size_t raw_stride = 0;
     int max_levels = 0;            // levels allocated per slot
     // pinned + device staging for the host-pointer entry points
     uint8_t *h_stage = nullptr;
