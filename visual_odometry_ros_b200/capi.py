@@ -96,6 +96,11 @@ def lib():
                                   c_int_p, c_int_p]
     L.vo_pose_gn_stereo.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, f32, vp, vp, c_int_p, c_int_p]
     L.vo_pose_gn_stereo_batch_d.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]
+    L.vo_triangulate_dlt.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    L.vo_depth_filter_normal.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
+    L.vo_depth_filter_student_t.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
+    L.vo_ft_calc_prior.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp]
+    L.vo_compact.argtypes = [vp, vp, ctypes.c_int, vp, c_int_p]
     _lib = L
     return L
 
@@ -285,3 +290,54 @@ class Context:
         check(self.h, self.L.vo_pose_gn_stereo_batch_d(
             self.h, n_prob, vp(offsets_d), vp(X_d), vp(pl_d), vp(pr_d), _ptr(Kl), _ptr(Kr), _ptr(Tlr), thres,
             vp(T01_d), vp(mask_d), vp(success_d) if success_d else None, vp(iters_d) if iters_d else None))
+
+    # ---------------------------------------------------------------- elementwise rows
+    def triangulate_dlt(self, pts0, pts1, R10, t10, K0, K1=None):
+        """mapping::triangulateDLT -> (X0, X1)."""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        n = len(p0)
+        if len(p1) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "pts0.size() != pts1.size()")   # triangulate_3d.cpp:10
+        R = np.ascontiguousarray(R10, np.float32)
+        t = np.ascontiguousarray(t10, np.float32)
+        K0 = np.ascontiguousarray(K0, np.float32)
+        K1 = K0 if K1 is None else np.ascontiguousarray(K1, np.float32)
+        X0 = np.zeros((n, 3), np.float32)
+        X1 = np.zeros((n, 3), np.float32)
+        check(self.h, self.L.vo_triangulate_dlt(self.h, _ptr(p0), _ptr(p1), n, _ptr(R), _ptr(t), _ptr(K0), _ptr(K1),
+                                                _ptr(X0), _ptr(X1)))
+        return X0, X1
+
+    def depth_filter_normal(self, x_prev, cov_prev, x_curr, cov_curr):
+        a = [np.ascontiguousarray(v, np.float64) for v in (x_prev, cov_prev, x_curr, cov_curr)]
+        n = len(a[0])
+        x, c = np.zeros(n), np.zeros(n)
+        check(self.h, self.L.vo_depth_filter_normal(self.h, *[_ptr(v) for v in a], n, _ptr(x), _ptr(c)))
+        return x, c
+
+    def depth_filter_student_t(self, x_prev, cov_prev, a, b, x_min, x_max, x_curr, cov_curr):
+        xp, cp, xc, cc = [np.ascontiguousarray(v, np.float64) for v in (x_prev, cov_prev, x_curr, cov_curr)]
+        a, b, lo, hi = [np.ascontiguousarray(v, np.float64).copy() for v in (a, b, x_min, x_max)]
+        n = len(xp)
+        x, c = np.zeros(n), np.zeros(n)
+        check(self.h, self.L.vo_depth_filter_student_t(self.h, _ptr(xp), _ptr(cp), _ptr(a), _ptr(b), _ptr(lo), _ptr(hi),
+                                                       _ptr(xc), _ptr(cc), n, _ptr(x), _ptr(c)))
+        return x, c, a, b, lo, hi
+
+    def calc_prior(self, pts0, Xw, Tw1, K4):
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        X = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3)
+        n = len(X)
+        T = np.ascontiguousarray(Tw1, np.float32)
+        K = np.ascontiguousarray(K4, np.float32)
+        out = p0.copy()
+        check(self.h, self.L.vo_ft_calc_prior(self.h, _ptr(p0), _ptr(X), n, _ptr(T), _ptr(K), _ptr(out)))
+        return out
+
+    def compact(self, mask):
+        m = np.ascontiguousarray(mask).astype(np.uint8)
+        idx = np.zeros(max(len(m), 1), np.int32)
+        k = ctypes.c_int(0)
+        check(self.h, self.L.vo_compact(self.h, _ptr(m), len(m), _ptr(idx), ctypes.byref(k)))
+        return idx[:k.value]

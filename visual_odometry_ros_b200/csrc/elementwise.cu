@@ -1,0 +1,413 @@
+// elementwise.cu -- K-tri, K-df, K-prior, K-compact: the batched elementwise rows of the hot path.
+//
+//   K-tri     mapping::triangulateDLT          core/util/triangulate_3d.cpp:5-130
+//   K-df      DepthFilter::update*Distribution standalone/depth_filter/depth_filter.cpp:3-46
+//   K-prior   FeatureTracker::calcPrior        core/visual_odometry/feature_tracker.cpp:208-234
+//   K-compact LandmarkTracking(src, mask)      core/visual_odometry/landmark.cpp:194-231, 291-332
+//
+// One thread per element, coalesced SoA-style streaming; all arithmetic in the reference's
+// precision (FP32 for K-tri / K-prior, FP64 for K-df) with the reference's operation order --
+// this file is compiled with -fmad=false so results match the non-FMA CPU build operation by
+// operation.  These kernels are pure HBM-streaming work (16 B in + 24 B out per triangulated
+// point, 48 B / 128 B per depth seed): they are launch-latency-bound at the reference's sizes.
+#include "vo_internal.cuh"
+
+#include <cfloat>
+#include <cstring>
+
+// ------------------------------------------------------------------------------ K-tri
+// 4x4 FP32 two-sided Jacobi SVD (the algorithm of Eigen::JacobiSVD for a square real matrix):
+// returns the right-singular vector of the smallest singular value.
+__device__ __forceinline__ void make_jacobi(float x, float y, float z, float &c, float &s)
+{
+    const float deno = 2.f * fabsf(y);
+    if (deno < FLT_MIN) { c = 1.f; s = 0.f; return; }
+    const float tau = (x - z) / deno;
+    const float w = sqrtf(tau * tau + 1.f);
+    const float t = (tau > 0.f) ? 1.f / (tau + w) : 1.f / (tau - w);
+    const float sign_t = t > 0.f ? 1.f : -1.f;
+    const float n = 1.f / sqrtf(t * t + 1.f);
+    s = -sign_t * (y / fabsf(y)) * fabsf(t) * n;
+    c = n;
+}
+
+__device__ void svd4_null(const float *M, float *v4)
+{
+    float W[16], V[16];
+    float scale = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) scale = fmaxf(scale, fabsf(M[i]));
+    if (scale == 0.f) scale = 1.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { W[i] = M[i] / scale; V[i] = (i % 5 == 0) ? 1.f : 0.f; }
+    float maxDiag = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) maxDiag = fmaxf(maxDiag, fabsf(W[i * 5]));
+    const float precision = 2.f * FLT_EPSILON;
+    bool finished = false;
+    int sweeps = 0;
+    while (!finished && sweeps < 64) {
+        finished = true;
+        ++sweeps;
+#pragma unroll
+        for (int p = 1; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < p; ++q) {
+                const float thr = fmaxf(FLT_MIN, precision * maxDiag);
+                if (fabsf(W[p * 4 + q]) > thr || fabsf(W[q * 4 + p]) > thr) {
+                    finished = false;
+                    const float m00 = W[p * 4 + p], m01 = W[p * 4 + q], m10 = W[q * 4 + p], m11 = W[q * 4 + q];
+                    const float t = m00 + m11, d = m10 - m01;
+                    float c1, s1;
+                    if (fabsf(d) < FLT_MIN) { s1 = 0.f; c1 = 1.f; }
+                    else { const float u = t / d; const float tmp = sqrtf(1.f + u * u); s1 = 1.f / tmp; c1 = u / tmp; }
+                    const float a00 = c1 * m00 + s1 * m10, a01 = c1 * m01 + s1 * m11;
+                    const float a11 = -s1 * m01 + c1 * m11;
+                    float cr, sr;
+                    make_jacobi(a00, a01, a11, cr, sr);
+                    const float cl = c1 * cr - s1 * (-sr);
+                    const float sl = c1 * (-sr) + s1 * cr;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {   // rows p,q of W
+                        const float xi = W[p * 4 + i], yi = W[q * 4 + i];
+                        W[p * 4 + i] = cl * xi + sl * yi;
+                        W[q * 4 + i] = -sl * xi + cl * yi;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {   // columns p,q of W and V
+                        const float xi = W[i * 4 + p], yi = W[i * 4 + q];
+                        W[i * 4 + p] = cr * xi - sr * yi;
+                        W[i * 4 + q] = sr * xi + cr * yi;
+                        const float xv = V[i * 4 + p], yv = V[i * 4 + q];
+                        V[i * 4 + p] = cr * xv - sr * yv;
+                        V[i * 4 + q] = sr * xv + cr * yv;
+                    }
+                    maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[p * 4 + p]), fabsf(W[q * 4 + q])));
+                }
+            }
+    }
+    int k = 0;
+    float best = fabsf(W[0]);
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (fabsf(W[i * 5]) < best) { best = fabsf(W[i * 5]); k = i; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v4[i] = V[i * 4 + k];
+}
+
+struct TriArgs {
+    const float2 *p0, *p1;
+    float *X0, *X1;
+    int n;
+    float R10[9], t10[3], K0[4], K1[4];
+};
+
+__global__ void __launch_bounds__(128) k_triangulate(const TriArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float fx0 = a.K0[0], fy0 = a.K0[1], cx0 = a.K0[2], cy0 = a.K0[3];
+    const float fx1 = a.K1[0], fy1 = a.K1[1], cx1 = a.K1[2], cy1 = a.K1[3];
+    float P10[12];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        P10[0 * 4 + j] = (fx1 * a.R10[0 * 3 + j] + 0.f * a.R10[1 * 3 + j]) + cx1 * a.R10[2 * 3 + j];
+        P10[1 * 4 + j] = (0.f * a.R10[0 * 3 + j] + fy1 * a.R10[1 * 3 + j]) + cy1 * a.R10[2 * 3 + j];
+        P10[2 * 4 + j] = (0.f * a.R10[0 * 3 + j] + 0.f * a.R10[1 * 3 + j]) + 1.f * a.R10[2 * 3 + j];
+    }
+    P10[0 * 4 + 3] = (fx1 * a.t10[0] + 0.f * a.t10[1]) + cx1 * a.t10[2];
+    P10[1 * 4 + 3] = (0.f * a.t10[0] + fy1 * a.t10[1]) + cy1 * a.t10[2];
+    P10[2 * 4 + 3] = (0.f * a.t10[0] + 0.f * a.t10[1]) + 1.f * a.t10[2];
+    const float2 q0 = a.p0[i], q1 = a.p1[i];
+    float M[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) M[j] = 0.f;
+    M[0] = -fx0; M[2] = q0.x - cx0;
+    M[5] = -fy0; M[6] = q0.y - cy0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        M[8 + j] = q1.x * P10[8 + j] - P10[0 + j];
+        M[12 + j] = q1.y * P10[8 + j] - P10[4 + j];
+    }
+    float v[4];
+    svd4_null(M, v);
+    const float x0 = v[0] / v[3], x1 = v[1] / v[3], x2 = v[2] / v[3];
+    a.X0[3 * i] = x0; a.X0[3 * i + 1] = x1; a.X0[3 * i + 2] = x2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        a.X1[3 * i + r] = ((a.R10[r * 3 + 0] * x0 + a.R10[r * 3 + 1] * x1) + a.R10[r * 3 + 2] * x2) + a.t10[r];
+}
+
+// ------------------------------------------------------------------------------ K-df
+__global__ void __launch_bounds__(256)
+k_df_normal(const double *__restrict__ xp, const double *__restrict__ cp, const double *__restrict__ xc,
+            const double *__restrict__ cc, int n, double *__restrict__ xu, double *__restrict__ cu)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double inv_cov_sum = 1.0 / (cp[i] + cc[i]);
+    cu[i] = (cp[i] * cc[i]) * inv_cov_sum;
+    xu[i] = (xp[i] * cc[i] + xc[i] * cp[i]) * inv_cov_sum;
+}
+
+__global__ void __launch_bounds__(256)
+k_df_student_t(const double *__restrict__ xp, const double *__restrict__ cp, double *__restrict__ a,
+               double *__restrict__ b, double *__restrict__ xmin, double *__restrict__ xmax,
+               const double *__restrict__ xc, const double *__restrict__ cc, int n, double *__restrict__ xu,
+               double *__restrict__ cu)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mu = xp[i], s2 = cp[i], t2 = cc[i], x = xc[i];
+    const double ai = a[i], bi = b[i];
+    const double inv_apb = 1.0 / (ai + bi);
+    const double x_range = xmax[i] - xmin[i];
+    const double sigma = sqrt(s2);
+    double C1 = ai * inv_apb * 1.0 / sqrt(2.0 * 3.141592) / sigma * exp(-(x - mu) * (x - mu) / (2.0 * s2));
+    double C2 = bi * inv_apb / x_range;
+    const double invC = 1.0 / (C1 + C2);
+    C1 *= invC;
+    C2 *= invC;
+    const double ss = 1.0 / (1.0 / s2 + 1.0 / t2);
+    const double m = ss * (mu / s2 + x / t2);
+    const double mu_new = C1 * m + C2 * mu;
+    const double var_new = C1 * (ss + m * m) + C2 * (s2 + mu * mu) - mu_new * mu_new;
+    const double F = C1 * (ai + 1.0) / (ai + bi + 1.0) + C2 * ai / (ai + bi + 1.0);
+    const double E = C1 * (ai + 1.0) / (ai + bi + 1.0) * (ai + 2.0) / (ai + bi + 2.0) +
+                     C2 * ai / (ai + bi + 1.0) * (ai + 1.0) / (ai + bi + 2.0);
+    const double a_new = (E - F) / (F - E / F);
+    a[i] = a_new;
+    b[i] = a_new * (1.0 - F) / F;
+    xu[i] = mu_new;
+    cu[i] = var_new;
+    xmin[i] = fmin(xmin[i], x);
+    xmax[i] = fmax(xmax[i], x);
+}
+
+// ------------------------------------------------------------------------------ K-prior
+struct PriorArgs {
+    const float2 *pts0;
+    const float *Xw;
+    float2 *out;
+    int n;
+    float T1w[12];
+    float K[4];
+};
+
+__global__ void __launch_bounds__(256) k_calc_prior(const PriorArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float x0 = a.Xw[3 * i], x1 = a.Xw[3 * i + 1], x2 = a.Xw[3 * i + 2];
+    float X1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) X1[r] = ((a.T1w[r * 4 + 0] * x0 + a.T1w[r * 4 + 1] * x1) + a.T1w[r * 4 + 2] * x2) + a.T1w[r * 4 + 3];
+    const float nrm = sqrtf((X1[0] * X1[0] + X1[1] * X1[1]) + X1[2] * X1[2]);
+    float2 o = a.pts0[i];
+    if (nrm > 0.f) {
+        o.x = a.K[0] * X1[0] / X1[2] + a.K[2];
+        o.y = a.K[1] * X1[1] / X1[2] + a.K[3];
+    }
+    a.out[i] = o;
+}
+
+// ------------------------------------------------------------------------------ K-compact
+// Stable stream compaction by one CTA: ballot/popc scan inside warps, shared-memory scan
+// across warps, running base across chunks (feature counts are a few thousand).
+__global__ void __launch_bounds__(1024) k_compact(const uint8_t *__restrict__ mask, int n, int *__restrict__ index_out,
+                                                   int *__restrict__ n_out)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+        const int i = c0 + tid;
+        const bool keep = (i < n) && mask[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int within = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        if (wid == 0) {
+            int v = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            s_warp[lane] = v;   // inclusive
+        }
+        __syncthreads();
+        const int base = s_base + (wid ? s_warp[wid - 1] : 0);
+        if (keep) index_out[base + within] = i;
+        __syncthreads();
+        if (tid == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = s_base;
+}
+
+// ------------------------------------------------------------------------------ host side
+static void inverse4_host(const float *m, float *out)
+{
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const float id = 1.0f / det;
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * id;
+}
+
+extern "C" int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,
+                                  const float *t10, const float *K0_4, const float *K1_4, float *X0, float *X1)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(pts0 && pts1 && R10 && t10 && K0_4 && K1_4 && X0 && X1, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t o0 = 0, o1 = (size_t)n * 8, oX0 = (size_t)n * 16, oX1 = oX0 + (size_t)n * 12, total = oX1 + (size_t)n * 12;
+    int rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h + o0, pts0, (size_t)n * 8);
+    memcpy(h + o1, pts1, (size_t)n * 8);
+    VO_CUDA(cudaMemcpyAsync(d, h, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    TriArgs a;
+    a.p0 = (const float2 *)(d + o0); a.p1 = (const float2 *)(d + o1);
+    a.X0 = (float *)(d + oX0); a.X1 = (float *)(d + oX1); a.n = n;
+    memcpy(a.R10, R10, 36); memcpy(a.t10, t10, 12); memcpy(a.K0, K0_4, 16); memcpy(a.K1, K1_4, 16);
+    k_triangulate<<<vo_div_up(n, 128), 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h + oX0, d + oX0, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(X0, h + oX0, (size_t)n * 12);
+    memcpy(X1, h + oX1, (size_t)n * 12);
+    return VO_OK;
+}
+
+extern "C" int vo_depth_filter_normal(vo_ctx *ctx, const double *x_prev, const double *cov_prev, const double *x_curr,
+                                      const double *cov_curr, int n, double *x_upd, double *cov_upd)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(x_prev && cov_prev && x_curr && cov_curr && x_upd && cov_upd, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n * 8;
+    int rc = vo_stage_reserve(ctx, 6 * N);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h, x_prev, N); memcpy(h + N, cov_prev, N); memcpy(h + 2 * N, x_curr, N); memcpy(h + 3 * N, cov_curr, N);
+    VO_CUDA(cudaMemcpyAsync(d, h, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    double *D = (double *)d;
+    k_df_normal<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(D, D + n, D + 2 * n, D + 3 * n, n, D + 4 * n, D + 5 * n);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h + 4 * N, d + 4 * N, 2 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(x_upd, h + 4 * N, N);
+    memcpy(cov_upd, h + 5 * N, N);
+    return VO_OK;
+}
+
+extern "C" int vo_depth_filter_student_t(vo_ctx *ctx, const double *x_prev, const double *cov_prev, double *a_inout,
+                                         double *b_inout, double *x_min_inout, double *x_max_inout, const double *x_curr,
+                                         const double *cov_curr, int n, double *x_upd, double *cov_upd)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(x_prev && cov_prev && a_inout && b_inout && x_min_inout && x_max_inout && x_curr && cov_curr && x_upd && cov_upd,
+               VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n * 8;
+    int rc = vo_stage_reserve(ctx, 10 * N);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    // layout: [a b xmin xmax | xu cu] (in-out + out, contiguous for one D2H) then inputs
+    memcpy(h, a_inout, N); memcpy(h + N, b_inout, N); memcpy(h + 2 * N, x_min_inout, N); memcpy(h + 3 * N, x_max_inout, N);
+    memcpy(h + 6 * N, x_prev, N); memcpy(h + 7 * N, cov_prev, N); memcpy(h + 8 * N, x_curr, N); memcpy(h + 9 * N, cov_curr, N);
+    VO_CUDA(cudaMemcpyAsync(d, h, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(d + 6 * N, h + 6 * N, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    double *D = (double *)d;
+    k_df_student_t<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(D + 6 * n, D + 7 * n, D, D + n, D + 2 * n, D + 3 * n,
+                                                              D + 8 * n, D + 9 * n, n, D + 4 * n, D + 5 * n);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h, d, 6 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(a_inout, h, N); memcpy(b_inout, h + N, N); memcpy(x_min_inout, h + 2 * N, N); memcpy(x_max_inout, h + 3 * N, N);
+    memcpy(x_upd, h + 4 * N, N); memcpy(cov_upd, h + 5 * N, N);
+    return VO_OK;
+}
+
+extern "C" int vo_ft_calc_prior(vo_ctx *ctx, const float *pts0, const float *Xw, int n, const float *Tw1, const float *K4,
+                                float *pts1_prior)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(pts0 && Xw && Tw1 && K4 && pts1_prior, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t oP = 0, oX = (size_t)n * 8, oO = oX + (size_t)n * 12, total = oO + (size_t)n * 8;
+    int rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h + oP, pts0, (size_t)n * 8);
+    memcpy(h + oX, Xw, (size_t)n * 12);
+    VO_CUDA(cudaMemcpyAsync(d, h, oO, cudaMemcpyHostToDevice, ctx->stream));
+    PriorArgs a;
+    a.pts0 = (const float2 *)(d + oP); a.Xw = (const float *)(d + oX); a.out = (float2 *)(d + oO); a.n = n;
+    float T1w[16];
+    inverse4_host(Tw1, T1w);   // Tw1.inverse(), feature_tracker.cpp:215 (a 4x4 parameter, not data)
+    memcpy(a.T1w, T1w, 48);
+    memcpy(a.K, K4, 16);
+    k_calc_prior<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h + oO, d + oO, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(pts1_prior, h + oO, (size_t)n * 8);
+    return VO_OK;
+}
+
+extern "C" int vo_compact(vo_ctx *ctx, const uint8_t *mask, int n, int *index_out, int *n_out)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0 && n_out, VO_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) { *n_out = 0; return VO_OK; }
+    VO_REQUIRE(mask && index_out, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t oM = 0, oC = ((size_t)n + 15) / 16 * 16, oI = oC + 16, total = oI + (size_t)n * 4;
+    int rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h + oM, mask, (size_t)n);
+    VO_CUDA(cudaMemcpyAsync(d, h, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    k_compact<<<1, 1024, 0, ctx->stream>>>(d + oM, n, (int *)(d + oI), (int *)(d + oC));
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h + oC, d + oC, total - oC, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int k = *(int *)(h + oC);
+    *n_out = k;
+    memcpy(index_out, h + oI, (size_t)k * 4);
+    return VO_OK;
+}
