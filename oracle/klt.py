@@ -172,3 +172,43 @@ def track_bidirection_with_prior(lk, img0, img1, pts0, prior, win, max_lvl, thre
     m &= (stb > 0) & (np.where(stb > 0, errb, 0) <= np.float32(thres_err))
     m &= dist2 <= thres_bi2 * np.float32(5)
     return p1, m
+
+
+# --------------------------------------------------------------------------
+# trackWithScale (feature_tracker.cpp:236-504) -- oracle/klt_scale_oracle.c
+# --------------------------------------------------------------------------
+def sobel3_f32(img):
+    """cv::Sobel(img, CV_32F, 1,0 / 0,1, ksize=3, BORDER_DEFAULT) restated (stereo_vo.cpp:551-552)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    du = np.empty((h, w), np.float32)
+    dv = np.empty((h, w), np.float32)
+    lib().orc_sobel3_f32(_p(img, _u8p), w, h, w, _p(du, _f32p), _p(dv, _f32p))
+    return du, dv
+
+
+def track_with_scale(img0, img1, pts0, scale_est, pts_track, mask_in=None, du0=None, dv0=None, faithful=False,
+                     return_iters=False):
+    img0 = np.ascontiguousarray(img0, np.uint8)
+    img1 = np.ascontiguousarray(img1, np.uint8)
+    h, w = img0.shape
+    if du0 is None:
+        du0, dv0 = sobel3_f32(img0)
+    du0 = np.ascontiguousarray(du0, np.float32)
+    dv0 = np.ascontiguousarray(dv0, np.float32)
+    pts0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+    n = len(pts0)
+    sc = np.ascontiguousarray(scale_est, np.float32)
+    pt = np.ascontiguousarray(pts_track, np.float32).reshape(-1, 2).copy()
+    if len(pt) != n:
+        raise RuntimeError("pts_track.size() != pts0.size()")
+    m = _mask0(mask_in, n).astype(np.uint8)
+    iters = np.zeros(max(n, 1), np.int32)
+    rc = lib().orc_track_with_scale(_p(img0, _u8p), _p(du0, _f32p), _p(dv0, _f32p), _p(img1, _u8p), w, h, w, w,
+                                    _p(pts0, _f32p), _p(sc, _f32p), n, _p(pt, _f32p), _p(m, _u8p),
+                                    1 if faithful else 0, _p(iters, _i32p))
+    if rc != 0:
+        raise RuntimeError("ax ay nan / dtu dtv nan")
+    if return_iters:
+        return pt, m.astype(bool), iters[:n]
+    return pt, m.astype(bool)

@@ -101,6 +101,7 @@ def lib():
     L.vo_depth_filter_student_t.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.vo_ft_calc_prior.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp]
     L.vo_compact.argtypes = [vp, vp, ctypes.c_int, vp, c_int_p]
+    L.vo_ft_track_with_scale.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]
     _lib = L
     return L
 
@@ -341,3 +342,15 @@ class Context:
         k = ctypes.c_int(0)
         check(self.h, self.L.vo_compact(self.h, _ptr(m), len(m), _ptr(idx), ctypes.byref(k)))
         return idx[:k.value]
+
+    def ft_track_with_scale(self, slot0, slot1, pts0, scale_est, pts_track, mask=None):
+        """FeatureTracker::trackWithScale -> (pts_track, mask)."""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        n = len(p0)
+        pt = np.ascontiguousarray(pts_track, np.float32).reshape(-1, 2).copy()
+        if len(pt) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "pts_track.size() != pts0.size()")   # feature_tracker.cpp:283
+        sc = np.ascontiguousarray(scale_est, np.float32)
+        m = np.ones(n, np.uint8) if mask is None else np.ascontiguousarray(mask).astype(np.uint8).copy()
+        check(self.h, self.L.vo_ft_track_with_scale(self.h, slot0, slot1, _ptr(p0), _ptr(sc), n, _ptr(pt), _ptr(m)))
+        return pt, m.astype(bool)
