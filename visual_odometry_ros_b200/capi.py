@@ -102,6 +102,7 @@ def lib():
     L.vo_ft_calc_prior.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp]
     L.vo_compact.argtypes = [vp, vp, ctypes.c_int, vp, c_int_p]
     L.vo_ft_track_with_scale.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]
+    L.vo_lba_solve.argtypes = [vp, ctypes.POINTER(LbaProblem), vp, vp, vp, c_int_p]
     _lib = L
     return L
 
@@ -354,3 +355,34 @@ class Context:
         m = np.ones(n, np.uint8) if mask is None else np.ascontiguousarray(mask).astype(np.uint8).copy()
         check(self.h, self.L.vo_ft_track_with_scale(self.h, slot0, slot1, _ptr(p0), _ptr(sc), n, _ptr(pt), _ptr(m)))
         return pt, m.astype(bool)
+
+    # ---------------------------------------------------------------- local bundle adjustment
+    def lba_solve(self, p):
+        """SparseBundleAdjustmentSolver::solveForFiniteIterations on a flat problem dict
+        (layout of synth.lba_problem / vo_lba_problem). Returns (poses, points, avg_err, success)."""
+        keep = {}
+        for k, dt in (("poses", np.float64), ("opt_index", np.int32), ("points", np.float64), ("obs_ptr", np.int32),
+                      ("obs_frame", np.int32), ("obs_right", np.uint8), ("obs_px", np.float64)):
+            keep[k] = np.ascontiguousarray(p[k], dt)
+        s = LbaProblem()
+        s.n_frames, s.n_opt, s.n_points, s.n_obs = int(p["n_frames"]), int(p["n_opt"]), int(p["n_points"]), int(p["n_obs"])
+        s.poses = keep["poses"].ctypes.data_as(c_f64_p)
+        s.opt_index = keep["opt_index"].ctypes.data_as(c_int_p)
+        s.points = keep["points"].ctypes.data_as(c_f64_p)
+        s.obs_ptr = keep["obs_ptr"].ctypes.data_as(c_int_p)
+        s.obs_frame = keep["obs_frame"].ctypes.data_as(c_int_p)
+        s.obs_right = keep["obs_right"].ctypes.data_as(c_u8_p)
+        s.obs_px = keep["obs_px"].ctypes.data_as(c_f64_p)
+        s.K_l = (ctypes.c_double * 4)(*[float(v) for v in p["K_l"]])
+        s.K_r = (ctypes.c_double * 4)(*[float(v) for v in p["K_r"]])
+        s.T_lr = (ctypes.c_double * 16)(*[float(v) for v in np.asarray(p["T_lr"], np.float64).ravel()])
+        s.is_stereo = int(p["is_stereo"])
+        s.huber = float(p["huber"])
+        s.lambda_ = float(p["lam"])
+        s.max_iter = int(p["max_iter"])
+        poses = np.zeros((s.n_frames, 4, 4))
+        points = np.zeros((max(s.n_points, 1), 3))
+        avg = np.zeros(s.max_iter)
+        ok = ctypes.c_int(0)
+        check(self.h, self.L.vo_lba_solve(self.h, ctypes.byref(s), _ptr(poses), _ptr(points), _ptr(avg), ctypes.byref(ok)))
+        return poses, points[:s.n_points], avg, bool(ok.value)

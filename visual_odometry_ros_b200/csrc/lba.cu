@@ -1,0 +1,763 @@
+// lba.cu -- K-lba-*: sliding-window local bundle adjustment (Schur-complement LM), FP64.
+//
+// Replaces SparseBundleAdjustmentSolver::solveForFiniteIterations
+// (core/visual_odometry/ba_solver/sparse_bundle_adjustment.cpp:150-768) on the flat problem that
+// SparseBAParameters::setPosesAndPoints packs (ba_solver/sparse_ba_parameters.h:292-465).
+//
+// Per LM iteration two launches (deterministic: no floating-point atomics anywhere):
+//   k_lba_build  one CTA per TILE of landmarks, one warp per landmark, one lane per observation.
+//                Applies the previous iteration's point update, evaluates residuals / Jacobians,
+//                C_i, b_i (warp shuffles), A_j, a_j (per-warp shared accumulators, summed in a fixed
+//                order), the last-writer cross blocks B[j][i], damps and inverts C_i (3x3 pivoted
+//                LDLT), forms BCinv and stages the tile as two dense shared-memory panels
+//                P = [BCinv_i], Q = [B_i | b_i]; the tile's Schur contribution P^T Q -- a dense
+//                (6 N_opt) x (6 N_opt + 1) x (3 TL) contraction -- is then formed with every thread
+//                owning fixed output entries.  The reference instead memsets and walks four dense
+//                N_opt x M block arrays (23 MB) per iteration (:844-885).
+//   k_lba_solve  one CTA: fixed-order reduction of the tile partials, damping, reduced camera system
+//                S = blkdiag(A) - BCinvBt, pivoted LDLT (the algorithm of Eigen::LDLT) in shared
+//                memory, pose retraction T <- Exp(Log(Exp(x) Exp(Log T))), error bookkeeping.
+// Reference defects kept: B assigned not accumulated (last observation
+// of (landmark, keyframe) wins), right-camera Q fed to the Q(0,1)=Q(1,0)=0 shortcut, strict '>' Huber
+// gate, SE3Log's w=0 snap, transposed diagonal blocks of BCinvBt.  Compiled with -fmad=false.
+#include "vo_internal.cuh"
+
+#include <cstring>
+#include <vector>
+
+#define LBA_WARPS 8
+#define LBA_THREADS (LBA_WARPS * 32)
+#define LBA_MAX_OPT 16
+#define LBA_NA 27            // 21 upper entries of Q^T W Q + 6 entries of Q^T W r
+
+struct LbaDev {
+    int n_frames, n_opt, n_points, n_obs, n_tiles, tile, n6;
+    double *poses;           // [n_frames][16]
+    const int *opt_index;    // [n_frames]
+    int *opt_frame;          // [n_opt]
+    double *points;          // [n_points][3]
+    const int *obs_ptr;
+    const int *obs_frame;
+    const uint8_t *obs_right;
+    const double *obs_px;
+    double *bcinv;           // [n_obs][18]   BCinv[j][i] of left-opt observations (row-major 6x3)
+    double *cinv_b;          // [n_points][3]
+    double *s_part;          // [n_tiles][n6*(n6+1)]
+    double *a_part;          // [n_tiles][n_opt][27]
+    double *err_part;        // [n_tiles]
+    double *x;               // [n6]
+    double *avg_err;         // [max_iter]
+    int *nan_flag;
+    double K_l[4], K_r[4];
+    double R_rl[9], t_rl[3];
+    double huber, lambda;
+};
+
+// ------------------------------------------------------------------ small FP64 helpers
+__device__ void ldlt3_inverse(const double *Cin, double *Cinv)
+{
+    // Eigen::LDLT<Matrix3d>::solve(Identity): unblocked, diagonal pivoting, lower storage
+    double m[9];
+    int tr[3];
+    for (int i = 0; i < 9; ++i) m[i] = Cin[i];
+#define M3(i, j) m[(i) * 3 + (j)]
+    for (int k = 0; k < 3; ++k) {
+        int big = k;
+        double bv = fabs(M3(k, k));
+        for (int i = k + 1; i < 3; ++i) if (fabs(M3(i, i)) > bv) { bv = fabs(M3(i, i)); big = i; }
+        tr[k] = big;
+        if (big != k) {
+            const int s = 3 - big - 1;
+            for (int j = 0; j < k; ++j) { const double t = M3(k, j); M3(k, j) = M3(big, j); M3(big, j) = t; }
+            for (int i = 0; i < s; ++i) { const double t = M3(big + 1 + i, k); M3(big + 1 + i, k) = M3(big + 1 + i, big); M3(big + 1 + i, big) = t; }
+            { const double t = M3(k, k); M3(k, k) = M3(big, big); M3(big, big) = t; }
+            for (int i = k + 1; i < big; ++i) { const double t = M3(i, k); M3(i, k) = M3(big, i); M3(big, i) = t; }
+        }
+        const int rs = 3 - k - 1;
+        if (k > 0) {
+            double temp[3];
+            for (int j = 0; j < k; ++j) temp[j] = M3(j, j) * M3(k, j);
+            double s = 0;
+            for (int j = 0; j < k; ++j) s += M3(k, j) * temp[j];
+            M3(k, k) -= s;
+            for (int i = 0; i < rs; ++i) {
+                double s2 = 0;
+                for (int j = 0; j < k; ++j) s2 += M3(k + 1 + i, j) * temp[j];
+                M3(k + 1 + i, k) -= s2;
+            }
+        }
+        const double akk = M3(k, k);
+        if (rs > 0 && fabs(akk) > 0.0) for (int i = 0; i < rs; ++i) M3(k + 1 + i, k) /= akk;
+    }
+    const double tol = 1.0 / 1.7976931348623157e308;
+    for (int c = 0; c < 3; ++c) {
+        double y[3] = {c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0};
+        for (int k = 0; k < 3; ++k) if (tr[k] != k) { const double t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+        for (int i = 0; i < 3; ++i) { double s = y[i]; for (int j = 0; j < i; ++j) s -= M3(i, j) * y[j]; y[i] = s; }
+        for (int i = 0; i < 3; ++i) y[i] = fabs(M3(i, i)) > tol ? y[i] / M3(i, i) : 0.0;
+        for (int i = 2; i >= 0; --i) { double s = y[i]; for (int j = i + 1; j < 3; ++j) s -= M3(j, i) * y[j]; y[i] = s; }
+        for (int k = 2; k >= 0; --k) if (tr[k] != k) { const double t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+        for (int i = 0; i < 3; ++i) Cinv[i * 3 + c] = y[i];
+    }
+#undef M3
+}
+
+__device__ void se3exp_d(const double *xi, double *T)
+{
+    const double v[3] = {xi[0], xi[1], xi[2]}, w[3] = {xi[3], xi[4], xi[5]};
+    const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double wx[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double wxwx[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += wx[i * 3 + k] * wx[k * 3 + j];
+            wxwx[i * 3 + j] = s;
+        }
+    double a, b, c;
+    if (theta < 1e-9) { a = 1.0; b = 0.5; c = 0.33333333333333333333333333; }
+    else {
+        const double invtheta2 = 1.0 / (theta * theta);
+        a = sin(theta) / theta;
+        b = (1 - cos(theta)) * invtheta2;
+        c = (theta - sin(theta)) / (theta * theta * theta);
+    }
+    double V[9];
+    for (int i = 0; i < 16; ++i) T[i] = 0.0;
+    for (int i = 0; i < 9; ++i) {
+        const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+        const int r = i / 3, cc = i - 3 * r;
+        T[r * 4 + cc] = (id + a * wx[i]) + b * wxwx[i];
+        V[i] = (id + b * wx[i]) + c * wxwx[i];
+    }
+    for (int i = 0; i < 3; ++i) T[i * 4 + 3] = (V[i * 3] * v[0] + V[i * 3 + 1] * v[1]) + V[i * 3 + 2] * v[2];
+    T[15] = 1.0;
+}
+
+__device__ void se3log_d(const double *T, double *xi)
+{
+    double R[9], t[3];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = T[i * 4 + j]; t[i] = T[i * 4 + 3]; }
+    const double inCos = ((R[0] + R[4] + R[8]) - 1.0) * 0.5;
+    double w[3] = {0, 0, 0};
+    double Vin[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (!(inCos >= 0.999999999)) {
+        const double theta = acos(inCos);
+        const double invTheta = 1.0 / theta, invTheta2 = invTheta * invTheta;
+        const double k = theta / (2.0 * sin(theta));
+        double lnR[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) lnR[i * 3 + j] = k * (R[i * 3 + j] - R[j * 3 + i]);
+        w[0] = -lnR[5]; w[1] = lnR[2]; w[2] = -lnR[1];
+        const double wx[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+        double wxwx[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int kk = 0; kk < 3; ++kk) s += wx[i * 3 + kk] * wx[kk * 3 + j];
+                wxwx[i * 3 + j] = s;
+            }
+        const double A = sin(theta) * invTheta;
+        const double B = (1.0 - cos(theta)) * invTheta2;
+        const double cc = invTheta2 * (1.0 - A / (2.0 * B));
+        for (int i = 0; i < 9; ++i) {
+            const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+            Vin[i] = (id - 0.5 * wx[i]) + cc * wxwx[i];
+        }
+    }
+    for (int i = 0; i < 3; ++i) xi[i] = (Vin[i * 3] * t[0] + Vin[i * 3 + 1] * t[1]) + Vin[i * 3 + 2] * t[2];
+    xi[3] = w[0]; xi[4] = w[1]; xi[5] = w[2];
+}
+
+__device__ void pose_retract(double *T, const double *x)
+{
+    double xi[6], Tjw[16], dT[16], Tn[16];
+    se3log_d(T, xi);
+    se3exp_d(xi, Tjw);
+    se3exp_d(x, dT);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += dT[i * 4 + k] * Tjw[k * 4 + j];
+            Tn[i * 4 + j] = s;
+        }
+    se3log_d(Tn, xi);
+    se3exp_d(xi, T);
+}
+
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ k_lba_build
+// dynamic shared memory layout (doubles):
+//   P     [3*TL][n6]        P[3*il+m][6j+r] = BCinv[j][i](r, m)
+//   Q     [3*TL][n6+1]      Q[3*il+m][6k+c] = B[k][i](c, m) ; Q[3*il+m][n6] = b_i(m)
+//   Aacc  [LBA_WARPS][n_opt][27]
+//   Btmp  [LBA_WARPS][n_opt][18]
+//   errw  [LBA_WARPS]
+__global__ void __launch_bounds__(LBA_THREADS, 1)
+k_lba_build(const LbaDev d, int apply_update)
+{
+    extern __shared__ double smem[];
+    const int n6 = d.n6, No = d.n_opt, TL = d.tile;
+    double *P = smem;
+    double *Q = P + (size_t)3 * TL * n6;
+    double *Aacc = Q + (size_t)3 * TL * (n6 + 1);
+    double *Btmp = Aacc + (size_t)LBA_WARPS * No * LBA_NA;
+    double *errw = Btmp + (size_t)LBA_WARPS * No * 18;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_smem = (int)(errw + LBA_WARPS - smem);
+    for (int i = tid; i < n_smem; i += LBA_THREADS) smem[i] = 0.0;
+    __syncthreads();
+
+    const int tile_base = blockIdx.x * TL;
+    double *myA = Aacc + (size_t)wid * No * LBA_NA;
+    double *myB = Btmp + (size_t)wid * No * 18;
+    double err_w = 0.0;
+
+    for (int il = wid; il < TL; il += LBA_WARPS) {
+        const int i = tile_base + il;
+        if (i >= d.n_points) break;
+        const int o_beg = d.obs_ptr[i], o_end = d.obs_ptr[i + 1];
+        double Xi[3] = {d.points[3 * i], d.points[3 * i + 1], d.points[3 * i + 2]};
+
+        // ---- apply the previous iteration's landmark update: X_i += Cinv_b_i - sum_j CinvBt[i][j] x_j
+        if (apply_update) {
+            double cb[3] = {0, 0, 0};
+            for (int o = o_beg + lane; o < o_end; o += 32) {
+                if (d.obs_right[o]) continue;
+                const int j = d.opt_index[d.obs_frame[o]];
+                if (j < 0) continue;
+                const double *BC = d.bcinv + (size_t)o * 18;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double s = 0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s += BC[c * 3 + r] * d.x[6 * j + c];
+                    cb[r] += s;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                cb[r] = wsum(cb[r]);
+                Xi[r] += d.cinv_b[3 * i + r] - cb[r];
+            }
+            __syncwarp();
+            if (lane == 0) { d.points[3 * i] = Xi[0]; d.points[3 * i + 1] = Xi[1]; d.points[3 * i + 2] = Xi[2]; }
+        }
+
+        // ---- observations: lane per observation (chunks of 32)
+        double Cs[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+        for (int o0 = o_beg; o0 < o_end; o0 += 32) {
+            const int o = o0 + lane;
+            const bool act = o < o_end;
+            int j = -1, right = 0;
+            double Rij[6], rij[2] = {0, 0}, weight = 1.0, Qm[12];
+            if (act) {
+                const int f = d.obs_frame[o];
+                right = d.obs_right[o];
+                j = d.opt_index[f];
+                const double *T = d.poses + 16 * f;
+                double R_jw[9], t_jw[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { R_jw[r * 3] = T[r * 4]; R_jw[r * 3 + 1] = T[r * 4 + 1]; R_jw[r * 3 + 2] = T[r * 4 + 2]; t_jw[r] = T[r * 4 + 3]; }
+                double Xij[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) Xij[r] = ((R_jw[r * 3] * Xi[0] + R_jw[r * 3 + 1] * Xi[1]) + R_jw[r * 3 + 2] * Xi[2]) + t_jw[r];
+                double Rm[9], Xc[3], fx, fy, cx, cy;
+                if (right) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            Rm[r * 3 + c] = (d.R_rl[r * 3] * R_jw[c] + d.R_rl[r * 3 + 1] * R_jw[3 + c]) + d.R_rl[r * 3 + 2] * R_jw[6 + c];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) Xc[r] = ((d.R_rl[r * 3] * Xij[0] + d.R_rl[r * 3 + 1] * Xij[1]) + d.R_rl[r * 3 + 2] * Xij[2]) + d.t_rl[r];
+                    fx = d.K_r[0]; fy = d.K_r[1]; cx = d.K_r[2]; cy = d.K_r[3];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rm[k] = R_jw[k];
+                    Xc[0] = Xij[0]; Xc[1] = Xij[1]; Xc[2] = Xij[2];
+                    fx = d.K_l[0]; fy = d.K_l[1]; cx = d.K_l[2]; cy = d.K_l[3];
+                }
+                const double invz = 1.0 / Xc[2];
+                const double fxinvz = fx * invz, fyinvz = fy * invz, xinvz = Xc[0] * invz, yinvz = Xc[1] * invz;
+                const double fx_xinvz2 = fxinvz * xinvz, fy_yinvz2 = fyinvz * yinvz, xinvz_yinvz = xinvz * yinvz;
+                rij[0] = (fx * xinvz + cx) - d.obs_px[2 * o];
+                rij[1] = (fy * yinvz + cy) - d.obs_px[2 * o + 1];
+                const double absrxry = fabs(rij[0]) + fabs(rij[1]);
+                if (absrxry > d.huber) weight = d.huber / absrxry;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    Rij[c] = fxinvz * Rm[c] - fx_xinvz2 * Rm[6 + c];
+                    Rij[3 + c] = fyinvz * Rm[3 + c] - fy_yinvz2 * Rm[6 + c];
+                }
+                Cs[0] += weight * (Rij[0] * Rij[0] + Rij[3] * Rij[3]);
+                Cs[1] += weight * (Rij[0] * Rij[1] + Rij[3] * Rij[4]);
+                Cs[2] += weight * (Rij[0] * Rij[2] + Rij[3] * Rij[5]);
+                Cs[3] += weight * (Rij[1] * Rij[1] + Rij[4] * Rij[4]);
+                Cs[4] += weight * (Rij[1] * Rij[2] + Rij[4] * Rij[5]);
+                Cs[5] += weight * (Rij[2] * Rij[2] + Rij[5] * Rij[5]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) bs[c] += -(weight * (Rij[c] * rij[0] + Rij[3 + c] * rij[1]));
+                err_w += rij[0] * rij[0] + rij[1] * rij[1];
+                if (j >= 0) {
+                    if (right) {
+                        const double dp[6] = {fxinvz, 0, -fx_xinvz2, 0, fyinvz, -fy_yinvz2};
+                        double dpR[6];
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                dpR[r * 3 + c] = (dp[r * 3] * d.R_rl[c] + dp[r * 3 + 1] * d.R_rl[3 + c]) + dp[r * 3 + 2] * d.R_rl[6 + c];
+                        const double sk[9] = {0, -Xij[2], Xij[1], Xij[2], 0, -Xij[0], -Xij[1], Xij[0], 0};
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                Qm[r * 6 + c] = dpR[r * 3 + c];
+                                Qm[r * 6 + 3 + c] = ((-dpR[r * 3]) * sk[c] + (-dpR[r * 3 + 1]) * sk[3 + c]) + (-dpR[r * 3 + 2]) * sk[6 + c];
+                            }
+                    } else {
+                        Qm[0] = fxinvz; Qm[1] = 0; Qm[2] = -fx_xinvz2; Qm[3] = -fx * xinvz_yinvz; Qm[4] = fx * (1.0 + xinvz * xinvz); Qm[5] = -fx * yinvz;
+                        Qm[6] = 0; Qm[7] = fyinvz; Qm[8] = -fy_yinvz2; Qm[9] = -fy * (1.0 + yinvz * yinvz); Qm[10] = fy * xinvz_yinvz; Qm[11] = fy * xinvz;
+                    }
+                }
+            }
+            // A_j / a_j: left-camera lanes first, then right-camera lanes -- within one pass a keyframe
+            // occurs at most once per landmark, so the per-warp accumulators see no write conflict
+            // and the summation order is fixed.
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                if (act && j >= 0 && right == pass) {
+                    double wa[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) wa[k] = weight * Qm[k];
+                    double *Aj = myA + (size_t)j * LBA_NA;
+                    // upper triangle in row order (21 entries), shortcut of calc_Qij_t_Qij_weight
+                    int idx = 0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = r; c < 6; ++c, ++idx) {
+                            double v;
+                            if (r == 0) v = (c == 1) ? 0.0 : wa[0] * Qm[c];
+                            else if (r == 1) v = wa[7] * Qm[6 + c];
+                            else v = wa[r] * Qm[c] + wa[6 + r] * Qm[6 + c];
+                            Aj[idx] += v;
+                        }
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) Aj[21 + r] += -(weight * (Qm[r] * rij[0] + Qm[6 + r] * rij[1]));
+                }
+                __syncwarp();
+            }
+            // B[j][i]: last writer (highest observation index) of each optimisable keyframe
+            {
+                const int key = (act && j >= 0) ? j : -1 - lane;
+                const unsigned grp = __match_any_sync(0xffffffffu, key);
+                const bool last = act && j >= 0 && (lane == 31 - __clz(grp));
+                if (last) {
+                    double *Bj = myB + (size_t)j * 18;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) Bj[r * 3 + c] = weight * (Qm[r] * Rij[c] + Qm[6 + r] * Rij[3 + c]);
+                }
+                __syncwarp();
+            }
+        }
+        // ---- C_i, b_i across lanes; damping; inverse; Cinv_b
+        double C[9], b[3];
+        {
+            double c6[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c6[k] = wsum(Cs[k]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) b[k] = wsum(bs[k]);
+            C[0] = c6[0]; C[1] = c6[1]; C[2] = c6[2]; C[3] = c6[1]; C[4] = c6[3]; C[5] = c6[4]; C[6] = c6[2]; C[7] = c6[4]; C[8] = c6[5];
+        }
+        C[0] += d.lambda * C[0]; C[4] += d.lambda * C[4]; C[8] += d.lambda * C[8];
+        double Cinv[9];
+        ldlt3_inverse(C, Cinv);
+        double cib[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) cib[r] = (Cinv[r * 3] * b[0] + Cinv[r * 3 + 1] * b[1]) + Cinv[r * 3 + 2] * b[2];
+        if (lane == 0) { d.cinv_b[3 * i] = cib[0]; d.cinv_b[3 * i + 1] = cib[1]; d.cinv_b[3 * i + 2] = cib[2]; }
+        if (lane < 3) Q[(size_t)(3 * il + lane) * (n6 + 1) + n6] = b[lane];
+        // ---- BCinv for the left-camera observations of optimisable keyframes; stage P and Q
+        for (int o0 = o_beg; o0 < o_end; o0 += 32) {
+            const int o = o0 + lane;
+            if (o < o_end && !d.obs_right[o]) {
+                const int j = d.opt_index[d.obs_frame[o]];
+                if (j >= 0) {
+                    const double *Bj = myB + (size_t)j * 18;
+                    double BC[18];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            BC[r * 3 + c] = (Bj[r * 3] * Cinv[c] + Bj[r * 3 + 1] * Cinv[3 + c]) + Bj[r * 3 + 2] * Cinv[6 + c];
+                    double *g = d.bcinv + (size_t)o * 18;
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) g[k] = BC[k];
+#pragma unroll
+                    for (int m = 0; m < 3; ++m)
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) {
+                            P[(size_t)(3 * il + m) * n6 + 6 * j + r] = BC[r * 3 + m];
+                            Q[(size_t)(3 * il + m) * (n6 + 1) + 6 * j + r] = Bj[r * 3 + m];
+                        }
+                }
+            }
+        }
+        __syncwarp();
+        // clear the last-writer scratch for the next landmark of this warp
+        for (int k = lane; k < No * 18; k += 32) myB[k] = 0.0;
+        __syncwarp();
+    }
+    err_w = wsum(err_w);
+    if (lane == 0) errw[wid] = err_w;
+    __syncthreads();
+
+    // ---- tile contribution to the reduced camera system: out[r][c] = sum_k P[k][r] * Q[k][c]
+    const int ncol = n6 + 1;
+    double *out = d.s_part + (size_t)blockIdx.x * n6 * ncol;
+    const int K3 = 3 * TL;
+    for (int e = tid; e < n6 * ncol; e += LBA_THREADS) {
+        const int r = e / ncol, c = e - r * ncol;
+        double acc = 0.0;
+        if (c == n6 || (c / 6) >= (r / 6)) {   // upper block triangle + rhs column
+            for (int k = 0; k < K3; ++k) acc += P[(size_t)k * n6 + r] * Q[(size_t)k * ncol + c];
+        }
+        out[e] = acc;
+    }
+    for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) {
+        double acc = 0.0;
+        for (int w = 0; w < LBA_WARPS; ++w) acc += Aacc[(size_t)w * No * LBA_NA + e];
+        d.a_part[(size_t)blockIdx.x * No * LBA_NA + e] = acc;
+    }
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int w = 0; w < LBA_WARPS; ++w) acc += errw[w];
+        d.err_part[blockIdx.x] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ k_lba_solve (one CTA)
+__global__ void __launch_bounds__(LBA_THREADS, 1)
+k_lba_solve(const LbaDev d, int iter)
+{
+    extern __shared__ double smem[];
+    const int n = d.n6, No = d.n_opt, ncol = n + 1;
+    double *S = smem;                    // [n][n+1] (padded row)
+    double *rhs = S + (size_t)n * (n + 1);
+    double *temp = rhs + n;
+    double *Aj = temp + n;               // [No][27]
+    __shared__ int s_tr[6 * LBA_MAX_OPT];
+    __shared__ int s_big;
+    __shared__ double s_err;
+    const int tid = threadIdx.x;
+#define SM(i, j) S[(size_t)(i) * (n + 1) + (j)]
+
+    // fixed-order reduction of the tile partials
+    for (int e = tid; e < n * ncol; e += LBA_THREADS) {
+        double acc = 0.0;
+        for (int t = 0; t < d.n_tiles; ++t) acc += d.s_part[(size_t)t * n * ncol + e];
+        const int r = e / ncol, c = e - r * ncol;
+        if (c == n) rhs[r] = acc; else SM(r, c) = acc;
+    }
+    for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) {
+        double acc = 0.0;
+        for (int t = 0; t < d.n_tiles; ++t) acc += d.a_part[(size_t)t * No * LBA_NA + e];
+        Aj[e] = acc;
+    }
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int t = 0; t < d.n_tiles; ++t) acc += d.err_part[t];
+        s_err = acc;
+    }
+    __syncthreads();
+    // S <- blkdiag(A damped) - BCinvBt with the reference's mirror (upper blocks -> lower, diagonal
+    // blocks transposed, sparse_bundle_adjustment.cpp:501-512); rhs <- a - BCinv_b
+    for (int e = tid; e < n * n; e += LBA_THREADS) {
+        const int r = e / n, c = e - r * n;
+        const int jb = r / 6, kb = c / 6;
+        if (jb > kb) continue;                      // handle each upper-block entry once
+        const double up = SM(r, c);                 // BCinvBt[jb][kb](r%6, c%6), untouched so far
+        if (jb < kb) {
+            SM(c, r) = -up;                         // lower block = transpose
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += LBA_THREADS) {
+        const int r = e / n, c = e - r * n;
+        const int jb = r / 6, kb = c / 6;
+        if (jb < kb) SM(r, c) = -SM(r, c);
+    }
+    __syncthreads();
+    // diagonal blocks: A_j(r,c) - BCinvBt[j][j]^T(r,c)
+    for (int e = tid; e < No * 36; e += LBA_THREADS) {
+        const int jb = e / 36, rr = (e % 36) / 6, cc = e % 6;
+        if (rr > cc) continue;                      // one thread handles the (rr,cc)/(cc,rr) pair
+        const int lo = rr, hi = cc;
+        // upper index of (lo,hi) in the 21-entry packing
+        const int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+        double a_v = Aj[jb * LBA_NA + idx];
+        if (lo == hi) a_v += d.lambda * a_v;        // damping A(k,k) += lambda*A(k,k)
+        const double b_rc = SM(6 * jb + rr, 6 * jb + cc), b_cr = SM(6 * jb + cc, 6 * jb + rr);
+        SM(6 * jb + rr, 6 * jb + cc) = a_v - b_cr;  // transposed diagonal block
+        if (rr != cc) SM(6 * jb + cc, 6 * jb + rr) = a_v - b_rc;
+    }
+    for (int r = tid; r < n; r += LBA_THREADS) rhs[r] = Aj[(r / 6) * LBA_NA + 21 + (r % 6)] - rhs[r];
+    __syncthreads();
+
+    // ---- pivoted LDLT (lower storage), the algorithm of Eigen::LDLT::compute
+    for (int k = 0; k < n; ++k) {
+        if (tid < 32) {
+            double bv = -1.0;
+            int bi = k;
+            for (int i = k + tid; i < n; i += 32) {
+                const double v = fabs(SM(i, i));
+                if (v > bv) { bv = v; bi = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (tid == 0) { s_big = bi; s_tr[k] = bi; }
+        }
+        __syncthreads();
+        const int big = s_big;
+        if (big != k) {
+            const int s = n - big - 1;
+            for (int j = tid; j < k; j += LBA_THREADS) { const double t = SM(k, j); SM(k, j) = SM(big, j); SM(big, j) = t; }
+            for (int i = tid; i < s; i += LBA_THREADS) { const double t = SM(big + 1 + i, k); SM(big + 1 + i, k) = SM(big + 1 + i, big); SM(big + 1 + i, big) = t; }
+            for (int i = k + 1 + tid; i < big; i += LBA_THREADS) { const double t = SM(i, k); SM(i, k) = SM(big, i); SM(big, i) = t; }
+            if (tid == 0) { const double t = SM(k, k); SM(k, k) = SM(big, big); SM(big, big) = t; }
+            __syncthreads();
+        }
+        const int rs = n - k - 1;
+        if (k > 0) {
+            for (int j = tid; j < k; j += LBA_THREADS) temp[j] = SM(j, j) * SM(k, j);
+            __syncthreads();
+            if (tid == 0) {
+                double sacc = 0;
+                for (int j = 0; j < k; ++j) sacc += SM(k, j) * temp[j];
+                SM(k, k) -= sacc;
+            }
+            for (int i = tid; i < rs; i += LBA_THREADS) {
+                double s2 = 0;
+                for (int j = 0; j < k; ++j) s2 += SM(k + 1 + i, j) * temp[j];
+                SM(k + 1 + i, k) -= s2;
+            }
+            __syncthreads();
+        }
+        const double akk = SM(k, k);
+        if (rs > 0 && fabs(akk) > 0.0)
+            for (int i = tid; i < rs; i += LBA_THREADS) SM(k + 1 + i, k) /= akk;
+        __syncthreads();
+    }
+    // ---- solve: P b, L^-1, D^-1, L^-T, P^T  (column-oriented updates keep the row-wise order)
+    if (tid == 0) for (int k = 0; k < n; ++k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        const double yj = rhs[j];
+        for (int i = j + 1 + tid; i < n; i += LBA_THREADS) rhs[i] -= SM(i, j) * yj;
+        __syncthreads();
+    }
+    const double tol = 1.0 / 1.7976931348623157e308;
+    for (int i = tid; i < n; i += LBA_THREADS) rhs[i] = fabs(SM(i, i)) > tol ? rhs[i] / SM(i, i) : 0.0;
+    __syncthreads();
+    // backward: the reference order is, for row i descending, s -= M(j,i)*y[j] for j = i+1..n-1
+    // ascending; a column sweep would reverse that order, so rows are finished one at a time.
+    if (tid == 0) {
+        for (int i = n - 1; i >= 0; --i) {
+            double sacc = rhs[i];
+            for (int j = i + 1; j < n; ++j) sacc -= SM(j, i) * rhs[j];
+            rhs[i] = sacc;
+        }
+        for (int k = n - 1; k >= 0; --k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += LBA_THREADS) d.x[i] = rhs[i];
+    // ---- pose retraction of the optimisable keyframes + error bookkeeping
+    if (tid < No) {
+        double T[16], xj[6];
+        double *Tg = d.poses + 16 * d.opt_frame[tid];
+        for (int k = 0; k < 16; ++k) T[k] = Tg[k];
+        for (int k = 0; k < 6; ++k) xj[k] = rhs[6 * tid + k];
+        pose_retract(T, xj);
+        for (int k = 0; k < 16; ++k) Tg[k] = T[k];
+    }
+    if (tid == 0) {
+        d.avg_err[iter] = sqrt(s_err / (double)d.n_obs);
+        if (isnan(s_err)) atomicExch(d.nan_flag, 1);
+    }
+#undef SM
+}
+
+// final landmark update after the last iteration
+__global__ void __launch_bounds__(256) k_lba_update_points(const LbaDev d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_points) return;
+    double cb[3] = {0, 0, 0};
+    for (int o = d.obs_ptr[i]; o < d.obs_ptr[i + 1]; ++o) {
+        if (d.obs_right[o]) continue;
+        const int j = d.opt_index[d.obs_frame[o]];
+        if (j < 0) continue;
+        const double *BC = d.bcinv + (size_t)o * 18;
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int c = 0; c < 6; ++c) s += BC[c * 3 + r] * d.x[6 * j + c];
+            cb[r] += s;
+        }
+    }
+    for (int r = 0; r < 3; ++r) d.points[3 * i + r] += d.cinv_b[3 * i + r] - cb[r];
+}
+
+// ------------------------------------------------------------------ host
+static void inv_se3_host_d(const double *T, double *O)
+{
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) O[i * 4 + j] = T[j * 4 + i];
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += T[k * 4 + i] * T[k * 4 + 3];
+        O[i * 4 + 3] = -s;
+    }
+    O[12] = O[13] = O[14] = 0.0; O[15] = 1.0;
+}
+
+static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out,
+                            double *avg_err_out, int *success)
+{
+    if (!ctx || !p) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(p->n_frames > 0 && p->n_points >= 0 && p->n_obs >= 0 && p->max_iter >= 1, VO_ERR_INVALID_ARG, "bad sizes");
+    VO_REQUIRE(p->n_opt >= 1 && p->n_opt <= LBA_MAX_OPT, VO_ERR_INVALID_ARG, "n_opt must be in [1, 16]");
+    VO_REQUIRE(p->poses && p->opt_index && p->points && p->obs_ptr && p->obs_frame && p->obs_right && p->obs_px && poses_out && points_out,
+               VO_ERR_INVALID_ARG, "null pointer");
+    const int N = p->n_frames, No = p->n_opt, M = p->n_points, n_obs = p->n_obs, n6 = 6 * No;
+    // host-side validation of the index structure (cheap, O(n_obs)); the kernels rely on it
+    std::vector<int> opt_frame(No, -1);
+    for (int f = 0; f < N; ++f) {
+        const int j = p->opt_index[f];
+        VO_REQUIRE(j >= -1 && j < No, VO_ERR_INVALID_ARG, "opt_index out of range");
+        if (j >= 0) { VO_REQUIRE(opt_frame[j] < 0, VO_ERR_INVALID_ARG, "duplicate opt_index"); opt_frame[j] = f; }
+    }
+    for (int j = 0; j < No; ++j) VO_REQUIRE(opt_frame[j] >= 0, VO_ERR_INVALID_ARG, "opt_index does not cover [0, n_opt)");
+    VO_REQUIRE(p->obs_ptr[0] == 0 && p->obs_ptr[M] == n_obs, VO_ERR_SIZE_MISMATCH, "obs_ptr inconsistent with n_obs");
+    for (int i = 0; i < M; ++i) {
+        VO_REQUIRE(p->obs_ptr[i + 1] >= p->obs_ptr[i], VO_ERR_INVALID_ARG, "obs_ptr not monotone");
+        int last_left_opt = -1;
+        unsigned seen_l = 0, seen_r = 0;
+        for (int o = p->obs_ptr[i]; o < p->obs_ptr[i + 1]; ++o) {
+            const int f = p->obs_frame[o];
+            VO_REQUIRE(f >= 0 && f < N, VO_ERR_INVALID_ARG, "obs_frame out of range");
+            const int j = p->opt_index[f];
+            if (j < 0) continue;
+            unsigned &seen = p->obs_right[o] ? seen_r : seen_l;
+            VO_REQUIRE(!(seen & (1u << j)), VO_ERR_INVALID_ARG, "duplicate (landmark, keyframe, camera) observation");
+            seen |= 1u << j;
+            if (!p->obs_right[o]) {
+                // the reference accumulates BCinvBt[j][k] for observation order jj <= kk and then mirrors
+                // the upper block triangle: only chronological (ascending opt index) lists are well defined
+                VO_REQUIRE(j > last_left_opt, VO_ERR_INVALID_ARG, "left observations must be in ascending keyframe order");
+                last_left_opt = j;
+            }
+        }
+    }
+    VO_CUDA(cudaSetDevice(ctx->device));
+
+    // tile size from the shared-memory budget
+    const size_t budget = 200 * 1024;
+    const size_t fixed = ((size_t)LBA_WARPS * No * (LBA_NA + 18) + LBA_WARPS) * 8;
+    const size_t per_lm = (size_t)3 * (2 * n6 + 1) * 8;
+    int TL = (int)((budget - fixed) / per_lm);
+    TL = TL / LBA_WARPS * LBA_WARPS;
+    if (TL > 64) TL = 64;
+    VO_REQUIRE(TL >= LBA_WARPS, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
+    const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
+    const size_t smem_build = fixed + per_lm * TL;
+    const size_t smem_solve = ((size_t)n6 * (n6 + 1) + 2 * n6 + (size_t)No * LBA_NA) * 8;
+
+    // device scratch (one allocation, grow-only)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += a256(bytes); return o; };
+    const size_t o_poses = take((size_t)N * 128), o_opt = take((size_t)N * 4), o_optf = take((size_t)No * 4);
+    const size_t o_pts = take((size_t)M * 24), o_ptr = take((size_t)(M + 1) * 4), o_of = take((size_t)n_obs * 4);
+    const size_t o_or = take((size_t)n_obs), o_px = take((size_t)n_obs * 16);
+    const size_t in_bytes = off;
+    const size_t o_bc = take((size_t)n_obs * 144), o_cb = take((size_t)M * 24);
+    const size_t o_sp = take((size_t)n_tiles * n6 * (n6 + 1) * 8), o_ap = take((size_t)n_tiles * No * LBA_NA * 8);
+    const size_t o_ep = take((size_t)n_tiles * 8), o_x = take((size_t)n6 * 8);
+    const size_t o_ae = take((size_t)p->max_iter * 8), o_nan = take(16);
+    const size_t total = off;
+    if (total > ctx->lba_bytes) {
+        VO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_lba) cudaFree(ctx->d_lba);
+        ctx->d_lba = nullptr; ctx->lba_bytes = 0;
+        VO_CUDA(cudaMalloc(&ctx->d_lba, total));
+        ctx->lba_bytes = total;
+    }
+    int rc = vo_stage_reserve(ctx, in_bytes > (size_t)N * 128 + (size_t)M * 24 + 4096 ? in_bytes : (size_t)N * 128 + (size_t)M * 24 + 4096);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *dv = (uint8_t *)ctx->d_lba;
+    memcpy(h + o_poses, p->poses, (size_t)N * 128);
+    memcpy(h + o_opt, p->opt_index, (size_t)N * 4);
+    memcpy(h + o_optf, opt_frame.data(), (size_t)No * 4);
+    memcpy(h + o_pts, p->points, (size_t)M * 24);
+    memcpy(h + o_ptr, p->obs_ptr, (size_t)(M + 1) * 4);
+    memcpy(h + o_of, p->obs_frame, (size_t)n_obs * 4);
+    memcpy(h + o_or, p->obs_right, (size_t)n_obs);
+    memcpy(h + o_px, p->obs_px, (size_t)n_obs * 16);
+    VO_CUDA(cudaMemcpyAsync(dv, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA(cudaMemsetAsync(dv + o_bc, 0, total - o_bc, ctx->stream));
+
+    LbaDev d;
+    d.n_frames = N; d.n_opt = No; d.n_points = M; d.n_obs = n_obs; d.n_tiles = n_tiles; d.tile = TL; d.n6 = n6;
+    d.poses = (double *)(dv + o_poses); d.opt_index = (const int *)(dv + o_opt); d.opt_frame = (int *)(dv + o_optf);
+    d.points = (double *)(dv + o_pts); d.obs_ptr = (const int *)(dv + o_ptr); d.obs_frame = (const int *)(dv + o_of);
+    d.obs_right = dv + o_or; d.obs_px = (const double *)(dv + o_px);
+    d.bcinv = (double *)(dv + o_bc); d.cinv_b = (double *)(dv + o_cb); d.s_part = (double *)(dv + o_sp);
+    d.a_part = (double *)(dv + o_ap); d.err_part = (double *)(dv + o_ep); d.x = (double *)(dv + o_x);
+    d.avg_err = (double *)(dv + o_ae); d.nan_flag = (int *)(dv + o_nan);
+    memcpy(d.K_l, p->K_l, 32); memcpy(d.K_r, p->K_r, 32);
+    double T_rl[16];
+    inv_se3_host_d(p->T_lr, T_rl);   // geometry::inverseSE3(T_lr), sparse_bundle_adjustment.cpp:174
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) d.R_rl[i * 3 + j] = T_rl[i * 4 + j]; d.t_rl[i] = T_rl[i * 4 + 3]; }
+    d.huber = p->huber; d.lambda = p->lambda;
+
+    VO_CUDA(cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
+    VO_CUDA(cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    for (int it = 0; it < p->max_iter; ++it) {
+        k_lba_build<<<n_tiles, LBA_THREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
+        k_lba_solve<<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
+        ctx->launches += 2;
+    }
+    if (M > 0) { k_lba_update_points<<<vo_div_up(M, 256), 256, 0, ctx->stream>>>(d); ctx->launches++; }
+    VO_CUDA(cudaGetLastError());
+    // results: poses + points (+ avg_err, nan flag) through the pinned staging
+    const size_t r_poses = 0, r_pts = a256((size_t)N * 128), r_ae = r_pts + a256((size_t)M * 24), r_nan = r_ae + a256((size_t)p->max_iter * 8);
+    rc = vo_stage_reserve(ctx, r_nan + 256);
+    if (rc) return rc;
+    h = ctx->h_stage;
+    VO_CUDA(cudaMemcpyAsync(h + r_poses, dv + o_poses, (size_t)N * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    if (M > 0) VO_CUDA(cudaMemcpyAsync(h + r_pts, dv + o_pts, (size_t)M * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(h + r_ae, dv + o_ae, (size_t)p->max_iter * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(h + r_nan, dv + o_nan, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(poses_out, h + r_poses, (size_t)N * 128);
+    if (M > 0) memcpy(points_out, h + r_pts, (size_t)M * 24);
+    const double *ae = (const double *)(h + r_ae);
+    if (avg_err_out) memcpy(avg_err_out, ae, (size_t)p->max_iter * 8);
+    const bool nan = *(int *)(h + r_nan) != 0;
+    if (success) *success = (!nan && ae[p->max_iter - 1] <= 1.0) ? 1 : 0;
+    if (nan) { ctx->last_error = "Local BA NAN!"; return VO_ERR_NAN; }   // sparse_bundle_adjustment.cpp:624,761
+    return VO_OK;
+}

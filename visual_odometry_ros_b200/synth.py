@@ -124,3 +124,75 @@ def pose_scene(seed=1001, n=500, noise_px=0.3, outlier_frac=0.10,
     pl[idx] += sign * rng.uniform(5, 30, (n_out, 2))
     return dict(X=X.astype(np.float32), pts_l1=pl.astype(np.float32), pts_r1=pr.astype(np.float32),
                 T01_true=T01, outlier_idx=np.sort(idx))
+
+
+# ------------------------------------------------------------------ local BA problem (config 4)
+def lba_problem(seed=4004, n_kf=10, n_points=5000, n_fix=2, noise_px=0.3, point_sigma=0.05,
+                rot_sigma_deg=0.5, trans_sigma=0.05, pose_scale=10.0, stereo=True, outlier_frac=0.02):
+    """Flat sliding-window BA problem in the layout SparseBAParameters::setPosesAndPoints produces
+    (ba_solver/sparse_ba_parameters.h:292-465): reference frame = first keyframe, translations and
+    points divided by pose_scale, observations per landmark chronological, left then right.
+
+    Returns a dict of numpy arrays matching include/vo_b200.h::vo_lba_problem (+ ground truth).
+    """
+    rng = np.random.default_rng(seed)
+    # ground-truth keyframe poses T_wk (k -> ref): ~1 m forward per keyframe, gentle yaw
+    T_wk = []
+    for k in range(n_kf):
+        T = np.eye(4)
+        T[:3, :3] = so3_exp([0.0, 0.01 * k, 0.0])
+        T[:3, 3] = [0.02 * k, -0.005 * k, 1.0 * k]
+        T_wk.append(T)
+    T_kw = [np.linalg.inv(T) for T in T_wk]
+    T_lr = np.eye(4)
+    T_lr[0, 3] = BASELINE_M
+    T_rl = np.linalg.inv(T_lr)
+
+    k0 = rng.integers(0, n_kf - 1, n_points)
+    run = rng.integers(2, n_kf + 1, n_points)
+    k1 = np.minimum(k0 + run - 1, n_kf - 1)
+    Xw = np.stack([rng.uniform(-10, 10, n_points), rng.uniform(-3, 2, n_points),
+                   k1 * 1.0 + rng.uniform(5, 45, n_points)], 1)
+
+    obs_ptr = [0]
+    obs_frame, obs_right, obs_px = [], [], []
+    for i in range(n_points):
+        for k in range(k0[i], k1[i] + 1):
+            Xl = T_kw[k][:3, :3] @ Xw[i] + T_kw[k][:3, 3]
+            cams = [(0, Xl)]
+            if stereo:
+                cams.append((1, T_rl[:3, :3] @ Xl + T_rl[:3, 3]))
+            for right, Xc in cams:
+                px = np.array([FX * Xc[0] / Xc[2] + CX, FY * Xc[1] / Xc[2] + CY]) + rng.normal(0, noise_px, 2)
+                if rng.uniform() < outlier_frac:
+                    px += rng.uniform(-8, 8, 2)
+                obs_frame.append(k)
+                obs_right.append(right)
+                obs_px.append(px)
+        obs_ptr.append(len(obs_frame))
+
+    # initial values: perturbed points and optimisable poses
+    Xinit = Xw + rng.normal(0, 1, Xw.shape) * (point_sigma * Xw[:, 2:3])
+    poses = np.zeros((n_kf, 4, 4))
+    opt_index = np.full(n_kf, -1, np.int32)
+    for k in range(n_kf):
+        T = T_kw[k].copy()
+        if k >= n_fix:
+            opt_index[k] = k - n_fix
+            dR = so3_exp(rng.normal(0, np.deg2rad(rot_sigma_deg), 3))
+            T[:3, :3] = dR @ T[:3, :3]
+            T[:3, 3] += rng.normal(0, trans_sigma, 3)
+        T[:3, 3] /= pose_scale
+        poses[k] = T
+    T_lr_s = T_lr.copy()
+    T_lr_s[:3, 3] /= pose_scale
+    gt_poses = np.stack(T_kw)
+    gt_poses[:, :3, 3] /= pose_scale
+    return dict(n_frames=n_kf, n_opt=n_kf - n_fix, n_points=n_points, n_obs=len(obs_frame),
+                poses=np.ascontiguousarray(poses), opt_index=opt_index,
+                points=np.ascontiguousarray(Xinit / pose_scale), obs_ptr=np.asarray(obs_ptr, np.int32),
+                obs_frame=np.asarray(obs_frame, np.int32), obs_right=np.asarray(obs_right, np.uint8),
+                obs_px=np.ascontiguousarray(np.asarray(obs_px, np.float64)),
+                K_l=np.array([FX, FY, CX, CY]), K_r=np.array([FX, FY, CX, CY]),
+                T_lr=T_lr_s if stereo else np.eye(4), is_stereo=int(stereo), huber=0.5, lam=1e-5, max_iter=10,
+                gt_poses=gt_poses, gt_points=Xw / pose_scale)
