@@ -1,0 +1,177 @@
+// test_shim.cpp -- exercises the reference-API shim classes end to end on a GPU (run by tests/test_host_shim.py).
+#include "vo_shim.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#define CHECK(cond, msg) do { if (!(cond)) { printf("SHIM_FAIL %s:%d %s\n", __FILE__, __LINE__, msg); return 1; } } while (0)
+
+static unsigned lcg_state = 12345u;
+static float frand() { lcg_state = lcg_state * 1664525u + 1013904223u; return (float)((lcg_state >> 8) & 0xffffff) / 16777216.f; }
+
+// smooth random texture, analytically shiftable
+static float tex(float x, float y)
+{
+    float v = 0.f;
+    const float fx[6] = {0.11f, 0.23f, 0.37f, 0.05f, 0.17f, 0.29f}, fy[6] = {0.13f, 0.07f, 0.31f, 0.19f, 0.41f, 0.03f};
+    const float ph[6] = {0.3f, 1.1f, 2.0f, 4.2f, 5.5f, 0.7f};
+    for (int k = 0; k < 6; ++k) v += std::sin(fx[k] * x + fy[k] * y + ph[k]) * std::cos(fy[k] * x - fx[k] * y + 2 * ph[k]);
+    return 128.f + 20.f * v;
+}
+static void render(std::vector<unsigned char> &buf, int w, int h, float dx, float dy)
+{
+    buf.resize((size_t)w * h);
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+        float v = tex(x - dx, y - dy);
+        buf[(size_t)y * w + x] = (unsigned char)std::fmin(255.f, std::fmax(0.f, std::floor(v + 0.5f)));
+    }
+}
+
+template <class F> static bool throws_with(F f, const char *needle)
+{
+    try { f(); } catch (const std::runtime_error &e) { return std::string(e.what()).find(needle) != std::string::npos; }
+    return false;
+}
+
+int main()
+{
+    const int W = 640, H = 200;
+    std::vector<unsigned char> b0, b1;
+    const float sx = 2.4f, sy = -1.3f;
+    render(b0, W, H, 0, 0);
+    render(b1, W, H, sx, sy);
+    cv::Mat img0(H, W, b0.data()), img1(H, W, b1.data());
+    PixelVec pts0;
+    for (int y = 30; y < H - 30; y += 14) for (int x = 30; x < W - 30; x += 20) pts0.emplace_back(x + frand(), y + frand());
+    const size_t n = pts0.size();
+
+    // ---- FeatureTracker
+    FeatureTracker ft;
+    PixelVec p1; MaskVec m;
+    ft.track(img0, img1, pts0, 21, 3, 30.f, p1, m);
+    CHECK(p1.size() == n && m.size() == n, "track sizes");
+    size_t good = 0;
+    for (size_t i = 0; i < n; ++i) if (m[i] && std::fabs(p1[i].x - pts0[i].x - sx) < 0.1f && std::fabs(p1[i].y - pts0[i].y - sy) < 0.1f) ++good;
+    CHECK(good > n * 9 / 10, "track accuracy");
+    PixelVec p2 = pts0; MaskVec m2(n, true); m2[3] = false;
+    ft.trackWithPrior(img0, img1, pts0, 21, 3, 30.f, p2, m2);
+    CHECK(!m2[3], "pre-existing false mask entries must survive (Appendix B #7)");
+    PixelVec p3; MaskVec m3;
+    ft.trackBidirection(img0, img1, pts0, 21, 3, 30.f, 0.5f, p3, m3);
+    PixelVec p4 = p1; MaskVec m4;
+    ft.trackBidirectionWithPrior(img0, img1, pts0, 21, 3, 30.f, 0.5f, p4, m4);
+    size_t c3 = 0, c4 = 0;
+    for (size_t i = 0; i < n; ++i) { c3 += m3[i]; c4 += m4[i]; }
+    CHECK(c3 > n * 8 / 10 && c4 > n * 8 / 10, "bidirectional survivors");
+    std::vector<float> scale(n, 1.0f);
+    PixelVec p5 = p1; MaskVec m5;
+    ft.trackWithScale(img0, cv::Mat(), cv::Mat(), img1, pts0, scale, p5, m5);
+    size_t c5 = 0;
+    for (size_t i = 0; i < n; ++i) c5 += (m5[i] && std::fabs(p5[i].x - pts0[i].x - sx) < 0.15f);
+    CHECK(c5 > n * 8 / 10, "trackWithScale accuracy");
+    PixelVec bad(3);
+    CHECK(throws_with([&] { MaskVec mm; ft.trackWithScale(img0, cv::Mat(), cv::Mat(), img1, pts0, scale, bad, mm); }, "pts_track.size() != pts0.size()"),
+          "trackWithScale size error text");
+
+    // ---- MotionEstimator
+    const float fx = 718.856f, fy = 718.856f, cx = 607.19f, cy = 185.21f, base = 0.537f;
+    PointVec X; PixelVec pl, pr;
+    const float tz = 0.8f, tx = 0.03f;
+    for (int i = 0; i < 400; ++i) {
+        Point P; P(0) = -10.f + 20.f * frand(); P(1) = -3.f + 5.f * frand(); P(2) = 5.f + 40.f * frand();
+        X.push_back(P);
+        const float xl = P(0) - tx, yl = P(1), zl = P(2) - tz;      // T10 = translate(-t01)
+        pl.emplace_back(fx * xl / zl + cx + 0.2f * (frand() - 0.5f), fy * yl / zl + cy + 0.2f * (frand() - 0.5f));
+        pr.emplace_back(fx * (xl - base) / zl + cx + 0.2f * (frand() - 0.5f), fy * yl / zl + cy + 0.2f * (frand() - 0.5f));
+    }
+    PoseSE3 Tlr = PoseSE3::Identity(); Tlr(0, 3) = base;
+    MotionEstimator me(true, Tlr);
+    PoseSE3 T01 = PoseSE3::Identity(); MaskVec mi;
+    auto cam = std::make_shared<Camera>(fx, fy, cx, cy);
+    CameraConstPtr camc = cam;
+    CHECK(me.poseOnlyBundleAdjustment_Stereo(X, pl, pr, camc, camc, Tlr, 3.0f, T01, mi), "stereo pose success");
+    CHECK(std::fabs(T01(2, 3) - tz) < 5e-3f && std::fabs(T01(0, 3) - tx) < 5e-3f, "stereo pose value");
+    PoseSE3 T01b = PoseSE3::Identity(); MaskVec mib;
+    me.poseOnlyBundleAdjustment_Stereo(X, pl, pr, fx, fy, cx, cy, fx, fy, cx, cy, Tlr, 3.0f, T01b, mib);
+    CHECK(std::fabs(T01b(2, 3) - T01(2, 3)) < 1e-6f, "standalone overload agrees");
+    Rot3 R = Rot3::Identity(); Pos3 t; MaskVec mm;
+    CHECK(me.poseOnlyBundleAdjustment(X, pl, camc, 5, R, t, mm), "mono pose success");
+    CHECK(std::fabs(t(2) - tz) < 2e-2f, "mono pose value");
+    MotionEstimator me_mono(false);
+    CHECK(throws_with([&] { PoseSE3 T = PoseSE3::Identity(); MaskVec q; me_mono.poseOnlyBundleAdjustment_Stereo(X, pl, pr, camc, camc, Tlr, 3.f, T, q); },
+                      "is_stereo_mode_ == false"), "mode error text");
+    PixelVec shortv(5);
+    CHECK(throws_with([&] { PoseSE3 T = PoseSE3::Identity(); MaskVec q; me.poseOnlyBundleAdjustment_Stereo(X, shortv, pr, camc, camc, Tlr, 3.f, T, q); },
+                      "X.size() != pts_l1.size()"), "size error text");
+
+    // ---- triangulateDLT
+    Rot3 R10 = Rot3::Identity(); Pos3 t10; t10(0) = -base;
+    PixelVec q0, q1;
+    for (int i = 0; i < 100; ++i) { q0.emplace_back(fx * X[i](0) / X[i](2) + cx, fy * X[i](1) / X[i](2) + cy); q1.emplace_back(fx * (X[i](0) - base) / X[i](2) + cx, fy * X[i](1) / X[i](2) + cy); }
+    PointVec X0, X1;
+    mapping::triangulateDLT(q0, q1, R10, t10, camc, X0, X1);
+    double worst = 0;
+    for (int i = 0; i < 100; ++i) worst = std::fmax(worst, std::fabs(X0[i](2) - X[i](2)) / X[i](2));
+    CHECK(worst < 2e-3, "triangulation accuracy");
+    Point a0, a1;
+    mapping::triangulateDLT(q0[7], q1[7], R10, t10, camc, camc, a0, a1);
+    CHECK(a0(0) == X0[7](0) && a0(2) == X0[7](2), "scalar and vector triangulation agree bit for bit");
+
+    // ---- DepthFilter
+    DepthFilter df;
+    double xu, cu;
+    df.updateNormalDistribution(0.2, 1e-3, 0.25, 2e-3, xu, cu);
+    CHECK(std::fabs(cu - (1e-3 * 2e-3) / 3e-3) < 1e-18 && std::fabs(xu - (0.2 * 2e-3 + 0.25 * 1e-3) / 3e-3) < 1e-15, "depth filter");
+
+    // ---- local BA through the reference-shaped classes
+    const int NKF = 5;
+    std::vector<FramePtr> lefts, rights;
+    for (int k = 0; k < NKF; ++k) {
+        auto l = std::make_shared<Frame>(false), r = std::make_shared<Frame>(true);
+        PoseSE3 Twc = PoseSE3::Identity(); Twc(2, 3) = 1.0f * k; Twc(0, 3) = 0.01f * k;
+        if (k >= 2) { Twc(2, 3) += 0.03f * (frand() - 0.5f); Twc(0, 3) += 0.03f * (frand() - 0.5f); }   // perturbed
+        l->setPose(Twc);
+        PoseSE3 Twr = Twc; Twr(0, 3) += base;
+        r->setPose(Twr); r->setLeftFramePtr(l);
+        lefts.push_back(l); rights.push_back(r);
+    }
+    std::vector<LandmarkPtr> lms;
+    for (int i = 0; i < 120; ++i) {
+        auto lm = std::make_shared<Landmark>();
+        Point Xw; Xw(0) = -8.f + 16.f * frand(); Xw(1) = -2.f + 4.f * frand(); Xw(2) = 8.f + 30.f * frand();
+        for (int k = 0; k < NKF; ++k) {
+            const float xl = Xw(0) - 0.01f * k, yl = Xw(1), zl = Xw(2) - 1.0f * k;       // true poses
+            lm->addObservationOnKeyframe(Pixel(fx * xl / zl + cx, fy * yl / zl + cy), lefts[k]);
+            lm->addObservationOnKeyframe(Pixel(fx * (xl - base) / zl + cx, fy * yl / zl + cy), rights[k]);
+            lefts[k]->addRelatedLandmark(lm);
+        }
+        Point Xn = Xw; Xn(2) *= 1.f + 0.03f * (frand() - 0.5f);
+        lm->set3DPoint(Xn);
+        lms.push_back(lm);
+    }
+    FramePtrVec frames_ba;
+    for (auto &l : lefts) frames_ba.push_back(l);
+    for (auto &r : rights) frames_ba.push_back(r);
+    std::vector<int> idx_fix = {0, 1}, idx_opt;
+    for (int j = 2; j < (int)frames_ba.size(); ++j) if (!frames_ba[j]->isRightImage()) idx_opt.push_back(j);   // motion_estimator.cpp:1285-1293
+    auto params = std::make_shared<SparseBAParameters>(true, Tlr);
+    params->setPosesAndPoints(frames_ba, idx_fix, idx_opt);
+    CHECK(params->getNumOfOptimizeFrames() == NKF - 2 && params->getNumOfOptimizeLandmarks() == 120 && params->getNumOfObservations() == 120 * NKF * 2, "BA packing");
+    SparseBundleAdjustmentSolver solver(true);
+    solver.setStereoCameras(cam, cam);
+    solver.setBAParameters(params);
+    solver.setHuberThreshold(0.5);
+    const PoseSE3 before = lefts[3]->getPose();
+    solver.solveForFiniteIterations(10);
+    CHECK(lms[0]->isBundled(), "landmarks bundled");
+    CHECK(std::fabs(lefts[3]->getPose()(2, 3) - 3.0f) <= std::fabs(before(2, 3) - 3.0f) + 1e-3f, "BA did not diverge");
+    CHECK(lefts[0]->getPose()(2, 3) == 0.0f, "fixed keyframe untouched");
+    SparseBundleAdjustmentSolver mono_solver(false);
+    CHECK(throws_with([&] { mono_solver.setStereoCameras(cam, cam); }, "'is_stereo' should be set to 'true'"), "BA mode error text");
+
+    vo_b200::release_shared_context();
+    printf("SHIM_OK features=%zu tracked=%zu\n", n, good);
+    return 0;
+}
