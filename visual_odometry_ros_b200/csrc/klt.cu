@@ -17,6 +17,7 @@
 #include "vo_internal.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 #define W_BITS 14
 
@@ -55,6 +56,37 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, in
     iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, omb), (float)(1 << W_BITS)));
     iw10 = __float2int_rn(__fmul_rn(__fmul_rn(oma, b), (float)(1 << W_BITS)));
     iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+}
+
+// Result write-back + fused FeatureTracker post-filters (one lane per feature).
+__device__ __forceinline__ void klt_epilogue(const KltArgs &a, size_t gi, const SlotDesc &S0, float2 stored, int status, float errv)
+{
+    {
+        a.pts1[gi] = stored;
+        if (!status) errv = 0.f;
+        if (a.status) a.status[gi] = (uint8_t)status;
+        if (a.err) a.err[gi] = errv;
+        // ---- fused FeatureTracker post-filters
+        const KltPost &P = a.post;
+        if (P.mode == 1) {          // track(): feature_tracker.cpp:33-34
+            P.mask[gi] = P.mask[gi] && status && errv <= P.thres_err;
+        } else if (P.mode == 2) {   // trackWithPrior(): feature_tracker.cpp:191-197
+            const float w = (float)S0.lv[0].w, h = (float)S0.lv[0].h;
+            P.mask[gi] = P.mask[gi] && status && stored.x > 0.f && stored.x < w && stored.y > 0.f && stored.y < h &&
+                         errv <= P.thres_err;
+        } else if (P.mode == 4) {   // backward pass of trackBidirection(+WithPrior): :74-83 / :130-149
+            const float w = (float)S0.lv[0].w, h = (float)S0.lv[0].h;
+            const float2 ref = reinterpret_cast<const float2 *>(P.ref_pts)[gi];
+            const float2 fw = reinterpret_cast<const float2 *>(P.fwd_pts)[gi];
+            const float ddx = __fsub_rn(stored.x, ref.x), ddy = __fsub_rn(stored.y, ref.y);
+            const float dist2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+            const float bd = (float)P.border;
+            const bool inimg = fw.x > bd && fw.x < w - bd && fw.y > bd && fw.y < h - bd;
+            const bool fs = P.fwd_status[gi] != 0;
+            P.mask[gi] = P.mask[gi] && inimg && fs && status && P.fwd_err[gi] <= P.thres_err && errv <= P.thres_err &&
+                         dist2 <= P.thres_bi2;
+        }
+    }
 }
 
 template <int NPX>
@@ -210,32 +242,319 @@ k_klt(const KltArgs a)
         }
     }
 
-    if (lane == 0) {
-        a.pts1[gi] = stored;
-        if (!status) errv = 0.f;
-        if (a.status) a.status[gi] = (uint8_t)status;
-        if (a.err) a.err[gi] = errv;
-        // ---- fused FeatureTracker post-filters
-        const KltPost &P = a.post;
-        if (P.mode == 1) {          // track(): feature_tracker.cpp:33-34
-            P.mask[gi] = P.mask[gi] && status && errv <= P.thres_err;
-        } else if (P.mode == 2) {   // trackWithPrior(): feature_tracker.cpp:191-197
-            const float w = (float)S0.lv[0].w, h = (float)S0.lv[0].h;
-            P.mask[gi] = P.mask[gi] && status && stored.x > 0.f && stored.x < w && stored.y > 0.f && stored.y < h &&
-                         errv <= P.thres_err;
-        } else if (P.mode == 4) {   // backward pass of trackBidirection(+WithPrior): :74-83 / :130-149
-            const float w = (float)S0.lv[0].w, h = (float)S0.lv[0].h;
-            const float2 ref = reinterpret_cast<const float2 *>(P.ref_pts)[gi];
-            const float2 fw = reinterpret_cast<const float2 *>(P.fwd_pts)[gi];
-            const float ddx = __fsub_rn(stored.x, ref.x), ddy = __fsub_rn(stored.y, ref.y);
-            const float dist2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-            const float bd = (float)P.border;
-            const bool inimg = fw.x > bd && fw.x < w - bd && fw.y > bd && fw.y < h - bd;
-            const bool fs = P.fwd_status[gi] != 0;
-            P.mask[gi] = P.mask[gi] && inimg && fs && status && P.fwd_err[gi] <= P.thres_err && errv <= P.thres_err &&
-                         dist2 <= P.thres_bi2;
-        }
+    if (lane == 0) klt_epilogue(a, gi, S0, stored, status, errv);
+}
+
+
+// =======================================================================================
+// v2: shared-memory staged windows + dp2a sampling (WIN = 13 / 15 / 21).
+//
+// ncu on v1 (profiles/r1_v1_*) showed the kernel bound by L1 wavefronts: 229 M scattered byte
+// gathers per launch, 3.7 sectors each, 95 % L1 hits, long-scoreboard stalls.  v2 touches global
+// memory once per (feature, level): the template patch (u8), its Scharr patch (short2) and a
+// (WIN+1+2*MJ)^2 search region of the next image are brought in with coalesced, aligned 32-bit
+// word loads (lanes sweep rows), staged in per-warp shared memory with ODD word pitches so the
+// row-segment reads of the iterations are (nearly) bank-conflict free.  Each lane then owns
+// RPL horizontal runs of RL pixels; a run reads 3 words from each of 2 rows, realigns them with
+// funnel shifts and evaluates the fixed-point bilinear sample of a pixel with two dp2a
+// (s16 weight pair x u8 pixel pair) -- bit-identical to the scalar formula.  The search region
+// is re-staged only if the window drifts outside its margin.
+// =======================================================================================
+#define MJ 5    // search-region margin (pixels) on every side
+
+template <int WIN> struct Klt2Cfg {
+    static constexpr int W1 = WIN + 1;
+    static constexpr int SEG = (WIN > 16) ? 3 : 2;
+    static constexpr int RL = (WIN + SEG - 1) / SEG;              // pixels per run
+    static constexpr int NRUN = WIN * SEG;
+    static constexpr int RPL = (NRUN + 31) / 32;                  // runs per lane
+    static constexpr int IPW = ((W1 + 3 + 3) / 4) | 1;            // template patch pitch (words, odd)
+    static constexpr int DPW = W1 | 1;                            // derivative patch pitch (words, odd)
+    static constexpr int JR = W1 + 2 * MJ;                        // search-region rows
+    static constexpr int JPW = ((W1 + 2 * MJ + 3 + 3) / 4) | 1;   // search-region pitch (words, odd)
+    static constexpr int I_WORDS = W1 * IPW, D_WORDS = W1 * DPW, J_WORDS = JR * JPW;
+    static constexpr int WARP_WORDS = I_WORDS + D_WORDS + J_WORDS + 4;   // +4: load_run may touch one word past a row
+    static constexpr int NPX = RPL * RL;                          // template registers per lane
+};
+
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Coalesced copy of a ROWS x PW-word rectangle (aligned 32-bit words) from global to shared.
+template <int ROWS, int PW>
+__device__ __forceinline__ void stage_words(uint32_t *dst, const uint8_t *src_aligned, int pitch_bytes, int lane)
+{
+    constexpr int N = ROWS * PW;
+    constexpr int T = (N + 31) / 32;
+    uint32_t v[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int idx = lane + 32 * t;
+        const int r = idx / PW, c = idx - r * PW;
+        v[t] = (idx < N) ? __ldg(reinterpret_cast<const uint32_t *>(src_aligned + (ptrdiff_t)r * pitch_bytes) + c) : 0u;
     }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < N) dst[idx] = v[t];
+    }
+}
+
+// 8-bit sample stream of one run: E holds bytes e0.., O the same shifted by one byte.
+template <int RL>
+__device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_t E[3], uint32_t O[3])
+{
+    const uint32_t *p = row + (byte0 >> 2);
+    const int sh = (byte0 & 3) * 8;
+    const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+    E[0] = __funnelshift_r(w0, w1, sh);
+    E[1] = __funnelshift_r(w1, w2, sh);
+    E[2] = w2 >> sh;
+    O[0] = __funnelshift_r(E[0], E[1], 8);
+    O[1] = __funnelshift_r(E[1], E[2], 8);
+    O[2] = E[2] >> 8;
+}
+
+// bilinear fixed-point sample of pixel k of a run: rows A (weights wA = {iw00,iw01}) and B ({iw10,iw11})
+#define KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, rnd)                                                   \
+    (((k) & 3) == 0 ? dp2a_lo_su(wB, EB[(k) >> 2], dp2a_lo_su(wA, EA[(k) >> 2], rnd))                 \
+   : ((k) & 3) == 1 ? dp2a_lo_su(wB, OB[(k) >> 2], dp2a_lo_su(wA, OA[(k) >> 2], rnd))                 \
+   : ((k) & 3) == 2 ? dp2a_hi_su(wB, EB[(k) >> 2], dp2a_hi_su(wA, EA[(k) >> 2], rnd))                 \
+                    : dp2a_hi_su(wB, OB[(k) >> 2], dp2a_hi_su(wA, OA[(k) >> 2], rnd)))
+
+template <int WIN>
+__global__ void __launch_bounds__(128)
+k_klt2(const KltArgs a)
+{
+    using C = Klt2Cfg<WIN>;
+    extern __shared__ uint32_t smem_u32[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int pair = blockIdx.y;
+    if (f >= a.n) return;
+    uint32_t *Ibuf = smem_u32 + wib * C::WARP_WORDS;
+    uint32_t *Dbuf = Ibuf + C::I_WORDS;
+    uint32_t *Jbuf = Dbuf + C::D_WORDS;
+    const size_t gi = (size_t)pair * a.n + f;
+    const SlotDesc &S0 = a.slots[a.s0.id[pair]];
+    const SlotDesc &S1 = a.slots[a.s1.id[pair]];
+    const float halfWin = (float)(WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+
+    // run geometry of this lane (level independent)
+    int run_row[C::RPL], run_x0[C::RPL], run_len[C::RPL];
+#pragma unroll
+    for (int q = 0; q < C::RPL; ++q) {
+        const int id = lane + 32 * q;
+        const int r = id / C::SEG, sgm = id - r * C::SEG;
+        run_row[q] = r;
+        run_x0[q] = sgm * C::RL;
+        int len = WIN - sgm * C::RL;
+        len = len > C::RL ? C::RL : len;
+        run_len[q] = (id < C::NRUN) ? len : 0;
+    }
+
+    const float2 p0 = a.pts0[gi];
+    float2 stored = (a.flags & VO_KLT_USE_INITIAL_FLOW) ? a.pts1[gi] : p0;
+    int status = 1;
+    float errv = 0.f;
+
+    for (int level = a.top_level; level >= 0; --level) {
+        const LevelDesc I = S0.lv[level];
+        const LevelDesc J = S1.lv[level];
+        const float sc = 1.f / (float)(1 << level);
+        float prevx = __fmul_rn(p0.x, sc), prevy = __fmul_rn(p0.y, sc);
+        if (level == a.top_level) {
+            if (a.flags & VO_KLT_USE_INITIAL_FLOW) { stored.x = __fmul_rn(stored.x, sc); stored.y = __fmul_rn(stored.y, sc); }
+            else { stored.x = prevx; stored.y = prevy; }
+        } else {
+            stored.x = __fmul_rn(stored.x, 2.f); stored.y = __fmul_rn(stored.y, 2.f);
+        }
+        float nextx = stored.x, nexty = stored.y;
+        prevx = __fsub_rn(prevx, halfWin); prevy = __fsub_rn(prevy, halfWin);
+        const int ipx = __float2int_rd(prevx), ipy = __float2int_rd(prevy);
+        if (ipx < -WIN || ipx >= I.w || ipy < -WIN || ipy >= I.h) {
+            if (level == 0) { status = 0; errv = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(__fsub_rn(prevx, (float)ipx), __fsub_rn(prevy, (float)ipy), iw00, iw01, iw10, iw11);
+
+        // ---- stage template patch, derivative patch and the initial search region (all loads first)
+        nextx = __fsub_rn(nextx, halfWin); nexty = __fsub_rn(nexty, halfWin);
+        int jx0, jy0;   // origin (pixel coords) of the staged search region; jx0 is 4-aligned
+        {
+            const int iax = ipx & ~3;
+            stage_words<C::W1, C::IPW>(Ibuf, I.img + (ptrdiff_t)ipy * I.pitch + iax, I.pitch, lane);
+            stage_words<C::W1, C::DPW>(Dbuf, reinterpret_cast<const uint8_t *>(I.deriv + (ptrdiff_t)ipy * I.pitch + ipx), I.pitch * 4, lane);
+            int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
+            // clamp the staging origin so that it stays inside the padded plane even for a wild start
+            inx = max(-WIN, min(inx, J.w - 1)); iny = max(-WIN, min(iny, J.h - 1));
+            jx0 = (inx - MJ) & ~3; jy0 = iny - MJ;
+            stage_words<C::JR, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+        }
+        __syncwarp();
+
+        // ---- template: I (5 frac bits), Ix, Iy in registers; exact A sums
+        int Iv[C::NPX], Ix[C::NPX], Iy[C::NPX];
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+        {
+            const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
+            const int offI = ipx & 3;
+#pragma unroll
+            for (int q = 0; q < C::RPL; ++q) {
+                uint32_t EA[3], OA[3], EB[3], OB[3];
+                const int r = run_len[q] ? run_row[q] : 0;
+                load_run<C::RL>(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
+                load_run<C::RL>(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
+                const uint32_t *d0 = Dbuf + r * C::DPW + run_x0[q];
+                const uint32_t *d1 = d0 + C::DPW;
+                uint32_t da = d0[0], db = d1[0];
+#pragma unroll
+                for (int k = 0; k < C::RL; ++k) {
+                    const uint32_t da1 = d0[k + 1], db1 = d1[k + 1];
+                    const int iv = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, 1 << (W_BITS - 5 - 1)) >> (W_BITS - 5);
+                    int ix = ((int)(short)(da & 0xffff) * iw00 + (int)(short)(da1 & 0xffff) * iw01 + (int)(short)(db & 0xffff) * iw10 +
+                              (int)(short)(db1 & 0xffff) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    int iy = (((int)da >> 16) * iw00 + ((int)da1 >> 16) * iw01 + ((int)db >> 16) * iw10 + ((int)db1 >> 16) * iw11 +
+                              (1 << (W_BITS - 1))) >> W_BITS;
+                    const bool ok = k < run_len[q];
+                    if (!ok) { ix = 0; iy = 0; }
+                    Iv[q * C::RL + k] = ok ? iv : 0;
+                    Ix[q * C::RL + k] = ix; Iy[q * C::RL + k] = iy;
+                    sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+                    da = da1; db = db1;
+                }
+            }
+        }
+        const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
+        const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
+        const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dif = __fsub_rn(A11, A22);
+        const float minEig = __fdiv_rn(
+            __fsub_rn(__fadd_rn(A22, A11),
+                      __fsqrt_rn(__fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
+            (float)(2 * WIN * WIN));
+        if (a.counters && lane == 0) atomicAdd(a.counters + 2 * level, 1ull);
+        if (minEig < a.min_eig || D < FLT_EPSILON) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+
+        float pdx = 0.f, pdy = 0.f;
+        int j = 0;
+        for (; j < a.max_count; ++j) {
+            const float qx = nextx, qy = nexty;
+            const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
+            if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            int offx = inx - jx0, offy = iny - jy0;
+            if (offx < 0 || offx + C::W1 > 4 * C::JPW || offy < 0 || offy + C::W1 > C::JR) {
+                __syncwarp();
+                jx0 = (inx - MJ) & ~3; jy0 = iny - MJ;
+                stage_words<C::JR, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+                __syncwarp();
+                offx = inx - jx0; offy = iny - jy0;
+            }
+            bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), iw00, iw01, iw10, iw11);
+            const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
+            int sb1 = 0, sb2 = 0;
+#pragma unroll
+            for (int q = 0; q < C::RPL; ++q) {
+                uint32_t EA[3], OA[3], EB[3], OB[3];
+                const int r = run_len[q] ? run_row[q] : 0;
+                const uint32_t *rowA = Jbuf + (offy + r) * C::JPW;
+                load_run<C::RL>(rowA, offx + run_x0[q], EA, OA);
+                load_run<C::RL>(rowA + C::JPW, offx + run_x0[q], EB, OB);
+#pragma unroll
+                for (int k = 0; k < C::RL; ++k) {
+                    const int diff = (KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, 1 << (W_BITS - 5 - 1)) >> (W_BITS - 5)) - Iv[q * C::RL + k];
+                    sb1 += diff * Ix[q * C::RL + k];     // Ix = Iy = 0 beyond the run / on idle lanes
+                    sb2 += diff * Iy[q * C::RL + k];
+                }
+            }
+            const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
+            const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nextx = __fadd_rn(nextx, dx); nexty = __fadd_rn(nexty, dy);
+            stored.x = __fadd_rn(nextx, halfWin); stored.y = __fadd_rn(nexty, halfWin);
+            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= a.eps2) { ++j; break; }
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                stored.x = __fsub_rn(stored.x, __fmul_rn(dx, 0.5f));
+                stored.y = __fsub_rn(stored.y, __fmul_rn(dy, 0.5f));
+                ++j;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (a.counters && lane == 0) atomicAdd(a.counters + 2 * level + 1, (unsigned long long)j);
+
+        if (status && level == 0) {
+            const float npx = __fsub_rn(stored.x, halfWin), npy = __fsub_rn(stored.y, halfWin);
+            const int inx = __float2int_rd(npx), iny = __float2int_rd(npy);
+            if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
+                status = 0;
+            } else {
+                int offx = inx - jx0, offy = iny - jy0;
+                if (offx < 0 || offx + C::W1 > 4 * C::JPW || offy < 0 || offy + C::W1 > C::JR) {
+                    __syncwarp();
+                    jx0 = (inx - MJ) & ~3; jy0 = iny - MJ;
+                    stage_words<C::JR, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+                    __syncwarp();
+                    offx = inx - jx0; offy = iny - jy0;
+                }
+                bilinear_weights(__fsub_rn(npx, (float)inx), __fsub_rn(npy, (float)iny), iw00, iw01, iw10, iw11);
+                const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
+                int sabs = 0;
+#pragma unroll
+                for (int q = 0; q < C::RPL; ++q) {
+                    uint32_t EA[3], OA[3], EB[3], OB[3];
+                    const int r = run_len[q] ? run_row[q] : 0;
+                    const uint32_t *rowA = Jbuf + (offy + r) * C::JPW;
+                    load_run<C::RL>(rowA, offx + run_x0[q], EA, OA);
+                    load_run<C::RL>(rowA + C::JPW, offx + run_x0[q], EB, OB);
+#pragma unroll
+                    for (int k = 0; k < C::RL; ++k) {
+                        const int diff = (KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, 1 << (W_BITS - 5 - 1)) >> (W_BITS - 5)) - Iv[q * C::RL + k];
+                        sabs += (k < run_len[q]) ? abs(diff) : 0;
+                    }
+                }
+                const int tot = __reduce_add_sync(0xffffffffu, sabs);
+                errv = __fdiv_rn(__fmul_rn((float)tot, 1.f), (float)(32 * WIN * WIN));
+            }
+        }
+        __syncwarp();   // the next level overwrites the staging buffers
+    }
+
+    if (lane == 0) klt_epilogue(a, gi, S0, stored, status, errv);
+}
+
+template <int WIN>
+static cudaError_t launch_klt2(const KltArgs &a, dim3 grd, cudaStream_t st)
+{
+    const size_t smem = (size_t)4 * Klt2Cfg<WIN>::WARP_WORDS * 4;
+    static bool attr_done = false;
+    if (!attr_done && smem > 48 * 1024) {
+        cudaFuncSetAttribute(k_klt2<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    k_klt2<WIN><<<grd, 128, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1, const float *pts0_d,
@@ -286,7 +605,13 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
             a.post = KltPost{};
         }
         dim3 grd(vo_div_up(n, 4), nb);
-        if (npx <= 6) k_klt<6><<<grd, 128, 0, ctx->stream>>>(a);
+        static const bool force_v1 = getenv("VO_KLT_V1") != nullptr;   // A/B switch for profiling
+        if (!force_v1 && (win == 21 || win == 15 || win == 13)) {
+            cudaError_t e = win == 21 ? launch_klt2<21>(a, grd, ctx->stream)
+                          : win == 15 ? launch_klt2<15>(a, grd, ctx->stream) : launch_klt2<13>(a, grd, ctx->stream);
+            if (e != cudaSuccess) { ctx->last_error = std::string("k_klt2: ") + cudaGetErrorString(e); return VO_ERR_CUDA; }
+        }
+        else if (npx <= 6) k_klt<6><<<grd, 128, 0, ctx->stream>>>(a);
         else if (npx <= 8) k_klt<8><<<grd, 128, 0, ctx->stream>>>(a);
         else if (npx <= 10) k_klt<10><<<grd, 128, 0, ctx->stream>>>(a);
         else if (npx <= 14) k_klt<14><<<grd, 128, 0, ctx->stream>>>(a);
