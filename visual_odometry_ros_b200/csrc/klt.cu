@@ -20,6 +20,9 @@
 #include <cstdlib>
 
 #define W_BITS 14
+#ifndef KLT2_MIN_BLOCKS
+#define KLT2_MIN_BLOCKS 5
+#endif
 
 struct KltArgs {
     const SlotDesc *slots;
@@ -260,7 +263,7 @@ k_klt(const KltArgs a)
 // (s16 weight pair x u8 pixel pair) -- bit-identical to the scalar formula.  The search region
 // is re-staged only if the window drifts outside its margin.
 // =======================================================================================
-#define MJ 5    // search-region margin (pixels) on every side
+#define MJ 5    // minimum search-region margin (pixels) on every side
 
 template <int WIN> struct Klt2Cfg {
     static constexpr int W1 = WIN + 1;
@@ -268,11 +271,17 @@ template <int WIN> struct Klt2Cfg {
     static constexpr int RL = (WIN + SEG - 1) / SEG;              // pixels per run
     static constexpr int NRUN = WIN * SEG;
     static constexpr int RPL = (NRUN + 31) / 32;                  // runs per lane
-    static constexpr int IPW = ((W1 + 3 + 3) / 4) | 1;            // template patch pitch (words, odd)
-    static constexpr int DPW = W1 | 1;                            // derivative patch pitch (words, odd)
+    static constexpr bool FULL = (WIN % SEG) == 0;                // every run has RL pixels
+    // staging rectangles are fetched as aligned 128-bit words (16 B): x origins are rounded down to 16 B
+    static constexpr int I_V4 = (15 + W1 + 15) / 16;              // uint4 per template-patch row
+    static constexpr int IPW = I_V4 * 4;                          // pitch in 32-bit words
+    static constexpr int D_V4 = (3 + W1 + 3) / 4;                 // short2 elements: origin rounded down to 4 elements
+    static constexpr int DPW = D_V4 * 4;
     static constexpr int JR = W1 + 2 * MJ;                        // search-region rows
-    static constexpr int JPW = ((W1 + 2 * MJ + 3 + 3) / 4) | 1;   // search-region pitch (words, odd)
-    static constexpr int I_WORDS = W1 * IPW, D_WORDS = W1 * DPW, J_WORDS = JR * JPW;
+    static constexpr int J_V4 = (15 + W1 + 2 * MJ + 15) / 16;
+    static constexpr int JBYTES = J_V4 * 16;                      // valid bytes per staged row
+    static constexpr int JPW = (J_V4 * 4) | 1;                    // ODD pitch (stored with 32-bit stores): conflict-light row reads
+    static constexpr int I_WORDS = W1 * IPW, D_WORDS = W1 * DPW, J_WORDS = ((JR * JPW + 3) / 4) * 4;
     static constexpr int WARP_WORDS = I_WORDS + D_WORDS + J_WORDS + 4;   // +4: load_run may touch one word past a row
     static constexpr int NPX = RPL * RL;                          // template registers per lane
 };
@@ -290,28 +299,37 @@ __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c)
     return d;
 }
 
-// Coalesced copy of a ROWS x PW-word rectangle (aligned 32-bit words) from global to shared.
-template <int ROWS, int PW>
-__device__ __forceinline__ void stage_words(uint32_t *dst, const uint8_t *src_aligned, int pitch_bytes, int lane)
+// Coalesced copy of a ROWS x V4 rectangle of aligned 128-bit words from global to shared memory.
+// PW = destination pitch in 32-bit words; if PW == 4*V4 the rows are stored with 128-bit stores,
+// otherwise (odd pitch) with four 32-bit stores.
+template <int ROWS, int V4, int PW>
+__device__ __forceinline__ void stage_v4(uint32_t *dst, const uint8_t *src_aligned, int pitch_bytes, int lane)
 {
-    constexpr int N = ROWS * PW;
+    constexpr int N = ROWS * V4;
     constexpr int T = (N + 31) / 32;
-    uint32_t v[T];
+    uint4 v[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int idx = lane + 32 * t;
-        const int r = idx / PW, c = idx - r * PW;
-        v[t] = (idx < N) ? __ldg(reinterpret_cast<const uint32_t *>(src_aligned + (ptrdiff_t)r * pitch_bytes) + c) : 0u;
+        const int r = idx / V4, c = idx - r * V4;
+        if (idx < N) v[t] = __ldg(reinterpret_cast<const uint4 *>(src_aligned + (ptrdiff_t)r * pitch_bytes) + c);
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int idx = lane + 32 * t;
-        if (idx < N) dst[idx] = v[t];
+        const int r = idx / V4, c = idx - r * V4;
+        if (idx < N) {
+            if (PW == 4 * V4) {
+                *reinterpret_cast<uint4 *>(dst + r * PW + 4 * c) = v[t];
+            } else {
+                uint32_t *p = dst + r * PW + 4 * c;
+                p[0] = v[t].x; p[1] = v[t].y; p[2] = v[t].z; p[3] = v[t].w;
+            }
+        }
     }
 }
 
 // 8-bit sample stream of one run: E holds bytes e0.., O the same shifted by one byte.
-template <int RL>
 __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_t E[3], uint32_t O[3])
 {
     const uint32_t *p = row + (byte0 >> 2);
@@ -325,19 +343,23 @@ __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_
     O[2] = E[2] >> 8;
 }
 
-// bilinear fixed-point sample of pixel k of a run: rows A (weights wA = {iw00,iw01}) and B ({iw10,iw11})
-#define KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, rnd)                                                   \
-    (((k) & 3) == 0 ? dp2a_lo_su(wB, EB[(k) >> 2], dp2a_lo_su(wA, EA[(k) >> 2], rnd))                 \
-   : ((k) & 3) == 1 ? dp2a_lo_su(wB, OB[(k) >> 2], dp2a_lo_su(wA, OA[(k) >> 2], rnd))                 \
-   : ((k) & 3) == 2 ? dp2a_hi_su(wB, EB[(k) >> 2], dp2a_hi_su(wA, EA[(k) >> 2], rnd))                 \
-                    : dp2a_hi_su(wB, OB[(k) >> 2], dp2a_hi_su(wA, OA[(k) >> 2], rnd)))
+// fixed-point bilinear sample of pixel k of a run, accumulated onto `acc`:
+// rows A (weights wA = {iw00,iw01}) and B (wB = {iw10,iw11})
+#define KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, acc)                                                   \
+    (((k) & 3) == 0 ? dp2a_lo_su(wB, EB[(k) >> 2], dp2a_lo_su(wA, EA[(k) >> 2], acc))                 \
+   : ((k) & 3) == 1 ? dp2a_lo_su(wB, OB[(k) >> 2], dp2a_lo_su(wA, OA[(k) >> 2], acc))                 \
+   : ((k) & 3) == 2 ? dp2a_hi_su(wB, EB[(k) >> 2], dp2a_hi_su(wA, EA[(k) >> 2], acc))                 \
+                    : dp2a_hi_su(wB, OB[(k) >> 2], dp2a_hi_su(wA, OA[(k) >> 2], acc)))
 
-template <int WIN>
-__global__ void __launch_bounds__(128)
+#define KLT2_RND (1 << (W_BITS - 5 - 1))
+#define KLT2_SH (W_BITS - 5)
+
+template <int WIN, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_klt2(const KltArgs a)
 {
     using C = Klt2Cfg<WIN>;
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(16) uint32_t smem_u32[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int pair = blockIdx.y;
@@ -351,17 +373,19 @@ k_klt2(const KltArgs a)
     const float halfWin = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
 
-    // run geometry of this lane (level independent)
-    int run_row[C::RPL], run_x0[C::RPL], run_len[C::RPL];
+    // run geometry of this lane (level independent). Idle slots alias an existing run; their
+    // contributions are dropped per RUN (run_ok), never per pixel.
+    int run_row[C::RPL], run_x0[C::RPL];
+    bool run_ok[C::RPL], last_ok[C::RPL];
 #pragma unroll
     for (int q = 0; q < C::RPL; ++q) {
         const int id = lane + 32 * q;
-        const int r = id / C::SEG, sgm = id - r * C::SEG;
+        run_ok[q] = id < C::NRUN;
+        const int idm = run_ok[q] ? id : id - C::NRUN;
+        const int r = idm / C::SEG, sgm = idm - r * C::SEG;
         run_row[q] = r;
         run_x0[q] = sgm * C::RL;
-        int len = WIN - sgm * C::RL;
-        len = len > C::RL ? C::RL : len;
-        run_len[q] = (id < C::NRUN) ? len : 0;
+        last_ok[q] = C::FULL || (sgm * C::RL + C::RL <= WIN);     // does pixel RL-1 of this run exist?
     }
 
     const float2 p0 = a.pts0[gi];
@@ -392,49 +416,51 @@ k_klt2(const KltArgs a)
 
         // ---- stage template patch, derivative patch and the initial search region (all loads first)
         nextx = __fsub_rn(nextx, halfWin); nexty = __fsub_rn(nexty, halfWin);
-        int jx0, jy0;   // origin (pixel coords) of the staged search region; jx0 is 4-aligned
+        int jx0, jy0;   // origin (pixel coords) of the staged search region; jx0 is 16-aligned
         {
-            const int iax = ipx & ~3;
-            stage_words<C::W1, C::IPW>(Ibuf, I.img + (ptrdiff_t)ipy * I.pitch + iax, I.pitch, lane);
-            stage_words<C::W1, C::DPW>(Dbuf, reinterpret_cast<const uint8_t *>(I.deriv + (ptrdiff_t)ipy * I.pitch + ipx), I.pitch * 4, lane);
+            const int iax = ipx & ~15, dax = ipx & ~3;
+            stage_v4<C::W1, C::I_V4, C::IPW>(Ibuf, I.img + (ptrdiff_t)ipy * I.pitch + iax, I.pitch, lane);
+            stage_v4<C::W1, C::D_V4, C::DPW>(Dbuf, reinterpret_cast<const uint8_t *>(I.deriv + (ptrdiff_t)ipy * I.pitch + dax), I.pitch * 4, lane);
             int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
             // clamp the staging origin so that it stays inside the padded plane even for a wild start
             inx = max(-WIN, min(inx, J.w - 1)); iny = max(-WIN, min(iny, J.h - 1));
-            jx0 = (inx - MJ) & ~3; jy0 = iny - MJ;
-            stage_words<C::JR, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+            jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
+            stage_v4<C::JR, C::J_V4, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
         }
         __syncwarp();
 
-        // ---- template: I (5 frac bits), Ix, Iy in registers; exact A sums
-        int Iv[C::NPX], Ix[C::NPX], Iy[C::NPX];
+        // ---- template. Registers per pixel: Cn = RND - (I << SH) (the dp2a accumulator seed, so that an
+        // iteration's diff is one shift after the two dp2a), Ix, Iy. Exact A sums.
+        int Cn[C::NPX], Ix[C::NPX], Iy[C::NPX];
         int sA11 = 0, sA12 = 0, sA22 = 0;
         {
             const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
-            const int offI = ipx & 3;
+            const int offI = ipx & 15, offD = ipx & 3;
 #pragma unroll
             for (int q = 0; q < C::RPL; ++q) {
                 uint32_t EA[3], OA[3], EB[3], OB[3];
-                const int r = run_len[q] ? run_row[q] : 0;
-                load_run<C::RL>(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
-                load_run<C::RL>(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
-                const uint32_t *d0 = Dbuf + r * C::DPW + run_x0[q];
+                const int r = run_row[q];
+                load_run(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
+                load_run(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
+                const uint32_t *d0 = Dbuf + r * C::DPW + offD + run_x0[q];
                 const uint32_t *d1 = d0 + C::DPW;
                 uint32_t da = d0[0], db = d1[0];
+                int a11 = 0, a12 = 0, a22 = 0;
 #pragma unroll
                 for (int k = 0; k < C::RL; ++k) {
                     const uint32_t da1 = d0[k + 1], db1 = d1[k + 1];
-                    const int iv = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, 1 << (W_BITS - 5 - 1)) >> (W_BITS - 5);
+                    const int iv = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, KLT2_RND) >> KLT2_SH;
                     int ix = ((int)(short)(da & 0xffff) * iw00 + (int)(short)(da1 & 0xffff) * iw01 + (int)(short)(db & 0xffff) * iw10 +
                               (int)(short)(db1 & 0xffff) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
                     int iy = (((int)da >> 16) * iw00 + ((int)da1 >> 16) * iw01 + ((int)db >> 16) * iw10 + ((int)db1 >> 16) * iw11 +
                               (1 << (W_BITS - 1))) >> W_BITS;
-                    const bool ok = k < run_len[q];
-                    if (!ok) { ix = 0; iy = 0; }
-                    Iv[q * C::RL + k] = ok ? iv : 0;
+                    if (!C::FULL && k == C::RL - 1 && !last_ok[q]) { ix = 0; iy = 0; }
+                    Cn[q * C::RL + k] = KLT2_RND - (iv << KLT2_SH);
                     Ix[q * C::RL + k] = ix; Iy[q * C::RL + k] = iy;
-                    sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
                     da = da1; db = db1;
                 }
+                sA11 += run_ok[q] ? a11 : 0; sA12 += run_ok[q] ? a12 : 0; sA22 += run_ok[q] ? a22 : 0;
             }
         }
         const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
@@ -456,36 +482,36 @@ k_klt2(const KltArgs a)
         float pdx = 0.f, pdy = 0.f;
         int j = 0;
         for (; j < a.max_count; ++j) {
-            const float qx = nextx, qy = nexty;
-            const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
+            const int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
             if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
                 if (level == 0) status = 0;
                 break;
             }
             int offx = inx - jx0, offy = iny - jy0;
-            if (offx < 0 || offx + C::W1 > 4 * C::JPW || offy < 0 || offy + C::W1 > C::JR) {
+            if (offx < 0 || offx + C::W1 > C::JBYTES || offy < 0 || offy + C::W1 > C::JR) {
                 __syncwarp();
-                jx0 = (inx - MJ) & ~3; jy0 = iny - MJ;
-                stage_words<C::JR, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+                jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
+                stage_v4<C::JR, C::J_V4, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
                 __syncwarp();
                 offx = inx - jx0; offy = iny - jy0;
             }
-            bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), iw00, iw01, iw10, iw11);
+            bilinear_weights(__fsub_rn(nextx, (float)inx), __fsub_rn(nexty, (float)iny), iw00, iw01, iw10, iw11);
             const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
             int sb1 = 0, sb2 = 0;
 #pragma unroll
             for (int q = 0; q < C::RPL; ++q) {
                 uint32_t EA[3], OA[3], EB[3], OB[3];
-                const int r = run_len[q] ? run_row[q] : 0;
-                const uint32_t *rowA = Jbuf + (offy + r) * C::JPW;
-                load_run<C::RL>(rowA, offx + run_x0[q], EA, OA);
-                load_run<C::RL>(rowA + C::JPW, offx + run_x0[q], EB, OB);
+                const uint32_t *rowA = Jbuf + (offy + run_row[q]) * C::JPW;
+                load_run(rowA, offx + run_x0[q], EA, OA);
+                load_run(rowA + C::JPW, offx + run_x0[q], EB, OB);
+                int b1q = 0, b2q = 0;
 #pragma unroll
                 for (int k = 0; k < C::RL; ++k) {
-                    const int diff = (KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, 1 << (W_BITS - 5 - 1)) >> (W_BITS - 5)) - Iv[q * C::RL + k];
-                    sb1 += diff * Ix[q * C::RL + k];     // Ix = Iy = 0 beyond the run / on idle lanes
-                    sb2 += diff * Iy[q * C::RL + k];
+                    const int diff = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, Cn[q * C::RL + k]) >> KLT2_SH;
+                    b1q += diff * Ix[q * C::RL + k];     // Ix = Iy = 0 on a non-existent last pixel
+                    b2q += diff * Iy[q * C::RL + k];
                 }
+                sb1 += run_ok[q] ? b1q : 0; sb2 += run_ok[q] ? b2q : 0;
             }
             const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
             const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
@@ -511,10 +537,10 @@ k_klt2(const KltArgs a)
                 status = 0;
             } else {
                 int offx = inx - jx0, offy = iny - jy0;
-                if (offx < 0 || offx + C::W1 > 4 * C::JPW || offy < 0 || offy + C::W1 > C::JR) {
+                if (offx < 0 || offx + C::W1 > C::JBYTES || offy < 0 || offy + C::W1 > C::JR) {
                     __syncwarp();
-                    jx0 = (inx - MJ) & ~3; jy0 = iny - MJ;
-                    stage_words<C::JR, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+                    jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
+                    stage_v4<C::JR, C::J_V4, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
                     __syncwarp();
                     offx = inx - jx0; offy = iny - jy0;
                 }
@@ -524,15 +550,16 @@ k_klt2(const KltArgs a)
 #pragma unroll
                 for (int q = 0; q < C::RPL; ++q) {
                     uint32_t EA[3], OA[3], EB[3], OB[3];
-                    const int r = run_len[q] ? run_row[q] : 0;
-                    const uint32_t *rowA = Jbuf + (offy + r) * C::JPW;
-                    load_run<C::RL>(rowA, offx + run_x0[q], EA, OA);
-                    load_run<C::RL>(rowA + C::JPW, offx + run_x0[q], EB, OB);
+                    const uint32_t *rowA = Jbuf + (offy + run_row[q]) * C::JPW;
+                    load_run(rowA, offx + run_x0[q], EA, OA);
+                    load_run(rowA + C::JPW, offx + run_x0[q], EB, OB);
+                    int sq = 0;
 #pragma unroll
                     for (int k = 0; k < C::RL; ++k) {
-                        const int diff = (KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, 1 << (W_BITS - 5 - 1)) >> (W_BITS - 5)) - Iv[q * C::RL + k];
-                        sabs += (k < run_len[q]) ? abs(diff) : 0;
+                        const int diff = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, Cn[q * C::RL + k]) >> KLT2_SH;
+                        sq += (!C::FULL && k == C::RL - 1 && !last_ok[q]) ? 0 : abs(diff);
                     }
+                    sabs += run_ok[q] ? sq : 0;
                 }
                 const int tot = __reduce_add_sync(0xffffffffu, sabs);
                 errv = __fdiv_rn(__fmul_rn((float)tot, 1.f), (float)(32 * WIN * WIN));
@@ -548,12 +575,10 @@ template <int WIN>
 static cudaError_t launch_klt2(const KltArgs &a, dim3 grd, cudaStream_t st)
 {
     const size_t smem = (size_t)4 * Klt2Cfg<WIN>::WARP_WORDS * 4;
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k_klt2<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    k_klt2<WIN><<<grd, 128, smem, st>>>(a);
+    static const int minb = getenv("VO_KLT_MINB") ? atoi(getenv("VO_KLT_MINB")) : KLT2_MIN_BLOCKS;   // tuning switch
+    if (minb >= 6) k_klt2<WIN, 6><<<grd, 128, smem, st>>>(a);
+    else if (minb == 5) k_klt2<WIN, 5><<<grd, 128, smem, st>>>(a);
+    else k_klt2<WIN, 4><<<grd, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 
