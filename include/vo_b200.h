@@ -165,6 +165,35 @@ VO_API int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *offsets
                               float *T01_inout_d, uint8_t *mask_inlier_d, int *success_d,
                               int *iters_d);
 
+/* ------------------------------------------------------------------ stereo tracking step
+ * Steady-state part of StereoVO::trackStereoImages (core/visual_odometry/stereo_vo/stereo_vo.cpp:475-670,
+ * steps [2]..[7]): constant-velocity prior, trackWithPrior(l0->l1), trackWithScale, trackWithPrior(l1->r1),
+ * stereo pose-only GN on the triangulated survivors, the y > sampson_y stub, stable compaction.
+ * Device resident: one H2D (two images + landmark state), one D2H (pose + survivors), one sync.
+ * slot_l0 must already hold the previous left image (its pyramid stays cached between frames).
+ * img_l1 / img_r1: host CV_8UC1 images (NULL = the slot already holds the image).
+ * Xw: landmark 3-D points in the world frame; triangulated[i] = Landmark::isTriangulated().
+ * Outputs: T_wc = T_wp * dT_pc (4x4 row-major), dT_pc (the GN result, next frame's dT_pc_prev),
+ * index_out[k] = original index of the k-th surviving landmark (stable order == the reference's
+ * StereoLandmarkTracking compactions), its tracked pixels, counts_out[5] (nullable) = survivors after
+ * l0->l1, scale refinement, l1->r1, points fed to the GN, final.
+ * Returns VO_ERR_NAN with the reference's text if the GN fails ("PoseOnlyStereoBA is failed!"). */
+typedef struct vo_stereo_step_params {
+    int window_size, max_level;      /* feature_tracker.window_size / max_level */
+    float thres_error;               /* feature_tracker.thres_error */
+    float thres_poseba_error;        /* motion_estimator.thres_poseba_error */
+    float K_l[4], K_r[4];            /* fx, fy, cx, cy */
+    float T_lr[16];                  /* row-major */
+    int do_scale_refine;             /* 1 = run trackWithScale (stereo_vo.cpp:553) */
+    float sampson_y;                 /* 660 (stereo_vo.cpp:663) */
+} vo_stereo_step_params;
+VO_API int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *prm, int slot_l0, int slot_l1,
+                         int slot_r1, const uint8_t *img_l1, const uint8_t *img_r1, int w, int h,
+                         size_t step, int n, const float *pts_l0, const float *pts_r0, const float *Xw,
+                         const uint8_t *triangulated, const float *T_wp, const float *dT_pc_prev,
+                         float *T_wc_out, float *dT_pc_out, int *n_out, int *index_out,
+                         float *pts_l1_out, float *pts_r1_out, int *counts_out);
+
 /* ------------------------------------------------------------------ triangulation
  * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */
 VO_API int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,

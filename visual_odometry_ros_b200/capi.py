@@ -44,6 +44,12 @@ c_i64_p = ctypes.POINTER(ctypes.c_longlong)
 vp = ctypes.c_void_p
 
 
+class StereoStepParams(ctypes.Structure):
+    _fields_ = [("window_size", ctypes.c_int), ("max_level", ctypes.c_int), ("thres_error", ctypes.c_float),
+                ("thres_poseba_error", ctypes.c_float), ("K_l", ctypes.c_float * 4), ("K_r", ctypes.c_float * 4),
+                ("T_lr", ctypes.c_float * 16), ("do_scale_refine", ctypes.c_int), ("sampson_y", ctypes.c_float)]
+
+
 class LbaProblem(ctypes.Structure):
     _fields_ = [
         ("n_frames", ctypes.c_int), ("n_opt", ctypes.c_int), ("n_points", ctypes.c_int), ("n_obs", ctypes.c_int),
@@ -103,6 +109,9 @@ def lib():
     L.vo_compact.argtypes = [vp, vp, ctypes.c_int, vp, c_int_p]
     L.vo_ft_track_with_scale.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]
     L.vo_lba_solve.argtypes = [vp, ctypes.POINTER(LbaProblem), vp, vp, vp, c_int_p]
+    L.vo_stereo_track_step.argtypes = [vp, ctypes.POINTER(StereoStepParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       c_int_p, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -386,3 +395,42 @@ class Context:
         ok = ctypes.c_int(0)
         check(self.h, self.L.vo_lba_solve(self.h, ctypes.byref(s), _ptr(poses), _ptr(points), _ptr(avg), ctypes.byref(ok)))
         return poses, points[:s.n_points], avg, bool(ok.value)
+
+    # ---------------------------------------------------------------- stereo tracking step (S1)
+    def stereo_track_step(self, slot_l0, slot_l1, slot_r1, img_l1, img_r1, pts_l0, pts_r0, Xw, tri, T_wp, dT_pc_prev,
+                          K_l, K_r, T_lr, win, max_level, thres_err, thres_poseba, do_scale_refine=True, sampson_y=660.0,
+                          want_counts=True):
+        """Steady-state part of StereoVO::trackStereoImages (stereo_vo.cpp:475-670), device resident."""
+        prm = StereoStepParams()
+        prm.window_size, prm.max_level, prm.thres_error, prm.thres_poseba_error = int(win), int(max_level), float(thres_err), float(thres_poseba)
+        prm.K_l = (ctypes.c_float * 4)(*[float(v) for v in K_l])
+        prm.K_r = (ctypes.c_float * 4)(*[float(v) for v in K_r])
+        prm.T_lr = (ctypes.c_float * 16)(*[float(v) for v in np.asarray(T_lr, np.float32).ravel()])
+        prm.do_scale_refine = 1 if do_scale_refine else 0
+        prm.sampson_y = float(sampson_y)
+        l0 = np.ascontiguousarray(pts_l0, np.float32).reshape(-1, 2)
+        r0 = np.ascontiguousarray(pts_r0, np.float32).reshape(-1, 2)
+        X = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(tri).astype(np.uint8)
+        n = len(l0)
+        Twp = np.ascontiguousarray(T_wp, np.float32)
+        dTp = np.ascontiguousarray(dT_pc_prev, np.float32)
+        T_wc, dT = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+        idx = np.zeros(max(n, 1), np.int32)
+        o_l1, o_r1 = np.zeros((max(n, 1), 2), np.float32), np.zeros((max(n, 1), 2), np.float32)
+        counts = np.zeros(5, np.int32)
+        n_out = ctypes.c_int(0)
+        w = h = step = 0
+        for im in (img_l1, img_r1):
+            if im is not None:
+                assert im.dtype == np.uint8 and im.ndim == 2 and im.strides[1] == 1
+                h, w, step = im.shape[0], im.shape[1], im.strides[0]
+        if w == 0:
+            raise ValueError("pass the new images (use upload_image + the raw C ABI to keep them resident)")
+        check(self.h, self.L.vo_stereo_track_step(
+            self.h, ctypes.byref(prm), slot_l0, slot_l1, slot_r1, _ptr(img_l1), _ptr(img_r1), w, h, step, n, _ptr(l0), _ptr(r0),
+            _ptr(X), _ptr(t), _ptr(Twp), _ptr(dTp), _ptr(T_wc), _ptr(dT), ctypes.byref(n_out), _ptr(idx), _ptr(o_l1), _ptr(o_r1),
+            _ptr(counts) if want_counts else None))
+        k = n_out.value
+        return dict(T_wc=T_wc, dT_pc=dT, index=idx[:k].copy(), pts_l1=o_l1[:k].copy(), pts_r1=o_r1[:k].copy(),
+                    counts=[int(c) for c in counts])

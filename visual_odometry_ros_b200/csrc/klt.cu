@@ -32,6 +32,7 @@ struct KltArgs {
     uint8_t *status;
     float *err;
     unsigned long long *counters;   // [2*VO_MAX_LEVELS] or null
+    const uint8_t *skip_mask;       // nullable: features whose entry is 0 are not tracked (outputs untouched)
     int n;
     int win;
     int top_level;      // effective maxLevel
@@ -101,6 +102,7 @@ k_klt(const KltArgs a)
     const int pair = blockIdx.y;
     if (f >= a.n) return;
     const size_t gi = (size_t)pair * a.n + f;
+    if (a.skip_mask && !a.skip_mask[gi]) return;
     const SlotDesc &S0 = a.slots[a.s0.id[pair]];
     const SlotDesc &S1 = a.slots[a.s1.id[pair]];
     const int win = a.win;
@@ -368,6 +370,7 @@ k_klt2(const KltArgs a)
     uint32_t *Dbuf = Ibuf + C::I_WORDS;
     uint32_t *Jbuf = Dbuf + C::D_WORDS;
     const size_t gi = (size_t)pair * a.n + f;
+    if (a.skip_mask && !a.skip_mask[gi]) return;
     const SlotDesc &S0 = a.slots[a.s0.id[pair]];
     const SlotDesc &S1 = a.slots[a.s1.id[pair]];
     const float halfWin = (float)(WIN - 1) * 0.5f;
@@ -617,6 +620,7 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
         a.status = status_d ? status_d + off : nullptr;
         a.err = err_d ? err_d + off : nullptr;
         a.counters = reinterpret_cast<unsigned long long *>(counters_d);
+        a.skip_mask = (post && post->skip_masked && post->mask) ? post->mask + off : nullptr;
         a.n = n; a.win = win; a.top_level = eff; a.flags = flags;
         a.max_count = 30; a.min_eig = 1e-4f; a.eps2 = 0.01 * 0.01;
         if (post) {

@@ -163,6 +163,19 @@ __global__ void __launch_bounds__(128) k_klt_scale(const KltScaleArgs a)
     }
 }
 
+int vo_klt_scale_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, const float *scale_d, int n,
+                          float *pts_track_d, uint8_t *mask_d, int *nan_flag_d)
+{
+    KltScaleArgs a;
+    a.slots = ctx->d_slots; a.slot0 = slot0; a.slot1 = slot1;
+    a.pts0 = (const float2 *)pts0_d; a.scale = scale_d;
+    a.pts_track = (float2 *)pts_track_d; a.mask = mask_d; a.nan_flag = nan_flag_d; a.iters = nullptr; a.n = n;
+    k_klt_scale<<<vo_div_up(n, 4), 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
 extern "C" int vo_ft_track_with_scale(vo_ctx *ctx, int slot0, int slot1, const float *pts0, const float *scale_est, int n,
                                       float *pts_track_inout, uint8_t *mask_inout)
 {
@@ -190,13 +203,9 @@ extern "C" int vo_ft_track_with_scale(vo_ctx *ctx, int slot0, int slot1, const f
     memset(h + oFlag, 0, 16);
     memcpy(h + oM, mask_inout, N);
     VO_CUDA(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, ctx->stream));
-    KltScaleArgs a;
-    a.slots = ctx->d_slots; a.slot0 = slot0; a.slot1 = slot1;
-    a.pts0 = (const float2 *)(d + oP0); a.scale = (const float *)(d + oS);
-    a.pts_track = (float2 *)(d + oPt); a.mask = d + oM; a.nan_flag = (int *)(d + oFlag); a.iters = nullptr; a.n = n;
-    k_klt_scale<<<vo_div_up(n, 4), 128, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    VO_CUDA(cudaGetLastError());
+    rc = vo_klt_scale_launch_d(ctx, slot0, slot1, (const float *)(d + oP0), (const float *)(d + oS), n, (float *)(d + oPt), d + oM,
+                               (int *)(d + oFlag));
+    if (rc) return rc;
     VO_CUDA(cudaMemcpyAsync(h + oPt, d + oPt, total - oPt, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(pts_track_inout, h + oPt, N * 8);

@@ -23,6 +23,7 @@
 struct PoseArgs {
     const int *offsets;   // [n_prob+1] device, or null (single problem of n points)
     int n_single;
+    const int *n_single_d;  // nullable: point count read from device memory (device-resident pipelines)
     const float *X, *pl, *pr;
     float Kl[4], Kr[4];
     float T_rl[16];       // row-major
@@ -182,7 +183,7 @@ k_pose_gn(const PoseArgs a)
 
     const int prob = blockIdx.x;
     const int beg = a.offsets ? a.offsets[prob] : 0;
-    const int n = a.offsets ? a.offsets[prob + 1] - beg : a.n_single;
+    const int n = a.offsets ? a.offsets[prob + 1] - beg : (a.n_single_d ? *a.n_single_d : a.n_single);
     const float *X = a.X + 3 * (size_t)beg;
     const float *pl = a.pl + 2 * (size_t)beg;
     const float *pr = a.mono ? nullptr : a.pr + 2 * (size_t)beg;
@@ -338,12 +339,12 @@ static void host_inv_se3(const float *T, float *O)
     O[12] = O[13] = O[14] = 0.f; O[15] = 1.f;
 }
 
-static int pose_launch(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const float *X_d, const float *pl_d,
-                       const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres, int mono,
-                       int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d)
+int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
+                     const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
+                     int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d)
 {
     PoseArgs a;
-    a.offsets = offsets_d; a.n_single = n_single;
+    a.offsets = offsets_d; a.n_single = n_single; a.n_single_d = n_single_d;
     a.X = X_d; a.pl = pl_d; a.pr = pr_d;
     for (int i = 0; i < 4; ++i) { a.Kl[i] = Kl[i]; a.Kr[i] = Kr ? Kr[i] : Kl[i]; }
     if (T_lr) host_inv_se3(T_lr, a.T_rl);
@@ -367,7 +368,7 @@ extern "C" int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *off
     VO_REQUIRE(offsets_d && X_d && pts_l1_d && pts_r1_d && K_l4 && K_r4 && T_lr && T01_inout_d && mask_inlier_d,
                VO_ERR_INVALID_ARG, "null pointer");
     VO_CUDA(cudaSetDevice(ctx->device));
-    return pose_launch(ctx, n_prob, offsets_d, 0, X_d, pts_l1_d, pts_r1_d, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0,
+    return vo_pose_launch_d(ctx, n_prob, offsets_d, 0, nullptr, X_d, pts_l1_d, pts_r1_d, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0,
                        T01_inout_d, mask_inlier_d, success_d, iters_d);
 }
 
@@ -387,7 +388,7 @@ static int pose_host(vo_ctx *ctx, const float *X, const float *pl, const float *
     if (pr) memcpy(h + oPr, pr, (size_t)n * 8);
     memcpy(h + oT, T01_inout, 64);
     VO_CUDA(cudaMemcpyAsync(d, h, oFlags, cudaMemcpyHostToDevice, ctx->stream));
-    rc = pose_launch(ctx, 1, nullptr, n, (const float *)(d + oX), (const float *)(d + oPl), (const float *)(d + oPr), Kl, Kr,
+    rc = vo_pose_launch_d(ctx, 1, nullptr, n, nullptr, (const float *)(d + oX), (const float *)(d + oPl), (const float *)(d + oPr), Kl, Kr,
                      T_lr, thres, mono, variant, (float *)(d + oT), d + oMask, (int *)(d + oFlags), (int *)(d + oFlags + 4));
     if (rc) return rc;
     VO_CUDA(cudaMemcpyAsync(h + oT, d + oT, total - oT, cudaMemcpyDeviceToHost, ctx->stream));

@@ -99,7 +99,7 @@ struct KltPost {           // fused FeatureTracker post-filter (feature_tracker.
     float thres_err;
     float thres_bi2;       // already squared (and x5 for the with-prior variant)
     int border;            // 3 for trackBidirection, 0 for the *WithPrior variants
-    int strict_border;     // unused
+    int skip_masked;       // 1: features whose mask entry is 0 are skipped entirely
     const float *ref_pts;      // bidir-backward: pts0 to compare the back-track with
     const float *fwd_pts;      // bidir-backward: forward-tracked points (border test)
     const uint8_t *fwd_status; // bidir-backward
@@ -109,5 +109,12 @@ struct KltPost {           // fused FeatureTracker post-filter (feature_tracker.
 int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1, const float *pts0_d,
                   int n, int win, int max_level, int flags, float *pts1_d, uint8_t *status_d,
                   float *err_d, long long *counters_d, const KltPost *post);
+
+// klt_scale.cu / pose_gn.cu: device-pointer launchers (asynchronous, no staging)
+int vo_klt_scale_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, const float *scale_d, int n,
+                          float *pts_track_d, uint8_t *mask_d, int *nan_flag_d);
+int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
+                     const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
+                     int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d);
 
 static inline int vo_div_up(int a, int b) { return (a + b - 1) / b; }

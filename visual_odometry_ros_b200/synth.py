@@ -196,3 +196,66 @@ def lba_problem(seed=4004, n_kf=10, n_points=5000, n_fix=2, noise_px=0.3, point_
                 K_l=np.array([FX, FY, CX, CY]), K_r=np.array([FX, FY, CX, CY]),
                 T_lr=T_lr_s if stereo else np.eye(4), is_stereo=int(stereo), huber=0.5, lam=1e-5, max_iter=10,
                 gt_poses=gt_poses, gt_points=Xw / pose_scale)
+
+
+# ------------------------------------------------------------------ stereo frame pair (configs 3/5)
+def _inverse_warp(img, fwd_dx, fwd_dy, iters=3):
+    """Image seen after every source pixel p moved to p + fwd(p): out(q) = img(p) with p + fwd(p) = q
+    (fixed-point inversion of the forward flow, bilinear resampling)."""
+    import cv2
+    h, w = img.shape
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    px, py = xs.copy(), ys.copy()
+    for _ in range(iters):
+        fx = cv2.remap(fwd_dx, px, py, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        fy = cv2.remap(fwd_dy, px, py, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        px, py = xs - fx, ys - fy
+    return cv2.remap(img, px, py, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101), (px, py)
+
+
+def stereo_frame_pair(seed=3003, n=2000, w=KITTI_W, h=KITTI_H, rotvec=(0.001, -0.008, 0.0005), t=(0.01, -0.005, 0.9),
+                      tri_frac=0.9):
+    """Two consecutive stereo frames of a static scene (depth from a ground-plane-like disparity field)
+    seen by a KITTI-like rig that moves by T01 = (rotvec, t), plus the landmark state StereoVO would
+    hold after the first frame. Returns a dict with images L0,R0,L1,R1, pts_l0, pts_r0, Xw, tri,
+    T_wp, dT_pc_prev (a slightly wrong constant-velocity guess), T01_true."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    L0 = textured_image(rng, w, h)
+    disp0 = disparity_plane(w, h)
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    z0 = (FX * BASELINE_M) / disp0
+    X0 = np.stack([(xs - CX) / FX * z0, (ys - CY) / FY * z0, z0], -1).astype(np.float64)      # points in left-0 frame
+    R01 = so3_exp(rotvec)
+    t01 = np.asarray(t, np.float64)
+    X1 = (X0 - t01) @ R01                                                                   # = R01^T (X0 - t01)
+    u1 = FX * X1[..., 0] / X1[..., 2] + CX
+    v1 = FY * X1[..., 1] / X1[..., 2] + CY
+    flow_x, flow_y = (u1 - xs).astype(np.float32), (v1 - ys).astype(np.float32)
+    noise = lambda im: np.clip(im.astype(np.float32) + rng.normal(0, 1.0, im.shape), 0, 255).astype(np.uint8)
+    R0 = noise(_inverse_warp(L0, -disp0, np.zeros_like(disp0))[0])
+    L1f, (sx, sy) = _inverse_warp(L0, flow_x, flow_y)
+    L1 = noise(L1f)
+    disp1_src = (FX * BASELINE_M / X1[..., 2]).astype(np.float32)                             # disparity after the motion, at source pixels
+    disp1 = cv2.remap(disp1_src, sx, sy, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)   # at L1 pixels
+    R1 = noise(_inverse_warp(L1f, -disp1, np.zeros_like(disp1))[0])
+
+    pts_l0 = grid_features(rng, n, w, h, border=30)
+    d0 = cv2.remap(disp0, pts_l0[:, 0].copy(), pts_l0[:, 1].copy(), cv2.INTER_LINEAR).ravel()
+    pts_r0 = (pts_l0 - np.stack([d0, np.zeros_like(d0)], 1)).astype(np.float32)
+    zf = FX * BASELINE_M / d0
+    Xl0 = np.stack([(pts_l0[:, 0] - CX) / FX * zf, (pts_l0[:, 1] - CY) / FY * zf, zf], 1)
+    Xl0 = Xl0 * (1.0 + rng.normal(0, 0.003, (n, 1)))                                         # triangulation noise
+    T_wp = np.eye(4)
+    T_wp[:3, :3] = so3_exp([0.01, 0.3, -0.02])
+    T_wp[:3, 3] = [12.0, -0.4, 35.0]
+    Xw = Xl0 @ T_wp[:3, :3].T + T_wp[:3, 3]
+    tri = (rng.uniform(size=n) < tri_frac).astype(np.uint8)
+    T01 = np.eye(4)
+    T01[:3, :3] = R01
+    T01[:3, 3] = t01
+    dT_prev = np.eye(4)
+    dT_prev[:3, :3] = so3_exp(np.asarray(rotvec) * 0.8)
+    dT_prev[:3, 3] = t01 * 0.9 + [0.01, 0.0, 0.02]
+    return dict(L0=L0, R0=R0, L1=L1, R1=R1, pts_l0=pts_l0, pts_r0=pts_r0, Xw=Xw.astype(np.float32), tri=tri,
+                T_wp=T_wp.astype(np.float32), dT_pc_prev=dT_prev.astype(np.float32), T01_true=T01)
