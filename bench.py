@@ -384,30 +384,38 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
     res["pose_gn"] = {"solves_per_s": nprob / (ms * 1e-3), "batch": nprob, "points": npts, "ms_per_batch": ms,
                       "mean_iters": float(it_d.float().mean().item()),
                       "cpu_port_solves_per_s_1core": cpu_rate}
-    # ---- single frame through the host C ABI: upload 2 new images, track L0->L1 and L1->R1, pose GN
-    nxt = synth.klt_stereo_case(seed=2002, n=NFEAT)
-    L0, L1, R1 = nxt["left"], nxt["next_left"], nxt["right"]
-    p0 = nxt["pts0"]
-    sc = synth.pose_scene(seed=1001, n=NFEAT)
+    # ---- single frame: the device-resident stereo tracking step (S1, stereo_vo.cpp:475-670) through the host C ABI:
+    #      H2D of the two new images + landmark state, prior, 2x trackWithPrior, trackWithScale, stereo pose GN,
+    #      compactions, D2H of pose + survivors; wall clock incl. every copy and the one synchronisation.
+    from oracle import step as ostep
+    fp = synth.stereo_frame_pair(seed=3003, n=NFEAT)
+    ctx.upload_image(0, fp["L0"])
+    args = (fp["pts_l0"], fp["pts_r0"], fp["Xw"], fp["tri"], fp["T_wp"], fp["dT_pc_prev"], K4, K4, Tlr, WIN, MAXLVL, THRES_ERR, 3.0)
 
-    ctx.upload_image(0, L0)   # previous left: pyramid + derivative stay cached from the previous frame
-
-    def frame():
-        ctx.upload_image(1, L1)
-        ctx.upload_image(2, R1)
-        pt, m = ctx.ft_track_with_prior(0, 1, p0, p0, WIN, MAXLVL, THRES_ERR)
-        pt2, m2 = ctx.ft_track_with_prior(1, 2, pt, pt, WIN, MAXLVL, THRES_ERR)
-        return ctx.pose_gn_stereo(sc["X"], sc["pts_l1"], sc["pts_r1"], K4, K4, Tlr, 3.0, np.eye(4))
-    for _ in range(5):
-        frame()
+    def frame(refine):
+        return ctx.stereo_track_step(0, 1, 2, fp["L1"], fp["R1"], *args, do_scale_refine=refine, want_counts=False)
+    out_frame = {}
+    for name, refine in (("with_scale_refine", True), ("track_plus_pose", False)):
+        for _ in range(5):
+            frame(refine)
+        reps = 50
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            g = frame(refine)
+        out_frame[name] = (time.perf_counter() - t0) * 1e3 / reps
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
     t0 = time.perf_counter()
-    reps = 50
-    for _ in range(reps):
-        frame()
-    ms_frame = (time.perf_counter() - t0) * 1e3 / reps
-    res["single_frame"] = {"ms_per_frame": ms_frame,
-                           "what": "host C ABI: 2 image uploads + 2x trackWithPrior(2000 feat) + stereo pose GN "
-                                   "(2000 pts), wall clock incl. all copies and syncs"}
+    creps = 3
+    for _ in range(creps):
+        o = ostep.stereo_track_step(fp["L0"], fp["L1"], fp["R1"], *args, do_scale_refine=False)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / creps
+    res["single_frame"] = {"ms_per_frame": out_frame["track_plus_pose"], "ms_per_frame_with_scale_refine": out_frame["with_scale_refine"],
+                           "features": NFEAT, "survivors": int(len(g["index"])),
+                           "cpu_ms_per_frame": cpu_ms, "cpu_cores": os.cpu_count() or 1,
+                           "what": "vo_stereo_track_step (host buffers): 2 image uploads + prior + 2x trackWithPrior (2000 feat, "
+                                   "4 levels, win 21) [+ trackWithScale] + stereo pose GN + compactions, wall clock incl. all "
+                                   "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
     return res
 
 

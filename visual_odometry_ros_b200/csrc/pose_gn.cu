@@ -90,9 +90,11 @@ __device__ void se3exp_f(const float *xi, float *T)
         a = 1.f; b = 0.5f; c = 0.33333333333333333333333333f;
     } else {
         const double th = (double)theta;
-        a = (float)(sin(th) / th);
-        b = (float)((1 - cos(th)) / (double)(theta * theta));
-        c = (float)((th - sin(th)) / (double)(theta * theta * theta));
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        a = (float)(sn / th);
+        b = (float)((1 - cs) / (double)(theta * theta));
+        c = (float)((th - sn) / (double)(theta * theta * theta));
     }
     float V[9];
     for (int i = 0; i < 9; ++i) {
@@ -105,51 +107,114 @@ __device__ void se3exp_f(const float *xi, float *T)
     T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
 }
 
-// Eigen::LDLT<Matrix<float,6,6>,Lower> (diagonal pivoting, unblocked) + solve.
-__device__ void ldlt6_solve(float *m /*6x6 row-major sym, destroyed*/, const float *b, float *x)
+// Eigen::LDLT<Matrix<float,6,6>,Lower> (diagonal pivoting, unblocked) + solve, with the matrix held
+// in REGISTERS: every loop has compile-time bounds and the data-dependent pivot swap is expressed as
+// a chain of compile-time (k, b) swap routines, so no element is ever addressed dynamically (the
+// first version kept the matrix in local memory and its serial latency chain cost ~15 us per GN
+// iteration). The arithmetic and its order are exactly those of the oracle's pivoted LDLT.
+struct Sym6 {
+    float m[36];   // full 6x6 row-major; only the lower triangle is referenced after the swaps
+};
+
+template <int K, int B>
+__device__ __forceinline__ void swap_rc(Sym6 &S)
 {
-    const int n = 6;
-    int tr[6];
-#define M(i, j) m[(i) * 6 + (j)]
-    for (int k = 0; k < n; ++k) {
-        int big = k;
-        float bv = fabsf(M(k, k));
-        for (int i = k + 1; i < n; ++i)
-            if (fabsf(M(i, i)) > bv) { bv = fabsf(M(i, i)); big = i; }
-        tr[k] = big;
-        if (big != k) {
-            const int s = n - big - 1;
-            for (int j = 0; j < k; ++j) { const float t = M(k, j); M(k, j) = M(big, j); M(big, j) = t; }
-            for (int i = 0; i < s; ++i) { const float t = M(big + 1 + i, k); M(big + 1 + i, k) = M(big + 1 + i, big); M(big + 1 + i, big) = t; }
-            { const float t = M(k, k); M(k, k) = M(big, big); M(big, big) = t; }
-            for (int i = k + 1; i < big; ++i) { const float t = M(i, k); M(i, k) = M(big, i); M(big, i) = t; }
+    // Eigen ldlt_inplace<Lower>: symmetric swap of rows/cols K and B (B > K) in lower storage
+#define M(i, j) S.m[(i) * 6 + (j)]
+#pragma unroll
+    for (int j = 0; j < K; ++j) { const float t = M(K, j); M(K, j) = M(B, j); M(B, j) = t; }
+#pragma unroll
+    for (int i = B + 1; i < 6; ++i) { const float t = M(i, K); M(i, K) = M(i, B); M(i, B) = t; }
+    { const float t = M(K, K); M(K, K) = M(B, B); M(B, B) = t; }
+#pragma unroll
+    for (int i = K + 1; i < B; ++i) { const float t = M(i, K); M(i, K) = M(B, i); M(B, i) = t; }
+#undef M
+}
+
+template <int K>
+__device__ __forceinline__ int ldlt_step(Sym6 &S)
+{
+#define M(i, j) S.m[(i) * 6 + (j)]
+    // pivot: first index of the largest |diagonal| in K..5
+    int big = K;
+    float bv = fabsf(M(K, K));
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) { const float v = fabsf(M(i, i)); if (v > bv) { bv = v; big = i; } }
+    if (K + 1 < 6 && big == K + 1) swap_rc<K, (K + 1 < 6 ? K + 1 : 5)>(S);
+    if (K + 2 < 6 && big == K + 2) swap_rc<K, (K + 2 < 6 ? K + 2 : 5)>(S);
+    if (K + 3 < 6 && big == K + 3) swap_rc<K, (K + 3 < 6 ? K + 3 : 5)>(S);
+    if (K + 4 < 6 && big == K + 4) swap_rc<K, (K + 4 < 6 ? K + 4 : 5)>(S);
+    if (K + 5 < 6 && big == K + 5) swap_rc<K, (K + 5 < 6 ? K + 5 : 5)>(S);
+    if (K > 0) {
+        float temp[K > 0 ? K : 1];
+#pragma unroll
+        for (int j = 0; j < K; ++j) temp[j] = M(j, j) * M(K, j);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) s += M(K, j) * temp[j];
+        M(K, K) -= s;
+#pragma unroll
+        for (int i = K + 1; i < 6; ++i) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) s2 += M(i, j) * temp[j];
+            M(i, K) -= s2;
         }
-        const int rs = n - k - 1;
-        if (k > 0) {
-            float temp[6];
-            for (int j = 0; j < k; ++j) temp[j] = M(j, j) * M(k, j);
-            float s = 0.f;
-            for (int j = 0; j < k; ++j) s += M(k, j) * temp[j];
-            M(k, k) -= s;
-            for (int i = 0; i < rs; ++i) {
-                float s2 = 0.f;
-                for (int j = 0; j < k; ++j) s2 += M(k + 1 + i, j) * temp[j];
-                M(k + 1 + i, k) -= s2;
-            }
-        }
-        const float akk = M(k, k);
-        if (rs > 0 && fabsf(akk) > 0.f)
-            for (int i = 0; i < rs; ++i) M(k + 1 + i, k) /= akk;
     }
+    const float akk = M(K, K);
+    if (K < 5 && fabsf(akk) > 0.f) {
+#pragma unroll
+        for (int i = K + 1; i < 6; ++i) M(i, K) /= akk;
+    }
+    return big;
+#undef M
+}
+
+__device__ __forceinline__ void swap_dyn(float *y, int k, int b)
+{
+    // y[k] <-> y[b] without dynamic register indexing
+    float yk = 0.f, yb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { if (i == k) yk = y[i]; if (i == b) yb = y[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { if (i == k) y[i] = yb; else if (i == b) y[i] = yk; }
+}
+
+__device__ void ldlt6_solve(float *m_in /*6x6 row-major sym*/, const float *b, float *x)
+{
+    Sym6 S;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) S.m[i] = m_in[i];
+    int tr[6];
+    tr[0] = ldlt_step<0>(S); tr[1] = ldlt_step<1>(S); tr[2] = ldlt_step<2>(S);
+    tr[3] = ldlt_step<3>(S); tr[4] = ldlt_step<4>(S); tr[5] = ldlt_step<5>(S);
+#define M(i, j) S.m[(i) * 6 + (j)]
     float y[6];
-    for (int i = 0; i < n; ++i) y[i] = b[i];
-    for (int k = 0; k < n; ++k) if (tr[k] != k) { const float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-    for (int i = 0; i < n; ++i) { float s = y[i]; for (int j = 0; j < i; ++j) s -= M(i, j) * y[j]; y[i] = s; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = b[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (tr[k] != k) swap_dyn(y, k, tr[k]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        float s = y[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) s -= M(i, j) * y[j];
+        y[i] = s;
+    }
     const float tol = 1.0f / 3.402823466e+38f;
-    for (int i = 0; i < n; ++i) y[i] = fabsf(M(i, i)) > tol ? y[i] / M(i, i) : 0.f;
-    for (int i = n - 1; i >= 0; --i) { float s = y[i]; for (int j = i + 1; j < n; ++j) s -= M(j, i) * y[j]; y[i] = s; }
-    for (int k = n - 1; k >= 0; --k) if (tr[k] != k) { const float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-    for (int i = 0; i < n; ++i) x[i] = y[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = fabsf(M(i, i)) > tol ? y[i] / M(i, i) : 0.f;
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        float s = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) s -= M(j, i) * y[j];
+        y[i] = s;
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; --k) if (tr[k] != k) swap_dyn(y, k, tr[k]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
 #undef M
 }
 

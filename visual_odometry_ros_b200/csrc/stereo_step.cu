@@ -254,6 +254,12 @@ extern "C" int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *pr
     memcpy(d.K_l, prm->K_l, 16); memcpy(d.K_r, prm->K_r, 16);
     d.sampson_y = prm->sampson_y;
 
+    {   // both new images' pyramids (and Scharr planes) in ONE batched launch set
+        const int both[2] = {slot_l1, slot_r1};
+        const int eff = vo_effective_max_level(w, h, prm->window_size, prm->max_level);
+        rc = vo_ensure_pyramids(ctx, both, 2, (eff + 1 < ctx->max_levels ? eff + 1 : ctx->max_levels), 1);
+        if (rc) return rc;
+    }
     k_step_prior<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(d);
     ctx->launches++;
     // [4] l0 -> l1
