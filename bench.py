@@ -149,7 +149,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "features/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16 fixed-point + f32", "data": "synthetic",
-        "config": {"workload": "cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21 (one pair per step)"},
+        "config": {"workload": "cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21; step = pyramids(both) + Scharr + LK",
+                   "reference_sample": "one stereo pair per step (bounded sample of the batched workload)",
+                   "features_per_pair": NFEAT, "window": WIN, "levels": MAXLVL + 1},
         "cpu_baseline": {"value": val, "unit": "features/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -311,7 +313,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": Ke, "api": "vo_ft_track_batch (host buffers)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_klt<14>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_klt2<21,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": klt_bytes_per_step / klt_launches_per_step,
                      "launch_ms": klt_ms / klt_launches_per_step, "launches_per_step": klt_launches_per_step,

@@ -2,8 +2,10 @@
 #include "vo_internal.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #ifndef VO_VERSION
 #define VO_VERSION "0.1.0"
@@ -118,6 +120,8 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     for (int i = 0; i < 4; ++i) if (ctx->d_f32[i]) cudaFree(ctx->d_f32[i]);
     if (ctx->d_lba) cudaFree(ctx->d_lba);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VO_OK;
@@ -190,8 +194,10 @@ static int slot_set_geometry(vo_ctx *ctx, int slot, int w, int h)
     return VO_OK;
 }
 
-static int set_image_common(vo_ctx *ctx, int slot, const uint8_t *data, int w, int h, size_t step, cudaMemcpyKind kind)
+static int set_image_common(vo_ctx *ctx, int slot, const uint8_t *data, int w, int h, size_t step, cudaMemcpyKind kind,
+                            cudaStream_t st = nullptr)
 {
+    if (ctx && !st) st = ctx->stream;
     if (!ctx) return VO_ERR_INVALID_ARG;
     VO_REQUIRE(slot >= 0 && slot < ctx->n_slots, VO_ERR_INVALID_ARG, "slot id out of range");
     VO_REQUIRE(data && w >= 8 && h >= 8 && step >= (size_t)w, VO_ERR_INVALID_ARG, "bad image arguments");
@@ -203,8 +209,8 @@ static int set_image_common(vo_ctx *ctx, int slot, const uint8_t *data, int w, i
     // DMA into the dense raw staging area (one contiguous copy when the source is dense);
     // the ingest kernel moves it into the padded level-0 plane when the pyramid is built.
     uint8_t *raw = ctx->raw_base + (size_t)slot * ctx->raw_stride;
-    if (step == (size_t)w) VO_CUDA(cudaMemcpyAsync(raw, data, (size_t)w * h, kind, ctx->stream));
-    else VO_CUDA(cudaMemcpy2DAsync(raw, w, data, step, w, h, kind, ctx->stream));
+    if (step == (size_t)w) VO_CUDA(cudaMemcpyAsync(raw, data, (size_t)w * h, kind, st));
+    else VO_CUDA(cudaMemcpy2DAsync(raw, w, data, step, w, h, kind, st));
     S.levels_built = 0; S.deriv_built = 0; S.border0 = false; S.raw_pending = true;
     return VO_OK;
 }
@@ -399,7 +405,8 @@ extern "C" int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int sl
 // Upload a list of images; consecutive slots fed from consecutive dense host images are merged
 // into ONE contiguous DMA (the raw staging areas of consecutive slots are adjacent when the
 // image fills max_w x max_h), which is what reaches full PCIe bandwidth.
-static int upload_many(vo_ctx *ctx, int n, const int *slots, const uint8_t *const *imgs, int w, int h, size_t step)
+static int upload_many(vo_ctx *ctx, int n, const int *slots, const uint8_t *const *imgs, int w, int h, size_t step,
+                       cudaStream_t st)
 {
     if (!imgs) return VO_OK;
     const size_t img_bytes = (size_t)w * h;
@@ -418,9 +425,9 @@ static int upload_many(vo_ctx *ctx, int n, const int *slots, const uint8_t *cons
                 S.levels_built = 0; S.deriv_built = 0; S.border0 = false; S.raw_pending = true;
             }
             VO_CUDA(cudaMemcpyAsync(ctx->raw_base + (size_t)slots[i] * ctx->raw_stride, imgs[i], img_bytes * (j - i),
-                                    cudaMemcpyHostToDevice, ctx->stream));
+                                    cudaMemcpyHostToDevice, st));
         } else {
-            int rc = vo_upload_image(ctx, slots[i], imgs[i], w, h, step);
+            int rc = set_image_common(ctx, slots[i], imgs[i], w, h, step, cudaMemcpyHostToDevice, st);
             if (rc) return rc;
         }
         i = j;
@@ -439,10 +446,6 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     VO_REQUIRE(slots0 && slots1 && pts0 && pts_track_inout && mask_inout, VO_ERR_INVALID_ARG, "null pointer");
     VO_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    rc = upload_many(ctx, n_pairs, slots0, imgs0, w, h, step);
-    if (rc) return rc;
-    rc = upload_many(ctx, n_pairs, slots1, imgs1, w, h, step);
-    if (rc) return rc;
     const size_t N = (size_t)n_pairs * n;
     // staging: [pts0 N*8][pts1 N*8][err N*4][status N][mask N]
     const size_t o_p0 = 0, o_p1 = o_p0 + N * 8, o_err = o_p1 + N * 8, o_st = o_err + N * 4, o_mask = o_st + align_up(N, 16);
@@ -455,14 +458,46 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     memcpy(hs + o_mask, mask_inout, N);
     VO_CUDA(cudaMemcpyAsync(d, hs, with_prior ? N * 16 : N * 8, cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA(cudaMemcpyAsync(d + o_mask, hs + o_mask, N, cudaMemcpyHostToDevice, ctx->stream));
+    // Chunked software pipeline: the image DMA of chunk c+1 (copy stream) overlaps the pyramid + LK
+    // kernels of chunk c (compute stream). Slots of different chunks are disjoint, so the only
+    // dependency is "chunk c's kernels wait for chunk c's upload" (one event per chunk).
+    if (!ctx->copy_stream) VO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // chunk sizes ramp up (8, 16, then CH pairs) so the pipeline fills after a short first DMA
+    static const int CH = getenv("VO_BATCH_CHUNK") ? atoi(getenv("VO_BATCH_CHUNK")) : 32;
+    std::vector<int> chunk_begin;
+    for (int c0 = 0, sz = 8; c0 < n_pairs; ) {
+        chunk_begin.push_back(c0);
+        c0 += sz < CH ? sz : CH;
+        sz *= 2;
+    }
+    chunk_begin.push_back(n_pairs);
+    const int n_chunks = (int)chunk_begin.size() - 1;
+    while ((int)ctx->events.size() < n_chunks + 1) {
+        cudaEvent_t e;
+        VO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    // the uploads must not overtake work already queued on the compute stream that still reads these slots
+    VO_CUDA(cudaEventRecord(ctx->events[n_chunks], ctx->stream));
+    VO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->events[n_chunks], 0));
     KltPost post{};
     post.mode = with_prior ? 2 : 1;
     post.thres_err = thres_err;
-    post.mask = d + o_mask;
-    rc = vo_klt_launch(ctx, n_pairs, slots0, slots1, (const float *)(d + o_p0), n, window_size, max_pyr_lvl,
-                       with_prior ? VO_KLT_USE_INITIAL_FLOW : 0, (float *)(d + o_p1), d + o_st, (float *)(d + o_err),
-                       nullptr, &post);
-    if (rc) return rc;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int c0 = chunk_begin[c], nc = chunk_begin[c + 1] - c0;
+        rc = upload_many(ctx, nc, slots0 + c0, imgs0 ? imgs0 + c0 : nullptr, w, h, step, ctx->copy_stream);
+        if (rc) return rc;
+        rc = upload_many(ctx, nc, slots1 + c0, imgs1 ? imgs1 + c0 : nullptr, w, h, step, ctx->copy_stream);
+        if (rc) return rc;
+        VO_CUDA(cudaEventRecord(ctx->events[c], ctx->copy_stream));
+        VO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[c], 0));
+        const size_t off = (size_t)c0 * n;
+        post.mask = d + o_mask + off;
+        rc = vo_klt_launch(ctx, nc, slots0 + c0, slots1 + c0, (const float *)(d + o_p0) + 2 * off, n, window_size, max_pyr_lvl,
+                           with_prior ? VO_KLT_USE_INITIAL_FLOW : 0, (float *)(d + o_p1) + 2 * off, d + o_st + off,
+                           (float *)(d + o_err) + off, nullptr, &post);
+        if (rc) return rc;
+    }
     VO_CUDA(cudaMemcpyAsync(hs + o_p1, d + o_p1, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaMemcpyAsync(hs + o_mask, d + o_mask, N, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));

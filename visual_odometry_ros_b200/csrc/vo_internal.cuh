@@ -50,6 +50,8 @@ struct vo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;      // image DMA overlapped with compute in the batched entry points
+    std::vector<cudaEvent_t> events;
     int max_w = 0, max_h = 0, n_slots = 0, max_feat = 0;
     std::vector<Slot> slots;
     SlotDesc *d_slots = nullptr;   // device mirror of all slot descriptors
