@@ -194,6 +194,50 @@ VO_API int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *prm, i
                          float *T_wc_out, float *dT_pc_out, int *n_out, int *index_out,
                          float *pts_l1_out, float *pts_r1_out, int *counts_out);
 
+/* ------------------------------------------------------------------ feature extraction (bucketed)
+ * FeatureExtractor::updateWeightBin(pts_occupied) + extractORBwithBinning_fast(img)
+ * (core/visual_odometry/feature_extractor.cpp:94-98, 211-282; WeightBin feature_extractor.h:56-134): bins that hold
+ * an occupied point are skipped, every other bin returns its best-response keypoint, in bin-index order.
+ * The response is NOT cv::ORB's (third-party): it is the exact-integer Harris response on the slot's resident
+ * Scharr plane defined in DESIGN.md ("K-det"); edge = border without detections (ORB edgeThreshold, 31). */
+VO_API int vo_detect_bucketed(vo_ctx *ctx, int slot, const float *pts_occupied, int n_occupied, int n_bins_u,
+                       int n_bins_v, int edge, long long min_score, float *pts_out, int max_out, int *n_out);
+
+/* ------------------------------------------------------------------ stereo frame step (tracking + new features)
+ * vo_stereo_track_step followed, on the same stream and before the single synchronisation, by step [10] of
+ * StereoVO::trackStereoImages (stereo_vo.cpp:690-740): bucketed detection on the current left image with the
+ * survivors as occupancy, trackBidirection(l1 -> r1) of the detected points (feature_tracker.cpp:39-86), DLT of
+ * every match (triangulate_3d.cpp:91-130) and the `both depths > 0` gate, stable compaction.
+ * n == 0 with new_depth_gate == 0 is the first frame (stereo_vo.cpp:850-883): detection + bidirectional match only
+ * (slot_l0, T_wp, dT_pc_prev may then be -1 / NULL).  n_bins_u * n_bins_v == 0 disables the new-feature stage. */
+typedef struct vo_stereo_frame_params {
+    vo_stereo_step_params track;
+    float thres_bidirection;         /* feature_tracker.thres_bidirection */
+    int n_bins_u, n_bins_v;          /* feature_extractor.n_bins_u / n_bins_v */
+    int det_edge;                    /* 31 */
+    long long det_min_score;         /* candidates need score > det_min_score */
+    int new_depth_gate;              /* 1: keep a new feature only if both DLT depths are > 0 (stereo_vo.cpp:725) */
+} vo_stereo_frame_params;
+typedef struct vo_stereo_frame_result {
+    float *T_wc, *dT_pc;             /* [16] row-major each */
+    int n_tracked;                   /* survivors of the tracking step */
+    int *index;                      /* [n] original index of every survivor */
+    float *pts_l1, *pts_r1;          /* [n][2] */
+    int *counts;                     /* [5] nullable, as vo_stereo_track_step */
+    int n_detected;                  /* points returned by the detector */
+    int n_new;                       /* new features that passed the bidirectional match (and the depth gate) */
+    float *new_l1, *new_r1;          /* [n_bins_u * n_bins_v][2] */
+} vo_stereo_frame_result;
+VO_API int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *prm, int slot_l0, int slot_l1, int slot_r1,
+                         const uint8_t *img_l1, const uint8_t *img_r1, int w, int h, size_t step, int n,
+                         const float *pts_l0, const float *pts_r0, const float *Xw, const uint8_t *triangulated,
+                         const float *T_wp, const float *dT_pc_prev, vo_stereo_frame_result *res);
+/* Keyframe / first-frame reconstruction (stereo_vo.cpp:767-797, 911-941): DLT of every stereo match, 1-px^2
+ * reprojection gates in both images (Camera::projectToPixel, camera.cpp:208-213), both depths > 0;
+ * Xw_out = T_wc * X_left for every point, ok_out = 1 where all gates pass. */
+VO_API int vo_stereo_reconstruct(vo_ctx *ctx, const float *pts_l, const float *pts_r, int n, const float *K_l4,
+                          const float *K_r4, const float *T_lr, const float *T_wc, float *Xw_out, uint8_t *ok_out);
+
 /* ------------------------------------------------------------------ triangulation
  * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */
 VO_API int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,

@@ -1,0 +1,104 @@
+"""S1 over a sequence: the fused stereo frame step (tracking + new features), K-det and the keyframe reconstruction
+against the oracle composition of StereoVO::trackStereoImages (stereo_vo.cpp:392-989), teacher-forced: every frame
+the C ABI gets the oracle's own previous-frame state, so one borderline feature cannot snowball."""
+import numpy as np
+import pytest
+
+from oracle import detect as odet
+from oracle import stereo_vo as osvo
+from visual_odometry_ros_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+W, H = synth.SMALL_W, synth.SMALL_H
+NB_U, NB_V = 32, 12
+
+
+@pytest.fixture(scope="module")
+def seq():
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    L, R, T = synth.stereo_sequence(10, W, H, synth.small_K(), seed=3003, device=dev)
+    return L, R, T
+
+
+def _rot_angle(Ra, Rb):
+    dR = Ra.astype(np.float64) @ Rb.astype(np.float64).T
+    return float(np.arcsin(min(1.0, np.linalg.norm(dR - dR.T) / (2.0 * np.sqrt(2.0)))))
+
+
+def test_detect_bucketed_bit_exact(seq):
+    L, R, T = seq
+    ctx = capi.Context(device=0, max_w=W, max_h=H, n_slots=2, max_feat=4096)
+    rng = np.random.default_rng(5)
+    for k, (nbu, nbv, nocc) in enumerate([(32, 12, 0), (32, 12, 150), (24, 12, 60), (50, 16, 300), (7, 5, 3)]):
+        img = L[k % len(L)]
+        occ = np.stack([rng.uniform(0, W, nocc), rng.uniform(0, H, nocc)], 1).astype(np.float32)
+        ctx.upload_image(0, img)
+        got = ctx.detect_bucketed(0, occ, nbu, nbv, 31, 0)
+        ref = odet.detect_bucketed(img, occ, nbu, nbv, 31, 0)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (nbu, nbv, nocc)
+        assert len(ref) > 0
+    # min_score gate and the high-threshold "nothing found" case
+    ref = odet.detect_bucketed(L[0], np.zeros((0, 2)), 32, 12, 31, 10 ** 9)
+    got = ctx.detect_bucketed(0 if ctx.upload_image(0, L[0]) is None else 0, np.zeros((0, 2)), 32, 12, 31, 10 ** 9)
+    assert np.array_equal(got, ref)
+    assert len(ctx.detect_bucketed(0, np.zeros((0, 2)), 32, 12, 31, 2 ** 60)) == 0
+    ctx.close()
+
+
+def test_frame_step_sequence_teacher_forced(seq):
+    L, R, T = seq
+    K, Tlr = synth.small_K(), synth.kitti_T_lr()
+    prm = osvo.default_params(n_bins_u=NB_U, n_bins_v=NB_V, kf_trans=2.0)
+    vo = osvo.StereoVOOracle(W, H, K, K, Tlr, prm)
+    ctx = capi.Context(device=0, max_w=W, max_h=H, n_slots=4, max_feat=4096)
+    agree_idx, total_idx = 0, 0
+    px_ok = px_tot = frames_cmp = frames_new_equal = 0
+    n_kf = 0
+    for k in range(len(L)):
+        Twc_o, info = vo.track(L[k], R[k])
+        dbg = vo.dbg
+        sl, sr, sp = 2 * (k % 2), 2 * (k % 2) + 1, 2 * ((k + 1) % 2)
+        common = dict(K_l=K, K_r=K, T_lr=Tlr, win=prm["window_size"], max_level=prm["max_level"], thres_err=prm["thres_error"],
+                      thres_poseba=prm["thres_poseba_error"], thres_bi=prm["thres_bidirection"], n_bins_u=NB_U, n_bins_v=NB_V)
+        if k == 0:
+            g = ctx.stereo_frame_step(-1, sl, sr, L[k], R[k], np.zeros((0, 2)), np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0),
+                                      None, None, new_depth_gate=False, **common)
+            assert g["n_detected"] == len(dbg["pts_new"])
+            assert np.array_equal(g["new_l1"], dbg["new_l"])
+            assert np.abs(g["new_r1"] - dbg["new_r"]).max() <= 0.01
+            Xw, ok = ctx.stereo_reconstruct(dbg["new_l"], dbg["new_r"], K, K, Tlr, np.eye(4))
+            assert np.array_equal(ok, dbg["ok_recon"])
+            assert np.array_equal(Xw[ok], dbg["Xw_recon"][ok])          # same FP32 operation order -> bit-exact
+            continue
+        g = ctx.stereo_frame_step(sp, sl, sr, L[k], R[k], dbg["pts_l0"], dbg["pts_r0"], dbg["Xw"], dbg["tri"], dbg["T_wp"],
+                                  dbg["dT_prev"], **common)
+        st = dbg["step"]
+        inter = np.intersect1d(g["index"], st["index"])
+        agree_idx += len(inter)
+        total_idx += max(len(g["index"]), len(st["index"]))
+        if np.array_equal(g["index"], st["index"]):
+            # the pose is solved from pixel inputs that agree to ~1e-4 px, not from identical inputs: the bound is the
+            # propagated pixel tolerance with a few hundred points (identical-input parity is 1e-6, tests/test_pose_gpu.py)
+            dt = np.linalg.norm(g["dT_pc"][:3, 3].astype(np.float64) - st["dT_pc"][:3, 3])
+            dang = _rot_angle(g["dT_pc"][:3, :3], st["dT_pc"][:3, :3])
+            print(f"frame {k}: n={len(st['index'])} dT {dt:.2e} m {dang:.2e} rad, new {len(g['new_l1'])}")
+            assert dt <= 5e-5 and dang <= 5e-6
+            assert np.abs(g["T_wc"] - st["T_wc"]).max() <= 1e-4
+            d = np.concatenate([np.abs(g["pts_l1"] - st["pts_l1"]).max(1), np.abs(g["pts_r1"] - st["pts_r1"]).max(1)])
+            px_ok += int((d <= 0.01).sum()); px_tot += len(d)
+            assert d.max() <= 0.05                       # an LK stop-test flip moves a point by about one last step
+            assert g["counts"] == st["counts"]
+            # new features: the occupancy is the same set of survivors (positions within 0.01 px) -> same detections
+            frames_cmp += 1
+            if (g["n_detected"] == len(dbg["pts_new"]) and len(g["new_l1"]) == len(dbg["new_l"])
+                    and np.array_equal(g["new_l1"], dbg["new_l"]) and np.abs(g["new_r1"] - dbg["new_r"]).max() <= 0.01):
+                frames_new_equal += 1
+        if info["keyframe"]:
+            n_kf += 1
+    assert agree_idx >= 0.999 * total_idx, (agree_idx, total_idx)
+    assert px_ok >= 0.999 * px_tot, (px_ok, px_tot)          # tracked positions within 0.01 px
+    assert frames_cmp >= 5 and frames_new_equal >= frames_cmp - 1, (frames_new_equal, frames_cmp)
+    assert n_kf >= 2
+    ctx.close()

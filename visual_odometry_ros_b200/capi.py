@@ -50,6 +50,17 @@ class StereoStepParams(ctypes.Structure):
                 ("T_lr", ctypes.c_float * 16), ("do_scale_refine", ctypes.c_int), ("sampson_y", ctypes.c_float)]
 
 
+class StereoFrameParams(ctypes.Structure):
+    _fields_ = [("track", StereoStepParams), ("thres_bidirection", ctypes.c_float), ("n_bins_u", ctypes.c_int),
+                ("n_bins_v", ctypes.c_int), ("det_edge", ctypes.c_int), ("det_min_score", ctypes.c_longlong),
+                ("new_depth_gate", ctypes.c_int)]
+
+
+class StereoFrameResult(ctypes.Structure):
+    _fields_ = [("T_wc", vp), ("dT_pc", vp), ("n_tracked", ctypes.c_int), ("index", vp), ("pts_l1", vp), ("pts_r1", vp),
+                ("counts", vp), ("n_detected", ctypes.c_int), ("n_new", ctypes.c_int), ("new_l1", vp), ("new_r1", vp)]
+
+
 class LbaProblem(ctypes.Structure):
     _fields_ = [
         ("n_frames", ctypes.c_int), ("n_opt", ctypes.c_int), ("n_points", ctypes.c_int), ("n_obs", ctypes.c_int),
@@ -112,6 +123,12 @@ def lib():
     L.vo_stereo_track_step.argtypes = [vp, ctypes.POINTER(StereoStepParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp,
                                        c_int_p, vp, vp, vp, vp]
+    L.vo_detect_bucketed.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_longlong, vp, ctypes.c_int, c_int_p]
+    L.vo_stereo_frame_step.argtypes = [vp, ctypes.POINTER(StereoFrameParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, vp,
+                                       ctypes.POINTER(StereoFrameResult)]
+    L.vo_stereo_reconstruct.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -434,3 +451,75 @@ class Context:
         k = n_out.value
         return dict(T_wc=T_wc, dT_pc=dT, index=idx[:k].copy(), pts_l1=o_l1[:k].copy(), pts_r1=o_r1[:k].copy(),
                     counts=[int(c) for c in counts])
+
+    @staticmethod
+    def _step_params(K_l, K_r, T_lr, win, max_level, thres_err, thres_poseba, do_scale_refine, sampson_y):
+        prm = StereoStepParams()
+        prm.window_size, prm.max_level, prm.thres_error, prm.thres_poseba_error = int(win), int(max_level), float(thres_err), float(thres_poseba)
+        prm.K_l = (ctypes.c_float * 4)(*[float(v) for v in K_l])
+        prm.K_r = (ctypes.c_float * 4)(*[float(v) for v in K_r])
+        prm.T_lr = (ctypes.c_float * 16)(*[float(v) for v in np.asarray(T_lr, np.float32).ravel()])
+        prm.do_scale_refine = 1 if do_scale_refine else 0
+        prm.sampson_y = float(sampson_y)
+        return prm
+
+    def detect_bucketed(self, slot, pts_occupied, n_bins_u, n_bins_v, edge=31, min_score=0):
+        """FeatureExtractor::updateWeightBin + extractORBwithBinning_fast with the K-det response."""
+        occ = np.ascontiguousarray(pts_occupied, np.float32).reshape(-1, 2)
+        cap = n_bins_u * n_bins_v
+        out = np.zeros((cap, 2), np.float32)
+        n = ctypes.c_int(0)
+        check(self.h, self.L.vo_detect_bucketed(self.h, slot, _ptr(occ) if len(occ) else None, len(occ), n_bins_u, n_bins_v, edge,
+                                                int(min_score), _ptr(out), cap, ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    def stereo_reconstruct(self, pts_l, pts_r, K_l, K_r, T_lr, T_wc):
+        """stereo_vo.cpp:767-797: DLT + reprojection / depth gates + X_w = T_wc X_l. Returns (Xw, ok)."""
+        pl = np.ascontiguousarray(pts_l, np.float32).reshape(-1, 2)
+        pr = np.ascontiguousarray(pts_r, np.float32).reshape(-1, 2)
+        n = len(pl)
+        Xw = np.zeros((n, 3), np.float32)
+        ok = np.zeros(n, np.uint8)
+        Kl, Kr = np.ascontiguousarray(K_l, np.float32), np.ascontiguousarray(K_r, np.float32)
+        Tlr, Twc = np.ascontiguousarray(T_lr, np.float32), np.ascontiguousarray(T_wc, np.float32)
+        check(self.h, self.L.vo_stereo_reconstruct(self.h, _ptr(pl), _ptr(pr), n, _ptr(Kl), _ptr(Kr), _ptr(Tlr), _ptr(Twc), _ptr(Xw), _ptr(ok)))
+        return Xw, ok.astype(bool)
+
+    def stereo_frame_step(self, slot_l0, slot_l1, slot_r1, img_l1, img_r1, pts_l0, pts_r0, Xw, tri, T_wp, dT_pc_prev,
+                          K_l, K_r, T_lr, win, max_level, thres_err, thres_poseba, thres_bi, n_bins_u, n_bins_v, det_edge=31,
+                          det_min_score=0, new_depth_gate=True, do_scale_refine=True, sampson_y=660.0, want_counts=True):
+        """Tracking step + new-feature stage of StereoVO::trackStereoImages (stereo_vo.cpp:475-740), one synchronisation."""
+        fp = StereoFrameParams()
+        fp.track = self._step_params(K_l, K_r, T_lr, win, max_level, thres_err, thres_poseba, do_scale_refine, sampson_y)
+        fp.thres_bidirection, fp.n_bins_u, fp.n_bins_v, fp.det_edge = float(thres_bi), int(n_bins_u), int(n_bins_v), int(det_edge)
+        fp.det_min_score, fp.new_depth_gate = int(det_min_score), 1 if new_depth_gate else 0
+        l0 = np.ascontiguousarray(pts_l0, np.float32).reshape(-1, 2)
+        r0 = np.ascontiguousarray(pts_r0, np.float32).reshape(-1, 2)
+        X = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(tri).astype(np.uint8)
+        n = len(l0)
+        Twp = np.ascontiguousarray(T_wp if T_wp is not None else np.eye(4), np.float32)
+        dTp = np.ascontiguousarray(dT_pc_prev if dT_pc_prev is not None else np.eye(4), np.float32)
+        T_wc, dT = np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)
+        idx = np.zeros(max(n, 1), np.int32)
+        o_l1, o_r1 = np.zeros((max(n, 1), 2), np.float32), np.zeros((max(n, 1), 2), np.float32)
+        nbins = max(1, n_bins_u * n_bins_v)
+        n_l1, n_r1 = np.zeros((nbins, 2), np.float32), np.zeros((nbins, 2), np.float32)
+        counts = np.zeros(5, np.int32)
+        res = StereoFrameResult()
+        res.T_wc, res.dT_pc, res.index, res.pts_l1, res.pts_r1 = _ptr(T_wc), _ptr(dT), _ptr(idx), _ptr(o_l1), _ptr(o_r1)
+        res.counts = _ptr(counts) if want_counts else None
+        res.new_l1, res.new_r1 = _ptr(n_l1), _ptr(n_r1)
+        w = h = step = 0
+        for im in (img_l1, img_r1):
+            if im is not None:
+                assert im.dtype == np.uint8 and im.ndim == 2 and im.strides[1] == 1
+                h, w, step = im.shape[0], im.shape[1], im.strides[0]
+        if w == 0:
+            raise ValueError("pass the new images")
+        check(self.h, self.L.vo_stereo_frame_step(
+            self.h, ctypes.byref(fp), slot_l0, slot_l1, slot_r1, _ptr(img_l1), _ptr(img_r1), w, h, step, n, _ptr(l0), _ptr(r0),
+            _ptr(X), _ptr(t), _ptr(Twp), _ptr(dTp), ctypes.byref(res)))
+        k, m = res.n_tracked, res.n_new
+        return dict(T_wc=T_wc, dT_pc=dT, index=idx[:k].copy(), pts_l1=o_l1[:k].copy(), pts_r1=o_r1[:k].copy(),
+                    counts=[int(c) for c in counts], n_detected=res.n_detected, new_l1=n_l1[:m].copy(), new_r1=n_r1[:m].copy())

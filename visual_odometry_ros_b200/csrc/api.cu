@@ -120,6 +120,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     for (int i = 0; i < 4; ++i) if (ctx->d_f32[i]) cudaFree(ctx->d_f32[i]);
     if (ctx->d_lba) cudaFree(ctx->d_lba);
+    if (ctx->d_det) cudaFree(ctx->d_det);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -17,6 +17,7 @@
 // list is compacted once at the end -- results and indexing are identical, with two scans instead of five
 // reallocations.  Compiled with -fmad=false (FP32 glue arithmetic in the reference's operation order).
 #include "vo_internal.cuh"
+#include "tri_device.cuh"
 
 #include <cstring>
 
@@ -171,6 +172,76 @@ __global__ void __launch_bounds__(1024) k_step_count(const uint8_t *mask, int n,
     if (threadIdx.x == 0) *out = s;
 }
 
+// ------------------------------------------------------------------------------ new features / reconstruction
+// [10] stereo_vo.cpp:706-739 (and the first frame, :871-903): after the bidirectional L->R match of the freshly
+// detected points, keep those whose mask survived and -- in the steady state -- whose two DLT depths are positive;
+// stable compaction.  One CTA (a frame adds at most n_bins points).
+struct NewDev {
+    const float2 *pl, *pr;
+    const uint8_t *mask;
+    const int *n_in;             // device count of detected points
+    int depth_gate;
+    float R_rl[9], t_rl[3], K_l[4], K_r[4];
+    float2 *out_l, *out_r;
+    int *n_out;
+};
+
+__global__ void __launch_bounds__(1024) k_new_gate(const NewDev d)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int n = *d.n_in;
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        bool keep = i < n && d.mask[i];
+        if (keep && d.depth_gate) {
+            float Xl[3], Xr[3];
+            tri_point(d.pl[i], d.pr[i], d.R_rl, d.t_rl, d.K_l, d.K_r, Xl, Xr);
+            keep = Xl[2] > 0.f && Xr[2] > 0.f;
+        }
+        const int pos = scan_chunk(keep, s_warp, &s_base);
+        if (keep) { d.out_l[pos] = d.pl[i]; d.out_r[pos] = d.pr[i]; }
+    }
+    if (threadIdx.x == 0) *d.n_out = s_base;
+}
+
+// Keyframe / first-frame reconstruction (stereo_vo.cpp:767-797, :911-941): DLT, 1-px^2 reprojection gates on both
+// images, both depths positive, X_w = T_wc * X_l.
+struct ReconDev {
+    const float2 *pl, *pr;
+    int n;
+    float R_rl[9], t_rl[3], K_l[4], K_r[4], T_wc[12];
+    float *Xw;
+    uint8_t *ok;
+};
+
+__global__ void __launch_bounds__(128) k_reconstruct(const ReconDev d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const float2 p0 = d.pl[i], p1 = d.pr[i];
+    float Xl[3], Xr[3];
+    tri_point(p0, p1, d.R_rl, d.t_rl, d.K_l, d.K_r, Xl, Xr);
+    bool ok = true;
+    {
+        const float invz = 1.0f / Xl[2];                                   // Camera::projectToPixel (camera.cpp:208-213)
+        const float dx = p0.x - (d.K_l[0] * Xl[0] * invz + d.K_l[2]), dy = p0.y - (d.K_l[1] * Xl[1] * invz + d.K_l[3]);
+        if (dx * dx + dy * dy > 1.0f) ok = false;
+    }
+    {
+        const float invz = 1.0f / Xr[2];
+        const float dx = p1.x - (d.K_r[0] * Xr[0] * invz + d.K_r[2]), dy = p1.y - (d.K_r[1] * Xr[1] * invz + d.K_r[3]);
+        if (dx * dx + dy * dy > 1.0f) ok = false;
+    }
+    if (!(Xl[2] > 0.f && Xr[2] > 0.f)) ok = false;
+    float Xw[3];
+    xform(d.T_wc, Xl, Xw);
+    d.Xw[3 * i] = Xw[0]; d.Xw[3 * i + 1] = Xw[1]; d.Xw[3 * i + 2] = Xw[2];
+    d.ok[i] = ok ? 1 : 0;
+}
+
 static void inv_se3_f(const float *T, float *O)
 {
     for (int i = 0; i < 3; ++i) {
@@ -189,32 +260,66 @@ static void mul4_f(const float *A, const float *B, float *C)
 }
 static size_t a16(size_t v) { return (v + 15) / 16 * 16; }
 
-extern "C" int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *prm, int slot_l0, int slot_l1, int slot_r1,
+int vo_detect_launch_d(vo_ctx *ctx, int slot, const float *occ_d, const int *n_occ_d, int n_occ, int n_bins_u, int n_bins_v,
+                       int edge, long long min_score, float *out_d, uint8_t *out_mask_d, int *n_out_d, int max_out);
+
+extern "C" int vo_stereo_reconstruct(vo_ctx *ctx, const float *pts_l, const float *pts_r, int n, const float *K_l4, const float *K_r4,
+                                     const float *T_lr, const float *T_wc, float *Xw_out, uint8_t *ok_out)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(pts_l && pts_r && K_l4 && K_r4 && T_lr && T_wc && Xw_out && ok_out, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n, o_l = 0, o_r = N * 8, o_X = N * 16, o_ok = o_X + a16(N * 12), total = o_ok + a16(N);
+    int rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *dv = ctx->d_stage;
+    memcpy(h + o_l, pts_l, N * 8); memcpy(h + o_r, pts_r, N * 8);
+    VO_CUDA(cudaMemcpyAsync(dv, h, N * 16, cudaMemcpyHostToDevice, ctx->stream));
+    ReconDev d;
+    d.pl = (const float2 *)(dv + o_l); d.pr = (const float2 *)(dv + o_r); d.n = n;
+    float T_rl[16];
+    inv_se3_f(T_lr, T_rl);
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) d.R_rl[r * 3 + c] = T_rl[r * 4 + c]; d.t_rl[r] = T_rl[r * 4 + 3]; }
+    memcpy(d.K_l, K_l4, 16); memcpy(d.K_r, K_r4, 16); memcpy(d.T_wc, T_wc, 48);
+    d.Xw = (float *)(dv + o_X); d.ok = dv + o_ok;
+    k_reconstruct<<<vo_div_up(n, 128), 128, 0, ctx->stream>>>(d);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h + o_X, dv + o_X, total - o_X, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(Xw_out, h + o_X, N * 12);
+    memcpy(ok_out, h + o_ok, N);
+    return VO_OK;
+}
+
+extern "C" int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *fp, int slot_l0, int slot_l1, int slot_r1,
                                     const uint8_t *img_l1, const uint8_t *img_r1, int w, int h, size_t step, int n,
                                     const float *pts_l0, const float *pts_r0, const float *Xw, const uint8_t *triangulated,
-                                    const float *T_wp, const float *dT_pc_prev, float *T_wc_out, float *dT_pc_out, int *n_out,
-                                    int *index_out, float *pts_l1_out, float *pts_r1_out, int *counts_out)
+                                    const float *T_wp, const float *dT_pc_prev, vo_stereo_frame_result *res)
 {
-    if (!ctx || !prm) return VO_ERR_INVALID_ARG;
+    if (!ctx || !fp || !res) return VO_ERR_INVALID_ARG;
+    const vo_stereo_step_params *prm = &fp->track;
     VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
-    VO_REQUIRE(T_wp && dT_pc_prev && T_wc_out && dT_pc_out && n_out, VO_ERR_INVALID_ARG, "null pointer");
-    VO_REQUIRE(n == 0 || (pts_l0 && pts_r0 && Xw && triangulated && index_out && pts_l1_out && pts_r1_out), VO_ERR_INVALID_ARG, "null pointer");
+    VO_REQUIRE(n == 0 || (T_wp && dT_pc_prev && res->T_wc && res->dT_pc), VO_ERR_INVALID_ARG, "null pointer");
+    VO_REQUIRE(n == 0 || (pts_l0 && pts_r0 && Xw && triangulated && res->index && res->pts_l1 && res->pts_r1), VO_ERR_INVALID_ARG, "null pointer");
+    const int nb = fp->n_bins_u > 0 && fp->n_bins_v > 0 ? fp->n_bins_u * fp->n_bins_v : 0;
+    VO_REQUIRE(nb == 0 || (res->new_l1 && res->new_r1), VO_ERR_INVALID_ARG, "null pointer");
     VO_CUDA(cudaSetDevice(ctx->device));
     int rc;
     if (img_l1) { rc = vo_upload_image(ctx, slot_l1, img_l1, w, h, step); if (rc) return rc; }
     if (img_r1) { rc = vo_upload_image(ctx, slot_r1, img_r1, w, h, step); if (rc) return rc; }
-    VO_REQUIRE(slot_l0 >= 0 && slot_l0 < ctx->n_slots && ctx->slots[slot_l0].w == w && ctx->slots[slot_l0].h == h, VO_ERR_INVALID_ARG,
-               "previous-left slot has no image of this size");
-    if (n == 0) {   // nothing to track: the reference would run the GN on zero points and keep the prior
-        mul4_f(T_wp, dT_pc_prev, T_wc_out);
-        memcpy(dT_pc_out, dT_pc_prev, 64);
-        *n_out = 0;
-        if (counts_out) for (int k = 0; k < 5; ++k) counts_out[k] = 0;
-        return VO_OK;
-    }
-    const size_t N = (size_t)n;
+    VO_REQUIRE(slot_l1 >= 0 && slot_l1 < ctx->n_slots && ctx->slots[slot_l1].w == w && ctx->slots[slot_l1].h == h &&
+               slot_r1 >= 0 && slot_r1 < ctx->n_slots && ctx->slots[slot_r1].w == w && ctx->slots[slot_r1].h == h,
+               VO_ERR_INVALID_ARG, "current-frame slots have no image of this size");
+    if (n > 0)
+        VO_REQUIRE(slot_l0 >= 0 && slot_l0 < ctx->n_slots && ctx->slots[slot_l0].w == w && ctx->slots[slot_l0].h == h, VO_ERR_INVALID_ARG,
+                   "previous-left slot has no image of this size");
+    const size_t N = (size_t)n, NB = (size_t)nb;
     // staging: inputs [pts_l0][pts_r0][Xw][tri] | work [pts_l1][pts_r1][scale][mask][Xp][pl][pr][idx_po][mask_po]
-    //          | results [T01 16f][T_wc 16f][ints: n_po, po_success, n_out, nan, counts5][idx_out][out_l1][out_r1]
+    //          | new-feature work [cand NB*8][cand_r NB*8][back NB*8][err NB*4][errb NB*4][st NB][stb NB][mask NB]
+    //          | results [T01 16f][T_wc 16f][ints 16][idx_out][out_l1][out_r1][new_l NB*8][new_r NB*8]
     size_t o = 0;
     const size_t o_l0 = o; o += N * 8; const size_t o_r0 = o; o += N * 8; const size_t o_X = o; o += a16(N * 12);
     const size_t o_tri = o; o += a16(N);
@@ -222,37 +327,25 @@ extern "C" int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *pr
     const size_t o_l1 = o; o += N * 8; const size_t o_r1 = o; o += N * 8; const size_t o_sc = o; o += a16(N * 4);
     const size_t o_m = o; o += a16(N); const size_t o_Xp = o; o += a16(N * 12); const size_t o_pl = o; o += N * 8;
     const size_t o_pr = o; o += N * 8; const size_t o_ip = o; o += a16(N * 4); const size_t o_mp = o; o += a16(N);
+    const size_t o_c = o; o += NB * 8; const size_t o_cr = o; o += NB * 8; const size_t o_cb = o; o += NB * 8;
+    const size_t o_ce = o; o += a16(NB * 4); const size_t o_ceb = o; o += a16(NB * 4); const size_t o_cs = o; o += a16(NB);
+    const size_t o_csb = o; o += a16(NB); const size_t o_cm = o; o += a16(NB);
     const size_t o_res = o;
     const size_t o_T01 = o; o += 64; const size_t o_Twc = o; o += 64; const size_t o_int = o; o += 64;
     const size_t o_io = o; o += a16(N * 4); const size_t o_ol = o; o += N * 8; const size_t o_or = o; o += N * 8;
+    const size_t o_nl = o; o += NB * 8; const size_t o_nr = o; o += NB * 8;
     const size_t total = o;
     rc = vo_stage_reserve(ctx, total);
     if (rc) return rc;
     uint8_t *hs = ctx->h_stage, *dv = ctx->d_stage;
-    memcpy(hs + o_l0, pts_l0, N * 8); memcpy(hs + o_r0, pts_r0, N * 8); memcpy(hs + o_X, Xw, N * 12); memcpy(hs + o_tri, triangulated, N);
-    memcpy(hs + o_T01, dT_pc_prev, 64);           // GN starts from the previous motion (:586)
-    memset(hs + o_Twc, 0, 128);
-    VO_CUDA(cudaMemcpyAsync(dv, hs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int *ints = (int *)(dv + o_int);      // 0 n_po, 1 po_success, 2 n_out, 3 nan, 4..8 counts, 9 n_detected, 10 n_new
+    memset(hs + o_T01, 0, 192);
+    if (n > 0) {
+        memcpy(hs + o_l0, pts_l0, N * 8); memcpy(hs + o_r0, pts_r0, N * 8); memcpy(hs + o_X, Xw, N * 12); memcpy(hs + o_tri, triangulated, N);
+        memcpy(hs + o_T01, dT_pc_prev, 64);           // the GN starts from the previous motion (:586)
+        VO_CUDA(cudaMemcpyAsync(dv, hs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     VO_CUDA(cudaMemcpyAsync(dv + o_T01, hs + o_T01, 192, cudaMemcpyHostToDevice, ctx->stream));
-
-    StepDev d;
-    d.n = n; d.w = w; d.h = h;
-    d.pts_l0 = (const float2 *)(dv + o_l0); d.pts_r0 = (const float2 *)(dv + o_r0); d.Xw = (const float *)(dv + o_X); d.tri = dv + o_tri;
-    d.pts_l1 = (float2 *)(dv + o_l1); d.pts_r1 = (float2 *)(dv + o_r1); d.scale = (float *)(dv + o_sc); d.mask = dv + o_m;
-    d.Xp = (float *)(dv + o_Xp); d.pl = (float2 *)(dv + o_pl); d.pr = (float2 *)(dv + o_pr); d.idx_po = (int *)(dv + o_ip);
-    d.mask_po = dv + o_mp; d.T01 = (float *)(dv + o_T01); d.T_wc = (float *)(dv + o_Twc);
-    int *ints = (int *)(dv + o_int);
-    d.n_po = ints + 0; d.po_success = ints + 1; d.n_out = ints + 2; d.counts = ints + 4;
-    int *nan_flag = ints + 3;
-    d.idx_out = (int *)(dv + o_io); d.out_l1 = (float2 *)(dv + o_ol); d.out_r1 = (float2 *)(dv + o_or);
-    float T_wc_prior[16], T_cw_prior[16], T_pw[16], T_rl[16];
-    mul4_f(T_wp, dT_pc_prev, T_wc_prior);          // :478
-    inv_se3_f(T_wc_prior, T_cw_prior);             // :479 geometry::inverseSE3_f
-    inv_se3_f(T_wp, T_pw);                         // Frame::getPoseInv()
-    inv_se3_f(prm->T_lr, T_rl);
-    memcpy(d.T_cw_prior, T_cw_prior, 48); memcpy(d.T_pw, T_pw, 48); memcpy(d.T_rl, T_rl, 48); memcpy(d.T_wp, T_wp, 64);
-    memcpy(d.K_l, prm->K_l, 16); memcpy(d.K_r, prm->K_r, 16);
-    d.sampson_y = prm->sampson_y;
 
     {   // both new images' pyramids (and Scharr planes) in ONE batched launch set
         const int both[2] = {slot_l1, slot_r1};
@@ -260,47 +353,134 @@ extern "C" int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *pr
         rc = vo_ensure_pyramids(ctx, both, 2, (eff + 1 < ctx->max_levels ? eff + 1 : ctx->max_levels), 1);
         if (rc) return rc;
     }
-    k_step_prior<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(d);
-    ctx->launches++;
-    // [4] l0 -> l1
-    KltPost post{};
-    post.mode = 2; post.thres_err = prm->thres_error; post.mask = d.mask; post.skip_masked = 1;
-    rc = vo_klt_launch(ctx, 1, &slot_l0, &slot_l1, (const float *)d.pts_l0, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
-                       (float *)d.pts_l1, nullptr, nullptr, nullptr, &post);
-    if (rc) return rc;
-    if (counts_out) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 0); ctx->launches++; }
-    // [4-1] scale refinement
-    if (prm->do_scale_refine) {
-        rc = vo_klt_scale_launch_d(ctx, slot_l0, slot_l1, (const float *)d.pts_l0, d.scale, n, (float *)d.pts_l1, d.mask, nan_flag);
+    StepDev d;
+    memset(&d, 0, sizeof(d));
+    d.n = n; d.w = w; d.h = h;
+    d.out_l1 = (float2 *)(dv + o_ol); d.out_r1 = (float2 *)(dv + o_or); d.n_out = ints + 2;
+    if (n > 0) {
+        d.pts_l0 = (const float2 *)(dv + o_l0); d.pts_r0 = (const float2 *)(dv + o_r0); d.Xw = (const float *)(dv + o_X); d.tri = dv + o_tri;
+        d.pts_l1 = (float2 *)(dv + o_l1); d.pts_r1 = (float2 *)(dv + o_r1); d.scale = (float *)(dv + o_sc); d.mask = dv + o_m;
+        d.Xp = (float *)(dv + o_Xp); d.pl = (float2 *)(dv + o_pl); d.pr = (float2 *)(dv + o_pr); d.idx_po = (int *)(dv + o_ip);
+        d.mask_po = dv + o_mp; d.T01 = (float *)(dv + o_T01); d.T_wc = (float *)(dv + o_Twc);
+        d.n_po = ints + 0; d.po_success = ints + 1; d.counts = ints + 4;
+        int *nan_flag = ints + 3;
+        d.idx_out = (int *)(dv + o_io);
+        float T_wc_prior[16], T_cw_prior[16], T_pw[16], T_rl[16];
+        mul4_f(T_wp, dT_pc_prev, T_wc_prior);          // :478
+        inv_se3_f(T_wc_prior, T_cw_prior);             // :479 geometry::inverseSE3_f
+        inv_se3_f(T_wp, T_pw);                         // Frame::getPoseInv()
+        inv_se3_f(prm->T_lr, T_rl);
+        memcpy(d.T_cw_prior, T_cw_prior, 48); memcpy(d.T_pw, T_pw, 48); memcpy(d.T_rl, T_rl, 48); memcpy(d.T_wp, T_wp, 64);
+        memcpy(d.K_l, prm->K_l, 16); memcpy(d.K_r, prm->K_r, 16);
+        d.sampson_y = prm->sampson_y;
+        const bool want_counts = res->counts != nullptr;
+        k_step_prior<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(d);
+        ctx->launches++;
+        // [4] l0 -> l1
+        KltPost post{};
+        post.mode = 2; post.thres_err = prm->thres_error; post.mask = d.mask; post.skip_masked = 1;
+        rc = vo_klt_launch(ctx, 1, &slot_l0, &slot_l1, (const float *)d.pts_l0, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
+                           (float *)d.pts_l1, nullptr, nullptr, nullptr, &post);
         if (rc) return rc;
+        if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 0); ctx->launches++; }
+        // [4-1] scale refinement
+        if (prm->do_scale_refine) {
+            rc = vo_klt_scale_launch_d(ctx, slot_l0, slot_l1, (const float *)d.pts_l0, d.scale, n, (float *)d.pts_l1, d.mask, nan_flag);
+            if (rc) return rc;
+        }
+        if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 1); ctx->launches++; }
+        // [5] l1 -> r1
+        rc = vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, (const float *)d.pts_l1, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
+                           (float *)d.pts_r1, nullptr, nullptr, nullptr, &post);
+        if (rc) return rc;
+        if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 2); ctx->launches++; }
+        // [6] pose-only GN on the triangulated survivors
+        k_step_select<<<1, 1024, 0, ctx->stream>>>(d);
+        ctx->launches++;
+        rc = vo_pose_launch_d(ctx, 1, nullptr, 0, d.n_po, d.Xp, (const float *)d.pl, (const float *)d.pr, prm->K_l, prm->K_r, prm->T_lr,
+                              prm->thres_poseba_error, 0, 0, d.T01, d.mask_po, d.po_success, nullptr);
+        if (rc) return rc;
+        k_step_finish<<<1, 1024, 0, ctx->stream>>>(d);
+        ctx->launches++;
     }
-    if (counts_out) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 1); ctx->launches++; }
-    // [5] l1 -> r1
-    rc = vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, (const float *)d.pts_l1, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
-                       (float *)d.pts_r1, nullptr, nullptr, nullptr, &post);
-    if (rc) return rc;
-    if (counts_out) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 2); ctx->launches++; }
-    // [6] pose-only GN on the triangulated survivors
-    k_step_select<<<1, 1024, 0, ctx->stream>>>(d);
-    ctx->launches++;
-    rc = vo_pose_launch_d(ctx, 1, nullptr, 0, d.n_po, d.Xp, (const float *)d.pl, (const float *)d.pr, prm->K_l, prm->K_r, prm->T_lr,
-                          prm->thres_poseba_error, 0, 0, d.T01, d.mask_po, d.po_success, nullptr);
-    if (rc) return rc;
-    k_step_finish<<<1, 1024, 0, ctx->stream>>>(d);
-    ctx->launches++;
+    if (nb > 0) {
+        // [10] new features from the empty bins: detect on l1, bidirectional l1 <-> r1 match, depth gate, compaction
+        rc = vo_detect_launch_d(ctx, slot_l1, (const float *)d.out_l1, n > 0 ? d.n_out : nullptr, n, fp->n_bins_u, fp->n_bins_v, fp->det_edge,
+                                fp->det_min_score, (float *)(dv + o_c), dv + o_cm, ints + 9, nb);
+        if (rc) return rc;
+        KltPost post{};
+        post.thres_err = prm->thres_error; post.mask = dv + o_cm; post.skip_masked = 1;
+        post.mode = 3;                               // trackBidirection forward pass (feature_tracker.cpp:57-60)
+        rc = vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, (const float *)(dv + o_c), nb, prm->window_size, prm->max_level, 0,
+                           (float *)(dv + o_cr), dv + o_cs, (float *)(dv + o_ce), nullptr, &post);
+        if (rc) return rc;
+        VO_CUDA(cudaMemcpyAsync(dv + o_cb, dv + o_c, NB * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        post.mode = 4; post.border = 3; post.thres_bi2 = fp->thres_bidirection * fp->thres_bidirection;
+        post.ref_pts = (const float *)(dv + o_c); post.fwd_pts = (const float *)(dv + o_cr); post.fwd_status = dv + o_cs;
+        post.fwd_err = (const float *)(dv + o_ce);
+        const int back_lvl = prm->max_level - 1 < 0 ? 0 : prm->max_level - 1;      // :69 backward pass at maxLevel-1
+        rc = vo_klt_launch(ctx, 1, &slot_r1, &slot_l1, (const float *)(dv + o_cr), nb, prm->window_size, back_lvl, VO_KLT_USE_INITIAL_FLOW,
+                           (float *)(dv + o_cb), dv + o_csb, (float *)(dv + o_ceb), nullptr, &post);
+        if (rc) return rc;
+        NewDev nd;
+        nd.pl = (const float2 *)(dv + o_c); nd.pr = (const float2 *)(dv + o_cr); nd.mask = dv + o_cm; nd.n_in = ints + 9;
+        nd.depth_gate = fp->new_depth_gate;
+        float T_rl[16];
+        inv_se3_f(prm->T_lr, T_rl);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) nd.R_rl[r * 3 + c] = T_rl[r * 4 + c]; nd.t_rl[r] = T_rl[r * 4 + 3]; }
+        memcpy(nd.K_l, prm->K_l, 16); memcpy(nd.K_r, prm->K_r, 16);
+        nd.out_l = (float2 *)(dv + o_nl); nd.out_r = (float2 *)(dv + o_nr); nd.n_out = ints + 10;
+        k_new_gate<<<1, 1024, 0, ctx->stream>>>(nd);
+        ctx->launches++;
+    }
     VO_CUDA(cudaGetLastError());
     VO_CUDA(cudaMemcpyAsync(hs + o_res, dv + o_res, total - o_res, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     const int *hi = (const int *)(hs + o_int);
-    const int k_out = hi[2];
-    if (counts_out) for (int k = 0; k < 5; ++k) counts_out[k] = hi[4 + k];
-    if (hi[3]) { ctx->last_error = "ax ay nan (feature_tracker.cpp:414)"; return VO_ERR_NAN; }
-    if (!hi[1]) { ctx->last_error = "PoseOnlyStereoBA is failed!"; return VO_ERR_NAN; }   // stereo_vo.cpp:624-627
-    memcpy(dT_pc_out, hs + o_T01, 64);
-    memcpy(T_wc_out, hs + o_Twc, 64);
-    *n_out = k_out;
-    memcpy(index_out, hs + o_io, (size_t)k_out * 4);
-    memcpy(pts_l1_out, hs + o_ol, (size_t)k_out * 8);
-    memcpy(pts_r1_out, hs + o_or, (size_t)k_out * 8);
+    res->n_tracked = 0; res->n_new = 0; res->n_detected = 0;
+    if (n > 0) {
+        if (res->counts) for (int k = 0; k < 5; ++k) res->counts[k] = hi[4 + k];
+        if (hi[3]) { ctx->last_error = "ax ay nan (feature_tracker.cpp:414)"; return VO_ERR_NAN; }
+        if (!hi[1]) { ctx->last_error = "PoseOnlyStereoBA is failed!"; return VO_ERR_NAN; }   // stereo_vo.cpp:624-627
+        const int k_out = hi[2];
+        memcpy(res->dT_pc, hs + o_T01, 64);
+        memcpy(res->T_wc, hs + o_Twc, 64);
+        res->n_tracked = k_out;
+        memcpy(res->index, hs + o_io, (size_t)k_out * 4);
+        memcpy(res->pts_l1, hs + o_ol, (size_t)k_out * 8);
+        memcpy(res->pts_r1, hs + o_or, (size_t)k_out * 8);
+    } else if (T_wp && dT_pc_prev && res->T_wc && res->dT_pc) {
+        // nothing to track: the reference would run the GN on zero points and keep the prior
+        mul4_f(T_wp, dT_pc_prev, res->T_wc);
+        memcpy(res->dT_pc, dT_pc_prev, 64);
+        if (res->counts) for (int k = 0; k < 5; ++k) res->counts[k] = 0;
+    }
+    if (nb > 0) {
+        res->n_detected = hi[9];
+        res->n_new = hi[10];
+        memcpy(res->new_l1, hs + o_nl, (size_t)hi[10] * 8);
+        memcpy(res->new_r1, hs + o_nr, (size_t)hi[10] * 8);
+    }
+    return VO_OK;
+}
+
+extern "C" int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *prm, int slot_l0, int slot_l1, int slot_r1,
+                                    const uint8_t *img_l1, const uint8_t *img_r1, int w, int h, size_t step, int n,
+                                    const float *pts_l0, const float *pts_r0, const float *Xw, const uint8_t *triangulated,
+                                    const float *T_wp, const float *dT_pc_prev, float *T_wc_out, float *dT_pc_out, int *n_out,
+                                    int *index_out, float *pts_l1_out, float *pts_r1_out, int *counts_out)
+{
+    if (!ctx || !prm) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(T_wp && dT_pc_prev && T_wc_out && dT_pc_out && n_out, VO_ERR_INVALID_ARG, "null pointer");
+    vo_stereo_frame_params fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.track = *prm;
+    vo_stereo_frame_result res;
+    memset(&res, 0, sizeof(res));
+    res.T_wc = T_wc_out; res.dT_pc = dT_pc_out; res.index = index_out; res.pts_l1 = pts_l1_out; res.pts_r1 = pts_r1_out; res.counts = counts_out;
+    const int rc = vo_stereo_frame_step(ctx, &fp, slot_l0, slot_l1, slot_r1, img_l1, img_r1, w, h, step, n, pts_l0, pts_r0, Xw, triangulated,
+                                        T_wp, dT_pc_prev, &res);
+    if (rc) return rc;
+    *n_out = res.n_tracked;
     return VO_OK;
 }

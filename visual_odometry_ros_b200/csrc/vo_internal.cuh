@@ -67,6 +67,9 @@ struct vo_ctx {
     // trackWithScale scratch (float image + Sobel derivatives), lazily allocated
     float *d_f32[4] = {nullptr, nullptr, nullptr, nullptr};
     int f32_slot[2] = {-1, -1};
+    // K-det scratch (score plane + per-bin state)
+    void *d_det = nullptr;
+    size_t det_bytes = 0;
     // LBA scratch
     void *d_lba = nullptr;
     size_t lba_bytes = 0;

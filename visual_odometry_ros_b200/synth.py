@@ -259,3 +259,152 @@ def stereo_frame_pair(seed=3003, n=2000, w=KITTI_W, h=KITTI_H, rotvec=(0.001, -0
     dT_prev[:3, 3] = t01 * 0.9 + [0.01, 0.0, 0.02]
     return dict(L0=L0, R0=R0, L1=L1, R1=R1, pts_l0=pts_l0, pts_r0=pts_r0, Xw=Xw.astype(np.float32), tri=tri,
                 T_wp=T_wp.astype(np.float32), dT_pc_prev=dT_prev.astype(np.float32), T01_true=T01)
+
+
+# ------------------------------------------------------------------ stereo sequence (configs 3/5)
+# A static, fully finite scene -- an infinitely long rectangular corridor (ground, ceiling, two walls), every
+# surface carrying a periodic 1/f-noise texture with mip levels -- ray-cast per pixel for a KITTI-like rig that
+# drives along it (0.8-1.2 m/frame, yaw rate <= 1.5 deg/frame).  Written with torch tensor ops only so that the
+# same code renders on the CPU (tests) or on the GPU (bench.py manufactures 1000 frames in seconds); the
+# product never sees anything but the resulting u8 images.
+def corridor_trajectory(n_frames, seed=3003):
+    """Camera-to-world poses T_wc [n,4,4] float64 (x right, y down, z forward along the corridor)."""
+    rng = np.random.default_rng(seed)
+    speed = rng.uniform(0.8, 1.2, n_frames)
+    ph = rng.uniform(0, 2 * np.pi, 3)
+    t = np.arange(n_frames)
+    yaw = 0.12 * np.sin(2 * np.pi * t / 60.0 + ph[0]) + 0.05 * np.sin(2 * np.pi * t / 23.0 + ph[1])
+    pitch = 0.004 * np.sin(2 * np.pi * t / 17.0 + ph[2])
+    roll = 0.003 * np.sin(2 * np.pi * t / 29.0 + ph[0])
+    T = np.zeros((n_frames, 4, 4))
+    pos = np.zeros(3)
+    for k in range(n_frames):
+        R = so3_exp([0, yaw[k], 0]) @ so3_exp([pitch[k], 0, 0]) @ so3_exp([0, 0, roll[k]])
+        if k > 0:
+            pos = pos + R[:, 2] * speed[k] * np.array([1.0, 0.0, 1.0])   # stay at constant height
+        T[k, :3, :3] = R
+        T[k, :3, 3] = pos
+        T[k, 3, 3] = 1.0
+    return T
+
+
+def _fractal_texture(seed, size=1024):
+    """Periodic 1/f^0.9 noise, contrast-stretched to [0, 255] (float32 numpy, size x size)."""
+    rng = np.random.default_rng(seed)
+    white = rng.normal(size=(size, size))
+    fy = np.fft.fftfreq(size)[:, None]
+    fx = np.fft.fftfreq(size)[None, :]
+    f = np.sqrt(fx * fx + fy * fy)
+    f[0, 0] = 1.0
+    spec = np.fft.fft2(white) / f ** 0.9
+    spec[0, 0] = 0.0
+    tex = np.real(np.fft.ifft2(spec))
+    lo, hi = np.percentile(tex, [1, 99])
+    return np.clip((tex - lo) / (hi - lo), 0, 1).astype(np.float32) * 255.0
+
+
+class CorridorRenderer:
+    """render(T_wc) -> (left u8 [h,w], right u8 [h,w]) torch tensors on `device`."""
+
+    HALF_WIDTH, GROUND_Y, CEIL_Y, PPM, LEVELS = 7.0, 1.65, -5.0, 128.0, 7
+
+    def __init__(self, w=KITTI_W, h=KITTI_H, K=None, baseline=BASELINE_M, seed=3003, device="cpu", noise_sigma=1.0):
+        import torch
+        self.torch, self.device, self.w, self.h, self.baseline = torch, torch.device(device), w, h, baseline
+        K = kitti_K() if K is None else np.asarray(K, np.float32)
+        self.K = [float(v) for v in K]
+        self.noise_sigma, self.seed = noise_sigma, seed
+        mips = []
+        for plane in range(4):
+            t = torch.from_numpy(_fractal_texture(seed * 7 + plane)).to(self.device)
+            lv = [t]
+            for _ in range(self.LEVELS - 1):
+                lv.append(torch.nn.functional.avg_pool2d(lv[-1][None, None], 2)[0, 0])
+            mips.append(lv)
+        self.mips = mips
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64, device=self.device),
+                                torch.arange(w, dtype=torch.float64, device=self.device), indexing="ij")
+        self.dc = torch.stack([(xs - self.K[2]) / self.K[0], (ys - self.K[3]) / self.K[1], torch.ones_like(xs)], -1)
+        self.frame_no = 0
+
+    def _sample(self, plane, u, v, lam):
+        torch = self.torch
+        out = torch.zeros_like(u)
+        l0 = torch.clamp(torch.floor(lam), 0, self.LEVELS - 2)
+        fr = torch.clamp(lam - l0, 0.0, 1.0)
+        for l in range(self.LEVELS):
+            tex = self.mips[plane][l]
+            n = tex.shape[0]
+            wgt = torch.where(l0 == l, 1.0 - fr, torch.where(l0 == l - 1, fr, torch.zeros_like(fr)))
+            if not bool((wgt > 0).any()):
+                continue
+            s = 1.0 / (1 << l)
+            uu, vv = u * s - 0.5, v * s - 0.5
+            u0, v0 = torch.floor(uu), torch.floor(vv)
+            au, av = uu - u0, vv - v0
+            iu0, iv0 = u0.long() % n, v0.long() % n
+            iu1, iv1 = (iu0 + 1) % n, (iv0 + 1) % n
+            val = (tex[iv0, iu0] * (1 - au) * (1 - av) + tex[iv0, iu1] * au * (1 - av) +
+                   tex[iv1, iu0] * (1 - au) * av + tex[iv1, iu1] * au * av)
+            out = out + wgt * val
+        return out
+
+    def _render_one(self, R, o, gen):
+        torch = self.torch
+        d = self.dc @ torch.as_tensor(R, dtype=torch.float64, device=self.device).T          # world ray directions, d_cam.z == 1
+        ox, oy, oz = float(o[0]), float(o[1]), float(o[2])
+        inf = torch.full_like(d[..., 0], float("inf"))
+        tiny = 1e-12
+        t_g = torch.where(d[..., 1] > tiny, (self.GROUND_Y - oy) / d[..., 1], inf)
+        t_c = torch.where(d[..., 1] < -tiny, (self.CEIL_Y - oy) / d[..., 1], inf)
+        t_r = torch.where(d[..., 0] > tiny, (self.HALF_WIDTH - ox) / d[..., 0], inf)
+        t_l = torch.where(d[..., 0] < -tiny, (-self.HALF_WIDTH - ox) / d[..., 0], inf)
+        ts = torch.stack([t_g, t_c, t_r, t_l], 0)
+        t, which = ts.min(0)
+        t = torch.clamp(t, max=5000.0)
+        P = torch.stack([ox + t * d[..., 0], oy + t * d[..., 1], oz + t * d[..., 2]], -1)
+        lam = torch.log2(torch.clamp(t * self.PPM / self.K[0], min=1.0)) + 0.5
+        img = torch.zeros_like(t)
+        for plane in range(4):
+            m = which == plane
+            if not bool(m.any()):
+                continue
+            a = P[..., 0] if plane < 2 else P[..., 1]
+            u = (a * self.PPM + 137.0 * plane)[m]
+            v = (P[..., 2] * self.PPM)[m]
+            img[m] = self._sample(plane, u, v, lam[m]).to(img.dtype)
+        noise = torch.randn(img.shape, generator=gen, dtype=torch.float64) * self.noise_sigma
+        img = img + noise.to(self.device)
+        return torch.clamp(torch.round(img), 0, 255).to(torch.uint8), t
+
+    def render(self, T_wc, want_depth=False):
+        torch = self.torch
+        T_wc = np.asarray(T_wc, np.float64)
+        gen = torch.Generator().manual_seed(self.seed * 100003 + self.frame_no)
+        self.frame_no += 1
+        R, o = T_wc[:3, :3], T_wc[:3, 3]
+        left, depth = self._render_one(R, o, gen)
+        right, _ = self._render_one(R, o + R[:, 0] * self.baseline, gen)
+        return (left, right, depth) if want_depth else (left, right)
+
+
+def stereo_sequence(n_frames, w=KITTI_W, h=KITTI_H, K=None, seed=3003, device="cpu"):
+    """Returns (lefts u8 [n,h,w], rights u8 [n,h,w], T_wc_true [n,4,4]) as numpy arrays."""
+    import torch
+    traj = corridor_trajectory(n_frames, seed)
+    ren = CorridorRenderer(w, h, K, seed=seed, device=device)
+    L = torch.empty((n_frames, h, w), dtype=torch.uint8)
+    R = torch.empty((n_frames, h, w), dtype=torch.uint8)
+    for k in range(n_frames):
+        l, r = ren.render(traj[k])
+        L[k], R[k] = l.cpu(), r.cpu()
+    return L.numpy(), R.numpy(), traj
+
+
+SMALL_W, SMALL_H = 640, 192
+
+
+def small_K():
+    """Intrinsics for the 640x192 test-size rig (same field of view as KITTI)."""
+    s = SMALL_W / KITTI_W
+    return np.array([FX * s, FY * s, (SMALL_W - 1) * 0.5, (SMALL_H - 1) * 0.5], np.float32)
