@@ -1,0 +1,506 @@
+// stereo_vo.cpp -- host glue of StereoVO::trackStereoImages (core/visual_odometry/stereo_vo/stereo_vo.cpp:392-989)
+// over flat arrays; every numeric stage is a C-ABI call into libvo_b200.so (see stereo_vo.h).
+#include "stereo_vo.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+namespace {
+const float D2R = 3.14159265358979323846f / 180.0f;
+
+void ident(float *T) { for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f; }
+void mul4_f(const float *A, const float *B, float *C)
+{
+    float T[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float s = 0.f; for (int k = 0; k < 4; ++k) s += A[i * 4 + k] * B[k * 4 + j]; T[i * 4 + j] = s; }
+    memcpy(C, T, sizeof(T));
+}
+// geometry::inverseSE3_f (core/util/geometry_library.cpp:554-560)
+void inv_se3_f(const float *T, float *O)
+{
+    float R[16];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i * 4 + j] = T[j * 4 + i];
+        float s = 0.f;
+        for (int k = 0; k < 3; ++k) s += T[k * 4 + i] * T[k * 4 + 3];
+        R[i * 4 + 3] = -s;
+    }
+    R[12] = R[13] = R[14] = 0.f; R[15] = 1.f;
+    memcpy(O, R, sizeof(R));
+}
+// Eigen::Matrix4f::inverse() (stereo_vo.cpp:643) restated as the adjugate formula (third-party, unpinned)
+void inv4_f(const float *m, float *out)
+{
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const float id = 1.0f / det;
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * id;
+}
+void mul4_d(const double *A, const double *B, double *C)
+{
+    double T[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += A[i * 4 + k] * B[k * 4 + j]; T[i * 4 + j] = s; }
+    memcpy(C, T, sizeof(T));
+}
+void rowmajor_to_pose(const float *o, PoseSE3 &T) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T(r, c) = o[r * 4 + c]; }
+
+[[noreturn]] void fail(vo_ctx *ctx, int rc)
+{
+    std::string msg = ctx ? vo_last_error(ctx) : "";
+    if (rc == VO_ERR_NAN && !msg.empty()) throw std::runtime_error(msg);            // the reference's own texts
+    throw std::runtime_error(std::string("vo_b200: ") + vo_status_string(rc) + (msg.empty() ? "" : " (" + msg + ")"));
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------ construction
+StereoVO::StereoVO(const Parameters &prm) : p_(prm) { init(); }
+
+// stereo_vo.cpp:186-285: "%YAML:1.0" key: value pairs + the T_lr opencv-matrix block
+StereoVO::StereoVO(std::string mode, std::string directory_intrinsic)
+{
+    if (mode != "dataset" && mode != "rosbag") throw std::runtime_error("StereoVO - unknown mode.");     // stereo_vo.cpp:14-21
+    std::ifstream f(directory_intrinsic);
+    if (!f.is_open()) throw std::runtime_error("intrinsic file cannot be found!\n");                    // :190
+    std::map<std::string, std::string> kv;
+    std::string line, all;
+    std::vector<float> tlr;
+    bool in_tlr = false;
+    while (std::getline(f, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        const size_t c = line.find(':');
+        if (c == std::string::npos) continue;
+        std::string key = line.substr(0, c), val = line.substr(c + 1);
+        key.erase(0, key.find_first_not_of(" \t")); key.erase(key.find_last_not_of(" \t") + 1);
+        val.erase(0, val.find_first_not_of(" \t")); if (!val.empty()) val.erase(val.find_last_not_of(" \t\r") + 1);
+        if (key == "T_lr") { in_tlr = true; continue; }
+        if (in_tlr && key == "data") {
+            std::string d = val;
+            while (d.find(']') == std::string::npos && std::getline(f, line)) d += line;
+            for (char &ch : d) if (ch == '[' || ch == ']' || ch == ',') ch = ' ';
+            std::istringstream ss(d);
+            float v;
+            while (ss >> v) tlr.push_back(v);
+            in_tlr = false;
+            continue;
+        }
+        kv[key] = val;
+    }
+    auto num = [&](const char *k, double dflt) { auto it = kv.find(k); return it == kv.end() || it->second.empty() ? dflt : atof(it->second.c_str()); };
+    p_.width = (int)num("Camera.left.width", p_.width); p_.height = (int)num("Camera.left.height", p_.height);
+    const char *names[4] = {"fx", "fy", "cx", "cy"};
+    for (int i = 0; i < 4; ++i) {
+        p_.K_l[i] = (float)num((std::string("Camera.left.") + names[i]).c_str(), p_.K_l[i]);
+        p_.K_r[i] = (float)num((std::string("Camera.right.") + names[i]).c_str(), p_.K_r[i]);
+    }
+    if (num("flagDoUndistortion", 0) != 0)
+        throw std::runtime_error("vo_b200: flagDoUndistortion=1 (rectification remap) is outside the hot path of this build");
+    if (tlr.size() == 16) memcpy(p_.T_lr, tlr.data(), 64);
+    p_.thres_error = (float)num("feature_tracker.thres_error", p_.thres_error);
+    p_.thres_bidirection = (float)num("feature_tracker.thres_bidirection", p_.thres_bidirection);
+    p_.thres_sampson = (float)num("feature_tracker.thres_sampson", p_.thres_sampson);
+    p_.window_size = (int)num("feature_tracker.window_size", p_.window_size);
+    p_.max_level = (int)num("feature_tracker.max_level", p_.max_level);
+    p_.n_bins_u = (int)num("feature_extractor.n_bins_u", p_.n_bins_u);
+    p_.n_bins_v = (int)num("feature_extractor.n_bins_v", p_.n_bins_v);
+    p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
+    p_.thres_alive_ratio = (float)num("keyframe_update.thres_alive_ratio", p_.thres_alive_ratio);
+    p_.thres_trans = (float)num("keyframe_update.thres_trans", p_.thres_trans);
+    p_.thres_rotation_deg = (float)num("keyframe_update.thres_rotation", p_.thres_rotation_deg);
+    p_.n_max_keyframes_in_window = (int)num("keyframe_update.n_max_keyframes_in_window", p_.n_max_keyframes_in_window);
+    init();
+}
+
+void StereoVO::init()
+{
+    const int nb = std::max(1, p_.n_bins_u * p_.n_bins_v);
+    const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 4, 4 * nb + 4096, nullptr, &ctx_);
+    if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
+}
+
+StereoVO::~StereoVO() { if (ctx_) vo_ctx_destroy(ctx_); }
+
+long long StereoVO::launchCount() const { return vo_ctx_launch_count(ctx_); }
+const std::vector<int> &StereoVO::currentLandmarkIds() const { static const std::vector<int> e; return prev_ ? prev_->lm_ids : e; }
+const std::vector<float> &StereoVO::currentPtsLeft() const { static const std::vector<float> e; return prev_ ? prev_->pts_l : e; }
+const std::vector<float> &StereoVO::currentPtsRight() const { static const std::vector<float> e; return prev_ ? prev_->pts_r : e; }
+
+// ------------------------------------------------------------------------------ bookkeeping
+void StereoVO::setPose(FrameRec &f, const float *Twc)
+{
+    memcpy(f.Twc, Twc, 64);
+    inv_se3_f(f.Twc, f.Tcw);
+}
+
+int StereoVO::newLandmarks(int k, int frame_id)
+{
+    const int base = (int)lm_tri_.size();
+    lm_X_.resize((size_t)(base + k) * 3, 0.f);
+    lm_tri_.resize(base + k, 0); lm_alive_.resize(base + k, 1); lm_bundled_.resize(base + k, 0);
+    lm_last_frame_.resize(base + k, frame_id);
+    lm_kf_obs_.resize(base + k);
+    return base;
+}
+
+bool StereoVO::checkUpdateRule(const FrameRec &f) const
+{
+    if (window_.empty()) return true;
+    const FrameRec &kf = *window_.back();
+    int cnt_tracked = 0;
+    for (int id : kf.lm_ids) if (lm_last_frame_[id] == f.id) ++cnt_tracked;
+    const float ratio = (float)cnt_tracked / (float)kf.lm_ids.size();
+    if (ratio <= p_.thres_alive_ratio) return true;
+    float dT[16];
+    mul4_f(kf.Tcw, f.Twc, dT);
+    float costheta = (dT[0] + dT[5] + dT[10] - 1.0f) * 0.5f;
+    if (costheta >= 0.999999) costheta = 0.999999;
+    if (costheta <= -0.999999) costheta = -0.999999;
+    const float rot = acosf(costheta);
+    const float dtrans = std::sqrt(dT[3] * dT[3] + dT[7] * dT[7] + dT[11] * dT[11]);
+    return rot >= p_.thres_rotation_deg * D2R || dtrans >= p_.thres_trans;
+}
+
+void StereoVO::addKeyframe(const FrameRecPtr &f)
+{
+    all_keyframes_.push_back(f);
+    if ((int)window_.size() == p_.n_max_keyframes_in_window) window_.pop_front();
+    window_.push_back(f);
+    const size_t n = f->lm_ids.size();
+    for (size_t i = 0; i < n; ++i) lm_kf_obs_[f->lm_ids[i]].push_back({f->id, 0, f->pts_l[2 * i], f->pts_l[2 * i + 1]});
+    for (size_t i = 0; i < n; ++i) lm_kf_obs_[f->lm_ids[i]].push_back({f->id, 1, f->pts_r[2 * i], f->pts_r[2 * i + 1]});
+}
+
+void StereoVO::reconstruct(FrameRec &f, int n_first)
+{
+    info_.n_recon = 0;
+    if (n_first <= 0) return;
+    std::vector<float> Xw((size_t)n_first * 3);
+    std::vector<uint8_t> ok(n_first);
+    const int rc = vo_stereo_reconstruct(ctx_, f.pts_l.data(), f.pts_r.data(), n_first, p_.K_l, p_.K_r, p_.T_lr, f.Twc, Xw.data(), ok.data());
+    if (rc) fail(ctx_, rc);
+    for (int i = 0; i < n_first; ++i) {
+        if (!ok[i]) continue;
+        const int id = f.lm_ids[i];
+        memcpy(&lm_X_[(size_t)id * 3], &Xw[(size_t)i * 3], 12);      // Landmark::set3DPoint
+        lm_tri_[id] = 1;
+        ++info_.n_recon;
+    }
+}
+
+void StereoVO::localBundleAdjustment()
+{
+    const int NUM_MINIMUM_REQUIRED_KEYFRAMES = 3, NUM_FIX = 2;                     // motion_estimator.cpp:1245-1246
+    info_.lba_points = info_.lba_obs = info_.lba_ok = 0;
+    if ((int)window_.size() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return;
+    const int nf = (int)window_.size();
+    std::map<int, int> fidx;
+    for (int k = 0; k < nf; ++k) fidx[window_[k]->id] = k;
+    // 1) alive + triangulated landmarks of the window, first-seen order (the reference's unordered_set order is
+    //    address-hash dependent)
+    std::vector<int> lmset;
+    {
+        std::vector<uint8_t> seen(lm_tri_.size(), 0);
+        for (const auto &fr : window_)
+            for (int id : fr->lm_ids)
+                if (!seen[id] && lm_tri_[id] && lm_alive_[id]) { seen[id] = 1; lmset.push_back(id); }
+    }
+    double Twj_ref[16], Tjw_ref[16];
+    for (int i = 0; i < 12; ++i) Twj_ref[i] = window_[0]->Twc[i];
+    Twj_ref[12] = Twj_ref[13] = Twj_ref[14] = 0; Twj_ref[15] = 1;
+    memset(Tjw_ref, 0, sizeof(Tjw_ref));
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Tjw_ref[i * 4 + j] = Twj_ref[j * 4 + i];
+        double s = 0; for (int k = 0; k < 3; ++k) s += Twj_ref[k * 4 + i] * Twj_ref[k * 4 + 3];
+        Tjw_ref[i * 4 + 3] = -s;
+    }
+    Tjw_ref[15] = 1;
+    const double pose_scale = 10.0, inv_scale = 1.0 / pose_scale;
+    std::vector<int> lms, obs_ptr(1, 0), obs_frame;
+    std::vector<uint8_t> obs_right;
+    std::vector<double> points, obs_px;
+    for (int id : lmset) {
+        int cnt = 0;
+        for (const KfObs &o : lm_kf_obs_[id]) if (fidx.count(o.kf_id)) ++cnt;
+        if (cnt < 2) continue;                                                     // THRES_MINIMUM_SEEN
+        const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
+        for (int r = 0; r < 3; ++r)
+            points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
+        lms.push_back(id);
+        for (const KfObs &o : lm_kf_obs_[id]) {
+            auto it = fidx.find(o.kf_id);
+            if (it == fidx.end()) continue;
+            obs_frame.push_back(it->second); obs_right.push_back(o.right);
+            obs_px.push_back(o.x); obs_px.push_back(o.y);
+        }
+        obs_ptr.push_back((int)obs_frame.size());
+    }
+    if (lms.empty()) return;
+    std::vector<double> poses((size_t)nf * 16);
+    for (int k = 0; k < nf; ++k) {
+        double Tjw[16];
+        for (int i = 0; i < 12; ++i) Tjw[i] = window_[k]->Tcw[i];
+        Tjw[12] = Tjw[13] = Tjw[14] = 0; Tjw[15] = 1;
+        mul4_d(Tjw, Twj_ref, Tjw);
+        for (int r = 0; r < 3; ++r) Tjw[r * 4 + 3] *= inv_scale;
+        memcpy(&poses[(size_t)k * 16], Tjw, sizeof(Tjw));
+    }
+    std::vector<int> opt_index(nf, -1);
+    for (int k = NUM_FIX; k < nf; ++k) opt_index[k] = k - NUM_FIX;
+    vo_lba_problem pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.n_frames = nf; pr.n_opt = nf - NUM_FIX; pr.n_points = (int)lms.size(); pr.n_obs = (int)obs_frame.size();
+    pr.poses = poses.data(); pr.opt_index = opt_index.data(); pr.points = points.data(); pr.obs_ptr = obs_ptr.data();
+    pr.obs_frame = obs_frame.data(); pr.obs_right = obs_right.data(); pr.obs_px = obs_px.data();
+    for (int i = 0; i < 4; ++i) { pr.K_l[i] = p_.K_l[i]; pr.K_r[i] = p_.K_r[i]; }
+    for (int i = 0; i < 16; ++i) pr.T_lr[i] = p_.T_lr[i];
+    for (int r = 0; r < 3; ++r) pr.T_lr[r * 4 + 3] *= inv_scale;
+    pr.is_stereo = 1; pr.huber = 0.5; pr.lambda = 0.00001; pr.max_iter = 10;
+    std::vector<double> poses_out(poses.size()), points_out(points.size()), avg(pr.max_iter);
+    int ok = 0;
+    const int rc = vo_lba_solve(ctx_, &pr, poses_out.data(), points_out.data(), avg.data(), &ok);
+    if (rc == VO_ERR_NAN) throw std::runtime_error("Local BA NAN!\n");           // sparse_bundle_adjustment.cpp:761
+    if (rc) fail(ctx_, rc);
+    info_.lba_points = pr.n_points; info_.lba_obs = pr.n_obs; info_.lba_ok = ok;
+    // write-back (sparse_bundle_adjustment.cpp:631-718)
+    bool large_update = false;
+    for (int k = 0; k < nf; ++k) {
+        if (opt_index[k] < 0) continue;
+        double Tjw[16], Twj0[16], dT[16];
+        memcpy(Tjw, &poses_out[(size_t)k * 16], sizeof(Tjw));
+        for (int r = 0; r < 3; ++r) Tjw[r * 4 + 3] *= pose_scale;
+        mul4_d(Tjw, Tjw_ref, Tjw);
+        for (int i = 0; i < 12; ++i) Twj0[i] = window_[k]->Twc[i];
+        Twj0[12] = Twj0[13] = Twj0[14] = 0; Twj0[15] = 1;
+        mul4_d(Twj0, Tjw, dT);
+        if (std::sqrt(dT[3] * dT[3] + dT[7] * dT[7] + dT[11] * dT[11]) > 50) large_update = true;
+        float Tjw_f[16], Twj_f[16];
+        for (int i = 0; i < 12; ++i) Tjw_f[i] = (float)Tjw[i];
+        Tjw_f[12] = Tjw_f[13] = Tjw_f[14] = 0.f; Tjw_f[15] = 1.f;
+        inv_se3_f(Tjw_f, Twj_f);
+        setPose(*window_[k], Twj_f);
+    }
+    for (size_t j = 0; j < lms.size(); ++j) {
+        double X[3];
+        for (int r = 0; r < 3; ++r) X[r] = points_out[3 * j + r] * pose_scale;
+        float Xf[3];
+        for (int r = 0; r < 3; ++r) Xf[r] = (float)(Twj_ref[r * 4] * X[0] + Twj_ref[r * 4 + 1] * X[1] + Twj_ref[r * 4 + 2] * X[2] + Twj_ref[r * 4 + 3]);
+        const int id = lms[j];
+        memcpy(&lm_X_[(size_t)id * 3], Xf, 12);
+        lm_tri_[id] = 1;
+        if (std::sqrt(Xf[0] * Xf[0] + Xf[1] * Xf[1] + Xf[2] * Xf[2]) <= 3000) lm_bundled_[id] = 1;
+        else lm_alive_[id] = 0;
+    }
+    if (large_update) throw std::runtime_error("large update!");                  // :731
+}
+
+void StereoVO::pushStats(const FrameRec &f, bool keyframe)
+{
+    if (keyframe) {
+        stat_.stats_keyframe.emplace_back();
+        for (size_t j = 0; j < stat_.stats_keyframe.size() && j < all_keyframes_.size(); ++j) {   // stereo_vo.cpp:814-822
+            const FrameRec &kf = *all_keyframes_[j];
+            rowmajor_to_pose(kf.Twc, stat_.stats_keyframe[j].Twc);
+            PointVec &mp = stat_.stats_keyframe[j].mappoints;
+            mp.resize(kf.lm_ids.size());
+            for (size_t i = 0; i < kf.lm_ids.size(); ++i)
+                for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)kf.lm_ids[i] * 3 + r];
+        }
+    }
+    stat_.stats_frame.emplace_back();
+    rowmajor_to_pose(f.Twc, stat_.stats_frame.back().Twc);                       // :979-980
+    // the ROS1 node reads stats_landmark / stats_execution .back(): keep them in step
+    stat_.stats_landmark.emplace_back();
+    stat_.stats_landmark.back().n_initial = info_.n_in;
+    stat_.stats_landmark.back().n_new = info_.n_new;
+    stat_.stats_landmark.back().n_final = (int)f.lm_ids.size();
+    stat_.stats_execution.emplace_back();
+}
+
+// ------------------------------------------------------------------------------ the step
+void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_right, const double & /*timestamp*/)
+{
+    if (img_left.empty() || img_right.empty() || img_left.cols != img_right.cols || img_left.rows != img_right.rows)
+        throw std::runtime_error("vo_b200: bad stereo image pair");
+    const int w = img_left.cols, h = img_left.rows;
+    if (img_left.step != img_right.step) throw std::runtime_error("vo_b200: left/right row pitch differ");
+    auto fr = std::make_shared<FrameRec>();
+    fr->id = n_frames_++;
+    ident(fr->Twc); ident(fr->Tcw); ident(fr->dT01);
+    info_ = FrameInfo();
+    info_.frame = fr->id;
+    const int k = fr->id;
+    const int sl = 2 * (k % 2), sr = 2 * (k % 2) + 1, sp = 2 * ((k + 1) % 2);
+    const int nb = p_.n_bins_u * p_.n_bins_v;
+
+    vo_stereo_frame_params fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.track.window_size = p_.window_size; fp.track.max_level = p_.max_level; fp.track.thres_error = p_.thres_error;
+    fp.track.thres_poseba_error = p_.thres_poseba_error;
+    memcpy(fp.track.K_l, p_.K_l, 16); memcpy(fp.track.K_r, p_.K_r, 16); memcpy(fp.track.T_lr, p_.T_lr, 64);
+    fp.track.do_scale_refine = p_.do_scale_refine;
+    // mask_sampson = dist < THRES_SAMPSON with dist = 100 for y > 660 (stereo_vo.cpp:657-668): the stub only fires
+    // when the threshold is below 100
+    fp.track.sampson_y = p_.thres_sampson > 100.f ? 3.0e38f : 660.f;
+    fp.thres_bidirection = p_.thres_bidirection;
+    fp.n_bins_u = p_.n_bins_u; fp.n_bins_v = p_.n_bins_v; fp.det_edge = p_.det_edge; fp.det_min_score = p_.det_min_score;
+
+    new_l_.resize((size_t)std::max(nb, 1) * 2); new_r_.resize((size_t)std::max(nb, 1) * 2);
+    float T_wc[16], dT[16];
+    vo_stereo_frame_result res;
+    memset(&res, 0, sizeof(res));
+    res.T_wc = T_wc; res.dT_pc = dT; res.new_l1 = new_l_.data(); res.new_r1 = new_r_.data(); res.counts = info_.counts;
+
+    if (!prev_) {
+        // ---- the very first image (stereo_vo.cpp:842-949)
+        fp.new_depth_gate = 0;
+        const int rc = vo_stereo_frame_step(ctx_, &fp, -1, sl, sr, img_left.data, img_right.data, w, h, img_left.step, 0, nullptr, nullptr,
+                                            nullptr, nullptr, nullptr, nullptr, &res);
+        if (rc) fail(ctx_, rc);
+        const int m = res.n_new;
+        const int base = newLandmarks(m, fr->id);
+        fr->pts_l.assign(new_l_.begin(), new_l_.begin() + 2 * (size_t)m);
+        fr->pts_r.assign(new_r_.begin(), new_r_.begin() + 2 * (size_t)m);
+        fr->lm_ids.resize(m);
+        for (int i = 0; i < m; ++i) fr->lm_ids[i] = base + i;
+        info_.n_detected = res.n_detected; info_.n_new = m;
+        reconstruct(*fr, m);                         // pose is identity: X_w = X_l (:937)
+        pushStats(*fr, false);
+        prev_ = fr;
+        return;
+    }
+
+    // ---- steady state. landmark.cpp:304: dead landmarks never survive the first compaction
+    const FrameRec &pv = *prev_;
+    const size_t n_prev = pv.lm_ids.size();
+    in_ids_.clear(); in_l0_.clear(); in_r0_.clear(); in_X_.clear(); in_tri_.clear();
+    for (size_t i = 0; i < n_prev; ++i) {
+        const int id = pv.lm_ids[i];
+        if (!lm_alive_[id]) continue;
+        in_ids_.push_back(id);
+        in_l0_.push_back(pv.pts_l[2 * i]); in_l0_.push_back(pv.pts_l[2 * i + 1]);
+        in_r0_.push_back(pv.pts_r[2 * i]); in_r0_.push_back(pv.pts_r[2 * i + 1]);
+        for (int r = 0; r < 3; ++r) in_X_.push_back(lm_X_[(size_t)id * 3 + r]);
+        in_tri_.push_back(lm_tri_[id]);
+    }
+    const int n = (int)in_ids_.size();
+    out_idx_.resize(std::max(n, 1)); out_l1_.resize((size_t)std::max(n, 1) * 2); out_r1_.resize((size_t)std::max(n, 1) * 2);
+    res.index = out_idx_.data(); res.pts_l1 = out_l1_.data(); res.pts_r1 = out_r1_.data();
+    fp.new_depth_gate = 1;
+    const int rc = vo_stereo_frame_step(ctx_, &fp, sp, sl, sr, img_left.data, img_right.data, w, h, img_left.step, n, in_l0_.data(), in_r0_.data(),
+                                        in_X_.data(), in_tri_.data(), pv.Twc, pv.dT01, &res);
+    if (rc) fail(ctx_, rc);
+    setPose(*fr, T_wc);                              // :642
+    float dT10[16];
+    inv4_f(dT, dT10);                                // :643 dT_pc_poBA.inverse()
+    inv_se3_f(dT10, fr->dT01);                       // frame.cpp:50-54
+    const int nt = res.n_tracked, m = res.n_new;
+    fr->lm_ids.resize((size_t)nt + m);
+    fr->pts_l.resize(2 * ((size_t)nt + m)); fr->pts_r.resize(2 * ((size_t)nt + m));
+    for (int i = 0; i < nt; ++i) {
+        const int id = in_ids_[out_idx_[i]];
+        fr->lm_ids[i] = id;
+        lm_last_frame_[id] = fr->id;                 // [8] addObservationAndRelatedFrame
+    }
+    memcpy(fr->pts_l.data(), out_l1_.data(), (size_t)nt * 8);
+    memcpy(fr->pts_r.data(), out_r1_.data(), (size_t)nt * 8);
+    const int base = newLandmarks(m, fr->id);        // [10] :729-734
+    for (int i = 0; i < m; ++i) fr->lm_ids[nt + i] = base + i;
+    memcpy(fr->pts_l.data() + 2 * (size_t)nt, new_l_.data(), (size_t)m * 8);
+    memcpy(fr->pts_r.data() + 2 * (size_t)nt, new_r_.data(), (size_t)m * 8);
+    info_.n_in = n; info_.n_tracked = nt; info_.n_detected = res.n_detected; info_.n_new = m;
+    // [12] keyframe (:755-827)
+    const bool kf = checkUpdateRule(*fr);
+    if (kf) {
+        info_.keyframe = 1;
+        addKeyframe(fr);
+        reconstruct(*fr, nt);                        // only the tracked survivors (n_pts is fixed before the appends, :767)
+        localBundleAdjustment();
+    }
+    pushStats(*fr, kf);
+    prev_ = fr;
+}
+
+// ------------------------------------------------------------------------------ C wrapper
+struct vo_svo { StereoVO *vo; };
+static thread_local std::string g_svo_error;
+
+extern "C" const char *vo_svo_last_error(void) { return g_svo_error.c_str(); }
+
+extern "C" int vo_svo_create(const StereoVO::Parameters *prm, vo_svo **out)
+{
+    if (!prm || !out) return VO_ERR_INVALID_ARG;
+    try { *out = new vo_svo{new StereoVO(*prm)}; return VO_OK; }
+    catch (const std::exception &e) { g_svo_error = e.what(); *out = nullptr; return VO_ERR_NO_DEVICE; }
+}
+extern "C" int vo_svo_create_from_yaml(const char *dir, vo_svo **out)
+{
+    if (!dir || !out) return VO_ERR_INVALID_ARG;
+    try { *out = new vo_svo{new StereoVO("dataset", dir)}; return VO_OK; }
+    catch (const std::exception &e) { g_svo_error = e.what(); *out = nullptr; return VO_ERR_INVALID_ARG; }
+}
+extern "C" void vo_svo_destroy(vo_svo *s) { if (s) { delete s->vo; delete s; } }
+extern "C" int vo_svo_track(vo_svo *s, const unsigned char *img_l, const unsigned char *img_r, int w, int h, size_t step, double timestamp)
+{
+    if (!s || !img_l || !img_r) return VO_ERR_INVALID_ARG;
+    try {
+        cv::Mat L(h, w, const_cast<unsigned char *>(img_l), step), R(h, w, const_cast<unsigned char *>(img_r), step);
+        s->vo->trackStereoImages(L, R, timestamp);
+        return VO_OK;
+    } catch (const std::exception &e) { g_svo_error = e.what(); return VO_ERR_NAN; }
+}
+extern "C" int vo_svo_pose(const vo_svo *s, float *T)
+{
+    if (!s || !T || s->vo->getStatistics().stats_frame.empty()) return VO_ERR_INVALID_ARG;
+    const PoseSE3 &P = s->vo->getStatistics().stats_frame.back().Twc;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[r * 4 + c] = P(r, c);
+    return VO_OK;
+}
+extern "C" int vo_svo_frame_info(const vo_svo *s, StereoVO::FrameInfo *out)
+{
+    if (!s || !out) return VO_ERR_INVALID_ARG;
+    *out = s->vo->lastFrameInfo();
+    return VO_OK;
+}
+extern "C" int vo_svo_tracks(const vo_svo *s, int cap, int *ids, float *pts_l, float *pts_r)
+{
+    if (!s) return VO_ERR_INVALID_ARG;
+    const auto &id = s->vo->currentLandmarkIds();
+    const int n = std::min<int>(cap, (int)id.size());
+    if (ids) memcpy(ids, id.data(), (size_t)n * 4);
+    if (pts_l) memcpy(pts_l, s->vo->currentPtsLeft().data(), (size_t)n * 8);
+    if (pts_r) memcpy(pts_r, s->vo->currentPtsRight().data(), (size_t)n * 8);
+    return (int)id.size();
+}
+extern "C" int vo_svo_keyframe_poses(const vo_svo *s, int cap, float *T)
+{
+    if (!s) return VO_ERR_INVALID_ARG;
+    const auto &kf = s->vo->getStatistics().stats_keyframe;
+    const int n = std::min<int>(cap, (int)kf.size());
+    for (int k = 0; k < n && T; ++k)
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[k * 16 + r * 4 + c] = kf[k].Twc(r, c);
+    return (int)kf.size();
+}
+extern "C" long long vo_svo_launch_count(const vo_svo *s) { return s ? s->vo->launchCount() : 0; }

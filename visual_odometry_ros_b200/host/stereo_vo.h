@@ -1,0 +1,141 @@
+// stereo_vo.h -- StereoVO with the reference's public API (core/visual_odometry/stereo_vo/stereo_vo.h:233-249) on top
+// of the C ABI.  The unchanged ROS nodes construct it with (mode, yaml directory), feed it image pairs and read
+// getStatistics() / getDebugImage() (ros2/visual_odometry/stereo_vo_ros2.cpp:50,104,112;
+// ros1/visual_odometry/stereo_vo_ros1.cpp:101,108,199).
+//
+// What moved: one device call per frame (vo_stereo_frame_step: both pyramids, prior, 2x trackWithPrior,
+// trackWithScale, stereo pose-only GN, compactions, bucketed detection, bidirectional stereo match of the new
+// features, depth gate -- one H2D, one D2H, one synchronisation), one more per keyframe (vo_stereo_reconstruct) and
+// the local BA (vo_lba_solve).  What stays on the host, as in the reference: the landmark / frame / keyframe
+// bookkeeping (landmark.cpp, frame.cpp, keyframes.cpp) and the window -> problem packing
+// (sparse_ba_parameters.h:292-465) -- here over flat arrays instead of a shared_ptr graph with hash lookups.
+// cv::imshow drawing, the /home/kch trajectory dump of the destructor and the console prints are not reproduced.
+#pragma once
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/vo_b200.h"
+#include "vo_shim_types.h"
+
+class StereoVO {
+public:
+    // stereo_vo.h:106-186 (field-compatible with what the nodes read)
+    struct AlgorithmStatistics {
+        struct LandmarkStatistics {
+            int n_initial = 0, n_pass_bidirection = 0, n_pass_1p = 0, n_pass_5p = 0, n_new = 0, n_final = 0;
+            int max_age = 0, min_age = 0;
+            float avg_age = 0.f;
+            int n_ok_parallax = 0;
+            float min_parallax = 0.f, max_parallax = 0.f, avg_parallax = 0.f;
+        };
+        struct FrameStatistics {
+            PoseSE3 Twc = PoseSE3::Identity(), Tcw = PoseSE3::Identity(), dT_01 = PoseSE3::Identity(), dT_10 = PoseSE3::Identity();
+            PointVec mappoints;
+        };
+        struct KeyframeStatistics {
+            PoseSE3 Twc = PoseSE3::Identity();
+            PointVec mappoints;
+        };
+        struct ExecutionStatistics {
+            float time_track = 0.f, time_1p = 0.f, time_5p = 0.f, time_localba = 0.f, time_new = 0.f, time_total = 0.f;
+        };
+        std::vector<LandmarkStatistics> stats_landmark;
+        std::vector<FrameStatistics> stats_frame;
+        std::vector<KeyframeStatistics> stats_keyframe;
+        std::vector<ExecutionStatistics> stats_execution;
+    };
+
+    // All user parameters of config/stereo/*.yaml that the step reads (stereo_vo.cpp:186-285), plus the K-det knobs.
+    struct Parameters {
+        int width = 1241, height = 376;
+        float K_l[4] = {718.856f, 718.856f, 607.1928f, 185.2157f}, K_r[4] = {718.856f, 718.856f, 607.1928f, 185.2157f};
+        float T_lr[16] = {1, 0, 0, 0.5371657189f, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // row-major
+        float thres_error = 80.f, thres_bidirection = 0.5f, thres_sampson = 60.f;
+        int window_size = 21, max_level = 6;
+        int n_bins_u = 24, n_bins_v = 12;
+        float thres_poseba_error = 3.f;
+        float thres_alive_ratio = 0.6f, thres_trans = 10.f, thres_rotation_deg = 15.f;
+        int n_max_keyframes_in_window = 9;
+        int do_scale_refine = 1;
+        int det_edge = 31;
+        long long det_min_score = 0;
+        int device = 0;
+    };
+
+    StereoVO(std::string mode, std::string directory_intrinsic);   // stereo_vo.cpp:9-53 (yaml via a minimal parser)
+    explicit StereoVO(const Parameters &prm);
+    ~StereoVO();
+    StereoVO(const StereoVO &) = delete;
+    StereoVO &operator=(const StereoVO &) = delete;
+
+    void trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_right, const double &timestamp);
+    const AlgorithmStatistics &getStatistics() const { return stat_; }
+    const cv::Mat &getDebugImage() { return img_debug_; }
+
+    // ---- introspection used by tests / bench (not part of the reference surface)
+    struct FrameInfo {
+        int frame = 0, keyframe = 0, n_in = 0, n_tracked = 0, n_detected = 0, n_new = 0, n_recon = 0;
+        int lba_points = 0, lba_obs = 0, lba_ok = 0;
+        int counts[5] = {0, 0, 0, 0, 0};
+    };
+    const FrameInfo &lastFrameInfo() const { return info_; }
+    const std::vector<int> &currentLandmarkIds() const;
+    const std::vector<float> &currentPtsLeft() const;
+    const std::vector<float> &currentPtsRight() const;
+    long long launchCount() const;
+
+private:
+    struct KfObs { int kf_id; uint8_t right; float x, y; };
+    struct FrameRec {
+        int id = 0;
+        float Twc[16], Tcw[16], dT01[16];
+        std::vector<float> pts_l, pts_r;    // interleaved x, y
+        std::vector<int> lm_ids;
+    };
+    using FrameRecPtr = std::shared_ptr<FrameRec>;
+
+    void init();
+    void setPose(FrameRec &f, const float *Twc);                 // frame.cpp:44-48
+    int newLandmarks(int k, int frame_id);
+    bool checkUpdateRule(const FrameRec &f) const;               // keyframes.cpp:217-303
+    void addKeyframe(const FrameRecPtr &f);                      // keyframes.cpp:177-215
+    void reconstruct(FrameRec &f, int n_first);                  // stereo_vo.cpp:767-797 / 911-941
+    void localBundleAdjustment();                                // motion_estimator.cpp:1207-1340 + sparse_ba_parameters.h:292-465
+    void pushStats(const FrameRec &f, bool keyframe);
+
+    Parameters p_;
+    vo_ctx *ctx_ = nullptr;
+    AlgorithmStatistics stat_;
+    cv::Mat img_debug_;
+    FrameInfo info_;
+    // landmark table (SoA)
+    std::vector<float> lm_X_;
+    std::vector<uint8_t> lm_tri_, lm_alive_, lm_bundled_;
+    std::vector<int> lm_last_frame_;
+    std::vector<std::vector<KfObs>> lm_kf_obs_;
+    FrameRecPtr prev_;
+    std::deque<FrameRecPtr> window_;
+    std::vector<FrameRecPtr> all_keyframes_;
+    int n_frames_ = 0;
+    // per-frame scratch
+    std::vector<float> in_l0_, in_r0_, in_X_, out_l1_, out_r1_, new_l_, new_r_;
+    std::vector<uint8_t> in_tri_;
+    std::vector<int> in_ids_, out_idx_;
+};
+
+// C wrapper so that the tests and bench.py (ctypes) can drive the class.
+extern "C" {
+typedef struct vo_svo vo_svo;
+VO_API int vo_svo_create(const StereoVO::Parameters *prm, vo_svo **out);
+VO_API int vo_svo_create_from_yaml(const char *directory_intrinsic, vo_svo **out);
+VO_API void vo_svo_destroy(vo_svo *s);
+VO_API int vo_svo_track(vo_svo *s, const unsigned char *img_l, const unsigned char *img_r, int w, int h, size_t step, double timestamp);
+VO_API int vo_svo_pose(const vo_svo *s, float *T_wc16);                      // row-major, last frame
+VO_API int vo_svo_frame_info(const vo_svo *s, StereoVO::FrameInfo *out);
+VO_API int vo_svo_tracks(const vo_svo *s, int cap, int *ids, float *pts_l, float *pts_r);   // returns the count
+VO_API int vo_svo_keyframe_poses(const vo_svo *s, int cap, float *T_wc16);                    // returns the count
+VO_API long long vo_svo_launch_count(const vo_svo *s);
+VO_API const char *vo_svo_last_error(void);
+}
