@@ -418,7 +418,89 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                            "what": "vo_stereo_track_step (host buffers): 2 image uploads + prior + 2x trackWithPrior (2000 feat, "
                                    "4 levels, win 21) [+ trackWithScale] + stereo pose GN + compactions, wall clock incl. all "
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
+    res["sequence"] = sequence_measurement(torch, dev, synth)
+    res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
     return res
+
+
+def cfg4_measurement(ctx, synth):
+    """BASELINE config 4: sliding-window local BA (10 stereo keyframes x 5000 landmarks, Schur-complement LM, 10
+    iterations) and the depth filter (20 000 seeds) through the host C ABI, next to the 1-core CPU restatement."""
+    from oracle import lba as olba, misc as omisc
+    p = synth.lba_problem(seed=4004, n_kf=10, n_points=5000)
+    for _ in range(3):
+        out = ctx.lba_solve(p)
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = ctx.lba_solve(p)
+    gpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+    t0 = time.perf_counter()
+    rc, poses_o, points_o, avg_o, ok_o = olba.lba_solve(p)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    rng = np.random.default_rng(4004)
+    n = 20000
+    x0, c0 = rng.uniform(0.02, 0.5, n), rng.uniform(1e-6, 1e-3, n)
+    x1, c1 = rng.uniform(0.02, 0.5, n), rng.uniform(1e-6, 1e-3, n)
+    for _ in range(3):
+        ctx.depth_filter_normal(x0, c0, x1, c1)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.depth_filter_normal(x0, c0, x1, c1)
+    df_ms = (time.perf_counter() - t0) * 1e3 / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        omisc.depth_filter_normal(x0, c0, x1, c1)
+    df_cpu_ms = (time.perf_counter() - t0) * 1e3 / 20
+    return {"lba_ms": gpu_ms, "lba_cpu_port_ms_1core": cpu_ms, "keyframes": 10, "landmarks": int(p["n_points"]), "observations": int(p["n_obs"]),
+            "iterations": int(p["max_iter"]), "lba_final_avg_err_px": float(out[2][-1]), "lba_max_pose_diff_vs_cpu": float(np.abs(out[0] - poses_o).max()),
+            "depth_filter_ms": df_ms, "depth_filter_cpu_port_ms_1core": df_cpu_ms, "seeds": n,
+            "what": "vo_lba_solve / vo_depth_filter_normal with host buffers, wall clock incl. H2D/D2H and the sync"}
+
+
+def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12):
+    """BASELINE config 3: the full stereo VO step over a synthetic KITTI-like sequence through the reference-API class
+    (host images in, pose out; tracking + new features every frame, reconstruction + local BA on keyframes)."""
+    from oracle import stereo_vo as osvo
+    from visual_odometry_ros_b200 import stereo_vo as svo
+    L, R, T_true = synth.stereo_sequence(n_frames, W, H, synth.kitti_K(), seed=3003, device=str(dev))
+    K4, Tlr = synth.kitti_K(), synth.kitti_T_lr()
+    nbu, nbv = 64, 32
+    Lp, Rp = torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()
+    vo = svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    ms, kf, nfeat = [], [], []
+    launches0 = vo.launch_count
+    for k in range(n_frames):
+        t0 = time.perf_counter()
+        vo.trackStereoImages(Lp[k], Rp[k], 0.1 * k)
+        ms.append((time.perf_counter() - t0) * 1e3)
+        fi = vo.frame_info()
+        kf.append(fi["keyframe"])
+        nfeat.append(fi["n_in"])
+    launches = vo.launch_count - launches0
+    T_g = vo.pose()
+    gt = np.linalg.inv(T_true[0]) @ T_true[n_frames - 1]
+    drift = float(np.linalg.norm(T_g[:3, 3] - gt[:3, 3]) / max(1e-9, np.linalg.norm(gt[:3, 3])))
+    vo.close()
+    ms, kf = np.asarray(ms[2:]), np.asarray(kf[2:], bool)       # skip the first frame and the first (allocating) step
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
+    ora = osvo.StereoVOOracle(W, H, K4, K4, Tlr, osvo.default_params(window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    cms = []
+    for k in range(n_cpu):
+        t0 = time.perf_counter()
+        ora.track(L[k], R[k])
+        cms.append((time.perf_counter() - t0) * 1e3)
+    return {"frames": n_frames, "ms_per_frame_mean": float(ms.mean()), "ms_per_frame_median": float(np.median(ms)),
+            "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
+            "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None, "keyframes": int(kf.sum()),
+            "mean_tracked_features": float(np.mean(nfeat[2:])), "bins": [nbu, nbv], "gpu_launches": int(launches),
+            "translation_drift_vs_ground_truth": drift,
+            "cpu_ms_per_frame": float(np.mean(cms[2:])), "cpu_frames": n_cpu, "cpu_cores": os.cpu_count() or 1,
+            "what": "StereoVO::trackStereoImages drop-in (host u8 images in, pose out): fused frame step (pyramids, prior, 2x trackWithPrior, "
+                    "trackWithScale, stereo pose GN, compactions, bucketed detection, bidirectional stereo match of new features) every "
+                    "frame; reconstruction + 10-iteration local BA on keyframes; wall clock incl. all copies/syncs and the host "
+                    "bookkeeping; cpu = oracle composition (cv2 LK on all threads + C restatements + numpy detector)"}
 
 
 if __name__ == "__main__":
