@@ -296,6 +296,7 @@ __device__ __forceinline__ void pf_hsum4(uint32_t w0, uint32_t w1, uint32_t w2, 
 
 // Write one level from its shared-memory tile: interior (optional), ring copies of the owned pixels, Scharr plane.
 // s points at the tile, (CXl, HYl) is the tile position of the owned origin (ax, ay).  Requires w, h >= VO_PAD + 2.
+template <int LOGWQ>      // log2 of the words per owned row of a full tile: (128 >> l) / 4
 __device__ __forceinline__ void pf_emit(const LevelDesc L, const uint8_t *__restrict__ s, int P, int CXl, int HYl, int ax, int bx, int ay,
                                         int by, bool write_interior, bool write_ring, bool with_deriv)
 {
@@ -303,29 +304,28 @@ __device__ __forceinline__ void pf_emit(const LevelDesc L, const uint8_t *__rest
     if (ow <= 0 || oh <= 0) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int wq = (ow + 3) >> 2;
+    constexpr int WQF = 1 << LOGWQ;
     const int mx = L.w - 1, my = L.h - 1;
     // ---- interior words + the vertical ring copies of the same words (rows 1..32 -> -1..-32, rows h-33..h-2 -> h..h+31)
     if (write_interior || write_ring) {
-        for (int r = ty; r < oh; r += 8) {
+        for (int i = threadIdx.x; i < (oh << LOGWQ); i += 256) {
+            const int r = i >> LOGWQ, c = i & (WQF - 1);
+            if (c >= wq) continue;
             const int y = ay + r;
             // up to three destination rows: the row itself, its copy above the image, its copy below the image
-            int yt[3], ny = 0;
-            if (write_interior) yt[ny++] = y;
-            if (write_ring && y >= 1 && y <= VO_PAD) yt[ny++] = -y;
-            if (write_ring && my - y >= 1 && my - y <= VO_PAD) yt[ny++] = 2 * my - y;
-            if (ny == 0) continue;
-            const uint8_t *srow = s + (r + HYl) * P + CXl;
-            for (int c = tx; c < wq; c += 32) {
-                const int x = ax + 4 * c;
-                const uint32_t v = *reinterpret_cast<const uint32_t *>(srow + 4 * c);
-                const bool full = x + 3 < L.w;
+            const int yt0 = write_interior ? y : 0x7fffffff;
+            const int yt1 = (write_ring && y >= 1 && y <= VO_PAD) ? -y : 0x7fffffff;
+            const int yt2 = (write_ring && my - y >= 1 && my - y <= VO_PAD) ? 2 * my - y : 0x7fffffff;
+            const int x = ax + 4 * c;
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(s + (r + HYl) * P + CXl + 4 * c);
+            const bool full = x + 3 < L.w;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (q >= ny) break;
-                    uint8_t *o = L.img + (ptrdiff_t)yt[q] * L.pitch + x;
-                    if (full) *reinterpret_cast<uint32_t *>(o) = v;
-                    else for (int k = 0; x + k < L.w; ++k) o[k] = (uint8_t)(v >> (8 * k));
-                }
+            for (int q = 0; q < 3; ++q) {
+                const int yt = q == 0 ? yt0 : (q == 1 ? yt1 : yt2);
+                if (yt == 0x7fffffff) continue;
+                uint8_t *o = L.img + (ptrdiff_t)yt * L.pitch + x;
+                if (full) *reinterpret_cast<uint32_t *>(o) = v;
+                else for (int k = 0; x + k < L.w; ++k) o[k] = (uint8_t)(v >> (8 * k));
             }
         }
     }
@@ -351,10 +351,12 @@ __device__ __forceinline__ void pf_emit(const LevelDesc L, const uint8_t *__rest
     }
     // ---- Scharr plane: 4 pixels per thread, dp4a on byte-transposed columns (a_j, b_j, c_j, 0)
     if (with_deriv) {
-        for (int r = ty; r < oh; r += 8) {
+        for (int i = threadIdx.x; i < (oh << LOGWQ); i += 256) {
+            const int r = i >> LOGWQ, c = i & (WQF - 1);
+            if (c >= wq) continue;
             const int y = ay + r;
             const uint8_t *r0 = s + (r + HYl - 1) * P + CXl, *r1 = r0 + P, *r2 = r1 + P;
-            for (int c = tx; c < wq; c += 32) {
+            {
                 const int x0 = ax + 4 * c;
                 const uint32_t a = *reinterpret_cast<const uint32_t *>(r0 + 4 * c);
                 const uint32_t b = *reinterpret_cast<const uint32_t *>(r1 + 4 * c);
@@ -424,7 +426,7 @@ __device__ __forceinline__ void pf_level(const SlotDesc &S, uint8_t *smem, int X
     const int ax = X0 >> l, ay = Y0 >> l;
     const int bx = min(L.w, (X0 + PF_TW) >> l), by = min(L.h, (Y0 + PF_TH) >> l);
     const uint8_t *sl = smem + C::OFF(l);
-    pf_emit(L, sl, C::P(l), C::CX(l), C::HY(l), ax, bx, ay, by, l > 0 || from_raw, l > 0 || write_ring0, with_deriv != 0);
+    pf_emit<5 - l>(L, sl, C::P(l), C::CX(l), C::HY(l), ax, bx, ay, by, l > 0 || from_raw, l > 0 || write_ring0, with_deriv != 0);
     if constexpr (l + 1 < NL) {
         const LevelDesc D = S.lv[l + 1];
         uint8_t *sd = smem + C::OFF(l + 1);
