@@ -314,38 +314,47 @@ class CorridorRenderer:
         K = kitti_K() if K is None else np.asarray(K, np.float32)
         self.K = [float(v) for v in K]
         self.noise_sigma, self.seed = noise_sigma, seed
-        mips = []
+        # mip atlas: every level of every plane flattened into one 1-D tensor, so a pixel's two mip levels are
+        # fetched with plain gathers (8 taps per pixel whatever its level)
+        chunks, self.atlas_off, self.atlas_n = [], [], []
+        pos = 0
         for plane in range(4):
             t = torch.from_numpy(_fractal_texture(seed * 7 + plane)).to(self.device)
-            lv = [t]
-            for _ in range(self.LEVELS - 1):
-                lv.append(torch.nn.functional.avg_pool2d(lv[-1][None, None], 2)[0, 0])
-            mips.append(lv)
-        self.mips = mips
+            offs, ns = [], []
+            for _ in range(self.LEVELS):
+                offs.append(pos); ns.append(t.shape[0])
+                chunks.append(t.reshape(-1))
+                pos += t.numel()
+                t = torch.nn.functional.avg_pool2d(t[None, None], 2)[0, 0]
+            self.atlas_off.append(offs); self.atlas_n.append(ns)
+        self.atlas = torch.cat(chunks)
+        self.atlas_off_t = torch.tensor(self.atlas_off, dtype=torch.long, device=self.device)      # [4, LEVELS]
+        self.atlas_n_t = torch.tensor(self.atlas_n, dtype=torch.long, device=self.device)
         ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64, device=self.device),
                                 torch.arange(w, dtype=torch.float64, device=self.device), indexing="ij")
         self.dc = torch.stack([(xs - self.K[2]) / self.K[0], (ys - self.K[3]) / self.K[1], torch.ones_like(xs)], -1)
         self.frame_no = 0
 
     def _sample(self, plane, u, v, lam):
+        """Trilinear sample; plane is a per-pixel long tensor."""
         torch = self.torch
-        out = torch.zeros_like(u)
         l0 = torch.clamp(torch.floor(lam), 0, self.LEVELS - 2)
         fr = torch.clamp(lam - l0, 0.0, 1.0)
-        for l in range(self.LEVELS):
-            tex = self.mips[plane][l]
-            n = tex.shape[0]
-            wgt = torch.where(l0 == l, 1.0 - fr, torch.where(l0 == l - 1, fr, torch.zeros_like(fr)))
-            if not bool((wgt > 0).any()):
-                continue
-            s = 1.0 / (1 << l)
+        l0 = l0.long()
+        out = torch.zeros_like(u)
+        for dl, wgt in ((0, 1.0 - fr), (1, fr)):
+            l = l0 + dl
+            n = self.atlas_n_t[plane, l]
+            off = self.atlas_off_t[plane, l]
+            s = torch.pow(0.5, l.to(u.dtype))
             uu, vv = u * s - 0.5, v * s - 0.5
             u0, v0 = torch.floor(uu), torch.floor(vv)
             au, av = uu - u0, vv - v0
             iu0, iv0 = u0.long() % n, v0.long() % n
             iu1, iv1 = (iu0 + 1) % n, (iv0 + 1) % n
-            val = (tex[iv0, iu0] * (1 - au) * (1 - av) + tex[iv0, iu1] * au * (1 - av) +
-                   tex[iv1, iu0] * (1 - au) * av + tex[iv1, iu1] * au * av)
+            A = self.atlas
+            val = (A[off + iv0 * n + iu0] * (1 - au) * (1 - av) + A[off + iv0 * n + iu1] * au * (1 - av) +
+                   A[off + iv1 * n + iu0] * (1 - au) * av + A[off + iv1 * n + iu1] * au * av)
             out = out + wgt * val
         return out
 
@@ -364,15 +373,10 @@ class CorridorRenderer:
         t = torch.clamp(t, max=5000.0)
         P = torch.stack([ox + t * d[..., 0], oy + t * d[..., 1], oz + t * d[..., 2]], -1)
         lam = torch.log2(torch.clamp(t * self.PPM / self.K[0], min=1.0)) + 0.5
-        img = torch.zeros_like(t)
-        for plane in range(4):
-            m = which == plane
-            if not bool(m.any()):
-                continue
-            a = P[..., 0] if plane < 2 else P[..., 1]
-            u = (a * self.PPM + 137.0 * plane)[m]
-            v = (P[..., 2] * self.PPM)[m]
-            img[m] = self._sample(plane, u, v, lam[m]).to(img.dtype)
+        a = torch.where(which < 2, P[..., 0], P[..., 1])
+        u = a * self.PPM + 137.0 * which.to(a.dtype)
+        v = P[..., 2] * self.PPM
+        img = self._sample(which, u, v, lam)
         noise = torch.randn(img.shape, generator=gen, dtype=torch.float64) * self.noise_sigma
         img = img + noise.to(self.device)
         return torch.clamp(torch.round(img), 0, 255).to(torch.uint8), t
