@@ -238,6 +238,41 @@ VO_API int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *prm, 
 VO_API int vo_stereo_reconstruct(vo_ctx *ctx, const float *pts_l, const float *pts_r, int n, const float *K_l4,
                           const float *K_r4, const float *T_lr, const float *T_wc, float *Xw_out, uint8_t *ok_out);
 
+/* ------------------------------------------------------------------ mono frame step
+ * Steady-state branch of MonoVO::trackImage (core/visual_odometry/mono_vo/mono_vo.cpp:724-992), device resident, one
+ * synchronisation: constant-velocity prior and patch scale for the bundled landmarks (:739-761),
+ * trackBidirectionWithPrior(I0 -> I1) (:768), trackWithScale (:783), selection of the pose-only-BA landmarks (bundled
+ * when use_bundled_only, i.e. more than 5 keyframes, else triangulated; depth in the previous frame > 0.1, :799-827),
+ * mono pose-only GN from dT01_prior (:860-866), inlier scatter, dT10 = inverseSE3_f(dT01), T_wc = T_wc_prev * dT01,
+ * Sampson gate with F10 = Kinv^T [t10]x R10 Kinv (motion_estimator.cpp:539-568; mono_vo.cpp:957-962), stable
+ * compaction; then bucketed detection on I1 with the survivors as occupancy and trackBidirection(I1 -> I0) of the new
+ * points (:981-992).  flags[i]: bit 0 = Landmark::isTriangulated(), bit 1 = Landmark::isBundled().
+ * The reference's fallback to cv::findEssentialMat when fewer than 11 landmarks are selected or the GN fails
+ * (:909-949) is third-party RANSAC outside this build: the call then returns VO_ERR_MODE (new features are still
+ * returned) and leaves the pose outputs untouched. */
+typedef struct vo_mono_frame_params {
+    int window_size, max_level;      /* feature_tracker.window_size / max_level */
+    float thres_error, thres_bidirection, thres_sampson;
+    float thres_poseba_error;        /* truncated to int as the reference's `const int &` parameter does */
+    float K[4];                      /* fx, fy, cx, cy */
+    int use_bundled_only;            /* keyframes_->getList().size() > 5 (mono_vo.cpp:800) */
+    int do_scale_refine;
+    int n_bins_u, n_bins_v, det_edge;
+    long long det_min_score;
+} vo_mono_frame_params;
+typedef struct vo_mono_frame_result {
+    float *T_wc, *dT01, *dT10;       /* [16] row-major each */
+    int n_tracked;
+    int *index;                      /* [n] */
+    float *pts1;                     /* [n][2] */
+    int *counts;                     /* [5] nullable: after K4, after K7, GN points, after the motion gate, final */
+    int n_detected, n_new;
+    float *new_p1, *new_p0;          /* [n_bins_u * n_bins_v][2]: new points in I1 and their back-tracked position in I0 */
+} vo_mono_frame_result;
+VO_API int vo_mono_frame_step(vo_ctx *ctx, const vo_mono_frame_params *prm, int slot_0, int slot_1, const uint8_t *img_1,
+                       int w, int h, size_t step, int n, const float *pts0, const float *Xw, const uint8_t *flags,
+                       const float *T_wc_prev, const float *dT01_prior, vo_mono_frame_result *res);
+
 /* ------------------------------------------------------------------ triangulation
  * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */
 VO_API int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,

@@ -61,6 +61,18 @@ class StereoFrameResult(ctypes.Structure):
                 ("counts", vp), ("n_detected", ctypes.c_int), ("n_new", ctypes.c_int), ("new_l1", vp), ("new_r1", vp)]
 
 
+class MonoFrameParams(ctypes.Structure):
+    _fields_ = [("window_size", ctypes.c_int), ("max_level", ctypes.c_int), ("thres_error", ctypes.c_float),
+                ("thres_bidirection", ctypes.c_float), ("thres_sampson", ctypes.c_float), ("thres_poseba_error", ctypes.c_float),
+                ("K", ctypes.c_float * 4), ("use_bundled_only", ctypes.c_int), ("do_scale_refine", ctypes.c_int),
+                ("n_bins_u", ctypes.c_int), ("n_bins_v", ctypes.c_int), ("det_edge", ctypes.c_int), ("det_min_score", ctypes.c_longlong)]
+
+
+class MonoFrameResult(ctypes.Structure):
+    _fields_ = [("T_wc", vp), ("dT01", vp), ("dT10", vp), ("n_tracked", ctypes.c_int), ("index", vp), ("pts1", vp), ("counts", vp),
+                ("n_detected", ctypes.c_int), ("n_new", ctypes.c_int), ("new_p1", vp), ("new_p0", vp)]
+
+
 class LbaProblem(ctypes.Structure):
     _fields_ = [
         ("n_frames", ctypes.c_int), ("n_opt", ctypes.c_int), ("n_points", ctypes.c_int), ("n_obs", ctypes.c_int),
@@ -128,6 +140,8 @@ def lib():
     L.vo_stereo_frame_step.argtypes = [vp, ctypes.POINTER(StereoFrameParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, vp,
                                        ctypes.POINTER(StereoFrameResult)]
+    L.vo_mono_frame_step.argtypes = [vp, ctypes.POINTER(MonoFrameParams), ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.POINTER(MonoFrameResult)]
     L.vo_stereo_reconstruct.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
@@ -523,3 +537,36 @@ class Context:
         k, m = res.n_tracked, res.n_new
         return dict(T_wc=T_wc, dT_pc=dT, index=idx[:k].copy(), pts_l1=o_l1[:k].copy(), pts_r1=o_r1[:k].copy(),
                     counts=[int(c) for c in counts], n_detected=res.n_detected, new_l1=n_l1[:m].copy(), new_r1=n_r1[:m].copy())
+
+    def mono_frame_step(self, slot_0, slot_1, img_1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_prior, K, win, max_level,
+                        thres_err, thres_bi, thres_sampson, thres_poseba, use_bundled_only, n_bins_u=0, n_bins_v=0, det_edge=31,
+                        det_min_score=0, do_scale_refine=True):
+        """Steady-state branch of MonoVO::trackImage (mono_vo.cpp:724-992), one synchronisation."""
+        prm = MonoFrameParams()
+        prm.window_size, prm.max_level, prm.thres_error = int(win), int(max_level), float(thres_err)
+        prm.thres_bidirection, prm.thres_sampson, prm.thres_poseba_error = float(thres_bi), float(thres_sampson), float(thres_poseba)
+        prm.K = (ctypes.c_float * 4)(*[float(v) for v in K])
+        prm.use_bundled_only, prm.do_scale_refine = int(bool(use_bundled_only)), int(bool(do_scale_refine))
+        prm.n_bins_u, prm.n_bins_v, prm.det_edge, prm.det_min_score = int(n_bins_u), int(n_bins_v), int(det_edge), int(det_min_score)
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        X = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3)
+        fl = (np.asarray(triangulated).astype(np.uint8) | (np.asarray(bundled).astype(np.uint8) << 1)).astype(np.uint8)
+        n = len(p0)
+        Twp = np.ascontiguousarray(T_wc_prev, np.float32)
+        dTp = np.ascontiguousarray(dT01_prior, np.float32)
+        T_wc, dT01, dT10 = (np.zeros((4, 4), np.float32) for _ in range(3))
+        idx = np.zeros(max(n, 1), np.int32)
+        o1 = np.zeros((max(n, 1), 2), np.float32)
+        nbins = max(1, n_bins_u * n_bins_v)
+        n1, n0 = np.zeros((nbins, 2), np.float32), np.zeros((nbins, 2), np.float32)
+        counts = np.zeros(5, np.int32)
+        res = MonoFrameResult()
+        res.T_wc, res.dT01, res.dT10, res.index, res.pts1, res.counts = _ptr(T_wc), _ptr(dT01), _ptr(dT10), _ptr(idx), _ptr(o1), _ptr(counts)
+        res.new_p1, res.new_p0 = _ptr(n1), _ptr(n0)
+        assert img_1.dtype == np.uint8 and img_1.ndim == 2 and img_1.strides[1] == 1
+        h, w, step = img_1.shape[0], img_1.shape[1], img_1.strides[0]
+        check(self.h, self.L.vo_mono_frame_step(self.h, ctypes.byref(prm), slot_0, slot_1, _ptr(img_1), w, h, step, n, _ptr(p0), _ptr(X),
+                                                _ptr(fl), _ptr(Twp), _ptr(dTp), ctypes.byref(res)))
+        k, m = res.n_tracked, res.n_new
+        return dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx[:k].copy(), pts1=o1[:k].copy(), counts=[int(c) for c in counts],
+                    n_detected=res.n_detected, new_p1=n1[:m].copy(), new_p0=n0[:m].copy())

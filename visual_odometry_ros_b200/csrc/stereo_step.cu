@@ -17,6 +17,7 @@
 // list is compacted once at the end -- results and indexing are identical, with two scans instead of five
 // reallocations.  Compiled with -fmad=false (FP32 glue arithmetic in the reference's operation order).
 #include "vo_internal.cuh"
+#include "step_device.cuh"
 #include "tri_device.cuh"
 
 #include <cstring>
@@ -46,12 +47,6 @@ struct StepDev {
     float sampson_y;
 };
 
-__device__ __forceinline__ void xform(const float *T, const float *X, float *Y)
-{
-#pragma unroll
-    for (int r = 0; r < 3; ++r) Y[r] = ((T[r * 4 + 0] * X[0] + T[r * 4 + 1] * X[1]) + T[r * 4 + 2] * X[2]) + T[r * 4 + 3];
-}
-
 // stereo_vo.cpp:485-522
 __global__ void __launch_bounds__(256) k_step_prior(const StepDev d)
 {
@@ -78,32 +73,6 @@ __global__ void __launch_bounds__(256) k_step_prior(const StepDev d)
     d.pts_r1[i] = q1;
     d.scale[i] = scale;
     d.mask[i] = 1;
-}
-
-// Single-CTA stable compaction helper: returns, for every thread's element of the current chunk, its
-// output position (or -1), and advances the running base in shared memory.
-__device__ __forceinline__ int scan_chunk(bool keep, int *s_warp, int *s_base)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    const int within = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
-    if (wid == 0) {
-        int v = s_warp[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += t;
-        }
-        s_warp[lane] = v;
-    }
-    __syncthreads();
-    const int pos = keep ? (*s_base + (wid ? s_warp[wid - 1] : 0) + within) : -1;
-    __syncthreads();
-    if (tid == 0) *s_base += s_warp[31];
-    __syncthreads();
-    return pos;
 }
 
 // [6] input: stable compaction of (mask AND triangulated), Xp = T_pw * X  (stereo_vo.cpp:595-614)
@@ -157,19 +126,6 @@ __global__ void __launch_bounds__(1024) k_step_finish(const StepDev d)
         if (keep) { d.idx_out[pos] = i; d.out_l1[pos] = d.pts_l1[i]; d.out_r1[pos] = d.pts_r1[i]; }
     }
     if (tid == 0) { *d.n_out = s_base; d.counts[4] = s_base; d.counts[3] = n_po; }
-}
-
-__global__ void __launch_bounds__(1024) k_step_count(const uint8_t *mask, int n, int *out)
-{
-    __shared__ int s;
-    if (threadIdx.x == 0) s = 0;
-    __syncthreads();
-    int c = 0;
-    for (int i = threadIdx.x; i < n; i += 1024) c += mask[i] ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s, c);
-    __syncthreads();
-    if (threadIdx.x == 0) *out = s;
 }
 
 // ------------------------------------------------------------------------------ new features / reconstruction
