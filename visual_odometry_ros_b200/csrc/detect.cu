@@ -9,7 +9,7 @@
 //     a = sum_7x7 Ix^2 >> 10, b = sum_7x7 Ix*Iy >> 10, c = sum_7x7 Iy^2 >> 10
 //     score = 25 * (a*c - b*b) - (a+c)^2          (int64; Harris with k = 1/25)
 // Candidates are integer pixels with edge <= x < w-edge, edge <= y < h-edge, score > min_score; ties inside a
-// bin go to the first pixel in raster order.  Bit-exact against oracle/detect.py.
+// bin go to the first pixel in raster order.  Bit-exact against its numpy restatement (test infrastructure).
 //
 // Launch sequence (all asynchronous on the context's stream):
 //   k_det_reset  : weight = 1, best = min_score, arg = INT_MAX
