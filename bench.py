@@ -314,7 +314,11 @@ def main():
                 "ms_per_step": e2e_ms, "steps": Ke, "api": "vo_ft_track_batch (host buffers)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_klt2<21,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_klt2 launch (64 pairs x 2000 features) from the
+                     # committed `ncu --set full` capture profiles/r1_v3_klt_full_raw.csv: 241.54 MB + 5.46 MB
+                     "traffic": 247.0e6 if klt_launches_per_step * 64 == P else None, "traffic_source": "profiles/r1_v3_klt_full_raw.csv",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": klt_bytes_per_step / klt_launches_per_step,
                      "launch_ms": klt_ms / klt_launches_per_step, "launches_per_step": klt_launches_per_step,
                      "lk_templates": n_templ, "lk_iterations": n_iter},
