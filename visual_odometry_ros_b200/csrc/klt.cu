@@ -53,6 +53,28 @@ __device__ __forceinline__ long long warp_sum_exact(int v)
     return ((long long)shi << 16) + (long long)slo;
 }
 
+// The same exact 32-lane sum, rounded ONCE to float: |hi-sum| <= 2^20 and lo-sum < 2^21 are exact in FP32 and the
+// fused multiply-add rounds the exact value hi*2^16 + lo once, i.e. identically to I2F.S64 of the 64-bit sum
+// (which costs an IMAD.WIDE and a multi-cycle 64-bit conversion per sum in the iteration tail).
+__device__ __forceinline__ float warp_sum_exact_f(int v)
+{
+    const int shi = __reduce_add_sync(0xffffffffu, v >> 16);
+    const int slo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    return __fmaf_rn((float)shi, 65536.f, (float)slo);
+}
+
+// OpenCV's stop tests are written in double on float operands; both have exact FP32 equivalents except inside a
+// 2e-4 relative band around epsilon^2, where the double path decides (warp-uniform branch):
+//   delta.ddot(delta) <= eps2            dx*dx + dy*dy, products exact in double, one rounding
+//   std::abs(dx + prevDelta.x) < 0.01    f < 0.01 (double)  <=>  f <= 0.01f, because 0.01f < 0.01 < nextafter(0.01f)
+__device__ __forceinline__ bool klt_eps_reached(float dx, float dy, double eps2, float eps2_lo, float eps2_hi)
+{
+    const float s = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+    if (s < eps2_lo) return true;
+    if (s > eps2_hi) return false;
+    return __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2;
+}
+
 __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11)
 {
     const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
@@ -375,6 +397,7 @@ k_klt2(const KltArgs a)
     const SlotDesc &S1 = a.slots[a.s1.id[pair]];
     const float halfWin = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
+    const float eps2_lo = (float)a.eps2 * 0.9999f, eps2_hi = (float)a.eps2 * 1.0001f;
 
     // run geometry of this lane (level independent). Idle slots alias an existing run; their
     // contributions are dropped per RUN (run_ok), never per pixel.
@@ -466,9 +489,9 @@ k_klt2(const KltArgs a)
                 sA11 += run_ok[q] ? a11 : 0; sA12 += run_ok[q] ? a12 : 0; sA22 += run_ok[q] ? a22 : 0;
             }
         }
-        const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
-        const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
-        const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
+        const float A11 = __fmul_rn(warp_sum_exact_f(sA11), FLT_SCALE);
+        const float A12 = __fmul_rn(warp_sum_exact_f(sA12), FLT_SCALE);
+        const float A22 = __fmul_rn(warp_sum_exact_f(sA22), FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dif = __fsub_rn(A11, A22);
         const float minEig = __fdiv_rn(
@@ -516,14 +539,14 @@ k_klt2(const KltArgs a)
                 }
                 sb1 += run_ok[q] ? b1q : 0; sb2 += run_ok[q] ? b2q : 0;
             }
-            const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
-            const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
+            const float b1 = __fmul_rn(warp_sum_exact_f(sb1), FLT_SCALE);
+            const float b2 = __fmul_rn(warp_sum_exact_f(sb2), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nextx = __fadd_rn(nextx, dx); nexty = __fadd_rn(nexty, dy);
             stored.x = __fadd_rn(nextx, halfWin); stored.y = __fadd_rn(nexty, halfWin);
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= a.eps2) { ++j; break; }
-            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+            if (klt_eps_reached(dx, dy, a.eps2, eps2_lo, eps2_hi)) { ++j; break; }
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                 stored.x = __fsub_rn(stored.x, __fmul_rn(dx, 0.5f));
                 stored.y = __fsub_rn(stored.y, __fmul_rn(dy, 0.5f));
                 ++j;
