@@ -140,6 +140,8 @@ extern "C" long long vo_ctx_launch_count(const vo_ctx *ctx) { return ctx ? ctx->
 int vo_stage_reserve(vo_ctx *ctx, size_t bytes)
 {
     if (bytes <= ctx->stage_bytes) return VO_OK;
+    // grow geometrically (pinned allocations cost tens of milliseconds; callers' sizes creep up frame by frame)
+    if (ctx->stage_bytes && bytes < ctx->stage_bytes * 2) bytes = ctx->stage_bytes * 2;
     bytes = align_up(bytes, 4096);
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);

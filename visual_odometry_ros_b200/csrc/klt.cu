@@ -378,8 +378,11 @@ __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_
 #define KLT2_RND (1 << (W_BITS - 5 - 1))
 #define KLT2_SH (W_BITS - 5)
 
+#ifndef KLT2_WPB
+#define KLT2_WPB 4          // warps (features) per CTA
+#endif
 template <int WIN, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+__global__ void __launch_bounds__(32 * KLT2_WPB, MINB * 4 / KLT2_WPB)
 k_klt2(const KltArgs a)
 {
     using C = Klt2Cfg<WIN>;
@@ -600,11 +603,12 @@ k_klt2(const KltArgs a)
 template <int WIN>
 static cudaError_t launch_klt2(const KltArgs &a, dim3 grd, cudaStream_t st)
 {
-    const size_t smem = (size_t)4 * Klt2Cfg<WIN>::WARP_WORDS * 4;
+    const size_t smem = (size_t)KLT2_WPB * Klt2Cfg<WIN>::WARP_WORDS * 4;
+    grd.x = (grd.x * 4 + KLT2_WPB - 1) / KLT2_WPB;
     static const int minb = getenv("VO_KLT_MINB") ? atoi(getenv("VO_KLT_MINB")) : KLT2_MIN_BLOCKS;   // tuning switch
-    if (minb >= 6) k_klt2<WIN, 6><<<grd, 128, smem, st>>>(a);
-    else if (minb == 5) k_klt2<WIN, 5><<<grd, 128, smem, st>>>(a);
-    else k_klt2<WIN, 4><<<grd, 128, smem, st>>>(a);
+    if (minb >= 6) k_klt2<WIN, 6><<<grd, 32 * KLT2_WPB, smem, st>>>(a);
+    else if (minb == 5) k_klt2<WIN, 5><<<grd, 32 * KLT2_WPB, smem, st>>>(a);
+    else k_klt2<WIN, 4><<<grd, 32 * KLT2_WPB, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -702,8 +702,11 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
         VO_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_lba) cudaFree(ctx->d_lba);
         ctx->d_lba = nullptr; ctx->lba_bytes = 0;
-        VO_CUDA(cudaMalloc(&ctx->d_lba, total));
-        ctx->lba_bytes = total;
+        // grow geometrically: window problems grow by a few landmarks per keyframe and a cudaFree + cudaMalloc
+        // pair costs milliseconds
+        const size_t want = total + total / 2;
+        VO_CUDA(cudaMalloc(&ctx->d_lba, want));
+        ctx->lba_bytes = want;
     }
     int rc = vo_stage_reserve(ctx, in_bytes > (size_t)N * 128 + (size_t)M * 24 + 4096 ? in_bytes : (size_t)N * 128 + (size_t)M * 24 + 4096);
     if (rc) return rc;

@@ -291,7 +291,7 @@ extern "C" int vo_mono_frame_step(vo_ctx *ctx, const vo_mono_frame_params *prm, 
         k_mono_select<<<1, 1024, 0, ctx->stream>>>(d);
         ctx->launches += 2;
         // the reference passes the float threshold through a `const int &` parameter (motion_estimator.h:117): truncation
-        rc = vo_pose_launch_d(ctx, 1, nullptr, 0, d.n_po, d.Xp, (const float *)d.p1, nullptr, prm->K, prm->K, nullptr,
+        rc = vo_pose_launch_d(ctx, 1, nullptr, n, d.n_po, d.Xp, (const float *)d.p1, nullptr, prm->K, prm->K, nullptr,
                               (float)(int)prm->thres_poseba_error, 1, 0, d.T01, d.mask_po, d.po_success, nullptr);
         if (rc) return rc;
         k_mono_finish<<<1, 1024, 0, ctx->stream>>>(d);

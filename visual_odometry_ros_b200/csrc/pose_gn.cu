@@ -14,9 +14,12 @@
 // (:1008-1031), int outlier threshold in mono (motion_estimator.h:117), err without sqrt in mono.
 #include "vo_internal.cuh"
 
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include <cstring>
 
-#define POSE_THREADS 256
 #define POSE_MAX_ITER 100
 #define NACC 28   // 21 (upper JtWJ) + 6 (mJtWr) + 1 (err)
 
@@ -238,6 +241,103 @@ __device__ __forceinline__ void acc_row(double *acc, const float *Jt, float w, f
         if (i != ZERO) acc[21 + i] -= (double)(wr * Jt[i]);
 }
 
+// Residuals / Jacobian rows of the points first, first + stride, ... accumulated into the 28 FP64 partials
+// (per-point arithmetic in the reference's FP32 operation order; motion_estimator.cpp:720-800 mono, :915-1050 stereo).
+__device__ __forceinline__ void pose_points(const PoseArgs &a, const float *__restrict__ X, const float *__restrict__ pl,
+                                            const float *__restrict__ pr, uint8_t *__restrict__ mask, int n, int first, int stride,
+                                            const float *T10, double *acc)
+{
+    const float fx_l = a.Kl[0], fy_l = a.Kl[1], cx_l = a.Kl[2], cy_l = a.Kl[3];
+    const float fx_r = a.Kr[0], fy_r = a.Kr[1], cx_r = a.Kr[2], cy_r = a.Kr[3];
+    const float THRES_HUBER = 0.5f;
+    for (int i = first; i < n; i += stride) {
+        const float x0 = X[3 * i], x1 = X[3 * i + 1], x2 = X[3 * i + 2];
+        float Xl[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Xl[r] = ((T10[r * 4 + 0] * x0 + T10[r * 4 + 1] * x1) + T10[r * 4 + 2] * x2) + T10[r * 4 + 3];
+        const float iz_l = 1.0f / Xl[2], xiz_l = Xl[0] * iz_l, yiz_l = Xl[1] * iz_l;
+        const float fxxiz_l = fx_l * xiz_l, fyyiz_l = fy_l * yiz_l;
+        const float rx_l = (fxxiz_l + cx_l) - pl[2 * i], ry_l = (fyyiz_l + cy_l) - pl[2 * i + 1];
+        float Jt[6];
+        if (a.mono) {
+            float weight = 1.0f;
+            bool fw = false;
+            const float absrxry = fabsf(rx_l) + fabsf(ry_l);
+            if (absrxry >= THRES_HUBER) { weight = THRES_HUBER / absrxry; fw = true; }
+            mask[i] = (absrxry >= a.thres) ? 0 : 1;
+            Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
+            Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
+            acc_row<1>(acc, Jt, weight, rx_l, fw);
+            acc[27] += (double)(rx_l * rx_l);
+            Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
+            Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
+            acc_row<0>(acc, Jt, weight, ry_l, fw);
+            if (fw && a.variant == 0) acc[27] += (double)((weight * ry_l) * ry_l);
+            else acc[27] += (double)(ry_l * ry_l);
+        } else {
+            float Xr[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                Xr[r] = ((a.T_rl[r * 4 + 0] * Xl[0] + a.T_rl[r * 4 + 1] * Xl[1]) + a.T_rl[r * 4 + 2] * Xl[2]) + a.T_rl[r * 4 + 3];
+            const float iz_r = 1.0f / Xr[2], xiz_r = Xr[0] * iz_r, yiz_r = Xr[1] * iz_r;
+            const float fxxiz_r = fx_r * xiz_r, fyyiz_r = fy_r * yiz_r;
+            const float rx_r = (fxxiz_r + cx_r) - pr[2 * i], ry_r = (fyyiz_r + cy_r) - pr[2 * i + 1];
+            float weight = 1.0f;
+            float absrxry = fabsf(rx_l) + fabsf(ry_l) + fabsf(rx_r) + fabsf(ry_r);
+            absrxry *= 0.5f;
+            if (absrxry >= THRES_HUBER) weight = THRES_HUBER / absrxry;
+            mask[i] = (absrxry >= a.thres) ? 0 : 1;
+            Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
+            Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
+            acc_row<1>(acc, Jt, weight, rx_l, true); acc[27] += (double)(rx_l * rx_l);
+            Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
+            Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
+            acc_row<0>(acc, Jt, weight, ry_l, true); acc[27] += (double)(ry_l * ry_l);
+            Jt[0] = fx_r * iz_r; Jt[1] = 0.f; Jt[2] = -fxxiz_r * iz_r; Jt[3] = -fxxiz_r * yiz_r;
+            Jt[4] = fx_r * (1.0f + xiz_r * xiz_r); Jt[5] = -fx_r * yiz_r;
+            acc_row<1>(acc, Jt, weight, rx_r, true); acc[27] += (double)(rx_r * rx_r);
+            Jt[0] = 0.f; Jt[1] = fy_r * iz_r; Jt[2] = -fyyiz_r * iz_r; Jt[3] = -fy_r * (1.0f + yiz_r * yiz_r);
+            Jt[4] = fyyiz_r * xiz_r; Jt[5] = fy_r * xiz_r;
+            acc_row<0>(acc, Jt, weight, ry_r, true); acc[27] += (double)(ry_r * ry_r);
+        }
+    }
+}
+
+// The serial part of one GN iteration (one thread): normal equations from the reduced partials, damped 6x6 LDLT,
+// se3Exp_f, left-multiplication of T10, stop test (motion_estimator.cpp:803-840 / :1052-1070).
+__device__ __forceinline__ void pose_solve(const PoseArgs &a, const double *red, int n, float *s_T10, float *s_err_prev, int *s_stop)
+{
+            float H[36], g[6];
+            int idx = 0;
+            for (int i = 0; i < 6; ++i)
+                for (int j = i; j < 6; ++j, ++idx) { const float v = (float)red[idx]; H[i * 6 + j] = v; H[j * 6 + i] = v; }
+            for (int i = 0; i < 6; ++i) g[i] = (float)red[21 + i];
+            float err_curr = (float)red[27];
+            const float inv_npts = 1.0f / (float)n;
+            err_curr *= (inv_npts * 0.5f);
+            if (!a.mono) err_curr = sqrtf(err_curr);
+            const float delta_err = fabsf(err_curr - (*s_err_prev));
+            for (int i = 0; i < 6; ++i) H[i * 6 + i] *= (1.0f + 0.00001f);
+            float dxi[6], dT[16], Tn[16];
+            ldlt6_solve(H, g, dxi);
+            se3exp_f(dxi, dT);
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    float s = 0.f;
+                    for (int k = 0; k < 4; ++k) s += dT[i * 4 + k] * s_T10[k * 4 + j];
+                    Tn[i * 4 + j] = s;
+                }
+            for (int i = 0; i < 16; ++i) s_T10[i] = Tn[i];
+            (*s_err_prev) = err_curr;
+            float nrm = 0.f;
+            for (int i = 0; i < 6; ++i) nrm += dxi[i] * dxi[i];
+            nrm = sqrtf(nrm);
+            *s_stop = (nrm < 1e-6f || delta_err < 1e-7f) ? 1 : 0;
+}
+
+// THREADS per problem: 128 for the batched small problems (4 resident CTAs per SM overlap the serial solve of one
+// problem with the point loops of the others), 512 for one large problem (the frame step: 2000+ points, 4 per thread).
+template <int POSE_THREADS>
 __global__ void __launch_bounds__(POSE_THREADS)
 k_pose_gn(const PoseArgs a)
 {
@@ -268,9 +368,6 @@ k_pose_gn(const PoseArgs a)
     }
     __syncthreads();
 
-    const float fx_l = a.Kl[0], fy_l = a.Kl[1], cx_l = a.Kl[2], cy_l = a.Kl[3];
-    const float fx_r = a.Kr[0], fy_r = a.Kr[1], cx_r = a.Kr[2], cy_r = a.Kr[3];
-    const float THRES_HUBER = 0.5f;
     int iter = 0;
     for (; iter < POSE_MAX_ITER; ++iter) {
         float T10[12];
@@ -280,57 +377,7 @@ k_pose_gn(const PoseArgs a)
 #pragma unroll
         for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
-        for (int i = tid; i < n; i += POSE_THREADS) {
-            const float x0 = X[3 * i], x1 = X[3 * i + 1], x2 = X[3 * i + 2];
-            float Xl[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) Xl[r] = ((T10[r * 4 + 0] * x0 + T10[r * 4 + 1] * x1) + T10[r * 4 + 2] * x2) + T10[r * 4 + 3];
-            const float iz_l = 1.0f / Xl[2], xiz_l = Xl[0] * iz_l, yiz_l = Xl[1] * iz_l;
-            const float fxxiz_l = fx_l * xiz_l, fyyiz_l = fy_l * yiz_l;
-            const float rx_l = (fxxiz_l + cx_l) - pl[2 * i], ry_l = (fyyiz_l + cy_l) - pl[2 * i + 1];
-            float Jt[6];
-            if (a.mono) {
-                float weight = 1.0f;
-                bool fw = false;
-                const float absrxry = fabsf(rx_l) + fabsf(ry_l);
-                if (absrxry >= THRES_HUBER) { weight = THRES_HUBER / absrxry; fw = true; }
-                mask[i] = (absrxry >= a.thres) ? 0 : 1;
-                Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
-                Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
-                acc_row<1>(acc, Jt, weight, rx_l, fw);
-                acc[27] += (double)(rx_l * rx_l);
-                Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
-                Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
-                acc_row<0>(acc, Jt, weight, ry_l, fw);
-                if (fw && a.variant == 0) acc[27] += (double)((weight * ry_l) * ry_l);
-                else acc[27] += (double)(ry_l * ry_l);
-            } else {
-                float Xr[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-                    Xr[r] = ((a.T_rl[r * 4 + 0] * Xl[0] + a.T_rl[r * 4 + 1] * Xl[1]) + a.T_rl[r * 4 + 2] * Xl[2]) + a.T_rl[r * 4 + 3];
-                const float iz_r = 1.0f / Xr[2], xiz_r = Xr[0] * iz_r, yiz_r = Xr[1] * iz_r;
-                const float fxxiz_r = fx_r * xiz_r, fyyiz_r = fy_r * yiz_r;
-                const float rx_r = (fxxiz_r + cx_r) - pr[2 * i], ry_r = (fyyiz_r + cy_r) - pr[2 * i + 1];
-                float weight = 1.0f;
-                float absrxry = fabsf(rx_l) + fabsf(ry_l) + fabsf(rx_r) + fabsf(ry_r);
-                absrxry *= 0.5f;
-                if (absrxry >= THRES_HUBER) weight = THRES_HUBER / absrxry;
-                mask[i] = (absrxry >= a.thres) ? 0 : 1;
-                Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
-                Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
-                acc_row<1>(acc, Jt, weight, rx_l, true); acc[27] += (double)(rx_l * rx_l);
-                Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
-                Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
-                acc_row<0>(acc, Jt, weight, ry_l, true); acc[27] += (double)(ry_l * ry_l);
-                Jt[0] = fx_r * iz_r; Jt[1] = 0.f; Jt[2] = -fxxiz_r * iz_r; Jt[3] = -fxxiz_r * yiz_r;
-                Jt[4] = fx_r * (1.0f + xiz_r * xiz_r); Jt[5] = -fx_r * yiz_r;
-                acc_row<1>(acc, Jt, weight, rx_r, true); acc[27] += (double)(rx_r * rx_r);
-                Jt[0] = 0.f; Jt[1] = fy_r * iz_r; Jt[2] = -fyyiz_r * iz_r; Jt[3] = -fy_r * (1.0f + yiz_r * yiz_r);
-                Jt[4] = fyyiz_r * xiz_r; Jt[5] = fy_r * xiz_r;
-                acc_row<0>(acc, Jt, weight, ry_r, true); acc[27] += (double)(ry_r * ry_r);
-            }
-        }
+        pose_points(a, X, pl, pr, mask, n, tid, POSE_THREADS, T10, acc);
         // warp-level then block-level reduction of the 28 FP64 partials
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
@@ -347,34 +394,7 @@ k_pose_gn(const PoseArgs a)
             s_part[0][tid] = v;
         }
         __syncthreads();
-        if (tid == 0) {
-            float H[36], g[6];
-            int idx = 0;
-            for (int i = 0; i < 6; ++i)
-                for (int j = i; j < 6; ++j, ++idx) { const float v = (float)s_part[0][idx]; H[i * 6 + j] = v; H[j * 6 + i] = v; }
-            for (int i = 0; i < 6; ++i) g[i] = (float)s_part[0][21 + i];
-            float err_curr = (float)s_part[0][27];
-            const float inv_npts = 1.0f / (float)n;
-            err_curr *= (inv_npts * 0.5f);
-            if (!a.mono) err_curr = sqrtf(err_curr);
-            const float delta_err = fabsf(err_curr - s_err_prev);
-            for (int i = 0; i < 6; ++i) H[i * 6 + i] *= (1.0f + 0.00001f);
-            float dxi[6], dT[16], Tn[16];
-            ldlt6_solve(H, g, dxi);
-            se3exp_f(dxi, dT);
-            for (int i = 0; i < 4; ++i)
-                for (int j = 0; j < 4; ++j) {
-                    float s = 0.f;
-                    for (int k = 0; k < 4; ++k) s += dT[i * 4 + k] * s_T10[k * 4 + j];
-                    Tn[i * 4 + j] = s;
-                }
-            for (int i = 0; i < 16; ++i) s_T10[i] = Tn[i];
-            s_err_prev = err_curr;
-            float nrm = 0.f;
-            for (int i = 0; i < 6; ++i) nrm += dxi[i] * dxi[i];
-            nrm = sqrtf(nrm);
-            s_stop = (nrm < 1e-6f || delta_err < 1e-7f) ? 1 : 0;
-        }
+        if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop);
         __syncthreads();
         if (s_stop) { ++iter; break; }
     }
@@ -390,6 +410,100 @@ k_pose_gn(const PoseArgs a)
         }
         if (a.success) a.success[prob] = ok ? 1 : 0;
         if (a.iters) a.iters[prob] = iter;
+    }
+}
+
+// One LARGE problem (the frame step: 2000+ points) on a thread-block cluster: 8 CTAs x 256 threads share the point
+// loop (one point per thread at 2048 points instead of 8 per thread on one SM); the 28 FP64 partials go warp -> CTA
+// -> rank 0 through distributed shared memory, rank 0 solves and broadcasts the new pose and the stop flag back
+// through DSMEM; two cluster barriers per iteration.  Summation order is fixed (lanes by shuffle tree, warps 0..7,
+// ranks 0..7), so the result is deterministic.
+#define POSE_CLUSTER 8
+__global__ void __cluster_dims__(POSE_CLUSTER, 1, 1) __launch_bounds__(256)
+k_pose_gn_cluster(const PoseArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    __shared__ double s_part[8][NACC];
+    __shared__ double s_cta[POSE_CLUSTER][NACC];      // used on rank 0: one row per CTA, written remotely
+    __shared__ float s_T10[16];
+    __shared__ int s_stop;
+    __shared__ float s_err_prev;
+
+    const int n = a.n_single_d ? *a.n_single_d : a.n_single;
+    const float *X = a.X, *pl = a.pl, *pr = a.mono ? nullptr : a.pr;
+    uint8_t *mask = a.mask;
+    float *T01 = a.T01;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) {
+        float T[16], Ti[16];
+        for (int i = 0; i < 16; ++i) T[i] = T01[i];
+        if (a.mono) inverse4(T, Ti);
+        else inv_se3(T, Ti);
+        for (int i = 0; i < 16; ++i) s_T10[i] = Ti[i];
+        s_stop = 0;
+        s_err_prev = 1e10f;
+    }
+    cluster.sync();
+    double *cta_row_on_rank0 = cluster.map_shared_rank(&s_cta[0][0], 0) + rank * NACC;
+    int iter = 0;
+    for (; iter < POSE_MAX_ITER; ++iter) {
+        float T10[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T10[i] = s_T10[i];
+        double acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+        pose_points(a, X, pl, pr, mask, n, rank * 256 + tid, POSE_CLUSTER * 256, T10, acc);
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) s_part[wid][k] = v;
+        }
+        __syncthreads();
+        if (tid < NACC) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += s_part[w][tid];
+            cta_row_on_rank0[tid] = v;
+        }
+        cluster.sync();
+        if (rank == 0) {
+            if (tid < NACC) {
+                double v = 0.0;
+#pragma unroll
+                for (int r = 0; r < POSE_CLUSTER; ++r) v += s_cta[r][tid];
+                s_part[0][tid] = v;
+            }
+            __syncthreads();
+            if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop);
+            __syncthreads();
+            // broadcast the new pose (16 floats) and the stop flag to the other CTAs
+            if (tid < 17 * (POSE_CLUSTER - 1)) {
+                const int r = 1 + tid / 17, k = tid % 17;
+                if (k < 16) *(cluster.map_shared_rank(&s_T10[0], r) + k) = s_T10[k];
+                else *cluster.map_shared_rank(&s_stop, r) = s_stop;
+            }
+        }
+        cluster.sync();
+        if (s_stop) { ++iter; break; }
+    }
+    if (rank == 0 && tid == 0) {
+        float nrm2 = 0.f;
+        for (int i = 0; i < 16; ++i) nrm2 += s_T10[i] * s_T10[i];
+        const bool ok = !isnan(nrm2);
+        if (ok) {
+            float T10[16], Ti[16];
+            for (int i = 0; i < 16; ++i) T10[i] = s_T10[i];
+            inv_se3(T10, Ti);
+            for (int i = 0; i < 16; ++i) T01[i] = Ti[i];
+        }
+        if (a.success) a.success[0] = ok ? 1 : 0;
+        if (a.iters) a.iters[0] = iter;
     }
 }
 
@@ -416,7 +530,19 @@ int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single
     else { for (int i = 0; i < 16; ++i) a.T_rl[i] = (i % 5 == 0) ? 1.f : 0.f; }
     a.thres = thres; a.mono = mono; a.variant = variant;
     a.T01 = T01_d; a.mask = mask_d; a.success = success_d; a.iters = iters_d;
-    k_pose_gn<<<n_prob, POSE_THREADS, 0, ctx->stream>>>(a);
+    static const int force = getenv("VO_POSE_THREADS") ? atoi(getenv("VO_POSE_THREADS")) : 0;   // tuning switch
+    // one large problem (n_single = exact count or upper bound): thread-block cluster of 8 CTAs
+    static const bool no_cluster = getenv("VO_POSE_NO_CLUSTER") != nullptr;
+    if (!force && !no_cluster && n_prob == 1 && !offsets_d && n_single >= 1024) {
+        k_pose_gn_cluster<<<POSE_CLUSTER, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        VO_CUDA(cudaGetLastError());
+        return VO_OK;
+    }
+    const int thr = force ? force : (n_prob > 1 ? 128 : 512);
+    if (thr <= 128) k_pose_gn<128><<<n_prob, 128, 0, ctx->stream>>>(a);
+    else if (thr <= 256) k_pose_gn<256><<<n_prob, 256, 0, ctx->stream>>>(a);
+    else k_pose_gn<512><<<n_prob, 512, 0, ctx->stream>>>(a);
     ctx->launches++;
     VO_CUDA(cudaGetLastError());
     return VO_OK;

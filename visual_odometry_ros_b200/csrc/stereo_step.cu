@@ -353,7 +353,7 @@ extern "C" int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *f
         // [6] pose-only GN on the triangulated survivors
         k_step_select<<<1, 1024, 0, ctx->stream>>>(d);
         ctx->launches++;
-        rc = vo_pose_launch_d(ctx, 1, nullptr, 0, d.n_po, d.Xp, (const float *)d.pl, (const float *)d.pr, prm->K_l, prm->K_r, prm->T_lr,
+        rc = vo_pose_launch_d(ctx, 1, nullptr, n, d.n_po, d.Xp, (const float *)d.pl, (const float *)d.pr, prm->K_l, prm->K_r, prm->T_lr,
                               prm->thres_poseba_error, 0, 0, d.T01, d.mask_po, d.po_success, nullptr);
         if (rc) return rc;
         k_step_finish<<<1, 1024, 0, ctx->stream>>>(d);

@@ -137,7 +137,9 @@ StereoVO::StereoVO(std::string mode, std::string directory_intrinsic)
 void StereoVO::init()
 {
     const int nb = std::max(1, p_.n_bins_u * p_.n_bins_v);
-    const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 4, 4 * nb + 4096, nullptr, &ctx_);
+    // staging for 256 k "feature units" (16 MB pinned + device) up front: the frame step and the local-BA problem
+    // (a few thousand landmarks x ~10 observations) then never re-allocate pinned memory inside the frame loop
+    const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 4, std::max(4 * nb + 4096, 262144), nullptr, &ctx_);
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
 }
 
