@@ -280,8 +280,14 @@ def main():
     ptrs1 = [host_np[P + i].ctypes.data for i in range(P)]
     Ke = max(3, min(K, 10))
 
+    # the caller's point / mask arrays live in page-locked memory like the images (a real feeder's ring buffers would)
+    pts0_pin = torch.from_numpy(pts0_h).pin_memory().numpy()
+    pt_out_pin = torch.zeros((P, n, 2), dtype=torch.float32).pin_memory().numpy()
+    mask_pin = torch.ones((P, n), dtype=torch.uint8).pin_memory().numpy()
+
     def e2e_step():
-        return ctx.ft_track_batch(slots0, slots1, ptrs0, ptrs1, W, H, W, pts0_h, WIN, MAXLVL, THRES_ERR)
+        mask_pin.fill(1)                     # FeatureTracker::track starts from an all-true mask
+        return ctx.ft_track_batch(slots0, slots1, ptrs0, ptrs1, W, H, W, pts0_pin, WIN, MAXLVL, THRES_ERR, pts_track=pt_out_pin, mask=mask_pin)
 
     for _ in range(2):
         e2e_step()

@@ -123,6 +123,8 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->d_det) cudaFree(ctx->d_det);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    for (int i = 0; i < 2; ++i) if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VO_OK;
@@ -456,11 +458,22 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     rc = vo_stage_reserve(ctx, total);
     if (rc) return rc;
     uint8_t *hs = ctx->h_stage, *d = ctx->d_stage;
-    memcpy(hs + o_p0, pts0, N * 8);
-    if (with_prior) memcpy(hs + o_p1, pts_track_inout, N * 8);
-    memcpy(hs + o_mask, mask_inout, N);
-    VO_CUDA(cudaMemcpyAsync(d, hs, with_prior ? N * 16 : N * 8, cudaMemcpyHostToDevice, ctx->stream));
-    VO_CUDA(cudaMemcpyAsync(d + o_mask, hs + o_mask, N, cudaMemcpyHostToDevice, ctx->stream));
+    // Caller buffers that are page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are DMA'd
+    // directly; pageable ones go through the context's pinned staging (two extra host copies of every array).
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool pin_p0 = pinned(pts0), pin_pt = pinned(pts_track_inout), pin_m = pinned(mask_inout);
+    if (pin_p0) VO_CUDA(cudaMemcpyAsync(d + o_p0, pts0, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    else { memcpy(hs + o_p0, pts0, N * 8); VO_CUDA(cudaMemcpyAsync(d + o_p0, hs + o_p0, N * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (with_prior) {
+        if (pin_pt) VO_CUDA(cudaMemcpyAsync(d + o_p1, pts_track_inout, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        else { memcpy(hs + o_p1, pts_track_inout, N * 8); VO_CUDA(cudaMemcpyAsync(d + o_p1, hs + o_p1, N * 8, cudaMemcpyHostToDevice, ctx->stream)); }
+    }
+    if (pin_m) VO_CUDA(cudaMemcpyAsync(d + o_mask, mask_inout, N, cudaMemcpyHostToDevice, ctx->stream));
+    else { memcpy(hs + o_mask, mask_inout, N); VO_CUDA(cudaMemcpyAsync(d + o_mask, hs + o_mask, N, cudaMemcpyHostToDevice, ctx->stream)); }
     // Chunked software pipeline: the image DMA of chunk c+1 (copy stream) overlaps the pyramid + LK
     // kernels of chunk c (compute stream). Slots of different chunks are disjoint, so the only
     // dependency is "chunk c's kernels wait for chunk c's upload" (one event per chunk).
@@ -486,6 +499,13 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     KltPost post{};
     post.mode = with_prior ? 2 : 1;
     post.thres_err = thres_err;
+    // Chunks alternate between two compute streams so that the tail wave of chunk c's LK kernel overlaps the
+    // pyramid / head of chunk c+1 (chunks touch disjoint slots and disjoint ranges of the point arrays).
+    if (!ctx->stream2) VO_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->ev_aux[0]) for (int i = 0; i < 2; ++i) VO_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux[i], cudaEventDisableTiming));
+    cudaStream_t main_stream = ctx->stream;
+    VO_CUDA(cudaEventRecord(ctx->ev_aux[0], main_stream));          // the point / mask uploads above
+    VO_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_aux[0], 0));
     for (int c = 0; c < n_chunks; ++c) {
         const int c0 = chunk_begin[c], nc = chunk_begin[c + 1] - c0;
         rc = upload_many(ctx, nc, slots0 + c0, imgs0 ? imgs0 + c0 : nullptr, w, h, step, ctx->copy_stream);
@@ -493,18 +513,23 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
         rc = upload_many(ctx, nc, slots1 + c0, imgs1 ? imgs1 + c0 : nullptr, w, h, step, ctx->copy_stream);
         if (rc) return rc;
         VO_CUDA(cudaEventRecord(ctx->events[c], ctx->copy_stream));
-        VO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->events[c], 0));
+        cudaStream_t cs = (c & 1) ? ctx->stream2 : main_stream;
+        VO_CUDA(cudaStreamWaitEvent(cs, ctx->events[c], 0));
         const size_t off = (size_t)c0 * n;
         post.mask = d + o_mask + off;
+        ctx->stream = cs;                                            // the launch helpers enqueue on ctx->stream
         rc = vo_klt_launch(ctx, nc, slots0 + c0, slots1 + c0, (const float *)(d + o_p0) + 2 * off, n, window_size, max_pyr_lvl,
                            with_prior ? VO_KLT_USE_INITIAL_FLOW : 0, (float *)(d + o_p1) + 2 * off, d + o_st + off,
                            (float *)(d + o_err) + off, nullptr, &post);
+        ctx->stream = main_stream;
         if (rc) return rc;
     }
-    VO_CUDA(cudaMemcpyAsync(hs + o_p1, d + o_p1, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA(cudaMemcpyAsync(hs + o_mask, d + o_mask, N, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaEventRecord(ctx->ev_aux[1], ctx->stream2));
+    VO_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_aux[1], 0));
+    VO_CUDA(cudaMemcpyAsync(pin_pt ? (void *)pts_track_inout : (void *)(hs + o_p1), d + o_p1, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaMemcpyAsync(pin_m ? (void *)mask_inout : (void *)(hs + o_mask), d + o_mask, N, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(pts_track_inout, hs + o_p1, N * 8);
-    memcpy(mask_inout, hs + o_mask, N);
+    if (!pin_pt) memcpy(pts_track_inout, hs + o_p1, N * 8);
+    if (!pin_m) memcpy(mask_inout, hs + o_mask, N);
     return VO_OK;
 }
