@@ -33,7 +33,9 @@ def main():
         gt = T0inv @ T[k]
         err = np.abs(vo.pose()[:3, 3] - gt[:3, 3]).max()
         print(f"frame {k:4d}  {ms:7.3f} ms  kf={fi['keyframe']}  in={fi['n_in']:5d} tracked={fi['n_tracked']:5d} new={fi['n_new']:4d} "
-              f"lba={fi['lba_points']:5d}/{fi['lba_obs']:6d}  |t - t_gt|max={err:.4f} m")
+              f"lba={fi['lba_points']:5d}/{fi['lba_obs']:6d}  |t - t_gt|max={err:.4f} m  "
+              f"[step {fi['ms_step']:.2f} book {fi['ms_book']:.2f} recon {fi['ms_recon']:.2f} pack {fi['ms_lba_pack']:.2f} "
+              f"solve {fi['ms_lba_solve']:.2f} stats {fi['ms_stats']:.2f}]")
     vo.close()
 
 

@@ -22,6 +22,9 @@
 // gate, SE3Log's w=0 snap, transposed diagonal blocks of BCinvBt.  Compiled with -fmad=false.
 #include "vo_internal.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <cstring>
 #include <vector>
 
@@ -45,9 +48,11 @@ struct LbaDev {
     double *s_part;          // [n_tiles][n6*(n6+1)]
     double *a_part;          // [n_tiles][n_opt][27]
     double *err_part;        // [n_tiles]
+    double *red;             // [n6*(n6+1) + n_opt*27 + 1] tile partials summed in tile order (k_lba_reduce)
     double *x;               // [n6]
     double *avg_err;         // [max_iter]
     int *nan_flag;
+    long long *dbg;          // nullable: clock64 stamps of k_lba_solve (VO_LBA_TRACE)
     double K_l[4], K_r[4];
     double R_rl[9], t_rl[3];
     double huber, lambda;
@@ -446,6 +451,28 @@ k_lba_build(const LbaDev d, int apply_update)
     }
 }
 
+// ------------------------------------------------------------------ k_lba_reduce
+// Fixed-order (tile 0, 1, ...) sums of the per-tile partial systems, one thread per entry, coalesced across entries.
+// (Inside the single solve CTA this reduction was a 100-microsecond chain of dependent L2 loads per iteration.)
+__global__ void __launch_bounds__(256) k_lba_reduce(const LbaDev d)
+{
+    const int n = d.n6, ncol = n + 1, nS = n * ncol, nA = d.n_opt * LBA_NA;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nS + nA + 1) return;
+    const double *src; size_t stride;
+    if (e < nS) { src = d.s_part + e; stride = (size_t)nS; }
+    else if (e < nS + nA) { src = d.a_part + (e - nS); stride = (size_t)nA; }
+    else { src = d.err_part; stride = 1; }
+    double acc = 0.0;
+    int t = 0;
+    for (; t + 4 <= d.n_tiles; t += 4) {
+        const double v0 = src[(size_t)t * stride], v1 = src[(size_t)(t + 1) * stride], v2 = src[(size_t)(t + 2) * stride], v3 = src[(size_t)(t + 3) * stride];
+        acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; t < d.n_tiles; ++t) acc += src[(size_t)t * stride];
+    d.red[e] = acc;
+}
+
 // ------------------------------------------------------------------ k_lba_solve (one CTA)
 __global__ void __launch_bounds__(LBA_THREADS, 1)
 k_lba_solve(const LbaDev d, int iter)
@@ -461,24 +488,17 @@ k_lba_solve(const LbaDev d, int iter)
     __shared__ double s_err;
     const int tid = threadIdx.x;
 #define SM(i, j) S[(size_t)(i) * (n + 1) + (j)]
+#define STAMP(k) do { if (d.dbg && tid == 0) d.dbg[k] = clock64(); } while (0)
+    STAMP(0);
 
     // fixed-order reduction of the tile partials
     for (int e = tid; e < n * ncol; e += LBA_THREADS) {
-        double acc = 0.0;
-        for (int t = 0; t < d.n_tiles; ++t) acc += d.s_part[(size_t)t * n * ncol + e];
+        const double acc = d.red[e];
         const int r = e / ncol, c = e - r * ncol;
         if (c == n) rhs[r] = acc; else SM(r, c) = acc;
     }
-    for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) {
-        double acc = 0.0;
-        for (int t = 0; t < d.n_tiles; ++t) acc += d.a_part[(size_t)t * No * LBA_NA + e];
-        Aj[e] = acc;
-    }
-    if (tid == 0) {
-        double acc = 0.0;
-        for (int t = 0; t < d.n_tiles; ++t) acc += d.err_part[t];
-        s_err = acc;
-    }
+    for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) Aj[e] = d.red[n * ncol + e];
+    if (tid == 0) s_err = d.red[n * ncol + No * LBA_NA];
     __syncthreads();
     // S <- blkdiag(A damped) - BCinvBt with the reference's mirror (upper blocks -> lower, diagonal
     // blocks transposed, sparse_bundle_adjustment.cpp:501-512); rhs <- a - BCinv_b
@@ -514,75 +534,113 @@ k_lba_solve(const LbaDev d, int iter)
     for (int r = tid; r < n; r += LBA_THREADS) rhs[r] = Aj[(r / 6) * LBA_NA + 21 + (r % 6)] - rhs[r];
     __syncthreads();
 
-    // ---- pivoted LDLT (lower storage), the algorithm of Eigen::LDLT::compute
-    for (int k = 0; k < n; ++k) {
-        if (tid < 32) {
-            double bv = -1.0;
-            int bi = k;
-            for (int i = k + tid; i < n; i += 32) {
-                const double v = fabs(SM(i, i));
-                if (v > bv) { bv = v; bi = i; }
+    STAMP(1);
+    // The factorisation and the forward solve are latency chains over a 6N x 6N (<= 96 x 96) matrix in shared
+    // memory: they run on ONE warp with warp barriers (the 8-warp version spent most of each column in
+    // __syncthreads); the arithmetic and its order are unchanged.
+    if (tid < 32) {
+        // ---- pivoted LDLT (lower storage), the algorithm of Eigen::LDLT::compute
+        for (int k = 0; k < n; ++k) {
+            {
+                double bv = -1.0;
+                int bi = k;
+                for (int i = k + tid; i < n; i += 32) {
+                    const double v = fabs(SM(i, i));
+                    if (v > bv) { bv = v; bi = i; }
+                }
+                // warp arg-max of |diag| (first maximal index, as Eigen's maxCoeff): non-negative doubles order like
+                // their bit patterns, so three integer redux.sync replace five rounds of 64-bit shuffles + FP64 compares
+                {
+                    const unsigned long long key = bv >= 0.0 ? (unsigned long long)__double_as_longlong(bv) : 0ull;
+                    const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
+                    const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
+                    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                    const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
+                    const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+                    const bool win = has && hi == mhi && (unsigned)key == mlo;
+                    bi = __reduce_min_sync(0xffffffffu, win ? bi : 0x7fffffff);
+                    if (bi == 0x7fffffff) bi = k;
+                }
+                if (tid == 0) { s_big = bi; s_tr[k] = bi; }
             }
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            __syncwarp();
+            const int big = s_big;
+            if (big != k) {
+                const int s = n - big - 1;
+                for (int j = tid; j < k; j += 32) { const double t = SM(k, j); SM(k, j) = SM(big, j); SM(big, j) = t; }
+                for (int i = tid; i < s; i += 32) { const double t = SM(big + 1 + i, k); SM(big + 1 + i, k) = SM(big + 1 + i, big); SM(big + 1 + i, big) = t; }
+                for (int i = k + 1 + tid; i < big; i += 32) { const double t = SM(i, k); SM(i, k) = SM(big, i); SM(big, i) = t; }
+                if (tid == 0) { const double t = SM(k, k); SM(k, k) = SM(big, big); SM(big, big) = t; }
+                __syncwarp();
             }
-            if (tid == 0) { s_big = bi; s_tr[k] = bi; }
+            // right-looking column step (the products are Eigen's, L(i,j) * (D_j L(k,j)); they are subtracted one
+            // column at a time instead of as a pre-summed dot product, so every element update of a column is
+            // independent and the serial chain is one FP64 operation per column instead of k)
+            const int rs = n - k - 1;
+            const double akk = SM(k, k);
+            // L(:,k) = A(:,k) / D_k as a multiplication by the correctly rounded reciprocal: an IEEE FP64 division is a
+            // ~1100-cycle dependent sequence on this machine and sat on the critical path of every column (measured:
+            // 2300 of 3400 cycles per column); the quotient may differ from Eigen's by one ulp
+            if (rs > 0 && fabs(akk) > 0.0) {
+                const double rk = __drcp_rn(akk);
+                for (int i = tid; i < rs; i += 32) SM(k + 1 + i, k) *= rk;
+            }
+            __syncwarp();
+            for (int i = tid; i < rs; i += 32) temp[i] = akk * SM(k + 1 + i, k);      // D_k * L(k+1+i, k)
+            __syncwarp();
+            // trailing lower triangle: A(r, c) -= L(r, k) * temp[c - k - 1] for k < c <= r
+            // rows are paired (a, rs-1-a) so that every active lane updates rs + 1 elements
+            for (int a0 = tid; 2 * a0 < rs; a0 += 32) {
+                const int a1 = rs - 1 - a0;
+                const double l0 = SM(k + 1 + a0, k), l1 = SM(k + 1 + a1, k);
+                // explicit load-4 / store-4 groups: S and temp are both shared-memory doubles, so the compiler
+                // must otherwise order every load after the previous store
+                double *row0 = &SM(k + 1 + a0, k + 1), *row1 = &SM(k + 1 + a1, k + 1);
+                const int n0 = a0 + 1, n1 = (a1 != a0) ? a1 + 1 : 0;
+                int bc = 0;
+                for (; bc + 4 <= n0; bc += 4) {
+                    const double t0 = temp[bc], t1 = temp[bc + 1], t2 = temp[bc + 2], t3 = temp[bc + 3];
+                    const double v0 = row0[bc], v1 = row0[bc + 1], v2 = row0[bc + 2], v3 = row0[bc + 3];
+                    row0[bc] = v0 - l0 * t0; row0[bc + 1] = v1 - l0 * t1; row0[bc + 2] = v2 - l0 * t2; row0[bc + 3] = v3 - l0 * t3;
+                }
+                for (; bc < n0; ++bc) row0[bc] -= l0 * temp[bc];
+                bc = 0;
+                for (; bc + 4 <= n1; bc += 4) {
+                    const double t0 = temp[bc], t1 = temp[bc + 1], t2 = temp[bc + 2], t3 = temp[bc + 3];
+                    const double v0 = row1[bc], v1 = row1[bc + 1], v2 = row1[bc + 2], v3 = row1[bc + 3];
+                    row1[bc] = v0 - l1 * t0; row1[bc + 1] = v1 - l1 * t1; row1[bc + 2] = v2 - l1 * t2; row1[bc + 3] = v3 - l1 * t3;
+                }
+                for (; bc < n1; ++bc) row1[bc] -= l1 * temp[bc];
+            }
+            __syncwarp();
         }
-        __syncthreads();
-        const int big = s_big;
-        if (big != k) {
-            const int s = n - big - 1;
-            for (int j = tid; j < k; j += LBA_THREADS) { const double t = SM(k, j); SM(k, j) = SM(big, j); SM(big, j) = t; }
-            for (int i = tid; i < s; i += LBA_THREADS) { const double t = SM(big + 1 + i, k); SM(big + 1 + i, k) = SM(big + 1 + i, big); SM(big + 1 + i, big) = t; }
-            for (int i = k + 1 + tid; i < big; i += LBA_THREADS) { const double t = SM(i, k); SM(i, k) = SM(big, i); SM(big, i) = t; }
-            if (tid == 0) { const double t = SM(k, k); SM(k, k) = SM(big, big); SM(big, big) = t; }
-            __syncthreads();
+        // ---- solve: P b, L^-1, D^-1, L^-T, P^T  (column-oriented updates keep the row-wise order)
+        if (tid == 0) for (int k = 0; k < n; ++k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
+        __syncwarp();
+        for (int j = 0; j < n; ++j) {
+            const double yj = rhs[j];
+            for (int i = j + 1 + tid; i < n; i += 32) rhs[i] -= SM(i, j) * yj;
+            __syncwarp();
         }
-        const int rs = n - k - 1;
-        if (k > 0) {
-            for (int j = tid; j < k; j += LBA_THREADS) temp[j] = SM(j, j) * SM(k, j);
-            __syncthreads();
-            if (tid == 0) {
-                double sacc = 0;
-                for (int j = 0; j < k; ++j) sacc += SM(k, j) * temp[j];
-                SM(k, k) -= sacc;
-            }
-            for (int i = tid; i < rs; i += LBA_THREADS) {
-                double s2 = 0;
-                for (int j = 0; j < k; ++j) s2 += SM(k + 1 + i, j) * temp[j];
-                SM(k + 1 + i, k) -= s2;
-            }
-            __syncthreads();
-        }
-        const double akk = SM(k, k);
-        if (rs > 0 && fabs(akk) > 0.0)
-            for (int i = tid; i < rs; i += LBA_THREADS) SM(k + 1 + i, k) /= akk;
-        __syncthreads();
     }
-    // ---- solve: P b, L^-1, D^-1, L^-T, P^T  (column-oriented updates keep the row-wise order)
-    if (tid == 0) for (int k = 0; k < n; ++k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        const double yj = rhs[j];
-        for (int i = j + 1 + tid; i < n; i += LBA_THREADS) rhs[i] -= SM(i, j) * yj;
-        __syncthreads();
-    }
+    STAMP(2);
     const double tol = 1.0 / 1.7976931348623157e308;
     for (int i = tid; i < n; i += LBA_THREADS) rhs[i] = fabs(SM(i, i)) > tol ? rhs[i] / SM(i, i) : 0.0;
     __syncthreads();
-    // backward: the reference order is, for row i descending, s -= M(j,i)*y[j] for j = i+1..n-1
-    // ascending; a column sweep would reverse that order, so rows are finished one at a time.
-    if (tid == 0) {
-        for (int i = n - 1; i >= 0; --i) {
-            double sacc = rhs[i];
-            for (int j = i + 1; j < n; ++j) sacc -= SM(j, i) * rhs[j];
-            rhs[i] = sacc;
+    // backward substitution L^T x = y, column-oriented: once x_i is final, every x_j (j < i) takes its update
+    // independently (one serial FP64 step per row instead of a dot-product chain), then P^T
+    if (tid < 32) {
+        for (int i = n - 1; i > 0; --i) {
+            const double xi = rhs[i];
+            for (int j = tid; j < i; j += 32) rhs[j] -= SM(i, j) * xi;
+            __syncwarp();
         }
-        for (int k = n - 1; k >= 0; --k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
+        if (tid == 0)
+            for (int k = n - 1; k >= 0; --k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
     }
     __syncthreads();
+    STAMP(3);
     for (int i = tid; i < n; i += LBA_THREADS) d.x[i] = rhs[i];
     // ---- pose retraction of the optimisable keyframes + error bookkeeping
     if (tid < No) {
@@ -593,6 +651,7 @@ k_lba_solve(const LbaDev d, int iter)
         pose_retract(T, xj);
         for (int k = 0; k < 16; ++k) Tg[k] = T[k];
     }
+    STAMP(4);
     if (tid == 0) {
         d.avg_err[iter] = sqrt(s_err / (double)d.n_obs);
         if (isnan(s_err)) atomicExch(d.nan_flag, 1);
@@ -681,6 +740,14 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     int TL = (int)((budget - fixed) / per_lm);
     TL = TL / LBA_WARPS * LBA_WARPS;
     if (TL > 64) TL = 64;
+    {   // fill the machine: about one tile per SM (a tile's warps walk their landmarks sequentially, so fewer
+        // landmarks per tile is lower latency; more tiles only cost a longer k_lba_reduce)
+        static int n_sm = 0;
+        if (!n_sm) { cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device); if (n_sm <= 0) n_sm = 148; }
+        int want = vo_div_up(vo_div_up(M > 0 ? M : 1, n_sm), LBA_WARPS) * LBA_WARPS;
+        if (want < LBA_WARPS) want = LBA_WARPS;
+        if (want < TL) TL = want;
+    }
     VO_REQUIRE(TL >= LBA_WARPS, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
     const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
     const size_t smem_build = fixed + per_lm * TL;
@@ -696,7 +763,8 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     const size_t o_bc = take((size_t)n_obs * 144), o_cb = take((size_t)M * 24);
     const size_t o_sp = take((size_t)n_tiles * n6 * (n6 + 1) * 8), o_ap = take((size_t)n_tiles * No * LBA_NA * 8);
     const size_t o_ep = take((size_t)n_tiles * 8), o_x = take((size_t)n6 * 8);
-    const size_t o_ae = take((size_t)p->max_iter * 8), o_nan = take(16);
+    const size_t o_red = take(((size_t)n6 * (n6 + 1) + (size_t)No * LBA_NA + 1) * 8);
+    const size_t o_ae = take((size_t)p->max_iter * 8), o_nan = take(16), o_dbg = take(128);
     const size_t total = off;
     if (total > ctx->lba_bytes) {
         VO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -728,8 +796,9 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     d.points = (double *)(dv + o_pts); d.obs_ptr = (const int *)(dv + o_ptr); d.obs_frame = (const int *)(dv + o_of);
     d.obs_right = dv + o_or; d.obs_px = (const double *)(dv + o_px);
     d.bcinv = (double *)(dv + o_bc); d.cinv_b = (double *)(dv + o_cb); d.s_part = (double *)(dv + o_sp);
-    d.a_part = (double *)(dv + o_ap); d.err_part = (double *)(dv + o_ep); d.x = (double *)(dv + o_x);
+    d.a_part = (double *)(dv + o_ap); d.err_part = (double *)(dv + o_ep); d.x = (double *)(dv + o_x); d.red = (double *)(dv + o_red);
     d.avg_err = (double *)(dv + o_ae); d.nan_flag = (int *)(dv + o_nan);
+    d.dbg = getenv("VO_LBA_TRACE") ? (long long *)(dv + o_dbg) : nullptr;
     memcpy(d.K_l, p->K_l, 32); memcpy(d.K_r, p->K_r, 32);
     double T_rl[16];
     inv_se3_host_d(p->T_lr, T_rl);   // geometry::inverseSE3(T_lr), sparse_bundle_adjustment.cpp:174
@@ -738,10 +807,41 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
 
     VO_CUDA(cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
     VO_CUDA(cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    {   // the three kernels alternate 21 times: keep ONE L1 / shared-memory carve-out so that the SMs are not
+        // re-partitioned (and drained) between every pair of launches
+        static bool once = false;
+        if (!once) {
+            once = true;
+            cudaFuncSetAttribute(k_lba_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_update_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+    }
+    static const bool trace = getenv("VO_LBA_TRACE") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    if (trace) { evs.resize(2 * p->max_iter + 1); for (auto &e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], ctx->stream); }
     for (int it = 0; it < p->max_iter; ++it) {
         k_lba_build<<<n_tiles, LBA_THREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
+        k_lba_reduce<<<vo_div_up(n6 * (n6 + 1) + No * LBA_NA + 1, 256), 256, 0, ctx->stream>>>(d);
+        if (trace) cudaEventRecord(evs[2 * it + 1], ctx->stream);
         k_lba_solve<<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
-        ctx->launches += 2;
+        if (trace) cudaEventRecord(evs[2 * it + 2], ctx->stream);
+        ctx->launches += 3;
+    }
+    if (trace) {
+        cudaStreamSynchronize(ctx->stream);
+        for (int it = 0; it < p->max_iter; ++it) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, evs[2 * it], evs[2 * it + 1]); cudaEventElapsedTime(&b, evs[2 * it + 1], evs[2 * it + 2]);
+            fprintf(stderr, "lba it %d: build %.1f us, solve %.1f us (tiles %d, smem %zu / %zu)\n", it, a * 1e3f, b * 1e3f, n_tiles, smem_build, smem_solve);
+        }
+        for (auto &e : evs) cudaEventDestroy(e);
+        long long st[8];
+        long long st2[16];
+        cudaMemcpy(st2, dv + o_dbg, 104, cudaMemcpyDeviceToHost);
+        memcpy(st, st2, 40);
+
+        fprintf(stderr, "k_lba_solve cycles: assemble %lld, ldlt+fwd %lld, diag+backward %lld, retract %lld\n", st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3]);
     }
     if (M > 0) { k_lba_update_points<<<vo_div_up(M, 256), 256, 0, ctx->stream>>>(d); ctx->launches++; }
     VO_CUDA(cudaGetLastError());

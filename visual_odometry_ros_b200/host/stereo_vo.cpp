@@ -3,6 +3,7 @@
 #include "stereo_vo.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,8 @@
 #include <stdexcept>
 
 namespace {
+using Clock = std::chrono::steady_clock;
+inline float ms_since(Clock::time_point t0) { return std::chrono::duration<float, std::milli>(Clock::now() - t0).count(); }
 const float D2R = 3.14159265358979323846f / 180.0f;
 
 void ident(float *T) { for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f; }
@@ -217,6 +220,7 @@ void StereoVO::localBundleAdjustment()
     const int NUM_MINIMUM_REQUIRED_KEYFRAMES = 3, NUM_FIX = 2;                     // motion_estimator.cpp:1245-1246
     info_.lba_points = info_.lba_obs = info_.lba_ok = 0;
     if ((int)window_.size() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return;
+    const auto t_pack = Clock::now();
     const int nf = (int)window_.size();
     std::map<int, int> fidx;
     for (int k = 0; k < nf; ++k) fidx[window_[k]->id] = k;
@@ -282,6 +286,8 @@ void StereoVO::localBundleAdjustment()
     pr.is_stereo = 1; pr.huber = 0.5; pr.lambda = 0.00001; pr.max_iter = 10;
     std::vector<double> poses_out(poses.size()), points_out(points.size()), avg(pr.max_iter);
     int ok = 0;
+    info_.ms_lba_pack = ms_since(t_pack);
+    const auto t_solve = Clock::now();
     const int rc = vo_lba_solve(ctx_, &pr, poses_out.data(), points_out.data(), avg.data(), &ok);
     if (rc == VO_ERR_NAN) throw std::runtime_error("Local BA NAN!\n");           // sparse_bundle_adjustment.cpp:761
     if (rc) fail(ctx_, rc);
@@ -315,6 +321,7 @@ void StereoVO::localBundleAdjustment()
         if (std::sqrt(Xf[0] * Xf[0] + Xf[1] * Xf[1] + Xf[2] * Xf[2]) <= 3000) lm_bundled_[id] = 1;
         else lm_alive_[id] = 0;
     }
+    info_.ms_lba_solve = ms_since(t_solve);
     if (large_update) throw std::runtime_error("large update!");                  // :731
 }
 
@@ -348,6 +355,7 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
         throw std::runtime_error("vo_b200: bad stereo image pair");
     const int w = img_left.cols, h = img_left.rows;
     if (img_left.step != img_right.step) throw std::runtime_error("vo_b200: left/right row pitch differ");
+    const auto t_total = Clock::now();
     auto fr = std::make_shared<FrameRec>();
     fr->id = n_frames_++;
     ident(fr->Twc); ident(fr->Tcw); ident(fr->dT01);
@@ -411,9 +419,11 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     out_idx_.resize(std::max(n, 1)); out_l1_.resize((size_t)std::max(n, 1) * 2); out_r1_.resize((size_t)std::max(n, 1) * 2);
     res.index = out_idx_.data(); res.pts_l1 = out_l1_.data(); res.pts_r1 = out_r1_.data();
     fp.new_depth_gate = 1;
+    const auto t_step = Clock::now();
     const int rc = vo_stereo_frame_step(ctx_, &fp, sp, sl, sr, img_left.data, img_right.data, w, h, img_left.step, n, in_l0_.data(), in_r0_.data(),
                                         in_X_.data(), in_tri_.data(), pv.Twc, pv.dT01, &res);
     if (rc) fail(ctx_, rc);
+    const float ms_step = ms_since(t_step);
     setPose(*fr, T_wc);                              // :642
     float dT10[16];
     inv4_f(dT, dT10);                                // :643 dT_pc_poBA.inverse()
@@ -438,10 +448,22 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     if (kf) {
         info_.keyframe = 1;
         addKeyframe(fr);
+        const auto t_rec = Clock::now();
         reconstruct(*fr, nt);                        // only the tracked survivors (n_pts is fixed before the appends, :767)
+        info_.ms_recon = ms_since(t_rec);
         localBundleAdjustment();
     }
+    const auto t_stats = Clock::now();
     pushStats(*fr, kf);
+    info_.ms_stats = ms_since(t_stats);
+    info_.ms_step = ms_step;
+    info_.ms_total = ms_since(t_total);
+    info_.ms_book = info_.ms_total - info_.ms_step - info_.ms_recon - info_.ms_lba_pack - info_.ms_lba_solve - info_.ms_stats;
+    // ExecutionStatistics as the reference declares them (stereo_vo.h:166-176)
+    stat_.stats_execution.back().time_track = info_.ms_step;
+    stat_.stats_execution.back().time_localba = info_.ms_lba_pack + info_.ms_lba_solve;
+    stat_.stats_execution.back().time_new = info_.ms_recon;
+    stat_.stats_execution.back().time_total = info_.ms_total;
     prev_ = fr;
 }
 

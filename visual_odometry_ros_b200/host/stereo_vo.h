@@ -79,6 +79,9 @@ public:
         int frame = 0, keyframe = 0, n_in = 0, n_tracked = 0, n_detected = 0, n_new = 0, n_recon = 0;
         int lba_points = 0, lba_obs = 0, lba_ok = 0;
         int counts[5] = {0, 0, 0, 0, 0};
+        // wall-clock milliseconds: frame step (device call incl. copies and the sync), host bookkeeping, keyframe
+        // reconstruction, local-BA packing, local-BA solve + write-back, statistics refresh, total
+        float ms_step = 0.f, ms_book = 0.f, ms_recon = 0.f, ms_lba_pack = 0.f, ms_lba_solve = 0.f, ms_stats = 0.f, ms_total = 0.f;
     };
     const FrameInfo &lastFrameInfo() const { return info_; }
     const std::vector<int> &currentLandmarkIds() const;

@@ -26,7 +26,9 @@ class Parameters(ctypes.Structure):
 class FrameInfo(ctypes.Structure):
     _fields_ = [("frame", ctypes.c_int), ("keyframe", ctypes.c_int), ("n_in", ctypes.c_int), ("n_tracked", ctypes.c_int),
                 ("n_detected", ctypes.c_int), ("n_new", ctypes.c_int), ("n_recon", ctypes.c_int), ("lba_points", ctypes.c_int),
-                ("lba_obs", ctypes.c_int), ("lba_ok", ctypes.c_int), ("counts", ctypes.c_int * 5)]
+                ("lba_obs", ctypes.c_int), ("lba_ok", ctypes.c_int), ("counts", ctypes.c_int * 5),
+                ("ms_step", ctypes.c_float), ("ms_book", ctypes.c_float), ("ms_recon", ctypes.c_float), ("ms_lba_pack", ctypes.c_float),
+                ("ms_lba_solve", ctypes.c_float), ("ms_stats", ctypes.c_float), ("ms_total", ctypes.c_float)]
 
 
 def host_lib():
