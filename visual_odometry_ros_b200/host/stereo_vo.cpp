@@ -222,8 +222,12 @@ void StereoVO::localBundleAdjustment()
     if ((int)window_.size() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return;
     const auto t_pack = Clock::now();
     const int nf = (int)window_.size();
-    std::map<int, int> fidx;
-    for (int k = 0; k < nf; ++k) fidx[window_[k]->id] = k;
+    // frame id -> window position (frame ids are dense and increasing: a flat table instead of the reference's
+    // unordered_map lookups per observation, sparse_ba_parameters.h:384)
+    const int id0 = window_.front()->id;
+    std::vector<int> fidx_tab((size_t)(window_.back()->id - id0 + 1), -1);
+    for (int k = 0; k < nf; ++k) fidx_tab[window_[k]->id - id0] = k;
+    auto fidx_of = [&](int kf_id) { const int r = kf_id - id0; return (r >= 0 && r < (int)fidx_tab.size()) ? fidx_tab[r] : -1; };
     // 1) alive + triangulated landmarks of the window, first-seen order (the reference's unordered_set order is
     //    address-hash dependent)
     std::vector<int> lmset;
@@ -247,18 +251,20 @@ void StereoVO::localBundleAdjustment()
     std::vector<int> lms, obs_ptr(1, 0), obs_frame;
     std::vector<uint8_t> obs_right;
     std::vector<double> points, obs_px;
+    lms.reserve(lmset.size()); obs_ptr.reserve(lmset.size() + 1); points.reserve(lmset.size() * 3);
+    obs_frame.reserve(lmset.size() * 8); obs_right.reserve(lmset.size() * 8); obs_px.reserve(lmset.size() * 16);
     for (int id : lmset) {
         int cnt = 0;
-        for (const KfObs &o : lm_kf_obs_[id]) if (fidx.count(o.kf_id)) ++cnt;
+        for (const KfObs &o : lm_kf_obs_[id]) if (fidx_of(o.kf_id) >= 0) ++cnt;
         if (cnt < 2) continue;                                                     // THRES_MINIMUM_SEEN
         const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
         for (int r = 0; r < 3; ++r)
             points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
         lms.push_back(id);
         for (const KfObs &o : lm_kf_obs_[id]) {
-            auto it = fidx.find(o.kf_id);
-            if (it == fidx.end()) continue;
-            obs_frame.push_back(it->second); obs_right.push_back(o.right);
+            const int fk = fidx_of(o.kf_id);
+            if (fk < 0) continue;
+            obs_frame.push_back(fk); obs_right.push_back(o.right);
             obs_px.push_back(o.x); obs_px.push_back(o.y);
         }
         obs_ptr.push_back((int)obs_frame.size());
