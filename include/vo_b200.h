@@ -93,6 +93,19 @@ VO_API int vo_effective_max_level(int w, int h, int win, int max_level);
 VO_API int vo_read_pyramid_level(vo_ctx *ctx, int slot, int level, uint8_t *img, int16_t *deriv,
                           int *w_l, int *h_l);
 
+/* ------------------------------------------------------------------ stereo rectification
+ * StereoCamera::generateStereoImagesUndistortAndRectifyMaps (core/visual_odometry/camera.cpp:364-546): builds the four
+ * CV_32FC1 rectification maps on the device from the pinhole-radtan parameters (K = fx, fy, cx, cy; D = k1, k2, p1, p2,
+ * k3 as in camera.cpp:30-35; T_lr 4x4 row-major) and returns the rectified intrinsics (fx, fy, cx, cy) and T_lr_rect. */
+VO_API int vo_rectify_init(vo_ctx *ctx, const float *K_l4, const float *D_l5, const float *K_r4, const float *D_r5,
+                    const float *T_lr, int w, int h, float *K_rect4_out, float *T_lr_rect_out);
+/* Debug / parity read-back of one camera's maps (w*h floats each). */
+VO_API int vo_read_rectify_maps(vo_ctx *ctx, int right, float *map_u, float *map_v);
+/* StereoCamera::rectifyStereoImages for one image + the convertTo(CV_8UC1) of StereoVO (camera.cpp:300-336,
+ * stereo_vo.cpp:416-421): H2D of the distorted image, cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) on the device, result
+ * becomes the slot's image (pyramid stale). right = 0 / 1 selects the left / right maps. */
+VO_API int vo_upload_image_rectified(vo_ctx *ctx, int slot, int right, const uint8_t *data, int w, int h, size_t step);
+
 /* ------------------------------------------------------------------ raw pyramidal LK
  * == cv::calcOpticalFlowPyrLK(img[slot0], img[slot1], pts0, pts1, status, err,
  *        Size(win,win), max_level, TermCriteria(COUNT+EPS,30,0.01), flags, 1e-4)

@@ -115,7 +115,13 @@ def test_stereo_vo_from_reference_yaml(frames, tmp_path):
     vo.close(); ref.close()
     with pytest.raises(capi.VoError):
         svo.StereoVO(yaml_path=str(tmp_path / "missing.yaml"))
-    bad = tmp_path / "undist.yaml"
-    bad.write_text(YAML.format(fx=1.0, fy=1.0, cx=1.0, cy=1.0, w=W, h=H).replace("flagDoUndistortion: 0", "flagDoUndistortion: 1"))
-    with pytest.raises(capi.VoError):
-        svo.StereoVO(yaml_path=str(bad))
+    # flagDoUndistortion: 1 with zero distortion and an already rectified rig: rectification is the identity up to the
+    # reference's own conventions (K_rect = mean focal length / image centre, camera.cpp:401-412), so the step runs
+    und = tmp_path / "undist.yaml"
+    und.write_text(YAML.format(fx=float(K[0]), fy=float(K[1]), cx=float(K[2]), cy=float(K[3]), w=W, h=H).replace("flagDoUndistortion: 0", "flagDoUndistortion: 1"))
+    vu = svo.StereoVO(yaml_path=str(und))
+    for k in range(len(L)):
+        vu.trackStereoImages(L[k], R[k], 0.1 * k)
+    assert vu.frame_info()["n_tracked"] > 100
+    assert np.abs(vu.pose()[:3, 3] - gt[:3, 3]).max() < 0.1
+    vu.close()

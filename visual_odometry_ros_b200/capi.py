@@ -142,6 +142,9 @@ def lib():
                                        ctypes.POINTER(StereoFrameResult)]
     L.vo_mono_frame_step.argtypes = [vp, ctypes.POINTER(MonoFrameParams), ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.POINTER(MonoFrameResult)]
+    L.vo_rectify_init.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    L.vo_read_rectify_maps.argtypes = [vp, ctypes.c_int, vp, vp]
+    L.vo_upload_image_rectified.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
     L.vo_stereo_reconstruct.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
@@ -570,3 +573,22 @@ class Context:
         k, m = res.n_tracked, res.n_new
         return dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx[:k].copy(), pts1=o1[:k].copy(), counts=[int(c) for c in counts],
                     n_detected=res.n_detected, new_p1=n1[:m].copy(), new_p0=n0[:m].copy())
+
+    # ---------------------------------------------------------------- stereo rectification (camera.cpp:300-546)
+    def rectify_init(self, K_l, D_l, K_r, D_r, T_lr, w, h):
+        """Build the rectification maps on the device; returns (K_rect [4], T_lr_rect [4,4])."""
+        a = [np.ascontiguousarray(v, np.float32) for v in (K_l, D_l, K_r, D_r, T_lr)]
+        K_rect, T_rect = np.zeros(4, np.float32), np.zeros((4, 4), np.float32)
+        check(self.h, self.L.vo_rectify_init(self.h, *[_ptr(v) for v in a], int(w), int(h), _ptr(K_rect), _ptr(T_rect)))
+        self._rect_wh = (int(w), int(h))
+        return K_rect, T_rect
+
+    def read_rectify_maps(self, right):
+        w, h = self._rect_wh
+        mu, mv = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+        check(self.h, self.L.vo_read_rectify_maps(self.h, 1 if right else 0, _ptr(mu), _ptr(mv)))
+        return mu, mv
+
+    def upload_image_rectified(self, slot, right, img):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        check(self.h, self.L.vo_upload_image_rectified(self.h, slot, 1 if right else 0, _ptr(img), img.shape[1], img.shape[0], img.strides[0]))

@@ -121,6 +121,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     for (int i = 0; i < 4; ++i) if (ctx->d_f32[i]) cudaFree(ctx->d_f32[i]);
     if (ctx->d_lba) cudaFree(ctx->d_lba);
     if (ctx->d_det) cudaFree(ctx->d_det);
+    if (ctx->d_rect) cudaFree(ctx->d_rect);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
@@ -216,6 +217,15 @@ static int set_image_common(vo_ctx *ctx, int slot, const uint8_t *data, int w, i
     uint8_t *raw = ctx->raw_base + (size_t)slot * ctx->raw_stride;
     if (step == (size_t)w) VO_CUDA(cudaMemcpyAsync(raw, data, (size_t)w * h, kind, st));
     else VO_CUDA(cudaMemcpy2DAsync(raw, w, data, step, w, h, kind, st));
+    S.levels_built = 0; S.deriv_built = 0; S.border0 = false; S.raw_pending = true;
+    return VO_OK;
+}
+
+int vo_slot_prepare(vo_ctx *ctx, int slot, int w, int h)
+{
+    int rc = slot_set_geometry(ctx, slot, w, h);
+    if (rc) return rc;
+    Slot &S = ctx->slots[slot];
     S.levels_built = 0; S.deriv_built = 0; S.border0 = false; S.raw_pending = true;
     return VO_OK;
 }

@@ -72,6 +72,10 @@ struct vo_ctx {
     // K-det scratch (score plane + per-bin state)
     void *d_det = nullptr;
     size_t det_bytes = 0;
+    // rectification: four CV_32FC1 maps + one distorted-image scratch plane (rectify.cu)
+    void *d_rect = nullptr;
+    size_t rect_bytes = 0;
+    int rect_w = 0, rect_h = 0;
     // LBA scratch
     void *d_lba = nullptr;
     size_t lba_bytes = 0;
@@ -96,6 +100,8 @@ struct vo_ctx {
 
 // Grow-only device+pinned staging; returns VO_OK or error.
 int vo_stage_reserve(vo_ctx *ctx, size_t bytes);
+// Size a slot for a w x h image whose pixels are about to be written into its raw plane by a kernel (api.cu).
+int vo_slot_prepare(vo_ctx *ctx, int slot, int w, int h);
 
 // pyramid.cu
 int vo_ensure_pyramids(vo_ctx *ctx, const int *slots, int n, int n_levels, int with_deriv);

@@ -119,8 +119,12 @@ StereoVO::StereoVO(std::string mode, std::string directory_intrinsic)
         p_.K_l[i] = (float)num((std::string("Camera.left.") + names[i]).c_str(), p_.K_l[i]);
         p_.K_r[i] = (float)num((std::string("Camera.right.") + names[i]).c_str(), p_.K_r[i]);
     }
-    if (num("flagDoUndistortion", 0) != 0)
-        throw std::runtime_error("vo_b200: flagDoUndistortion=1 (rectification remap) is outside the hot path of this build");
+    p_.do_undistortion = num("flagDoUndistortion", 0) != 0 ? 1 : 0;
+    const char *dn[5] = {"k1", "k2", "p1", "p2", "k3"};               // cvD order, stereo_vo.cpp:158-164
+    for (int i = 0; i < 5; ++i) {
+        p_.D_l[i] = (float)num((std::string("Camera.left.") + dn[i]).c_str(), 0.0);
+        p_.D_r[i] = (float)num((std::string("Camera.right.") + dn[i]).c_str(), 0.0);
+    }
     if (tlr.size() == 16) memcpy(p_.T_lr, tlr.data(), 64);
     p_.thres_error = (float)num("feature_tracker.thres_error", p_.thres_error);
     p_.thres_bidirection = (float)num("feature_tracker.thres_bidirection", p_.thres_bidirection);
@@ -144,6 +148,14 @@ void StereoVO::init()
     // (a few thousand landmarks x ~10 observations) then never re-allocate pinned memory inside the frame loop
     const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 4, std::max(4 * nb + 4096, 262144), nullptr, &ctx_);
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
+    memcpy(K_use_l_, p_.K_l, 16); memcpy(K_use_r_, p_.K_r, 16); memcpy(T_lr_use_, p_.T_lr, 64);
+    if (p_.do_undistortion) {
+        // stereo_vo.cpp:414-428: rectified images, the rectified camera for both sides, the rectified extrinsics
+        float K_rect[4];
+        const int rr = vo_rectify_init(ctx_, p_.K_l, p_.D_l, p_.K_r, p_.D_r, p_.T_lr, p_.width, p_.height, K_rect, T_lr_use_);
+        if (rr) fail(ctx_, rr);
+        memcpy(K_use_l_, K_rect, 16); memcpy(K_use_r_, K_rect, 16);
+    }
 }
 
 StereoVO::~StereoVO() { if (ctx_) vo_ctx_destroy(ctx_); }
@@ -204,7 +216,7 @@ void StereoVO::reconstruct(FrameRec &f, int n_first)
     if (n_first <= 0) return;
     std::vector<float> Xw((size_t)n_first * 3);
     std::vector<uint8_t> ok(n_first);
-    const int rc = vo_stereo_reconstruct(ctx_, f.pts_l.data(), f.pts_r.data(), n_first, p_.K_l, p_.K_r, p_.T_lr, f.Twc, Xw.data(), ok.data());
+    const int rc = vo_stereo_reconstruct(ctx_, f.pts_l.data(), f.pts_r.data(), n_first, K_use_l_, K_use_r_, T_lr_use_, f.Twc, Xw.data(), ok.data());
     if (rc) fail(ctx_, rc);
     for (int i = 0; i < n_first; ++i) {
         if (!ok[i]) continue;
@@ -286,8 +298,8 @@ void StereoVO::localBundleAdjustment()
     pr.n_frames = nf; pr.n_opt = nf - NUM_FIX; pr.n_points = (int)lms.size(); pr.n_obs = (int)obs_frame.size();
     pr.poses = poses.data(); pr.opt_index = opt_index.data(); pr.points = points.data(); pr.obs_ptr = obs_ptr.data();
     pr.obs_frame = obs_frame.data(); pr.obs_right = obs_right.data(); pr.obs_px = obs_px.data();
-    for (int i = 0; i < 4; ++i) { pr.K_l[i] = p_.K_l[i]; pr.K_r[i] = p_.K_r[i]; }
-    for (int i = 0; i < 16; ++i) pr.T_lr[i] = p_.T_lr[i];
+    for (int i = 0; i < 4; ++i) { pr.K_l[i] = K_use_l_[i]; pr.K_r[i] = K_use_r_[i]; }
+    for (int i = 0; i < 16; ++i) pr.T_lr[i] = T_lr_use_[i];
     for (int r = 0; r < 3; ++r) pr.T_lr[r * 4 + 3] *= inv_scale;
     pr.is_stereo = 1; pr.huber = 0.5; pr.lambda = 0.00001; pr.max_iter = 10;
     std::vector<double> poses_out(poses.size()), points_out(points.size()), avg(pr.max_iter);
@@ -375,7 +387,7 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     memset(&fp, 0, sizeof(fp));
     fp.track.window_size = p_.window_size; fp.track.max_level = p_.max_level; fp.track.thres_error = p_.thres_error;
     fp.track.thres_poseba_error = p_.thres_poseba_error;
-    memcpy(fp.track.K_l, p_.K_l, 16); memcpy(fp.track.K_r, p_.K_r, 16); memcpy(fp.track.T_lr, p_.T_lr, 64);
+    memcpy(fp.track.K_l, K_use_l_, 16); memcpy(fp.track.K_r, K_use_r_, 16); memcpy(fp.track.T_lr, T_lr_use_, 64);
     fp.track.do_scale_refine = p_.do_scale_refine;
     // mask_sampson = dist < THRES_SAMPSON with dist = 100 for y > 660 (stereo_vo.cpp:657-668): the stub only fires
     // when the threshold is below 100
@@ -389,10 +401,19 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     memset(&res, 0, sizeof(res));
     res.T_wc = T_wc; res.dT_pc = dT; res.new_l1 = new_l_.data(); res.new_r1 = new_r_.data(); res.counts = info_.counts;
 
+    const unsigned char *up_l = img_left.data, *up_r = img_right.data;
+    if (p_.do_undistortion) {
+        // stereo_vo.cpp:414-421: rectify on the device; the frame step then finds the images already in their slots
+        int rr = vo_upload_image_rectified(ctx_, sl, 0, img_left.data, w, h, img_left.step);
+        if (!rr) rr = vo_upload_image_rectified(ctx_, sr, 1, img_right.data, w, h, img_right.step);
+        if (rr == VO_ERR_SIZE_MISMATCH) throw std::runtime_error(vo_last_error(ctx_));
+        if (rr) fail(ctx_, rr);
+        up_l = up_r = nullptr;
+    }
     if (!prev_) {
         // ---- the very first image (stereo_vo.cpp:842-949)
         fp.new_depth_gate = 0;
-        const int rc = vo_stereo_frame_step(ctx_, &fp, -1, sl, sr, img_left.data, img_right.data, w, h, img_left.step, 0, nullptr, nullptr,
+        const int rc = vo_stereo_frame_step(ctx_, &fp, -1, sl, sr, up_l, up_r, w, h, img_left.step, 0, nullptr, nullptr,
                                             nullptr, nullptr, nullptr, nullptr, &res);
         if (rc) fail(ctx_, rc);
         const int m = res.n_new;
@@ -426,7 +447,7 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     res.index = out_idx_.data(); res.pts_l1 = out_l1_.data(); res.pts_r1 = out_r1_.data();
     fp.new_depth_gate = 1;
     const auto t_step = Clock::now();
-    const int rc = vo_stereo_frame_step(ctx_, &fp, sp, sl, sr, img_left.data, img_right.data, w, h, img_left.step, n, in_l0_.data(), in_r0_.data(),
+    const int rc = vo_stereo_frame_step(ctx_, &fp, sp, sl, sr, up_l, up_r, w, h, img_left.step, n, in_l0_.data(), in_r0_.data(),
                                         in_X_.data(), in_tri_.data(), pv.Twc, pv.dT01, &res);
     if (rc) fail(ctx_, rc);
     const float ms_step = ms_since(t_step);

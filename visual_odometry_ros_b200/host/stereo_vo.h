@@ -62,6 +62,10 @@ public:
         int det_edge = 31;
         long long det_min_score = 0;
         int device = 0;
+        // flagDoUndistortion (stereo_vo.cpp:239, 414-428): rectify both images on the device; K_l / K_r / T_lr above are
+        // then the RAW pinhole-radtan cameras and D_l / D_r their distortion (k1, k2, p1, p2, k3; camera.cpp:30-35)
+        int do_undistortion = 0;
+        float D_l[5] = {0, 0, 0, 0, 0}, D_r[5] = {0, 0, 0, 0, 0};
     };
 
     StereoVO(std::string mode, std::string directory_intrinsic);   // stereo_vo.cpp:9-53 (yaml via a minimal parser)
@@ -109,6 +113,7 @@ private:
     void pushStats(const FrameRec &f, bool keyframe);
 
     Parameters p_;
+    float K_use_l_[4], K_use_r_[4], T_lr_use_[16];   // what the step uses: raw or rectified cameras
     vo_ctx *ctx_ = nullptr;
     AlgorithmStatistics stat_;
     cv::Mat img_debug_;
