@@ -139,3 +139,39 @@ def test_stereo_vo_class_free_running(seq):
     assert same_ids >= 3
     assert vo.launch_count > 0
     vo.close()
+
+
+def test_full_size_sequence_properties():
+    """BASELINE config 3 at KITTI size (1241x376, ~2000+ tracked features): properties that do not need the oracle --
+    determinism (two instances, bit-identical poses and tracks), bounded drift against the rendered ground truth,
+    unique landmark ids, tracks inside the image, keyframes + local BA happening, statistics in step with the frames."""
+    import torch
+    from visual_odometry_ros_b200 import stereo_vo as svo
+    n = 24
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    L, R, T = synth.stereo_sequence(n, synth.KITTI_W, synth.KITTI_H, synth.kitti_K(), seed=3303, device=dev)
+    K, Tlr = synth.kitti_K(), synth.kitti_T_lr()
+    mk = lambda: svo.StereoVO(svo.make_parameters(synth.KITTI_W, synth.KITTI_H, K, K, Tlr, n_bins_u=64, n_bins_v=32))
+    a, b = mk(), mk()
+    T0inv = np.linalg.inv(T[0])
+    n_kf = n_lba = 0
+    for k in range(n):
+        a.trackStereoImages(L[k], R[k], 0.1 * k)
+        b.trackStereoImages(L[k], R[k], 0.1 * k)
+        fa, fb = a.frame_info(), b.frame_info()
+        assert np.array_equal(a.pose(), b.pose()), k
+        ids, pl, pr = a.tracks()
+        ids_b, pl_b, pr_b = b.tracks()
+        assert np.array_equal(ids, ids_b) and np.array_equal(pl, pl_b) and np.array_equal(pr, pr_b)
+        assert len(np.unique(ids)) == len(ids)
+        assert np.all((pl[:, 0] > 0) & (pl[:, 0] < synth.KITTI_W) & (pl[:, 1] > 0) & (pl[:, 1] < synth.KITTI_H))
+        assert fa["keyframe"] == fb["keyframe"] and fa["lba_points"] == fb["lba_points"]
+        n_kf += fa["keyframe"]; n_lba += int(fa["lba_points"] > 0)
+        if k >= 2:
+            assert fa["n_tracked"] > 1200, (k, fa)
+        gt = T0inv @ T[k]
+        dist = max(1.0, float(np.linalg.norm(gt[:3, 3])))
+        assert np.linalg.norm(a.pose()[:3, 3] - gt[:3, 3]) <= 0.01 * dist + 0.01, k          # <= 1 % translation drift
+    assert n_kf >= 5 and n_lba >= 3
+    assert len(a.keyframe_poses()) == n_kf
+    a.close(); b.close()
