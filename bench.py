@@ -443,20 +443,30 @@ def concurrent_sequences(svo, Lp, Rp, K4, Tlr, nbu, nbv, n_seq=8, n_frames=60):
     for vo in vos:                       # first frame + first step outside the timed region (allocations)
         vo.trackStereoImages(Lp[0], Rp[0], 0.0)
         vo.trackStereoImages(Lp[1], Rp[1], 0.1)
-    bar = threading.Barrier(n_seq + 1)
+    bar = threading.Barrier(n_seq + 1, timeout=120)
+    errors = []
 
     def run(vo):
-        bar.wait()
-        for k in range(2, n_frames):
-            vo.trackStereoImages(Lp[k], Rp[k], 0.1 * k)
-        bar.wait()
-    th = [threading.Thread(target=run, args=(vo,)) for vo in vos]
+        try:
+            bar.wait()
+            for k in range(2, n_frames):
+                vo.trackStereoImages(Lp[k], Rp[k], 0.1 * k)
+            bar.wait()
+        except Exception as e:          # a failing sequence must not leave the others (and the bench) waiting
+            errors.append(repr(e))
+            bar.abort()
+    th = [threading.Thread(target=run, args=(vo,), daemon=True) for vo in vos]
     for t in th:
         t.start()
-    bar.wait()
-    t0 = time.perf_counter()
-    bar.wait()
-    dt = time.perf_counter() - t0
+    try:
+        bar.wait()
+        t0 = time.perf_counter()
+        bar.wait()
+        dt = time.perf_counter() - t0
+    except threading.BrokenBarrierError:
+        for t in th:
+            t.join(timeout=5)
+        return {"sequences": n_seq, "error": errors[:1] or ["barrier broken"]}
     for t in th:
         t.join()
     poses = [vo.pose() for vo in vos]

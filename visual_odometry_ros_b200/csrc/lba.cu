@@ -23,6 +23,7 @@
 #include "vo_internal.cuh"
 
 #include <cstdio>
+#include <mutex>
 #include <cstdlib>
 
 #include <cstring>
@@ -805,17 +806,21 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) d.R_rl[i * 3 + j] = T_rl[i * 4 + j]; d.t_rl[i] = T_rl[i * 4 + 3]; }
     d.huber = p->huber; d.lambda = p->lambda;
 
-    VO_CUDA(cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
-    VO_CUDA(cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
-    {   // the three kernels alternate 21 times: keep ONE L1 / shared-memory carve-out so that the SMs are not
-        // re-partitioned (and drained) between every pair of launches
-        static bool once = false;
-        if (!once) {
-            once = true;
+    {   // Function attributes are process-wide: set them ONCE to the largest value any problem can need (several
+        // contexts may solve concurrently from different host threads; a per-call value would race).  One carve-out
+        // for the three kernels, which alternate 21 times per solve.
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [&]() {
+            const size_t max_solve = ((size_t)(6 * LBA_MAX_OPT) * (6 * LBA_MAX_OPT + 1) + 2 * 6 * LBA_MAX_OPT + (size_t)LBA_MAX_OPT * LBA_NA) * 8;
+            cudaError_t e = cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
             cudaFuncSetAttribute(k_lba_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_update_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        }
+            attr_err = e;
+        });
+        if (attr_err != cudaSuccess) { ctx->last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err); return VO_ERR_CUDA; }
     }
     static const bool trace = getenv("VO_LBA_TRACE") != nullptr;
     std::vector<cudaEvent_t> evs;
