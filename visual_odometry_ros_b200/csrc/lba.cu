@@ -773,7 +773,10 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
         ctx->d_lba = nullptr; ctx->lba_bytes = 0;
         // grow geometrically: window problems grow by a few landmarks per keyframe and a cudaFree + cudaMalloc
         // pair costs milliseconds
-        const size_t want = total + total / 2;
+        // (and cudaFree synchronises the whole device, stalling every other context's stream): start at 32 MB,
+        // enough for ~10 k landmarks with 10 stereo observations each
+        size_t want = total + total / 2;
+        if (want < ((size_t)32 << 20)) want = (size_t)32 << 20;
         VO_CUDA(cudaMalloc(&ctx->d_lba, want));
         ctx->lba_bytes = want;
     }
