@@ -536,85 +536,64 @@ k_lba_solve(const LbaDev d, int iter)
     __syncthreads();
 
     STAMP(1);
-    // The factorisation and the forward solve are latency chains over a 6N x 6N (<= 96 x 96) matrix in shared
-    // memory: they run on ONE warp with warp barriers (the 8-warp version spent most of each column in
-    // __syncthreads); the arithmetic and its order are unchanged.
-    if (tid < 32) {
-        // ---- pivoted LDLT (lower storage), the algorithm of Eigen::LDLT::compute
-        for (int k = 0; k < n; ++k) {
-            {
-                double bv = -1.0;
-                int bi = k;
-                for (int i = k + tid; i < n; i += 32) {
-                    const double v = fabs(SM(i, i));
-                    if (v > bv) { bv = v; bi = i; }
-                }
-                // warp arg-max of |diag| (first maximal index, as Eigen's maxCoeff): non-negative doubles order like
-                // their bit patterns, so three integer redux.sync replace five rounds of 64-bit shuffles + FP64 compares
-                {
-                    const unsigned long long key = bv >= 0.0 ? (unsigned long long)__double_as_longlong(bv) : 0ull;
-                    const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
-                    const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
-                    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-                    const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
-                    const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-                    const bool win = has && hi == mhi && (unsigned)key == mlo;
-                    bi = __reduce_min_sync(0xffffffffu, win ? bi : 0x7fffffff);
-                    if (bi == 0x7fffffff) bi = k;
-                }
-                if (tid == 0) { s_big = bi; s_tr[k] = bi; }
+    // ---- pivoted LDLT (lower storage), pivoting as Eigen::LDLT::compute (largest remaining |diagonal|, first index on
+    // ties), right-looking: the products are Eigen's, L(i,j) * (D_j L(k,j)), subtracted one column at a time instead of
+    // as a pre-summed dot product, so every element update of a column is independent.  Per column: warp 0 finds the
+    // pivot with three integer redux.sync (non-negative doubles order like their bit patterns), all eight warps swap,
+    // scale and update the trailing triangle (warp w owns rows w, w+8, ...; lanes own columns).
+    for (int k = 0; k < n; ++k) {
+        if (tid < 32) {
+            double bv = -1.0;
+            int bi = k;
+            for (int i = k + tid; i < n; i += 32) {
+                const double v = fabs(SM(i, i));
+                if (v > bv) { bv = v; bi = i; }
             }
-            __syncwarp();
-            const int big = s_big;
-            if (big != k) {
-                const int s = n - big - 1;
-                for (int j = tid; j < k; j += 32) { const double t = SM(k, j); SM(k, j) = SM(big, j); SM(big, j) = t; }
-                for (int i = tid; i < s; i += 32) { const double t = SM(big + 1 + i, k); SM(big + 1 + i, k) = SM(big + 1 + i, big); SM(big + 1 + i, big) = t; }
-                for (int i = k + 1 + tid; i < big; i += 32) { const double t = SM(i, k); SM(i, k) = SM(big, i); SM(big, i) = t; }
-                if (tid == 0) { const double t = SM(k, k); SM(k, k) = SM(big, big); SM(big, big) = t; }
-                __syncwarp();
-            }
-            // right-looking column step (the products are Eigen's, L(i,j) * (D_j L(k,j)); they are subtracted one
-            // column at a time instead of as a pre-summed dot product, so every element update of a column is
-            // independent and the serial chain is one FP64 operation per column instead of k)
-            const int rs = n - k - 1;
-            const double akk = SM(k, k);
-            // L(:,k) = A(:,k) / D_k as a multiplication by the correctly rounded reciprocal: an IEEE FP64 division is a
-            // ~1100-cycle dependent sequence on this machine and sat on the critical path of every column (measured:
-            // 2300 of 3400 cycles per column); the quotient may differ from Eigen's by one ulp
-            if (rs > 0 && fabs(akk) > 0.0) {
-                const double rk = __drcp_rn(akk);
-                for (int i = tid; i < rs; i += 32) SM(k + 1 + i, k) *= rk;
-            }
-            __syncwarp();
-            for (int i = tid; i < rs; i += 32) temp[i] = akk * SM(k + 1 + i, k);      // D_k * L(k+1+i, k)
-            __syncwarp();
-            // trailing lower triangle: A(r, c) -= L(r, k) * temp[c - k - 1] for k < c <= r
-            // rows are paired (a, rs-1-a) so that every active lane updates rs + 1 elements
-            for (int a0 = tid; 2 * a0 < rs; a0 += 32) {
-                const int a1 = rs - 1 - a0;
-                const double l0 = SM(k + 1 + a0, k), l1 = SM(k + 1 + a1, k);
-                // explicit load-4 / store-4 groups: S and temp are both shared-memory doubles, so the compiler
-                // must otherwise order every load after the previous store
-                double *row0 = &SM(k + 1 + a0, k + 1), *row1 = &SM(k + 1 + a1, k + 1);
-                const int n0 = a0 + 1, n1 = (a1 != a0) ? a1 + 1 : 0;
-                int bc = 0;
-                for (; bc + 4 <= n0; bc += 4) {
-                    const double t0 = temp[bc], t1 = temp[bc + 1], t2 = temp[bc + 2], t3 = temp[bc + 3];
-                    const double v0 = row0[bc], v1 = row0[bc + 1], v2 = row0[bc + 2], v3 = row0[bc + 3];
-                    row0[bc] = v0 - l0 * t0; row0[bc + 1] = v1 - l0 * t1; row0[bc + 2] = v2 - l0 * t2; row0[bc + 3] = v3 - l0 * t3;
-                }
-                for (; bc < n0; ++bc) row0[bc] -= l0 * temp[bc];
-                bc = 0;
-                for (; bc + 4 <= n1; bc += 4) {
-                    const double t0 = temp[bc], t1 = temp[bc + 1], t2 = temp[bc + 2], t3 = temp[bc + 3];
-                    const double v0 = row1[bc], v1 = row1[bc + 1], v2 = row1[bc + 2], v3 = row1[bc + 3];
-                    row1[bc] = v0 - l1 * t0; row1[bc + 1] = v1 - l1 * t1; row1[bc + 2] = v2 - l1 * t2; row1[bc + 3] = v3 - l1 * t3;
-                }
-                for (; bc < n1; ++bc) row1[bc] -= l1 * temp[bc];
-            }
-            __syncwarp();
+            const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
+            const unsigned long long key = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
+            const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
+            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
+            const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+            const bool win = has && hi == mhi && (unsigned)key == mlo;
+            bi = __reduce_min_sync(0xffffffffu, win ? bi : 0x7fffffff);
+            if (bi == 0x7fffffff) bi = k;
+            if (tid == 0) { s_big = bi; s_tr[k] = bi; }
         }
+        __syncthreads();
+        const int big = s_big;
+        if (big != k) {
+            const int sr = n - big - 1;
+            for (int j = tid; j < k; j += LBA_THREADS) { const double t = SM(k, j); SM(k, j) = SM(big, j); SM(big, j) = t; }
+            for (int i = tid; i < sr; i += LBA_THREADS) { const double t = SM(big + 1 + i, k); SM(big + 1 + i, k) = SM(big + 1 + i, big); SM(big + 1 + i, big) = t; }
+            for (int i = k + 1 + tid; i < big; i += LBA_THREADS) { const double t = SM(i, k); SM(i, k) = SM(big, i); SM(big, i) = t; }
+            if (tid == 0) { const double t = SM(k, k); SM(k, k) = SM(big, big); SM(big, big) = t; }
+            __syncthreads();
+        }
+        const int rs = n - k - 1;
+        const double akk = SM(k, k);
+        {   // L(:,k) = A(:,k) * (1 / D_k) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp),
+            // temp = D_k * L(:,k)
+            const bool scale = rs > 0 && fabs(akk) > 0.0;
+            const double rk = scale ? __drcp_rn(akk) : 0.0;
+            for (int i = tid; i < rs; i += LBA_THREADS) {
+                double l = SM(k + 1 + i, k);
+                if (scale) { l *= rk; SM(k + 1 + i, k) = l; }
+                temp[i] = akk * l;
+            }
+        }
+        __syncthreads();
+        // trailing lower triangle: A(k+1+r, k+1+c) -= L(k+1+r, k) * temp[c] for c <= r
+        {
+            const int lane = tid & 31, wid = tid >> 5;
+            for (int r = wid; r < rs; r += LBA_THREADS / 32) {
+                const double l = SM(k + 1 + r, k);
+                for (int c = lane; c <= r; c += 32) SM(k + 1 + r, k + 1 + c) -= l * temp[c];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < 32) {
         // ---- solve: P b, L^-1, D^-1, L^-T, P^T  (column-oriented updates keep the row-wise order)
         if (tid == 0) for (int k = 0; k < n; ++k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
         __syncwarp();
