@@ -142,6 +142,17 @@ struct NewDev {
     int *n_out;
 };
 
+// depth gate of the new features (stereo_vo.cpp:723-725): one thread per candidate, many CTAs (a 4x4 Jacobi SVD per
+// point is ~2 k dependent instructions; inside the single compaction CTA it was 22 us of the frame)
+__global__ void __launch_bounds__(128) k_new_depth(const NewDev d, uint8_t *mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *d.n_in || !mask[i]) return;
+    float Xl[3], Xr[3];
+    tri_point(d.pl[i], d.pr[i], d.R_rl, d.t_rl, d.K_l, d.K_r, Xl, Xr);
+    if (!(Xl[2] > 0.f && Xr[2] > 0.f)) mask[i] = 0;
+}
+
 __global__ void __launch_bounds__(1024) k_new_gate(const NewDev d)
 {
     __shared__ int s_warp[32];
@@ -151,12 +162,7 @@ __global__ void __launch_bounds__(1024) k_new_gate(const NewDev d)
     const int n = *d.n_in;
     for (int c0 = 0; c0 < n; c0 += 1024) {
         const int i = c0 + threadIdx.x;
-        bool keep = i < n && d.mask[i];
-        if (keep && d.depth_gate) {
-            float Xl[3], Xr[3];
-            tri_point(d.pl[i], d.pr[i], d.R_rl, d.t_rl, d.K_l, d.K_r, Xl, Xr);
-            keep = Xl[2] > 0.f && Xr[2] > 0.f;
-        }
+        const bool keep = i < n && d.mask[i];
         const int pos = scan_chunk(keep, s_warp, &s_base);
         if (keep) { d.out_l[pos] = d.pl[i]; d.out_r[pos] = d.pr[i]; }
     }
@@ -386,6 +392,7 @@ extern "C" int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *f
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) nd.R_rl[r * 3 + c] = T_rl[r * 4 + c]; nd.t_rl[r] = T_rl[r * 4 + 3]; }
         memcpy(nd.K_l, prm->K_l, 16); memcpy(nd.K_r, prm->K_r, 16);
         nd.out_l = (float2 *)(dv + o_nl); nd.out_r = (float2 *)(dv + o_nr); nd.n_out = ints + 10;
+        if (nd.depth_gate) { k_new_depth<<<vo_div_up(nb, 128), 128, 0, ctx->stream>>>(nd, dv + o_cm); ctx->launches++; }
         k_new_gate<<<1, 1024, 0, ctx->stream>>>(nd);
         ctx->launches++;
     }

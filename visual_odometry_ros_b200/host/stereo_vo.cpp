@@ -399,7 +399,7 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     float T_wc[16], dT[16];
     vo_stereo_frame_result res;
     memset(&res, 0, sizeof(res));
-    res.T_wc = T_wc; res.dT_pc = dT; res.new_l1 = new_l_.data(); res.new_r1 = new_r_.data(); res.counts = info_.counts;
+    res.T_wc = T_wc; res.dT_pc = dT; res.new_l1 = new_l_.data(); res.new_r1 = new_r_.data(); res.counts = p_.collect_gate_counts ? info_.counts : nullptr;
 
     const unsigned char *up_l = img_left.data, *up_r = img_right.data;
     if (p_.do_undistortion) {

@@ -66,6 +66,7 @@ public:
         // then the RAW pinhole-radtan cameras and D_l / D_r their distortion (k1, k2, p1, p2, k3; camera.cpp:30-35)
         int do_undistortion = 0;
         float D_l[5] = {0, 0, 0, 0, 0}, D_r[5] = {0, 0, 0, 0, 0};
+        int collect_gate_counts = 0;     // 1: FrameInfo::counts (survivors after every gate; three extra tiny launches per frame)
     };
 
     StereoVO(std::string mode, std::string directory_intrinsic);   // stereo_vo.cpp:9-53 (yaml via a minimal parser)
