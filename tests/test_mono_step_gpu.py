@@ -56,6 +56,9 @@ def test_mono_frame_step_matches_oracle(states, bundled_only):
             continue
         ctx.upload_image(0, s["I0"])
         g = ctx.mono_frame_step(0, 1, s["I1"], *args, **kw)
+        gf = ctx.mono_frame_step(0, 1, s["I1"], *args, want_counts=False, **kw)      # fused K4 + K7 chain
+        for key in ("index", "pts1", "T_wc", "dT01", "dT10", "new_p1", "new_p0"):
+            assert np.array_equal(gf[key], g[key]), (s["k"], key)
         inter = np.intersect1d(g["index"], o["index"])
         agree += len(inter); total += max(len(g["index"]), len(o["index"]))
         if np.array_equal(g["index"], o["index"]):

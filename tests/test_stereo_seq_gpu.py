@@ -74,6 +74,12 @@ def test_frame_step_sequence_teacher_forced(seq):
             continue
         g = ctx.stereo_frame_step(sp, sl, sr, L[k], R[k], dbg["pts_l0"], dbg["pts_r0"], dbg["Xw"], dbg["tri"], dbg["T_wp"],
                                   dbg["dT_prev"], **common)
+        # the fused per-feature chain (no gate counts: one launch for l0->l1 / trackWithScale / l1->r1 and one for the
+        # bidirectional match of the new features) must give exactly what the separate launches give
+        gf = ctx.stereo_frame_step(sp, sl, sr, L[k], R[k], dbg["pts_l0"], dbg["pts_r0"], dbg["Xw"], dbg["tri"], dbg["T_wp"],
+                                   dbg["dT_prev"], want_counts=False, **common)
+        for key in ("index", "pts_l1", "pts_r1", "T_wc", "dT_pc", "new_l1", "new_r1"):
+            assert np.array_equal(gf[key], g[key]), (k, key)
         st = dbg["step"]
         inter = np.intersect1d(g["index"], st["index"])
         agree_idx += len(inter)

@@ -543,7 +543,7 @@ class Context:
 
     def mono_frame_step(self, slot_0, slot_1, img_1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_prior, K, win, max_level,
                         thres_err, thres_bi, thres_sampson, thres_poseba, use_bundled_only, n_bins_u=0, n_bins_v=0, det_edge=31,
-                        det_min_score=0, do_scale_refine=True):
+                        det_min_score=0, do_scale_refine=True, want_counts=True):
         """Steady-state branch of MonoVO::trackImage (mono_vo.cpp:724-992), one synchronisation."""
         prm = MonoFrameParams()
         prm.window_size, prm.max_level, prm.thres_error = int(win), int(max_level), float(thres_err)
@@ -564,7 +564,8 @@ class Context:
         n1, n0 = np.zeros((nbins, 2), np.float32), np.zeros((nbins, 2), np.float32)
         counts = np.zeros(5, np.int32)
         res = MonoFrameResult()
-        res.T_wc, res.dT01, res.dT10, res.index, res.pts1, res.counts = _ptr(T_wc), _ptr(dT01), _ptr(dT10), _ptr(idx), _ptr(o1), _ptr(counts)
+        res.T_wc, res.dT01, res.dT10, res.index, res.pts1 = _ptr(T_wc), _ptr(dT01), _ptr(dT10), _ptr(idx), _ptr(o1)
+        res.counts = _ptr(counts) if want_counts else None
         res.new_p1, res.new_p0 = _ptr(n1), _ptr(n0)
         assert img_1.dtype == np.uint8 and img_1.ndim == 2 and img_1.strides[1] == 1
         h, w, step = img_1.shape[0], img_1.shape[1], img_1.strides[0]

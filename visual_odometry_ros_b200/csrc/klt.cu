@@ -15,6 +15,7 @@
 // L1/L2 (the padded pyramids make the gathers branch-free), so a level costs
 // (w+1)^2 * (1 + 4 + k) algorithmic bytes, which is the figure bench.py reports against.
 #include "vo_internal.cuh"
+#include "klt_scale_device.cuh"
 
 #include <cfloat>
 #include <cstdlib>
@@ -381,19 +382,12 @@ __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_
 #ifndef KLT2_WPB
 #define KLT2_WPB 4          // warps (features) per CTA
 #endif
-template <int WIN, int MINB>
-__global__ void __launch_bounds__(32 * KLT2_WPB, MINB * 4 / KLT2_WPB)
-k_klt2(const KltArgs a)
+// One (pair, feature) on one warp: every level, every iteration, the fused post-filter epilogue.
+template <int WIN>
+__device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, const int f, uint32_t *Ibuf, uint32_t *Dbuf, uint32_t *Jbuf,
+                                             const int lane)
 {
     using C = Klt2Cfg<WIN>;
-    extern __shared__ __align__(16) uint32_t smem_u32[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int pair = blockIdx.y;
-    if (f >= a.n) return;
-    uint32_t *Ibuf = smem_u32 + wib * C::WARP_WORDS;
-    uint32_t *Dbuf = Ibuf + C::I_WORDS;
-    uint32_t *Jbuf = Dbuf + C::D_WORDS;
     const size_t gi = (size_t)pair * a.n + f;
     if (a.skip_mask && !a.skip_mask[gi]) return;
     const SlotDesc &S0 = a.slots[a.s0.id[pair]];
@@ -600,6 +594,45 @@ k_klt2(const KltArgs a)
     if (lane == 0) klt_epilogue(a, gi, S0, stored, status, errv);
 }
 
+template <int WIN, int MINB>
+__global__ void __launch_bounds__(32 * KLT2_WPB, MINB * 4 / KLT2_WPB)
+k_klt2(const KltArgs a)
+{
+    using C = Klt2Cfg<WIN>;
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= a.n) return;
+    uint32_t *Ibuf = smem_u32 + wib * C::WARP_WORDS;
+    klt2_feature<WIN>(a, blockIdx.y, f, Ibuf, Ibuf + C::I_WORDS, Ibuf + C::I_WORDS + C::D_WORDS, lane);
+}
+
+// Fused tracking chain of the stereo frame step (stereo_vo.cpp:533-571): trackWithPrior(l0 -> l1), trackWithScale,
+// trackWithPrior(l1 -> r1) for ONE feature on ONE warp, back to back.  The three stages of a feature depend on each
+// other, but features do not depend on each other: as three launches every stage waits for its slowest feature (a
+// non-converging feature runs 30 iterations x 4 levels ~ 70 us while the median one needs a few), as one launch only
+// the sum over one feature's stages matters.  Results are identical to the three-launch sequence.
+#define VO_CHAIN_BACK 1     // second LK pass (the backward pass of a bidirectional track)
+#define VO_CHAIN_SCALE 2    // trackWithScale
+#define VO_CHAIN_NEXT 4     // third LK pass (l1 -> r1)
+template <int WIN>
+__global__ void __launch_bounds__(32 * KLT2_WPB, 4 * 4 / KLT2_WPB)
+k_track_chain(const KltArgs a1, const KltArgs a2, const KltScaleArgs sc, const KltArgs a3, const int stages)
+{
+    using C = Klt2Cfg<WIN>;
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= a1.n) return;
+    uint32_t *Ibuf = smem_u32 + wib * C::WARP_WORDS;
+    uint32_t *Dbuf = Ibuf + C::I_WORDS, *Jbuf = Dbuf + C::D_WORDS;
+    klt2_feature<WIN>(a1, 0, f, Ibuf, Dbuf, Jbuf, lane);
+    __syncwarp();                          // lane 0's point / status / mask stores are visible to the whole warp
+    if (stages & VO_CHAIN_BACK) { klt2_feature<WIN>(a2, 0, f, Ibuf, Dbuf, Jbuf, lane); __syncwarp(); }
+    if (stages & VO_CHAIN_SCALE) { klt_scale_feature(sc, f, lane); __syncwarp(); }
+    if (stages & VO_CHAIN_NEXT) klt2_feature<WIN>(a3, 0, f, Ibuf, Dbuf, Jbuf, lane);
+}
+
 template <int WIN>
 static cudaError_t launch_klt2(const KltArgs &a, dim3 grd, cudaStream_t st)
 {
@@ -675,6 +708,112 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
         else k_klt<31><<<grd, 128, 0, ctx->stream>>>(a);
         ctx->launches++;
     }
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
+// Fused per-feature chains (one pair, device pointers, asynchronous).  They fall back to separate launches for window
+// sizes without a k_klt2 instantiation or when VO_CHAIN_UNFUSED is set (A/B switch).
+static void fill_klt_args(vo_ctx *ctx, KltArgs &a, int s0, int s1, const float *pts0_d, float *pts1_d, uint8_t *status_d, float *err_d, int n,
+                          int win, int eff, int flags, const KltPost &post)
+{
+    a.slots = ctx->d_slots;
+    a.s0.id[0] = s0; a.s1.id[0] = s1;
+    a.pts0 = reinterpret_cast<const float2 *>(pts0_d); a.pts1 = reinterpret_cast<float2 *>(pts1_d);
+    a.status = status_d; a.err = err_d; a.counters = nullptr;
+    a.skip_mask = (post.skip_masked && post.mask) ? post.mask : nullptr;
+    a.n = n; a.win = win; a.top_level = eff; a.flags = flags;
+    a.max_count = 30; a.min_eig = 1e-4f; a.eps2 = 0.01 * 0.01;
+    a.post = post;
+}
+static bool chain_unfused(int win)
+{
+    static const bool unfused = getenv("VO_CHAIN_UNFUSED") != nullptr;
+    return unfused || win != 21;
+}
+static int clamp_level(vo_ctx *ctx, int slot, int win, int max_level)
+{
+    const Slot &A = ctx->slots[slot];
+    int eff = vo_effective_max_level(A.w, A.h, win, max_level < 0 ? 0 : max_level);
+    return eff > ctx->max_levels - 1 ? ctx->max_levels - 1 : eff;
+}
+
+// stereo_vo.cpp:533-571: trackWithPrior(l0 -> l1), trackWithScale, trackWithPrior(l1 -> r1)
+int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, const float *pts_l0_d, float *pts_l1_d, float *pts_r1_d,
+                            const float *scale_d, uint8_t *mask_d, int *nan_flag_d, int n, int win, int max_level, float thres_err,
+                            int do_scale)
+{
+    if (n <= 0) return VO_OK;
+    const int eff = clamp_level(ctx, slot_l0, win, max_level);
+    const int sl[3] = {slot_l0, slot_l1, slot_r1};
+    int rc = vo_ensure_pyramids(ctx, sl, 2, eff + 1, 1);          // templates come from l0 and l1
+    if (rc) return rc;
+    rc = vo_ensure_pyramids(ctx, sl + 2, 1, eff + 1, 0);
+    if (rc) return rc;
+    KltPost post{};
+    post.mode = 2; post.thres_err = thres_err; post.mask = mask_d; post.skip_masked = 1;
+    if (chain_unfused(win)) {
+        rc = vo_klt_launch(ctx, 1, &slot_l0, &slot_l1, pts_l0_d, n, win, max_level, VO_KLT_USE_INITIAL_FLOW, pts_l1_d, nullptr, nullptr, nullptr, &post);
+        if (rc) return rc;
+        if (do_scale) { rc = vo_klt_scale_launch_d(ctx, slot_l0, slot_l1, pts_l0_d, scale_d, n, pts_l1_d, mask_d, nan_flag_d); if (rc) return rc; }
+        return vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, pts_l1_d, n, win, max_level, VO_KLT_USE_INITIAL_FLOW, pts_r1_d, nullptr, nullptr, nullptr, &post);
+    }
+    KltArgs a1, a3;
+    fill_klt_args(ctx, a1, slot_l0, slot_l1, pts_l0_d, pts_l1_d, nullptr, nullptr, n, win, eff, VO_KLT_USE_INITIAL_FLOW, post);
+    fill_klt_args(ctx, a3, slot_l1, slot_r1, pts_l1_d, pts_r1_d, nullptr, nullptr, n, win, eff, VO_KLT_USE_INITIAL_FLOW, post);
+    KltScaleArgs sc;
+    sc.slots = ctx->d_slots; sc.slot0 = slot_l0; sc.slot1 = slot_l1;
+    sc.pts0 = reinterpret_cast<const float2 *>(pts_l0_d); sc.scale = scale_d;
+    sc.pts_track = reinterpret_cast<float2 *>(pts_l1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
+    const size_t smem = (size_t)KLT2_WPB * Klt2Cfg<21>::WARP_WORDS * 4;
+    k_track_chain<21><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, smem, ctx->stream>>>(a1, a1, sc, a3, (do_scale ? VO_CHAIN_SCALE : 0) | VO_CHAIN_NEXT);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
+// Bidirectional track of one pair (feature_tracker.cpp:39-169): forward pass, backward pass seeded with pts0 whose
+// epilogue fuses the validity test, optionally followed by trackWithScale (the mono step, mono_vo.cpp:768-783).
+// with_prior: both passes start from the given prior and run at max_level (trackBidirectionWithPrior, 5x gate,
+// 0-px border); otherwise the forward pass starts at pts0 and the backward pass runs at max_level - 1 (3-px border).
+// back_d / st_d / stb_d / err_d / errb_d: scratch [n].  scale_d == nullptr skips the scale stage.
+int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, float *pts1_d, float *back_d, uint8_t *st_d, uint8_t *stb_d,
+                            float *err_d, float *errb_d, uint8_t *mask_d, int skip_masked, int n, int win, int max_level, float thres_err,
+                            float thres_bi, int with_prior, const float *scale_d, int *nan_flag_d)
+{
+    if (n <= 0) return VO_OK;
+    const int sl[2] = {slot0, slot1};
+    const int eff_f = clamp_level(ctx, slot0, win, max_level);
+    const int back_lvl = with_prior ? max_level : (max_level - 1 < 0 ? 0 : max_level - 1);
+    const int eff_b = clamp_level(ctx, slot0, win, back_lvl);
+    int rc = vo_ensure_pyramids(ctx, sl, 2, eff_f + 1, 1);         // both images serve as template
+    if (rc) return rc;
+    VO_CUDA(cudaMemcpyAsync(back_d, pts0_d, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));   // backward pass starts at pts0
+    KltPost pf{}, pb{};
+    pf.mode = 3; pf.thres_err = thres_err; pf.mask = mask_d; pf.skip_masked = skip_masked;
+    pb = pf;
+    pb.mode = 4; pb.border = with_prior ? 0 : 3;
+    pb.thres_bi2 = with_prior ? (thres_bi * thres_bi) * 5 : thres_bi * thres_bi;
+    pb.ref_pts = pts0_d; pb.fwd_pts = pts1_d; pb.fwd_status = st_d; pb.fwd_err = err_d;
+    const int flags_f = with_prior ? VO_KLT_USE_INITIAL_FLOW : 0;
+    if (chain_unfused(win)) {
+        rc = vo_klt_launch(ctx, 1, &slot0, &slot1, pts0_d, n, win, max_level, flags_f, pts1_d, st_d, err_d, nullptr, &pf);
+        if (rc) return rc;
+        rc = vo_klt_launch(ctx, 1, &slot1, &slot0, pts1_d, n, win, back_lvl, VO_KLT_USE_INITIAL_FLOW, back_d, stb_d, errb_d, nullptr, &pb);
+        if (rc) return rc;
+        if (scale_d) return vo_klt_scale_launch_d(ctx, slot0, slot1, pts0_d, scale_d, n, pts1_d, mask_d, nan_flag_d);
+        return VO_OK;
+    }
+    KltArgs a1, a2;
+    fill_klt_args(ctx, a1, slot0, slot1, pts0_d, pts1_d, st_d, err_d, n, win, eff_f, flags_f, pf);
+    fill_klt_args(ctx, a2, slot1, slot0, pts1_d, back_d, stb_d, errb_d, n, win, eff_b, VO_KLT_USE_INITIAL_FLOW, pb);
+    KltScaleArgs sc;
+    sc.slots = ctx->d_slots; sc.slot0 = slot0; sc.slot1 = slot1;
+    sc.pts0 = reinterpret_cast<const float2 *>(pts0_d); sc.scale = scale_d;
+    sc.pts_track = reinterpret_cast<float2 *>(pts1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
+    const size_t smem = (size_t)KLT2_WPB * Klt2Cfg<21>::WARP_WORDS * 4;
+    k_track_chain<21><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, smem, ctx->stream>>>(a1, a2, sc, a1, VO_CHAIN_BACK | (scale_d ? VO_CHAIN_SCALE : 0));
+    ctx->launches++;
     VO_CUDA(cudaGetLastError());
     return VO_OK;
 }

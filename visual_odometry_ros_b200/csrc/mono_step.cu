@@ -267,25 +267,25 @@ extern "C" int vo_mono_frame_step(vo_ctx *ctx, const vo_mono_frame_params *prm, 
         d.use_bundled_only = prm->use_bundled_only; d.thres_sampson = prm->thres_sampson;
         k_mono_prior<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(d);
         ctx->launches++;
-        // K4: forward pass with the prior, backward pass seeded with pts0; the bidirectional test is fused in its epilogue
-        KltPost post{};
-        post.thres_err = prm->thres_error; post.mask = d.mask;
-        post.mode = 3;
-        rc = vo_klt_launch(ctx, 1, &slot_0, &slot_1, (const float *)d.pts0, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
-                           (float *)d.pts1, dv + o_st, (float *)(dv + o_er), nullptr, &post);
-        if (rc) return rc;
-        VO_CUDA(cudaMemcpyAsync(dv + o_bk, dv + o_p0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        post.mode = 4; post.border = 0; post.thres_bi2 = (prm->thres_bidirection * prm->thres_bidirection) * 5;
-        post.ref_pts = (const float *)d.pts0; post.fwd_pts = (const float *)d.pts1; post.fwd_status = dv + o_st;
-        post.fwd_err = (const float *)(dv + o_er);
-        rc = vo_klt_launch(ctx, 1, &slot_1, &slot_0, (const float *)d.pts1, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
-                           (float *)(dv + o_bk), dv + o_sb, (float *)(dv + o_eb), nullptr, &post);
-        if (rc) return rc;
-        k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 0);
-        ctx->launches++;
-        if (prm->do_scale_refine) {
-            rc = vo_klt_scale_launch_d(ctx, slot_0, slot_1, (const float *)d.pts0, d.scale, n, (float *)d.pts1, d.mask, nan_flag);
+        // K4 + K7: trackBidirectionWithPrior (forward pass from the prior, backward pass seeded with pts0, validity test
+        // fused in its epilogue) and trackWithScale.  Without gate counts the three dependent stages of a feature run back
+        // to back in ONE launch; with counts they are separate launches so that the mask can be counted in between.
+        if (!res->counts) {
+            rc = vo_bidir_chain_launch_d(ctx, slot_0, slot_1, (const float *)d.pts0, (float *)d.pts1, (float *)(dv + o_bk), dv + o_st, dv + o_sb,
+                                         (float *)(dv + o_er), (float *)(dv + o_eb), d.mask, 0, n, prm->window_size, prm->max_level,
+                                         prm->thres_error, prm->thres_bidirection, 1, prm->do_scale_refine ? d.scale : nullptr, nan_flag);
             if (rc) return rc;
+        } else {
+            rc = vo_bidir_chain_launch_d(ctx, slot_0, slot_1, (const float *)d.pts0, (float *)d.pts1, (float *)(dv + o_bk), dv + o_st, dv + o_sb,
+                                         (float *)(dv + o_er), (float *)(dv + o_eb), d.mask, 0, n, prm->window_size, prm->max_level,
+                                         prm->thres_error, prm->thres_bidirection, 1, nullptr, nullptr);
+            if (rc) return rc;
+            k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 0);
+            ctx->launches++;
+            if (prm->do_scale_refine) {
+                rc = vo_klt_scale_launch_d(ctx, slot_0, slot_1, (const float *)d.pts0, d.scale, n, (float *)d.pts1, d.mask, nan_flag);
+                if (rc) return rc;
+            }
         }
         k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 1);
         k_mono_select<<<1, 1024, 0, ctx->stream>>>(d);
@@ -302,19 +302,9 @@ extern "C" int vo_mono_frame_step(vo_ctx *ctx, const vo_mono_frame_params *prm, 
         rc = vo_detect_launch_d(ctx, slot_1, (const float *)d.out1, n > 0 ? d.n_out : nullptr, n, prm->n_bins_u, prm->n_bins_v, prm->det_edge,
                                 prm->det_min_score, (float *)(dv + o_c), dv + o_cm, ints + 9, nb);
         if (rc) return rc;
-        KltPost post{};
-        post.thres_err = prm->thres_error; post.mask = dv + o_cm; post.skip_masked = 1;
-        post.mode = 3;
-        rc = vo_klt_launch(ctx, 1, &slot_1, &slot_0, (const float *)(dv + o_c), nb, prm->window_size, prm->max_level, 0,
-                           (float *)(dv + o_c0), dv + o_cs, (float *)(dv + o_ce), nullptr, &post);
-        if (rc) return rc;
-        VO_CUDA(cudaMemcpyAsync(dv + o_cb, dv + o_c, NB * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        post.mode = 4; post.border = 3; post.thres_bi2 = prm->thres_bidirection * prm->thres_bidirection;
-        post.ref_pts = (const float *)(dv + o_c); post.fwd_pts = (const float *)(dv + o_c0); post.fwd_status = dv + o_cs;
-        post.fwd_err = (const float *)(dv + o_ce);
-        const int back_lvl = prm->max_level - 1 < 0 ? 0 : prm->max_level - 1;
-        rc = vo_klt_launch(ctx, 1, &slot_0, &slot_1, (const float *)(dv + o_c0), nb, prm->window_size, back_lvl, VO_KLT_USE_INITIAL_FLOW,
-                           (float *)(dv + o_cb), dv + o_csb, (float *)(dv + o_ceb), nullptr, &post);
+        rc = vo_bidir_chain_launch_d(ctx, slot_1, slot_0, (const float *)(dv + o_c), (float *)(dv + o_c0), (float *)(dv + o_cb), dv + o_cs,
+                                     dv + o_csb, (float *)(dv + o_ce), (float *)(dv + o_ceb), dv + o_cm, 1, nb, prm->window_size,
+                                     prm->max_level, prm->thres_error, prm->thres_bidirection, 0, nullptr, nullptr);
         if (rc) return rc;
         k_mono_new<<<1, 1024, 0, ctx->stream>>>((const float2 *)(dv + o_c), (const float2 *)(dv + o_c0), dv + o_cm, ints + 9,
                                                 (float2 *)(dv + o_n1), (float2 *)(dv + o_n0), ints + 10);

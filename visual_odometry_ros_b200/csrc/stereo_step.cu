@@ -338,24 +338,31 @@ extern "C" int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *f
         const bool want_counts = res->counts != nullptr;
         k_step_prior<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(d);
         ctx->launches++;
-        // [4] l0 -> l1
-        KltPost post{};
-        post.mode = 2; post.thres_err = prm->thres_error; post.mask = d.mask; post.skip_masked = 1;
-        rc = vo_klt_launch(ctx, 1, &slot_l0, &slot_l1, (const float *)d.pts_l0, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
-                           (float *)d.pts_l1, nullptr, nullptr, nullptr, &post);
-        if (rc) return rc;
-        if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 0); ctx->launches++; }
-        // [4-1] scale refinement
-        if (prm->do_scale_refine) {
-            rc = vo_klt_scale_launch_d(ctx, slot_l0, slot_l1, (const float *)d.pts_l0, d.scale, n, (float *)d.pts_l1, d.mask, nan_flag);
+        if (!want_counts) {
+            // [4], [4-1], [5] as ONE launch: each feature runs its three dependent stages back to back on its warp
+            rc = vo_track_chain_launch_d(ctx, slot_l0, slot_l1, slot_r1, (const float *)d.pts_l0, (float *)d.pts_l1, (float *)d.pts_r1, d.scale,
+                                         d.mask, nan_flag, n, prm->window_size, prm->max_level, prm->thres_error, prm->do_scale_refine);
             if (rc) return rc;
+        } else {
+            // [4] l0 -> l1
+            KltPost post{};
+            post.mode = 2; post.thres_err = prm->thres_error; post.mask = d.mask; post.skip_masked = 1;
+            rc = vo_klt_launch(ctx, 1, &slot_l0, &slot_l1, (const float *)d.pts_l0, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
+                               (float *)d.pts_l1, nullptr, nullptr, nullptr, &post);
+            if (rc) return rc;
+            if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 0); ctx->launches++; }
+            // [4-1] scale refinement
+            if (prm->do_scale_refine) {
+                rc = vo_klt_scale_launch_d(ctx, slot_l0, slot_l1, (const float *)d.pts_l0, d.scale, n, (float *)d.pts_l1, d.mask, nan_flag);
+                if (rc) return rc;
+            }
+            if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 1); ctx->launches++; }
+            // [5] l1 -> r1
+            rc = vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, (const float *)d.pts_l1, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
+                               (float *)d.pts_r1, nullptr, nullptr, nullptr, &post);
+            if (rc) return rc;
+            if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 2); ctx->launches++; }
         }
-        if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 1); ctx->launches++; }
-        // [5] l1 -> r1
-        rc = vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, (const float *)d.pts_l1, n, prm->window_size, prm->max_level, VO_KLT_USE_INITIAL_FLOW,
-                           (float *)d.pts_r1, nullptr, nullptr, nullptr, &post);
-        if (rc) return rc;
-        if (want_counts) { k_step_count<<<1, 1024, 0, ctx->stream>>>(d.mask, n, d.counts + 2); ctx->launches++; }
         // [6] pose-only GN on the triangulated survivors
         k_step_select<<<1, 1024, 0, ctx->stream>>>(d);
         ctx->launches++;
@@ -370,19 +377,11 @@ extern "C" int vo_stereo_frame_step(vo_ctx *ctx, const vo_stereo_frame_params *f
         rc = vo_detect_launch_d(ctx, slot_l1, (const float *)d.out_l1, n > 0 ? d.n_out : nullptr, n, fp->n_bins_u, fp->n_bins_v, fp->det_edge,
                                 fp->det_min_score, (float *)(dv + o_c), dv + o_cm, ints + 9, nb);
         if (rc) return rc;
-        KltPost post{};
-        post.thres_err = prm->thres_error; post.mask = dv + o_cm; post.skip_masked = 1;
-        post.mode = 3;                               // trackBidirection forward pass (feature_tracker.cpp:57-60)
-        rc = vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, (const float *)(dv + o_c), nb, prm->window_size, prm->max_level, 0,
-                           (float *)(dv + o_cr), dv + o_cs, (float *)(dv + o_ce), nullptr, &post);
-        if (rc) return rc;
-        VO_CUDA(cudaMemcpyAsync(dv + o_cb, dv + o_c, NB * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        post.mode = 4; post.border = 3; post.thres_bi2 = fp->thres_bidirection * fp->thres_bidirection;
-        post.ref_pts = (const float *)(dv + o_c); post.fwd_pts = (const float *)(dv + o_cr); post.fwd_status = dv + o_cs;
-        post.fwd_err = (const float *)(dv + o_ce);
-        const int back_lvl = prm->max_level - 1 < 0 ? 0 : prm->max_level - 1;      // :69 backward pass at maxLevel-1
-        rc = vo_klt_launch(ctx, 1, &slot_r1, &slot_l1, (const float *)(dv + o_cr), nb, prm->window_size, back_lvl, VO_KLT_USE_INITIAL_FLOW,
-                           (float *)(dv + o_cb), dv + o_csb, (float *)(dv + o_ceb), nullptr, &post);
+        // trackBidirection(l1 -> r1) of the detected points (feature_tracker.cpp:39-86): forward + backward pass of a
+        // feature back to back on its warp, validity test fused in the backward epilogue
+        rc = vo_bidir_chain_launch_d(ctx, slot_l1, slot_r1, (const float *)(dv + o_c), (float *)(dv + o_cr), (float *)(dv + o_cb), dv + o_cs,
+                                     dv + o_csb, (float *)(dv + o_ce), (float *)(dv + o_ceb), dv + o_cm, 1, nb, prm->window_size,
+                                     prm->max_level, prm->thres_error, fp->thres_bidirection, 0, nullptr, nullptr);
         if (rc) return rc;
         NewDev nd;
         nd.pl = (const float2 *)(dv + o_c); nd.pr = (const float2 *)(dv + o_cr); nd.mask = dv + o_cm; nd.n_in = ints + 9;

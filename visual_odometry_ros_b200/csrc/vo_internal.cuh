@@ -130,4 +130,12 @@ int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single
                      const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
                      int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d);
 
+int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, const float *pts_l0_d, float *pts_l1_d, float *pts_r1_d,
+                            const float *scale_d, uint8_t *mask_d, int *nan_flag_d, int n, int win, int max_level, float thres_err,
+                            int do_scale);
+
+int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, float *pts1_d, float *back_d, uint8_t *st_d, uint8_t *stb_d,
+                            float *err_d, float *errb_d, uint8_t *mask_d, int skip_masked, int n, int win, int max_level, float thres_err,
+                            float thres_bi, int with_prior, const float *scale_d, int *nan_flag_d);
+
 static inline int vo_div_up(int a, int b) { return (a + b - 1) / b; }
