@@ -261,8 +261,8 @@ VO_API int vo_stereo_reconstruct(vo_ctx *ctx, const float *pts_l, const float *p
  * compaction; then bucketed detection on I1 with the survivors as occupancy and trackBidirection(I1 -> I0) of the new
  * points (:981-992).  flags[i]: bit 0 = Landmark::isTriangulated(), bit 1 = Landmark::isBundled().
  * The reference's fallback to cv::findEssentialMat when fewer than 11 landmarks are selected or the GN fails
- * (:909-949) is third-party RANSAC outside this build: the call then returns VO_ERR_MODE (new features are still
- * returned) and leaves the pose outputs untouched. */
+ * (:909-949) runs vo_pose_5point's device stage on the K7 survivors and scales the unit translation to the length of
+ * the previous motion; with thres_5p <= 0 the fallback is disabled and the call returns VO_ERR_MODE instead. */
 typedef struct vo_mono_frame_params {
     int window_size, max_level;      /* feature_tracker.window_size / max_level */
     float thres_error, thres_bidirection, thres_sampson;
@@ -272,6 +272,11 @@ typedef struct vo_mono_frame_params {
     int do_scale_refine;
     int n_bins_u, n_bins_v, det_edge;
     long long det_min_score;
+    float thres_5p;                  /* motion_estimator.thres_5p_error; <= 0 disables the five-point fallback (VO_ERR_MODE) */
+    int n_hypotheses;                /* five-point RANSAC hypotheses, 0 = 1024 */
+    unsigned seed;                   /* five-point sampling seed */
+    int init_mode;                   /* 1: the second image of a sequence (mono_vo.cpp:562-659): K1 track + five-point, |t10| = 1;
+                                        Xw / flags / dT01_prior are not read */
 } vo_mono_frame_params;
 typedef struct vo_mono_frame_result {
     float *T_wc, *dT01, *dT10;       /* [16] row-major each */
@@ -281,10 +286,28 @@ typedef struct vo_mono_frame_result {
     int *counts;                     /* [5] nullable: after K4, after K7, GN points, after the motion gate, final */
     int n_detected, n_new;
     float *new_p1, *new_p0;          /* [n_bins_u * n_bins_v][2]: new points in I1 and their back-tracked position in I0 */
+    int used_5point;                 /* out: the pose came from calcPose5PointsAlgorithm (init, or the fallback of :909-949) */
+    int n_5p_ransac;                 /* out: RANSAC inliers of that model */
 } vo_mono_frame_result;
 VO_API int vo_mono_frame_step(vo_ctx *ctx, const vo_mono_frame_params *prm, int slot_0, int slot_1, const uint8_t *img_1,
                        int w, int h, size_t step, int n, const float *pts0, const float *Xw, const uint8_t *flags,
                        const float *T_wc_prev, const float *dT01_prior, vo_mono_frame_result *res);
+
+/* ------------------------------------------------------------------ five-point relative pose
+ * MotionEstimator::calcPose5PointsAlgorithm (core/visual_odometry/motion_estimator.cpp:21-123): essential matrix by
+ * five-point RANSAC (the reference calls cv::findEssentialMat(pts0, pts1, K, RANSAC, 0.999, thres_5p), :41), its SVD
+ * decomposition into four (R10, t10) candidates (:70-96) and findCorrectRT (:205-263): the candidate with most
+ * DLT-triangulated points in front of both cameras.  All n_hypotheses (0 = 1024) minimal samples are solved and scored
+ * in parallel; sampling is a counter-based hash of (seed, hypothesis), so a call is reproducible.
+ * R10[9] row-major, t10[3] (unit norm), X0 [n][3] nullable (points of the chosen candidate in camera 0),
+ * mask[n] = RANSAC inlier AND cheirality (:115), E[9] nullable (row-major, Frobenius norm 1),
+ * info[3] nullable = {RANSAC inliers, cheirality inliers, ok}.  VO_ERR_MODE when no model was found
+ * ("calcPose5PointsAlgorithm() is failed.", mono_vo.cpp:590). */
+VO_API int vo_pose_5point(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *K4, float thres_px,
+                   int n_hypotheses, unsigned seed, float *R10, float *t10, float *X0, uint8_t *mask, float *E, int *info);
+/* The minimal solver alone (Nister): q [n_sets][5][4] = normalised (x0, y0, x1, y1) with x1^T E x0 = 0;
+ * E [n_sets][10][9] row-major unit-norm candidates, n_solutions [n_sets]. */
+VO_API int vo_five_point_minimal(vo_ctx *ctx, const double *q, int n_sets, double *E, int *n_solutions);
 
 /* ------------------------------------------------------------------ triangulation
  * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */

@@ -5,12 +5,14 @@ Composes the per-stage oracles in the order of the steady-state branch of MonoVO
 (:739-761), trackBidirectionWithPrior (cv2, :768), trackWithScale (C restatement, :783), landmark selection for the
 pose-only BA (:799-827), mono poseOnlyBundleAdjustment (C restatement, :864), Sampson gate
 (motion_estimator.cpp:539-568, mono_vo.cpp:957-962), bucketed extraction of new features on the current image and their
-back-tracking into the previous one with trackBidirection (:985-992).  The 5-point fallback (:909-949,
-cv::findEssentialMat) is third-party RANSAC and outside this path: the oracle raises instead.
+back-tracking into the previous one with trackBidirection (:985-992).  The 5-point fallback (:909-949) and the
+initialisation step of the second image (:562-659) take ``five_point`` = a callable (pts0, pts1) -> (ok, R10, t10, mask):
+by default the reference's own library call (oracle/five_point.py: cv2.findEssentialMat + restated decomposition).
 """
 import numpy as np
 
 from . import detect as odet
+from . import five_point as ofp
 from . import klt as oklt
 from . import pose as opose
 from . import step as ostep
@@ -71,7 +73,7 @@ def sampson(pts0, pts1, F):
 
 def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_prior, K4, win, max_level, thres_err, thres_bi,
                     thres_sampson, thres_poseba, use_bundled_only, n_bins_u=0, n_bins_v=0, det_edge=31, det_min_score=0,
-                    do_scale_refine=True, lk=oklt.lk_cv2):
+                    do_scale_refine=True, lk=oklt.lk_cv2, five_point=None, thres_5p=0.0):
     h, w = I0.shape
     pts0 = np.asarray(pts0, f32).reshape(-1, 2)
     Xw = np.asarray(Xw, f32).reshape(-1, 3)
@@ -107,16 +109,33 @@ def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_pri
     flag = bun[idx] if use_bundled_only else tri[idx]
     sel = flag & (Xp[idx, 2].astype(np.float64) > 0.1)
     counts.append(int(sel.sum()))
-    if sel.sum() <= 10:
-        raise RuntimeError("insufficient points: 5-point fallback required")
-    ok, R01, t01, mask_ba, iters = opose.pose_gn_mono(Xp[idx[sel]], p1c[sel], K4, int(thres_poseba), dT01_prior[:3, :3], dT01_prior[:3, 3])
-    if not ok:
-        raise RuntimeError("pose-only BA failed: 5-point fallback required")
+    ok, iters = False, 0
+    if sel.sum() > 10:
+        ok, R01, t01, mask_ba, iters = opose.pose_gn_mono(Xp[idx[sel]], p1c[sel], K4, int(thres_poseba), dT01_prior[:3, :3], dT01_prior[:3, 3])
     mask_motion = np.ones(len(idx), bool)
-    mask_motion[np.flatnonzero(sel)] = mask_ba
-    dT01 = np.eye(4, dtype=f32)
-    dT01[:3, :3], dT01[:3, 3] = R01, t01
-    dT10 = opose.inverse_se3_f(dT01)
+    used_5point = False
+    if ok:
+        mask_motion[np.flatnonzero(sel)] = mask_ba
+        dT01 = np.eye(4, dtype=f32)
+        dT01[:3, :3], dT01[:3, 3] = R01, t01
+        dT10 = opose.inverse_se3_f(dT01)
+    else:
+        # :909-949: five-point on all K7 survivors, translation scaled to the previous motion's length
+        if five_point is None and not thres_5p > 0:
+            raise RuntimeError("insufficient points / pose-only BA failed: 5-point fallback required")
+        fp = five_point or (lambda a, b: _five_point_cv(a, b, K4, thres_5p))
+        ok5, R10, t10, m5 = fp(p0c, p1c)
+        if not ok5:
+            raise RuntimeError("'calcPose5PointsAlgorithm()' is failed. Terminate the algorithm.")
+        t10 = np.asarray(t10, f32)
+        scale5 = f32(np.sqrt(f32(f32(f32(dT01_prior[0, 3] * dT01_prior[0, 3]) + f32(dT01_prior[1, 3] * dT01_prior[1, 3])) + f32(dT01_prior[2, 3] * dT01_prior[2, 3]))))
+        nrm = f32(np.sqrt(f32(f32(f32(t10[0] * t10[0]) + f32(t10[1] * t10[1])) + f32(t10[2] * t10[2]))))
+        dT10 = np.eye(4, dtype=f32)
+        dT10[:3, :3] = np.asarray(R10, f32)
+        dT10[:3, 3] = (f32(scale5 / nrm) * t10).astype(f32)
+        dT01 = opose.inverse_se3_f(dT10)
+        mask_motion = np.asarray(m5, bool)
+        used_5point = True
     T_wc = ostep.mul4_f32(Twc_prev, dT01)
     idx, p0c, p1c = idx[mask_motion], p0c[mask_motion], p1c[mask_motion]
     counts.append(len(idx))
@@ -127,8 +146,54 @@ def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_pri
         keep = d < f32(thres_sampson)
     idx, p0c, p1c = idx[keep], p0c[keep], p1c[keep]
     counts.append(len(idx))
-    out = dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx.astype(np.int32), pts1=p1c, counts=counts, gn_iters=iters, F10=F)
+    out = dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx.astype(np.int32), pts1=p1c, counts=counts, gn_iters=iters, F10=F, used_5point=used_5point)
     # new features (:981-992): extraction on I1 with the survivors as occupancy, back-tracking I1 -> I0
+    if n_bins_u * n_bins_v > 0:
+        pts_new = odet.detect_bucketed(I1, p1c, n_bins_u, n_bins_v, det_edge, det_min_score)
+        if len(pts_new):
+            p0_new, m = oklt.track_bidirection(lk, I1, I0, pts_new, win, max_level, thres_err, thres_bi)
+            out.update(new_p1=pts_new[m], new_p0=p0_new[m])
+        else:
+            out.update(new_p1=np.zeros((0, 2), f32), new_p0=np.zeros((0, 2), f32))
+        out["n_detected"] = len(pts_new)
+    return out
+
+
+def _five_point_cv(p0, p1, K4, thres_5p):
+    ok, R, t, X0, m, E = ofp.calc_pose_5point(p0, p1, K4, thres_5p)
+    return ok, R, t, m
+
+
+def mono_init_step(I0, I1, pts0, T_wc_prev, K4, win, max_level, thres_err, thres_bi, thres_sampson, thres_5p, n_bins_u=0, n_bins_v=0,
+                   det_edge=31, det_min_score=0, lk=oklt.lk_cv2, five_point=None):
+    """The second image of a sequence (mono_vo.cpp:562-659): track (:573), calcPose5PointsAlgorithm (:589), Sampson gate
+    (:594-597), |t10| = 1 (:606-609), pose (:611), new features back-tracked with trackBidirection (:623-636)."""
+    pts0 = np.asarray(pts0, f32).reshape(-1, 2)
+    K4 = np.asarray(K4, f32)
+    Twc_prev = np.asarray(T_wc_prev, f32)
+    idx = np.arange(len(pts0))
+    p1, m = oklt.track(lk, I0, I1, pts0, win, max_level, thres_err)
+    idx, p0c, p1c = idx[m], pts0[m], p1[m]
+    counts = [len(idx)]
+    fp = five_point or (lambda a, b: _five_point_cv(a, b, K4, thres_5p))
+    ok5, R10, t10, m5 = fp(p0c, p1c)
+    if not ok5:
+        raise RuntimeError("calcPose5PointsAlgorithm() is failed.")
+    t10 = np.asarray(t10, f32)
+    nrm = f32(np.sqrt(f32(f32(f32(t10[0] * t10[0]) + f32(t10[1] * t10[1])) + f32(t10[2] * t10[2]))))
+    dT10 = np.eye(4, dtype=f32)
+    dT10[:3, :3] = np.asarray(R10, f32)
+    dT10[:3, 3] = ((t10 / nrm).astype(f32) * f32(1.0)).astype(f32)
+    dT01 = opose.inverse_se3_f(dT10)
+    T_wc = ostep.mul4_f32(Twc_prev, dT01)
+    F = fundamental(K4, dT10[:3, :3], dT10[:3, 3])
+    d = sampson(p0c, p1c, F)
+    with np.errstate(invalid="ignore"):
+        keep = np.asarray(m5, bool) & (d < f32(thres_sampson))
+    counts.append(int(np.asarray(m5, bool).sum()))
+    idx, p0c, p1c = idx[keep], p0c[keep], p1c[keep]
+    counts.append(len(idx))
+    out = dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx.astype(np.int32), pts1=p1c, counts=counts, F10=F, used_5point=True)
     if n_bins_u * n_bins_v > 0:
         pts_new = odet.detect_bucketed(I1, p1c, n_bins_u, n_bins_v, det_edge, det_min_score)
         if len(pts_new):

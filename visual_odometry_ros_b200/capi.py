@@ -65,12 +65,14 @@ class MonoFrameParams(ctypes.Structure):
     _fields_ = [("window_size", ctypes.c_int), ("max_level", ctypes.c_int), ("thres_error", ctypes.c_float),
                 ("thres_bidirection", ctypes.c_float), ("thres_sampson", ctypes.c_float), ("thres_poseba_error", ctypes.c_float),
                 ("K", ctypes.c_float * 4), ("use_bundled_only", ctypes.c_int), ("do_scale_refine", ctypes.c_int),
-                ("n_bins_u", ctypes.c_int), ("n_bins_v", ctypes.c_int), ("det_edge", ctypes.c_int), ("det_min_score", ctypes.c_longlong)]
+                ("n_bins_u", ctypes.c_int), ("n_bins_v", ctypes.c_int), ("det_edge", ctypes.c_int), ("det_min_score", ctypes.c_longlong),
+                ("thres_5p", ctypes.c_float), ("n_hypotheses", ctypes.c_int), ("seed", ctypes.c_uint), ("init_mode", ctypes.c_int)]
 
 
 class MonoFrameResult(ctypes.Structure):
     _fields_ = [("T_wc", vp), ("dT01", vp), ("dT10", vp), ("n_tracked", ctypes.c_int), ("index", vp), ("pts1", vp), ("counts", vp),
-                ("n_detected", ctypes.c_int), ("n_new", ctypes.c_int), ("new_p1", vp), ("new_p0", vp)]
+                ("n_detected", ctypes.c_int), ("n_new", ctypes.c_int), ("new_p1", vp), ("new_p0", vp),
+                ("used_5point", ctypes.c_int), ("n_5p_ransac", ctypes.c_int)]
 
 
 class LbaProblem(ctypes.Structure):
@@ -145,6 +147,8 @@ def lib():
     L.vo_rectify_init.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
     L.vo_read_rectify_maps.argtypes = [vp, ctypes.c_int, vp, vp]
     L.vo_upload_image_rectified.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+    L.vo_pose_5point.argtypes = [vp, vp, vp, ctypes.c_int, vp, f32, ctypes.c_int, ctypes.c_uint, vp, vp, vp, vp, vp, vp]
+    L.vo_five_point_minimal.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     L.vo_stereo_reconstruct.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
@@ -354,6 +358,28 @@ class Context:
                                                 _ptr(X0), _ptr(X1)))
         return X0, X1
 
+    def pose_5point(self, pts0, pts1, K4, thres_5p, n_hypotheses=0, seed=0):
+        """MotionEstimator::calcPose5PointsAlgorithm -> dict(R10, t10, X0, mask, E, n_ransac, n_cheirality)."""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        n = len(p0)
+        if len(p1) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "calcPose5PointsAlgorithm(): pts0.size() != pts1.size()")   # motion_estimator.cpp:26
+        K = np.ascontiguousarray(K4, np.float32)
+        R, t, E = np.zeros((3, 3), np.float32), np.zeros(3, np.float32), np.zeros((3, 3), np.float32)
+        X0, mask, info = np.zeros((max(n, 1), 3), np.float32), np.zeros(max(n, 1), np.uint8), np.zeros(3, np.int32)
+        check(self.h, self.L.vo_pose_5point(self.h, _ptr(p0), _ptr(p1), n, _ptr(K), float(thres_5p), int(n_hypotheses), int(seed),
+                                            _ptr(R), _ptr(t), _ptr(X0), _ptr(mask), _ptr(E), _ptr(info)))
+        return dict(R10=R, t10=t, X0=X0[:n], mask=mask[:n].astype(bool), E=E, n_ransac=int(info[0]), n_cheirality=int(info[1]))
+
+    def five_point_minimal(self, q):
+        """Minimal solver alone: q (S, 5, 4) normalised (x0, y0, x1, y1) -> list of (k_s, 3, 3) solution arrays."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, 5, 4)
+        S = len(q)
+        E, ns = np.zeros((S, 10, 3, 3)), np.zeros(S, np.int32)
+        check(self.h, self.L.vo_five_point_minimal(self.h, _ptr(q), S, _ptr(E), _ptr(ns)))
+        return [E[s, :ns[s]] for s in range(S)]
+
     def depth_filter_normal(self, x_prev, cov_prev, x_curr, cov_curr):
         a = [np.ascontiguousarray(v, np.float64) for v in (x_prev, cov_prev, x_curr, cov_curr)]
         n = len(a[0])
@@ -543,20 +569,25 @@ class Context:
 
     def mono_frame_step(self, slot_0, slot_1, img_1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_prior, K, win, max_level,
                         thres_err, thres_bi, thres_sampson, thres_poseba, use_bundled_only, n_bins_u=0, n_bins_v=0, det_edge=31,
-                        det_min_score=0, do_scale_refine=True, want_counts=True):
-        """Steady-state branch of MonoVO::trackImage (mono_vo.cpp:724-992), one synchronisation."""
+                        det_min_score=0, do_scale_refine=True, want_counts=True, thres_5p=0.0, n_hypotheses=0, seed=0, init_mode=False):
+        """Steady-state branch of MonoVO::trackImage (mono_vo.cpp:724-992), one synchronisation; init_mode: the second
+        image of a sequence (:562-659; Xw / flags / dT01_prior may be None)."""
         prm = MonoFrameParams()
+        prm.thres_5p, prm.n_hypotheses, prm.seed, prm.init_mode = float(thres_5p), int(n_hypotheses), int(seed), int(bool(init_mode))
         prm.window_size, prm.max_level, prm.thres_error = int(win), int(max_level), float(thres_err)
         prm.thres_bidirection, prm.thres_sampson, prm.thres_poseba_error = float(thres_bi), float(thres_sampson), float(thres_poseba)
         prm.K = (ctypes.c_float * 4)(*[float(v) for v in K])
         prm.use_bundled_only, prm.do_scale_refine = int(bool(use_bundled_only)), int(bool(do_scale_refine))
         prm.n_bins_u, prm.n_bins_v, prm.det_edge, prm.det_min_score = int(n_bins_u), int(n_bins_v), int(det_edge), int(det_min_score)
         p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
-        X = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3)
-        fl = (np.asarray(triangulated).astype(np.uint8) | (np.asarray(bundled).astype(np.uint8) << 1)).astype(np.uint8)
         n = len(p0)
+        if init_mode:
+            X, fl, dTp = np.zeros((max(n, 1), 3), np.float32), np.zeros(max(n, 1), np.uint8), np.eye(4, dtype=np.float32)
+        else:
+            X = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3)
+            fl = (np.asarray(triangulated).astype(np.uint8) | (np.asarray(bundled).astype(np.uint8) << 1)).astype(np.uint8)
+            dTp = np.ascontiguousarray(dT01_prior, np.float32)
         Twp = np.ascontiguousarray(T_wc_prev, np.float32)
-        dTp = np.ascontiguousarray(dT01_prior, np.float32)
         T_wc, dT01, dT10 = (np.zeros((4, 4), np.float32) for _ in range(3))
         idx = np.zeros(max(n, 1), np.int32)
         o1 = np.zeros((max(n, 1), 2), np.float32)
@@ -573,7 +604,8 @@ class Context:
                                                 _ptr(fl), _ptr(Twp), _ptr(dTp), ctypes.byref(res)))
         k, m = res.n_tracked, res.n_new
         return dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx[:k].copy(), pts1=o1[:k].copy(), counts=[int(c) for c in counts],
-                    n_detected=res.n_detected, new_p1=n1[:m].copy(), new_p0=n0[:m].copy())
+                    n_detected=res.n_detected, new_p1=n1[:m].copy(), new_p0=n0[:m].copy(), used_5point=bool(res.used_5point),
+                    n_5p_ransac=int(res.n_5p_ransac))
 
     # ---------------------------------------------------------------- stereo rectification (camera.cpp:300-546)
     def rectify_init(self, K_l, D_l, K_r, D_r, T_lr, w, h):

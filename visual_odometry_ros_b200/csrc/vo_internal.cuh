@@ -76,6 +76,9 @@ struct vo_ctx {
     void *d_rect = nullptr;
     size_t rect_bytes = 0;
     int rect_w = 0, rect_h = 0;
+    // five-point RANSAC scratch (normalised points, hypotheses)
+    void *d_fp = nullptr;
+    size_t fp_bytes = 0;
     // LBA scratch
     void *d_lba = nullptr;
     size_t lba_bytes = 0;
@@ -137,5 +140,9 @@ int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, 
 int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, float *pts1_d, float *back_d, uint8_t *st_d, uint8_t *stb_d,
                             float *err_d, float *errb_d, uint8_t *mask_d, int skip_masked, int n, int win, int max_level, float thres_err,
                             float thres_bi, int with_prior, const float *scale_d, int *nan_flag_d);
+
+// five_point.cu
+int vo_5pt_launch_d(vo_ctx *ctx, const float *pts0_d, const float *pts1_d, int n, const int *n_d, const float *K, float thres_px,
+                    int n_hyp, unsigned seed, float *R10_d, float *t10_d, float *X0_d, uint8_t *mask_d, float *E_d, int *info_d);
 
 static inline int vo_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -126,6 +126,25 @@ def pose_scene(seed=1001, n=500, noise_px=0.3, outlier_frac=0.10,
                 T01_true=T01, outlier_idx=np.sort(idx))
 
 
+def two_view_scene(seed=6006, n=1500, noise_px=0.3, outlier_frac=0.25, rotvec=(0.004, -0.02, 0.003), t=(0.05, -0.02, 0.9)):
+    """Mono initialisation case (mono_vo.cpp:562-696): n correspondences of a pinhole scene between two views of the
+    KITTI camera, pixel noise and gross outliers.  Returns pts0, pts1, R10, t10 (unit norm; X1 = R10 X0 + t10), K4."""
+    rng = np.random.default_rng(seed)
+    X0 = np.stack([rng.uniform(-12, 12, n), rng.uniform(-3, 2, n), rng.uniform(4, 50, n)], 1)
+    R01 = so3_exp(rotvec)
+    t01 = np.asarray(t, np.float64)
+    R10 = R01.T
+    t10 = -R01.T @ t01
+    X1 = X0 @ R10.T + t10
+    p0 = np.stack([FX * X0[:, 0] / X0[:, 2] + CX, FY * X0[:, 1] / X0[:, 2] + CY], 1) + rng.normal(0, noise_px, (n, 2))
+    p1 = np.stack([FX * X1[:, 0] / X1[:, 2] + CX, FY * X1[:, 1] / X1[:, 2] + CY], 1) + rng.normal(0, noise_px, (n, 2))
+    n_out = int(round(outlier_frac * n))
+    idx = rng.choice(n, n_out, replace=False)
+    p1[idx] += rng.choice([-1.0, 1.0], (n_out, 2)) * rng.uniform(4, 40, (n_out, 2))
+    return dict(pts0=p0.astype(np.float32), pts1=p1.astype(np.float32), R10=R10, t10=t10 / np.linalg.norm(t10),
+                K4=np.array([FX, FY, CX, CY], np.float32), outlier_idx=np.sort(idx), X0=X0)
+
+
 # ------------------------------------------------------------------ local BA problem (config 4)
 def lba_problem(seed=4004, n_kf=10, n_points=5000, n_fix=2, noise_px=0.3, point_sigma=0.05,
                 rot_sigma_deg=0.5, trans_sigma=0.05, pose_scale=10.0, stereo=True, outlier_frac=0.02):
