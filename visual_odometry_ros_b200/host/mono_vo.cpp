@@ -1,0 +1,573 @@
+// mono_vo.cpp -- host glue of MonoVO::trackImage (core/visual_odometry/mono_vo/mono_vo.cpp:496-1194) over flat arrays;
+// every numeric stage is a C-ABI call into libvo_b200.so (see mono_vo.h).
+#include "mono_vo.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+#include "vo_host_util.h"
+using namespace vo_host;
+
+// ------------------------------------------------------------------------------ construction
+MonoVO::MonoVO(const Parameters &prm) : p_(prm) { init(); }
+
+// mono_vo.cpp:140-235: "%YAML:1.0" key: value pairs
+MonoVO::MonoVO(std::string mode, std::string directory_intrinsic)
+{
+    if (mode == "dataset") throw std::runtime_error("dataset mode is not supported.");     // mono_vo.cpp:21
+    if (mode != "rosbag") throw std::runtime_error("MonoVO - unknown mode.");              // :31
+    std::ifstream f(directory_intrinsic);
+    if (!f.is_open()) throw std::runtime_error("intrinsic file cannot be found!\n");
+    std::map<std::string, std::string> kv;
+    std::string line;
+    while (std::getline(f, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        const size_t c = line.find(':');
+        if (c == std::string::npos) continue;
+        std::string key = line.substr(0, c), val = line.substr(c + 1);
+        key.erase(0, key.find_first_not_of(" \t")); key.erase(key.find_last_not_of(" \t") + 1);
+        val.erase(0, val.find_first_not_of(" \t")); if (!val.empty()) val.erase(val.find_last_not_of(" \t\r") + 1);
+        kv[key] = val;
+    }
+    auto num = [&](const char *k, double dflt) { auto it = kv.find(k); return it == kv.end() || it->second.empty() ? dflt : atof(it->second.c_str()); };
+    p_.width = (int)num("Camera.width", p_.width); p_.height = (int)num("Camera.height", p_.height);
+    const char *names[4] = {"fx", "fy", "cx", "cy"};
+    for (int i = 0; i < 4; ++i) p_.K[i] = (float)num((std::string("Camera.") + names[i]).c_str(), p_.K[i]);
+    if (num("flagDoUndistortion", 0) != 0)
+        throw std::runtime_error("vo_b200: MonoVO with flagDoUndistortion = 1 is not built (single-camera undistortion maps, camera.cpp:57-87)");
+    p_.thres_error = (float)num("feature_tracker.thres_error", p_.thres_error);
+    p_.thres_bidirection = (float)num("feature_tracker.thres_bidirection", p_.thres_bidirection);
+    p_.thres_sampson = (float)num("feature_tracker.thres_sampson", p_.thres_sampson);
+    p_.window_size = (int)num("feature_tracker.window_size", p_.window_size);
+    p_.max_level = (int)num("feature_tracker.max_level", p_.max_level);
+    p_.thres_parallax_deg = (float)num("map_update.thres_parallax", p_.thres_parallax_deg);
+    p_.n_bins_u = (int)num("feature_extractor.n_bins_u", p_.n_bins_u);
+    p_.n_bins_v = (int)num("feature_extractor.n_bins_v", p_.n_bins_v);
+    p_.thres_5p_error = (float)num("motion_estimator.thres_5p_error", p_.thres_5p_error);
+    p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
+    p_.thres_overlap_ratio = (float)num("keyframe_update.thres_overlap_ratio", p_.thres_overlap_ratio);
+    p_.thres_translation = (float)num("keyframe_update.thres_translation", p_.thres_translation);
+    p_.thres_rotation_deg = (float)num("keyframe_update.thres_rotation", p_.thres_rotation_deg);
+    p_.n_max_keyframes_in_window = (int)num("keyframe_update.n_max_keyframes_in_window", p_.n_max_keyframes_in_window);
+    init();
+}
+
+void MonoVO::init()
+{
+    const int nb = std::max(1, p_.n_bins_u * p_.n_bins_v);
+    const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 2, std::max(4 * nb + 4096, 262144), nullptr, &ctx_);
+    if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
+}
+
+MonoVO::~MonoVO() { if (ctx_) vo_ctx_destroy(ctx_); }
+
+long long MonoVO::launchCount() const { return vo_ctx_launch_count(ctx_); }
+const std::vector<int> &MonoVO::currentLandmarkIds() const { static const std::vector<int> e; return prev_ ? prev_->lm_ids : e; }
+const std::vector<float> &MonoVO::currentPts() const { static const std::vector<float> e; return prev_ ? prev_->pts : e; }
+int MonoVO::framePose(int frame_id, float *T) const
+{
+    if (frame_id < 0 || frame_id >= (int)frames_.size() || !T) return VO_ERR_INVALID_ARG;
+    memcpy(T, frames_[frame_id]->Twc, 64);
+    return VO_OK;
+}
+
+// ------------------------------------------------------------------------------ bookkeeping
+void MonoVO::setPose(FrameRec &f, const float *Twc)
+{
+    memcpy(f.Twc, Twc, 64);
+    inv_se3_f(f.Twc, f.Tcw);
+}
+void MonoVO::setPoseDiff10(FrameRec &f, const float *dT10)
+{
+    memcpy(f.dT10, dT10, 64);
+    inv_se3_f(f.dT10, f.dT01);
+}
+
+// Landmark(p, frame) (landmark.cpp:28-52): first observation, age 1
+int MonoVO::newLandmarks(int k, const float *pts, const FrameRec &f)
+{
+    const int base = (int)lm_tri_.size();
+    const size_t n = (size_t)base + k;
+    lm_X_.resize(n * 3, 0.f);
+    lm_tri_.resize(n, 0); lm_alive_.resize(n, 1); lm_bundled_.resize(n, 0);
+    lm_last_frame_.resize(n, f.id); lm_first_frame_.resize(n, f.id); lm_age_.resize(n, 1);
+    lm_last_parallax_.resize(n, 0.f);
+    lm_first_px_.resize(n * 2); lm_last_px_.resize(n * 2);
+    memcpy(&lm_first_px_[(size_t)base * 2], pts, (size_t)k * 8);
+    memcpy(&lm_last_px_[(size_t)base * 2], pts, (size_t)k * 8);
+    lm_kf_obs_.resize(n);
+    return base;
+}
+
+// Landmark::addObservationAndRelatedFrame (landmark.cpp:76-135): parallax of the new observation against the FIRST one,
+// through the current poses of the two frames
+void MonoVO::addObservations(const int *ids, const float *pts, int k, const FrameRec &f)
+{
+    const float fxinv = 1.0f / p_.K[0], fyinv = 1.0f / p_.K[1], cx = p_.K[2], cy = p_.K[3];
+    int f0_cached = -1;
+    float T01[16];
+    for (int j = 0; j < k; ++j) {
+        const int id = ids[j];
+        ++lm_age_[id];
+        lm_last_frame_[id] = f.id;
+        lm_last_px_[2 * (size_t)id] = pts[2 * j]; lm_last_px_[2 * (size_t)id + 1] = pts[2 * j + 1];
+        const int f0 = lm_first_frame_[id];
+        if (f0 != f0_cached) { mul4_f(frames_[f0]->Tcw, f.Twc, T01); f0_cached = f0; }
+        const float x0[3] = {(lm_first_px_[2 * (size_t)id] - cx) * fxinv, (lm_first_px_[2 * (size_t)id + 1] - cy) * fyinv, 1.0f};
+        const float b[3] = {(pts[2 * j] - cx) * fxinv, (pts[2 * j + 1] - cy) * fyinv, 1.0f};
+        float x1[3];
+        for (int r = 0; r < 3; ++r) x1[r] = (T01[r * 4] * b[0] + T01[r * 4 + 1] * b[1]) + T01[r * 4 + 2] * b[2];
+        const float dot = (x0[0] * x1[0] + x0[1] * x1[1]) + x0[2] * x1[2];
+        const float n0 = std::sqrt((x0[0] * x0[0] + x0[1] * x0[1]) + x0[2] * x0[2]);
+        const float n1 = std::sqrt((x1[0] * x1[0] + x1[1] * x1[1]) + x1[2] * x1[2]);
+        float c = dot / (n0 * n1);
+        if (c >= 1.0f) c = 0.99999f;
+        if (c <= -1.0f) c = -0.99999f;
+        lm_last_parallax_[id] = acosf(c);
+    }
+}
+
+bool MonoVO::checkUpdateRule(const FrameRec &f) const
+{
+    if (window_.empty()) return true;
+    const FrameRec &kf = *window_.back();
+    int cnt_tracked = 0;
+    for (int id : kf.lm_ids) if (lm_last_frame_[id] == f.id) ++cnt_tracked;
+    const float ratio = (float)cnt_tracked / (float)kf.lm_ids.size();
+    if (ratio <= p_.thres_overlap_ratio) return true;
+    float dT[16];
+    mul4_f(kf.Tcw, f.Twc, dT);
+    float costheta = (dT[0] + dT[5] + dT[10] - 1.0f) * 0.5f;
+    if (costheta >= 0.999999f) costheta = 0.999999f;
+    if (costheta <= -0.999999f) costheta = -0.999999f;
+    const float rot = acosf(costheta);
+    const float dtrans = std::sqrt(dT[3] * dT[3] + dT[7] * dT[7] + dT[11] * dT[11]);
+    return rot >= p_.thres_rotation_deg * D2R || dtrans >= p_.thres_translation;
+}
+
+void MonoVO::addKeyframe(const FrameRecPtr &f)
+{
+    f->is_keyframe = true;
+    all_keyframes_.push_back(f);
+    if ((int)window_.size() == p_.n_max_keyframes_in_window) window_.pop_front();
+    window_.push_back(f);
+    for (int id : f->lm_ids) lm_kf_obs_[id].push_back({f->id, lm_last_px_[2 * (size_t)id], lm_last_px_[2 * (size_t)id + 1]});   // observations.back()
+}
+
+// triangulateDLT of the candidates, one device call per distinct frame of the first point (T10 = T1w * Tw0)
+int MonoVO::dltGroups(const std::vector<int> &cand, const std::vector<float> &pt0, const std::vector<float> &pt1,
+                      const std::vector<int> &f0, const FrameRec &f1, std::vector<float> &X0, std::vector<float> &X1)
+{
+    const size_t n = cand.size();
+    X0.assign(n * 3, 0.f); X1.assign(n * 3, 0.f);
+    std::vector<int> groups(f0);
+    std::sort(groups.begin(), groups.end());
+    groups.erase(std::unique(groups.begin(), groups.end()), groups.end());
+    std::vector<float> a, b, xa, xb;
+    std::vector<int> sel;
+    for (int g : groups) {
+        sel.clear(); a.clear(); b.clear();
+        for (size_t j = 0; j < n; ++j)
+            if (f0[j] == g) { sel.push_back((int)j); a.push_back(pt0[2 * j]); a.push_back(pt0[2 * j + 1]); b.push_back(pt1[2 * j]); b.push_back(pt1[2 * j + 1]); }
+        float T10[16], R10[9], t10[3];
+        mul4_f(f1.Tcw, frames_[g]->Twc, T10);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R10[r * 3 + c] = T10[r * 4 + c]; t10[r] = T10[r * 4 + 3]; }
+        xa.resize(sel.size() * 3); xb.resize(sel.size() * 3);
+        const int rc = vo_triangulate_dlt(ctx_, a.data(), b.data(), (int)sel.size(), R10, t10, p_.K, p_.K, xa.data(), xb.data());
+        if (rc) fail(ctx_, rc);
+        for (size_t q = 0; q < sel.size(); ++q) {
+            memcpy(&X0[(size_t)sel[q] * 3], &xa[q * 3], 12);
+            memcpy(&X1[(size_t)sel[q] * 3], &xb[q * 3], 12);
+        }
+    }
+    return (int)groups.size();
+}
+
+static inline void to_world(const float *Tw0, const float *X0, float *Xw)
+{
+    for (int r = 0; r < 3; ++r) Xw[r] = ((Tw0[r * 4] * X0[0] + Tw0[r * 4 + 1] * X0[1]) + Tw0[r * 4 + 2] * X0[2]) + Tw0[r * 4 + 3];
+}
+
+// mono_vo.cpp:660-687: first / last observation of every landmark of the frame with enough parallax; depth > 0 only
+int MonoVO::reconstructInitial(const FrameRec &f)
+{
+    const float thr = p_.thres_parallax_deg * D2R;
+    std::vector<int> cand, f0;
+    std::vector<float> pt0, pt1, X0, X1;
+    for (int id : f.lm_ids)
+        if (!lm_tri_[id] && lm_last_parallax_[id] >= thr) {
+            cand.push_back(id); f0.push_back(lm_first_frame_[id]);
+            pt0.push_back(lm_first_px_[2 * (size_t)id]); pt0.push_back(lm_first_px_[2 * (size_t)id + 1]);
+            pt1.push_back(lm_last_px_[2 * (size_t)id]); pt1.push_back(lm_last_px_[2 * (size_t)id + 1]);
+        }
+    if (cand.empty()) return 0;
+    dltGroups(cand, pt0, pt1, f0, f, X0, X1);
+    int n = 0;
+    for (size_t j = 0; j < cand.size(); ++j)
+        if (X0[3 * j + 2] > 0.f) {
+            to_world(frames_[f0[j]]->Twc, &X0[3 * j], &lm_X_[(size_t)cand[j] * 3]);
+            lm_tri_[cand[j]] = 1;
+            ++n;
+        }
+    return n;
+}
+
+// mono_vo.cpp:1032-1076: first / last KEYFRAME observation, more than two of them, 1-px^2 gates, both depths > 0
+int MonoVO::reconstructKeyframe(const FrameRec &f)
+{
+    const float thr = p_.thres_parallax_deg * D2R;
+    std::vector<int> cand, f0;
+    std::vector<float> pt0, pt1, X0, X1;
+    for (int id : f.lm_ids)
+        if (lm_alive_[id] && !lm_tri_[id] && lm_last_parallax_[id] >= thr && lm_kf_obs_[id].size() > 2) {
+            const KfObs &a = lm_kf_obs_[id].front(), &b = lm_kf_obs_[id].back();
+            cand.push_back(id); f0.push_back(a.kf_id);
+            pt0.push_back(a.x); pt0.push_back(a.y); pt1.push_back(b.x); pt1.push_back(b.y);
+        }
+    if (cand.empty()) return 0;
+    dltGroups(cand, pt0, pt1, f0, f, X0, X1);
+    int n = 0;
+    const float fx = p_.K[0], fy = p_.K[1], cx = p_.K[2], cy = p_.K[3];
+    for (size_t j = 0; j < cand.size(); ++j) {
+        const float *a = &X0[3 * j], *b = &X1[3 * j];
+        const float iz0 = 1.0f / a[2], iz1 = 1.0f / b[2];
+        const float d0x = pt0[2 * j] - (fx * a[0] * iz0 + cx), d0y = pt0[2 * j + 1] - (fy * a[1] * iz0 + cy);
+        if (d0x * d0x + d0y * d0y > 1.0) continue;
+        const float d1x = pt1[2 * j] - (fx * b[0] * iz1 + cx), d1y = pt1[2 * j + 1] - (fy * b[1] * iz1 + cy);
+        if (d1x * d1x + d1y * d1y > 1.0) continue;
+        if (a[2] > 0.f && b[2] > 0.f) {
+            to_world(frames_[f0[j]]->Twc, a, &lm_X_[(size_t)cand[j] * 3]);
+            lm_tri_[cand[j]] = 1;
+            ++n;
+        }
+    }
+    return n;
+}
+
+void MonoVO::localBundleAdjustment()
+{
+    const int NUM_MINIMUM_REQUIRED_KEYFRAMES = 3, NUM_FIX = 2;                     // motion_estimator.cpp:1126-1127
+    info_.lba_points = info_.lba_obs = info_.lba_ok = 0;
+    if ((int)window_.size() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return;
+    const auto t_pack = Clock::now();
+    const int nf = (int)window_.size();
+    const int id0 = window_.front()->id;
+    std::vector<int> fidx_tab((size_t)(window_.back()->id - id0 + 1), -1);
+    for (int k = 0; k < nf; ++k) fidx_tab[window_[k]->id - id0] = k;
+    auto fidx_of = [&](int kf_id) { const int r = kf_id - id0; return (r >= 0 && r < (int)fidx_tab.size()) ? fidx_tab[r] : -1; };
+    std::vector<int> lmset;
+    {
+        std::vector<uint8_t> seen(lm_tri_.size(), 0);
+        for (const auto &fr : window_)
+            for (int id : fr->lm_ids)
+                if (!seen[id] && lm_tri_[id] && lm_alive_[id]) { seen[id] = 1; lmset.push_back(id); }
+    }
+    double Twj_ref[16], Tjw_ref[16];
+    for (int i = 0; i < 12; ++i) Twj_ref[i] = window_[0]->Twc[i];
+    Twj_ref[12] = Twj_ref[13] = Twj_ref[14] = 0; Twj_ref[15] = 1;
+    memset(Tjw_ref, 0, sizeof(Tjw_ref));
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Tjw_ref[i * 4 + j] = Twj_ref[j * 4 + i];
+        double s = 0; for (int k = 0; k < 3; ++k) s += Twj_ref[k * 4 + i] * Twj_ref[k * 4 + 3];
+        Tjw_ref[i * 4 + 3] = -s;
+    }
+    Tjw_ref[15] = 1;
+    const double pose_scale = 10.0, inv_scale = 1.0 / pose_scale;
+    std::vector<int> lms, obs_ptr(1, 0), obs_frame;
+    std::vector<double> points, obs_px;
+    for (int id : lmset) {
+        int cnt = 0;
+        for (const KfObs &o : lm_kf_obs_[id]) if (fidx_of(o.kf_id) >= 0) ++cnt;
+        if (cnt < 2) continue;                                                     // THRES_MINIMUM_SEEN
+        const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
+        for (int r = 0; r < 3; ++r)
+            points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
+        lms.push_back(id);
+        for (const KfObs &o : lm_kf_obs_[id]) {
+            const int fk = fidx_of(o.kf_id);
+            if (fk < 0) continue;
+            obs_frame.push_back(fk);
+            obs_px.push_back(o.x); obs_px.push_back(o.y);
+        }
+        obs_ptr.push_back((int)obs_frame.size());
+    }
+    if (lms.empty()) return;
+    std::vector<uint8_t> obs_right(obs_frame.size(), 0);
+    std::vector<double> poses((size_t)nf * 16);
+    for (int k = 0; k < nf; ++k) {
+        double Tjw[16];
+        for (int i = 0; i < 12; ++i) Tjw[i] = window_[k]->Tcw[i];
+        Tjw[12] = Tjw[13] = Tjw[14] = 0; Tjw[15] = 1;
+        mul4_d(Tjw, Twj_ref, Tjw);
+        for (int r = 0; r < 3; ++r) Tjw[r * 4 + 3] *= inv_scale;
+        memcpy(&poses[(size_t)k * 16], Tjw, sizeof(Tjw));
+    }
+    std::vector<int> opt_index(nf, -1);
+    for (int k = NUM_FIX; k < nf; ++k) opt_index[k] = k - NUM_FIX;
+    vo_lba_problem pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.n_frames = nf; pr.n_opt = nf - NUM_FIX; pr.n_points = (int)lms.size(); pr.n_obs = (int)obs_frame.size();
+    pr.poses = poses.data(); pr.opt_index = opt_index.data(); pr.points = points.data(); pr.obs_ptr = obs_ptr.data();
+    pr.obs_frame = obs_frame.data(); pr.obs_right = obs_right.data(); pr.obs_px = obs_px.data();
+    for (int i = 0; i < 4; ++i) { pr.K_l[i] = p_.K[i]; pr.K_r[i] = p_.K[i]; }
+    for (int i = 0; i < 16; ++i) pr.T_lr[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    pr.is_stereo = 0; pr.huber = 0.5; pr.lambda = 0.00001; pr.max_iter = 10;
+    std::vector<double> poses_out(poses.size()), points_out(points.size()), avg(pr.max_iter);
+    int ok = 0;
+    info_.ms_lba_pack = ms_since(t_pack);
+    const auto t_solve = Clock::now();
+    const int rc = vo_lba_solve(ctx_, &pr, poses_out.data(), points_out.data(), avg.data(), &ok);
+    if (rc == VO_ERR_NAN) throw std::runtime_error("Local BA NAN!\n");           // sparse_bundle_adjustment.cpp:761
+    if (rc) fail(ctx_, rc);
+    info_.lba_points = pr.n_points; info_.lba_obs = pr.n_obs; info_.lba_ok = ok;
+    bool large_update = false;
+    for (int k = 0; k < nf; ++k) {                                                // write-back (:631-718)
+        if (opt_index[k] < 0) continue;
+        double Tjw[16], Twj0[16], dT[16];
+        memcpy(Tjw, &poses_out[(size_t)k * 16], sizeof(Tjw));
+        for (int r = 0; r < 3; ++r) Tjw[r * 4 + 3] *= pose_scale;
+        mul4_d(Tjw, Tjw_ref, Tjw);
+        for (int i = 0; i < 12; ++i) Twj0[i] = window_[k]->Twc[i];
+        Twj0[12] = Twj0[13] = Twj0[14] = 0; Twj0[15] = 1;
+        mul4_d(Twj0, Tjw, dT);
+        if (std::sqrt(dT[3] * dT[3] + dT[7] * dT[7] + dT[11] * dT[11]) > 50) large_update = true;
+        float Tjw_f[16], Twj_f[16];
+        for (int i = 0; i < 12; ++i) Tjw_f[i] = (float)Tjw[i];
+        Tjw_f[12] = Tjw_f[13] = Tjw_f[14] = 0.f; Tjw_f[15] = 1.f;
+        inv_se3_f(Tjw_f, Twj_f);
+        setPose(*window_[k], Twj_f);
+    }
+    for (size_t j = 0; j < lms.size(); ++j) {
+        double X[3];
+        for (int r = 0; r < 3; ++r) X[r] = points_out[3 * j + r] * pose_scale;
+        float Xf[3];
+        for (int r = 0; r < 3; ++r) Xf[r] = (float)(Twj_ref[r * 4] * X[0] + Twj_ref[r * 4 + 1] * X[1] + Twj_ref[r * 4 + 2] * X[2] + Twj_ref[r * 4 + 3]);
+        const int id = lms[j];
+        memcpy(&lm_X_[(size_t)id * 3], Xf, 12);
+        lm_tri_[id] = 1;
+        if (std::sqrt(Xf[0] * Xf[0] + Xf[1] * Xf[1] + Xf[2] * Xf[2]) <= 3000) lm_bundled_[id] = 1;
+        else lm_alive_[id] = 0;
+    }
+    info_.ms_lba_solve = ms_since(t_solve);
+    if (large_update) throw std::runtime_error("large update!");                  // :731
+}
+
+void MonoVO::pushStats(const FrameRec &f, bool keyframe)
+{
+    if (keyframe) {
+        stat_.stats_keyframe.emplace_back();
+        for (size_t j = 0; j < stat_.stats_keyframe.size() && j < all_keyframes_.size(); ++j) {   // mono_vo.cpp:1142-1152
+            const FrameRec &kf = *all_keyframes_[j];
+            rowmajor_to_pose(kf.Twc, stat_.stats_keyframe[j].Twc);
+            PointVec &mp = stat_.stats_keyframe[j].mappoints;
+            mp.resize(kf.lm_ids.size());
+            for (size_t i = 0; i < kf.lm_ids.size(); ++i)
+                for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)kf.lm_ids[i] * 3 + r];
+        }
+    }
+    stat_.stats_frame.emplace_back();
+    AlgorithmStatistics::FrameStatistics &sf = stat_.stats_frame.back();
+    rowmajor_to_pose(f.Twc, sf.Twc); rowmajor_to_pose(f.Tcw, sf.Tcw);              // :969-974
+    rowmajor_to_pose(f.dT10, sf.dT_10); rowmajor_to_pose(f.dT01, sf.dT_01);
+    if (p_.record_frame_mappoints)                                                 // :1166-1177
+        for (size_t id = 0; id < lm_tri_.size(); ++id)
+            if (lm_tri_[id]) {
+                Point X;
+                for (int r = 0; r < 3; ++r) X(r) = lm_X_[id * 3 + r];
+                sf.mappoints.push_back(X);
+            }
+    // :1184-1185 refreshes every frame's pose; only the window's keyframes can have moved
+    if (keyframe)
+        for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_frame[kf->id].Twc);
+    stat_.stats_landmark.emplace_back();
+    stat_.stats_landmark.back().n_initial = info_.n_in;
+    stat_.stats_landmark.back().n_pass_bidirection = info_.counts[0];
+    stat_.stats_landmark.back().n_new = info_.n_new;
+    stat_.stats_landmark.back().n_final = (int)f.lm_ids.size();
+    stat_.stats_execution.emplace_back();
+}
+
+// ------------------------------------------------------------------------------ the step
+void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
+{
+    if (img.empty()) throw std::runtime_error("vo_b200: empty image");
+    const int w = img.cols, h = img.rows;
+    const auto t_total = Clock::now();
+    auto fr = std::make_shared<FrameRec>();
+    fr->id = (int)frames_.size();
+    ident(fr->Twc); ident(fr->Tcw); ident(fr->dT01); ident(fr->dT10);
+    frames_.push_back(fr);
+    info_ = FrameInfo();
+    info_.frame = fr->id;
+    const int k = fr->id;
+    const int s1 = k % 2, s0 = (k + 1) % 2;
+    const int nb = p_.n_bins_u * p_.n_bins_v;
+
+    vo_mono_frame_params fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.window_size = p_.window_size; fp.max_level = p_.max_level; fp.thres_error = p_.thres_error;
+    fp.thres_bidirection = p_.thres_bidirection; fp.thres_sampson = p_.thres_sampson; fp.thres_poseba_error = p_.thres_poseba_error;
+    memcpy(fp.K, p_.K, 16);
+    fp.use_bundled_only = (int)window_.size() > 5;               // mono_vo.cpp:800
+    fp.do_scale_refine = p_.do_scale_refine;
+    fp.n_bins_u = p_.n_bins_u; fp.n_bins_v = p_.n_bins_v; fp.det_edge = p_.det_edge; fp.det_min_score = p_.det_min_score;
+    fp.thres_5p = p_.thres_5p_error; fp.n_hypotheses = p_.n_hypotheses; fp.seed = p_.seed + (unsigned)k;
+
+    new_p1_.resize((size_t)std::max(nb, 1) * 2); new_p0_.resize((size_t)std::max(nb, 1) * 2);
+    float T_wc[16], dT01[16], dT10[16];
+    vo_mono_frame_result res;
+    memset(&res, 0, sizeof(res));
+    res.T_wc = T_wc; res.dT01 = dT01; res.dT10 = dT10; res.new_p1 = new_p1_.data(); res.new_p0 = new_p0_.data();
+    res.counts = p_.collect_gate_counts ? info_.counts : nullptr;
+
+    bool kf = false;
+    if (!prev_) {
+        // ---- the very first image (mono_vo.cpp:528-561): extraction only, identity pose, dT10 = [I | (0, 0, -1)]
+        int n_det = 0;
+        const int rc0 = vo_upload_image(ctx_, s1, img.data, w, h, img.step);
+        if (rc0) fail(ctx_, rc0);
+        const int rc = vo_detect_bucketed(ctx_, s1, nullptr, 0, p_.n_bins_u, p_.n_bins_v, p_.det_edge, p_.det_min_score, new_p1_.data(), std::max(nb, 1), &n_det);
+        if (rc) fail(ctx_, rc);
+        const int base = newLandmarks(n_det, new_p1_.data(), *fr);
+        fr->pts.assign(new_p1_.begin(), new_p1_.begin() + 2 * (size_t)n_det);
+        fr->lm_ids.resize(n_det);
+        for (int i = 0; i < n_det; ++i) fr->lm_ids[i] = base + i;
+        float T_init[16];
+        ident(T_init);
+        T_init[11] = -1.0f;
+        setPoseDiff10(*fr, T_init);
+        info_.n_detected = n_det; info_.n_new = n_det;
+    } else {
+        // ---- LandmarkTracking(pts, pts, lms) keeps the alive landmarks of the previous frame (landmark.cpp:233-270)
+        const FrameRec &pv = *prev_;
+        const size_t n_prev = pv.lm_ids.size();
+        in_ids_.clear(); in_p0_.clear(); in_X_.clear(); in_flags_.clear();
+        for (size_t i = 0; i < n_prev; ++i) {
+            const int id = pv.lm_ids[i];
+            if (!lm_alive_[id]) continue;
+            in_ids_.push_back(id);
+            in_p0_.push_back(pv.pts[2 * i]); in_p0_.push_back(pv.pts[2 * i + 1]);
+            for (int r = 0; r < 3; ++r) in_X_.push_back(lm_X_[(size_t)id * 3 + r]);
+            in_flags_.push_back((uint8_t)((lm_tri_[id] ? 1 : 0) | (lm_bundled_[id] ? 2 : 0)));
+        }
+        const int n = (int)in_ids_.size();
+        out_idx_.resize(std::max(n, 1)); out_p1_.resize((size_t)std::max(n, 1) * 2);
+        res.index = out_idx_.data(); res.pts1 = out_p1_.data();
+        fp.init_mode = initialised_ ? 0 : 1;
+        const auto t_step = Clock::now();
+        const int rc = vo_mono_frame_step(ctx_, &fp, s0, s1, img.data, w, h, img.step, n, in_p0_.data(), in_X_.data(), in_flags_.data(),
+                                          pv.Twc, pv.dT01, &res);
+        if (rc == VO_ERR_MODE) throw std::runtime_error(vo_last_error(ctx_));      // "calcPose5PointsAlgorithm() is failed." (:590 / :940)
+        if (rc) fail(ctx_, rc);
+        info_.ms_step = ms_since(t_step);
+        const int nt = res.n_tracked, m = res.n_new;
+        fr->lm_ids.resize((size_t)nt + m);
+        fr->pts.resize(2 * ((size_t)nt + m));
+        for (int i = 0; i < nt; ++i) fr->lm_ids[i] = in_ids_[out_idx_[i]];
+        memcpy(fr->pts.data(), out_p1_.data(), (size_t)nt * 8);
+        if (!initialised_) {
+            addObservations(fr->lm_ids.data(), out_p1_.data(), nt, *fr);           // :602-603: the frame still has the identity pose
+            setPose(*fr, T_wc); setPoseDiff10(*fr, dT10);                          // :611-612
+        } else {
+            setPose(*fr, T_wc); setPoseDiff10(*fr, dT10);                          // :889-890 / :947-948
+            addObservations(fr->lm_ids.data(), out_p1_.data(), nt, *fr);           // :966-967
+        }
+        // new features: born in the PREVIOUS frame at their back-tracked position, observed in this one (:638-657 / :993-1012)
+        const int base = newLandmarks(m, new_p0_.data(), pv);
+        for (int i = 0; i < m; ++i) fr->lm_ids[nt + i] = base + i;
+        memcpy(fr->pts.data() + 2 * (size_t)nt, new_p1_.data(), (size_t)m * 8);
+        addObservations(fr->lm_ids.data() + nt, new_p1_.data(), m, *fr);
+        info_.n_in = n; info_.n_tracked = nt; info_.n_detected = res.n_detected; info_.n_new = m; info_.used_5point = res.used_5point;
+        if (!initialised_) {
+            const auto t_rec = Clock::now();
+            info_.n_recon = reconstructInitial(*fr);
+            info_.ms_recon = ms_since(t_rec);
+            initialised_ = true;
+        }
+    }
+    // ---- keyframe (:1021-1157)
+    kf = checkUpdateRule(*fr);
+    if (kf) {
+        info_.keyframe = 1;
+        addKeyframe(fr);
+        const auto t_rec = Clock::now();
+        info_.n_recon += reconstructKeyframe(*fr);
+        info_.ms_recon += ms_since(t_rec);
+        localBundleAdjustment();
+    }
+    const auto t_stats = Clock::now();
+    pushStats(*fr, kf);
+    info_.ms_stats = ms_since(t_stats);
+    info_.ms_total = ms_since(t_total);
+    info_.ms_book = info_.ms_total - info_.ms_step - info_.ms_recon - info_.ms_lba_pack - info_.ms_lba_solve - info_.ms_stats;
+    stat_.stats_execution.back().time_track = info_.ms_step;
+    stat_.stats_execution.back().time_localba = info_.ms_lba_pack + info_.ms_lba_solve;
+    stat_.stats_execution.back().time_new = info_.ms_recon;
+    stat_.stats_execution.back().time_total = info_.ms_total;
+    // the previous frame's pixel / landmark lists are only needed again if it is a keyframe
+    if (prev_ && !prev_->is_keyframe) {
+        std::vector<float>().swap(prev_->pts);
+        std::vector<int>().swap(prev_->lm_ids);
+    }
+    prev_ = fr;
+}
+
+// ------------------------------------------------------------------------------ C wrapper
+struct vo_mvo { MonoVO *vo; };
+static thread_local std::string g_mvo_error;
+
+extern "C" const char *vo_mvo_last_error(void) { return g_mvo_error.c_str(); }
+
+extern "C" int vo_mvo_create(const MonoVO::Parameters *prm, vo_mvo **out)
+{
+    if (!prm || !out) return VO_ERR_INVALID_ARG;
+    try { *out = new vo_mvo{new MonoVO(*prm)}; return VO_OK; }
+    catch (const std::exception &e) { g_mvo_error = e.what(); *out = nullptr; return VO_ERR_NO_DEVICE; }
+}
+extern "C" int vo_mvo_create_from_yaml(const char *dir, vo_mvo **out)
+{
+    if (!dir || !out) return VO_ERR_INVALID_ARG;
+    try { *out = new vo_mvo{new MonoVO("rosbag", dir)}; return VO_OK; }
+    catch (const std::exception &e) { g_mvo_error = e.what(); *out = nullptr; return VO_ERR_INVALID_ARG; }
+}
+extern "C" void vo_mvo_destroy(vo_mvo *s) { if (s) { delete s->vo; delete s; } }
+extern "C" int vo_mvo_track(vo_mvo *s, const unsigned char *img, int w, int h, size_t step, double timestamp)
+{
+    if (!s || !img) return VO_ERR_INVALID_ARG;
+    try {
+        cv::Mat I(h, w, const_cast<unsigned char *>(img), step);
+        s->vo->trackImage(I, timestamp);
+        return VO_OK;
+    } catch (const std::exception &e) { g_mvo_error = e.what(); return VO_ERR_NAN; }
+}
+extern "C" int vo_mvo_pose(const vo_mvo *s, float *T)
+{
+    if (!s || !T || s->vo->getStatistics().stats_frame.empty()) return VO_ERR_INVALID_ARG;
+    const PoseSE3 &P = s->vo->getStatistics().stats_frame.back().Twc;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[r * 4 + c] = P(r, c);
+    return VO_OK;
+}
+extern "C" int vo_mvo_frame_pose(const vo_mvo *s, int frame_id, float *T) { return s ? s->vo->framePose(frame_id, T) : VO_ERR_INVALID_ARG; }
+extern "C" int vo_mvo_frame_info(const vo_mvo *s, MonoVO::FrameInfo *out)
+{
+    if (!s || !out) return VO_ERR_INVALID_ARG;
+    *out = s->vo->lastFrameInfo();
+    return VO_OK;
+}
+extern "C" int vo_mvo_tracks(const vo_mvo *s, int cap, int *ids, float *pts)
+{
+    if (!s) return VO_ERR_INVALID_ARG;
+    const auto &id = s->vo->currentLandmarkIds();
+    const int n = std::min<int>(cap, (int)id.size());
+    if (ids) memcpy(ids, id.data(), (size_t)n * 4);
+    if (pts) memcpy(pts, s->vo->currentPts().data(), (size_t)n * 8);
+    return (int)id.size();
+}
+extern "C" long long vo_mvo_launch_count(const vo_mvo *s) { return s ? s->vo->launchCount() : 0; }
+// layout check for language bindings: 0 = sizeof(Parameters), 1 = sizeof(FrameInfo)
+extern "C" int vo_mvo_struct_size(int which) { return which == 0 ? (int)sizeof(MonoVO::Parameters) : (int)sizeof(MonoVO::FrameInfo); }

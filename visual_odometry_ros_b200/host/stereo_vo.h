@@ -147,4 +147,5 @@ VO_API int vo_svo_tracks(const vo_svo *s, int cap, int *ids, float *pts_l, float
 VO_API int vo_svo_keyframe_poses(const vo_svo *s, int cap, float *T_wc16);                    // returns the count
 VO_API long long vo_svo_launch_count(const vo_svo *s);
 VO_API const char *vo_svo_last_error(void);
+VO_API int vo_svo_struct_size(int which);                                       // 0 Parameters, 1 FrameInfo (binding layout check)
 }
