@@ -429,6 +429,7 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                                    "4 levels, win 21) [+ trackWithScale] + stereo pose GN + compactions, wall clock incl. all "
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
     res["sequence"] = sequence_measurement(torch, dev, synth)
+    res["mono_sequence"] = mono_sequence_measurement(torch, dev, synth)
     res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
     return res
 
@@ -564,6 +565,61 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12):
                     "trackWithScale, stereo pose GN, compactions, bucketed detection, bidirectional stereo match of new features) every "
                     "frame; reconstruction + 10-iteration local BA on keyframes; wall clock incl. all copies/syncs and the host "
                     "bookkeeping; cpu = oracle composition (cv2 LK on all threads + C restatements + numpy detector)"}
+
+
+def mono_sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12):
+    """The mono VO step over the left images of the same synthetic sequence through the reference-API class
+    MonoVO::trackImage: five-point initialisation on the second image, then tracking + pose-only GN + new features every
+    frame, DLT reconstruction + mono local BA on keyframes."""
+    from oracle import mono_vo as omvo
+    from visual_odometry_ros_b200 import mono_vo as mvo
+    L, _, T_true = synth.stereo_sequence(n_frames, W, H, synth.kitti_K(), seed=3003, device=str(dev))
+    K4 = synth.kitti_K()
+    nbu, nbv = 64, 32
+    Lp = torch.from_numpy(L).pin_memory().numpy()
+    mk = lambda: mvo.MonoVO(mvo.make_parameters(W, H, K4, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    warm = mk()
+    for k in range(min(16, n_frames)):
+        warm.trackImage(Lp[k], 0.1 * k)
+    warm.close()
+    vo = mk()
+    ms, kf, nfeat, n5 = [], [], [], 0
+    launches0 = vo.launch_count
+    for k in range(n_frames):
+        t0 = time.perf_counter()
+        vo.trackImage(Lp[k], 0.1 * k)
+        ms.append((time.perf_counter() - t0) * 1e3)
+        fi = vo.frame_info()
+        kf.append(fi["keyframe"]); nfeat.append(fi["n_in"]); n5 += fi["used_5point"]
+    launches = vo.launch_count - launches0
+    P = np.stack([vo.frame_pose(j) for j in range(n_frames)])
+    T0inv = np.linalg.inv(T_true[0])
+    gt = np.stack([T0inv @ T_true[k] for k in range(n_frames)])
+    scale = np.linalg.norm(gt[1][:3, 3]) / max(1e-9, np.linalg.norm(P[1][:3, 3]))       # the unit first step fixes the mono scale
+    drift = float(np.linalg.norm(scale * P[-1][:3, 3] - gt[-1][:3, 3]) / max(1e-9, np.linalg.norm(gt[-1][:3, 3])))
+    ms_init = ms[1]
+    vo.close()
+    ms, kf = np.asarray(ms[2:]), np.asarray(kf[2:], bool)
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
+    ora = omvo.MonoVOOracle(W, H, K4, omvo.default_params(window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    cms = []
+    for k in range(n_cpu):
+        t0 = time.perf_counter()
+        ora.track(L[k])
+        cms.append((time.perf_counter() - t0) * 1e3)
+    return {"frames": n_frames, "ms_per_frame_mean": float(ms.mean()), "ms_per_frame_median": float(np.median(ms)),
+            "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
+            "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None, "keyframes": int(kf.sum()),
+            "ms_five_point_init_frame": float(ms_init), "five_point_frames": int(n5),
+            "mean_tracked_features": float(np.mean(nfeat[2:])), "bins": [nbu, nbv], "gpu_launches": int(launches),
+            "scaled_translation_drift_vs_ground_truth": drift,
+            "cpu_ms_per_frame": float(np.mean(cms[2:])), "cpu_init_frame_ms": float(cms[1]), "cpu_frames": n_cpu, "cpu_cores": os.cpu_count() or 1,
+            "what": "MonoVO::trackImage drop-in (host u8 image in, pose out): five-point RANSAC initialisation (1024 hypotheses) on "
+                    "the second image; then the fused mono step (pyramid, prior, trackBidirectionWithPrior, trackWithScale, mono "
+                    "pose GN, Sampson gate, compactions, bucketed detection, back-tracking of new features) every frame; DLT "
+                    "reconstruction + 10-iteration mono local BA on keyframes; wall clock incl. copies/syncs and host bookkeeping; "
+                    "cpu = oracle composition (cv2 LK + cv2.findEssentialMat on all threads + C restatements + numpy detector)"}
 
 
 if __name__ == "__main__":

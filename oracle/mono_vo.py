@@ -92,32 +92,35 @@ class MonoVOOracle:
         return np.arange(base, base + len(pts), dtype=np.int64)
 
     def _add_observations(self, ids, pts, fr):
-        """Landmark::addObservationAndRelatedFrame (landmark.cpp:76-135) for a batch."""
+        """Landmark::addObservationAndRelatedFrame (landmark.cpp:76-135) for a batch (vectorised per first frame; float32 in
+        the reference's operation order)."""
         if len(ids) == 0:
             return
         K = self.K
         fxinv, fyinv = f32(f32(1.0) / K[0]), f32(f32(1.0) / K[1])
         pts = np.asarray(pts, f32).reshape(-1, 2)
-        for i, p1 in zip(ids, pts):
-            i = int(i)
+        ids = [int(i) for i in ids]
+        f0 = np.asarray([self.first_frame[i] for i in ids], np.int64)
+        p0 = np.asarray([self.first_px[i] for i in ids], f32).reshape(-1, 2)
+        par = np.zeros(len(ids), f32)
+        for g in np.unique(f0):
+            sel = np.flatnonzero(f0 == g)
+            R = ostep.mul4_f32(self.frames[int(g)].Tcw, fr.Twc)[:3, :3]
+            x0 = np.stack([(p0[sel, 0] - K[2]) * fxinv, (p0[sel, 1] - K[3]) * fyinv, np.ones(len(sel), f32)], 1).astype(f32)
+            b = np.stack([(pts[sel, 0] - K[2]) * fxinv, (pts[sel, 1] - K[3]) * fyinv, np.ones(len(sel), f32)], 1).astype(f32)
+            x1 = np.stack([((R[r, 0] * b[:, 0] + R[r, 1] * b[:, 1]) + R[r, 2] * b[:, 2]) for r in range(3)], 1).astype(f32)
+            dot = ((x0[:, 0] * x1[:, 0] + x0[:, 1] * x1[:, 1]) + x0[:, 2] * x1[:, 2]).astype(f32)
+            n0 = np.sqrt(((x0[:, 0] * x0[:, 0] + x0[:, 1] * x0[:, 1]) + x0[:, 2] * x0[:, 2]).astype(f32)).astype(f32)
+            n1 = np.sqrt(((x1[:, 0] * x1[:, 0] + x1[:, 1] * x1[:, 1]) + x1[:, 2] * x1[:, 2]).astype(f32)).astype(f32)
+            c = (dot / (n0 * n1).astype(f32)).astype(f32)
+            c = np.where(c >= 1.0, f32(0.99999), c)
+            c = np.where(c <= -1.0, f32(-0.99999), c).astype(f32)
+            par[sel] = np.arccos(c).astype(f32)
+        for j, i in enumerate(ids):
             self.age[i] += 1
             self.last_frame[i] = fr.id
-            self.last_px[i] = p1.copy()
-            p0 = self.first_px[i]
-            T01 = ostep.mul4_f32(self.frames[self.first_frame[i]].Tcw, fr.Twc)
-            x0 = np.array([f32(f32(p0[0] - K[2]) * fxinv), f32(f32(p0[1] - K[3]) * fyinv), f32(1.0)], f32)
-            x1 = np.array([f32(f32(p1[0] - K[2]) * fxinv), f32(f32(p1[1] - K[3]) * fyinv), f32(1.0)], f32)
-            R = T01[:3, :3]
-            x1 = np.array([f32(f32(f32(R[r, 0] * x1[0]) + f32(R[r, 1] * x1[1])) + f32(R[r, 2] * x1[2])) for r in range(3)], f32)
-            dot = f32(f32(f32(x0[0] * x1[0]) + f32(x0[1] * x1[1])) + f32(x0[2] * x1[2]))
-            n0 = f32(np.sqrt(f32(f32(f32(x0[0] * x0[0]) + f32(x0[1] * x0[1])) + f32(x0[2] * x0[2]))))
-            n1 = f32(np.sqrt(f32(f32(f32(x1[0] * x1[0]) + f32(x1[1] * x1[1])) + f32(x1[2] * x1[2]))))
-            c = f32(dot / f32(n0 * n1))
-            if c >= 1.0:
-                c = f32(0.99999)
-            if c <= -1.0:
-                c = f32(-0.99999)
-            self.last_parallax[i] = f32(np.arccos(c))
+            self.last_px[i] = pts[j].copy()
+            self.last_parallax[i] = par[j]
 
     def _extract(self, img, occupied):
         p = self.p

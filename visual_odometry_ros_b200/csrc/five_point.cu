@@ -8,12 +8,14 @@
 //   k_5pt_solve   one thread per hypothesis: 5 distinct correspondences from a counter-based hash of (seed, hypothesis),
 //                 Nister's minimal solver -- null space of the 5x9 epipolar system, the ten cubic constraints
 //                 det(E) = 0 and 2 E E^T E - tr(E E^T) E = 0 as a 10x20 matrix, Gauss-Jordan, the 3x3 polynomial matrix in z,
-//                 its degree-10 determinant, real roots by monotone-interval bisection -- up to 10 essential matrices
+//                 its degree-10 determinant, real roots by monotone-interval safeguarded Newton -- up to 10 essential matrices
 //   k_5pt_score   one block per hypothesis: the error OpenCV's RANSAC uses, (x1^T E x0)^2 / (|E x0|_xy^2 + |E^T x1|_xy^2)
 //                 on normalised coordinates against (thres / mean focal)^2, for every candidate over ALL correspondences;
 //                 the best (count, first hypothesis, first candidate) is kept with one 64-bit atomicMax
-//   k_5pt_finish  one block: inlier mask of the best E, SVD decomposition, the four cheirality passes over all points
-//                 (mapping::triangulateDLT, core/util/triangulate_3d.cpp:5-50), R10 / t10 / X0 / mask
+//   k_5pt_decomp  SVD decomposition of the best E into the four (R, t) candidates
+//   k_5pt_cheir   one thread per correspondence: inlier bit of the best E and the four cheirality tests
+//                 (mapping::triangulateDLT, core/util/triangulate_3d.cpp:5-50), counted with block + global atomics
+//   k_5pt_final   the winning candidate: R10 / t10 / X0 / mask
 // All hypotheses are evaluated in parallel (a fixed number, default 1024) instead of OpenCV's sequential, adaptively
 // terminated loop: same model class, same error, same acceptance rule; the random samples differ, so parity with the
 // reference is statistical -- tests/test_five_point_gpu.py states the criteria.
@@ -21,6 +23,8 @@
 #include "vo_internal.cuh"
 #include "tri_device.cuh"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -41,6 +45,16 @@ struct FpDev {
     uint8_t *mask;
     int *info;               // 0 RANSAC inliers, 1 cheirality inliers of the chosen candidate, 2 ok
     float K[4];
+    struct FpPose *pose;     // decomposition of the best model + counters
+    uint8_t *bits;           // [n] bit 0 RANSAC inlier, bits 1..4 cheirality of the four candidates
+    float *X0c;              // [n][4][3] triangulated points of the four candidates
+};
+
+struct FpPose {
+    double E[9];
+    float R[2][9], t[3];
+    int valid;
+    int cnt[5];              // RANSAC inliers, cheirality counts of the four candidates
 };
 
 __device__ __forceinline__ int fp_count(const FpDev &d) { return d.n_d ? min(*d.n_d, d.n) : d.n; }
@@ -85,54 +99,82 @@ __device__ __forceinline__ void zmul(const double *a, int da, const double *b, i
         for (int j = 0; j <= db; ++j) o[i + j] = fma(a[i], b[j], o[i + j]);
 }
 
+// (i + k)! / i!: coefficient i of the k-th derivative is c[i + k] * c_dfact[k][i]
+__constant__ double c_dfact[11][11] = {
+    {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0},
+    {1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0, 10.0, 0.0},
+    {2.0, 6.0, 12.0, 20.0, 30.0, 42.0, 56.0, 72.0, 90.0, 0.0, 0.0},
+    {6.0, 24.0, 60.0, 120.0, 210.0, 336.0, 504.0, 720.0, 0.0, 0.0, 0.0},
+    {24.0, 120.0, 360.0, 840.0, 1680.0, 3024.0, 5040.0, 0.0, 0.0, 0.0, 0.0},
+    {120.0, 720.0, 2520.0, 6720.0, 15120.0, 30240.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {720.0, 5040.0, 20160.0, 60480.0, 151200.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {5040.0, 40320.0, 181440.0, 604800.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {40320.0, 362880.0, 1814400.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {362880.0, 3628800.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {3628800.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}};
+
+// p(x) and p'(x) of a degree-10 polynomial held in registers (coefficients above the actual degree are zero)
+__device__ __forceinline__ void horner11(const double (&d)[11], double x, double &p, double &dp)
+{
+    p = d[10]; dp = 0.0;
+#pragma unroll
+    for (int i = 9; i >= 0; --i) { dp = fma(dp, x, p); p = fma(p, x, d[i]); }
+}
+
 // All real roots of a polynomial of degree <= 10: the roots of the k-th derivative split the line into intervals on
-// which the (k-1)-th derivative is monotone, so every sign change brackets exactly one root (bisection + Newton polish).
+// which the (k-1)-th derivative is monotone, so every sign change brackets exactly one root (safeguarded Newton).
+// 32 hypotheses run in lockstep in a warp: the level's coefficients sit in registers and every evaluation is the same
+// fully unrolled 10-step Horner pair, so lanes with different degrees / root counts share one instruction stream.
 __device__ int real_roots(const double *c_in, int deg, double *roots)
 {
     double c[11];
     double cmax = 0.0;
     for (int i = 0; i <= deg; ++i) cmax = fmax(cmax, fabs(c_in[i]));
     if (!(cmax > 0.0) || !isfinite(cmax)) return 0;
-    for (int i = 0; i <= deg; ++i) c[i] = c_in[i] / cmax;
-    while (deg > 0 && fabs(c[deg]) < 1e-13) --deg;
+    for (int i = 0; i <= 10; ++i) c[i] = i <= deg ? c_in[i] / cmax : 0.0;
+    while (deg > 0 && fabs(c[deg]) < 1e-13) { c[deg] = 0.0; --deg; }
     if (deg == 0) return 0;
     double ra[10], rb[10];
     int na = 0;
     for (int k = deg - 1; k >= 0; --k) {
         const int m = deg - k;
-        double dk[11];
-        for (int i = 0; i <= m; ++i) {
-            double f = 1.0;
-            for (int j = 1; j <= k; ++j) f *= (double)(i + j);
-            dk[i] = c[i + k] * f;
-        }
+        double d[11];
+#pragma unroll
+        for (int i = 0; i <= 10; ++i) d[i] = (i + k <= 10) ? c[min(i + k, 10)] * c_dfact[k][i] : 0.0;
+        const double lead = c[deg] * c_dfact[k][m];
         double R = 0.0;
-        for (int i = 0; i < m; ++i) R = fmax(R, fabs(dk[i] / dk[m]));
+#pragma unroll
+        for (int i = 0; i < 10; ++i) R = fmax(R, i < m ? fabs(d[i] / lead) : 0.0);
         R += 1.0;
         int nb = 0;
-        double lo = -R, flo = horner(dk, m, lo);
+        double lo = -R, flo, tmp;
+        horner11(d, lo, flo, tmp);
         for (int j = 0; j <= na; ++j) {
             const double hi = j < na ? ra[j] : R;
-            const double fhi = horner(dk, m, hi);
+            double fhi;
+            horner11(d, hi, fhi, tmp);
             if (fhi == 0.0) {
                 if (nb < 10) rb[nb++] = hi;
             } else if (flo != 0.0 && ((flo < 0.0) != (fhi < 0.0))) {
+                // safeguarded Newton inside the bracket (bisection whenever the Newton step leaves it or stalls)
                 double a = lo, b = hi;
                 const bool neg_a = flo < 0.0;
-                for (int it = 0; it < 80; ++it) {
-                    const double mid = 0.5 * (a + b);
-                    if (mid <= a || mid >= b) break;
-                    const double fm = horner(dk, m, mid);
-                    if ((fm < 0.0) == neg_a) a = mid; else b = mid;
-                }
-                double x = 0.5 * (a + b);
-                for (int it = 0; it < 2; ++it) {                       // Newton polish inside the bracket
-                    double p = dk[m], dp = 0.0;
-                    for (int i = m - 1; i >= 0; --i) { dp = fma(dp, x, p); p = fma(p, x, dk[i]); }
-                    if (dp != 0.0) {
-                        const double xn = x - p / dp;
-                        if (xn > a && xn < b) x = xn;
-                    }
+                double x = 0.5 * (a + b), dx_old = b - a, dx = dx_old;
+                for (int it = 0; it < 100; ++it) {
+                    double p, dp;
+                    horner11(d, x, p, dp);
+                    if (p == 0.0) break;
+                    if ((p < 0.0) == neg_a) a = x; else b = x;
+                    const double tol = 4.0e-16 * fmax(1.0, fabs(x));
+                    const double step = dp != 0.0 ? p / dp : 0.0;
+                    if ((dp != 0.0 && fabs(step) <= tol) || b - a <= tol) break;        // converged (x is one end of the bracket)
+                    const double xn = x - step;
+                    const bool newton_ok = dp != 0.0 && xn > a && xn < b && fabs(2.0 * p) <= fabs(dx_old * dp);
+                    dx_old = dx;
+                    const double x_new = newton_ok ? xn : 0.5 * (a + b);
+                    dx = x_new - x;
+                    if (x_new == x) break;
+                    x = x_new;
                 }
                 if (nb < 10) rb[nb++] = x;
             }
@@ -147,8 +189,10 @@ __device__ int real_roots(const double *c_in, int deg, double *roots)
 
 // Nister's five-point minimal solver.  q[i] = (x0, y0, x1, y1) with x1^T E x0 = 0.  E_out[s][9] row-major, Frobenius
 // norm 1; returns the number of real solutions (<= 10).
-__device__ int solve5(const double4 *q, double *E_out)
+__device__ int solve5(const double4 *q, double *E_out, long long *trace = nullptr)
 {
+#define FP_STAMP(k) do { if (trace) trace[k] = clock64(); } while (0)
+    FP_STAMP(0);
     // ---- null space of the 5x9 system: Gauss-Jordan with full pivoting
     double Q[5][9];
     for (int i = 0; i < 5; ++i) {
@@ -176,6 +220,7 @@ __device__ int solve5(const double4 *q, double *E_out)
             if (f != 0.0) for (int j = 0; j < 9; ++j) Q[i][j] = fma(-f, Q[r][j], Q[i][j]);
         }
     }
+    FP_STAMP(1);
     double Ep[9][4];                                                 // entry -> {X, Y, Z, W} coefficients
     {
         int k = 0;
@@ -220,6 +265,7 @@ __device__ int solve5(const double4 *q, double *E_out)
             for (int j = 0; j < 3; ++j)
                 for (int k = 0; k < 3; ++k) p2p1_acc(L[li[i][k]], Ep[3 * k + j], A[1 + 3 * i + j], 1.0);
     }
+    FP_STAMP(2);
     // ---- Gauss-Jordan on the first ten columns (partial pivoting)
     for (int c = 0; c < 10; ++c) {
         int br = c;
@@ -237,6 +283,7 @@ __device__ int solve5(const double4 *q, double *E_out)
             if (f != 0.0) for (int j = c; j < 20; ++j) A[r][j] = fma(-f, A[c][j], A[r][j]);
         }
     }
+    FP_STAMP(3);
     // ---- B(z): rows <k> = <e> - z<f>, <l> = <g> - z<h>, <m> = <i> - z<j>; columns x (deg 3), y (deg 3), 1 (deg 4)
     double B[3][3][5];
     for (int r = 0; r < 3; ++r) {
@@ -273,8 +320,10 @@ __device__ int solve5(const double4 *q, double *E_out)
         zmul(B[0][2], 4, t6, 6, pr);
         for (int i = 0; i < 11; ++i) poly[i] += pr[i];
     }
+    FP_STAMP(4);
     double zs[10];
     const int nz = real_roots(poly, 10, zs);
+    FP_STAMP(5);
     int ns = 0;
     for (int s = 0; s < nz; ++s) {
         const double z = zs[s];
@@ -308,7 +357,9 @@ __device__ int solve5(const double4 *q, double *E_out)
         for (int e = 0; e < 9; ++e) E_out[ns * 9 + e] = E[e] * inv;
         ++ns;
     }
+    FP_STAMP(6);
     return ns;
+#undef FP_STAMP
 }
 
 __device__ __forceinline__ unsigned fp_hash(unsigned a, unsigned b, unsigned c)
@@ -319,7 +370,7 @@ __device__ __forceinline__ unsigned fp_hash(unsigned a, unsigned b, unsigned c)
     return (unsigned)((z ^ (z >> 31)) >> 16);
 }
 
-__global__ void __launch_bounds__(64) k_5pt_solve(const FpDev d)
+__global__ void __launch_bounds__(32) k_5pt_solve(const FpDev d)
 {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= d.H) return;
@@ -344,11 +395,11 @@ __global__ void __launch_bounds__(64) k_5pt_solve(const FpDev d)
 }
 
 // thread per correspondence set: the minimal solver alone (parity tests against the action-matrix oracle)
-__global__ void __launch_bounds__(64) k_5pt_minimal(const double4 *q, int n_sets, double *Es, int *nsol)
+__global__ void __launch_bounds__(64) k_5pt_minimal(const double4 *q, int n_sets, double *Es, int *nsol, long long *trace)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sets) return;
-    nsol[s] = solve5(q + 5 * (size_t)s, Es + (size_t)s * 90);
+    nsol[s] = solve5(q + 5 * (size_t)s, Es + (size_t)s * 90, (trace && s == 0) ? trace : nullptr);
 }
 
 __device__ __forceinline__ bool fp_inlier(const double *E, const double4 q, double thr2)
@@ -432,115 +483,122 @@ __device__ void jacobi_eig3(double A[3][3], double V[3][3], double w[3])
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
 }
 
-__global__ void __launch_bounds__(1024) k_5pt_finish(const FpDev d)
+// decomposition of the best model (one thread): E = U diag(s, s, 0) V^T (motion_estimator.cpp:70-96)
+__global__ void k_5pt_decomp(const FpDev d)
 {
-    __shared__ double sE[9];
-    __shared__ float sR[2][9], st[3];
-    __shared__ int s_cnt[5];
-    __shared__ int s_best;
-    const int tid = threadIdx.x;
-    const int n = fp_count(d);
+    if (threadIdx.x != 0) return;
+    FpPose &P = *d.pose;
+    for (int i = 0; i < 5; ++i) P.cnt[i] = 0;
     const unsigned long long key = *d.best;
     const int count = (int)(key >> 32);
-    if (count < 5) {                                  // no model: cv::findEssentialMat returns an empty matrix
-        for (int i = tid; i < n; i += 1024) d.mask[i] = 0;
-        if (tid == 0) { d.info[0] = 0; d.info[1] = 0; d.info[2] = 0; }
-        return;
-    }
+    P.valid = count >= 5 ? 1 : 0;                     // no model: cv::findEssentialMat returns an empty matrix
+    if (!P.valid) return;
     const unsigned id = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
     const int h = (int)(id >> 4), c = (int)(id & 15u);
-    if (tid < 9) sE[tid] = d.Es[(size_t)h * 90 + c * 9 + tid];
+    double sE[9];
+    for (int i = 0; i < 9; ++i) { sE[i] = d.Es[(size_t)h * 90 + c * 9 + i]; P.E[i] = sE[i]; }
+    // V from the eigenvectors of E^T E, u_i = E v_i / s_i, u_3 = u_1 x u_2 (det U = +1, what the reference's sign fix
+    // produces), det V forced to +1 through v_3
+    double A[3][3], V[3][3], w[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A[i][j] = sE[0 + i] * sE[0 + j] + sE[3 + i] * sE[3 + j] + sE[6 + i] * sE[6 + j];
+    jacobi_eig3(A, V, w);
+    int o[3] = {0, 1, 2};
+    for (int a = 0; a < 2; ++a)
+        for (int b = a + 1; b < 3; ++b)
+            if (w[o[b]] > w[o[a]]) { const int t = o[a]; o[a] = o[b]; o[b] = t; }
+    double v[3][3], u[3][3];                          // v[k] = k-th right singular vector
+    for (int k = 0; k < 3; ++k)
+        for (int i = 0; i < 3; ++i) v[k][i] = V[i][o[k]];
+    for (int k = 0; k < 2; ++k) {
+        double nn = 0.0;
+        for (int i = 0; i < 3; ++i) u[k][i] = sE[3 * i] * v[k][0] + sE[3 * i + 1] * v[k][1] + sE[3 * i + 2] * v[k][2];
+        if (k == 1) {
+            const double dp = u[1][0] * u[0][0] + u[1][1] * u[0][1] + u[1][2] * u[0][2];
+            for (int i = 0; i < 3; ++i) u[1][i] -= dp * u[0][i];
+        }
+        for (int i = 0; i < 3; ++i) nn += u[k][i] * u[k][i];
+        const double inv = 1.0 / sqrt(nn);
+        for (int i = 0; i < 3; ++i) u[k][i] *= inv;
+    }
+    u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
+    u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
+    u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+    const double cx0 = v[0][1] * v[1][2] - v[0][2] * v[1][1], cx1 = v[0][2] * v[1][0] - v[0][0] * v[1][2],
+                 cx2 = v[0][0] * v[1][1] - v[0][1] * v[1][0];
+    if (cx0 * v[2][0] + cx1 * v[2][1] + cx2 * v[2][2] < 0.0)
+        for (int i = 0; i < 3; ++i) v[2][i] = -v[2][i];
+    // W = [0 -1 0; 1 0 0; 0 0 1]: the columns of U W are (u2, -u1, u3)
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            P.R[0][3 * i + j] = (float)(u[1][i] * v[0][j] - u[0][i] * v[1][j] + u[2][i] * v[2][j]);   // U W V^T
+            P.R[1][3 * i + j] = (float)(-u[1][i] * v[0][j] + u[0][i] * v[1][j] + u[2][i] * v[2][j]);  // U W^T V^T
+        }
+    for (int i = 0; i < 3; ++i) P.t[i] = (float)u[2][i];
+    if (d.E_out) for (int i = 0; i < 9; ++i) d.E_out[i] = (float)sE[i];
+}
+
+// one thread per correspondence: RANSAC inlier bit of the best model (what cv::findEssentialMat returns) and the
+// cheirality of the four candidates (findCorrectRT :205-263 triangulates ALL correspondences for every candidate)
+__global__ void __launch_bounds__(128) k_5pt_cheir(const FpDev d)
+{
+    __shared__ int s_cnt[5];
+    const FpPose &P = *d.pose;
+    if (!P.valid) return;
+    const int tid = threadIdx.x, i = blockIdx.x * 128 + tid;
     if (tid < 5) s_cnt[tid] = 0;
     __syncthreads();
-    if (tid == 0) {
-        // E = U diag(s, s, 0) V^T (motion_estimator.cpp:70-96): V from the eigenvectors of E^T E, u_i = E v_i / s_i,
-        // u_3 = u_1 x u_2 (det U = +1, what the reference's sign fix produces), det V forced to +1 through v_3
-        double A[3][3], V[3][3], w[3];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) A[i][j] = sE[0 + i] * sE[0 + j] + sE[3 + i] * sE[3 + j] + sE[6 + i] * sE[6 + j];
-        jacobi_eig3(A, V, w);
-        int o[3] = {0, 1, 2};
-        for (int a = 0; a < 2; ++a)
-            for (int b = a + 1; b < 3; ++b)
-                if (w[o[b]] > w[o[a]]) { const int t = o[a]; o[a] = o[b]; o[b] = t; }
-        double v[3][3], u[3][3];                      // v[k] = k-th right singular vector
-        for (int k = 0; k < 3; ++k)
-            for (int i = 0; i < 3; ++i) v[k][i] = V[i][o[k]];
-        for (int k = 0; k < 2; ++k) {
-            double nn = 0.0;
-            for (int i = 0; i < 3; ++i) { u[k][i] = sE[3 * i] * v[k][0] + sE[3 * i + 1] * v[k][1] + sE[3 * i + 2] * v[k][2]; }
-            if (k == 1) {
-                const double dp = u[1][0] * u[0][0] + u[1][1] * u[0][1] + u[1][2] * u[0][2];
-                for (int i = 0; i < 3; ++i) u[1][i] -= dp * u[0][i];
-            }
-            for (int i = 0; i < 3; ++i) nn += u[k][i] * u[k][i];
-            const double inv = 1.0 / sqrt(nn);
-            for (int i = 0; i < 3; ++i) u[k][i] *= inv;
-        }
-        u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
-        u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
-        u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
-        const double cx0 = v[0][1] * v[1][2] - v[0][2] * v[1][1], cx1 = v[0][2] * v[1][0] - v[0][0] * v[1][2],
-                     cx2 = v[0][0] * v[1][1] - v[0][1] * v[1][0];
-        if (cx0 * v[2][0] + cx1 * v[2][1] + cx2 * v[2][2] < 0.0)
-            for (int i = 0; i < 3; ++i) v[2][i] = -v[2][i];
-        // U W V^T = -u1 v2^T + u2 v1^T + u3 v3^T ... with W = [0 -1 0; 1 0 0; 0 0 1]: (U W) columns = (u2, -u1, u3)
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                sR[0][3 * i + j] = (float)(u[1][i] * v[0][j] - u[0][i] * v[1][j] + u[2][i] * v[2][j]);   // U W V^T
-                sR[1][3 * i + j] = (float)(-u[1][i] * v[0][j] + u[0][i] * v[1][j] + u[2][i] * v[2][j]);  // U W^T V^T
-            }
-        for (int i = 0; i < 3; ++i) st[i] = (float)u[2][i];
-        if (d.E_out) for (int i = 0; i < 9; ++i) d.E_out[i] = (float)sE[i];
-    }
-    __syncthreads();
-    // RANSAC inlier mask of the best model (what cv::findEssentialMat returns)
-    int n_in = 0;
-    for (int i = tid; i < n; i += 1024) {
-        const bool in = fp_inlier(sE, d.q[i], d.thr2);
-        d.mask[i] = in ? 1 : 0;
-        n_in += in ? 1 : 0;
-    }
-    n_in = __reduce_add_sync(0xffffffffu, n_in);
-    if ((tid & 31) == 0) atomicAdd(&s_cnt[4], n_in);
-    // findCorrectRT (:205-263): cheirality count of the four candidates over ALL correspondences
-    for (int cand = 0; cand < 4; ++cand) {
-        const float *R = sR[cand >> 1];
-        const float sg = (cand & 1) ? -1.f : 1.f;
-        const float t[3] = {sg * st[0], sg * st[1], sg * st[2]};
-        int cnt = 0;
-        for (int i = tid; i < n; i += 1024) {
+    const int n = fp_count(d);
+    int bits = 0;
+    if (i < n) {
+        if (fp_inlier(P.E, d.q[i], d.thr2)) bits |= 1;
+        const float2 a = d.p0[i], b = d.p1[i];
+#pragma unroll 1
+        for (int cand = 0; cand < 4; ++cand) {
+            const float sg = (cand & 1) ? -1.f : 1.f;
+            const float t[3] = {sg * P.t[0], sg * P.t[1], sg * P.t[2]};
             float X0[3], X1[3];
-            tri_point(d.p0[i], d.p1[i], R, t, d.K, d.K, X0, X1);
-            cnt += (X0[2] > 0.f && X1[2] > 0.f) ? 1 : 0;
+            tri_point(a, b, P.R[cand >> 1], t, d.K, d.K, X0, X1);
+            if (X0[2] > 0.f && X1[2] > 0.f) bits |= 2 << cand;
+            float *o = d.X0c + ((size_t)i * 4 + cand) * 3;
+            o[0] = X0[0]; o[1] = X0[1]; o[2] = X0[2];
         }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if ((tid & 31) == 0) atomicAdd(&s_cnt[cand], cnt);
+        d.bits[i] = (uint8_t)bits;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int w = __reduce_add_sync(0xffffffffu, (bits >> k) & 1);
+        if ((tid & 31) == 0 && w) atomicAdd(&s_cnt[k], w);
     }
     __syncthreads();
-    if (tid == 0) {
-        int mx = 0, b = -1;
+    if (tid < 5 && s_cnt[tid]) atomicAdd(&d.pose->cnt[tid], s_cnt[tid]);
+}
+
+// the candidate with strictly most points in front of both cameras, first one on ties (:244-252); outputs
+__global__ void __launch_bounds__(128) k_5pt_final(const FpDev d)
+{
+    const FpPose &P = *d.pose;
+    const int n = fp_count(d);
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    int mx = 0, b = -1;
+    if (P.valid)
         for (int cand = 0; cand < 4; ++cand)
-            if (s_cnt[cand] > mx) { mx = s_cnt[cand]; b = cand; }
-        s_best = b;
-        d.info[0] = s_cnt[4]; d.info[1] = mx; d.info[2] = b >= 0 ? 1 : 0;
+            if (P.cnt[1 + cand] > mx) { mx = P.cnt[1 + cand]; b = cand; }
+    if (i == 0) {
+        d.info[0] = P.valid ? P.cnt[0] : 0; d.info[1] = mx; d.info[2] = b >= 0 ? 1 : 0;
         if (b >= 0) {
             const float sg = (b & 1) ? -1.f : 1.f;
-            for (int i = 0; i < 9; ++i) d.R10[i] = sR[b >> 1][i];
-            for (int i = 0; i < 3; ++i) d.t10[i] = sg * st[i];
+            for (int k = 0; k < 9; ++k) d.R10[k] = P.R[b >> 1][k];
+            for (int k = 0; k < 3; ++k) d.t10[k] = sg * P.t[k];
         }
     }
-    __syncthreads();
-    const int b = s_best;
-    if (b < 0) return;                                // the reference leaves R10_true / t10_true unset here; reported as failure
-    const float *R = sR[b >> 1];
-    const float sg = (b & 1) ? -1.f : 1.f;
-    const float t[3] = {sg * st[0], sg * st[1], sg * st[2]};
-    for (int i = tid; i < n; i += 1024) {
-        float X0[3], X1[3];
-        tri_point(d.p0[i], d.p1[i], R, t, d.K, d.K, X0, X1);
-        if (d.X0) { d.X0[3 * i] = X0[0]; d.X0[3 * i + 1] = X0[1]; d.X0[3 * i + 2] = X0[2]; }
-        d.mask[i] = (d.mask[i] && X0[2] > 0.f && X1[2] > 0.f) ? 1 : 0;          // mask_inlier = verify && 5p (:115)
+    if (i >= n) return;
+    if (b < 0) { d.mask[i] = 0; return; }             // the reference leaves R10_true / t10_true unset here; reported as failure
+    const int bits = d.bits[i];
+    d.mask[i] = ((bits & 1) && ((bits >> (1 + b)) & 1)) ? 1 : 0;                  // mask_inlier = verify && 5p (:115)
+    if (d.X0) {
+        const float *o = d.X0c + ((size_t)i * 4 + b) * 3;
+        d.X0[3 * i] = o[0]; d.X0[3 * i + 1] = o[1]; d.X0[3 * i + 2] = o[2];
     }
 }
 
@@ -566,7 +624,8 @@ int vo_5pt_launch_d(vo_ctx *ctx, const float *pts0_d, const float *pts1_d, int n
     VO_REQUIRE(n_hyp <= (1 << 20), VO_ERR_INVALID_ARG, "too many hypotheses");
     const size_t a = 256;
     const size_t o_q = 0, o_E = o_q + ((size_t)n * 32 + a - 1) / a * a, o_ns = o_E + (size_t)n_hyp * 720, o_b = o_ns + ((size_t)n_hyp * 4 + a - 1) / a * a;
-    const int rc = fp_scratch(ctx, o_b + 64);
+    const size_t o_P = o_b + a, o_bits = o_P + (sizeof(FpPose) + a - 1) / a * a, o_Xc = o_bits + ((size_t)n + a - 1) / a * a;
+    const int rc = fp_scratch(ctx, o_Xc + (size_t)n * 48);
     if (rc) return rc;
     uint8_t *s = (uint8_t *)ctx->d_fp;
     FpDev d;
@@ -578,12 +637,15 @@ int vo_5pt_launch_d(vo_ctx *ctx, const float *pts0_d, const float *pts1_d, int n
     d.H = n_hyp; d.seed = seed;
     d.q = (double4 *)(s + o_q); d.Es = (double *)(s + o_E); d.nsol = (int *)(s + o_ns); d.best = (unsigned long long *)(s + o_b);
     d.R10 = R10_d; d.t10 = t10_d; d.X0 = X0_d; d.E_out = E_d; d.mask = mask_d; d.info = info_d;
+    d.pose = (FpPose *)(s + o_P); d.bits = s + o_bits; d.X0c = (float *)(s + o_Xc);
     memcpy(d.K, K, 16);
     k_5pt_norm<<<vo_div_up(n > 0 ? n : 1, 256), 256, 0, ctx->stream>>>(d);
-    k_5pt_solve<<<vo_div_up(n_hyp, 64), 64, 0, ctx->stream>>>(d);
+    k_5pt_solve<<<vo_div_up(n_hyp, 32), 32, 0, ctx->stream>>>(d);
     k_5pt_score<<<n_hyp, 128, 0, ctx->stream>>>(d);
-    k_5pt_finish<<<1, 1024, 0, ctx->stream>>>(d);
-    ctx->launches += 4;
+    k_5pt_decomp<<<1, 32, 0, ctx->stream>>>(d);
+    k_5pt_cheir<<<vo_div_up(n > 0 ? n : 1, 128), 128, 0, ctx->stream>>>(d);
+    k_5pt_final<<<vo_div_up(n > 0 ? n : 1, 128), 128, 0, ctx->stream>>>(d);
+    ctx->launches += 6;
     VO_CUDA(cudaGetLastError());
     return VO_OK;
 }
@@ -635,11 +697,21 @@ extern "C" int vo_five_point_minimal(vo_ctx *ctx, const double *q, int n_sets, d
     memcpy(hs + o_q, q, S * 160);
     VO_CUDA(cudaMemcpyAsync(dv, hs, S * 160, cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA(cudaMemsetAsync(dv + o_E, 0, total - o_E, ctx->stream));
-    k_5pt_minimal<<<vo_div_up(n_sets, 64), 64, 0, ctx->stream>>>((const double4 *)(dv + o_q), n_sets, (double *)(dv + o_E), (int *)(dv + o_n));
+    static const bool trace = getenv("VO_5PT_TRACE") != nullptr;      // phase clocks of set 0 (profiling aid)
+    long long *trace_d = nullptr;
+    if (trace) { VO_CUDA(cudaMalloc(&trace_d, 64)); }
+    k_5pt_minimal<<<vo_div_up(n_sets, 64), 64, 0, ctx->stream>>>((const double4 *)(dv + o_q), n_sets, (double *)(dv + o_E), (int *)(dv + o_n), trace_d);
     ctx->launches++;
     VO_CUDA(cudaGetLastError());
     VO_CUDA(cudaMemcpyAsync(hs + o_E, dv + o_E, total - o_E, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace) {
+        long long t[8];
+        VO_CUDA(cudaMemcpy(t, trace_d, 56, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[5pt trace] null %lld | constraints %lld | gauss-jordan %lld | B(z)+det %lld | roots %lld | back-subst %lld cycles\n",
+                t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]);
+        cudaFree(trace_d);
+    }
     memcpy(E, hs + o_E, S * 720);
     memcpy(n_solutions, hs + o_n, S * 4);
     return VO_OK;
