@@ -309,6 +309,22 @@ VO_API int vo_pose_5point(vo_ctx *ctx, const float *pts0, const float *pts1, int
  * E [n_sets][10][9] row-major unit-norm candidates, n_solutions [n_sets]. */
 VO_API int vo_five_point_minimal(vo_ctx *ctx, const double *q, int n_sets, double *E, int *n_solutions);
 
+/* ------------------------------------------------------------------ epipolar distances / 1-point voting
+ * MotionEstimator::calcSampsonDistance (core/visual_odometry/motion_estimator.cpp:539-570; the F10 overload :572-600),
+ * calcSymmetricEpipolarDistance (:621-653): per-correspondence distances for the motion X1 = R10 X0 + t10, pixels in,
+ * F10 = Kinv^T skew(t10) R10 Kinv.  R10 [9] row-major, t10 [3], K4 = fx, fy, cx, cy, dist [n]. */
+VO_API int vo_sampson_distance(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *K4, const float *R10,
+                        const float *t10, float *dist);
+VO_API int vo_sampson_distance_F(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *F10, float *dist);
+VO_API int vo_symmetric_epipolar_distance(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *K4,
+                                   const float *R10, const float *t10, float *dist);
+/* MotionEstimator::findInliers1PointHistogram (:471-537): planar one-point motion voting -- theta_i = -2 atan((x0 y1 - y0 x1) /
+ * (y0 + y1)) on normalised coordinates, 400-bin histogram over [-0.5, 0.5] rad (core/util/histogram.h:11-35), the centre
+ * of the fullest bin (first one on ties), mask_i = symmetric epipolar distance for that motion <= thres_1p^2.
+ * theta_opt [1]; R10 [9], t10 [3], theta [n] nullable. */
+VO_API int vo_inliers_1point_histogram(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *K4, float thres_1p,
+                                uint8_t *mask, float *theta_opt, float *R10, float *t10, float *theta);
+
 /* ------------------------------------------------------------------ triangulation
  * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */
 VO_API int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,

@@ -203,3 +203,51 @@ def mono_init_step(I0, I1, pts0, T_wc_prev, K4, win, max_level, thres_err, thres
             out.update(new_p1=np.zeros((0, 2), f32), new_p0=np.zeros((0, 2), f32))
         out["n_detected"] = len(pts_new)
     return out
+
+
+def symmetric_epipolar(pts0, pts1, F):
+    """motion_estimator.cpp:638-652, float32 in the reference's operation order."""
+    p0, p1 = np.asarray(pts0, f32).reshape(-1, 2), np.asarray(pts1, f32).reshape(-1, 2)
+    F = np.asarray(F, f32)
+    one = f32(1.0)
+    a = [((F[r, 0] * p0[:, 0] + F[r, 1] * p0[:, 1]) + F[r, 2] * one).astype(f32) for r in range(3)]
+    b = [((F[0, r] * p1[:, 0] + F[1, r] * p1[:, 1]) + F[2, r] * one).astype(f32) for r in range(2)]
+    num = np.abs(((p1[:, 0] * a[0] + p1[:, 1] * a[1]) + one * a[2]).astype(f32))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        den = (one / np.sqrt((a[0] * a[0] + a[1] * a[1]).astype(f32)).astype(f32) +
+               one / np.sqrt((b[0] * b[0] + b[1] * b[1]).astype(f32)).astype(f32)).astype(f32)
+        return (num * den).astype(f32)
+
+
+def inliers_1point_histogram(pts0, pts1, K4, thres_1p):
+    """MotionEstimator::findInliers1PointHistogram (motion_estimator.cpp:471-537) with histogram::makeHistogram
+    (core/util/histogram.h:11-35) and medianHistogram (histogram.cpp:4-28: the centre of the fullest bin; std::sort leaves
+    ties unspecified -- the first such bin here).  Returns (theta_opt, mask, theta, counts, R10, t10)."""
+    p0, p1 = np.asarray(pts0, f32).reshape(-1, 2), np.asarray(pts1, f32).reshape(-1, 2)
+    K4 = np.asarray(K4, f32)
+    ifx, ify = f32(f32(1.0) / K4[0]), f32(f32(1.0) / K4[1])
+    x0, y0 = ((p0[:, 0] - K4[2]) * ifx).astype(f32), ((p0[:, 1] - K4[3]) * ify).astype(f32)
+    x1, y1 = ((p1[:, 0] - K4[2]) * ifx).astype(f32), ((p1[:, 1] - K4[3]) * ify).astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        val = ((x0 * y1 - y0 * x1).astype(f32) / (y0 * f32(1) + f32(1) * y1).astype(f32)).astype(f32)
+    theta = (np.float64(-2.0) * np.arctan(val).astype(f32).astype(np.float64)).astype(f32)
+    nb = 400
+    hmin, hmax = f32(-0.5), f32(0.5)
+    step = f32(f32(hmax - hmin) / f32(nb))
+    centers = np.zeros(nb, f32)
+    centers[0] = hmin
+    for i in range(1, nb - 1):
+        centers[i] = f32(centers[i - 1] + step)
+    centers[nb - 1] = hmax
+    with np.errstate(invalid="ignore"):
+        q = np.floor(((theta - hmin).astype(f32) / step).astype(f32))
+        ok = (q >= 0) & (q < nb)
+    counts = np.bincount(q[ok].astype(np.int64), minlength=nb)
+    th = centers[int(np.argmax(counts))]
+    c, s_ = f32(np.cos(th)), f32(np.sin(th))
+    R10 = np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]], f32)
+    t10 = np.array([f32(np.sin(f32(th * f32(0.5)))), 0, f32(np.cos(f32(th * f32(0.5))))], f32)
+    d = symmetric_epipolar(p0, p1, fundamental(K4, R10, t10))
+    with np.errstate(invalid="ignore"):
+        mask = d <= f32(f32(thres_1p) * f32(thres_1p))
+    return float(th), mask, theta, counts, R10, t10

@@ -57,3 +57,24 @@ def test_decomposition_picks_the_cheirality_winner():
         assert max(counts) == len(m) and sorted(counts)[-2] < len(m) // 2
         scale = np.linalg.norm(synth.so3_exp((0.004, -0.02, 0.003)).T @ np.array([0.05, -0.02, 0.9]))   # |t10| of the scene
         assert np.abs(X0 * scale - sc["X0"]).max() < 0.05 * np.abs(sc["X0"]).max()
+
+
+def test_epipolar_distances_and_one_point_vote():
+    """oracle/mono_step.py restatements of motion_estimator.cpp:471-653 on the synthetic two-view case."""
+    from oracle import mono_step as omono
+    sc = synth.two_view_scene(seed=21, n=2000)
+    F = omono.fundamental(sc["K4"], sc["R10"].astype(np.float32), sc["t10"].astype(np.float32))
+    ds, de = omono.sampson(sc["pts0"], sc["pts1"], F), omono.symmetric_epipolar(sc["pts0"], sc["pts1"], F)
+    inl = np.ones(len(ds), bool)
+    inl[sc["outlier_idx"]] = False
+    assert np.median(ds[inl]) < 0.5 and np.median(ds[~inl]) > 10 and np.median(de[inl]) < 1.5 and np.median(de[~inl]) > 5
+    # (1/g0 + 1/g1)^2 >= 4 / (g0 g1) >= 8 / (g0^2 + g1^2): symmetric^2 >= 8 Sampson, with equality for equal gradients
+    assert np.all(de.astype(np.float64) ** 2 >= 8 * ds.astype(np.float64) * (1 - 1e-4))
+    assert np.median(de[~inl] ** 2 / (8 * ds[~inl])) < 1.2
+    yaw = 0.05
+    sp = synth.two_view_scene(seed=33, n=2000, rotvec=(0.0, yaw, 0.0), t=(np.sin(yaw / 2) * 0.9, 0.0, np.cos(yaw / 2) * 0.9), outlier_frac=0.2)
+    th, mask, theta, counts, R10, t10 = omono.inliers_1point_histogram(sp["pts0"], sp["pts1"], sp["K4"], 5.0)
+    assert abs(th + yaw) <= 1.5 / 400 and counts.sum() <= len(theta) and counts.max() > 0.3 * len(theta)
+    inl = np.ones(len(mask), bool)
+    inl[sp["outlier_idx"]] = False
+    assert mask[inl].mean() > 0.9 and mask[~inl].mean() < 0.3

@@ -147,6 +147,10 @@ def lib():
     L.vo_rectify_init.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
     L.vo_read_rectify_maps.argtypes = [vp, ctypes.c_int, vp, vp]
     L.vo_upload_image_rectified.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+    L.vo_sampson_distance.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp]
+    L.vo_sampson_distance_F.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp]
+    L.vo_symmetric_epipolar_distance.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp]
+    L.vo_inliers_1point_histogram.argtypes = [vp, vp, vp, ctypes.c_int, vp, f32, vp, vp, vp, vp, vp]
     L.vo_pose_5point.argtypes = [vp, vp, vp, ctypes.c_int, vp, f32, ctypes.c_int, ctypes.c_uint, vp, vp, vp, vp, vp, vp]
     L.vo_five_point_minimal.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     L.vo_stereo_reconstruct.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
@@ -357,6 +361,37 @@ class Context:
         check(self.h, self.L.vo_triangulate_dlt(self.h, _ptr(p0), _ptr(p1), n, _ptr(R), _ptr(t), _ptr(K0), _ptr(K1),
                                                 _ptr(X0), _ptr(X1)))
         return X0, X1
+
+    def epipolar_distance(self, pts0, pts1, K4=None, R10=None, t10=None, F10=None, symmetric=False):
+        """calcSampsonDistance / calcSymmetricEpipolarDistance -> dist [n] (float32)."""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        n = len(p0)
+        if len(p1) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "Error in 'fineInliers1PointHistogram()': pts0.size() != pts1.size()")   # motion_estimator.cpp:543
+        d = np.zeros(max(n, 1), np.float32)
+        if F10 is not None:
+            F = np.ascontiguousarray(F10, np.float32)
+            check(self.h, self.L.vo_sampson_distance_F(self.h, _ptr(p0), _ptr(p1), n, _ptr(F), _ptr(d)))
+        else:
+            K, R, t = (np.ascontiguousarray(v, np.float32) for v in (K4, R10, t10))
+            fn = self.L.vo_symmetric_epipolar_distance if symmetric else self.L.vo_sampson_distance
+            check(self.h, fn(self.h, _ptr(p0), _ptr(p1), n, _ptr(K), _ptr(R), _ptr(t), _ptr(d)))
+        return d[:n]
+
+    def inliers_1point_histogram(self, pts0, pts1, K4, thres_1p):
+        """findInliers1PointHistogram -> dict(theta_opt, mask, R10, t10, theta)."""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        n = len(p0)
+        if len(p1) != n:
+            raise VoError(VO_ERR_SIZE_MISMATCH, "Error in 'fineInliers1PointHistogram()': pts0.size() != pts1.size()")   # :477
+        K = np.ascontiguousarray(K4, np.float32)
+        mask, th = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.float32)
+        th_opt, R, t = np.zeros(1, np.float32), np.zeros((3, 3), np.float32), np.zeros(3, np.float32)
+        check(self.h, self.L.vo_inliers_1point_histogram(self.h, _ptr(p0), _ptr(p1), n, _ptr(K), float(thres_1p), _ptr(mask), _ptr(th_opt),
+                                                         _ptr(R), _ptr(t), _ptr(th)))
+        return dict(theta_opt=float(th_opt[0]), mask=mask[:n].astype(bool), R10=R, t10=t, theta=th[:n])
 
     def pose_5point(self, pts0, pts1, K4, thres_5p, n_hypotheses=0, seed=0):
         """MotionEstimator::calcPose5PointsAlgorithm -> dict(R10, t10, X0, mask, E, n_ransac, n_cheirality)."""

@@ -106,6 +106,39 @@ int main()
     CHECK(throws_with([&] { PoseSE3 T = PoseSE3::Identity(); MaskVec q; me.poseOnlyBundleAdjustment_Stereo(X, shortv, pr, camc, camc, Tlr, 3.f, T, q); },
                       "X.size() != pts_l1.size()"), "size error text");
 
+    // ---- mono geometric front-end: five-point, Sampson / symmetric epipolar distance, 1-point voting
+    {
+        PixelVec m0, m1;
+        const float yaw = 0.02f, cyw = std::cos(yaw), syw = std::sin(yaw);
+        const float tx = 0.9f * std::sin(0.5f * yaw), tzz = 0.9f * std::cos(0.5f * yaw);               // planar motion: X1 = Ry(yaw) X0 + t
+        for (size_t i = 0; i < X.size(); ++i) {
+            const float x1 = cyw * X[i](0) + syw * X[i](2) + tx, y1 = X[i](1), z1 = -syw * X[i](0) + cyw * X[i](2) + tzz;
+            m0.emplace_back(fx * X[i](0) / X[i](2) + cx, fy * X[i](1) / X[i](2) + cy);
+            m1.emplace_back(fx * x1 / z1 + cx, fy * y1 / z1 + cy);
+        }
+        MotionEstimator mm5(false);
+        mm5.setThres5p(1.0f);
+        Rot3 R5; Pos3 t5; PointVec X5; MaskVec k5;
+        CHECK(mm5.calcPose5PointsAlgorithm(m0, m1, camc, R5, t5, X5, k5), "five-point success");
+        const float tn = std::sqrt(tx * tx + tzz * tzz);
+        CHECK(std::fabs(R5(0, 2) - syw) < 2e-3f && std::fabs(t5(2) - tzz / tn) < 2e-2f, "five-point pose value");
+        size_t n_in = 0; for (size_t i = 0; i < k5.size(); ++i) n_in += k5[i];
+        CHECK(n_in > k5.size() * 9 / 10 && X5.size() == m0.size(), "five-point inliers");
+        std::vector<float> ds, de;
+        mm5.calcSampsonDistance(m0, m1, camc, R5, t5, ds);
+        mm5.calcSymmetricEpipolarDistance(m0, m1, camc, R5, t5, de);
+        float worst_s = 0, worst_e = 0;
+        for (size_t i = 0; i < ds.size(); ++i) { worst_s = std::fmax(worst_s, ds[i]); worst_e = std::fmax(worst_e, de[i]); }
+        CHECK(ds.size() == m0.size() && worst_s < 1.0f && worst_e < 2.0f, "epipolar distances of exact correspondences");
+        mm5.setThres1p(5.0f);
+        MaskVec k1;
+        const float th = mm5.findInliers1PointHistogram(m0, m1, camc, k1);
+        CHECK(std::fabs(th - yaw) < 0.01f || std::fabs(th + yaw) < 0.01f, "1-point histogram finds the yaw");
+        PixelVec shortp(3);
+        CHECK(throws_with([&] { mm5.calcPose5PointsAlgorithm(m0, shortp, camc, R5, t5, X5, k5); }, "pts0.size() != pts1.size()"), "five-point size error text");
+        CHECK(throws_with([&] { mm5.calcSymmetricEpipolarDistance(m0, shortp, camc, R5, t5, de); }, "calcSymmetricEpipolarDistance"), "epipolar size error text");
+    }
+
     // ---- triangulateDLT
     Rot3 R10 = Rot3::Identity(); Pos3 t10; t10(0) = -base;
     PixelVec q0, q1;

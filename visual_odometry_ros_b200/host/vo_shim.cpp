@@ -256,6 +256,94 @@ bool MotionEstimator::poseOnlyBundleAdjustment_Stereo(const PointVec &X, const P
     return stereoImpl(X, pts_l1, pts_r1, Kl, Kr, T_lr, thres, T01, mask_inlier);
 }
 
+// ---- mono geometric front-end
+bool MotionEstimator::calcPose5PointsAlgorithm(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, Rot3 &R10_true,
+                                               Pos3 &t10_true, PointVec &X0_true, MaskVec &mask_inlier)
+{
+    if (pts0.size() != pts1.size()) throw std::runtime_error("calcPose5PointsAlgorithm(): pts0.size() != pts1.size()");        // :28
+    if (pts0.size() == 0) throw std::runtime_error("calcPose5PointsAlgorithm(): pts0.size() == pts1.size() == 0");             // :33
+    const size_t n = pts0.size();
+    mask_inlier.resize(n, true);
+    std::vector<uint8_t> m(n, 0);
+    X0_true.resize(n);
+    const float K4[4] = {cam->fx(), cam->fy(), cam->cx(), cam->cy()};
+    float R[9], t[3];
+    vo_ctx *ctx = shared_context();
+    const int rc = vo_pose_5point(ctx, pix(pts0), pix(pts1), (int)n, K4, thres_5p_, n_hypotheses_, seed_, R, t,
+                                  reinterpret_cast<float *>(X0_true.data()), m.data(), nullptr, nullptr);
+    if (rc == VO_ERR_MODE) return false;                       // no model (cv::findEssentialMat would return an empty matrix)
+    if (rc) throw_status(ctx, rc, nullptr);
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R10_true(r, c) = R[r * 3 + c]; t10_true(r) = t[r]; }
+    pack_mask(m, mask_inlier);
+    return true;
+}
+
+float MotionEstimator::findInliers1PointHistogram(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, MaskVec &maskvec_inlier)
+{
+    if (pts0.size() != pts1.size()) throw std::runtime_error("Error in 'fineInliers1PointHistogram()': pts0.size() != pts1.size()");   // :477
+    const size_t n = pts0.size();
+    maskvec_inlier.resize(n, false);
+    std::vector<uint8_t> m(std::max<size_t>(n, 1), 0);
+    const float K4[4] = {cam->fx(), cam->fy(), cam->cx(), cam->cy()};
+    float th = 0.f;
+    vo_ctx *ctx = shared_context();
+    const int rc = vo_inliers_1point_histogram(ctx, pix(pts0), pix(pts1), (int)n, K4, thres_1p_, m.data(), &th, nullptr, nullptr, nullptr);
+    if (rc) throw_status(ctx, rc, nullptr);
+    m.resize(n);
+    if (n) pack_mask(m, maskvec_inlier);
+    return th;
+}
+
+static void epi_impl(int which, const PixelVec &pts0, const PixelVec &pts1, const float *K4, const Rot3 *R10, const Pos3 *t10, const Mat33 *F10,
+                     std::vector<float> &dist, const char *msg)
+{
+    if (pts0.size() != pts1.size()) throw std::runtime_error(msg);
+    const size_t n = pts0.size();
+    dist.resize(n);
+    if (n == 0) return;
+    vo_ctx *ctx = shared_context();
+    int rc;
+    if (F10) {
+        float F[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F[r * 3 + c] = (*F10)(r, c);
+        rc = vo_sampson_distance_F(ctx, pix(pts0), pix(pts1), (int)n, F, dist.data());
+    } else {
+        float R[9], t[3];
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r * 3 + c] = (*R10)(r, c); t[r] = (*t10)(r); }
+        rc = which == 0 ? vo_sampson_distance(ctx, pix(pts0), pix(pts1), (int)n, K4, R, t, dist.data())
+                        : vo_symmetric_epipolar_distance(ctx, pix(pts0), pix(pts1), (int)n, K4, R, t, dist.data());
+    }
+    if (rc) throw_status(ctx, rc, nullptr);
+}
+
+void MotionEstimator::calcSampsonDistance(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, const Rot3 &R10, const Pos3 &t10,
+                                          std::vector<float> &sampson_dist)
+{
+    const float K4[4] = {cam->fx(), cam->fy(), cam->cx(), cam->cy()};
+    epi_impl(0, pts0, pts1, K4, &R10, &t10, nullptr, sampson_dist, "Error in 'fineInliers1PointHistogram()': pts0.size() != pts1.size()");   // :543
+}
+void MotionEstimator::calcSampsonDistance(const PixelVec &pts0, const PixelVec &pts1, const Mat33 &F10, std::vector<float> &sampson_dist)
+{
+    epi_impl(0, pts0, pts1, nullptr, nullptr, nullptr, &F10, sampson_dist, "Error in 'fineInliers1PointHistogram()': pts0.size() != pts1.size()");   // :576
+}
+float MotionEstimator::calcSampsonDistance(const Pixel &pt0, const Pixel &pt1, const Mat33 &F10)
+{
+    // one correspondence (:602-619): not worth a launch -- the same float arithmetic on the host
+    const float F[9] = {F10(0, 0), F10(0, 1), F10(0, 2), F10(1, 0), F10(1, 1), F10(1, 2), F10(2, 0), F10(2, 1), F10(2, 2)};
+    const float a0 = (F[0] * pt0.x + F[1] * pt0.y) + F[2] * 1.0f, a1 = (F[3] * pt0.x + F[4] * pt0.y) + F[5] * 1.0f,
+                a2 = (F[6] * pt0.x + F[7] * pt0.y) + F[8] * 1.0f;
+    const float b0 = (F[0] * pt1.x + F[3] * pt1.y) + F[6] * 1.0f, b1 = (F[1] * pt1.x + F[4] * pt1.y) + F[7] * 1.0f;
+    float num = (pt1.x * a0 + pt1.y * a1) + 1.0f * a2;
+    num *= num;
+    return num / (((a0 * a0 + a1 * a1) + b0 * b0) + b1 * b1);
+}
+void MotionEstimator::calcSymmetricEpipolarDistance(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, const Rot3 &R10,
+                                                    const Pos3 &t10, std::vector<float> &sym_epi_dist)
+{
+    const float K4[4] = {cam->fx(), cam->fy(), cam->cx(), cam->cy()};
+    epi_impl(1, pts0, pts1, K4, &R10, &t10, nullptr, sym_epi_dist, "In 'calcSymmetricEpipolarDistance()', pts0.size() != pts1.size()");   // :626
+}
+
 // ------------------------------------------------------------------------------ mapping::triangulateDLT
 namespace mapping {
 static void tri_impl(const float *p0, const float *p1, int n, const Rot3 &R10, const Pos3 &t10, const Camera &c0, const Camera &c1,

@@ -60,6 +60,18 @@ public:
                                          const float fy_l, const float cx_l, const float cy_l, const float fx_r, const float fy_r,
                                          const float cx_r, const float cy_r, const PoseSE3 &T_lr, float thres_reproj_outlier,
                                          PoseSE3 &T01, MaskVec &mask_inlier);
+    // mono geometric front-end (core motion_estimator.h:110-115, 137-143)
+    bool calcPose5PointsAlgorithm(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, Rot3 &R10_true, Pos3 &t10_true,
+                                  PointVec &X0_true, MaskVec &mask_inlier);
+    float findInliers1PointHistogram(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, MaskVec &maskvec_inlier);
+    void calcSampsonDistance(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, const Rot3 &R10, const Pos3 &t10,
+                             std::vector<float> &sampson_dist);
+    void calcSampsonDistance(const PixelVec &pts0, const PixelVec &pts1, const Mat33 &F10, std::vector<float> &sampson_dist);
+    float calcSampsonDistance(const Pixel &pt0, const Pixel &pt1, const Mat33 &F10);
+    void calcSymmetricEpipolarDistance(const PixelVec &pts0, const PixelVec &pts1, CameraConstPtr &cam, const Rot3 &R10, const Pos3 &t10,
+                                       std::vector<float> &sym_epi_dist);
+    // five-point RANSAC knobs of this build (the reference's cv::findEssentialMat draws its own samples)
+    void setRansac(int n_hypotheses, unsigned seed) { n_hypotheses_ = n_hypotheses; seed_ = seed; }
     // core :1090-1340 (drivers of the local BA) -- flat-window form; see SparseBundleAdjustmentSolver
     void setThres1p(float thres_1p) { thres_1p_ = thres_1p; }
     void setThres5p(float thres_5p) { thres_5p_ = thres_5p; }
@@ -70,7 +82,9 @@ private:
                     float thres, PoseSE3 &T01, MaskVec &mask);
     bool is_stereo_mode_;
     PoseSE3 T_lr_;
-    float thres_1p_ = 0, thres_5p_ = 0;
+    float thres_1p_ = 10.0f, thres_5p_ = 1.5f;                                          // motion_estimator.cpp:6-7
+    int n_hypotheses_ = 0;
+    unsigned seed_ = 0;
 };
 
 // core/util/triangulate_3d.h:16-30

@@ -69,6 +69,7 @@ using MaskVec = std::vector<bool>;
 using Pos3 = Eigen::Vector3f;
 using Rot3 = Eigen::Matrix3f;
 using PoseSE3 = Eigen::Matrix4f;
+using Mat33 = Eigen::Matrix3f;
 
 #ifndef VO_SHIM_USE_REAL_HEADERS
 // The subset of core/visual_odometry/camera.h the hot path reads (pinhole intrinsics).
