@@ -74,7 +74,7 @@ def test_epipolar_distances_and_one_point_vote():
     yaw = 0.05
     sp = synth.two_view_scene(seed=33, n=2000, rotvec=(0.0, yaw, 0.0), t=(np.sin(yaw / 2) * 0.9, 0.0, np.cos(yaw / 2) * 0.9), outlier_frac=0.2)
     th, mask, theta, counts, R10, t10 = omono.inliers_1point_histogram(sp["pts0"], sp["pts1"], sp["K4"], 5.0)
-    assert abs(th + yaw) <= 1.5 / 400 and counts.sum() <= len(theta) and counts.max() > 0.3 * len(theta)
+    assert abs(th + yaw) <= 1.5 / 400 and counts.sum() <= len(theta) and counts.max() > 0.2 * len(theta)
     inl = np.ones(len(mask), bool)
     inl[sp["outlier_idx"]] = False
     assert mask[inl].mean() > 0.9 and mask[~inl].mean() < 0.3
