@@ -43,3 +43,17 @@ for H in (256, 1024, 4096):
     t0 = time.perf_counter()
     for _ in range(20): ctx.pose_5point(sc["pts0"], sc["pts1"], sc["K4"], 1.0, n_hypotheses=H)
     print("H", H, "ms/call", (time.perf_counter() - t0) * 50)
+
+import cv2
+cv2.setNumThreads(16)
+Kcv = np.array([[sc["K4"][0], 0, sc["K4"][2]], [0, sc["K4"][1], sc["K4"][3]], [0, 0, 1]], np.float64)
+for frac in (0.1, 0.25, 0.4):
+    s2 = synth.two_view_scene(seed=2, n=2000, outlier_frac=frac)
+    cv2.findEssentialMat(s2["pts0"], s2["pts1"], Kcv, cv2.RANSAC, 0.999, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(10): cv2.findEssentialMat(s2["pts0"], s2["pts1"], Kcv, cv2.RANSAC, 0.999, 1.0)
+    tc = (time.perf_counter() - t0) * 100
+    ctx.pose_5point(s2["pts0"], s2["pts1"], s2["K4"], 1.0)
+    t0 = time.perf_counter()
+    for _ in range(10): ctx.pose_5point(s2["pts0"], s2["pts1"], s2["K4"], 1.0)
+    print("outliers", frac, "cv2.findEssentialMat ms", tc, "vo_pose_5point ms", (time.perf_counter() - t0) * 100)
