@@ -216,6 +216,23 @@ VO_API int vo_stereo_track_step(vo_ctx *ctx, const vo_stereo_step_params *prm, i
 VO_API int vo_detect_bucketed(vo_ctx *ctx, int slot, const float *pts_occupied, int n_occupied, int n_bins_u,
                        int n_bins_v, int edge, long long min_score, float *pts_out, int max_out, int *n_out);
 
+/* Keypoint detector behind vo_detect_bucketed and both frame steps.
+ * VO_DETECTOR_HARRIS_SCHARR (default): K-det, exact-integer Harris on the resident Scharr plane, non-occupied bins only.
+ * VO_DETECTOR_ORB: the reference's extractor, cv::ORB::detect as configured at feature_extractor.cpp:26-60 (10000 features,
+ * scale 1.2, 8 levels, edge 31, HARRIS_SCORE, FAST threshold = feature_extractor.thres_fastscore), restated stage by stage
+ * (INTER_LINEAR_EXACT pyramid, FAST-9/16 + non-maximum suppression, retainBest on the FAST score, Harris responses,
+ * retainBest per level) and pinned bit-exact against cv2.ORB 4.13 through its numpy twin. */
+#define VO_DETECTOR_HARRIS_SCHARR 0
+#define VO_DETECTOR_ORB 1
+VO_API int vo_set_detector(vo_ctx *ctx, int kind, int fast_threshold);
+/* The whole keypoint list of cv::ORB::detect on the slot's image (unordered): pts [max][2] in level-0 pixels, Harris
+ * response, octave.  VO_ERR_INVALID_ARG if max_keypoints is too small. */
+VO_API int vo_orb_detect(vo_ctx *ctx, int slot, int fast_threshold, int edge, int max_keypoints, float *pts, float *response,
+                  int *octave, int *n_out);
+/* Test hook: plane of the last K-orb run (0 pyramid level, 1 FAST score, 2 score after non-maximum suppression; the last two
+ * are defined inside the evaluated border band only).  dst nullable (size query), dense w x h. */
+VO_API int vo_orb_read_level(vo_ctx *ctx, int level, int plane, uint8_t *dst, int *w, int *h);
+
 /* ------------------------------------------------------------------ stereo frame step (tracking + new features)
  * vo_stereo_track_step followed, on the same stream and before the single synchronisation, by step [10] of
  * StereoVO::trackStereoImages (stereo_vo.cpp:690-740): bucketed detection on the current left image with the

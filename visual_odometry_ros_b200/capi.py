@@ -151,6 +151,9 @@ def lib():
     L.vo_sampson_distance_F.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp]
     L.vo_symmetric_epipolar_distance.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp]
     L.vo_inliers_1point_histogram.argtypes = [vp, vp, vp, ctypes.c_int, vp, f32, vp, vp, vp, vp, vp]
+    L.vo_set_detector.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.vo_orb_detect.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, c_int_p]
+    L.vo_orb_read_level.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, c_int_p, c_int_p]
     L.vo_pose_5point.argtypes = [vp, vp, vp, ctypes.c_int, vp, f32, ctypes.c_int, ctypes.c_uint, vp, vp, vp, vp, vp, vp]
     L.vo_five_point_minimal.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     L.vo_stereo_reconstruct.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
@@ -392,6 +395,25 @@ class Context:
         check(self.h, self.L.vo_inliers_1point_histogram(self.h, _ptr(p0), _ptr(p1), n, _ptr(K), float(thres_1p), _ptr(mask), _ptr(th_opt),
                                                          _ptr(R), _ptr(t), _ptr(th)))
         return dict(theta_opt=float(th_opt[0]), mask=mask[:n].astype(bool), R10=R, t10=t, theta=th[:n])
+
+    def set_detector(self, kind, fast_threshold=20):
+        """kind: "harris" (K-det, default) or "orb" (cv::ORB::detect restated, the reference's extractor)."""
+        check(self.h, self.L.vo_set_detector(self.h, {"harris": 0, "orb": 1}[kind], int(fast_threshold)))
+
+    def orb_detect(self, slot, fast_threshold, edge=31, max_keypoints=20000):
+        """cv::ORB::detect on the slot's image -> (pts [n,2], response [n], octave [n]), unordered."""
+        pts, resp = np.zeros((max_keypoints, 2), np.float32), np.zeros(max_keypoints, np.float32)
+        octv, n = np.zeros(max_keypoints, np.int32), ctypes.c_int(0)
+        check(self.h, self.L.vo_orb_detect(self.h, int(slot), int(fast_threshold), int(edge), int(max_keypoints), _ptr(pts), _ptr(resp),
+                                           _ptr(octv), ctypes.byref(n)))
+        return pts[:n.value].copy(), resp[:n.value].copy(), octv[:n.value].copy()
+
+    def orb_read_level(self, level, plane=0):
+        w, h = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.h, self.L.vo_orb_read_level(self.h, int(level), int(plane), None, ctypes.byref(w), ctypes.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        check(self.h, self.L.vo_orb_read_level(self.h, int(level), int(plane), _ptr(out), ctypes.byref(w), ctypes.byref(h)))
+        return out
 
     def pose_5point(self, pts0, pts1, K4, thres_5p, n_hypotheses=0, seed=0):
         """MotionEstimator::calcPose5PointsAlgorithm -> dict(R10, t10, X0, mask, E, n_ransac, n_cheirality)."""

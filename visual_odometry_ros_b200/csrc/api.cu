@@ -122,6 +122,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->d_lba) cudaFree(ctx->d_lba);
     if (ctx->d_det) cudaFree(ctx->d_det);
     if (ctx->d_fp) cudaFree(ctx->d_fp);
+    if (ctx->d_orb) cudaFree(ctx->d_orb);
     if (ctx->d_rect) cudaFree(ctx->d_rect);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

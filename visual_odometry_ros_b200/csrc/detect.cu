@@ -149,6 +149,9 @@ int vo_detect_launch_d(vo_ctx *ctx, int slot, const float *occ_d, const int *n_o
 {
     VO_REQUIRE(slot >= 0 && slot < ctx->n_slots && ctx->slots[slot].w > 0, VO_ERR_INVALID_ARG, "slot has no image");
     VO_REQUIRE(n_bins_u > 0 && n_bins_v > 0 && edge >= 3 && edge <= VO_PAD + 3, VO_ERR_INVALID_ARG, "bad detector arguments");
+    if (ctx->detector == VO_DETECTOR_ORB)        // the reference's own keypoints (cv::ORB), orb.cu; min_score has no meaning there
+        return vo_orb_launch_d(ctx, slot, occ_d, n_occ_d, n_occ, n_bins_u, n_bins_v, edge < 4 ? 4 : edge, out_d, out_mask_d, n_out_d, max_out,
+                               nullptr, nullptr, nullptr, nullptr, 0);
     const Slot &S = ctx->slots[slot];
     VO_REQUIRE(S.w / n_bins_u >= 1 && S.h / n_bins_v >= 1, VO_ERR_INVALID_ARG, "more bins than pixels");
     int rc = vo_ensure_pyramids(ctx, &slot, 1, 1, 1);

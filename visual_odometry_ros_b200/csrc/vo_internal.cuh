@@ -72,6 +72,12 @@ struct vo_ctx {
     // K-det scratch (score plane + per-bin state)
     void *d_det = nullptr;
     size_t det_bytes = 0;
+    // K-orb scratch (8-level pyramid, score planes, keypoint lists) and the detector the frame steps use
+    void *d_orb = nullptr;
+    size_t orb_bytes = 0;
+    int detector = 0;              // VO_DETECTOR_*
+    int orb_fast_threshold = 20;
+    struct { const uint8_t *img, *score, *nms; int w, h, pitch; } orb_dbg[8] = {};   // planes of the last K-orb run (vo_orb_read_level)
     // rectification: four CV_32FC1 maps + one distorted-image scratch plane (rectify.cu)
     void *d_rect = nullptr;
     size_t rect_bytes = 0;
@@ -140,6 +146,11 @@ int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, 
 int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, float *pts1_d, float *back_d, uint8_t *st_d, uint8_t *stb_d,
                             float *err_d, float *errb_d, uint8_t *mask_d, int skip_masked, int n, int win, int max_level, float thres_err,
                             float thres_bi, int with_prior, const float *scale_d, int *nan_flag_d);
+
+// orb.cu
+int vo_orb_launch_d(vo_ctx *ctx, int slot, const float *occ_d, const int *n_occ_d, int n_occ, int n_bins_u, int n_bins_v, int edge,
+                    float *out_d, uint8_t *out_mask_d, int *n_out_d, int max_out, float *all_pt_d, float *all_resp_d, int *all_octave_d,
+                    int *n_all_d, int max_all);
 
 // five_point.cu
 int vo_5pt_launch_d(vo_ctx *ctx, const float *pts0_d, const float *pts1_d, int n, const int *n_d, const float *K, float thres_px,
