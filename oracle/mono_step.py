@@ -73,7 +73,7 @@ def sampson(pts0, pts1, F):
 
 def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_prior, K4, win, max_level, thres_err, thres_bi,
                     thres_sampson, thres_poseba, use_bundled_only, n_bins_u=0, n_bins_v=0, det_edge=31, det_min_score=0,
-                    do_scale_refine=True, lk=oklt.lk_cv2, five_point=None, thres_5p=0.0):
+                    do_scale_refine=True, lk=oklt.lk_cv2, five_point=None, thres_5p=0.0, detect_fn=None):
     h, w = I0.shape
     pts0 = np.asarray(pts0, f32).reshape(-1, 2)
     Xw = np.asarray(Xw, f32).reshape(-1, 3)
@@ -149,7 +149,7 @@ def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_pri
     out = dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx.astype(np.int32), pts1=p1c, counts=counts, gn_iters=iters, F10=F, used_5point=used_5point)
     # new features (:981-992): extraction on I1 with the survivors as occupancy, back-tracking I1 -> I0
     if n_bins_u * n_bins_v > 0:
-        pts_new = odet.detect_bucketed(I1, p1c, n_bins_u, n_bins_v, det_edge, det_min_score)
+        pts_new = detect_fn(I1, p1c) if detect_fn else odet.detect_bucketed(I1, p1c, n_bins_u, n_bins_v, det_edge, det_min_score)
         if len(pts_new):
             p0_new, m = oklt.track_bidirection(lk, I1, I0, pts_new, win, max_level, thres_err, thres_bi)
             out.update(new_p1=pts_new[m], new_p0=p0_new[m])
@@ -165,7 +165,7 @@ def _five_point_cv(p0, p1, K4, thres_5p):
 
 
 def mono_init_step(I0, I1, pts0, T_wc_prev, K4, win, max_level, thres_err, thres_bi, thres_sampson, thres_5p, n_bins_u=0, n_bins_v=0,
-                   det_edge=31, det_min_score=0, lk=oklt.lk_cv2, five_point=None):
+                   det_edge=31, det_min_score=0, lk=oklt.lk_cv2, five_point=None, detect_fn=None):
     """The second image of a sequence (mono_vo.cpp:562-659): track (:573), calcPose5PointsAlgorithm (:589), Sampson gate
     (:594-597), |t10| = 1 (:606-609), pose (:611), new features back-tracked with trackBidirection (:623-636)."""
     pts0 = np.asarray(pts0, f32).reshape(-1, 2)
@@ -195,7 +195,7 @@ def mono_init_step(I0, I1, pts0, T_wc_prev, K4, win, max_level, thres_err, thres
     counts.append(len(idx))
     out = dict(T_wc=T_wc, dT01=dT01, dT10=dT10, index=idx.astype(np.int32), pts1=p1c, counts=counts, F10=F, used_5point=True)
     if n_bins_u * n_bins_v > 0:
-        pts_new = odet.detect_bucketed(I1, p1c, n_bins_u, n_bins_v, det_edge, det_min_score)
+        pts_new = detect_fn(I1, p1c) if detect_fn else odet.detect_bucketed(I1, p1c, n_bins_u, n_bins_v, det_edge, det_min_score)
         if len(pts_new):
             p0_new, m = oklt.track_bidirection(lk, I1, I0, pts_new, win, max_level, thres_err, thres_bi)
             out.update(new_p1=pts_new[m], new_p0=p0_new[m])

@@ -38,7 +38,7 @@ def default_params(**kw):
     p = dict(window_size=21, max_level=6, thres_error=60.0, thres_bidirection=0.5, thres_sampson=1000.0, thres_parallax_deg=1.0,
              n_bins_u=30, n_bins_v=12, det_edge=31, det_min_score=0, thres_5p=1.0, thres_poseba_error=5.0,
              kf_overlap_ratio=0.6, kf_rot_deg=10.0, kf_trans=4.0, kf_window=9, do_scale_refine=True,
-             lba_max_iter=10, lba_huber=0.5, lba_min_kf=3, lba_n_fix=2)
+             lba_max_iter=10, lba_huber=0.5, lba_min_kf=3, lba_n_fix=2, detector="harris", fast_threshold=15)
     p.update(kw)
     return p
 
@@ -124,6 +124,9 @@ class MonoVOOracle:
 
     def _extract(self, img, occupied):
         p = self.p
+        if p.get("detector", "harris") == "orb":          # the reference's extractor (oracle/orb.py, pinned against cv2.ORB)
+            from . import orb as oorb
+            return oorb.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["fast_threshold"])
         return odet.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["det_edge"], p["det_min_score"])
 
     # ------------------------------------------------------------------ keyframes
@@ -306,7 +309,7 @@ class MonoVOOracle:
                 # ---- second image (:562-696)
                 st = omono.mono_init_step(self.prev_img, img, pts0, pv.Twc, self.K, p["window_size"], p["max_level"], p["thres_error"],
                                           p["thres_bidirection"], p["thres_sampson"], p["thres_5p"], p["n_bins_u"], p["n_bins_v"],
-                                          p["det_edge"], p["det_min_score"], lk=self.lk, five_point=fp)
+                                          p["det_edge"], p["det_min_score"], lk=self.lk, five_point=fp, detect_fn=self._extract)
                 ids = ids0[st["index"]]
                 self._add_observations(ids, st["pts1"], fr)                          # :602-603, pose still identity
                 fr.set_pose(st["T_wc"])
@@ -318,7 +321,7 @@ class MonoVOOracle:
                 st = omono.mono_frame_step(self.prev_img, img, pts0, Xw, tri, bun, pv.Twc, pv.dT01, self.K, p["window_size"], p["max_level"],
                                            p["thres_error"], p["thres_bidirection"], p["thres_sampson"], p["thres_poseba_error"],
                                            len(self.window) > 5, p["n_bins_u"], p["n_bins_v"], p["det_edge"], p["det_min_score"],
-                                           do_scale_refine=p["do_scale_refine"], lk=self.lk, five_point=fp, thres_5p=p["thres_5p"])
+                                           do_scale_refine=p["do_scale_refine"], lk=self.lk, five_point=fp, thres_5p=p["thres_5p"], detect_fn=self._extract)
                 ids = ids0[st["index"]]
                 fr.set_pose(st["T_wc"])                                              # :889 / :947
                 fr.set_pose_diff10(st["dT10"])

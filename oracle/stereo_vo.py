@@ -36,7 +36,7 @@ def default_params(**kw):
     p = dict(window_size=21, max_level=3, thres_error=80.0, thres_bidirection=0.5, sampson_y=660.0,
              thres_poseba_error=3.0, n_bins_u=64, n_bins_v=32, det_edge=31, det_min_score=0,
              kf_overlap_ratio=0.6, kf_rot_deg=15.0, kf_trans=10.0, kf_window=9, do_scale_refine=True,
-             lba_max_iter=10, lba_huber=0.5, lba_min_kf=3, lba_n_fix=2)
+             lba_max_iter=10, lba_huber=0.5, lba_min_kf=3, lba_n_fix=2, detector="harris", fast_threshold=20)
     p.update(kw)
     return p
 
@@ -146,6 +146,9 @@ class StereoVOOracle:
 
     def _extract(self, img, occupied):
         p = self.p
+        if p.get("detector", "harris") == "orb":          # the reference's extractor (oracle/orb.py, pinned against cv2.ORB)
+            from . import orb as oorb
+            return oorb.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["fast_threshold"])
         return odet.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["det_edge"], p["det_min_score"])
 
     # ------------------------------------------------------------------ keyframes

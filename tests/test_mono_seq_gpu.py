@@ -38,7 +38,8 @@ def _make(seed=SEED, **kw):
                                           seed=seed, **kw))
 
 
-def test_mono_vo_class_next_to_oracle(seq):
+@pytest.mark.parametrize("detector", ["harris", "orb"])
+def test_mono_vo_class_next_to_oracle(seq, detector):
     L, _, T = seq
     K = synth.small_K()
     ctx = capi.Context(device=0, max_w=W, max_h=H, n_slots=2, max_feat=4096)
@@ -46,8 +47,9 @@ def test_mono_vo_class_next_to_oracle(seq):
     def fp_gpu(frame_id, p0, p1):
         r = ctx.pose_5point(p0, p1, K, 1.0, seed=SEED + frame_id)
         return True, r["R10"], r["t10"], r["mask"]
-    ora = omvo.MonoVOOracle(W, H, K, omvo.default_params(n_bins_u=NB_U, n_bins_v=NB_V, max_level=3, kf_trans=2.0), five_point=fp_gpu)
-    vo = _make()
+    ora = omvo.MonoVOOracle(W, H, K, omvo.default_params(n_bins_u=NB_U, n_bins_v=NB_V, max_level=3, kf_trans=2.0, detector=detector,
+                                                         fast_threshold=15), five_point=fp_gpu)
+    vo = _make(detector=detector, thres_fastscore=15)
     same_ids = n_kf = n_lba = 0
     in_step = True            # no borderline feature has flipped between the two LK implementations yet
     for k in range(len(L)):
@@ -135,7 +137,7 @@ def test_mono_vo_deterministic_and_yaml(seq, tmp_path):
                  "feature_extractor.n_bins_u: 32\nfeature_extractor.n_bins_v: 12\nmotion_estimator.thres_5p_error: 1.0\n"
                  "map_update.thres_parallax: 1.0\nkeyframe_update.thres_translation: 2.0\n")
     c = mvo.MonoVO(yaml_path=str(y))
-    d = _make(seed=0)
+    d = _make(seed=0, detector="orb", thres_fastscore=20)      # the yaml constructor runs the reference's extractor (default FAST 20)
     for k in range(5):
         c.trackImage(L[k], 0.1 * k)
         d.trackImage(L[k], 0.1 * k)

@@ -48,6 +48,8 @@ MonoVO::MonoVO(std::string mode, std::string directory_intrinsic)
     p_.thres_parallax_deg = (float)num("map_update.thres_parallax", p_.thres_parallax_deg);
     p_.n_bins_u = (int)num("feature_extractor.n_bins_u", p_.n_bins_u);
     p_.n_bins_v = (int)num("feature_extractor.n_bins_v", p_.n_bins_v);
+    p_.detector = VO_DETECTOR_ORB;                                    // the reference's extractor
+    p_.thres_fastscore = (int)num("feature_extractor.thres_fastscore", p_.thres_fastscore);   // initParams(..., int THRES_FAST, ...)
     p_.thres_5p_error = (float)num("motion_estimator.thres_5p_error", p_.thres_5p_error);
     p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
     p_.thres_overlap_ratio = (float)num("keyframe_update.thres_overlap_ratio", p_.thres_overlap_ratio);
@@ -62,6 +64,8 @@ void MonoVO::init()
     const int nb = std::max(1, p_.n_bins_u * p_.n_bins_v);
     const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 2, std::max(4 * nb + 4096, 262144), nullptr, &ctx_);
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
+    const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
+    if (rd) fail(ctx_, rd);
 }
 
 MonoVO::~MonoVO() { if (ctx_) vo_ctx_destroy(ctx_); }

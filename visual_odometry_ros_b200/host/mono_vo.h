@@ -68,6 +68,10 @@ public:
         unsigned seed = 0;                            // five-point sampling seed; frame k uses seed + k
         int collect_gate_counts = 0;
         int record_frame_mappoints = 0;               // 1: stats_frame[k].mappoints = all triangulated landmarks (:1166-1177; O(all landmarks) per frame)
+        // keypoint extractor: VO_DETECTOR_HARRIS_SCHARR (K-det) or VO_DETECTOR_ORB (cv::ORB::detect restated, what the
+        // reference runs; the yaml constructor selects it with feature_extractor.thres_fastscore, mono_vo.cpp:36-40)
+        int detector = VO_DETECTOR_HARRIS_SCHARR;
+        int thres_fastscore = 20;
     };
 
     MonoVO(std::string mode, std::string directory_intrinsic);     // mono_vo.cpp:11-55 (yaml via a minimal parser)

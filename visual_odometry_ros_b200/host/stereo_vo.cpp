@@ -71,6 +71,8 @@ StereoVO::StereoVO(std::string mode, std::string directory_intrinsic)
     p_.max_level = (int)num("feature_tracker.max_level", p_.max_level);
     p_.n_bins_u = (int)num("feature_extractor.n_bins_u", p_.n_bins_u);
     p_.n_bins_v = (int)num("feature_extractor.n_bins_v", p_.n_bins_v);
+    p_.detector = VO_DETECTOR_ORB;                                    // the reference's extractor
+    p_.thres_fastscore = (int)num("feature_extractor.thres_fastscore", p_.thres_fastscore);   // initParams(..., int THRES_FAST, ...)
     p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
     p_.thres_alive_ratio = (float)num("keyframe_update.thres_alive_ratio", p_.thres_alive_ratio);
     p_.thres_trans = (float)num("keyframe_update.thres_trans", p_.thres_trans);
@@ -86,6 +88,8 @@ void StereoVO::init()
     // (a few thousand landmarks x ~10 observations) then never re-allocate pinned memory inside the frame loop
     const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 4, std::max(4 * nb + 4096, 262144), nullptr, &ctx_);
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
+    const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
+    if (rd) fail(ctx_, rd);
     memcpy(K_use_l_, p_.K_l, 16); memcpy(K_use_r_, p_.K_r, 16); memcpy(T_lr_use_, p_.T_lr, 64);
     if (p_.do_undistortion) {
         // stereo_vo.cpp:414-428: rectified images, the rectified camera for both sides, the rectified extrinsics

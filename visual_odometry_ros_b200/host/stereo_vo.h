@@ -67,6 +67,10 @@ public:
         int do_undistortion = 0;
         float D_l[5] = {0, 0, 0, 0, 0}, D_r[5] = {0, 0, 0, 0, 0};
         int collect_gate_counts = 0;     // 1: FrameInfo::counts (survivors after every gate; three extra tiny launches per frame)
+        // keypoint extractor: VO_DETECTOR_HARRIS_SCHARR (K-det) or VO_DETECTOR_ORB (cv::ORB::detect restated, what the
+        // reference runs; the yaml constructor selects it with feature_extractor.thres_fastscore, stereo_vo.cpp:31-36)
+        int detector = VO_DETECTOR_HARRIS_SCHARR;
+        int thres_fastscore = 20;
     };
 
     StereoVO(std::string mode, std::string directory_intrinsic);   // stereo_vo.cpp:9-53 (yaml via a minimal parser)

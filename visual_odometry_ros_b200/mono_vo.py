@@ -21,7 +21,7 @@ class Parameters(ctypes.Structure):
                 ("thres_translation", ctypes.c_float), ("thres_rotation_deg", ctypes.c_float), ("n_max_keyframes_in_window", ctypes.c_int),
                 ("do_scale_refine", ctypes.c_int), ("det_edge", ctypes.c_int), ("det_min_score", ctypes.c_longlong), ("device", ctypes.c_int),
                 ("n_hypotheses", ctypes.c_int), ("seed", ctypes.c_uint), ("collect_gate_counts", ctypes.c_int),
-                ("record_frame_mappoints", ctypes.c_int)]
+                ("record_frame_mappoints", ctypes.c_int), ("detector", ctypes.c_int), ("thres_fastscore", ctypes.c_int)]
 
 
 class FrameInfo(ctypes.Structure):
@@ -59,7 +59,8 @@ def host_lib():
 def make_parameters(w, h, K, *, window_size=21, max_level=6, thres_error=60.0, thres_bidirection=0.5, thres_sampson=1000.0,
                     thres_parallax_deg=1.0, n_bins_u=30, n_bins_v=12, thres_5p_error=1.0, thres_poseba_error=5.0, thres_overlap_ratio=0.6,
                     thres_translation=4.0, thres_rotation_deg=10.0, n_max_keyframes_in_window=9, do_scale_refine=True, det_edge=31,
-                    det_min_score=0, device=0, n_hypotheses=0, seed=0, collect_gate_counts=False, record_frame_mappoints=False):
+                    det_min_score=0, device=0, n_hypotheses=0, seed=0, collect_gate_counts=False, record_frame_mappoints=False,
+                    detector="harris", thres_fastscore=20):
     """Defaults = config/mono/kitti_00.yaml."""
     p = Parameters()
     p.width, p.height = int(w), int(h)
@@ -73,6 +74,7 @@ def make_parameters(w, h, K, *, window_size=21, max_level=6, thres_error=60.0, t
     p.det_edge, p.det_min_score, p.device = int(det_edge), int(det_min_score), int(device)
     p.n_hypotheses, p.seed = int(n_hypotheses), int(seed)
     p.collect_gate_counts, p.record_frame_mappoints = int(bool(collect_gate_counts)), int(bool(record_frame_mappoints))
+    p.detector, p.thres_fastscore = {"harris": 0, "orb": 1}[detector], int(thres_fastscore)
     return p
 
 
