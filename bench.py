@@ -430,6 +430,7 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
     res["sequence"] = sequence_measurement(torch, dev, synth)
     res["mono_sequence"] = mono_sequence_measurement(torch, dev, synth)
+    res["sequence_orb"] = sequence_measurement(torch, dev, synth, n_frames=60, n_cpu=6, detector="orb", with_concurrent=False)
     res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
     return res
 
@@ -514,7 +515,7 @@ def cfg4_measurement(ctx, synth):
             "what": "vo_lba_solve / vo_depth_filter_normal with host buffers, wall clock incl. H2D/D2H and the sync"}
 
 
-def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12):
+def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="harris", with_concurrent=True):
     """BASELINE config 3: the full stereo VO step over a synthetic KITTI-like sequence through the reference-API class
     (host images in, pose out; tracking + new features every frame, reconstruction + local BA on keyframes)."""
     from oracle import stereo_vo as osvo
@@ -524,11 +525,13 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12):
     nbu, nbv = 64, 32
     Lp, Rp = torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()
     # warm-up instance: first use of every kernel (lazy module loading), first pinned / device allocations
-    warm = svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    mk = lambda: svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv,
+                                                  detector=detector, thres_fastscore=20))
+    warm = mk()
     for k in range(min(16, n_frames)):
         warm.trackStereoImages(Lp[k], Rp[k], 0.1 * k)
     warm.close()
-    vo = svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    vo = mk()
     ms, kf, nfeat = [], [], []
     launches0 = vo.launch_count
     for k in range(n_frames):
@@ -546,14 +549,15 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12):
     ms, kf = np.asarray(ms[2:]), np.asarray(kf[2:], bool)       # skip the first frame and the first (allocating) step
     import cv2
     cv2.setNumThreads(os.cpu_count() or 1)
-    ora = osvo.StereoVOOracle(W, H, K4, K4, Tlr, osvo.default_params(window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv))
+    ora = osvo.StereoVOOracle(W, H, K4, K4, Tlr, osvo.default_params(window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv,
+                                                                    detector=detector, fast_threshold=20))
     cms = []
     for k in range(n_cpu):
         t0 = time.perf_counter()
         ora.track(L[k], R[k])
         cms.append((time.perf_counter() - t0) * 1e3)
-    conc = concurrent_sequences(svo, Lp, Rp, K4, Tlr, nbu, nbv)
-    return {"concurrent_sequences": conc,
+    conc = concurrent_sequences(svo, Lp, Rp, K4, Tlr, nbu, nbv) if with_concurrent else None
+    return {"concurrent_sequences": conc, "detector": "K-det (Harris on the Scharr plane)" if detector == "harris" else "cv::ORB restated (the reference's extractor), FAST threshold 20",
             "frames": n_frames, "ms_per_frame_mean": float(ms.mean()), "ms_per_frame_median": float(np.median(ms)),
             "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
             "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None,

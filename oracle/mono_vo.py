@@ -126,7 +126,7 @@ class MonoVOOracle:
         p = self.p
         if p.get("detector", "harris") == "orb":          # the reference's extractor (oracle/orb.py, pinned against cv2.ORB)
             from . import orb as oorb
-            return oorb.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["fast_threshold"])
+            return oorb.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["fast_threshold"], backend="cv2")
         return odet.detect_bucketed(img, occupied, p["n_bins_u"], p["n_bins_v"], p["det_edge"], p["det_min_score"])
 
     # ------------------------------------------------------------------ keyframes

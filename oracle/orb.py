@@ -172,12 +172,31 @@ def detect(img, fast_threshold, nfeatures=10000, n_levels=8, scale_factor=1.2, e
     return np.concatenate(P), np.concatenate(R), np.concatenate(O)
 
 
-def detect_bucketed(img, occupied, n_bins_u, n_bins_v, fast_threshold, **kw):
+_CV_ORB = {}
+
+
+def detect_cv2(img, fast_threshold):
+    """The reference's own library call: cv::ORB configured as feature_extractor.cpp:30-56, keypoints in OpenCV's order."""
+    import cv2
+    o = _CV_ORB.get(int(fast_threshold))
+    if o is None:
+        o = cv2.ORB_create()
+        o.setMaxFeatures(10000); o.setScaleFactor(1.2); o.setNLevels(8); o.setEdgeThreshold(31); o.setFirstLevel(0); o.setWTA_K(2)
+        o.setScoreType(cv2.ORB_HARRIS_SCORE); o.setPatchSize(31); o.setFastThreshold(int(fast_threshold))
+        _CV_ORB[int(fast_threshold)] = o
+    kp = o.detect(np.ascontiguousarray(img), None)
+    if not kp:
+        return np.zeros((0, 2), f32), np.zeros(0, f32), np.zeros(0, np.int32)
+    return (np.asarray([k.pt for k in kp], f32), np.asarray([k.response for k in kp], f32), np.asarray([k.octave for k in kp], np.int32))
+
+
+def detect_bucketed(img, occupied, n_bins_u, n_bins_v, fast_threshold, backend="numpy", **kw):
     """FeatureExtractor::updateWeightBin + extractORBwithBinning_fast (feature_extractor.cpp:94-98, 211-282) over
-    cv::ORB keypoints: the best-response keypoint of every bin that holds no occupied point, in bin order."""
+    cv::ORB keypoints: the best-response keypoint of every bin that holds no occupied point, in bin order.
+    backend "numpy": the restatement above; "cv2": cv2.ORB itself (same keypoint set, pinned; much faster)."""
     from .detect import weight_bins
     h, w = img.shape
-    pts, resp, _ = detect(img, fast_threshold, **kw)
+    pts, resp, _ = detect_cv2(img, fast_threshold) if backend == "cv2" else detect(img, fast_threshold, **kw)
     weight, u_step, v_step = weight_bins(occupied, w, h, n_bins_u, n_bins_v)
     inv_u, inv_v = f32(1.0) / f32(u_step), f32(1.0) / f32(v_step)
     best = np.full(n_bins_u * n_bins_v, -1, np.int64)

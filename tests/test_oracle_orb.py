@@ -58,3 +58,6 @@ def test_orb_bucketing_follows_reference():
     occ_bins = set((int(p[1] // vb) * 32 + int(p[0] // ub)) for p in occ)
     got_bins = [int(p[1] // vb) * 32 + int(p[0] // ub) for p in pts]
     assert not (set(got_bins) & occ_bins) and got_bins == sorted(got_bins) and len(set(got_bins)) == len(got_bins)
+    # the cv2 backend (the reference's own call, OpenCV's keypoint order) buckets to the same points
+    assert np.array_equal(pts, orb.detect_bucketed(img, occ, 32, 12, 15, backend="cv2"))
+    assert np.array_equal(pts_all, orb.detect_bucketed(img, np.zeros((0, 2), np.float32), 32, 12, 15, backend="cv2"))

@@ -13,8 +13,9 @@
 //                  for every pixel that can be, or can suppress, a keypoint inside the 31-px border
 //   k_orb_nms      3x3 non-maximum suppression (strict), border filter, per-level 256-bin score histogram
 //   k_orb_cut      retainBest(2 * quota) on the FAST score: cutoff score per level from the histogram (ties kept)
-//   k_orb_emit     surviving pixels -> per-level keypoint lists with their Harris response (orb.cpp HarrisResponses: 7x7 block
-//                  of integer Sobel-like gradients, float32 response)
+//   k_orb_emit     surviving pixels -> per-level keypoint lists
+//   k_orb_harris   Harris response of every listed keypoint (orb.cpp HarrisResponses: 7x7 block of integer Sobel-like
+//                  gradients, float32 response), one warp per keypoint
 //   k_orb_select   retainBest(quota) on the Harris response: exact n-th largest float per level by a 4-pass radix select
 //   k_orb_bucket   kept keypoints, scaled to level-0 pixels -> per-bin 64-bit atomicMax of (response, first keypoint)
 //   k_orb_out      ordered scan over the bins -> new points in bin order; k_orb_gather: the whole keypoint list (tests)
@@ -178,37 +179,40 @@ __global__ void __launch_bounds__(256) k_orb_nms(const OrbArgs a)
     if (hv) atomicAdd(a.hist + blockIdx.z * 256 + threadIdx.x, hv);
 }
 
-// KeyPointsFilter::retainBest(keypoints, 2 * featuresNum) on the FAST score: everything >= the n-th largest
-__global__ void k_orb_cut(const OrbArgs a)
+// KeyPointsFilter::retainBest(keypoints, 2 * featuresNum) on the FAST score: everything >= the n-th largest.
+// One CTA per level: histogram into shared memory, one thread scans it.
+__global__ void __launch_bounds__(256) k_orb_cut(const OrbArgs a)
 {
-    const int lv = threadIdx.x;
-    if (lv >= a.n_levels || !a.lv[lv].active) return;
+    __shared__ int s_h[256];
+    const int lv = blockIdx.x;
+    if (!a.lv[lv].active) return;
+    s_h[threadIdx.x] = a.hist[lv * 256 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     const int n = 2 * a.lv[lv].quota;
-    const int *h = a.hist + lv * 256;
     int total = 0;
-    for (int s = 1; s < 256; ++s) total += h[s];
+    for (int s = 1; s < 256; ++s) total += s_h[s];
     int cut = 1;
     if (n == 0) cut = 256;
     else if (total > n) {
         int acc = 0;
-        for (int s = 255; s >= 1; --s) { acc += h[s]; if (acc >= n) { cut = s; break; } }
+        for (int s = 255; s >= 1; --s) { acc += s_h[s]; if (acc >= n) { cut = s; break; } }
     }
     a.cut[lv] = cut;
 }
 
-// orb.cpp HarrisResponses (blockSize 7, HARRIS_K 0.04)
-__device__ __forceinline__ float orb_harris(const uint8_t *img, int pitch, int x, int y)
+// orb.cpp HarrisResponses (blockSize 7, HARRIS_K 0.04): one warp per keypoint, lanes over the 49 block positions
+__device__ __forceinline__ float orb_harris_warp(const uint8_t *img, int pitch, int x, int y, int lane)
 {
     int sa = 0, sb = 0, sc = 0;
-    for (int dy = -3; dy <= 3; ++dy) {
-        const uint8_t *r = img + (size_t)(y + dy) * pitch + x;
-        for (int dx = -3; dx <= 3; ++dx) {
-            const uint8_t *q = r + dx;
-            const int Ix = ((int)q[1] - (int)q[-1]) * 2 + ((int)q[-pitch + 1] - (int)q[-pitch - 1]) + ((int)q[pitch + 1] - (int)q[pitch - 1]);
-            const int Iy = ((int)q[pitch] - (int)q[-pitch]) * 2 + ((int)q[pitch - 1] - (int)q[-pitch - 1]) + ((int)q[pitch + 1] - (int)q[-pitch + 1]);
-            sa += Ix * Ix; sb += Iy * Iy; sc += Ix * Iy;
-        }
+    for (int k = lane; k < 49; k += 32) {
+        const int dy = k / 7 - 3, dx = k % 7 - 3;
+        const uint8_t *q = img + (size_t)(y + dy) * pitch + x + dx;
+        const int Ix = ((int)q[1] - (int)q[-1]) * 2 + ((int)q[-pitch + 1] - (int)q[-pitch - 1]) + ((int)q[pitch + 1] - (int)q[pitch - 1]);
+        const int Iy = ((int)q[pitch] - (int)q[-pitch]) * 2 + ((int)q[pitch - 1] - (int)q[-pitch - 1]) + ((int)q[pitch + 1] - (int)q[-pitch + 1]);
+        sa += Ix * Ix; sb += Iy * Iy; sc += Ix * Iy;
     }
+    sa = __reduce_add_sync(0xffffffffu, sa); sb = __reduce_add_sync(0xffffffffu, sb); sc = __reduce_add_sync(0xffffffffu, sc);
     const float scale = 1.f / ((float)((1 << 2) * 7) * 255.f);
     const float s4 = scale * scale * scale * scale;
     const float fa = (float)sa, fb = (float)sb, fc = (float)sc;
@@ -226,7 +230,19 @@ __global__ void __launch_bounds__(256) k_orb_emit(const OrbArgs a)
     const int idx = atomicAdd(a.count + blockIdx.z, 1);
     if (idx >= L.cap) { *a.overflow = 1; return; }
     L.xy[idx] = ((unsigned)y << 16) | (unsigned)x;
-    L.resp[idx] = orb_harris(L.img, L.pitch, x, y);
+}
+
+__global__ void __launch_bounds__(256) k_orb_harris(const OrbArgs a)
+{
+    const int lv = blockIdx.y, lane = threadIdx.x & 31;
+    const OrbLevel L = a.lv[lv];
+    if (!L.active) return;
+    const int n = min(a.count[lv], L.cap);
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+        const unsigned xy = L.xy[i];
+        const float r = orb_harris_warp(L.img, L.pitch, (int)(xy & 0xFFFFu), (int)(xy >> 16), lane);
+        if (lane == 0) L.resp[i] = r;
+    }
 }
 
 __device__ __forceinline__ unsigned orb_key(float f)
@@ -431,12 +447,13 @@ int vo_orb_launch_d(vo_ctx *ctx, int slot, const float *occ_d, const int *n_occ_
         dim3 g(vo_div_up(cw, 32), vo_div_up(ch, 8), n_levels);
         k_orb_fast<<<g, 256, 0, ctx->stream>>>(a);
         k_orb_nms<<<g, 256, 0, ctx->stream>>>(a);
-        k_orb_cut<<<1, 32, 0, ctx->stream>>>(a);
+        k_orb_cut<<<n_levels, 256, 0, ctx->stream>>>(a);
         k_orb_emit<<<g, 256, 0, ctx->stream>>>(a);
+        k_orb_harris<<<dim3(148, n_levels), 256, 0, ctx->stream>>>(a);
         k_orb_select<<<n_levels, 1024, 0, ctx->stream>>>(a);
         dim3 gb(vo_div_up(a.lv[0].cap, 256), n_levels);
         k_orb_bucket<<<gb, 256, 0, ctx->stream>>>(a);
-        ctx->launches += 6;
+        ctx->launches += 7;
     }
     if (bucket) { k_orb_out<<<1, 1024, 0, ctx->stream>>>(a); ctx->launches++; }
     ctx->launches += 1 + (n_levels - 1);
