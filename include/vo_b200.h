@@ -105,6 +105,11 @@ VO_API int vo_read_rectify_maps(vo_ctx *ctx, int right, float *map_u, float *map
  * stereo_vo.cpp:416-421): H2D of the distorted image, cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) on the device, result
  * becomes the slot's image (pyramid stale). right = 0 / 1 selects the left / right maps. */
 VO_API int vo_upload_image_rectified(vo_ctx *ctx, int slot, int right, const uint8_t *data, int w, int h, size_t step);
+/* Single-camera undistortion for MonoVO with flagDoUndistortion: 1 (mono_vo.cpp:509-513): the map of
+ * Camera::generateImageUndistortMaps (core/visual_odometry/camera.cpp:57-87; D5 = k1 k2 p1 p2 k3) becomes map set 0, so
+ * vo_upload_image_rectified(ctx, slot, 0, ...) = Camera::undistortImage (:163-183) + convertTo(CV_8UC1).  The camera
+ * matrix is unchanged. */
+VO_API int vo_undistort_init(vo_ctx *ctx, const float *K4, const float *D5, int w, int h);
 
 /* ------------------------------------------------------------------ raw pyramidal LK
  * == cv::calcOpticalFlowPyrLK(img[slot0], img[slot1], pts0, pts1, status, err,

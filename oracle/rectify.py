@@ -105,3 +105,27 @@ def remap_linear(img, map_u, map_v):
         return np.where(ok, src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], f32(0)).astype(f32)
     val = ((tap(iy, ix) * w00 + tap(iy, ix + 1) * w01) + tap(iy + 1, ix) * w10) + tap(iy + 1, ix + 1) * w11
     return np.clip(np.rint(val.astype(f32)), 0, 255).astype(np.uint8)
+
+
+def undistort_maps(K4, D5, w, h):
+    """Camera::generateImageUndistortMaps (core/visual_odometry/camera.cpp:57-87): float variables, double literals (the
+    promotions of `2.0 * x * y`, `1.0 + k1 * r2 + ...`, `2.0 * xx` restated)."""
+    f32, f64 = np.float32, np.float64
+    fx, fy, cx, cy = [f32(v) for v in K4]
+    k1, k2, p1, p2, k3 = [f32(v) for v in D5]
+    fxinv, fyinv = f32(f32(1.0) / fx), f32(f32(1.0) / fy)
+    u = np.arange(w, dtype=f32)[None, :].repeat(h, 0)
+    v = np.arange(h, dtype=f32)[:, None].repeat(w, 1)
+    y = ((v - cy).astype(f32) * fyinv).astype(f32)
+    x = ((u - cx).astype(f32) * fxinv).astype(f32)
+    xy2 = ((f64(2.0) * x.astype(f64)) * y.astype(f64)).astype(f32)
+    xx, yy = (x * x).astype(f32), (y * y).astype(f32)
+    r2 = (xx + yy).astype(f32)
+    r4 = (r2 * r2).astype(f32)
+    r6 = (r4 * r2).astype(f32)
+    r_radial = (((f64(1.0) + (k1 * r2).astype(f32).astype(f64)) + (k2 * r4).astype(f32).astype(f64)) + (k3 * r6).astype(f32).astype(f64)).astype(f32)
+    x_dist = (((x * r_radial).astype(f32) + (p1 * xy2).astype(f32)).astype(f32).astype(f64) +
+              f64(p2) * (r2.astype(f64) + f64(2.0) * xx.astype(f64))).astype(f32)
+    y_dist = (((y * r_radial).astype(f32).astype(f64) + f64(p1) * (r2.astype(f64) + f64(2.0) * yy.astype(f64))) +
+              (p2 * xy2).astype(f32).astype(f64)).astype(f32)
+    return (cx + (x_dist * fx).astype(f32)).astype(f32), (cy + (y_dist * fy).astype(f32)).astype(f32)

@@ -145,3 +145,20 @@ def test_mono_vo_deterministic_and_yaml(seq, tmp_path):
     c.close(); d.close()
     with pytest.raises(capi.VoError):
         mvo.MonoVO(yaml_path=str(tmp_path / "missing.yaml"))
+
+
+def test_mono_vo_undistortion_path(seq):
+    """flagDoUndistortion with zero distortion: the map of camera.cpp:57-87 is the identity to float rounding, which the
+    1/32-px quantisation of cv::remap absorbs -- the run must equal the plain one; with real distortion coefficients it runs."""
+    L, _, _ = seq
+    a, b = _make(), _make(D=(0.0, 0.0, 0.0, 0.0, 0.0))
+    for k in range(6):
+        a.trackImage(L[k], 0.1 * k)
+        b.trackImage(L[k], 0.1 * k)
+        assert np.array_equal(a.pose(), b.pose()), k
+    a.close(); b.close()
+    c = _make(D=(-0.05, 0.01, 1e-4, -1e-4, 0.0))
+    for k in range(6):
+        c.trackImage(L[k], 0.1 * k)
+    assert c.frame_info()["n_tracked"] > 100 and np.isfinite(c.pose()).all()
+    c.close()

@@ -60,3 +60,23 @@ def test_maps_against_float64_geometry():
         assert np.abs(m["map_" + name + "v"] - (yd * float(K[1]) + float(K[3]) - 1)).max() < 2e-3
     assert abs(float(m["T_lr_rect"][0, 3]) - np.linalg.norm(t)) < 1e-5 and np.abs(m["T_lr_rect"][1:3, 3]).max() < 1e-5
     assert np.allclose(m["K_rect"], [f_n, f_n, w * 0.5, h * 0.5])
+
+
+def test_mono_undistort_maps_oracle():
+    """Camera::generateImageUndistortMaps (camera.cpp:57-87) restated: equals a float64 evaluation of the radtan model to
+    float rounding, is the identity without distortion, and inverts the distortion for the remap oracle."""
+    w, h = 320, 240
+    K4 = np.array([300.0, 305.0, 160.5, 120.25], np.float32)
+    D5 = np.array([-0.25, 0.06, 3e-4, -2e-4, 0.01], np.float32)
+    mu, mv = orect.undistort_maps(K4, D5, w, h)
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    x, y = (u - K4[2]) / K4[0], (v - K4[3]) / K4[1]
+    r2 = x * x + y * y
+    rad = 1 + D5[0] * r2 + D5[1] * r2 ** 2 + D5[4] * r2 ** 3
+    xd = x * rad + D5[2] * 2 * x * y + D5[3] * (r2 + 2 * x * x)
+    yd = y * rad + D5[2] * (r2 + 2 * y * y) + D5[3] * 2 * x * y
+    assert np.abs(mu - (K4[2] + xd * K4[0])).max() < 2e-3 and np.abs(mv - (K4[3] + yd * K4[1])).max() < 2e-3
+    iu, iv = orect.undistort_maps(K4, np.zeros(5, np.float32), w, h)
+    assert np.abs(iu - u).max() < 1e-3 and np.abs(iv - v).max() < 1e-3
+    img = np.random.default_rng(1).integers(0, 256, (h, w), dtype=np.uint8)
+    assert np.array_equal(orect.remap_linear(img, iu, iv), img)       # 1/32-px quantisation absorbs the float rounding

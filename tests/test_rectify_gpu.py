@@ -49,3 +49,25 @@ def test_rectify_maps_and_remap():
     with pytest.raises(capi.VoError):
         ctx.upload_image_rectified(0, 0, np.zeros((h - 2, w), np.uint8))          # camera.cpp:308 size check
     ctx.close()
+
+
+def test_mono_undistortion_maps_and_image(gpu_ctx):
+    """Camera::generateImageUndistortMaps + undistortImage (camera.cpp:57-87, 163-183) for MonoVO's flagDoUndistortion:
+    the map is bit-identical to the numpy restatement (float / double promotions included), the undistorted image bit-exact
+    with the cv2-pinned remap oracle."""
+    from oracle import rectify as orect
+    w, h = 752, 480
+    K4 = np.array([458.654, 457.296, 367.215, 248.375], np.float32)
+    D5 = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0], np.float32)
+    gpu_ctx_local = capi.Context(device=0, max_w=w, max_h=h, n_slots=2, max_feat=1024)
+    gpu_ctx_local.undistort_init(K4, D5, w, h)
+    mu, mv = gpu_ctx_local.read_rectify_maps(0)
+    ou, ov = orect.undistort_maps(K4, D5, w, h)
+    assert np.array_equal(mu, ou) and np.array_equal(mv, ov)
+    img = synth.textured_image(np.random.default_rng(5), w, h)
+    gpu_ctx_local.upload_image_rectified(0, 0, img)
+    gpu_ctx_local.build_pyramids(np.array([0], np.int32), 1, True)
+    got = gpu_ctx_local.read_pyramid_level(0, 0)[0]
+    assert np.array_equal(got, orect.remap_linear(img, ou, ov))
+    assert np.abs(got.astype(int) - img.astype(int)).mean() > 1.0          # the distortion does move pixels
+    gpu_ctx_local.close()

@@ -145,6 +145,7 @@ def lib():
     L.vo_mono_frame_step.argtypes = [vp, ctypes.POINTER(MonoFrameParams), ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_size_t, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.POINTER(MonoFrameResult)]
     L.vo_rectify_init.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    L.vo_undistort_init.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int]
     L.vo_read_rectify_maps.argtypes = [vp, ctypes.c_int, vp, vp]
     L.vo_upload_image_rectified.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
     L.vo_sampson_distance.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp]
@@ -672,6 +673,12 @@ class Context:
         check(self.h, self.L.vo_rectify_init(self.h, *[_ptr(v) for v in a], int(w), int(h), _ptr(K_rect), _ptr(T_rect)))
         self._rect_wh = (int(w), int(h))
         return K_rect, T_rect
+
+    def undistort_init(self, K4, D5, w, h):
+        """Single-camera undistortion map (camera.cpp:57-87) into map set 0."""
+        K, D = np.ascontiguousarray(K4, np.float32), np.ascontiguousarray(D5, np.float32)
+        check(self.h, self.L.vo_undistort_init(self.h, _ptr(K), _ptr(D), int(w), int(h)))
+        self._rect_wh = (int(w), int(h))
 
     def read_rectify_maps(self, right):
         w, h = self._rect_wh

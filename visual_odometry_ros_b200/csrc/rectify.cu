@@ -56,6 +56,26 @@ __global__ void __launch_bounds__(256) k_rectify_maps(const RectMapArgs a)
     a.map_ru[o] = mu; a.map_rv[o] = mv;
 }
 
+// Camera::generateImageUndistortMaps (core/visual_odometry/camera.cpp:57-87): single-camera undistortion map, no rotation and
+// the same intrinsics.  The reference mixes float variables with double literals (2.0, 1.0): promotions restated.
+__global__ void __launch_bounds__(256) k_undistort_maps(int w, int h, const float4 K, const float k1, const float k2, const float p1,
+                                                        const float p2, const float k3, float *map_u, float *map_v)
+{
+    const int u = blockIdx.x * 32 + (threadIdx.x & 31), v = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (u >= w || v >= h) return;
+    const float fxinv = 1.0f / K.x, fyinv = 1.0f / K.y;
+    const float y = ((float)v - K.w) * fyinv, x = ((float)u - K.z) * fxinv;
+    const float xy2 = (float)((2.0 * (double)x) * (double)y);
+    const float xx = x * x, yy = y * y;
+    const float r2 = xx + yy, r4 = r2 * r2, r6 = r4 * r2;
+    const float r_radial = (float)(((1.0 + (double)(k1 * r2)) + (double)(k2 * r4)) + (double)(k3 * r6));
+    const float x_dist = (float)((double)(x * r_radial + p1 * xy2) + (double)p2 * ((double)r2 + 2.0 * (double)xx));
+    const float y_dist = (float)(((double)(y * r_radial) + (double)p1 * ((double)r2 + 2.0 * (double)yy)) + (double)(p2 * xy2));
+    const size_t o = (size_t)v * w + u;
+    map_u[o] = K.z + x_dist * K.x;
+    map_v[o] = K.w + y_dist * K.y;
+}
+
 __global__ void __launch_bounds__(256)
 k_remap(const uint8_t *__restrict__ src, int w, int h, const float *__restrict__ map_u, const float *__restrict__ map_v, uint8_t *__restrict__ dst)
 {
@@ -183,6 +203,33 @@ extern "C" int vo_upload_image_rectified(vo_ctx *ctx, int slot, int right, const
     const float *mp = (const float *)ctx->d_rect + (right ? 2 : 0) * plane;
     k_remap<<<dim3(vo_div_up(w, 32), vo_div_up(h, 8)), 256, 0, ctx->stream>>>(scratch, w, h, mp, mp + plane,
                                                                              ctx->raw_base + (size_t)slot * ctx->raw_stride);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
+// MonoVO with flagDoUndistortion (mono_vo.cpp:509-513): Camera::undistortImage (camera.cpp:163-183) = cv::remap with the
+// maps of generateImageUndistortMaps (:57-87) + convertTo(CV_8UC1).  Fills map set 0; vo_upload_image_rectified(slot, 0, ...)
+// then undistorts on upload.  D5 = k1 k2 p1 p2 k3 (cvD order, camera.cpp:30-34).
+extern "C" int vo_undistort_init(vo_ctx *ctx, const float *K4, const float *D5, int w, int h)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(K4 && D5, VO_ERR_INVALID_ARG, "null pointer");
+    VO_REQUIRE(w >= 8 && h >= 8 && w <= ctx->max_w && h <= ctx->max_h, VO_ERR_INVALID_ARG, "image larger than the context's max_w x max_h");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t plane = (size_t)w * h;
+    const size_t need = plane * 4 * 4 + plane + 256;
+    if (need > ctx->rect_bytes) {
+        VO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_rect) cudaFree(ctx->d_rect);
+        ctx->d_rect = nullptr; ctx->rect_bytes = 0;
+        VO_CUDA(cudaMalloc(&ctx->d_rect, need));
+        ctx->rect_bytes = need;
+    }
+    float *mp = (float *)ctx->d_rect;
+    ctx->rect_w = w; ctx->rect_h = h;
+    k_undistort_maps<<<dim3(vo_div_up(w, 32), vo_div_up(h, 8)), 256, 0, ctx->stream>>>(w, h, make_float4(K4[0], K4[1], K4[2], K4[3]), D5[0], D5[1],
+                                                                                    D5[2], D5[3], D5[4], mp, mp + plane);
     ctx->launches++;
     VO_CUDA(cudaGetLastError());
     return VO_OK;

@@ -38,8 +38,9 @@ MonoVO::MonoVO(std::string mode, std::string directory_intrinsic)
     p_.width = (int)num("Camera.width", p_.width); p_.height = (int)num("Camera.height", p_.height);
     const char *names[4] = {"fx", "fy", "cx", "cy"};
     for (int i = 0; i < 4; ++i) p_.K[i] = (float)num((std::string("Camera.") + names[i]).c_str(), p_.K[i]);
-    if (num("flagDoUndistortion", 0) != 0)
-        throw std::runtime_error("vo_b200: MonoVO with flagDoUndistortion = 1 is not built (single-camera undistortion maps, camera.cpp:57-87)");
+    p_.do_undistortion = num("flagDoUndistortion", 0) != 0 ? 1 : 0;
+    const char *dn[5] = {"k1", "k2", "p1", "p2", "k3"};               // cvD order, mono_vo.cpp:166-172
+    for (int i = 0; i < 5; ++i) p_.D[i] = (float)num((std::string("Camera.") + dn[i]).c_str(), 0.0);
     p_.thres_error = (float)num("feature_tracker.thres_error", p_.thres_error);
     p_.thres_bidirection = (float)num("feature_tracker.thres_bidirection", p_.thres_bidirection);
     p_.thres_sampson = (float)num("feature_tracker.thres_sampson", p_.thres_sampson);
@@ -66,6 +67,10 @@ void MonoVO::init()
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
+    if (p_.do_undistortion) {
+        const int ru = vo_undistort_init(ctx_, p_.K, p_.D, p_.width, p_.height);
+        if (ru) fail(ctx_, ru);
+    }
 }
 
 MonoVO::~MonoVO() { if (ctx_) vo_ctx_destroy(ctx_); }
@@ -429,12 +434,22 @@ void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
     res.T_wc = T_wc; res.dT01 = dT01; res.dT10 = dT10; res.new_p1 = new_p1_.data(); res.new_p0 = new_p0_.data();
     res.counts = p_.collect_gate_counts ? info_.counts : nullptr;
 
+    const unsigned char *up = img.data;
+    if (p_.do_undistortion) {
+        // mono_vo.cpp:509-513: Camera::undistortImage + convertTo(CV_8UC1), on the device; the step finds the image in its slot
+        const int rr = vo_upload_image_rectified(ctx_, s1, 0, img.data, w, h, img.step);
+        if (rr == VO_ERR_SIZE_MISMATCH) throw std::runtime_error("undistort image: provided image has not the same size as the camera model!\n");   // camera.cpp:166
+        if (rr) fail(ctx_, rr);
+        up = nullptr;
+    }
     bool kf = false;
     if (!prev_) {
         // ---- the very first image (mono_vo.cpp:528-561): extraction only, identity pose, dT10 = [I | (0, 0, -1)]
         int n_det = 0;
-        const int rc0 = vo_upload_image(ctx_, s1, img.data, w, h, img.step);
-        if (rc0) fail(ctx_, rc0);
+        if (up) {
+            const int rc0 = vo_upload_image(ctx_, s1, up, w, h, img.step);
+            if (rc0) fail(ctx_, rc0);
+        }
         const int rc = vo_detect_bucketed(ctx_, s1, nullptr, 0, p_.n_bins_u, p_.n_bins_v, p_.det_edge, p_.det_min_score, new_p1_.data(), std::max(nb, 1), &n_det);
         if (rc) fail(ctx_, rc);
         const int base = newLandmarks(n_det, new_p1_.data(), *fr);
@@ -464,7 +479,7 @@ void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
         res.index = out_idx_.data(); res.pts1 = out_p1_.data();
         fp.init_mode = initialised_ ? 0 : 1;
         const auto t_step = Clock::now();
-        const int rc = vo_mono_frame_step(ctx_, &fp, s0, s1, img.data, w, h, img.step, n, in_p0_.data(), in_X_.data(), in_flags_.data(),
+        const int rc = vo_mono_frame_step(ctx_, &fp, s0, s1, up, w, h, img.step, n, in_p0_.data(), in_X_.data(), in_flags_.data(),
                                           pv.Twc, pv.dT01, &res);
         if (rc == VO_ERR_MODE) throw std::runtime_error(vo_last_error(ctx_));      // "calcPose5PointsAlgorithm() is failed." (:590 / :940)
         if (rc) fail(ctx_, rc);

@@ -72,6 +72,10 @@ public:
         // reference runs; the yaml constructor selects it with feature_extractor.thres_fastscore, mono_vo.cpp:36-40)
         int detector = VO_DETECTOR_HARRIS_SCHARR;
         int thres_fastscore = 20;
+        // flagDoUndistortion (mono_vo.cpp:509-513): undistort every image on the device with the map of camera.cpp:57-87;
+        // D = k1 k2 p1 p2 k3 (camera.cpp:30-34).  The camera matrix is unchanged
+        int do_undistortion = 0;
+        float D[5] = {0, 0, 0, 0, 0};
     };
 
     MonoVO(std::string mode, std::string directory_intrinsic);     // mono_vo.cpp:11-55 (yaml via a minimal parser)
