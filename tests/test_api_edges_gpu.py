@@ -127,3 +127,49 @@ def test_stereo_vo_from_reference_yaml(frames, tmp_path):
     assert vu.frame_info()["n_tracked"] > 100
     assert np.abs(vu.pose()[:3, 3] - gt[:3, 3]).max() < 0.1
     vu.close()
+
+
+def test_new_entry_points_edge_cases():
+    """Degenerate inputs of the round's new entry points: loud, specific statuses instead of garbage."""
+    ctx = capi.Context(device=0, max_w=W, max_h=H, n_slots=2, max_feat=1024)
+    K = synth.small_K()
+    # five-point: all correspondences identical -> every minimal sample is degenerate -> no model (VO_ERR_MODE, mono_vo.cpp:590)
+    p = np.tile(np.array([[100.0, 80.0]], np.float32), (40, 1))
+    with pytest.raises(capi.VoError) as e:
+        ctx.pose_5point(p, p, K, 1.0)
+    assert e.value.status == capi.VO_ERR_MODE and "calcPose5PointsAlgorithm" in str(e.value)
+    # pure rotation (no translation): a model exists, the call must not fail or return NaNs
+    sc = synth.two_view_scene(seed=3, n=200, t=(0.0, 0.0, 1e-9), outlier_frac=0.0)
+    try:
+        r = ctx.pose_5point(sc["pts0"], sc["pts1"], sc["K4"], 1.0)
+        assert np.isfinite(r["R10"]).all() and np.isfinite(r["t10"]).all()
+    except capi.VoError as err:
+        assert err.status == capi.VO_ERR_MODE
+    # K-orb on an image whose every level is thinner than twice the 31-px border: no keypoints, no crash
+    tiny = np.random.default_rng(0).integers(0, 256, (60, 200), dtype=np.uint8)
+    ctx.upload_image(0, tiny)
+    P, R, O = ctx.orb_detect(0, 20)
+    assert len(P) == 0
+    ctx.set_detector("orb", 20)
+    assert len(ctx.detect_bucketed(0, np.zeros((0, 2), np.float32), 8, 4)) == 0
+    ctx.set_detector("harris")
+    # mono init step with fewer than five features
+    img = np.random.default_rng(1).integers(0, 256, (H, W), dtype=np.uint8)
+    ctx.upload_image(0, img)
+    with pytest.raises(capi.VoError) as e:
+        ctx.mono_frame_step(0, 1, img, np.array([[50, 50], [60, 60]], np.float32), None, None, None, np.eye(4, dtype=np.float32), None, K,
+                            21, 3, 60.0, 0.5, 1000.0, 5.0, False, thres_5p=1.0, init_mode=True)
+    assert e.value.status == capi.VO_ERR_INVALID_ARG
+    # epipolar distances with a degenerate (zero) fundamental matrix: NaN, like the reference's 0/0, but no error
+    d = ctx.epipolar_distance(sc["pts0"], sc["pts1"], F10=np.zeros((3, 3), np.float32))
+    assert np.isnan(d).all()
+    ctx.close()
+
+
+def test_mono_vo_rejects_wrong_image_size():
+    from visual_odometry_ros_b200 import mono_vo as mvo
+    vo = mvo.MonoVO(mvo.make_parameters(W, H, synth.small_K(), max_level=3, n_bins_u=16, n_bins_v=8, D=(0.0,) * 5))
+    with pytest.raises(capi.VoError) as e:
+        vo.trackImage(np.zeros((H + 2, W), np.uint8))
+    assert "same size as the camera model" in str(e.value)
+    vo.close()
