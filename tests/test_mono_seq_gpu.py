@@ -84,6 +84,7 @@ def test_mono_vo_class_next_to_oracle(seq, detector):
         assert np.abs(vo.frame_pose(j)[:3, 3] - Po[j][:3, 3]).max() <= (2e-4 if in_step else 2e-2), j
     assert same_ids >= 8 and n_kf >= 3 and n_lba >= 2
     assert vo.launch_count > 0
+    assert vo.stats_consistent()          # incremental keyframe statistics == the reference's full refresh (mono_vo.cpp:1142-1152)
     vo.close(); ctx.close()
 
 

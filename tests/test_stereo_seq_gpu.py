@@ -151,6 +151,7 @@ def test_stereo_vo_class_free_running(seq, detector):
               f"dt={np.abs(Twc_g[:3, 3] - Twc_o[:3, 3]).max():.2e} lba={fi['lba_points']}/{fi['lba_obs']}")
     assert same_ids >= 3
     assert vo.launch_count > 0
+    assert vo.stats_consistent()          # incremental keyframe statistics == the reference's full refresh (stereo_vo.cpp:814-822)
     vo.close()
 
 
@@ -187,4 +188,5 @@ def test_full_size_sequence_properties():
         assert np.linalg.norm(a.pose()[:3, 3] - gt[:3, 3]) <= 0.01 * dist + 0.01, k          # <= 1 % translation drift
     assert n_kf >= 5 and n_lba >= 3
     assert len(a.keyframe_poses()) == n_kf
+    assert a.stats_consistent() and b.stats_consistent()
     a.close(); b.close()

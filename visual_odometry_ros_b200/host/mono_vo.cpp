@@ -110,6 +110,7 @@ int MonoVO::newLandmarks(int k, const float *pts, const FrameRec &f)
     memcpy(&lm_first_px_[(size_t)base * 2], pts, (size_t)k * 8);
     memcpy(&lm_last_px_[(size_t)base * 2], pts, (size_t)k * 8);
     lm_kf_obs_.resize(n);
+    lm_kf_slots_.resize(n);
     return base;
 }
 
@@ -166,6 +167,9 @@ void MonoVO::addKeyframe(const FrameRecPtr &f)
     if ((int)window_.size() == p_.n_max_keyframes_in_window) window_.pop_front();
     window_.push_back(f);
     for (int id : f->lm_ids) lm_kf_obs_[id].push_back({f->id, lm_last_px_[2 * (size_t)id], lm_last_px_[2 * (size_t)id + 1]});   // observations.back()
+    const int kf_index = (int)all_keyframes_.size() - 1;
+    f->kf_index = kf_index;
+    for (size_t i = 0; i < f->lm_ids.size(); ++i) lm_kf_slots_[f->lm_ids[i]].push_back({kf_index, (int)i});
 }
 
 // triangulateDLT of the candidates, one device call per distinct frame of the first point (T10 = T1w * Tw0)
@@ -221,6 +225,7 @@ int MonoVO::reconstructInitial(const FrameRec &f)
         if (X0[3 * j + 2] > 0.f) {
             to_world(frames_[f0[j]]->Twc, &X0[3 * j], &lm_X_[(size_t)cand[j] * 3]);
             lm_tri_[cand[j]] = 1;
+            dirty_.push_back(cand[j]);
             ++n;
         }
     return n;
@@ -252,6 +257,7 @@ int MonoVO::reconstructKeyframe(const FrameRec &f)
         if (a[2] > 0.f && b[2] > 0.f) {
             to_world(frames_[f0[j]]->Twc, a, &lm_X_[(size_t)cand[j] * 3]);
             lm_tri_[cand[j]] = 1;
+            dirty_.push_back(cand[j]);
             ++n;
         }
     }
@@ -359,6 +365,7 @@ void MonoVO::localBundleAdjustment()
         const int id = lms[j];
         memcpy(&lm_X_[(size_t)id * 3], Xf, 12);
         lm_tri_[id] = 1;
+        dirty_.push_back(id);
         if (std::sqrt(Xf[0] * Xf[0] + Xf[1] * Xf[1] + Xf[2] * Xf[2]) <= 3000) lm_bundled_[id] = 1;
         else lm_alive_[id] = 0;
     }
@@ -369,15 +376,22 @@ void MonoVO::localBundleAdjustment()
 void MonoVO::pushStats(const FrameRec &f, bool keyframe)
 {
     if (keyframe) {
+        // mono_vo.cpp:1142-1152 refreshes the pose and every map point of EVERY keyframe ever made, each time.  Same values, incrementally:
+        // the new keyframe in full, the poses of the window (the only ones the LBA moves), and the points that changed
+        // in this frame (reconstruction, LBA) wherever they sit -- the cost no longer grows with the sequence length.
         stat_.stats_keyframe.emplace_back();
-        for (size_t j = 0; j < stat_.stats_keyframe.size() && j < all_keyframes_.size(); ++j) {   // mono_vo.cpp:1142-1152
-            const FrameRec &kf = *all_keyframes_[j];
-            rowmajor_to_pose(kf.Twc, stat_.stats_keyframe[j].Twc);
-            PointVec &mp = stat_.stats_keyframe[j].mappoints;
-            mp.resize(kf.lm_ids.size());
-            for (size_t i = 0; i < kf.lm_ids.size(); ++i)
-                for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)kf.lm_ids[i] * 3 + r];
+        if (stat_.stats_keyframe.size() == all_keyframes_.size()) {
+            const FrameRec &nk = *all_keyframes_.back();
+            PointVec &mp = stat_.stats_keyframe.back().mappoints;
+            mp.resize(nk.lm_ids.size());
+            for (size_t i = 0; i < nk.lm_ids.size(); ++i)
+                for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)nk.lm_ids[i] * 3 + r];
+            for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_keyframe[kf->kf_index].Twc);
+            for (int id : dirty_)
+                for (const KfSlot &sl : lm_kf_slots_[id])
+                    for (int r = 0; r < 3; ++r) stat_.stats_keyframe[sl.kf_index].mappoints[sl.slot](r) = lm_X_[(size_t)id * 3 + r];
         }
+        dirty_.clear();              // points that change on a non-keyframe (first-frame / initial reconstruction) wait for the next keyframe
     }
     stat_.stats_frame.emplace_back();
     AlgorithmStatistics::FrameStatistics &sf = stat_.stats_frame.back();
@@ -399,6 +413,21 @@ void MonoVO::pushStats(const FrameRec &f, bool keyframe)
     stat_.stats_landmark.back().n_new = info_.n_new;
     stat_.stats_landmark.back().n_final = (int)f.lm_ids.size();
     stat_.stats_execution.emplace_back();
+}
+
+// The reference's full refresh, recomputed and compared with the incrementally maintained statistics (test hook).
+bool MonoVO::statsConsistent() const
+{
+    if (stat_.stats_keyframe.size() != all_keyframes_.size()) return false;
+    for (size_t j = 0; j < all_keyframes_.size(); ++j) {
+        const FrameRec &kf = *all_keyframes_[j];
+        const auto &sk = stat_.stats_keyframe[j];
+        if (sk.mappoints.size() != kf.lm_ids.size()) return false;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) if (sk.Twc(r, c) != kf.Twc[r * 4 + c]) return false;
+        for (size_t i = 0; i < kf.lm_ids.size(); ++i)
+            for (int r = 0; r < 3; ++r) if (sk.mappoints[i](r) != lm_X_[(size_t)kf.lm_ids[i] * 3 + r]) return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------ the step
@@ -587,6 +616,7 @@ extern "C" int vo_mvo_tracks(const vo_mvo *s, int cap, int *ids, float *pts)
     if (pts) memcpy(pts, s->vo->currentPts().data(), (size_t)n * 8);
     return (int)id.size();
 }
+extern "C" int vo_mvo_stats_consistent(const vo_mvo *s) { return s ? (s->vo->statsConsistent() ? 1 : 0) : 0; }
 extern "C" long long vo_mvo_launch_count(const vo_mvo *s) { return s ? s->vo->launchCount() : 0; }
 // layout check for language bindings: 0 = sizeof(Parameters), 1 = sizeof(FrameInfo)
 extern "C" int vo_mvo_struct_size(int which) { return which == 0 ? (int)sizeof(MonoVO::Parameters) : (int)sizeof(MonoVO::FrameInfo); }

@@ -101,11 +101,13 @@ public:
     int framePose(int frame_id, float *T_wc16) const;   // current value (the local BA moves keyframe poses), row-major
     int numFrames() const { return (int)frames_.size(); }
     long long launchCount() const;
+    bool statsConsistent() const;       // stats_keyframe equals the reference's full refresh (test hook)
 
 private:
     struct KfObs { int kf_id; float x, y; };
     struct FrameRec {
         int id = 0;
+        int kf_index = -1;                  // position in all_keyframes_ / stats_keyframe
         bool is_keyframe = false;
         float Twc[16], Tcw[16], dT01[16], dT10[16];
         std::vector<float> pts;             // interleaved x, y (dropped once the frame is neither previous nor a keyframe)
@@ -138,6 +140,11 @@ private:
     std::vector<uint8_t> lm_tri_, lm_alive_, lm_bundled_;
     std::vector<int> lm_last_frame_, lm_first_frame_, lm_age_;
     std::vector<std::vector<KfObs>> lm_kf_obs_;
+    // where a landmark's point sits in stats_keyframe[k].mappoints, and the landmarks whose point changed in this frame:
+    // the per-keyframe refresh of the reference (all keyframes x all their points, every keyframe) becomes incremental
+    struct KfSlot { int kf_index, slot; };
+    std::vector<std::vector<KfSlot>> lm_kf_slots_;
+    std::vector<int> dirty_;
     std::vector<FrameRecPtr> frames_;      // all frames (poses stay readable: parallax and reconstruction use them)
     FrameRecPtr prev_;
     std::deque<FrameRecPtr> window_;
@@ -160,6 +167,7 @@ VO_API int vo_mvo_frame_pose(const vo_mvo *s, int frame_id, float *T_wc16);     
 VO_API int vo_mvo_frame_info(const vo_mvo *s, MonoVO::FrameInfo *out);
 VO_API int vo_mvo_tracks(const vo_mvo *s, int cap, int *ids, float *pts);        // returns the count
 VO_API long long vo_mvo_launch_count(const vo_mvo *s);
+VO_API int vo_mvo_stats_consistent(const vo_mvo *s);                             // 1 if stats_keyframe == the reference's full refresh
 VO_API const char *vo_mvo_last_error(void);
 VO_API int vo_mvo_struct_size(int which);                                       // 0 Parameters, 1 FrameInfo (binding layout check)
 }

@@ -121,6 +121,7 @@ int StereoVO::newLandmarks(int k, int frame_id)
     lm_tri_.resize(base + k, 0); lm_alive_.resize(base + k, 1); lm_bundled_.resize(base + k, 0);
     lm_last_frame_.resize(base + k, frame_id);
     lm_kf_obs_.resize(base + k);
+    lm_kf_slots_.resize(base + k);
     return base;
 }
 
@@ -150,6 +151,9 @@ void StereoVO::addKeyframe(const FrameRecPtr &f)
     const size_t n = f->lm_ids.size();
     for (size_t i = 0; i < n; ++i) lm_kf_obs_[f->lm_ids[i]].push_back({f->id, 0, f->pts_l[2 * i], f->pts_l[2 * i + 1]});
     for (size_t i = 0; i < n; ++i) lm_kf_obs_[f->lm_ids[i]].push_back({f->id, 1, f->pts_r[2 * i], f->pts_r[2 * i + 1]});
+    const int kf_index = (int)all_keyframes_.size() - 1;
+    f->kf_index = kf_index;
+    for (size_t i = 0; i < n; ++i) lm_kf_slots_[f->lm_ids[i]].push_back({kf_index, (int)i});
 }
 
 void StereoVO::reconstruct(FrameRec &f, int n_first)
@@ -165,6 +169,7 @@ void StereoVO::reconstruct(FrameRec &f, int n_first)
         const int id = f.lm_ids[i];
         memcpy(&lm_X_[(size_t)id * 3], &Xw[(size_t)i * 3], 12);      // Landmark::set3DPoint
         lm_tri_[id] = 1;
+        dirty_.push_back(id);
         ++info_.n_recon;
     }
 }
@@ -278,6 +283,7 @@ void StereoVO::localBundleAdjustment()
         const int id = lms[j];
         memcpy(&lm_X_[(size_t)id * 3], Xf, 12);
         lm_tri_[id] = 1;
+        dirty_.push_back(id);
         if (std::sqrt(Xf[0] * Xf[0] + Xf[1] * Xf[1] + Xf[2] * Xf[2]) <= 3000) lm_bundled_[id] = 1;
         else lm_alive_[id] = 0;
     }
@@ -288,15 +294,22 @@ void StereoVO::localBundleAdjustment()
 void StereoVO::pushStats(const FrameRec &f, bool keyframe)
 {
     if (keyframe) {
+        // stereo_vo.cpp:814-822 refreshes the pose and every map point of EVERY keyframe ever made, each time.  Same values, incrementally:
+        // the new keyframe in full, the poses of the window (the only ones the LBA moves), and the points that changed
+        // in this frame (reconstruction, LBA) wherever they sit -- the cost no longer grows with the sequence length.
         stat_.stats_keyframe.emplace_back();
-        for (size_t j = 0; j < stat_.stats_keyframe.size() && j < all_keyframes_.size(); ++j) {   // stereo_vo.cpp:814-822
-            const FrameRec &kf = *all_keyframes_[j];
-            rowmajor_to_pose(kf.Twc, stat_.stats_keyframe[j].Twc);
-            PointVec &mp = stat_.stats_keyframe[j].mappoints;
-            mp.resize(kf.lm_ids.size());
-            for (size_t i = 0; i < kf.lm_ids.size(); ++i)
-                for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)kf.lm_ids[i] * 3 + r];
+        if (stat_.stats_keyframe.size() == all_keyframes_.size()) {
+            const FrameRec &nk = *all_keyframes_.back();
+            PointVec &mp = stat_.stats_keyframe.back().mappoints;
+            mp.resize(nk.lm_ids.size());
+            for (size_t i = 0; i < nk.lm_ids.size(); ++i)
+                for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)nk.lm_ids[i] * 3 + r];
+            for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_keyframe[kf->kf_index].Twc);
+            for (int id : dirty_)
+                for (const KfSlot &sl : lm_kf_slots_[id])
+                    for (int r = 0; r < 3; ++r) stat_.stats_keyframe[sl.kf_index].mappoints[sl.slot](r) = lm_X_[(size_t)id * 3 + r];
         }
+        dirty_.clear();              // points that change on a non-keyframe (first-frame / initial reconstruction) wait for the next keyframe
     }
     stat_.stats_frame.emplace_back();
     rowmajor_to_pose(f.Twc, stat_.stats_frame.back().Twc);                       // :979-980
@@ -306,6 +319,21 @@ void StereoVO::pushStats(const FrameRec &f, bool keyframe)
     stat_.stats_landmark.back().n_new = info_.n_new;
     stat_.stats_landmark.back().n_final = (int)f.lm_ids.size();
     stat_.stats_execution.emplace_back();
+}
+
+// The reference's full refresh, recomputed and compared with the incrementally maintained statistics (test hook).
+bool StereoVO::statsConsistent() const
+{
+    if (stat_.stats_keyframe.size() != all_keyframes_.size()) return false;
+    for (size_t j = 0; j < all_keyframes_.size(); ++j) {
+        const FrameRec &kf = *all_keyframes_[j];
+        const auto &sk = stat_.stats_keyframe[j];
+        if (sk.mappoints.size() != kf.lm_ids.size()) return false;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) if (sk.Twc(r, c) != kf.Twc[r * 4 + c]) return false;
+        for (size_t i = 0; i < kf.lm_ids.size(); ++i)
+            for (int r = 0; r < 3; ++r) if (sk.mappoints[i](r) != lm_X_[(size_t)kf.lm_ids[i] * 3 + r]) return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------ the step
@@ -496,6 +524,7 @@ extern "C" int vo_svo_keyframe_poses(const vo_svo *s, int cap, float *T)
         for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[k * 16 + r * 4 + c] = kf[k].Twc(r, c);
     return (int)kf.size();
 }
+extern "C" int vo_svo_stats_consistent(const vo_svo *s) { return s ? (s->vo->statsConsistent() ? 1 : 0) : 0; }
 extern "C" long long vo_svo_launch_count(const vo_svo *s) { return s ? s->vo->launchCount() : 0; }
 // layout check for language bindings: 0 = sizeof(Parameters), 1 = sizeof(FrameInfo)
 extern "C" int vo_svo_struct_size(int which) { return which == 0 ? (int)sizeof(StereoVO::Parameters) : (int)sizeof(StereoVO::FrameInfo); }

@@ -97,11 +97,13 @@ public:
     const std::vector<float> &currentPtsLeft() const;
     const std::vector<float> &currentPtsRight() const;
     long long launchCount() const;
+    bool statsConsistent() const;       // stats_keyframe equals the reference's full refresh (test hook)
 
 private:
     struct KfObs { int kf_id; uint8_t right; float x, y; };
     struct FrameRec {
         int id = 0;
+        int kf_index = -1;                  // position in all_keyframes_ / stats_keyframe
         float Twc[16], Tcw[16], dT01[16];
         std::vector<float> pts_l, pts_r;    // interleaved x, y
         std::vector<int> lm_ids;
@@ -128,6 +130,11 @@ private:
     std::vector<uint8_t> lm_tri_, lm_alive_, lm_bundled_;
     std::vector<int> lm_last_frame_;
     std::vector<std::vector<KfObs>> lm_kf_obs_;
+    // where a landmark's point sits in stats_keyframe[k].mappoints, and the landmarks whose point changed in this frame:
+    // the per-keyframe refresh of the reference (all keyframes x all their points, every keyframe) becomes incremental
+    struct KfSlot { int kf_index, slot; };
+    std::vector<std::vector<KfSlot>> lm_kf_slots_;
+    std::vector<int> dirty_;
     FrameRecPtr prev_;
     std::deque<FrameRecPtr> window_;
     std::vector<FrameRecPtr> all_keyframes_;
@@ -150,6 +157,7 @@ VO_API int vo_svo_frame_info(const vo_svo *s, StereoVO::FrameInfo *out);
 VO_API int vo_svo_tracks(const vo_svo *s, int cap, int *ids, float *pts_l, float *pts_r);   // returns the count
 VO_API int vo_svo_keyframe_poses(const vo_svo *s, int cap, float *T_wc16);                    // returns the count
 VO_API long long vo_svo_launch_count(const vo_svo *s);
+VO_API int vo_svo_stats_consistent(const vo_svo *s);                             // 1 if stats_keyframe == the reference's full refresh
 VO_API const char *vo_svo_last_error(void);
 VO_API int vo_svo_struct_size(int which);                                       // 0 Parameters, 1 FrameInfo (binding layout check)
 }

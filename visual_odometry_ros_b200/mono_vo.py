@@ -50,6 +50,7 @@ def host_lib():
     H.vo_mvo_frame_pose.argtypes = [vp, ctypes.c_int, vp]
     H.vo_mvo_frame_info.argtypes = [vp, ctypes.POINTER(FrameInfo)]
     H.vo_mvo_tracks.argtypes = [vp, ctypes.c_int, vp, vp]
+    H.vo_mvo_stats_consistent.argtypes = [vp]
     H.vo_mvo_launch_count.argtypes = [vp]
     H.vo_mvo_launch_count.restype = ctypes.c_longlong
     H.vo_mvo_last_error.restype = ctypes.c_char_p
@@ -140,6 +141,9 @@ class MonoVO:
         ids, pts = np.zeros(n, np.int32), np.zeros((n, 2), np.float32)
         self.H.vo_mvo_tracks(self.h, n, ids.ctypes.data_as(vp), pts.ctypes.data_as(vp))
         return ids, pts
+
+    def stats_consistent(self):
+        return bool(self.H.vo_mvo_stats_consistent(self.h))
 
     @property
     def launch_count(self):

@@ -50,6 +50,7 @@ def host_lib():
     H.vo_svo_frame_info.argtypes = [vp, ctypes.POINTER(FrameInfo)]
     H.vo_svo_tracks.argtypes = [vp, ctypes.c_int, vp, vp, vp]
     H.vo_svo_keyframe_poses.argtypes = [vp, ctypes.c_int, vp]
+    H.vo_svo_stats_consistent.argtypes = [vp]
     H.vo_svo_launch_count.argtypes = [vp]
     H.vo_svo_launch_count.restype = ctypes.c_longlong
     H.vo_svo_last_error.restype = ctypes.c_char_p
@@ -139,6 +140,9 @@ class StereoVO:
         T = np.zeros((n, 4, 4), np.float32)
         self.H.vo_svo_keyframe_poses(self.h, n, T.ctypes.data_as(vp))
         return T
+
+    def stats_consistent(self):
+        return bool(self.H.vo_svo_stats_consistent(self.h))
 
     @property
     def launch_count(self):
