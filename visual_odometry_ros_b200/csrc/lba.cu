@@ -453,25 +453,39 @@ k_lba_build(const LbaDev d, int apply_update)
 }
 
 // ------------------------------------------------------------------ k_lba_reduce
-// Fixed-order (tile 0, 1, ...) sums of the per-tile partial systems, one thread per entry, coalesced across entries.
-// (Inside the single solve CTA this reduction was a 100-microsecond chain of dependent L2 loads per iteration.)
+// Sums of the per-tile partial systems in a FIXED order: eight lanes per entry, lane g adds the tiles g, g + 8, ... in
+// sequence (independent loads in flight), then the eight partials are added in lane order.  Coalesced across entries.
+// (Inside the single solve CTA this reduction was a 100-microsecond chain of dependent L2 loads per iteration; one thread
+// per entry over 133 tiles still took 17 us.)
+#define LBA_RED_G 8
 __global__ void __launch_bounds__(256) k_lba_reduce(const LbaDev d)
 {
     const int n = d.n6, ncol = n + 1, nS = n * ncol, nA = d.n_opt * LBA_NA;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nS + nA + 1) return;
-    const double *src; size_t stride;
-    if (e < nS) { src = d.s_part + e; stride = (size_t)nS; }
-    else if (e < nS + nA) { src = d.a_part + (e - nS); stride = (size_t)nA; }
-    else { src = d.err_part; stride = 1; }
-    double acc = 0.0;
-    int t = 0;
-    for (; t + 4 <= d.n_tiles; t += 4) {
-        const double v0 = src[(size_t)t * stride], v1 = src[(size_t)(t + 1) * stride], v2 = src[(size_t)(t + 2) * stride], v3 = src[(size_t)(t + 3) * stride];
-        acc += v0; acc += v1; acc += v2; acc += v3;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    // entries vary fastest across the 32 / LBA_RED_G = 4 ... keep an entry's lanes in one warp: e = warp-local mapping
+    const int warp = gid >> 5, lane = gid & 31;
+    const int e = warp * (32 / LBA_RED_G) + (lane % (32 / LBA_RED_G)), g = lane / (32 / LBA_RED_G);
+    const bool act = e < nS + nA + 1;
+    const double *src = d.err_part; size_t stride = 1;
+    if (act) {
+        if (e < nS) { src = d.s_part + e; stride = (size_t)nS; }
+        else if (e < nS + nA) { src = d.a_part + (e - nS); stride = (size_t)nA; }
     }
-    for (; t < d.n_tiles; ++t) acc += src[(size_t)t * stride];
-    d.red[e] = acc;
+    double acc = 0.0;
+    if (act) {
+        int t = g;
+        for (; t + 3 * LBA_RED_G < d.n_tiles; t += 4 * LBA_RED_G) {
+            const double v0 = src[(size_t)t * stride], v1 = src[(size_t)(t + LBA_RED_G) * stride], v2 = src[(size_t)(t + 2 * LBA_RED_G) * stride],
+                         v3 = src[(size_t)(t + 3 * LBA_RED_G) * stride];
+            acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; t < d.n_tiles; t += LBA_RED_G) acc += src[(size_t)t * stride];
+    }
+    // lane order g = 0, 1, ..., 7 (lanes of one entry are 4 apart)
+    double tot = __shfl_sync(0xffffffffu, acc, lane % (32 / LBA_RED_G));
+#pragma unroll
+    for (int k = 1; k < LBA_RED_G; ++k) tot += __shfl_sync(0xffffffffu, acc, (lane % (32 / LBA_RED_G)) + k * (32 / LBA_RED_G));
+    if (act && g == 0) d.red[e] = tot;
 }
 
 // ------------------------------------------------------------------ k_lba_solve (one CTA)
@@ -809,7 +823,7 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     if (trace) { evs.resize(2 * p->max_iter + 1); for (auto &e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], ctx->stream); }
     for (int it = 0; it < p->max_iter; ++it) {
         k_lba_build<<<n_tiles, LBA_THREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
-        k_lba_reduce<<<vo_div_up(n6 * (n6 + 1) + No * LBA_NA + 1, 256), 256, 0, ctx->stream>>>(d);
+        k_lba_reduce<<<vo_div_up((n6 * (n6 + 1) + No * LBA_NA + 1) * LBA_RED_G, 256), 256, 0, ctx->stream>>>(d);
         if (trace) cudaEventRecord(evs[2 * it + 1], ctx->stream);
         k_lba_solve<<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
         if (trace) cudaEventRecord(evs[2 * it + 2], ctx->stream);
