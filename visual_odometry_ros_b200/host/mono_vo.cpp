@@ -166,7 +166,11 @@ void MonoVO::addKeyframe(const FrameRecPtr &f)
     all_keyframes_.push_back(f);
     if ((int)window_.size() == p_.n_max_keyframes_in_window) window_.pop_front();
     window_.push_back(f);
-    for (int id : f->lm_ids) lm_kf_obs_[id].push_back({f->id, lm_last_px_[2 * (size_t)id], lm_last_px_[2 * (size_t)id + 1]});   // observations.back()
+    for (int id : f->lm_ids) {
+        auto &v = lm_kf_obs_[id];
+        if (v.empty()) { v.reserve(4); lm_kf_slots_[id].reserve(4); }              // one allocation instead of the 1-2-4 growth
+        v.push_back({f->id, lm_last_px_[2 * (size_t)id], lm_last_px_[2 * (size_t)id + 1]});   // observations.back()
+    }
     const int kf_index = (int)all_keyframes_.size() - 1;
     f->kf_index = kf_index;
     for (size_t i = 0; i < f->lm_ids.size(); ++i) lm_kf_slots_[f->lm_ids[i]].push_back({kf_index, (int)i});
@@ -275,12 +279,15 @@ void MonoVO::localBundleAdjustment()
     std::vector<int> fidx_tab((size_t)(window_.back()->id - id0 + 1), -1);
     for (int k = 0; k < nf; ++k) fidx_tab[window_[k]->id - id0] = k;
     auto fidx_of = [&](int kf_id) { const int r = kf_id - id0; return (r >= 0 && r < (int)fidx_tab.size()) ? fidx_tab[r] : -1; };
-    std::vector<int> lmset;
+    std::vector<int> &lmset = lba_lmset_;
+    lmset.clear();
     {
-        std::vector<uint8_t> seen(lm_tri_.size(), 0);
+        // stamp instead of a cleared flag array: no O(all landmarks) memset per keyframe
+        lm_seen_stamp_.resize(lm_tri_.size(), 0);
+        const int stamp = ++seen_stamp_;
         for (const auto &fr : window_)
             for (int id : fr->lm_ids)
-                if (!seen[id] && lm_tri_[id] && lm_alive_[id]) { seen[id] = 1; lmset.push_back(id); }
+                if (lm_seen_stamp_[id] != stamp && lm_tri_[id] && lm_alive_[id]) { lm_seen_stamp_[id] = stamp; lmset.push_back(id); }
     }
     double Twj_ref[16], Tjw_ref[16];
     for (int i = 0; i < 12; ++i) Twj_ref[i] = window_[0]->Twc[i];
@@ -293,26 +300,29 @@ void MonoVO::localBundleAdjustment()
     }
     Tjw_ref[15] = 1;
     const double pose_scale = 10.0, inv_scale = 1.0 / pose_scale;
-    std::vector<int> lms, obs_ptr(1, 0), obs_frame;
-    std::vector<double> points, obs_px;
+    // packing buffers live in the object: a few MB that would otherwise be mmap'ed, page-faulted and unmapped per keyframe
+    std::vector<int> &lms = lba_lms_, &obs_ptr = lba_obs_ptr_, &obs_frame = lba_obs_frame_;
+    std::vector<double> &points = lba_points_, &obs_px = lba_obs_px_;
+    lms.clear(); obs_ptr.assign(1, 0); obs_frame.clear(); points.clear(); obs_px.clear();
     for (int id : lmset) {
-        int cnt = 0;
-        for (const KfObs &o : lm_kf_obs_[id]) if (fidx_of(o.kf_id) >= 0) ++cnt;
-        if (cnt < 2) continue;                                                     // THRES_MINIMUM_SEEN
-        const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
-        for (int r = 0; r < 3; ++r)
-            points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
-        lms.push_back(id);
+        // one pass: append the window observations, roll back if the landmark has fewer than two (THRES_MINIMUM_SEEN)
+        const size_t o0 = obs_frame.size();
         for (const KfObs &o : lm_kf_obs_[id]) {
             const int fk = fidx_of(o.kf_id);
             if (fk < 0) continue;
             obs_frame.push_back(fk);
             obs_px.push_back(o.x); obs_px.push_back(o.y);
         }
+        if (obs_frame.size() - o0 < 2) { obs_frame.resize(o0); obs_px.resize(2 * o0); continue; }
+        const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
+        for (int r = 0; r < 3; ++r)
+            points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
+        lms.push_back(id);
         obs_ptr.push_back((int)obs_frame.size());
     }
     if (lms.empty()) return;
-    std::vector<uint8_t> obs_right(obs_frame.size(), 0);
+    std::vector<uint8_t> &obs_right = lba_obs_right_;
+    obs_right.assign(obs_frame.size(), 0);
     std::vector<double> poses((size_t)nf * 16);
     for (int k = 0; k < nf; ++k) {
         double Tjw[16];
@@ -332,7 +342,9 @@ void MonoVO::localBundleAdjustment()
     for (int i = 0; i < 4; ++i) { pr.K_l[i] = p_.K[i]; pr.K_r[i] = p_.K[i]; }
     for (int i = 0; i < 16; ++i) pr.T_lr[i] = (i % 5 == 0) ? 1.0 : 0.0;
     pr.is_stereo = 0; pr.huber = 0.5; pr.lambda = 0.00001; pr.max_iter = 10;
-    std::vector<double> poses_out(poses.size()), points_out(points.size()), avg(pr.max_iter);
+    std::vector<double> &poses_out = lba_poses_out_, &points_out = lba_points_out_;
+    poses_out.resize(poses.size()); points_out.resize(points.size());
+    std::vector<double> avg(pr.max_iter);
     int ok = 0;
     info_.ms_lba_pack = ms_since(t_pack);
     const auto t_solve = Clock::now();

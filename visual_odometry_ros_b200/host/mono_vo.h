@@ -145,6 +145,11 @@ private:
     struct KfSlot { int kf_index, slot; };
     std::vector<std::vector<KfSlot>> lm_kf_slots_;
     std::vector<int> dirty_;
+    // local-BA packing scratch (kept across keyframes)
+    std::vector<int> lm_seen_stamp_, lba_lmset_, lba_lms_, lba_obs_ptr_, lba_obs_frame_;
+    std::vector<uint8_t> lba_obs_right_;
+    std::vector<double> lba_points_, lba_obs_px_, lba_poses_out_, lba_points_out_;
+    int seen_stamp_ = 0;
     std::vector<FrameRecPtr> frames_;      // all frames (poses stay readable: parallax and reconstruction use them)
     FrameRecPtr prev_;
     std::deque<FrameRecPtr> window_;
