@@ -623,9 +623,10 @@ int vo_5pt_launch_d(vo_ctx *ctx, const float *pts0_d, const float *pts1_d, int n
     if (n_hyp <= 0) n_hyp = 1024;
     VO_REQUIRE(n_hyp <= (1 << 20), VO_ERR_INVALID_ARG, "too many hypotheses");
     const size_t a = 256;
-    const size_t o_q = 0, o_E = o_q + ((size_t)n * 32 + a - 1) / a * a, o_ns = o_E + (size_t)n_hyp * 720, o_b = o_ns + ((size_t)n_hyp * 4 + a - 1) / a * a;
-    const size_t o_P = o_b + a, o_bits = o_P + (sizeof(FpPose) + a - 1) / a * a, o_Xc = o_bits + ((size_t)n + a - 1) / a * a;
-    const int rc = fp_scratch(ctx, o_Xc + (size_t)n * 48);
+    const int n_cap = n > 8192 ? n : 8192;      // scratch sized for at least 8192 correspondences: no regrowth inside a sequence
+    const size_t o_q = 0, o_E = o_q + ((size_t)n_cap * 32 + a - 1) / a * a, o_ns = o_E + (size_t)n_hyp * 720, o_b = o_ns + ((size_t)n_hyp * 4 + a - 1) / a * a;
+    const size_t o_P = o_b + a, o_bits = o_P + (sizeof(FpPose) + a - 1) / a * a, o_Xc = o_bits + ((size_t)n_cap + a - 1) / a * a;
+    const int rc = fp_scratch(ctx, o_Xc + (size_t)n_cap * 48);
     if (rc) return rc;
     uint8_t *s = (uint8_t *)ctx->d_fp;
     FpDev d;

@@ -67,6 +67,12 @@ void MonoVO::init()
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
+    {   // allocate the five-point scratch and load its kernels now, not inside the initialisation frame
+        float q0[16], q1[16], R[9], t[3];
+        uint8_t m[8];
+        for (int i = 0; i < 8; ++i) { q0[2 * i] = 10.f + 37.f * i; q0[2 * i + 1] = 20.f + 11.f * (i % 3); q1[2 * i] = q0[2 * i] + 1.f + 0.3f * i; q1[2 * i + 1] = q0[2 * i + 1] + 0.5f; }
+        (void)vo_pose_5point(ctx_, q0, q1, 8, p_.K, p_.thres_5p_error, p_.n_hypotheses, p_.seed, R, t, nullptr, m, nullptr, nullptr);
+    }
     if (p_.do_undistortion) {
         const int ru = vo_undistort_init(ctx_, p_.K, p_.D, p_.width, p_.height);
         if (ru) fail(ctx_, ru);
