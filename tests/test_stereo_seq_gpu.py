@@ -47,12 +47,15 @@ def test_detect_bucketed_bit_exact(seq):
     ctx.close()
 
 
-def test_frame_step_sequence_teacher_forced(seq):
+@pytest.mark.parametrize("detector", ["harris", "orb"])
+def test_frame_step_sequence_teacher_forced(seq, detector):
+    """Every frame gets the oracle's previous state; detector "orb" = the reference's extractor (oracle side: cv2.ORB itself)."""
     L, R, T = seq
     K, Tlr = synth.small_K(), synth.kitti_T_lr()
-    prm = osvo.default_params(n_bins_u=NB_U, n_bins_v=NB_V, kf_trans=2.0)
+    prm = osvo.default_params(n_bins_u=NB_U, n_bins_v=NB_V, kf_trans=2.0, detector=detector, fast_threshold=20)
     vo = osvo.StereoVOOracle(W, H, K, K, Tlr, prm)
     ctx = capi.Context(device=0, max_w=W, max_h=H, n_slots=4, max_feat=4096)
+    ctx.set_detector(detector, 20)
     agree_idx, total_idx = 0, 0
     px_ok = px_tot = frames_cmp = frames_new_equal = 0
     n_kf = 0
