@@ -8,7 +8,8 @@
 //   k_5pt_solve   one thread per hypothesis: 5 distinct correspondences from a counter-based hash of (seed, hypothesis),
 //                 Nister's minimal solver -- null space of the 5x9 epipolar system, the ten cubic constraints
 //                 det(E) = 0 and 2 E E^T E - tr(E E^T) E = 0 as a 10x20 matrix, Gauss-Jordan, the 3x3 polynomial matrix in z,
-//                 its degree-10 determinant, real roots by monotone-interval safeguarded Newton -- up to 10 essential matrices
+//                 its degree-10 determinant, real roots by monotone-interval safeguarded Newton on [-1, 1] (polynomial and its
+//                 reversal) -- up to 10 essential matrices
 //   k_5pt_score   one block per hypothesis: the error OpenCV's RANSAC uses, (x1^T E x0)^2 / (|E x0|_xy^2 + |E^T x1|_xy^2)
 //                 on normalised coordinates against (thres / mean focal)^2, for every candidate over ALL correspondences;
 //                 the best (count, first hypothesis, first candidate) is kept with one 64-bit atomicMax
@@ -121,40 +122,28 @@ __device__ __forceinline__ void horner11(const double (&d)[11], double x, double
     for (int i = 9; i >= 0; --i) { dp = fma(dp, x, p); p = fma(p, x, d[i]); }
 }
 
-// All real roots of a polynomial of degree <= 10: the roots of the k-th derivative split the line into intervals on
-// which the (k-1)-th derivative is monotone, so every sign change brackets exactly one root (safeguarded Newton).
+// Real roots of a polynomial of degree <= 10 inside [-1, 1]: the roots of the k-th derivative split the interval into pieces
+// on which the (k-1)-th derivative is monotone, so every sign change brackets exactly one root (safeguarded Newton).
 // 32 hypotheses run in lockstep in a warp: the level's coefficients sit in registers and every evaluation is the same
-// fully unrolled 10-step Horner pair, so lanes with different degrees / root counts share one instruction stream.
-__device__ int real_roots(const double *c_in, int deg, double *roots)
+// fully unrolled 10-step Horner pair, so lanes with different root counts share one instruction stream.
+__device__ int roots_unit(const double *c, double *roots, bool closed)
 {
-    double c[11];
-    double cmax = 0.0;
-    for (int i = 0; i <= deg; ++i) cmax = fmax(cmax, fabs(c_in[i]));
-    if (!(cmax > 0.0) || !isfinite(cmax)) return 0;
-    for (int i = 0; i <= 10; ++i) c[i] = i <= deg ? c_in[i] / cmax : 0.0;
-    while (deg > 0 && fabs(c[deg]) < 1e-13) { c[deg] = 0.0; --deg; }
-    if (deg == 0) return 0;
     double ra[10], rb[10];
     int na = 0;
-    for (int k = deg - 1; k >= 0; --k) {
-        const int m = deg - k;
+    for (int k = 9; k >= 0; --k) {
         double d[11];
 #pragma unroll
         for (int i = 0; i <= 10; ++i) d[i] = (i + k <= 10) ? c[min(i + k, 10)] * c_dfact[k][i] : 0.0;
-        const double lead = c[deg] * c_dfact[k][m];
-        double R = 0.0;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) R = fmax(R, i < m ? fabs(d[i] / lead) : 0.0);
-        R += 1.0;
         int nb = 0;
-        double lo = -R, flo, tmp;
+        double lo = -1.0, flo, tmp;
         horner11(d, lo, flo, tmp);
+        if (flo == 0.0 && (closed || k > 0)) rb[nb++] = lo;
         for (int j = 0; j <= na; ++j) {
-            const double hi = j < na ? ra[j] : R;
+            const double hi = j < na ? ra[j] : 1.0;
             double fhi;
             horner11(d, hi, fhi, tmp);
             if (fhi == 0.0) {
-                if (nb < 10) rb[nb++] = hi;
+                if (nb < 10 && (j < na || closed || k > 0)) rb[nb++] = hi;
             } else if (flo != 0.0 && ((flo < 0.0) != (fhi < 0.0))) {
                 // safeguarded Newton inside the bracket (bisection whenever the Newton step leaves it or stalls)
                 double a = lo, b = hi;
@@ -165,9 +154,9 @@ __device__ int real_roots(const double *c_in, int deg, double *roots)
                     horner11(d, x, p, dp);
                     if (p == 0.0) break;
                     if ((p < 0.0) == neg_a) a = x; else b = x;
-                    const double tol = 4.0e-16 * fmax(1.0, fabs(x));
+                    const double tol = 4.0e-16;                                        // |x| <= 1
                     const double step = dp != 0.0 ? p / dp : 0.0;
-                    if ((dp != 0.0 && fabs(step) <= tol) || b - a <= tol) break;        // converged (x is one end of the bracket)
+                    if ((dp != 0.0 && fabs(step) <= tol) || b - a <= tol) break;       // converged (x is one end of the bracket)
                     const double xn = x - step;
                     const bool newton_ok = dp != 0.0 && xn > a && xn < b && fabs(2.0 * p) <= fabs(dx_old * dp);
                     dx_old = dx;
@@ -185,6 +174,24 @@ __device__ int real_roots(const double *c_in, int deg, double *roots)
     }
     for (int j = 0; j < na; ++j) roots[j] = ra[j];
     return na;
+}
+
+// All real roots of a degree-10 polynomial: those in [-1, 1] directly, the others as reciprocals of the roots of the
+// reversed polynomial in (-1, 1).  Both searches live on a bounded interval: no Cauchy-bound brackets to bisect through.
+__device__ int real_roots(const double *c_in, int deg, double *roots)
+{
+    double c[11], cr[11];
+    double cmax = 0.0;
+    for (int i = 0; i <= deg; ++i) cmax = fmax(cmax, fabs(c_in[i]));
+    if (!(cmax > 0.0) || !isfinite(cmax)) return 0;
+    for (int i = 0; i <= 10; ++i) c[i] = i <= deg ? c_in[i] / cmax : 0.0;
+    for (int i = 0; i <= 10; ++i) cr[i] = c[10 - i];
+    int n = roots_unit(c, roots, true);
+    double w[10];
+    const int nw = roots_unit(cr, w, false);
+    for (int j = 0; j < nw && n < 10; ++j)
+        if (fabs(w[j]) > 1e-12 && fabs(w[j]) < 1.0) roots[n++] = 1.0 / w[j];           // w = 0 <=> a root at infinity (degree < 10)
+    return n;
 }
 
 // Nister's five-point minimal solver.  q[i] = (x0, y0, x1, y1) with x1^T E x0 = 0.  E_out[s][9] row-major, Frobenius
