@@ -53,6 +53,10 @@ extern "C" int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int 
     if (!out) return VO_ERR_INVALID_ARG;
     *out = nullptr;
     if (max_w < 1 || max_h < 1 || n_slots < 0 || max_feat < 0) return VO_ERR_INVALID_ARG;
+    // Load every kernel of the library when CUDA comes up instead of at its first launch: lazy loading costs tens of
+    // milliseconds inside the first frames of a sequence.  Only effective if this is the first CUDA use of the process
+    // (a node that links nothing else on CUDA); an explicit CUDA_MODULE_LOADING in the environment wins.
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
         cudaGetLastError();

@@ -67,6 +67,14 @@ void MonoVO::init()
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
+    {   // landmark tables: room for 2^19 landmarks before the first reallocation (see StereoVO::init)
+        const size_t cap = (size_t)1 << 19;
+        lm_X_.reserve(cap * 3); lm_first_px_.reserve(cap * 2); lm_last_px_.reserve(cap * 2); lm_last_parallax_.reserve(cap);
+        lm_tri_.reserve(cap); lm_alive_.reserve(cap); lm_bundled_.reserve(cap);
+        lm_last_frame_.reserve(cap); lm_first_frame_.reserve(cap); lm_age_.reserve(cap);
+        lm_kf_obs_.reserve(cap); lm_kf_slots_.reserve(cap); lm_seen_stamp_.reserve(cap);
+        frames_.reserve(1 << 16);
+    }
     {   // allocate the five-point scratch and load its kernels now, not inside the initialisation frame
         float q0[16], q1[16], R[9], t[3];
         uint8_t m[8];

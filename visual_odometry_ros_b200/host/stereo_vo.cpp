@@ -90,6 +90,12 @@ void StereoVO::init()
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
+    {   // landmark tables: room for 2^19 landmarks (several hundred frames) before the first reallocation, which would
+        // otherwise move hundreds of thousands of per-landmark vectors inside a frame (a ~10 ms latency spike)
+        const size_t cap = (size_t)1 << 19;
+        lm_X_.reserve(cap * 3); lm_tri_.reserve(cap); lm_alive_.reserve(cap); lm_bundled_.reserve(cap); lm_last_frame_.reserve(cap);
+        lm_kf_obs_.reserve(cap); lm_kf_slots_.reserve(cap); lm_seen_stamp_.reserve(cap);
+    }
     memcpy(K_use_l_, p_.K_l, 16); memcpy(K_use_r_, p_.K_r, 16); memcpy(T_lr_use_, p_.T_lr, 64);
     if (p_.do_undistortion) {
         // stereo_vo.cpp:414-428: rectified images, the rectified camera for both sides, the rectified extrinsics
