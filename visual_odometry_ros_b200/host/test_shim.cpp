@@ -75,6 +75,21 @@ int main()
     CHECK(throws_with([&] { MaskVec mm; ft.trackWithScale(img0, cv::Mat(), cv::Mat(), img1, pts0, scale, bad, mm); }, "pts_track.size() != pts0.size()"),
           "trackWithScale size error text");
 
+    // ---- FeatureExtractor (reference API; cv::ORB keypoints restated on the device)
+    {
+        FeatureExtractor fe;
+        fe.initParams(img0.cols, img0.rows, 16, 8, 20, 5);
+        fe.resetWeightBin();
+        PixelVec e0, e1;
+        fe.extractORBwithBinning_fast(img0, e0, true);
+        CHECK(e0.size() > 20 && e0.size() <= 16 * 8, "bucketed ORB extraction");
+        fe.updateWeightBin(e0);
+        fe.extractORBwithBinning_fast(img0, e1, true);
+        CHECK(e1.size() < e0.size(), "occupied buckets are skipped");
+        FeatureExtractor fe2;
+        CHECK(throws_with([&] { PixelVec q; fe2.extractORBwithBinning_fast(img0, q, true); }, "initParams"), "extractor without initParams");
+    }
+
     // ---- MotionEstimator
     const float fx = 718.856f, fy = 718.856f, cx = 607.19f, cy = 185.21f, base = 0.537f;
     PointVec X; PixelVec pl, pr;

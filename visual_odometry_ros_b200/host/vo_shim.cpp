@@ -28,7 +28,7 @@ vo_ctx *shared_context(int min_w, int min_h)
     if (g_ctx) { vo_ctx_destroy(g_ctx); g_ctx = nullptr; }
     g_w = std::max(min_w, std::max(g_w, 1920));
     g_h = std::max(min_h, std::max(g_h, 1200));
-    const int rc = vo_ctx_create(0, g_w, g_h, 4, 8192, nullptr, &g_ctx);
+    const int rc = vo_ctx_create(0, g_w, g_h, 5, 8192, nullptr, &g_ctx);      // slots 0-3: FeatureTracker, slot 4: FeatureExtractor
     if (rc != VO_OK) throw_status(nullptr, rc, nullptr);
     return g_ctx;
 }
@@ -182,6 +182,37 @@ void FeatureTracker::trackWithScale(const cv::Mat &img0, const cv::Mat & /*du0*/
     if (rc == VO_ERR_NAN) throw std::runtime_error("ax ay nan");                                        // feature_tracker.cpp:414
     if (rc) throw_status(ctx, rc, nullptr);
     pack_mask(m, mask_valid);
+}
+
+// ------------------------------------------------------------------------------ FeatureExtractor
+FeatureExtractor::FeatureExtractor() {}
+FeatureExtractor::~FeatureExtractor() {}
+
+void FeatureExtractor::initParams(int n_cols, int n_rows, int n_bins_u, int n_bins_v, int THRES_FAST, int /*radius*/)
+{
+    n_cols_ = n_cols; n_rows_ = n_rows; n_bins_u_ = n_bins_u; n_bins_v_ = n_bins_v; thres_fast_ = THRES_FAST;
+    occupied_.clear();
+}
+void FeatureExtractor::resetWeightBin() { occupied_.clear(); }                           // WeightBin::reset (feature_extractor.cpp:62-64)
+void FeatureExtractor::updateWeightBin(const PixelVec &pts) { occupied_ = pts; }         // reset + update (:94-98)
+
+void FeatureExtractor::extractORBwithBinning_fast(const cv::Mat &img, PixelVec &pts_extracted, bool /*flag_nonmax*/)
+{
+    // the reference ignores the argument and buckets on its member flag_nonmax_ = true (:211-282)
+    if (img.empty()) throw std::runtime_error("vo_b200: empty image");
+    if (n_bins_u_ <= 0 || n_bins_v_ <= 0) throw std::runtime_error("vo_b200: FeatureExtractor::initParams has not been called");
+    vo_ctx *ctx = shared_context(img.cols, img.rows);
+    int rc = vo_upload_image(ctx, 4, img.data, img.cols, img.rows, img.step);
+    if (rc) throw_status(ctx, rc, nullptr);
+    rc = vo_set_detector(ctx, VO_DETECTOR_ORB, thres_fast_);
+    if (rc) throw_status(ctx, rc, nullptr);
+    const int cap = n_bins_u_ * n_bins_v_;
+    pts_extracted.resize(cap);
+    int n = 0;
+    rc = vo_detect_bucketed(ctx, 4, occupied_.empty() ? nullptr : pix(occupied_), (int)occupied_.size(), n_bins_u_, n_bins_v_, 31, 0,
+                            pix(pts_extracted), cap, &n);
+    if (rc) throw_status(ctx, rc, nullptr);
+    pts_extracted.resize(n);
 }
 
 // ------------------------------------------------------------------------------ MotionEstimator

@@ -42,6 +42,23 @@ private:
     int next_slot_ = 0;
 };
 
+// core/visual_odometry/feature_extractor.h:144-200: the bucketed extractor the VO classes call (initParams, resetWeightBin,
+// updateWeightBin, extractORBwithBinning_fast; feature_extractor.cpp:26-98, 211-282).  The keypoints are cv::ORB::detect's,
+// restated on the device (K-orb, bit-exact with cv2.ORB).  The per-bucket variant extractORBwithBinning / the descriptor
+// functions / suppressCenterBins have no caller on the VO path and are not provided.
+class FeatureExtractor {
+public:
+    FeatureExtractor();
+    ~FeatureExtractor();
+    void initParams(int n_cols, int n_rows, int n_bins_u, int n_bins_v, int THRES_FAST, int radius);
+    void updateWeightBin(const PixelVec &pts);
+    void resetWeightBin();
+    void extractORBwithBinning_fast(const cv::Mat &img, PixelVec &pts_extracted, bool flag_nonmax);
+private:
+    int n_cols_ = 0, n_rows_ = 0, n_bins_u_ = 0, n_bins_v_ = 0, thres_fast_ = 20;
+    PixelVec occupied_;
+};
+
 // core/visual_odometry/motion_estimator.h:107-147 (pose-only part) and
 // standalone/motion_estimator/motion_estimator.h:22-35 (scalar-intrinsics overloads)
 class MotionEstimator {
