@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -56,7 +57,8 @@ extern "C" int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int 
     // Load every kernel of the library when CUDA comes up instead of at its first launch: lazy loading costs tens of
     // milliseconds inside the first frames of a sequence.  Only effective if this is the first CUDA use of the process
     // (a node that links nothing else on CUDA); an explicit CUDA_MODULE_LOADING in the environment wins.
-    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    static std::once_flag eager_once;       // once, before the first CUDA call of the library (setenv is not re-entrant)
+    std::call_once(eager_once, [] { setenv("CUDA_MODULE_LOADING", "EAGER", 0); });
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
         cudaGetLastError();
