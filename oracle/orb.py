@@ -24,11 +24,13 @@ _RING = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, 
 
 
 def level_sizes(w, h, n_levels=8, scale_factor=1.2):
-    """orb.cpp detectAndCompute: layerScale = (float)pow(scaleFactor, level), sz = cvRound(dim / scale)."""
+    """orb.cpp detectAndCompute: the level size is cvRound(dim / scale) with the DOUBLE scale pow(scaleFactor, level)
+    (pinned on 129 x 97: 129 / 1.2 = 107.5 -> 108, where the float scale 1.2f would give 107); the keypoint coordinates are
+    multiplied by layerScale = (float)pow(scaleFactor, level)."""
     out = []
     for lv in range(n_levels):
-        s = f32(np.power(np.float64(scale_factor), np.float64(lv)))
-        out.append((int(np.rint(np.float32(w) / s)), int(np.rint(np.float32(h) / s)), s))
+        sd = np.power(np.float64(scale_factor), np.float64(lv))
+        out.append((int(np.rint(np.float64(w) / sd)), int(np.rint(np.float64(h) / sd)), f32(sd)))
     return out
 
 

@@ -22,10 +22,11 @@ def images():
     rng = np.random.default_rng(0)
     L, _, _ = synth.stereo_sequence(2, synth.SMALL_W, synth.SMALL_H, synth.small_K(), seed=3103, device="cpu")
     return {"corridor": L[0], "noise": rng.integers(0, 256, (200, 300), dtype=np.uint8),
+            "tie_size": rng.integers(0, 256, (97, 129), dtype=np.uint8),     # 129 / 1.2 = 107.5: the level size rounds in double
             "texture": np.ascontiguousarray(synth.textured_image(np.random.default_rng(3))[:300, :700])}
 
 
-@pytest.mark.parametrize("name", ["corridor", "noise", "texture"])
+@pytest.mark.parametrize("name", ["corridor", "noise", "texture", "tie_size"])
 def test_orb_stages_bit_exact_against_cv2(name):
     img = images()[name]
     h, w = img.shape
@@ -44,7 +45,7 @@ def test_orb_stages_bit_exact_against_cv2(name):
         ref = sorted((k.octave, np.float32(k.pt[1]), np.float32(k.pt[0]), np.float32(k.response)) for k in reference_orb(thr).detect(img, None))
         P, R, O = orb.detect(img, thr)
         got = sorted((int(o), np.float32(p[1]), np.float32(p[0]), np.float32(r)) for p, r, o in zip(P, R, O))
-        assert len(ref) > 500 and ref == got, (thr, len(ref), len(got))
+        assert len(ref) > 100 and ref == got, (thr, len(ref), len(got))
 
 
 def test_orb_bucketing_follows_reference():

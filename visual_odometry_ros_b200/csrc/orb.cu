@@ -393,9 +393,12 @@ int vo_orb_launch_d(vo_ctx *ctx, int slot, const float *occ_d, const int *n_occ_
     size_t off = 0, o_img[ORB_LEVELS], o_sc[ORB_LEVELS], o_nms[ORB_LEVELS], o_xy[ORB_LEVELS], o_rs[ORB_LEVELS];
     for (int l = 0; l < n_levels; ++l) {
         OrbLevel &L = a.lv[l];
-        L.scale = (float)std::pow(scale_factor, (double)l);
-        L.w = l ? (int)lrintf((float)S.w / L.scale) : S.w;
-        L.h = l ? (int)lrintf((float)S.h / L.scale) : S.h;
+        // size: cvRound(dim / scale) with the DOUBLE scale (129 / 1.2 = 107.5 -> 108; the float 1.2f would give 107);
+        // keypoint coordinates: multiplied by layerScale = (float)pow(scaleFactor, level)
+        const double sd = std::pow(scale_factor, (double)l);
+        L.scale = (float)sd;
+        L.w = l ? (int)lrint((double)S.w / sd) : S.w;
+        L.h = l ? (int)lrint((double)S.h / sd) : S.h;
         L.pitch = l ? L.w : S.desc.lv[0].pitch;
         L.active = (L.w > 2 * edge && L.h > 2 * edge) ? 1 : 0;
         const size_t px = (size_t)L.w * L.h;
