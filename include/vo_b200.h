@@ -146,7 +146,10 @@ VO_API int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int slot1,
  * imgs0/imgs1 are arrays of n_pairs host image pointers (CV_8UC1, w x h, row pitch `step`;
  * pinned memory makes the copies asynchronous; a NULL entry keeps the slot's current image),
  * pts0 / pts_track / mask_inout are [n_pairs][n].  One H2D per image, batched kernels, one
- * D2H of the results, one synchronisation. with_prior != 0 selects trackWithPrior. */
+ * D2H of the results, one synchronisation. with_prior != 0 selects trackWithPrior.
+ * Pairs whose slots are all distinct are pipelined in chunks (image DMA on a copy stream, chunks alternating between two
+ * compute streams).  A batch that reuses a slot across pairs (e.g. a chain slots1[i] == slots0[i+1] with imgs0[i+1] == NULL)
+ * is detected and processed strictly in order on the context's stream: same results, no overlap. */
 VO_API int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1,
                       const uint8_t *const *imgs0, const uint8_t *const *imgs1, int w, int h,
                       size_t step, const float *pts0, int n, int window_size, int max_pyr_lvl,
@@ -175,6 +178,36 @@ VO_API int vo_pose_gn_stereo(vo_ctx *ctx, const float *X, const float *pts_l1, c
                       const float *K_l4, const float *K_r4, const float *T_lr,
                       float thres_reproj_outlier, float *T01_inout, uint8_t *mask_inlier,
                       int *success, int *iters_out);
+/* Accumulation mode of the pose-only GN (and of the frame steps that run it).
+ * VO_POSE_FAST (default): per-point rows in the reference's FP32 operation order, JtWJ / mJtWr / err summed in FP64 by a
+ *   fixed tree and rounded once.  More accurate than the reference's sums, but the reference's stop test
+ *   `delta_err < 1e-7` (motion_estimator.cpp:1044,1063) fires when ITS sequential FP32 error sum repeats bit for bit, so
+ *   the stop iteration can differ by one or two and the poses then differ by the size of the last updates.
+ * VO_POSE_STRICT: the 28 sums are accumulated sequentially in FP32 in point order, exactly like
+ *   motion_estimator.cpp:720-810 / :925-1040 -- same iterates, same stop iteration, same pose as the reference's
+ *   arithmetic; costs the latency of a 4N-link dependent add chain per iteration (about 16 us at N = 2000).
+ * VO_POSE_NO_EARLY_STOP (only the _ex entry points): ignore the stop test and run max_iter iterations. */
+#define VO_POSE_FAST 0
+#define VO_POSE_STRICT 1
+#define VO_POSE_NO_EARLY_STOP 2
+VO_API int vo_set_pose_mode(vo_ctx *ctx, int flags);   /* VO_POSE_FAST or VO_POSE_STRICT; used by every non-_ex pose call */
+VO_API int vo_get_pose_mode(const vo_ctx *ctx);
+/* _ex: explicit flags (VO_POSE_STRICT | VO_POSE_NO_EARLY_STOP), max_iter (0 = the reference's 100) and an optional
+ * per-iteration trace [max_iter][24] = {T10 after the update (16, row-major), err_curr, delta_xi (6), delta_err}
+ * (rows past the executed iterations are zero). */
+VO_API int vo_pose_gn_mono_ex(vo_ctx *ctx, const float *X, const float *pts1, int n, float fx, float fy,
+                       float cx, float cy, int thres_reproj_outlier, int standalone_variant,
+                       float *R01_inout, float *t01_inout, uint8_t *mask_inlier, int *success,
+                       int *iters_out, int flags, int max_iter, float *trace);
+VO_API int vo_pose_gn_stereo_ex(vo_ctx *ctx, const float *X, const float *pts_l1, const float *pts_r1, int n,
+                         const float *K_l4, const float *K_r4, const float *T_lr,
+                         float thres_reproj_outlier, float *T01_inout, uint8_t *mask_inlier,
+                         int *success, int *iters_out, int flags, int max_iter, float *trace);
+VO_API int vo_pose_gn_stereo_batch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, const float *X_d,
+                                 const float *pts_l1_d, const float *pts_r1_d, const float *K_l4,
+                                 const float *K_r4, const float *T_lr, float thres_reproj_outlier,
+                                 float *T01_inout_d, uint8_t *mask_inlier_d, int *success_d,
+                                 int *iters_d, int flags, int max_iter, float *trace_d);
 /* Batched device-resident variant: n_prob independent problems, problem p owns points
  * [offsets[p], offsets[p+1]).  T01_inout_d: [n_prob][16]. One CTA per problem. */
 VO_API int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, const float *X_d,

@@ -209,9 +209,21 @@ static int finish_iteration(float *H, float *g, float *T10, float err_curr, floa
 /* Stereo. X n*3, pl/pr n*2, K = fx,fy,cx,cy, T_lr / T01 row-major 4x4 (T01 in-out).
  * trace (nullable): MAX_ITER x 24 floats {T10 after update (16), err, dxi(6), delta_err}.
  * Returns is_success; *iters_out = number of iterations executed. */
+int orc_pose_gn_stereo_ex(const float *X, const float *pl, const float *pr, int n, const float *Kl, const float *Kr,
+                          const float *T_lr, float thres_reproj_outlier, float *T01, uint8_t *mask, int *iters_out,
+                          float *trace, int max_iter, int no_early_stop);
 int orc_pose_gn_stereo(const float *X, const float *pl, const float *pr, int n, const float *Kl, const float *Kr,
                        const float *T_lr, float thres_reproj_outlier, float *T01, uint8_t *mask, int *iters_out,
                        float *trace)
+{
+    return orc_pose_gn_stereo_ex(X, pl, pr, n, Kl, Kr, T_lr, thres_reproj_outlier, T01, mask, iters_out, trace, MAX_ITER, 0);
+}
+
+/* _ex: max_iter <= MAX_ITER iterations; no_early_stop = 1 ignores the stop test (test-only: fixed-point and
+ * iterate-by-iterate comparisons with the kernel). */
+int orc_pose_gn_stereo_ex(const float *X, const float *pl, const float *pr, int n, const float *Kl, const float *Kr,
+                          const float *T_lr, float thres_reproj_outlier, float *T01, uint8_t *mask, int *iters_out,
+                          float *trace, int max_iter, int no_early_stop)
 {
     float T_rl[16];
     orc_inverse_se3_f(T_lr, T_rl);
@@ -222,7 +234,8 @@ int orc_pose_gn_stereo(const float *X, const float *pl, const float *pr, int n, 
     float T10[16];
     orc_inverse_se3_f(T01, T10); /* :903-904: explicit R^T, -R^T t */
     int iter = 0;
-    for (; iter < MAX_ITER; ++iter) {
+    if (max_iter <= 0 || max_iter > MAX_ITER) max_iter = MAX_ITER;
+    for (; iter < max_iter; ++iter) {
         float H[36] = {0}, g[6] = {0};
         float err_curr = 0.f;
         float inv_npts = 1.0f / (float)n;
@@ -261,7 +274,7 @@ int orc_pose_gn_stereo(const float *X, const float *pl, const float *pr, int n, 
         err_curr *= (inv_npts * 0.5f);
         err_curr = sqrtf(err_curr);
         int stop = finish_iteration(H, g, T10, err_curr, &err_prev, trace, iter);
-        if (stop) { ++iter; break; }
+        if (stop && !no_early_stop) { ++iter; break; }
     }
     if (iters_out) *iters_out = iter;
     if (!is_nan_mat(T10)) { orc_inverse_se3_f(T10, T01); return 1; }
@@ -271,8 +284,18 @@ int orc_pose_gn_stereo(const float *X, const float *pl, const float *pr, int n, 
 /* Mono. variant 0 = core (weighted y-row adds w*ry^2 to err, motion_estimator.cpp:794-799),
  *       variant 1 = standalone (adds ry^2, standalone/.../motion_estimator.cpp:135).
  * R01 (3x3 row-major) and t01 in-out. thres is an int (motion_estimator.h:117). */
+int orc_pose_gn_mono_ex(const float *X, const float *p1, int n, float fx, float fy, float cx, float cy, int thres,
+                        float *R01, float *t01, uint8_t *mask, int variant, int *iters_out, float *trace, int max_iter,
+                        int no_early_stop);
 int orc_pose_gn_mono(const float *X, const float *p1, int n, float fx, float fy, float cx, float cy, int thres,
                      float *R01, float *t01, uint8_t *mask, int variant, int *iters_out, float *trace)
+{
+    return orc_pose_gn_mono_ex(X, p1, n, fx, fy, cx, cy, thres, R01, t01, mask, variant, iters_out, trace, MAX_ITER, 0);
+}
+
+int orc_pose_gn_mono_ex(const float *X, const float *p1, int n, float fx, float fy, float cx, float cy, int thres,
+                        float *R01, float *t01, uint8_t *mask, int variant, int *iters_out, float *trace, int max_iter,
+                        int no_early_stop)
 {
     const float THRES_REPROJ_ERROR = (float)thres;
     float T01[16] = {0}, T10[16];
@@ -281,7 +304,8 @@ int orc_pose_gn_mono(const float *X, const float *p1, int n, float fx, float fy,
     orc_inverse4_f(T01, T10); /* :700 general Matrix4f::inverse() */
     float err_prev = 1e10f;
     int iter = 0;
-    for (; iter < MAX_ITER; ++iter) {
+    if (max_iter <= 0 || max_iter > MAX_ITER) max_iter = MAX_ITER;
+    for (; iter < max_iter; ++iter) {
         float H[36] = {0}, g[6] = {0};
         float err_curr = 0.f;
         float inv_npts = 1.0f / (float)n;
@@ -311,7 +335,7 @@ int orc_pose_gn_mono(const float *X, const float *p1, int n, float fx, float fy,
         }
         err_curr *= (inv_npts * 0.5f);
         int stop = finish_iteration(H, g, T10, err_curr, &err_prev, trace, iter);
-        if (stop) { ++iter; break; }
+        if (stop && !no_early_stop) { ++iter; break; }
     }
     if (iters_out) *iters_out = iter;
     if (!is_nan_mat(T10)) {

@@ -20,6 +20,7 @@ VO_ERR_MODE = -5
 VO_ERR_NO_DEVICE = -6
 VO_ERR_LARGE_UPDATE = -7
 VO_KLT_USE_INITIAL_FLOW = 4
+VO_POSE_FAST, VO_POSE_STRICT, VO_POSE_NO_EARLY_STOP = 0, 1, 2
 VO_MAX_LEVELS = 8
 
 
@@ -127,6 +128,11 @@ def lib():
                                   c_int_p, c_int_p]
     L.vo_pose_gn_stereo.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, f32, vp, vp, c_int_p, c_int_p]
     L.vo_pose_gn_stereo_batch_d.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]
+    L.vo_pose_gn_mono_ex.argtypes = L.vo_pose_gn_mono.argtypes + [ctypes.c_int, ctypes.c_int, vp]
+    L.vo_pose_gn_stereo_ex.argtypes = L.vo_pose_gn_stereo.argtypes + [ctypes.c_int, ctypes.c_int, vp]
+    L.vo_pose_gn_stereo_batch_ex_d.argtypes = L.vo_pose_gn_stereo_batch_d.argtypes + [ctypes.c_int, ctypes.c_int, vp]
+    L.vo_set_pose_mode.argtypes = [vp, ctypes.c_int]
+    L.vo_get_pose_mode.argtypes = [vp]
     L.vo_triangulate_dlt.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     L.vo_depth_filter_normal.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.vo_depth_filter_student_t.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
@@ -303,8 +309,13 @@ class Context:
                         [ctypes.c_float(thres_bi)], prior, mask)
 
     # ---------------------------------------------------------------- pose-only Gauss-Newton
-    def pose_gn_stereo(self, X, pts_l1, pts_r1, K_l, K_r, T_lr, thres, T01_init):
-        """MotionEstimator::poseOnlyBundleAdjustment_Stereo -> (success, T01, mask, iters)."""
+    def set_pose_mode(self, flags):
+        """VO_POSE_FAST (0) / VO_POSE_STRICT (1): accumulation mode of every non-_ex pose-GN call and of the frame steps."""
+        check(self.h, self.L.vo_set_pose_mode(self.h, int(flags)))
+
+    def pose_gn_stereo(self, X, pts_l1, pts_r1, K_l, K_r, T_lr, thres, T01_init, flags=None, max_iter=0, want_trace=False):
+        """MotionEstimator::poseOnlyBundleAdjustment_Stereo -> (success, T01, mask, iters[, trace]).
+        flags None = the context's mode; else VO_POSE_STRICT | VO_POSE_NO_EARLY_STOP through vo_pose_gn_stereo_ex."""
         X = np.ascontiguousarray(X, np.float32).reshape(-1, 3)
         pl = np.ascontiguousarray(pts_l1, np.float32).reshape(-1, 2)
         pr = np.ascontiguousarray(pts_r1, np.float32).reshape(-1, 2)
@@ -319,12 +330,22 @@ class Context:
         T01 = np.ascontiguousarray(T01_init, np.float32).copy()
         mask = np.ones(n, np.uint8)
         ok, it = ctypes.c_int(0), ctypes.c_int(0)
-        check(self.h, self.L.vo_pose_gn_stereo(self.h, _ptr(X), _ptr(pl), _ptr(pr), n, _ptr(Kl), _ptr(Kr), _ptr(Tlr),
-                                               thres, _ptr(T01), _ptr(mask), ctypes.byref(ok), ctypes.byref(it)))
-        return bool(ok.value), T01, mask.astype(bool), it.value
+        if flags is None and not want_trace and not max_iter:
+            check(self.h, self.L.vo_pose_gn_stereo(self.h, _ptr(X), _ptr(pl), _ptr(pr), n, _ptr(Kl), _ptr(Kr), _ptr(Tlr),
+                                                   thres, _ptr(T01), _ptr(mask), ctypes.byref(ok), ctypes.byref(it)))
+            return bool(ok.value), T01, mask.astype(bool), it.value
+        mi = max_iter if 0 < max_iter < 100 else 100
+        trace = np.zeros((mi, 24), np.float32)
+        fl = self.L.vo_get_pose_mode(self.h) if flags is None else int(flags)
+        check(self.h, self.L.vo_pose_gn_stereo_ex(self.h, _ptr(X), _ptr(pl), _ptr(pr), n, _ptr(Kl), _ptr(Kr), _ptr(Tlr),
+                                                  thres, _ptr(T01), _ptr(mask), ctypes.byref(ok), ctypes.byref(it), fl,
+                                                  int(max_iter), _ptr(trace) if want_trace else None))
+        out = (bool(ok.value), T01, mask.astype(bool), it.value)
+        return out + (trace[:it.value],) if want_trace else out
 
-    def pose_gn_mono(self, X, pts1, K, thres, R01_init, t01_init, standalone_variant=0):
-        """MotionEstimator::poseOnlyBundleAdjustment -> (success, R01, t01, mask, iters)."""
+    def pose_gn_mono(self, X, pts1, K, thres, R01_init, t01_init, standalone_variant=0, flags=None, max_iter=0,
+                     want_trace=False):
+        """MotionEstimator::poseOnlyBundleAdjustment -> (success, R01, t01, mask, iters[, trace])."""
         X = np.ascontiguousarray(X, np.float32).reshape(-1, 3)
         p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
         n = len(X)
@@ -334,19 +355,31 @@ class Context:
         t = np.ascontiguousarray(t01_init, np.float32).copy()
         mask = np.ones(n, np.uint8)
         ok, it = ctypes.c_int(0), ctypes.c_int(0)
-        check(self.h, self.L.vo_pose_gn_mono(self.h, _ptr(X), _ptr(p1), n, float(K[0]), float(K[1]), float(K[2]),
-                                             float(K[3]), int(thres), int(standalone_variant), _ptr(R), _ptr(t),
-                                             _ptr(mask), ctypes.byref(ok), ctypes.byref(it)))
-        return bool(ok.value), R, t, mask.astype(bool), it.value
+        if flags is None and not want_trace and not max_iter:
+            check(self.h, self.L.vo_pose_gn_mono(self.h, _ptr(X), _ptr(p1), n, float(K[0]), float(K[1]), float(K[2]),
+                                                 float(K[3]), int(thres), int(standalone_variant), _ptr(R), _ptr(t),
+                                                 _ptr(mask), ctypes.byref(ok), ctypes.byref(it)))
+            return bool(ok.value), R, t, mask.astype(bool), it.value
+        mi = max_iter if 0 < max_iter < 100 else 100
+        trace = np.zeros((mi, 24), np.float32)
+        fl = self.L.vo_get_pose_mode(self.h) if flags is None else int(flags)
+        check(self.h, self.L.vo_pose_gn_mono_ex(self.h, _ptr(X), _ptr(p1), n, float(K[0]), float(K[1]), float(K[2]),
+                                                float(K[3]), int(thres), int(standalone_variant), _ptr(R), _ptr(t),
+                                                _ptr(mask), ctypes.byref(ok), ctypes.byref(it), fl, int(max_iter),
+                                                _ptr(trace) if want_trace else None))
+        out = (bool(ok.value), R, t, mask.astype(bool), it.value)
+        return out + (trace[:it.value],) if want_trace else out
 
     def pose_gn_stereo_batch_d(self, n_prob, offsets_d, X_d, pl_d, pr_d, K_l, K_r, T_lr, thres, T01_d, mask_d,
-                               success_d=None, iters_d=None):
+                               success_d=None, iters_d=None, flags=None, max_iter=0, trace_d=None):
         Kl = np.ascontiguousarray(K_l, np.float32)
         Kr = np.ascontiguousarray(K_r, np.float32)
         Tlr = np.ascontiguousarray(T_lr, np.float32)
-        check(self.h, self.L.vo_pose_gn_stereo_batch_d(
+        fl = self.L.vo_get_pose_mode(self.h) if flags is None else int(flags)
+        check(self.h, self.L.vo_pose_gn_stereo_batch_ex_d(
             self.h, n_prob, vp(offsets_d), vp(X_d), vp(pl_d), vp(pr_d), _ptr(Kl), _ptr(Kr), _ptr(Tlr), thres,
-            vp(T01_d), vp(mask_d), vp(success_d) if success_d else None, vp(iters_d) if iters_d else None))
+            vp(T01_d), vp(mask_d), vp(success_d) if success_d else None, vp(iters_d) if iters_d else None, fl,
+            int(max_iter), vp(trace_d) if trace_d else None))
 
     # ---------------------------------------------------------------- elementwise rows
     def triangulate_dlt(self, pts0, pts1, R10, t10, K0, K1=None):

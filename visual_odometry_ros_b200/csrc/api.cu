@@ -103,6 +103,10 @@ extern "C" int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int 
         vo_ctx_destroy(ctx);
         return VO_ERR_CUDA;
     }
+    if (n_slots > 0 && cudaMalloc((void **)&ctx->d_tmaps, sizeof(CUtensorMap) * (size_t)n_slots * VO_MAX_LEVELS * 3) != cudaSuccess) {
+        vo_ctx_destroy(ctx);
+        return VO_ERR_CUDA;
+    }
     ctx->raw_stride = (size_t)max_w * max_h;   // dense: consecutive slots are adjacent -> mergeable DMA
     if (n_slots > 0 && cudaMalloc((void **)&ctx->raw_base, ctx->raw_stride * n_slots + 256) != cudaSuccess) {
         vo_ctx_destroy(ctx);
@@ -121,6 +125,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &S : ctx->slots) if (S.base) cudaFree(S.base);
     if (ctx->d_slots) cudaFree(ctx->d_slots);
+    if (ctx->d_tmaps) cudaFree(ctx->d_tmaps);
     if (ctx->raw_base) cudaFree(ctx->raw_base);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
@@ -201,6 +206,7 @@ static int slot_set_geometry(vo_ctx *ctx, int slot, int w, int h)
     }
     S.desc.raw = ctx->raw_base + (size_t)slot * ctx->raw_stride;
     S.w = w; S.h = h;
+    S.tmap_win = 0;              // plane addresses / sizes changed: the TMA descriptors are stale
     VO_CUDA(cudaMemcpyAsync(ctx->d_slots + slot, &S.desc, sizeof(SlotDesc), cudaMemcpyHostToDevice, ctx->stream));
     // the descriptor lives in pageable host memory inside the vector: make the copy complete
     // before anybody can move/modify it
@@ -497,7 +503,7 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     // dependency is "chunk c's kernels wait for chunk c's upload" (one event per chunk).
     if (!ctx->copy_stream) VO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     // chunk sizes ramp up (8, 16, then CH pairs) so the pipeline fills after a short first DMA
-    static const int CH = getenv("VO_BATCH_CHUNK") ? atoi(getenv("VO_BATCH_CHUNK")) : 32;
+    constexpr int CH = 32;
     std::vector<int> chunk_begin;
     for (int c0 = 0, sz = 8; c0 < n_pairs; ) {
         chunk_begin.push_back(c0);
@@ -506,6 +512,20 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     }
     chunk_begin.push_back(n_pairs);
     const int n_chunks = (int)chunk_begin.size() - 1;
+    // The two-stream / copy-stream overlap below is only valid when no slot is touched by more than one chunk.  A chained
+    // batch (slots1[i] == slots0[i+1], allowed by the header) or any other reuse across chunks runs every chunk, uploads
+    // included, in order on the context's stream instead.
+    bool chained = false;
+    {
+        std::vector<int> owner(ctx->n_slots, -1);
+        for (int c = 0; c < n_chunks && !chained; ++c)
+            for (int i = chunk_begin[c]; i < chunk_begin[c + 1] && !chained; ++i)
+                for (int sid : {slots0[i], slots1[i]}) {
+                    VO_REQUIRE(sid >= 0 && sid < ctx->n_slots, VO_ERR_INVALID_ARG, "slot id out of range");
+                    if (owner[sid] >= 0 && owner[sid] != c) { chained = true; break; }
+                    owner[sid] = c;
+                }
+    }
     while ((int)ctx->events.size() < n_chunks + 1) {
         cudaEvent_t e;
         VO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -524,15 +544,28 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     cudaStream_t main_stream = ctx->stream;
     VO_CUDA(cudaEventRecord(ctx->ev_aux[0], main_stream));          // the point / mask uploads above
     VO_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_aux[0], 0));
+    // error exits: nothing may stay queued on the side streams (vo_stage_reserve / the next call only order against ctx->stream)
+    auto drain = [&](int code) {
+        ctx->stream = main_stream;
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(main_stream);
+        return code;
+    };
     for (int c = 0; c < n_chunks; ++c) {
         const int c0 = chunk_begin[c], nc = chunk_begin[c + 1] - c0;
-        rc = upload_many(ctx, nc, slots0 + c0, imgs0 ? imgs0 + c0 : nullptr, w, h, step, ctx->copy_stream);
-        if (rc) return rc;
-        rc = upload_many(ctx, nc, slots1 + c0, imgs1 ? imgs1 + c0 : nullptr, w, h, step, ctx->copy_stream);
-        if (rc) return rc;
-        VO_CUDA(cudaEventRecord(ctx->events[c], ctx->copy_stream));
-        cudaStream_t cs = (c & 1) ? ctx->stream2 : main_stream;
-        VO_CUDA(cudaStreamWaitEvent(cs, ctx->events[c], 0));
+        cudaStream_t up = chained ? main_stream : ctx->copy_stream;
+        rc = upload_many(ctx, nc, slots0 + c0, imgs0 ? imgs0 + c0 : nullptr, w, h, step, up);
+        if (rc) return drain(rc);
+        rc = upload_many(ctx, nc, slots1 + c0, imgs1 ? imgs1 + c0 : nullptr, w, h, step, up);
+        if (rc) return drain(rc);
+        cudaStream_t cs = (!chained && (c & 1)) ? ctx->stream2 : main_stream;
+        if (!chained) {
+            if (cudaEventRecord(ctx->events[c], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(cs, ctx->events[c], 0) != cudaSuccess) {
+                ctx->last_error = "vo_ft_track_batch: event record / wait failed";
+                return drain(VO_ERR_CUDA);
+            }
+        }
         const size_t off = (size_t)c0 * n;
         post.mask = d + o_mask + off;
         ctx->stream = cs;                                            // the launch helpers enqueue on ctx->stream
@@ -540,10 +573,12 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
                            with_prior ? VO_KLT_USE_INITIAL_FLOW : 0, (float *)(d + o_p1) + 2 * off, d + o_st + off,
                            (float *)(d + o_err) + off, nullptr, &post);
         ctx->stream = main_stream;
-        if (rc) return rc;
+        if (rc) return drain(rc);
     }
-    VO_CUDA(cudaEventRecord(ctx->ev_aux[1], ctx->stream2));
-    VO_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_aux[1], 0));
+    if (cudaEventRecord(ctx->ev_aux[1], ctx->stream2) != cudaSuccess || cudaStreamWaitEvent(main_stream, ctx->ev_aux[1], 0) != cudaSuccess) {
+        ctx->last_error = "vo_ft_track_batch: joining the second compute stream failed";
+        return drain(VO_ERR_CUDA);
+    }
     VO_CUDA(cudaMemcpyAsync(pin_pt ? (void *)pts_track_inout : (void *)(hs + o_p1), d + o_p1, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaMemcpyAsync(pin_m ? (void *)mask_inout : (void *)(hs + o_mask), d + o_mask, N, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -34,6 +34,7 @@ struct KltArgs {
     float *err;
     unsigned long long *counters;   // [2*VO_MAX_LEVELS] or null
     const uint8_t *skip_mask;       // nullable: features whose entry is 0 are not tracked (outputs untouched)
+    const CUtensorMap *tmaps;       // [n_slots][VO_MAX_LEVELS][3] (k_klt3 / k_track_chain)
     int n;
     int win;
     int top_level;      // effective maxLevel
@@ -275,40 +276,50 @@ k_klt(const KltArgs a)
 
 
 // =======================================================================================
-// v2: shared-memory staged windows + dp2a sampling (WIN = 13 / 15 / 21).
+// v3: TMA-staged windows + dp2a sampling (every odd window 9 ... 31).
 //
-// ncu on v1 (profiles/r1_v1_*) showed the kernel bound by L1 wavefronts: 229 M scattered byte
-// gathers per launch, 3.7 sectors each, 95 % L1 hits, long-scoreboard stalls.  v2 touches global
-// memory once per (feature, level): the template patch (u8), its Scharr patch (short2) and a
-// (WIN+1+2*MJ)^2 search region of the next image are brought in with coalesced, aligned 32-bit
-// word loads (lanes sweep rows), staged in per-warp shared memory with ODD word pitches so the
-// row-segment reads of the iterations are (nearly) bank-conflict free.  Each lane then owns
-// RPL horizontal runs of RL pixels; a run reads 3 words from each of 2 rows, realigns them with
-// funnel shifts and evaluates the fixed-point bilinear sample of a pixel with two dp2a
-// (s16 weight pair x u8 pixel pair) -- bit-identical to the scalar formula.  The search region
-// is re-staged only if the window drifts outside its margin.
+// ncu on v1 (profiles/r1_v1_*) showed the kernel bound by L1 wavefronts: 229 M scattered byte gathers per launch.
+// v2 (round 1) staged the template patch, its Scharr patch and a search region of the next image in per-warp shared
+// memory with LDG.128 -> STS through registers; profiles/r1_v4_* showed it instruction-issue bound, with a third of the
+// per-(feature, level) set-up being the staging loop's address arithmetic (172 IMAD/IADD3/LEA + 68 STS + 23 LDG).
+// v3 hands the staging to the TMA unit: three cp.async.bulk.tensor.2d boxes per (feature, level) -- template patch
+// (u8), Scharr patch (short2 as 32-bit elements), search region (u8) -- issued by one lane against per-(slot, level)
+// tensor maps, landing on two per-warp mbarriers:
+//   * the boxes start at the EXACT window origin (TMA takes element coordinates), so the template is word-aligned by
+//     construction and the staging needs no address arithmetic, no registers and no STS;
+//   * the NEXT level's template / Scharr boxes are requested as soon as the current level's template registers are
+//     built, the current level's search region right at the level start: both land while the warp computes.
+// Box row pitches (48 B image rows, 28 / 36-element Scharr rows) are the dense TMA layout; they are chosen so that
+// r * pitch mod 32 banks has period 8, which keeps the row-segment reads of the iterations at most 2-way conflicted.
+// Each lane owns RPL horizontal runs of RL pixels; a run reads 3 words from each of 2 rows, realigns them with funnel
+// shifts and evaluates the fixed-point bilinear sample of a pixel with two dp2a (s16 weight pair x u8 pixel pair) --
+// bit-identical to the scalar formula.  The search region is re-requested only if the window drifts outside its margin.
 // =======================================================================================
-#define MJ 5    // minimum search-region margin (pixels) on every side
+#define MJ 5    // minimum search-region margin (pixels) above / below the window
 
-template <int WIN> struct Klt2Cfg {
+template <int WIN> struct Klt3Cfg {
     static constexpr int W1 = WIN + 1;
-    static constexpr int SEG = (WIN > 16) ? 3 : 2;
-    static constexpr int RL = (WIN + SEG - 1) / SEG;              // pixels per run
+    static constexpr int SEG = (WIN > 24) ? 4 : (WIN > 16) ? 3 : 2;       // runs per window row
+    static constexpr int RL = (WIN + SEG - 1) / SEG;                     // pixels per run (<= 8)
     static constexpr int NRUN = WIN * SEG;
-    static constexpr int RPL = (NRUN + 31) / 32;                  // runs per lane
-    static constexpr bool FULL = (WIN % SEG) == 0;                // every run has RL pixels
-    // staging rectangles are fetched as aligned 128-bit words (16 B): x origins are rounded down to 16 B
-    static constexpr int I_V4 = (15 + W1 + 15) / 16;              // uint4 per template-patch row
-    static constexpr int IPW = I_V4 * 4;                          // pitch in 32-bit words
-    static constexpr int D_V4 = (3 + W1 + 3) / 4;                 // short2 elements: origin rounded down to 4 elements
-    static constexpr int DPW = D_V4 * 4;
-    static constexpr int JR = W1 + 2 * MJ;                        // search-region rows
-    static constexpr int J_V4 = (15 + W1 + 2 * MJ + 15) / 16;
-    static constexpr int JBYTES = J_V4 * 16;                      // valid bytes per staged row
-    static constexpr int JPW = (J_V4 * 4) | 1;                    // ODD pitch (stored with 32-bit stores): conflict-light row reads
-    static constexpr int I_WORDS = W1 * IPW, D_WORDS = W1 * DPW, J_WORDS = ((JR * JPW + 3) / 4) * 4;
-    static constexpr int WARP_WORDS = I_WORDS + D_WORDS + J_WORDS + 4;   // +4: load_run may touch one word past a row
-    static constexpr int NPX = RPL * RL;                          // template registers per lane
+    static constexpr int RPL = (NRUN + 31) / 32;                         // runs per lane
+    static constexpr bool FULL = (WIN % SEG) == 0;                       // every run has RL pixels
+    static constexpr int NPX = RPL * RL;                                 // template registers per lane
+    // TMA boxes (dense rows in shared memory)
+    static constexpr int IBW = 48;                                       // template patch: bytes per row (12 words)
+    static constexpr int DBW = (SEG * RL + 1 <= 28) ? 28 : 36;           // Scharr patch: short2 elements per row
+    static constexpr int JBW = 48;                                       // search region: bytes per row
+    static constexpr int JR = W1 + 2 * MJ;                               // search region rows
+    static constexpr int JMX = (JBW - W1) / 2;                           // horizontal margin left of the window
+    static constexpr int IPW = IBW / 4, DPW = DBW, JPW = JBW / 4;        // pitches in 32-bit words
+    static constexpr int I_BYTES = W1 * IBW, D_BYTES = W1 * DBW * 4, J_BYTES = JR * JBW;
+    static constexpr int OFF_I = 0;
+    static constexpr int OFF_D = (I_BYTES + 127) & ~127;
+    static constexpr int OFF_J = OFF_D + ((D_BYTES + 127) & ~127);
+    static constexpr int WARP_BYTES = OFF_J + ((J_BYTES + 16 + 127) & ~127);   // +16: load_run may touch one word past a row
+    static constexpr int MINB = NPX <= 14 ? 5 : (NPX <= 24 ? 3 : 2);     // resident CTAs per SM the register budget is sized for
+    static_assert(RL <= 8, "load_run covers at most 8 pixels");
+    static_assert(W1 <= JBW - 2 && SEG * RL + 1 <= DBW, "boxes too small for this window");
 };
 
 __device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c)
@@ -324,34 +335,38 @@ __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c)
     return d;
 }
 
-// Coalesced copy of a ROWS x V4 rectangle of aligned 128-bit words from global to shared memory.
-// PW = destination pitch in 32-bit words; if PW == 4*V4 the rows are stored with 128-bit stores,
-// otherwise (odd pitch) with four 32-bit stores.
-template <int ROWS, int V4, int PW>
-__device__ __forceinline__ void stage_v4(uint32_t *dst, const uint8_t *src_aligned, int pitch_bytes, int lane)
+// ---- TMA / mbarrier plumbing (one lane issues, the warp waits)
+struct WarpPipe {
+    uint32_t bar_id, bar_j;     // shared-window addresses of the two mbarriers (template + Scharr boxes / search region)
+    uint32_t ph_id, ph_j;       // phase parity to wait for next
+};
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
 {
-    constexpr int N = ROWS * V4;
-    constexpr int T = (N + 31) / 32;
-    uint4 v[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        const int idx = lane + 32 * t;
-        const int r = idx / V4, c = idx - r * V4;
-        if (idx < N) v[t] = __ldg(reinterpret_cast<const uint4 *>(src_aligned + (ptrdiff_t)r * pitch_bytes) + c);
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        const int idx = lane + 32 * t;
-        const int r = idx / V4, c = idx - r * V4;
-        if (idx < N) {
-            if (PW == 4 * V4) {
-                *reinterpret_cast<uint4 *>(dst + r * PW + 4 * c) = v[t];
-            } else {
-                uint32_t *p = dst + r * PW + 4 * c;
-                p[0] = v[t].x; p[1] = v[t].y; p[2] = v[t].z; p[3] = v[t].w;
-            }
-        }
-    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    return ok != 0;
+}
+// All lanes wait for the phase; a transfer that never completes (a broken tensor map) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t &phase)
+{
+    int spins = 0;
+    while (!mbar_try_wait(bar, phase)) { if (++spins > (1 << 20)) __trap(); }
+    phase ^= 1u;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
 // 8-bit sample stream of one run: E holds bytes e0.., O the same shifted by one byte.
@@ -382,16 +397,34 @@ __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_
 #ifndef KLT2_WPB
 #define KLT2_WPB 4          // warps (features) per CTA
 #endif
-// One (pair, feature) on one warp: every level, every iteration, the fused post-filter epilogue.
-template <int WIN>
-__device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, const int f, uint32_t *Ibuf, uint32_t *Dbuf, uint32_t *Jbuf,
-                                             const int lane)
+
+// Template-window origin of a level (depends on pts0 only): false when the window misses the image (level skipped).
+__device__ __forceinline__ bool klt_tpl_origin(const float2 p0, const int level, const float halfWin, const int win, const int w, const int h,
+                                               float &prevx, float &prevy, int &ipx, int &ipy)
 {
-    using C = Klt2Cfg<WIN>;
+    const float sc = 1.f / (float)(1 << level);
+    prevx = __fsub_rn(__fmul_rn(p0.x, sc), halfWin); prevy = __fsub_rn(__fmul_rn(p0.y, sc), halfWin);
+    ipx = __float2int_rd(prevx); ipy = __float2int_rd(prevy);
+    return !(ipx < -win || ipx >= w || ipy < -win || ipy >= h);
+}
+
+// One (pair, feature) on one warp: every level, every iteration, the fused post-filter epilogue.
+// wbuf: this warp's 128-byte aligned staging area (Klt3Cfg<WIN>::WARP_BYTES); pp: its two mbarriers.
+template <int WIN>
+__device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, const int f, uint8_t *wbuf, WarpPipe &pp, const int lane)
+{
+    using C = Klt3Cfg<WIN>;
     const size_t gi = (size_t)pair * a.n + f;
     if (a.skip_mask && !a.skip_mask[gi]) return;
-    const SlotDesc &S0 = a.slots[a.s0.id[pair]];
-    const SlotDesc &S1 = a.slots[a.s1.id[pair]];
+    uint32_t *Ibuf = reinterpret_cast<uint32_t *>(wbuf + C::OFF_I);
+    uint32_t *Dbuf = reinterpret_cast<uint32_t *>(wbuf + C::OFF_D);
+    uint32_t *Jbuf = reinterpret_cast<uint32_t *>(wbuf + C::OFF_J);
+    const uint32_t sI = smem_addr(Ibuf), sD = smem_addr(Dbuf), sJ = smem_addr(Jbuf);
+    const int sid0 = a.s0.id[pair], sid1 = a.s1.id[pair];
+    const SlotDesc &S0 = a.slots[sid0];
+    const SlotDesc &S1 = a.slots[sid1];
+    const CUtensorMap *tm0 = a.tmaps + (size_t)sid0 * (VO_MAX_LEVELS * 3);   // per level: {template box, Scharr box, search box}
+    const CUtensorMap *tm1 = a.tmaps + (size_t)sid1 * (VO_MAX_LEVELS * 3);
     const float halfWin = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     const float eps2_lo = (float)a.eps2 * 0.9999f, eps2_hi = (float)a.eps2 * 1.0001f;
@@ -416,41 +449,52 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
     int status = 1;
     float errv = 0.f;
 
+    // request the top level's template + Scharr boxes
+    {
+        float px_, py_; int ix_, iy_;
+        const LevelDesc I = S0.lv[a.top_level];
+        if (klt_tpl_origin(p0, a.top_level, halfWin, WIN, I.w, I.h, px_, py_, ix_, iy_) && lane == 0) {
+            mbar_expect_tx(pp.bar_id, C::I_BYTES + C::D_BYTES);
+            tma_load_2d(sI, tm0 + a.top_level * 3 + 0, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
+            tma_load_2d(sD, tm0 + a.top_level * 3 + 1, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
+        }
+    }
+
     for (int level = a.top_level; level >= 0; --level) {
         const LevelDesc I = S0.lv[level];
         const LevelDesc J = S1.lv[level];
         const float sc = 1.f / (float)(1 << level);
-        float prevx = __fmul_rn(p0.x, sc), prevy = __fmul_rn(p0.y, sc);
         if (level == a.top_level) {
             if (a.flags & VO_KLT_USE_INITIAL_FLOW) { stored.x = __fmul_rn(stored.x, sc); stored.y = __fmul_rn(stored.y, sc); }
-            else { stored.x = prevx; stored.y = prevy; }
+            else { stored.x = __fmul_rn(p0.x, sc); stored.y = __fmul_rn(p0.y, sc); }
         } else {
             stored.x = __fmul_rn(stored.x, 2.f); stored.y = __fmul_rn(stored.y, 2.f);
         }
         float nextx = stored.x, nexty = stored.y;
-        prevx = __fsub_rn(prevx, halfWin); prevy = __fsub_rn(prevy, halfWin);
-        const int ipx = __float2int_rd(prevx), ipy = __float2int_rd(prevy);
-        if (ipx < -WIN || ipx >= I.w || ipy < -WIN || ipy >= I.h) {
+        float prevx, prevy;
+        int ipx, ipy;
+        if (!klt_tpl_origin(p0, level, halfWin, WIN, I.w, I.h, prevx, prevy, ipx, ipy)) {
+            // nothing was requested for this level
             if (level == 0) { status = 0; errv = 0.f; }
             continue;
         }
         int iw00, iw01, iw10, iw11;
         bilinear_weights(__fsub_rn(prevx, (float)ipx), __fsub_rn(prevy, (float)ipy), iw00, iw01, iw10, iw11);
 
-        // ---- stage template patch, derivative patch and the initial search region (all loads first)
+        // ---- request the search region around the start position (lands while the template is built)
         nextx = __fsub_rn(nextx, halfWin); nexty = __fsub_rn(nexty, halfWin);
-        int jx0, jy0;   // origin (pixel coords) of the staged search region; jx0 is 16-aligned
+        int jx0, jy0;   // origin (pixel coords) of the staged search region
         {
-            const int iax = ipx & ~15, dax = ipx & ~3;
-            stage_v4<C::W1, C::I_V4, C::IPW>(Ibuf, I.img + (ptrdiff_t)ipy * I.pitch + iax, I.pitch, lane);
-            stage_v4<C::W1, C::D_V4, C::DPW>(Dbuf, reinterpret_cast<const uint8_t *>(I.deriv + (ptrdiff_t)ipy * I.pitch + dax), I.pitch * 4, lane);
             int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
-            // clamp the staging origin so that it stays inside the padded plane even for a wild start
+            // clamp the staging origin so that it stays near the padded plane even for a wild start
             inx = max(-WIN, min(inx, J.w - 1)); iny = max(-WIN, min(iny, J.h - 1));
-            jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
-            stage_v4<C::JR, C::J_V4, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
+            jx0 = inx - C::JMX; jy0 = iny - MJ;
+            if (lane == 0) {
+                mbar_expect_tx(pp.bar_j, C::J_BYTES);
+                tma_load_2d(sJ, tm1 + level * 3 + 2, pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD);
+            }
         }
-        __syncwarp();
+        mbar_wait(pp.bar_id, pp.ph_id);        // template + Scharr boxes of this level (requested one level earlier)
 
         // ---- template. Registers per pixel: Cn = RND - (I << SH) (the dp2a accumulator seed, so that an
         // iteration's diff is one shift after the two dp2a), Ix, Iy. Exact A sums.
@@ -458,14 +502,13 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
         int sA11 = 0, sA12 = 0, sA22 = 0;
         {
             const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
-            const int offI = ipx & 15, offD = ipx & 3;
 #pragma unroll
             for (int q = 0; q < C::RPL; ++q) {
                 uint32_t EA[3], OA[3], EB[3], OB[3];
                 const int r = run_row[q];
-                load_run(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
-                load_run(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
-                const uint32_t *d0 = Dbuf + r * C::DPW + offD + run_x0[q];
+                load_run(Ibuf + r * C::IPW, run_x0[q], EA, OA);           // the box starts at the window origin
+                load_run(Ibuf + (r + 1) * C::IPW, run_x0[q], EB, OB);
+                const uint32_t *d0 = Dbuf + r * C::DPW + run_x0[q];
                 const uint32_t *d1 = d0 + C::DPW;
                 uint32_t da = d0[0], db = d1[0];
                 int a11 = 0, a12 = 0, a22 = 0;
@@ -486,6 +529,17 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
                 sA11 += run_ok[q] ? a11 : 0; sA12 += run_ok[q] ? a12 : 0; sA22 += run_ok[q] ? a22 : 0;
             }
         }
+        // ---- the template / Scharr buffers are free again: request the NEXT level's boxes now
+        __syncwarp();
+        if (level > 0) {
+            float px_, py_; int ix_, iy_;
+            const LevelDesc In = S0.lv[level - 1];
+            if (klt_tpl_origin(p0, level - 1, halfWin, WIN, In.w, In.h, px_, py_, ix_, iy_) && lane == 0) {
+                mbar_expect_tx(pp.bar_id, C::I_BYTES + C::D_BYTES);
+                tma_load_2d(sI, tm0 + (level - 1) * 3 + 0, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
+                tma_load_2d(sD, tm0 + (level - 1) * 3 + 1, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
+            }
+        }
         const float A11 = __fmul_rn(warp_sum_exact_f(sA11), FLT_SCALE);
         const float A12 = __fmul_rn(warp_sum_exact_f(sA12), FLT_SCALE);
         const float A22 = __fmul_rn(warp_sum_exact_f(sA22), FLT_SCALE);
@@ -496,8 +550,10 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
                       __fsqrt_rn(__fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
             (float)(2 * WIN * WIN));
         if (a.counters && lane == 0) atomicAdd(a.counters + 2 * level, 1ull);
+        mbar_wait(pp.bar_j, pp.ph_j);          // search region of this level
         if (minEig < a.min_eig || D < FLT_EPSILON) {
             if (level == 0) status = 0;
+            __syncwarp();
             continue;
         }
         D = __fdiv_rn(1.f, D);
@@ -511,11 +567,14 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
                 break;
             }
             int offx = inx - jx0, offy = iny - jy0;
-            if (offx < 0 || offx + C::W1 > C::JBYTES || offy < 0 || offy + C::W1 > C::JR) {
+            if (offx < 0 || offx + C::W1 > C::JBW || offy < 0 || offy + C::W1 > C::JR) {
                 __syncwarp();
-                jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
-                stage_v4<C::JR, C::J_V4, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
-                __syncwarp();
+                jx0 = inx - C::JMX; jy0 = iny - MJ;
+                if (lane == 0) {
+                    mbar_expect_tx(pp.bar_j, C::J_BYTES);
+                    tma_load_2d(sJ, tm1 + level * 3 + 2, pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD);
+                }
+                mbar_wait(pp.bar_j, pp.ph_j);
                 offx = inx - jx0; offy = iny - jy0;
             }
             bilinear_weights(__fsub_rn(nextx, (float)inx), __fsub_rn(nexty, (float)iny), iw00, iw01, iw10, iw11);
@@ -560,11 +619,14 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
                 status = 0;
             } else {
                 int offx = inx - jx0, offy = iny - jy0;
-                if (offx < 0 || offx + C::W1 > C::JBYTES || offy < 0 || offy + C::W1 > C::JR) {
+                if (offx < 0 || offx + C::W1 > C::JBW || offy < 0 || offy + C::W1 > C::JR) {
                     __syncwarp();
-                    jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
-                    stage_v4<C::JR, C::J_V4, C::JPW>(Jbuf, J.img + (ptrdiff_t)jy0 * J.pitch + jx0, J.pitch, lane);
-                    __syncwarp();
+                    jx0 = inx - C::JMX; jy0 = iny - MJ;
+                    if (lane == 0) {
+                        mbar_expect_tx(pp.bar_j, C::J_BYTES);
+                        tma_load_2d(sJ, tm1 + level * 3 + 2, pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD);
+                    }
+                    mbar_wait(pp.bar_j, pp.ph_j);
                     offx = inx - jx0; offy = iny - jy0;
                 }
                 bilinear_weights(__fsub_rn(npx, (float)inx), __fsub_rn(npy, (float)iny), iw00, iw01, iw10, iw11);
@@ -588,23 +650,43 @@ __device__ __forceinline__ void klt2_feature(const KltArgs &a, const int pair, c
                 errv = __fdiv_rn(__fmul_rn((float)tot, 1.f), (float)(32 * WIN * WIN));
             }
         }
-        __syncwarp();   // the next level overwrites the staging buffers
+        __syncwarp();   // the next level's search-region request overwrites the buffer
     }
 
     if (lane == 0) klt_epilogue(a, gi, S0, stored, status, errv);
 }
 
-template <int WIN, int MINB>
-__global__ void __launch_bounds__(32 * KLT2_WPB, MINB * 4 / KLT2_WPB)
-k_klt2(const KltArgs a)
+// per-warp staging area + mbarriers of a CTA of KLT2_WPB warps
+template <int WIN>
+__device__ __forceinline__ uint8_t *klt3_warp_setup(uint8_t *smem_raw, unsigned long long *bars, const int wib, const int lane, WarpPipe &pp)
 {
-    using C = Klt2Cfg<WIN>;
-    extern __shared__ __align__(16) uint32_t smem_u32[];
+    using C = Klt3Cfg<WIN>;
+    uint8_t *base = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);     // TMA destinations: 128-byte aligned
+    pp.bar_id = smem_addr(bars + 2 * wib);
+    pp.bar_j = smem_addr(bars + 2 * wib + 1);
+    pp.ph_id = 0; pp.ph_j = 0;
+    if (lane == 0) {
+        mbar_init(pp.bar_id, 1);
+        mbar_init(pp.bar_j, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    return base + (size_t)wib * C::WARP_BYTES;
+}
+#define KLT3_SMEM(WIN) ((size_t)KLT2_WPB * Klt3Cfg<WIN>::WARP_BYTES + 128)
+
+template <int WIN>
+__global__ void __launch_bounds__(32 * KLT2_WPB, Klt3Cfg<WIN>::MINB * 4 / KLT2_WPB)
+k_klt3(const KltArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * KLT2_WPB];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= a.n) return;
-    uint32_t *Ibuf = smem_u32 + wib * C::WARP_WORDS;
-    klt2_feature<WIN>(a, blockIdx.y, f, Ibuf, Ibuf + C::I_WORDS, Ibuf + C::I_WORDS + C::D_WORDS, lane);
+    WarpPipe pp;
+    uint8_t *wbuf = klt3_warp_setup<WIN>(smem_raw, bars, wib, lane, pp);
+    klt3_feature<WIN>(a, blockIdx.y, f, wbuf, pp, lane);
 }
 
 // Fused tracking chain of the stereo frame step (stereo_vo.cpp:533-571): trackWithPrior(l0 -> l1), trackWithScale,
@@ -616,32 +698,119 @@ k_klt2(const KltArgs a)
 #define VO_CHAIN_SCALE 2    // trackWithScale
 #define VO_CHAIN_NEXT 4     // third LK pass (l1 -> r1)
 template <int WIN>
-__global__ void __launch_bounds__(32 * KLT2_WPB, 4 * 4 / KLT2_WPB)
+__global__ void __launch_bounds__(32 * KLT2_WPB, (Klt3Cfg<WIN>::MINB > 4 ? 4 : Klt3Cfg<WIN>::MINB) * 4 / KLT2_WPB)
 k_track_chain(const KltArgs a1, const KltArgs a2, const KltScaleArgs sc, const KltArgs a3, const int stages)
 {
-    using C = Klt2Cfg<WIN>;
-    extern __shared__ __align__(16) uint32_t smem_u32[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * KLT2_WPB];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= a1.n) return;
-    uint32_t *Ibuf = smem_u32 + wib * C::WARP_WORDS;
-    uint32_t *Dbuf = Ibuf + C::I_WORDS, *Jbuf = Dbuf + C::D_WORDS;
-    klt2_feature<WIN>(a1, 0, f, Ibuf, Dbuf, Jbuf, lane);
+    WarpPipe pp;
+    uint8_t *wbuf = klt3_warp_setup<WIN>(smem_raw, bars, wib, lane, pp);
+    klt3_feature<WIN>(a1, 0, f, wbuf, pp, lane);
     __syncwarp();                          // lane 0's point / status / mask stores are visible to the whole warp
-    if (stages & VO_CHAIN_BACK) { klt2_feature<WIN>(a2, 0, f, Ibuf, Dbuf, Jbuf, lane); __syncwarp(); }
+    if (stages & VO_CHAIN_BACK) { klt3_feature<WIN>(a2, 0, f, wbuf, pp, lane); __syncwarp(); }
     if (stages & VO_CHAIN_SCALE) { klt_scale_feature(sc, f, lane); __syncwarp(); }
-    if (stages & VO_CHAIN_NEXT) klt2_feature<WIN>(a3, 0, f, Ibuf, Dbuf, Jbuf, lane);
+    if (stages & VO_CHAIN_NEXT) klt3_feature<WIN>(a3, 0, f, wbuf, pp, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+// every odd window 9 ... 31 has a k_klt3 / k_track_chain instantiation; other sizes (even, < 9) run the v1 kernel
+static bool klt3_window(int win) { return win >= 9 && win <= 31 && (win & 1); }
+#define KLT3_FOR_EACH_WIN(X) X(9) X(11) X(13) X(15) X(17) X(19) X(21) X(23) X(25) X(27) X(29) X(31)
+
+// run-time copy of the Klt3Cfg box geometry (static_asserts below keep the two in step)
+struct Klt3Boxes { int w1, ibw, dbw, jbw, jr; };
+static Klt3Boxes klt3_boxes(int win)
+{
+    const int seg = win > 24 ? 4 : (win > 16 ? 3 : 2), rl = (win + seg - 1) / seg;
+    Klt3Boxes b;
+    b.w1 = win + 1; b.ibw = 48; b.dbw = (seg * rl + 1 <= 28) ? 28 : 36; b.jbw = 48; b.jr = win + 1 + 2 * MJ;
+    return b;
+}
+#define KLT3_CHECK_BOXES(W) static_assert(Klt3Cfg<W>::IBW == 48 && Klt3Cfg<W>::JBW == 48 && Klt3Cfg<W>::JR == W + 1 + 2 * MJ && \
+                                          Klt3Cfg<W>::DBW == ((((W > 24 ? 4 : (W > 16 ? 3 : 2)) * Klt3Cfg<W>::RL + 1) <= 28) ? 28 : 36), "klt3_boxes out of step");
+KLT3_FOR_EACH_WIN(KLT3_CHECK_BOXES)
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled tmap_encoder()
+{
+    static PFN_tmapEncodeTiled fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }();
+    return fn;
+}
+
+// (Re)encode the TMA descriptors of these slots for window size `win` and put them on the device (stream-ordered before
+// the launch that follows).  Per (slot, level): [0] template box IBW x W1 (u8), [1] Scharr box DBW x W1 (short2 as 32-bit
+// elements), [2] search box JBW x JR (u8), all over the WHOLE padded plane (pitch x (h + 2 PAD)), so that any window
+// origin the kernel can produce is a valid (possibly partly out-of-bounds = zero-filled, never used) box coordinate.
+static int ensure_tmaps(vo_ctx *ctx, const int *slots, int n, int win)
+{
+    PFN_tmapEncodeTiled enc = nullptr;
+    const Klt3Boxes B = klt3_boxes(win);
+    bool copied = false;
+    for (int i = 0; i < n; ++i) {
+        Slot &S = ctx->slots[slots[i]];
+        if (S.tmap_win == win) continue;
+        if (!enc) {
+            enc = tmap_encoder();
+            VO_REQUIRE(enc != nullptr, VO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        CUtensorMap maps[VO_MAX_LEVELS * 3];
+        memset(maps, 0, sizeof(maps));
+        for (int l = 0; l < ctx->max_levels; ++l) {
+            const LevelDesc &L = S.desc.lv[l];
+            if (!L.img) continue;
+            const cuuint64_t rows = (cuuint64_t)L.h + 2 * VO_PAD;
+            const cuuint32_t estr[2] = {1, 1};
+            void *img_plane = L.img - (size_t)VO_PAD * L.pitch - VO_PAD;
+            void *der_plane = L.deriv - (size_t)VO_PAD * L.pitch - VO_PAD;
+            const cuuint64_t dim8[2] = {(cuuint64_t)L.pitch, rows}, str8[1] = {(cuuint64_t)L.pitch};
+            const cuuint64_t dim32[2] = {(cuuint64_t)L.pitch, rows}, str32[1] = {(cuuint64_t)L.pitch * 4};
+            const cuuint32_t boxI[2] = {(cuuint32_t)B.ibw, (cuuint32_t)B.w1}, boxD[2] = {(cuuint32_t)B.dbw, (cuuint32_t)B.w1};
+            const cuuint32_t boxJ[2] = {(cuuint32_t)B.jbw, (cuuint32_t)B.jr};
+            CUresult r0 = enc(&maps[l * 3 + 0], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img_plane, dim8, str8, boxI, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r1 = enc(&maps[l * 3 + 1], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, der_plane, dim32, str32, boxD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r2 = enc(&maps[l * 3 + 2], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img_plane, dim8, str8, boxJ, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+                ctx->last_error = "cuTensorMapEncodeTiled failed (level " + std::to_string(l) + ", codes " + std::to_string((int)r0) + " " +
+                                  std::to_string((int)r1) + " " + std::to_string((int)r2) + ")";
+                return VO_ERR_CUDA;
+            }
+        }
+        // pageable source: the runtime stages the bytes before returning, so `maps` may go out of scope
+        VO_CUDA(cudaMemcpyAsync(ctx->d_tmaps + (size_t)slots[i] * VO_MAX_LEVELS * 3, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
+        S.tmap_win = win;
+        copied = true;
+    }
+    // other streams of this context (the batched entry point alternates between two) may use these descriptors next
+    if (copied) VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
 }
 
 template <int WIN>
-static cudaError_t launch_klt2(const KltArgs &a, dim3 grd, cudaStream_t st)
+static cudaError_t launch_klt3(const KltArgs &a, dim3 grd, cudaStream_t st)
 {
-    const size_t smem = (size_t)KLT2_WPB * Klt2Cfg<WIN>::WARP_WORDS * 4;
     grd.x = (grd.x * 4 + KLT2_WPB - 1) / KLT2_WPB;
-    static const int minb = getenv("VO_KLT_MINB") ? atoi(getenv("VO_KLT_MINB")) : KLT2_MIN_BLOCKS;   // tuning switch
-    if (minb >= 6) k_klt2<WIN, 6><<<grd, 32 * KLT2_WPB, smem, st>>>(a);
-    else if (minb == 5) k_klt2<WIN, 5><<<grd, 32 * KLT2_WPB, smem, st>>>(a);
-    else k_klt2<WIN, 4><<<grd, 32 * KLT2_WPB, smem, st>>>(a);
+    k_klt3<WIN><<<grd, 32 * KLT2_WPB, KLT3_SMEM(WIN), st>>>(a);
+    return cudaGetLastError();
+}
+template <int WIN>
+static cudaError_t launch_chain(const KltArgs &a1, const KltArgs &a2, const KltScaleArgs &sc, const KltArgs &a3, int stages, int n, cudaStream_t st)
+{
+    k_track_chain<WIN><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, KLT3_SMEM(WIN), st>>>(a1, a2, sc, a3, stages);
     return cudaGetLastError();
 }
 
@@ -667,12 +836,19 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
     if (rc) return rc;
     rc = vo_ensure_pyramids(ctx, slots1, n_pairs, eff + 1, 0);
     if (rc) return rc;
+    if (klt3_window(win)) {
+        rc = ensure_tmaps(ctx, slots0, n_pairs, win);
+        if (rc) return rc;
+        rc = ensure_tmaps(ctx, slots1, n_pairs, win);
+        if (rc) return rc;
+    }
 
     const int npx = vo_div_up(win * win, 32);
     for (int c0 = 0; c0 < n_pairs; c0 += VO_IDLIST_MAX) {
         const int nb = n_pairs - c0 < VO_IDLIST_MAX ? n_pairs - c0 : VO_IDLIST_MAX;
         KltArgs a;
         a.slots = ctx->d_slots;
+        a.tmaps = ctx->d_tmaps;
         for (int i = 0; i < nb; ++i) { a.s0.id[i] = slots0[c0 + i]; a.s1.id[i] = slots1[c0 + i]; }
         const size_t off = (size_t)c0 * n;
         a.pts0 = reinterpret_cast<const float2 *>(pts0_d) + off;
@@ -694,11 +870,14 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
             a.post = KltPost{};
         }
         dim3 grd(vo_div_up(n, 4), nb);
-        static const bool force_v1 = getenv("VO_KLT_V1") != nullptr;   // A/B switch for profiling
-        if (!force_v1 && (win == 21 || win == 15 || win == 13)) {
-            cudaError_t e = win == 21 ? launch_klt2<21>(a, grd, ctx->stream)
-                          : win == 15 ? launch_klt2<15>(a, grd, ctx->stream) : launch_klt2<13>(a, grd, ctx->stream);
-            if (e != cudaSuccess) { ctx->last_error = std::string("k_klt2: ") + cudaGetErrorString(e); return VO_ERR_CUDA; }
+        if (klt3_window(win)) {
+            cudaError_t e = cudaErrorInvalidValue;
+            switch (win) {
+#define KLT3_CASE(W) case W: e = launch_klt3<W>(a, grd, ctx->stream); break;
+                KLT3_FOR_EACH_WIN(KLT3_CASE)
+#undef KLT3_CASE
+            }
+            if (e != cudaSuccess) { ctx->last_error = std::string("k_klt3: ") + cudaGetErrorString(e); return VO_ERR_CUDA; }
         }
         else if (npx <= 6) k_klt<6><<<grd, 128, 0, ctx->stream>>>(a);
         else if (npx <= 8) k_klt<8><<<grd, 128, 0, ctx->stream>>>(a);
@@ -718,6 +897,7 @@ static void fill_klt_args(vo_ctx *ctx, KltArgs &a, int s0, int s1, const float *
                           int win, int eff, int flags, const KltPost &post)
 {
     a.slots = ctx->d_slots;
+    a.tmaps = ctx->d_tmaps;
     a.s0.id[0] = s0; a.s1.id[0] = s1;
     a.pts0 = reinterpret_cast<const float2 *>(pts0_d); a.pts1 = reinterpret_cast<float2 *>(pts1_d);
     a.status = status_d; a.err = err_d; a.counters = nullptr;
@@ -726,10 +906,18 @@ static void fill_klt_args(vo_ctx *ctx, KltArgs &a, int s0, int s1, const float *
     a.max_count = 30; a.min_eig = 1e-4f; a.eps2 = 0.01 * 0.01;
     a.post = post;
 }
-static bool chain_unfused(int win)
+static bool chain_unfused(int win) { return !klt3_window(win); }   // even / tiny windows: separate v1 launches
+static int launch_chain_win(vo_ctx *ctx, int win, const KltArgs &a1, const KltArgs &a2, const KltScaleArgs &sc, const KltArgs &a3, int stages, int n)
 {
-    static const bool unfused = getenv("VO_CHAIN_UNFUSED") != nullptr;
-    return unfused || win != 21;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (win) {
+#define KLT3_CASE(W) case W: e = launch_chain<W>(a1, a2, sc, a3, stages, n, ctx->stream); break;
+        KLT3_FOR_EACH_WIN(KLT3_CASE)
+#undef KLT3_CASE
+    }
+    ctx->launches++;
+    if (e != cudaSuccess) { ctx->last_error = std::string("k_track_chain: ") + cudaGetErrorString(e); return VO_ERR_CUDA; }
+    return VO_OK;
 }
 static int clamp_level(vo_ctx *ctx, int slot, int win, int max_level)
 {
@@ -765,11 +953,9 @@ int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, 
     sc.slots = ctx->d_slots; sc.slot0 = slot_l0; sc.slot1 = slot_l1;
     sc.pts0 = reinterpret_cast<const float2 *>(pts_l0_d); sc.scale = scale_d;
     sc.pts_track = reinterpret_cast<float2 *>(pts_l1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
-    const size_t smem = (size_t)KLT2_WPB * Klt2Cfg<21>::WARP_WORDS * 4;
-    k_track_chain<21><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, smem, ctx->stream>>>(a1, a1, sc, a3, (do_scale ? VO_CHAIN_SCALE : 0) | VO_CHAIN_NEXT);
-    ctx->launches++;
-    VO_CUDA(cudaGetLastError());
-    return VO_OK;
+    rc = ensure_tmaps(ctx, sl, 3, win);
+    if (rc) return rc;
+    return launch_chain_win(ctx, win, a1, a1, sc, a3, (do_scale ? VO_CHAIN_SCALE : 0) | VO_CHAIN_NEXT, n);
 }
 
 // Bidirectional track of one pair (feature_tracker.cpp:39-169): forward pass, backward pass seeded with pts0 whose
@@ -811,9 +997,7 @@ int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0
     sc.slots = ctx->d_slots; sc.slot0 = slot0; sc.slot1 = slot1;
     sc.pts0 = reinterpret_cast<const float2 *>(pts0_d); sc.scale = scale_d;
     sc.pts_track = reinterpret_cast<float2 *>(pts1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
-    const size_t smem = (size_t)KLT2_WPB * Klt2Cfg<21>::WARP_WORDS * 4;
-    k_track_chain<21><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, smem, ctx->stream>>>(a1, a2, sc, a1, VO_CHAIN_BACK | (scale_d ? VO_CHAIN_SCALE : 0));
-    ctx->launches++;
-    VO_CUDA(cudaGetLastError());
-    return VO_OK;
+    rc = ensure_tmaps(ctx, sl, 2, win);
+    if (rc) return rc;
+    return launch_chain_win(ctx, win, a1, a2, sc, a1, VO_CHAIN_BACK | (scale_d ? VO_CHAIN_SCALE : 0), n);
 }

@@ -37,6 +37,9 @@ struct PoseArgs {
     uint8_t *mask;
     int *success;
     int *iters;
+    int max_iter;         // <= POSE_MAX_ITER
+    int no_early_stop;    // 1: ignore the stop test (fixed-point / trace comparisons)
+    float *trace;         // nullable: [n_prob][max_iter][24] = {T10 after update (16), err, dxi (6), delta_err}
 };
 
 __device__ __forceinline__ void inv_se3(const float *T, float *O)
@@ -241,71 +244,89 @@ __device__ __forceinline__ void acc_row(double *acc, const float *Jt, float w, f
         if (i != ZERO) acc[21 + i] -= (double)(wr * Jt[i]);
 }
 
-// Residuals / Jacobian rows of the points first, first + stride, ... accumulated into the 28 FP64 partials
-// (per-point arithmetic in the reference's FP32 operation order; motion_estimator.cpp:720-800 mono, :915-1050 stereo).
-__device__ __forceinline__ void pose_points(const PoseArgs &a, const float *__restrict__ X, const float *__restrict__ pl,
-                                            const float *__restrict__ pr, uint8_t *__restrict__ mask, int n, int first, int stride,
-                                            const float *T10, double *acc)
+// Residuals / Jacobian rows of ONE point handed to a sink, one call per row in the reference's row order (per-point
+// arithmetic in the reference's FP32 operation order; motion_estimator.cpp:720-800 mono, :915-1050 stereo).
+// sink.row<ZERO>(Jt, weight, r, weighted, e): ZERO = index of the structurally zero Jacobian entry of the row
+// (calcJtWJ_x / _y), e = the row's error term.
+template <class Sink>
+__device__ __forceinline__ void pose_point(const PoseArgs &a, const float *__restrict__ X, const float *__restrict__ pl,
+                                           const float *__restrict__ pr, uint8_t *__restrict__ mask, int i, const float *T10,
+                                           Sink &sink)
 {
     const float fx_l = a.Kl[0], fy_l = a.Kl[1], cx_l = a.Kl[2], cy_l = a.Kl[3];
     const float fx_r = a.Kr[0], fy_r = a.Kr[1], cx_r = a.Kr[2], cy_r = a.Kr[3];
     const float THRES_HUBER = 0.5f;
-    for (int i = first; i < n; i += stride) {
-        const float x0 = X[3 * i], x1 = X[3 * i + 1], x2 = X[3 * i + 2];
-        float Xl[3];
+    const float x0 = X[3 * i], x1 = X[3 * i + 1], x2 = X[3 * i + 2];
+    float Xl[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) Xl[r] = ((T10[r * 4 + 0] * x0 + T10[r * 4 + 1] * x1) + T10[r * 4 + 2] * x2) + T10[r * 4 + 3];
-        const float iz_l = 1.0f / Xl[2], xiz_l = Xl[0] * iz_l, yiz_l = Xl[1] * iz_l;
-        const float fxxiz_l = fx_l * xiz_l, fyyiz_l = fy_l * yiz_l;
-        const float rx_l = (fxxiz_l + cx_l) - pl[2 * i], ry_l = (fyyiz_l + cy_l) - pl[2 * i + 1];
-        float Jt[6];
-        if (a.mono) {
-            float weight = 1.0f;
-            bool fw = false;
-            const float absrxry = fabsf(rx_l) + fabsf(ry_l);
-            if (absrxry >= THRES_HUBER) { weight = THRES_HUBER / absrxry; fw = true; }
-            mask[i] = (absrxry >= a.thres) ? 0 : 1;
-            Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
-            Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
-            acc_row<1>(acc, Jt, weight, rx_l, fw);
-            acc[27] += (double)(rx_l * rx_l);
-            Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
-            Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
-            acc_row<0>(acc, Jt, weight, ry_l, fw);
-            if (fw && a.variant == 0) acc[27] += (double)((weight * ry_l) * ry_l);
-            else acc[27] += (double)(ry_l * ry_l);
-        } else {
-            float Xr[3];
+    for (int r = 0; r < 3; ++r) Xl[r] = ((T10[r * 4 + 0] * x0 + T10[r * 4 + 1] * x1) + T10[r * 4 + 2] * x2) + T10[r * 4 + 3];
+    const float iz_l = 1.0f / Xl[2], xiz_l = Xl[0] * iz_l, yiz_l = Xl[1] * iz_l;
+    const float fxxiz_l = fx_l * xiz_l, fyyiz_l = fy_l * yiz_l;
+    const float rx_l = (fxxiz_l + cx_l) - pl[2 * i], ry_l = (fyyiz_l + cy_l) - pl[2 * i + 1];
+    float Jt[6];
+    if (a.mono) {
+        float weight = 1.0f;
+        bool fw = false;
+        const float absrxry = fabsf(rx_l) + fabsf(ry_l);
+        if (absrxry >= THRES_HUBER) { weight = THRES_HUBER / absrxry; fw = true; }
+        mask[i] = (absrxry >= a.thres) ? 0 : 1;
+        Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
+        Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
+        sink.template row<1>(Jt, weight, rx_l, fw, rx_l * rx_l);
+        Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
+        Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
+        sink.template row<0>(Jt, weight, ry_l, fw, (fw && a.variant == 0) ? (weight * ry_l) * ry_l : ry_l * ry_l);
+    } else {
+        float Xr[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-                Xr[r] = ((a.T_rl[r * 4 + 0] * Xl[0] + a.T_rl[r * 4 + 1] * Xl[1]) + a.T_rl[r * 4 + 2] * Xl[2]) + a.T_rl[r * 4 + 3];
-            const float iz_r = 1.0f / Xr[2], xiz_r = Xr[0] * iz_r, yiz_r = Xr[1] * iz_r;
-            const float fxxiz_r = fx_r * xiz_r, fyyiz_r = fy_r * yiz_r;
-            const float rx_r = (fxxiz_r + cx_r) - pr[2 * i], ry_r = (fyyiz_r + cy_r) - pr[2 * i + 1];
-            float weight = 1.0f;
-            float absrxry = fabsf(rx_l) + fabsf(ry_l) + fabsf(rx_r) + fabsf(ry_r);
-            absrxry *= 0.5f;
-            if (absrxry >= THRES_HUBER) weight = THRES_HUBER / absrxry;
-            mask[i] = (absrxry >= a.thres) ? 0 : 1;
-            Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
-            Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
-            acc_row<1>(acc, Jt, weight, rx_l, true); acc[27] += (double)(rx_l * rx_l);
-            Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
-            Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
-            acc_row<0>(acc, Jt, weight, ry_l, true); acc[27] += (double)(ry_l * ry_l);
-            Jt[0] = fx_r * iz_r; Jt[1] = 0.f; Jt[2] = -fxxiz_r * iz_r; Jt[3] = -fxxiz_r * yiz_r;
-            Jt[4] = fx_r * (1.0f + xiz_r * xiz_r); Jt[5] = -fx_r * yiz_r;
-            acc_row<1>(acc, Jt, weight, rx_r, true); acc[27] += (double)(rx_r * rx_r);
-            Jt[0] = 0.f; Jt[1] = fy_r * iz_r; Jt[2] = -fyyiz_r * iz_r; Jt[3] = -fy_r * (1.0f + yiz_r * yiz_r);
-            Jt[4] = fyyiz_r * xiz_r; Jt[5] = fy_r * xiz_r;
-            acc_row<0>(acc, Jt, weight, ry_r, true); acc[27] += (double)(ry_r * ry_r);
-        }
+        for (int r = 0; r < 3; ++r)
+            Xr[r] = ((a.T_rl[r * 4 + 0] * Xl[0] + a.T_rl[r * 4 + 1] * Xl[1]) + a.T_rl[r * 4 + 2] * Xl[2]) + a.T_rl[r * 4 + 3];
+        const float iz_r = 1.0f / Xr[2], xiz_r = Xr[0] * iz_r, yiz_r = Xr[1] * iz_r;
+        const float fxxiz_r = fx_r * xiz_r, fyyiz_r = fy_r * yiz_r;
+        const float rx_r = (fxxiz_r + cx_r) - pr[2 * i], ry_r = (fyyiz_r + cy_r) - pr[2 * i + 1];
+        float weight = 1.0f;
+        float absrxry = fabsf(rx_l) + fabsf(ry_l) + fabsf(rx_r) + fabsf(ry_r);
+        absrxry *= 0.5f;
+        if (absrxry >= THRES_HUBER) weight = THRES_HUBER / absrxry;
+        mask[i] = (absrxry >= a.thres) ? 0 : 1;
+        Jt[0] = fx_l * iz_l; Jt[1] = 0.f; Jt[2] = -fxxiz_l * iz_l; Jt[3] = -fxxiz_l * yiz_l;
+        Jt[4] = fx_l * (1.0f + xiz_l * xiz_l); Jt[5] = -fx_l * yiz_l;
+        sink.template row<1>(Jt, weight, rx_l, true, rx_l * rx_l);
+        Jt[0] = 0.f; Jt[1] = fy_l * iz_l; Jt[2] = -fyyiz_l * iz_l; Jt[3] = -fy_l * (1.0f + yiz_l * yiz_l);
+        Jt[4] = fyyiz_l * xiz_l; Jt[5] = fy_l * xiz_l;
+        sink.template row<0>(Jt, weight, ry_l, true, ry_l * ry_l);
+        Jt[0] = fx_r * iz_r; Jt[1] = 0.f; Jt[2] = -fxxiz_r * iz_r; Jt[3] = -fxxiz_r * yiz_r;
+        Jt[4] = fx_r * (1.0f + xiz_r * xiz_r); Jt[5] = -fx_r * yiz_r;
+        sink.template row<1>(Jt, weight, rx_r, true, rx_r * rx_r);
+        Jt[0] = 0.f; Jt[1] = fy_r * iz_r; Jt[2] = -fyyiz_r * iz_r; Jt[3] = -fy_r * (1.0f + yiz_r * yiz_r);
+        Jt[4] = fyyiz_r * xiz_r; Jt[5] = fy_r * xiz_r;
+        sink.template row<0>(Jt, weight, ry_r, true, ry_r * ry_r);
     }
+}
+
+// Default ("fast") sink: 28 FP64 partials per thread, tree-reduced afterwards.
+struct AccSink {
+    double *acc;
+    template <int ZERO>
+    __device__ __forceinline__ void row(const float *Jt, float w, float r, bool weighted, float e)
+    {
+        acc_row<ZERO>(acc, Jt, w, r, weighted);
+        acc[27] += (double)e;
+    }
+};
+
+__device__ __forceinline__ void pose_points(const PoseArgs &a, const float *__restrict__ X, const float *__restrict__ pl,
+                                            const float *__restrict__ pr, uint8_t *__restrict__ mask, int n, int first, int stride,
+                                            const float *T10, double *acc)
+{
+    AccSink sink{acc};
+    for (int i = first; i < n; i += stride) pose_point(a, X, pl, pr, mask, i, T10, sink);
 }
 
 // The serial part of one GN iteration (one thread): normal equations from the reduced partials, damped 6x6 LDLT,
 // se3Exp_f, left-multiplication of T10, stop test (motion_estimator.cpp:803-840 / :1052-1070).
-__device__ __forceinline__ void pose_solve(const PoseArgs &a, const double *red, int n, float *s_T10, float *s_err_prev, int *s_stop)
+__device__ __forceinline__ void pose_solve(const PoseArgs &a, const double *red, int n, float *s_T10, float *s_err_prev, int *s_stop,
+                                           int prob, int iter)
 {
             float H[36], g[6];
             int idx = 0;
@@ -332,7 +353,14 @@ __device__ __forceinline__ void pose_solve(const PoseArgs &a, const double *red,
             float nrm = 0.f;
             for (int i = 0; i < 6; ++i) nrm += dxi[i] * dxi[i];
             nrm = sqrtf(nrm);
-            *s_stop = (nrm < 1e-6f || delta_err < 1e-7f) ? 1 : 0;
+            *s_stop = (!a.no_early_stop && (nrm < 1e-6f || delta_err < 1e-7f)) ? 1 : 0;
+            if (a.trace) {
+                float *tr = a.trace + ((size_t)prob * a.max_iter + iter) * 24;
+                for (int i = 0; i < 16; ++i) tr[i] = Tn[i];
+                tr[16] = err_curr;
+                for (int i = 0; i < 6; ++i) tr[17 + i] = dxi[i];
+                tr[23] = delta_err;
+            }
 }
 
 // THREADS per problem: 128 for the batched small problems (4 resident CTAs per SM overlap the serial solve of one
@@ -369,7 +397,7 @@ k_pose_gn(const PoseArgs a)
     __syncthreads();
 
     int iter = 0;
-    for (; iter < POSE_MAX_ITER; ++iter) {
+    for (; iter < a.max_iter; ++iter) {
         float T10[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) T10[i] = s_T10[i];
@@ -394,7 +422,7 @@ k_pose_gn(const PoseArgs a)
             s_part[0][tid] = v;
         }
         __syncthreads();
-        if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop);
+        if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop, prob, iter);
         __syncthreads();
         if (s_stop) { ++iter; break; }
     }
@@ -449,7 +477,7 @@ k_pose_gn_cluster(const PoseArgs a)
     cluster.sync();
     double *cta_row_on_rank0 = cluster.map_shared_rank(&s_cta[0][0], 0) + rank * NACC;
     int iter = 0;
-    for (; iter < POSE_MAX_ITER; ++iter) {
+    for (; iter < a.max_iter; ++iter) {
         float T10[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) T10[i] = s_T10[i];
@@ -480,7 +508,7 @@ k_pose_gn_cluster(const PoseArgs a)
                 s_part[0][tid] = v;
             }
             __syncthreads();
-            if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop);
+            if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop, 0, iter);
             __syncthreads();
             // broadcast the new pose (16 floats) and the stop flag to the other CTAs
             if (tid < 17 * (POSE_CLUSTER - 1)) {
@@ -507,6 +535,157 @@ k_pose_gn_cluster(const PoseArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// STRICT-ORDER mode: the reference adds every row's contribution to JtWJ / mJtWr / err_curr one after the other in
+// FP32, in point order (motion_estimator.cpp:770-800, :990-1040) -- and its stop test `delta_err < 1e-7` on an FP32
+// error of order 1 px only fires when that sum repeats (almost) bit for bit, so the stop iteration depends on the
+// summation order.  This kernel reproduces the order exactly: producer warps evaluate the rows of a chunk of points
+// (one point per lane, same FP32 arithmetic as the default kernel) and park {Jt, w*Jt, -w*r, e} per row in shared
+// memory; ONE consumer warp owns the 28 sums, one per lane, and walks the rows sequentially
+// (acc = acc + a*b, un-fused), i.e. 28 independent dependent-add chains of 4N (stereo) / 2N (mono) links -- the
+// chain latency (4 cycles per row) is the cost: about 16 us per iteration at N = 2000.  Chunks are double-buffered so
+// the producers stay ahead of the consumer.  Structurally zero entries contribute a*0 = +-0, which leaves an FP32 sum
+// unchanged, exactly like the `+= JtJ_tmp` of the zero-filled temporary in the reference.
+// Row record = 16 floats: [0..5] Jt, [6..11] w*Jt, [12] -(w*r), [13] e, [14] 1, [15] 0; its four 16-byte quads are
+// XOR-swizzled with (point & 3) so the producers' 128-bit stores of neighbouring points spread over the banks.
+#define STRICT_PTS 64                  // points per chunk = 2 producer warps x 32 lanes
+#define STRICT_THREADS 96              // warp 0 = consumer, warps 1..2 = producers
+
+template <int RPP>
+struct RecSink {
+    float *rec;      // first record of this lane's point
+    int swz;         // point & 3
+    int k;           // next row
+    template <int ZERO>
+    __device__ __forceinline__ void row(const float *Jt, float w, float r, bool weighted, float e)
+    {
+        float wJ[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) wJ[i] = weighted ? w * Jt[i] : Jt[i];
+        const float wr = weighted ? w * r : r;
+        float4 *q = reinterpret_cast<float4 *>(rec + k * 16);
+        q[0 ^ swz] = make_float4(Jt[0], Jt[1], Jt[2], Jt[3]);
+        q[1 ^ swz] = make_float4(Jt[4], Jt[5], wJ[0], wJ[1]);
+        q[2 ^ swz] = make_float4(wJ[2], wJ[3], wJ[4], wJ[5]);
+        q[3 ^ swz] = make_float4(-wr, e, 1.0f, 0.f);
+        ++k;
+    }
+};
+
+template <int RPP>   // rows per point: 2 mono, 4 stereo
+__global__ void __launch_bounds__(STRICT_THREADS)
+k_pose_gn_strict(const PoseArgs a)
+{
+    __shared__ __align__(16) float s_rec[2][STRICT_PTS * RPP * 16];
+    __shared__ double s_red[NACC];
+    __shared__ float s_T10[16];
+    __shared__ int s_stop;
+    __shared__ float s_err_prev;
+
+    const int prob = blockIdx.x;
+    const int beg = a.offsets ? a.offsets[prob] : 0;
+    const int n = a.offsets ? a.offsets[prob + 1] - beg : (a.n_single_d ? *a.n_single_d : a.n_single);
+    const float *X = a.X + 3 * (size_t)beg;
+    const float *pl = a.pl + 2 * (size_t)beg;
+    const float *pr = a.mono ? nullptr : a.pr + 2 * (size_t)beg;
+    uint8_t *mask = a.mask + beg;
+    float *T01 = a.T01 + 16 * (size_t)prob;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) {
+        float T[16], Ti[16];
+        for (int i = 0; i < 16; ++i) T[i] = T01[i];
+        if (a.mono) inverse4(T, Ti);
+        else inv_se3(T, Ti);
+        for (int i = 0; i < 16; ++i) s_T10[i] = Ti[i];
+        s_stop = 0;
+        s_err_prev = 1e10f;
+    }
+    __syncthreads();
+
+    // consumer lane -> the two record words it multiplies: H(i,j) = sum (w*Jt[i]) * Jt[j]; g(i) = sum (-(w*r)) * Jt[i];
+    // err = sum e * 1
+    int wa = 14, wb = 14;
+    if (lane < 21) {
+        int idx = 0;
+        for (int i = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j, ++idx)
+                if (idx == lane) { wa = 6 + i; wb = j; }
+    } else if (lane < 27) { wa = 12; wb = lane - 21; }
+    else if (lane == 27) { wa = 13; wb = 14; }
+    int offa[4], offb[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        offa[s] = ((((wa >> 2) ^ s) << 2) | (wa & 3));
+        offb[s] = ((((wb >> 2) ^ s) << 2) | (wb & 3));
+    }
+
+    const int n_chunks = (n + STRICT_PTS - 1) / STRICT_PTS;
+    int iter = 0;
+    for (; iter < a.max_iter; ++iter) {
+        float T10[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T10[i] = s_T10[i];
+        float acc = 0.f;
+        for (int c = 0; c <= n_chunks; ++c) {
+            if (wid > 0) {
+                if (c < n_chunks) {
+                    // producer: point (c*64 + p), p = lane of producer warp 1 / 2
+                    const int p = (wid - 1) * 32 + lane;
+                    const int i = c * STRICT_PTS + p;
+                    float *rec = &s_rec[c & 1][p * RPP * 16];
+                    if (i < n) {
+                        RecSink<RPP> sink{rec, p & 3, 0};
+                        pose_point(a, X, pl, pr, mask, i, T10, sink);
+                    } else if (i < ((n + 3) & ~3)) {
+                        // pad the last group of four points with all-zero rows (+0 leaves every sum unchanged)
+                        float4 *q = reinterpret_cast<float4 *>(rec);
+#pragma unroll
+                        for (int k = 0; k < RPP * 4; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            } else if (c > 0) {
+                // consumer: chunk c-1, groups of four points (= 4*RPP rows, swizzle pattern known at compile time)
+                const int cc = c - 1;
+                const int npts = min(STRICT_PTS, n - cc * STRICT_PTS);
+                const int groups = (npts + 3) >> 2;
+                const float *buf = s_rec[cc & 1];
+                for (int g = 0; g < groups; ++g) {
+                    const float *gb = buf + g * (4 * RPP * 16);
+                    float va[4 * RPP], vb[4 * RPP];
+#pragma unroll
+                    for (int r = 0; r < 4 * RPP; ++r) {
+                        va[r] = gb[r * 16 + offa[r / RPP]];
+                        vb[r] = gb[r * 16 + offb[r / RPP]];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4 * RPP; ++r) acc = acc + va[r] * vb[r];
+                }
+            }
+            __syncthreads();
+        }
+        if (wid == 0 && lane < NACC) s_red[lane] = (double)acc;
+        __syncthreads();
+        if (tid == 0) pose_solve(a, s_red, n, s_T10, &s_err_prev, &s_stop, prob, iter);
+        __syncthreads();
+        if (s_stop) { ++iter; break; }
+    }
+    if (tid == 0) {
+        float nrm2 = 0.f;
+        for (int i = 0; i < 16; ++i) nrm2 += s_T10[i] * s_T10[i];
+        const bool ok = !isnan(nrm2);
+        if (ok) {
+            float T10[16], Ti[16];
+            for (int i = 0; i < 16; ++i) T10[i] = s_T10[i];
+            inv_se3(T10, Ti);
+            for (int i = 0; i < 16; ++i) T01[i] = Ti[i];
+        }
+        if (a.success) a.success[prob] = ok ? 1 : 0;
+        if (a.iters) a.iters[prob] = iter;
+    }
+}
+
 static void host_inv_se3(const float *T, float *O)
 {
     for (int i = 0; i < 3; ++i) {
@@ -518,9 +697,10 @@ static void host_inv_se3(const float *T, float *O)
     O[12] = O[13] = O[14] = 0.f; O[15] = 1.f;
 }
 
-int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
-                     const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
-                     int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d)
+int vo_pose_launch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
+                        const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
+                        int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d, int flags,
+                        int max_iter, float *trace_d)
 {
     PoseArgs a;
     a.offsets = offsets_d; a.n_single = n_single; a.n_single_d = n_single_d;
@@ -530,22 +710,62 @@ int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single
     else { for (int i = 0; i < 16; ++i) a.T_rl[i] = (i % 5 == 0) ? 1.f : 0.f; }
     a.thres = thres; a.mono = mono; a.variant = variant;
     a.T01 = T01_d; a.mask = mask_d; a.success = success_d; a.iters = iters_d;
-    static const int force = getenv("VO_POSE_THREADS") ? atoi(getenv("VO_POSE_THREADS")) : 0;   // tuning switch
-    // one large problem (n_single = exact count or upper bound): thread-block cluster of 8 CTAs
-    static const bool no_cluster = getenv("VO_POSE_NO_CLUSTER") != nullptr;
-    if (!force && !no_cluster && n_prob == 1 && !offsets_d && n_single >= 1024) {
-        k_pose_gn_cluster<<<POSE_CLUSTER, 256, 0, ctx->stream>>>(a);
-        ctx->launches++;
+    a.max_iter = (max_iter > 0 && max_iter < POSE_MAX_ITER) ? max_iter : POSE_MAX_ITER;
+    a.no_early_stop = (flags & VO_POSE_NO_EARLY_STOP) ? 1 : 0;
+    a.trace = trace_d;
+    ctx->launches++;
+    if (flags & VO_POSE_STRICT) {
+        // sequential FP32 sums in point order: one CTA per problem whatever its size (the consumer chain is the cost)
+        if (mono) k_pose_gn_strict<2><<<n_prob, STRICT_THREADS, 0, ctx->stream>>>(a);
+        else k_pose_gn_strict<4><<<n_prob, STRICT_THREADS, 0, ctx->stream>>>(a);
         VO_CUDA(cudaGetLastError());
         return VO_OK;
     }
-    const int thr = force ? force : (n_prob > 1 ? 128 : 512);
-    if (thr <= 128) k_pose_gn<128><<<n_prob, 128, 0, ctx->stream>>>(a);
-    else if (thr <= 256) k_pose_gn<256><<<n_prob, 256, 0, ctx->stream>>>(a);
+    // one large problem (n_single = exact count or upper bound): thread-block cluster of 8 CTAs
+    if (n_prob == 1 && !offsets_d && n_single >= 1024) {
+        k_pose_gn_cluster<<<POSE_CLUSTER, 256, 0, ctx->stream>>>(a);
+        VO_CUDA(cudaGetLastError());
+        return VO_OK;
+    }
+    if (n_prob > 1) k_pose_gn<128><<<n_prob, 128, 0, ctx->stream>>>(a);
     else k_pose_gn<512><<<n_prob, 512, 0, ctx->stream>>>(a);
-    ctx->launches++;
     VO_CUDA(cudaGetLastError());
     return VO_OK;
+}
+
+int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
+                     const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
+                     int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d)
+{
+    return vo_pose_launch_ex_d(ctx, n_prob, offsets_d, n_single, n_single_d, X_d, pl_d, pr_d, Kl, Kr, T_lr, thres, mono, variant,
+                               T01_d, mask_d, success_d, iters_d, ctx->pose_flags & VO_POSE_STRICT, 0, nullptr);
+}
+
+extern "C" int vo_set_pose_mode(vo_ctx *ctx, int flags)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE((flags & ~VO_POSE_STRICT) == 0, VO_ERR_INVALID_ARG, "vo_set_pose_mode: VO_POSE_FAST or VO_POSE_STRICT");
+    ctx->pose_flags = flags;
+    return VO_OK;
+}
+
+extern "C" int vo_get_pose_mode(const vo_ctx *ctx) { return ctx ? ctx->pose_flags : VO_ERR_INVALID_ARG; }
+
+extern "C" int vo_pose_gn_stereo_batch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, const float *X_d,
+                                            const float *pts_l1_d, const float *pts_r1_d, const float *K_l4,
+                                            const float *K_r4, const float *T_lr, float thres_reproj_outlier,
+                                            float *T01_inout_d, uint8_t *mask_inlier_d, int *success_d, int *iters_d,
+                                            int flags, int max_iter, float *trace_d)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n_prob >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n_prob == 0) return VO_OK;
+    VO_REQUIRE(offsets_d && X_d && pts_l1_d && pts_r1_d && K_l4 && K_r4 && T_lr && T01_inout_d && mask_inlier_d,
+               VO_ERR_INVALID_ARG, "null pointer");
+    VO_REQUIRE((flags & ~(VO_POSE_STRICT | VO_POSE_NO_EARLY_STOP)) == 0 && max_iter >= 0, VO_ERR_INVALID_ARG, "bad pose flags");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_pose_launch_ex_d(ctx, n_prob, offsets_d, 0, nullptr, X_d, pts_l1_d, pts_r1_d, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0,
+                               T01_inout_d, mask_inlier_d, success_d, iters_d, flags, max_iter, trace_d);
 }
 
 extern "C" int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, const float *X_d,
@@ -554,23 +774,21 @@ extern "C" int vo_pose_gn_stereo_batch_d(vo_ctx *ctx, int n_prob, const int *off
                                          float *T01_inout_d, uint8_t *mask_inlier_d, int *success_d, int *iters_d)
 {
     if (!ctx) return VO_ERR_INVALID_ARG;
-    VO_REQUIRE(n_prob >= 0, VO_ERR_INVALID_ARG, "negative size");
-    if (n_prob == 0) return VO_OK;
-    VO_REQUIRE(offsets_d && X_d && pts_l1_d && pts_r1_d && K_l4 && K_r4 && T_lr && T01_inout_d && mask_inlier_d,
-               VO_ERR_INVALID_ARG, "null pointer");
-    VO_CUDA(cudaSetDevice(ctx->device));
-    return vo_pose_launch_d(ctx, n_prob, offsets_d, 0, nullptr, X_d, pts_l1_d, pts_r1_d, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0,
-                       T01_inout_d, mask_inlier_d, success_d, iters_d);
+    return vo_pose_gn_stereo_batch_ex_d(ctx, n_prob, offsets_d, X_d, pts_l1_d, pts_r1_d, K_l4, K_r4, T_lr, thres_reproj_outlier,
+                                        T01_inout_d, mask_inlier_d, success_d, iters_d, ctx->pose_flags & VO_POSE_STRICT, 0, nullptr);
 }
 
 // Host-pointer single-problem entry points: one H2D, one launch, one D2H.
 static int pose_host(vo_ctx *ctx, const float *X, const float *pl, const float *pr, int n, const float *Kl,
                      const float *Kr, const float *T_lr, float thres, int mono, int variant, float *T01_inout,
-                     uint8_t *mask, int *success, int *iters_out)
+                     uint8_t *mask, int *success, int *iters_out, int flags, int max_iter, float *trace)
 {
+    VO_REQUIRE((flags & ~(VO_POSE_STRICT | VO_POSE_NO_EARLY_STOP)) == 0 && max_iter >= 0, VO_ERR_INVALID_ARG, "bad pose flags");
     VO_CUDA(cudaSetDevice(ctx->device));
+    const int mi = (max_iter > 0 && max_iter < POSE_MAX_ITER) ? max_iter : POSE_MAX_ITER;
+    const size_t trace_bytes = trace ? (size_t)mi * 24 * sizeof(float) : 0;
     const size_t oX = 0, oPl = oX + (size_t)n * 12, oPr = oPl + (size_t)n * 8, oT = oPr + (size_t)n * 8;
-    const size_t oFlags = oT + 64, oMask = oFlags + 16, total = oMask + (size_t)n + 64;
+    const size_t oFlags = oT + 64, oMask = oFlags + 16, oTrace = (oMask + (size_t)n + 63) & ~(size_t)63, total = oTrace + trace_bytes + 64;
     int rc = vo_stage_reserve(ctx, total);
     if (rc) return rc;
     uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
@@ -579,14 +797,17 @@ static int pose_host(vo_ctx *ctx, const float *X, const float *pl, const float *
     if (pr) memcpy(h + oPr, pr, (size_t)n * 8);
     memcpy(h + oT, T01_inout, 64);
     VO_CUDA(cudaMemcpyAsync(d, h, oFlags, cudaMemcpyHostToDevice, ctx->stream));
-    rc = vo_pose_launch_d(ctx, 1, nullptr, n, nullptr, (const float *)(d + oX), (const float *)(d + oPl), (const float *)(d + oPr), Kl, Kr,
-                     T_lr, thres, mono, variant, (float *)(d + oT), d + oMask, (int *)(d + oFlags), (int *)(d + oFlags + 4));
+    if (trace) VO_CUDA(cudaMemsetAsync(d + oTrace, 0, trace_bytes, ctx->stream));
+    rc = vo_pose_launch_ex_d(ctx, 1, nullptr, n, nullptr, (const float *)(d + oX), (const float *)(d + oPl), (const float *)(d + oPr), Kl, Kr,
+                             T_lr, thres, mono, variant, (float *)(d + oT), d + oMask, (int *)(d + oFlags), (int *)(d + oFlags + 4), flags, mi,
+                             trace ? (float *)(d + oTrace) : nullptr);
     if (rc) return rc;
     VO_CUDA(cudaMemcpyAsync(h + oT, d + oT, total - oT, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     const int ok = *(int *)(h + oFlags);
     if (ok) memcpy(T01_inout, h + oT, 64);
     memcpy(mask, h + oMask, (size_t)n);
+    if (trace) memcpy(trace, h + oTrace, trace_bytes);
     if (success) *success = ok;
     if (iters_out) *iters_out = *(int *)(h + oFlags + 4);
     return VO_OK;
@@ -597,17 +818,37 @@ extern "C" int vo_pose_gn_stereo(vo_ctx *ctx, const float *X, const float *pts_l
                                  float *T01_inout, uint8_t *mask_inlier, int *success, int *iters_out)
 {
     if (!ctx) return VO_ERR_INVALID_ARG;
+    return vo_pose_gn_stereo_ex(ctx, X, pts_l1, pts_r1, n, K_l4, K_r4, T_lr, thres_reproj_outlier, T01_inout, mask_inlier, success,
+                                iters_out, ctx->pose_flags & VO_POSE_STRICT, 0, nullptr);
+}
+
+extern "C" int vo_pose_gn_stereo_ex(vo_ctx *ctx, const float *X, const float *pts_l1, const float *pts_r1, int n,
+                                    const float *K_l4, const float *K_r4, const float *T_lr, float thres_reproj_outlier,
+                                    float *T01_inout, uint8_t *mask_inlier, int *success, int *iters_out, int flags,
+                                    int max_iter, float *trace)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
     VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
     VO_REQUIRE(K_l4 && K_r4 && T_lr && T01_inout, VO_ERR_INVALID_ARG, "null pointer");
     if (n == 0) { if (success) *success = 1; if (iters_out) *iters_out = 1; return VO_OK; }
     VO_REQUIRE(X && pts_l1 && pts_r1 && mask_inlier, VO_ERR_INVALID_ARG, "null pointer");
     return pose_host(ctx, X, pts_l1, pts_r1, n, K_l4, K_r4, T_lr, thres_reproj_outlier, 0, 0, T01_inout, mask_inlier,
-                     success, iters_out);
+                     success, iters_out, flags, max_iter, trace);
 }
 
 extern "C" int vo_pose_gn_mono(vo_ctx *ctx, const float *X, const float *pts1, int n, float fx, float fy, float cx,
                                float cy, int thres_reproj_outlier, int standalone_variant, float *R01_inout,
                                float *t01_inout, uint8_t *mask_inlier, int *success, int *iters_out)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    return vo_pose_gn_mono_ex(ctx, X, pts1, n, fx, fy, cx, cy, thres_reproj_outlier, standalone_variant, R01_inout, t01_inout,
+                              mask_inlier, success, iters_out, ctx->pose_flags & VO_POSE_STRICT, 0, nullptr);
+}
+
+extern "C" int vo_pose_gn_mono_ex(vo_ctx *ctx, const float *X, const float *pts1, int n, float fx, float fy, float cx,
+                                  float cy, int thres_reproj_outlier, int standalone_variant, float *R01_inout,
+                                  float *t01_inout, uint8_t *mask_inlier, int *success, int *iters_out, int flags,
+                                  int max_iter, float *trace)
 {
     if (!ctx) return VO_ERR_INVALID_ARG;
     VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
@@ -620,7 +861,7 @@ extern "C" int vo_pose_gn_mono(vo_ctx *ctx, const float *X, const float *pts1, i
     const float K[4] = {fx, fy, cx, cy};
     int ok = 0;
     int rc = pose_host(ctx, X, pts1, nullptr, n, K, K, nullptr, (float)thres_reproj_outlier, 1, standalone_variant ? 1 : 0, T, mask_inlier, &ok,
-                       iters_out);
+                       iters_out, flags, max_iter, trace);
     if (rc) return rc;
     if (ok) for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R01_inout[i * 3 + j] = T[i * 4 + j]; t01_inout[i] = T[i * 4 + 3]; }
     if (success) *success = ok;

@@ -1,5 +1,6 @@
 // vo_internal.cuh -- shared device/host structures of libvo_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the driver entry point is fetched at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -44,6 +45,7 @@ struct Slot {
     int deriv_built = 0;      // derivative levels valid
     bool border0 = false;     // level-0 border filled
     bool raw_pending = false; // pixels sit in the raw staging area, not yet ingested into level 0
+    int tmap_win = 0;         // LK window size the slot's device tensor maps were encoded for (0 = none / stale)
 };
 
 struct vo_ctx {
@@ -57,6 +59,7 @@ struct vo_ctx {
     int max_w = 0, max_h = 0, n_slots = 0, max_feat = 0;
     std::vector<Slot> slots;
     SlotDesc *d_slots = nullptr;   // device mirror of all slot descriptors
+    CUtensorMap *d_tmaps = nullptr;   // [n_slots][VO_MAX_LEVELS][3] TMA descriptors of the pyramid planes (klt.cu)
     uint8_t *raw_base = nullptr;   // n_slots x raw_stride bytes: contiguous upload staging
     size_t raw_stride = 0;
     int max_levels = 0;            // levels allocated per slot
@@ -65,6 +68,7 @@ struct vo_ctx {
     uint8_t *d_stage = nullptr;
     size_t stage_bytes = 0;
     long long launches = 0;
+    int pose_flags = 0;            // VO_POSE_FAST / VO_POSE_STRICT (vo_set_pose_mode)
     std::string last_error;
     // trackWithScale scratch (float image + Sobel derivatives), lazily allocated
     float *d_f32[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -138,6 +142,11 @@ int vo_klt_scale_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d
 int vo_pose_launch_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
                      const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
                      int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d);
+
+int vo_pose_launch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_single, const int *n_single_d, const float *X_d,
+                        const float *pl_d, const float *pr_d, const float *Kl, const float *Kr, const float *T_lr, float thres,
+                        int mono, int variant, float *T01_d, uint8_t *mask_d, int *success_d, int *iters_d, int flags,
+                        int max_iter, float *trace_d);
 
 int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, const float *pts_l0_d, float *pts_l1_d, float *pts_r1_d,
                             const float *scale_d, uint8_t *mask_d, int *nan_flag_d, int n, int win, int max_level, float thres_err,

@@ -460,12 +460,16 @@ bool MonoVO::statsConsistent() const
 void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
 {
     if (img.empty()) throw std::runtime_error("vo_b200: empty image");
+    // A frame is COMMITTED (frame list, image-slot parity, landmark tables) only once its device step has succeeded: a
+    // step that throws before that point ("calcPose5PointsAlgorithm() is failed.", a CUDA error) leaves the object exactly
+    // as it was, so the caller may feed the next image.  An exception after that point (local BA NaN / "large update!")
+    // leaves the tables half updated -- the reference dies there too -- and the object refuses further images.
+    if (poisoned_) throw std::runtime_error("vo_b200: MonoVO state is inconsistent after a failed keyframe step; create a new object");
     const int w = img.cols, h = img.rows;
     const auto t_total = Clock::now();
     auto fr = std::make_shared<FrameRec>();
     fr->id = (int)frames_.size();
     ident(fr->Twc); ident(fr->Tcw); ident(fr->dT01); ident(fr->dT10);
-    frames_.push_back(fr);
     info_ = FrameInfo();
     info_.frame = fr->id;
     const int k = fr->id;
@@ -507,6 +511,8 @@ void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
         }
         const int rc = vo_detect_bucketed(ctx_, s1, nullptr, 0, p_.n_bins_u, p_.n_bins_v, p_.det_edge, p_.det_min_score, new_p1_.data(), std::max(nb, 1), &n_det);
         if (rc) fail(ctx_, rc);
+        frames_.push_back(fr);                       // commit point
+        poisoned_ = true;
         const int base = newLandmarks(n_det, new_p1_.data(), *fr);
         fr->pts.assign(new_p1_.begin(), new_p1_.begin() + 2 * (size_t)n_det);
         fr->lm_ids.resize(n_det);
@@ -538,6 +544,8 @@ void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
                                           pv.Twc, pv.dT01, &res);
         if (rc == VO_ERR_MODE) throw std::runtime_error(vo_last_error(ctx_));      // "calcPose5PointsAlgorithm() is failed." (:590 / :940)
         if (rc) fail(ctx_, rc);
+        frames_.push_back(fr);                       // commit point
+        poisoned_ = true;
         info_.ms_step = ms_since(t_step);
         const int nt = res.n_tracked, m = res.n_new;
         fr->lm_ids.resize((size_t)nt + m);
@@ -589,6 +597,7 @@ void MonoVO::trackImage(const cv::Mat &img, const double & /*timestamp*/)
         std::vector<int>().swap(prev_->lm_ids);
     }
     prev_ = fr;
+    poisoned_ = false;
 }
 
 // ------------------------------------------------------------------------------ C wrapper

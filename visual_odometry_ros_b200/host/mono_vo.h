@@ -152,6 +152,7 @@ private:
     int seen_stamp_ = 0;
     std::vector<FrameRecPtr> frames_;      // all frames (poses stay readable: parallax and reconstruction use them)
     FrameRecPtr prev_;
+    bool poisoned_ = false;      // an exception escaped after the frame was committed (see trackImage)
     std::deque<FrameRecPtr> window_;
     std::vector<FrameRecPtr> all_keyframes_;
     // per-frame scratch

@@ -358,9 +358,14 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
         throw std::runtime_error("vo_b200: bad stereo image pair");
     const int w = img_left.cols, h = img_left.rows;
     if (img_left.step != img_right.step) throw std::runtime_error("vo_b200: left/right row pitch differ");
+    // A frame is COMMITTED (frame counter = image-slot parity, landmark tables) only once its device step has succeeded: a
+    // step that throws before that point ("PoseOnlyStereoBA is failed!", a CUDA error) leaves the object as it was, so the
+    // next call still tracks from prev_'s image slot.  An exception after that point (local BA NaN / "large update!")
+    // leaves the tables half updated -- the reference dies there too -- and the object refuses further images.
+    if (poisoned_) throw std::runtime_error("vo_b200: StereoVO state is inconsistent after a failed keyframe step; create a new object");
     const auto t_total = Clock::now();
     auto fr = std::make_shared<FrameRec>();
-    fr->id = n_frames_++;
+    fr->id = n_frames_;
     ident(fr->Twc); ident(fr->Tcw); ident(fr->dT01);
     info_ = FrameInfo();
     info_.frame = fr->id;
@@ -401,6 +406,8 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
         const int rc = vo_stereo_frame_step(ctx_, &fp, -1, sl, sr, up_l, up_r, w, h, img_left.step, 0, nullptr, nullptr,
                                             nullptr, nullptr, nullptr, nullptr, &res);
         if (rc) fail(ctx_, rc);
+        ++n_frames_;                                 // commit point
+        poisoned_ = true;
         const int m = res.n_new;
         const int base = newLandmarks(m, fr->id);
         fr->pts_l.assign(new_l_.begin(), new_l_.begin() + 2 * (size_t)m);
@@ -411,6 +418,7 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
         reconstruct(*fr, m);                         // pose is identity: X_w = X_l (:937)
         pushStats(*fr, false);
         prev_ = fr;
+        poisoned_ = false;
         return;
     }
 
@@ -435,6 +443,8 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     const int rc = vo_stereo_frame_step(ctx_, &fp, sp, sl, sr, up_l, up_r, w, h, img_left.step, n, in_l0_.data(), in_r0_.data(),
                                         in_X_.data(), in_tri_.data(), pv.Twc, pv.dT01, &res);
     if (rc) fail(ctx_, rc);
+    ++n_frames_;                                     // commit point
+    poisoned_ = true;
     const float ms_step = ms_since(t_step);
     setPose(*fr, T_wc);                              // :642
     float dT10[16];
@@ -477,6 +487,7 @@ void StereoVO::trackStereoImages(const cv::Mat &img_left, const cv::Mat &img_rig
     stat_.stats_execution.back().time_new = info_.ms_recon;
     stat_.stats_execution.back().time_total = info_.ms_total;
     prev_ = fr;
+    poisoned_ = false;
 }
 
 // ------------------------------------------------------------------------------ C wrapper

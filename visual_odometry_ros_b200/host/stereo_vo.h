@@ -143,7 +143,8 @@ private:
     FrameRecPtr prev_;
     std::deque<FrameRecPtr> window_;
     std::vector<FrameRecPtr> all_keyframes_;
-    int n_frames_ = 0;
+    int n_frames_ = 0;           // committed frames (see trackStereoImages)
+    bool poisoned_ = false;      // an exception escaped after the frame was committed
     // per-frame scratch
     std::vector<float> in_l0_, in_r0_, in_X_, out_l1_, out_r1_, new_l_, new_r_;
     std::vector<uint8_t> in_tri_;

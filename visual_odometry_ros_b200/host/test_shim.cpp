@@ -219,6 +219,142 @@ int main()
     SparseBundleAdjustmentSolver mono_solver(false);
     CHECK(throws_with([&] { mono_solver.setStereoCameras(cam, cam); }, "'is_stereo' should be set to 'true'"), "BA mode error text");
 
+    // ---- the drivers the VO classes call (motion_estimator.h:122-123): same window through
+    //      MotionEstimator::localBundleAdjustmentSparseSolver_Stereo must give the same result as the explicit sequence above
+    {
+        std::vector<FramePtr> l2, r2;
+        std::vector<LandmarkPtr> lm2;
+        lcg_state = 777u;
+        auto build = [&](std::vector<FramePtr> &L, std::vector<FramePtr> &R, std::vector<LandmarkPtr> &LM) {
+            lcg_state = 777u;
+            for (int k = 0; k < NKF; ++k) {
+                auto l = std::make_shared<Frame>(false), r = std::make_shared<Frame>(true);
+                PoseSE3 Twc = PoseSE3::Identity(); Twc(2, 3) = 1.0f * k; Twc(0, 3) = 0.01f * k;
+                if (k >= 2) { Twc(2, 3) += 0.03f * (frand() - 0.5f); Twc(0, 3) += 0.03f * (frand() - 0.5f); }
+                l->setPose(Twc);
+                PoseSE3 Twr = Twc; Twr(0, 3) += base;
+                r->setPose(Twr); r->setLeftFramePtr(l);
+                L.push_back(l); R.push_back(r);
+            }
+            for (int i = 0; i < 90; ++i) {
+                auto lm = std::make_shared<Landmark>();
+                Point Xw; Xw(0) = -8.f + 16.f * frand(); Xw(1) = -2.f + 4.f * frand(); Xw(2) = 8.f + 30.f * frand();
+                for (int k = 0; k < NKF; ++k) {
+                    const float xl = Xw(0) - 0.01f * k, yl = Xw(1), zl = Xw(2) - 1.0f * k;
+                    lm->addObservationOnKeyframe(Pixel(fx * xl / zl + cx, fy * yl / zl + cy), L[k]);
+                    lm->addObservationOnKeyframe(Pixel(fx * (xl - base) / zl + cx, fy * yl / zl + cy), R[k]);
+                    L[k]->addRelatedLandmark(lm);
+                }
+                Point Xn = Xw; Xn(2) *= 1.f + 0.03f * (frand() - 0.5f);
+                lm->set3DPoint(Xn);
+                LM.push_back(lm);
+            }
+        };
+        std::vector<FramePtr> la, ra, lb, rb;
+        std::vector<LandmarkPtr> lma, lmb;
+        build(la, ra, lma);
+        build(lb, rb, lmb);
+        // (a) explicit sequence
+        {
+            FramePtrVec fb;
+            for (auto &l : la) fb.push_back(l);
+            for (auto &r : ra) fb.push_back(r);
+            std::vector<int> fix = {0, 1}, opt;
+            for (int j = 2; j < (int)fb.size(); ++j) if (!fb[j]->isRightImage()) opt.push_back(j);
+            auto prm = std::make_shared<SparseBAParameters>(true, Tlr);
+            prm->setPosesAndPoints(fb, fix, opt);
+            SparseBundleAdjustmentSolver sv(true);
+            sv.setStereoCameras(cam, cam); sv.setBAParameters(prm); sv.setHuberThreshold(0.5);
+            sv.solveForFiniteIterations(10);
+        }
+        // (b) the driver over a StereoKeyframes window
+        auto win = std::make_shared<StereoKeyframes>();
+        win->setMaxStereoKeyframes(NKF);
+        MotionEstimator me_st(true, Tlr);
+        win->addNewStereoKeyframe(std::make_shared<StereoFrame>(lb[0], rb[0]));
+        win->addNewStereoKeyframe(std::make_shared<StereoFrame>(lb[1], rb[1]));
+        CHECK(!me_st.localBundleAdjustmentSparseSolver_Stereo(win, camc, camc, Tlr), "fewer than 3 keyframes: local BA skipped");
+        for (int k = 2; k < NKF; ++k) win->addNewStereoKeyframe(std::make_shared<StereoFrame>(lb[k], rb[k]));
+        CHECK(me_st.localBundleAdjustmentSparseSolver_Stereo(win, camc, camc, Tlr), "stereo local-BA driver runs");
+        bool same = true;
+        for (int k = 0; k < NKF; ++k) for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) same &= la[k]->getPose()(r, c) == lb[k]->getPose()(r, c);
+        for (size_t i = 0; i < lma.size(); ++i) for (int r = 0; r < 3; ++r) same &= lma[i]->get3DPoint()(r) == lmb[i]->get3DPoint()(r);
+        CHECK(same, "driver result == explicit SparseBAParameters + solver sequence");
+        CHECK(lmb[0]->isBundled(), "driver bundles the landmarks");
+        MotionEstimator me_mono(false);
+        CHECK(throws_with([&] { me_mono.localBundleAdjustmentSparseSolver_Stereo(win, camc, camc, Tlr); }, "is_stereo_mode_ == false"),
+              "stereo driver mode error text");
+        // mono driver: left frames only, left observations only
+        auto kwin = std::make_shared<Keyframes>();
+        kwin->setMaxKeyframes(NKF);
+        std::vector<FramePtr> lm_f;
+        std::vector<LandmarkPtr> lm_l;
+        lcg_state = 4242u;
+        for (int k = 0; k < NKF; ++k) {
+            auto l = std::make_shared<Frame>(false);
+            PoseSE3 Twc = PoseSE3::Identity(); Twc(2, 3) = 1.0f * k; Twc(0, 3) = 0.3f * k;
+            if (k >= 2) { Twc(2, 3) += 0.02f * (frand() - 0.5f); Twc(0, 3) += 0.02f * (frand() - 0.5f); }
+            l->setPose(Twc);
+            lm_f.push_back(l);
+        }
+        for (int i = 0; i < 90; ++i) {
+            auto lm = std::make_shared<Landmark>();
+            Point Xw; Xw(0) = -8.f + 16.f * frand(); Xw(1) = -2.f + 4.f * frand(); Xw(2) = 8.f + 30.f * frand();
+            for (int k = 0; k < NKF; ++k) {
+                const float xl = Xw(0) - 0.3f * k, yl = Xw(1), zl = Xw(2) - 1.0f * k;
+                lm->addObservationOnKeyframe(Pixel(fx * xl / zl + cx, fy * yl / zl + cy), lm_f[k]);
+                lm_f[k]->addRelatedLandmark(lm);
+            }
+            Point Xn = Xw; Xn(2) *= 1.f + 0.02f * (frand() - 0.5f);
+            lm->set3DPoint(Xn);
+            lm_l.push_back(lm);
+        }
+        for (int k = 0; k < NKF; ++k) kwin->addNewKeyframe(lm_f[k]);
+        const float err_before = std::fabs(lm_f[3]->getPose()(2, 3) - 3.0f) + std::fabs(lm_f[3]->getPose()(0, 3) - 0.9f);
+        CHECK(me_mono.localBundleAdjustmentSparseSolver(kwin, camc), "mono local-BA driver runs");
+        const float err_after = std::fabs(lm_f[3]->getPose()(2, 3) - 3.0f) + std::fabs(lm_f[3]->getPose()(0, 3) - 0.9f);
+        CHECK(lm_l[0]->isBundled() && err_after <= err_before + 1e-3f, "mono driver bundles and does not diverge");
+    }
+
+    // ---- two FeatureTracker objects interleaved on the shared context: neither may see the other's upload as its own
+    {
+        std::vector<unsigned char> c0, c1;
+        render(c0, W, H, 7.f, 3.f);
+        render(c1, W, H, 7.f + sx, 3.f + sy);
+        cv::Mat jmg0(H, W, c0.data()), jmg1(H, W, c1.data());
+        FeatureTracker fa, fb;
+        PixelVec pa, pb, pa2; MaskVec ma, mb, ma2;
+        fa.track(img0, img1, pts0, 21, 3, 30.f, pa, ma);
+        fb.track(jmg0, jmg1, pts0, 21, 3, 30.f, pb, mb);          // evicts fa's images from the shared slots
+        fb.track(jmg1, jmg0, pts0, 21, 3, 30.f, pb, mb);
+        fa.track(img0, img1, pts0, 21, 3, 30.f, pa2, ma2);         // must re-upload, not hit a stale fingerprint
+        bool eq = true;
+        for (size_t i = 0; i < n; ++i) eq &= pa[i].x == pa2[i].x && pa[i].y == pa2[i].y && ma[i] == ma2[i];
+        CHECK(eq, "interleaved FeatureTracker objects do not alias each other's image slots");
+        // du0 / dv0: the true Sobel images are accepted, anything else is refused
+        std::vector<float> du((size_t)W * H), dv((size_t)W * H);
+        auto pxl = [&](int xx, int yy) -> float {
+            if (xx < 0) xx = -xx;
+            if (xx >= W) xx = 2 * W - 2 - xx;
+            if (yy < 0) yy = -yy;
+            if (yy >= H) yy = 2 * H - 2 - yy;
+            return (float)b0[(size_t)yy * W + xx];
+        };
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+            du[(size_t)y * W + x] = (pxl(x + 1, y - 1) - pxl(x - 1, y - 1)) + 2.f * (pxl(x + 1, y) - pxl(x - 1, y)) + (pxl(x + 1, y + 1) - pxl(x - 1, y + 1));
+            dv[(size_t)y * W + x] = (pxl(x - 1, y + 1) - pxl(x - 1, y - 1)) + 2.f * (pxl(x, y + 1) - pxl(x, y - 1)) + (pxl(x + 1, y + 1) - pxl(x + 1, y - 1));
+        }
+        cv::Mat du0(H, W, du.data()), dv0(H, W, dv.data());
+        PixelVec p6 = p1; MaskVec m6;
+        fa.trackWithScale(img0, du0, dv0, img1, pts0, scale, p6, m6);
+        bool eq5 = true;
+        for (size_t i = 0; i < n; ++i) eq5 &= p6[i].x == p5[i].x && p6[i].y == p5[i].y && m6[i] == m5[i];
+        CHECK(eq5, "trackWithScale with the true Sobel images == with empty derivative arguments");
+        du[0] += 3.f;                              // pixel (0, 0) is part of the verified sample
+        CHECK(throws_with([&] { PixelVec q = p1; MaskVec mm; fa.trackWithScale(img0, du0, dv0, img1, pts0, scale, q, mm); }, "cv::Sobel(img0"),
+              "trackWithScale refuses derivative images that are not the Sobel of img0");
+    }
+
     vo_b200::release_shared_context();
     printf("SHIM_OK features=%zu tracked=%zu\n", n, good);
     return 0;

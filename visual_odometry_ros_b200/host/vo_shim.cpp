@@ -11,6 +11,17 @@
 namespace vo_b200 {
 static vo_ctx *g_ctx = nullptr;
 static int g_w = 0, g_h = 0;
+// image fingerprint -> slot 0..3 of g_ctx; lives and dies with g_ctx
+struct SlotFp { const unsigned char *data = nullptr; int rows = 0, cols = 0; size_t step = 0; unsigned long long sum = 0; };
+static SlotFp g_fp[4];
+static int g_next_slot = 0;
+static void reset_slot_cache() { for (auto &f : g_fp) f = SlotFp(); g_next_slot = 0; }
+
+std::recursive_mutex &shared_mutex()
+{
+    static std::recursive_mutex m;
+    return m;
+}
 
 [[noreturn]] void throw_status(vo_ctx *ctx, int status, const char *reference_message)
 {
@@ -24,8 +35,10 @@ static int g_w = 0, g_h = 0;
 
 vo_ctx *shared_context(int min_w, int min_h)
 {
+    std::lock_guard<std::recursive_mutex> lock(shared_mutex());
     if (g_ctx && min_w <= g_w && min_h <= g_h) return g_ctx;
     if (g_ctx) { vo_ctx_destroy(g_ctx); g_ctx = nullptr; }
+    reset_slot_cache();                      // the new context's slots hold no image
     g_w = std::max(min_w, std::max(g_w, 1920));
     g_h = std::max(min_h, std::max(g_h, 1200));
     const int rc = vo_ctx_create(0, g_w, g_h, 5, 8192, nullptr, &g_ctx);      // slots 0-3: FeatureTracker, slot 4: FeatureExtractor
@@ -35,8 +48,37 @@ vo_ctx *shared_context(int min_w, int min_h)
 
 void release_shared_context()
 {
+    std::lock_guard<std::recursive_mutex> lock(shared_mutex());
     if (g_ctx) vo_ctx_destroy(g_ctx);
     g_ctx = nullptr; g_w = g_h = 0;
+    reset_slot_cache();
+}
+
+// slot holding `img` (uploading it if no slot does); never the slot `avoid` (the other image of the pair)
+static int shared_slot_for(const cv::Mat &img, int avoid)
+{
+    if (img.empty()) throw std::runtime_error("vo_b200: empty image");
+    unsigned long long sum = 1469598103934665603ull;
+    for (int y = 0; y < img.rows; ++y) {
+        const unsigned char *row = img.data + (size_t)y * img.step;
+        unsigned long long acc = 0;
+        int x = 0;
+        for (; x + 8 <= img.cols; x += 8) { unsigned long long w; memcpy(&w, row + x, 8); acc += w * (unsigned long long)(x + 1); }
+        for (; x < img.cols; ++x) acc += row[x];
+        sum = (sum ^ acc) * 1099511628211ull;
+    }
+    vo_ctx *ctx = shared_context(img.cols, img.rows);    // may recreate the context and clear the cache
+    for (int s = 0; s < 4; ++s)
+        if (g_fp[s].data == img.data && g_fp[s].rows == img.rows && g_fp[s].cols == img.cols && g_fp[s].step == img.step && g_fp[s].sum == sum)
+            return s;
+    int s = g_next_slot;
+    if (s == avoid) s = (s + 1) % 4;
+    g_next_slot = (s + 1) % 4;
+    g_fp[s] = SlotFp();                                   // invalid until the upload succeeded
+    const int rc = vo_upload_image(ctx, s, img.data, img.cols, img.rows, img.step);
+    if (rc) throw_status(ctx, rc, nullptr);
+    g_fp[s].data = img.data; g_fp[s].rows = img.rows; g_fp[s].cols = img.cols; g_fp[s].step = img.step; g_fp[s].sum = sum;
+    return s;
 }
 }  // namespace vo_b200
 
@@ -67,30 +109,9 @@ static_assert(sizeof(Point) == 12, "Eigen::Vector3f must be three packed floats"
 FeatureTracker::FeatureTracker() { printf(" - FEATURE_TRACKER is constructed.\n"); }
 FeatureTracker::~FeatureTracker() { printf(" - FEATURE_TRACKER is deleted.\n"); }
 
-int FeatureTracker::slotFor(const cv::Mat &img, int avoid)
-{
-    if (img.empty()) throw std::runtime_error("vo_b200: empty image");
-    unsigned long long sum = 1469598103934665603ull;
-    for (int y = 0; y < img.rows; ++y) {
-        const unsigned char *row = img.data + (size_t)y * img.step;
-        unsigned long long acc = 0;
-        int x = 0;
-        for (; x + 8 <= img.cols; x += 8) { unsigned long long w; memcpy(&w, row + x, 8); acc += w * (unsigned long long)(x + 1); }
-        for (; x < img.cols; ++x) acc += row[x];
-        sum = (sum ^ acc) * 1099511628211ull;
-    }
-    for (int s = 0; s < 4; ++s)
-        if (fp_[s].data == img.data && fp_[s].rows == img.rows && fp_[s].cols == img.cols && fp_[s].step == img.step && fp_[s].sum == sum)
-            return s;
-    int s = next_slot_;
-    if (s == avoid) s = (s + 1) % 4;
-    next_slot_ = (s + 1) % 4;
-    vo_ctx *ctx = shared_context(img.cols, img.rows);
-    const int rc = vo_upload_image(ctx, s, img.data, img.cols, img.rows, img.step);
-    if (rc) throw_status(ctx, rc, nullptr);
-    fp_[s].data = img.data; fp_[s].rows = img.rows; fp_[s].cols = img.cols; fp_[s].step = img.step; fp_[s].sum = sum;
-    return s;
-}
+int FeatureTracker::slotFor(const cv::Mat &img, int avoid) { return vo_b200::shared_slot_for(img, avoid); }
+
+#define VO_SHIM_LOCK std::lock_guard<std::recursive_mutex> vo_shim_lock_(vo_b200::shared_mutex())
 
 void FeatureTracker::track(const cv::Mat &img0, const cv::Mat &img1, const PixelVec &pts0, int window_size, int max_pyr_lvl,
                            float thres_err, PixelVec &pts_track, MaskVec &mask_valid)
@@ -99,6 +120,7 @@ void FeatureTracker::track(const cv::Mat &img0, const cv::Mat &img1, const Pixel
     std::vector<uint8_t> m = unpack_mask(mask_valid, n);
     pts_track.resize(n);
     if (n == 0) return;
+    VO_SHIM_LOCK;
     const int s0 = slotFor(img0, -1), s1 = slotFor(img1, s0);
     vo_ctx *ctx = shared_context();
     const int rc = vo_ft_track(ctx, s0, s1, pix(pts0), (int)n, window_size, max_pyr_lvl, thres_err, pix(pts_track), m.data());
@@ -113,6 +135,7 @@ void FeatureTracker::trackBidirection(const cv::Mat &img0, const cv::Mat &img1, 
     std::vector<uint8_t> m = unpack_mask(mask_valid, n);
     pts_track.resize(n);
     if (n == 0) return;
+    VO_SHIM_LOCK;
     const int s0 = slotFor(img0, -1), s1 = slotFor(img1, s0);
     vo_ctx *ctx = shared_context();
     const int rc = vo_ft_track_bidirection(ctx, s0, s1, pix(pts0), (int)n, window_size, max_pyr_lvl, thres_err, thres_bidirection,
@@ -129,6 +152,7 @@ void FeatureTracker::trackBidirectionWithPrior(const cv::Mat &img0, const cv::Ma
     std::vector<uint8_t> m = unpack_mask(mask_valid, n);
     if (pts_track.size() != n) throw std::runtime_error("vo_b200: prior pts_track.size() != pts0.size()");
     if (n == 0) return;
+    VO_SHIM_LOCK;
     const int s0 = slotFor(img0, -1), s1 = slotFor(img1, s0);
     vo_ctx *ctx = shared_context();
     const int rc = vo_ft_track_bidirection_with_prior(ctx, s0, s1, pix(pts0), (int)n, window_size, max_pyr_lvl, thres_err,
@@ -144,6 +168,7 @@ void FeatureTracker::trackWithPrior(const cv::Mat &img0, const cv::Mat &img1, co
     std::vector<uint8_t> m = unpack_mask(mask_valid, n);
     if (pts_track.size() != n) throw std::runtime_error("vo_b200: prior pts_track.size() != pts0.size()");
     if (n == 0) return;
+    VO_SHIM_LOCK;
     const int s0 = slotFor(img0, -1), s1 = slotFor(img1, s0);
     vo_ctx *ctx = shared_context();
     const int rc = vo_ft_track_with_prior(ctx, s0, s1, pix(pts0), (int)n, window_size, max_pyr_lvl, thres_err, pix(pts_track), m.data());
@@ -161,6 +186,7 @@ void FeatureTracker::calcPrior(const PixelVec &pts0, const PointVec &Xw, const P
     float T[16];
     pose_to_rowmajor(Tw1, T);
     const float K4[4] = {K(0, 0), K(1, 1), K(0, 2), K(1, 2)};
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     std::vector<float> out(n_pts * 2);
     const int rc = vo_ft_calc_prior(ctx, pix(pts0), reinterpret_cast<const float *>(Xw.data()), (int)n_pts, T, K4, out.data());
@@ -168,14 +194,48 @@ void FeatureTracker::calcPrior(const PixelVec &pts0, const PointVec &Xw, const P
     memcpy(static_cast<void *>(pts1_prior.data()), out.data(), n_pts * 8);
 }
 
-void FeatureTracker::trackWithScale(const cv::Mat &img0, const cv::Mat & /*du0*/, const cv::Mat & /*dv0*/, const cv::Mat &img1,
+// cv::Sobel(img, CV_32FC1, dx, dy, 3) with BORDER_REFLECT_101 at one pixel (exact in float: integer taps on u8 pixels)
+static float sobel3_at(const cv::Mat &img, int x, int y, bool horizontal)
+{
+    auto px = [&](int xx, int yy) -> float {
+        if (xx < 0) xx = -xx;
+        if (xx >= img.cols) xx = 2 * img.cols - 2 - xx;
+        if (yy < 0) yy = -yy;
+        if (yy >= img.rows) yy = 2 * img.rows - 2 - yy;
+        return (float)img.data[(size_t)yy * img.step + xx];
+    };
+    if (horizontal)
+        return (px(x + 1, y - 1) - px(x - 1, y - 1)) + 2.f * (px(x + 1, y) - px(x - 1, y)) + (px(x + 1, y + 1) - px(x - 1, y + 1));
+    return (px(x - 1, y + 1) - px(x - 1, y - 1)) + 2.f * (px(x, y + 1) - px(x, y - 1)) + (px(x + 1, y + 1) - px(x + 1, y - 1));
+}
+static void require_sobel_of(const cv::Mat &img0, const cv::Mat &d, bool horizontal)
+{
+    const char *msg = "vo_b200: trackWithScale needs du0 / dv0 == cv::Sobel(img0, CV_32FC1, 1,0 / 0,1, 3) (the device evaluates those "
+                      "taps from img0); other derivative images are not supported";
+    if (d.rows != img0.rows || d.cols != img0.cols || d.type() != CV_32FC1) throw std::runtime_error(msg);
+    if (img0.rows < 2 || img0.cols < 2) return;
+    // 23 x 17 pixel sample incl. the four borders
+    for (int iy = 0; iy < 17; ++iy) {
+        const int y = (int)((long long)iy * (img0.rows - 1) / 16);
+        const float *row = reinterpret_cast<const float *>(d.data + (size_t)y * d.step);
+        for (int ix = 0; ix < 23; ++ix) {
+            const int x = (int)((long long)ix * (img0.cols - 1) / 22);
+            if (row[x] != sobel3_at(img0, x, y, horizontal)) throw std::runtime_error(msg);
+        }
+    }
+}
+
+void FeatureTracker::trackWithScale(const cv::Mat &img0, const cv::Mat &du0, const cv::Mat &dv0, const cv::Mat &img1,
                                     const PixelVec &pts0, const std::vector<float> &scale_est, PixelVec &pts_track, MaskVec &mask_valid)
 {
     if (pts_track.size() != pts0.size()) throw std::runtime_error("pts_track.size() != pts0.size()");   // feature_tracker.cpp:283
+    if (!img0.empty() && !du0.empty()) require_sobel_of(img0, du0, true);
+    if (!img0.empty() && !dv0.empty()) require_sobel_of(img0, dv0, false);
     const size_t n = pts0.size();
     std::vector<uint8_t> m = unpack_mask(mask_valid, n);
     if (n == 0) return;
     if (scale_est.size() < n) throw std::runtime_error("vo_b200: scale_est.size() < pts0.size()");
+    VO_SHIM_LOCK;
     const int s0 = slotFor(img0, -1), s1 = slotFor(img1, s0);
     vo_ctx *ctx = shared_context();
     const int rc = vo_ft_track_with_scale(ctx, s0, s1, pix(pts0), scale_est.data(), (int)n, pix(pts_track), m.data());
@@ -201,6 +261,7 @@ void FeatureExtractor::extractORBwithBinning_fast(const cv::Mat &img, PixelVec &
     // the reference ignores the argument and buckets on its member flag_nonmax_ = true (:211-282)
     if (img.empty()) throw std::runtime_error("vo_b200: empty image");
     if (n_bins_u_ <= 0 || n_bins_v_ <= 0) throw std::runtime_error("vo_b200: FeatureExtractor::initParams has not been called");
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context(img.cols, img.rows);
     int rc = vo_upload_image(ctx, 4, img.data, img.cols, img.rows, img.step);
     if (rc) throw_status(ctx, rc, nullptr);
@@ -229,6 +290,7 @@ bool MotionEstimator::monoImpl(const PointVec &X, const PixelVec &pts1, float fx
     float R[9], t[3];
     for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r * 3 + c] = R01(r, c); t[r] = t01(r); }
     int ok = 0;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_pose_gn_mono(ctx, reinterpret_cast<const float *>(X.data()), pix(pts1), (int)n, fx, fy, cx, cy, thres, standalone, R, t,
                                    m.data(), &ok, nullptr);
@@ -251,6 +313,7 @@ bool MotionEstimator::stereoImpl(const PointVec &X, const PixelVec &pl, const Pi
     pose_to_rowmajor(T_lr, Tlr);
     pose_to_rowmajor(T01, T);
     int ok = 0;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_pose_gn_stereo(ctx, reinterpret_cast<const float *>(X.data()), pix(pl), pix(pr), (int)n, Kl, Kr, Tlr, thres, T, m.data(),
                                      &ok, nullptr);
@@ -299,6 +362,7 @@ bool MotionEstimator::calcPose5PointsAlgorithm(const PixelVec &pts0, const Pixel
     X0_true.resize(n);
     const float K4[4] = {cam->fx(), cam->fy(), cam->cx(), cam->cy()};
     float R[9], t[3];
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_pose_5point(ctx, pix(pts0), pix(pts1), (int)n, K4, thres_5p_, n_hypotheses_, seed_, R, t,
                                   reinterpret_cast<float *>(X0_true.data()), m.data(), nullptr, nullptr);
@@ -317,6 +381,7 @@ float MotionEstimator::findInliers1PointHistogram(const PixelVec &pts0, const Pi
     std::vector<uint8_t> m(std::max<size_t>(n, 1), 0);
     const float K4[4] = {cam->fx(), cam->fy(), cam->cx(), cam->cy()};
     float th = 0.f;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_inliers_1point_histogram(ctx, pix(pts0), pix(pts1), (int)n, K4, thres_1p_, m.data(), &th, nullptr, nullptr, nullptr);
     if (rc) throw_status(ctx, rc, nullptr);
@@ -332,6 +397,7 @@ static void epi_impl(int which, const PixelVec &pts0, const PixelVec &pts1, cons
     const size_t n = pts0.size();
     dist.resize(n);
     if (n == 0) return;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     int rc;
     if (F10) {
@@ -383,6 +449,7 @@ static void tri_impl(const float *p0, const float *p1, int n, const Rot3 &R10, c
     float R[9], t[3];
     for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[r * 3 + c] = R10(r, c); t[r] = t10(r); }
     const float K0[4] = {c0.fx(), c0.fy(), c0.cx(), c0.cy()}, K1[4] = {c1.fx(), c1.fy(), c1.cx(), c1.cy()};
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_triangulate_dlt(ctx, p0, p1, n, R, t, K0, K1, X0, X1);
     if (rc) throw_status(ctx, rc, nullptr);
@@ -418,6 +485,7 @@ Eigen::Matrix3f skew(const Eigen::Vector3f &v)
 void DepthFilter::updateNormalDistribution(double x_prev, double cov_prev, double x_curr, double cov_curr, double &x_updated,
                                            double &cov_updated)
 {
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_depth_filter_normal(ctx, &x_prev, &cov_prev, &x_curr, &cov_curr, 1, &x_updated, &cov_updated);
     if (rc) throw_status(ctx, rc, nullptr);
@@ -430,6 +498,7 @@ void DepthFilter::updateNormalDistribution(const std::vector<double> &x_prev, co
     if (cov_prev.size() != n || x_curr.size() != n || cov_curr.size() != n) throw std::runtime_error("vo_b200: depth filter size mismatch");
     x_updated.resize(n); cov_updated.resize(n);
     if (!n) return;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_depth_filter_normal(ctx, x_prev.data(), cov_prev.data(), x_curr.data(), cov_curr.data(), (int)n, x_updated.data(),
                                           cov_updated.data());
@@ -440,6 +509,7 @@ void DepthFilter::updateStudentTDistribution(double x_prev, double cov_prev, dou
                                              double &x_updated, double &cov_updated, double &x_min_updated, double &x_max_updated)
 {
     double a = a_prev, b = b_prev, lo = x_min_prev, hi = x_max_prev;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_depth_filter_student_t(ctx, &x_prev, &cov_prev, &a, &b, &lo, &hi, &x_curr, &cov_curr, 1, &x_updated, &cov_updated);
     if (rc) throw_status(ctx, rc, nullptr);
@@ -605,6 +675,7 @@ bool SparseBundleAdjustmentSolver::solveForFiniteIterations(int MAX_ITER)
     pr.is_stereo = is_stereo_mode_ ? 1 : 0; pr.huber = thres_huber_; pr.lambda = 0.00001; pr.max_iter = MAX_ITER;
     std::vector<double> poses_out(P.poses.size()), points_out(P.points.size() + 3), avg(MAX_ITER);
     int ok = 0;
+    VO_SHIM_LOCK;
     vo_ctx *ctx = shared_context();
     const int rc = vo_lba_solve(ctx, &pr, poses_out.data(), points_out.data(), avg.data(), &ok);
     if (rc == VO_ERR_NAN) throw std::runtime_error("Local BA NAN!\n");                                 // sparse_bundle_adjustment.cpp:761
@@ -653,5 +724,62 @@ bool SparseBundleAdjustmentSolver::solveForFiniteIterations(int MAX_ITER)
     }
     if (flag_large_update) throw std::runtime_error("large update!");                                   // :731
     return ok != 0;
+}
+#endif
+
+
+#ifndef VO_SHIM_USE_REAL_HEADERS
+// ------------------------------------------------------------------------------ local-BA drivers
+// MotionEstimator::localBundleAdjustmentSparseSolver (motion_estimator.cpp:1090-1205)
+bool MotionEstimator::localBundleAdjustmentSparseSolver(const std::shared_ptr<Keyframes> &kfs_window, CameraConstPtr &cam)
+{
+    constexpr int MAX_ITER = 10;
+    constexpr double THRES_HUBER = 0.5;
+    constexpr int NUM_MINIMUM_REQUIRED_KEYFRAMES = 3, NUM_FIX_KEYFRAMES_IN_WINDOW = 2;
+    if (kfs_window->getCurrentNumOfKeyframes() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return false;   // :1130-1134
+    FramePtrVec frames;
+    std::vector<int> idx_fix, idx_opt;
+    for (const auto &kf : kfs_window->getList()) frames.push_back(kf);
+    for (int j = 0; j < NUM_FIX_KEYFRAMES_IN_WINDOW; ++j) idx_fix.push_back(j);
+    for (size_t j = NUM_FIX_KEYFRAMES_IN_WINDOW; j < frames.size(); ++j) idx_opt.push_back((int)j);
+    auto ba_params = std::make_shared<SparseBAParameters>();
+    ba_params->setPosesAndPoints(frames, idx_fix, idx_opt);
+    SparseBundleAdjustmentSolver solver(false);                                                   // sparse_ba_solver_ (:18)
+    solver.reset();
+    solver.setCamera(cam);
+    solver.setBAParameters(ba_params);
+    solver.setHuberThreshold(THRES_HUBER);
+    solver.solveForFiniteIterations(MAX_ITER);
+    solver.reset();
+    return true;
+}
+
+// MotionEstimator::localBundleAdjustmentSparseSolver_Stereo (motion_estimator.cpp:1207-1340)
+bool MotionEstimator::localBundleAdjustmentSparseSolver_Stereo(const std::shared_ptr<StereoKeyframes> &stkfs_window, CameraConstPtr &cam_left,
+                                                               CameraConstPtr &cam_right, const PoseSE3 &T_lr)
+{
+    if (!is_stereo_mode_)
+        throw std::runtime_error("In 'MotionEstimator::localBundleAdjustmentSparseSolver_Stereo()', is_stereo_mode_ == false.");   // :1220
+    constexpr int MAX_ITER = 10;
+    constexpr double THRES_HUBER = 0.5;
+    constexpr int NUM_MINIMUM_REQUIRED_KEYFRAMES = 3, NUM_FIX_KEYFRAMES_IN_WINDOW = 2;
+    if (stkfs_window->getCurrentNumOfStereoKeyframes() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return false;
+    FramePtrVec frames_ba;                                     // all left frames, then all right frames (:1272-1276)
+    std::vector<int> idx_fix, idx_opt;
+    for (const auto &stkf : stkfs_window->getList()) frames_ba.push_back(stkf->getLeft());
+    for (const auto &stkf : stkfs_window->getList()) frames_ba.push_back(stkf->getRight());
+    for (int j = 0; j < NUM_FIX_KEYFRAMES_IN_WINDOW; ++j) idx_fix.push_back(j);
+    for (size_t j = NUM_FIX_KEYFRAMES_IN_WINDOW; j < frames_ba.size(); ++j)
+        if (!frames_ba[j]->isRightImage()) idx_opt.push_back((int)j);                            // left poses only (:1285-1293)
+    auto ba_params = std::make_shared<SparseBAParameters>(is_stereo_mode_, T_lr);
+    ba_params->setPosesAndPoints(frames_ba, idx_fix, idx_opt);
+    SparseBundleAdjustmentSolver solver(true);
+    solver.reset();
+    solver.setStereoCameras(cam_left, cam_right);
+    solver.setBAParameters(ba_params);
+    solver.setHuberThreshold(THRES_HUBER);
+    solver.solveForFiniteIterations(MAX_ITER);
+    solver.reset();
+    return true;
 }
 #endif

@@ -7,12 +7,18 @@
 #include "../../include/vo_b200.h"
 #include "vo_shim_types.h"
 
+#include <mutex>
+
 namespace vo_b200 {
 // One process-wide device context shared by the shim objects (the reference keeps one VO object per
 // node and is single-threaded, SURVEY 8b "Threading").  Created on first use; throws
 // std::runtime_error if no CUDA device is present (there is no CPU fallback).
+// The shim objects share that context's image slots 0-3 through ONE process-wide cache (image fingerprint -> slot), so
+// several FeatureTracker objects never see each other's uploads as their own; every shim method that touches the context
+// holds shared_mutex() for its duration (the shim may be called from several threads; calls are serialised).
 vo_ctx *shared_context(int min_w = 0, int min_h = 0);
 void release_shared_context();
+std::recursive_mutex &shared_mutex();
 [[noreturn]] void throw_status(vo_ctx *ctx, int status, const char *reference_message);
 }  // namespace vo_b200
 
@@ -30,16 +36,16 @@ public:
     void trackWithPrior(const cv::Mat &img0, const cv::Mat &img1, const PixelVec &pts0, int window_size, int max_pyr_lvl,
                         float thres_err, PixelVec &pts_track, MaskVec &mask_valid);
     void calcPrior(const PixelVec &pts0, const PointVec &Xw, const PoseSE3 &Tw1, const Eigen::Matrix3f &K, PixelVec &pts1_prior);
-    // du0 / dv0 must be the 3x3 Sobel derivatives of img0 (the only way the reference calls it,
-    // stereo_vo.cpp:551-553, mono_vo.cpp:781-783); they are recomputed on the device from img0.
+    // du0 / dv0: the reference passes cv::Sobel(img0, CV_32FC1, 1,0 / 0,1, 3) (stereo_vo.cpp:551-553, mono_vo.cpp:781-783).
+    // The kernel evaluates those taps on the fly from img0, so derivative images that are NOT the 3x3 Sobel of img0
+    // cannot be honoured: non-empty du0 / dv0 are verified on a pixel sample and a std::runtime_error is thrown if they
+    // are anything else.  Empty Mats skip the check.
     void trackWithScale(const cv::Mat &img0, const cv::Mat &du0, const cv::Mat &dv0, const cv::Mat &img1, const PixelVec &pts0,
                         const std::vector<float> &scale_est, PixelVec &pts_track, MaskVec &mask_valid);
 private:
-    // images are re-uploaded only when the (data pointer, size, first/last bytes) fingerprint changes
-    int slotFor(const cv::Mat &img, int preferred);
-    struct Fp { const unsigned char *data = nullptr; int rows = 0, cols = 0; size_t step = 0; unsigned long long sum = 0; };
-    Fp fp_[4];
-    int next_slot_ = 0;
+    // images are re-uploaded only when the (data pointer, size, content hash) fingerprint changes; the fingerprint table
+    // belongs to the shared context (vo_shim.cpp), not to this object
+    int slotFor(const cv::Mat &img, int avoid);
 };
 
 // core/visual_odometry/feature_extractor.h:144-200: the bucketed extractor the VO classes call (initParams, resetWeightBin,
@@ -89,7 +95,14 @@ public:
                                        std::vector<float> &sym_epi_dist);
     // five-point RANSAC knobs of this build (the reference's cv::findEssentialMat draws its own samples)
     void setRansac(int n_hypotheses, unsigned seed) { n_hypotheses_ = n_hypotheses; seed_ = seed; }
-    // core :1090-1340 (drivers of the local BA) -- flat-window form; see SparseBundleAdjustmentSolver
+#ifndef VO_SHIM_USE_REAL_HEADERS
+    // core motion_estimator.h:122-123, bodies motion_estimator.cpp:1090-1205 / :1207-1340: window -> SparseBAParameters
+    // (fixed = the two oldest keyframes, the others optimised; stereo: left poses only, right frames carry residuals),
+    // Huber 0.5, 10 iterations of SparseBundleAdjustmentSolver.  false when the window holds fewer than 3 keyframes.
+    bool localBundleAdjustmentSparseSolver(const std::shared_ptr<Keyframes> &kfs, CameraConstPtr &cam);
+    bool localBundleAdjustmentSparseSolver_Stereo(const std::shared_ptr<StereoKeyframes> &stkfs_window, CameraConstPtr &cam_left,
+                                                  CameraConstPtr &cam_right, const PoseSE3 &T_lr);
+#endif
     void setThres1p(float thres_1p) { thres_1p_ = thres_1p; }
     void setThres5p(float thres_5p) { thres_5p_ = thres_5p; }
 private:

@@ -27,15 +27,24 @@ struct Point2f {
     Point2f(float x_, float y_) : x(x_), y(y_) {}
 };
 enum { CV_8UC1_ = 0 };
+#ifndef CV_8UC1
+#define CV_8UC1 0
+#define CV_32FC1 5
+#endif
 // Header over caller-owned pixels (like cv::Mat constructed from a ROS message buffer,
-// ros2/visual_odometry/stereo_vo_ros2.cpp:96-99).
+// ros2/visual_odometry/stereo_vo_ros2.cpp:96-99).  CV_8UC1, or CV_32FC1 through the float constructor
+// (the Sobel derivative images of trackWithScale, stereo_vo.cpp:551-552).
 struct Mat {
     int rows = 0, cols = 0;
-    size_t step = 0;
+    size_t step = 0;          // row pitch in BYTES, as in OpenCV
     unsigned char *data = nullptr;
+    int type_ = CV_8UC1;
     Mat() {}
     Mat(int rows_, int cols_, unsigned char *data_, size_t step_ = 0) : rows(rows_), cols(cols_), step(step_ ? step_ : (size_t)cols_), data(data_) {}
+    Mat(int rows_, int cols_, float *data_, size_t step_ = 0)
+        : rows(rows_), cols(cols_), step(step_ ? step_ : (size_t)cols_ * sizeof(float)), data(reinterpret_cast<unsigned char *>(data_)), type_(CV_32FC1) {}
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    int type() const { return type_; }
 };
 }  // namespace cv
 
@@ -114,6 +123,55 @@ private:
     PoseSE3 Twc_, Tcw_;
     FramePtr left_;
     LandmarkPtrVec lms_;
+};
+
+// core/visual_odometry/frame.h:96-113 / keyframes.h:24-88: the window containers the local-BA drivers walk
+// (MotionEstimator::localBundleAdjustmentSparseSolver(_Stereo), motion_estimator.cpp:1090-1340).  Only the members those
+// drivers touch; the keyframe RULE (keyframes.cpp:217-303) lives in StereoVO / MonoVO (host/stereo_vo.cpp, mono_vo.cpp).
+class StereoFrame {
+public:
+    StereoFrame(const FramePtr &frame_left, const FramePtr &frame_right) : left_(frame_left), right_(frame_right) {}
+    const FramePtr &getLeft() const { return left_; }
+    const FramePtr &getRight() const { return right_; }
+private:
+    FramePtr left_, right_;
+};
+using StereoFramePtr = std::shared_ptr<StereoFrame>;
+
+class Keyframes {
+public:
+    Keyframes() : n_max_(9) {}
+    void setMaxKeyframes(int max_kf) { n_max_ = max_kf; }
+    void addNewKeyframe(const FramePtr &frame)          // keyframes.cpp:122-140: drop the oldest beyond the window size
+    {
+        kfs_list_.push_back(frame);
+        all_keyframes_.push_back(frame);
+        if ((int)kfs_list_.size() > n_max_) kfs_list_.erase(kfs_list_.begin());
+    }
+    const std::vector<FramePtr> &getList() const { return kfs_list_; }
+    int getCurrentNumOfKeyframes() const { return (int)kfs_list_.size(); }
+    int getMaxNumOfKeyframes() const { return n_max_; }
+private:
+    std::vector<FramePtr> kfs_list_, all_keyframes_;
+    int n_max_;
+};
+
+class StereoKeyframes {
+public:
+    StereoKeyframes() : n_max_(9) {}
+    void setMaxStereoKeyframes(int max_kf) { n_max_ = max_kf; }
+    void addNewStereoKeyframe(const StereoFramePtr &stframe)   // keyframes.cpp:305-323
+    {
+        list_.push_back(stframe);
+        all_.push_back(stframe);
+        if ((int)list_.size() > n_max_) list_.erase(list_.begin());
+    }
+    const std::vector<StereoFramePtr> &getList() const { return list_; }
+    int getCurrentNumOfStereoKeyframes() const { return (int)list_.size(); }
+    int getMaxNumOfStereoKeyframes() const { return n_max_; }
+private:
+    std::vector<StereoFramePtr> list_, all_;
+    int n_max_;
 };
 
 class Landmark {
