@@ -127,32 +127,102 @@ def cpu_reference_rate(left, right, pts0, threads, budget_s):
     return reps * len(pts0) / dt, reps, dt
 
 
+def workload_string(P):
+    return (f"cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21; {P} independent pairs "
+            f"per GPU per step (cfg5 batching); step = pyramids(both) + Scharr + LK")
+
+
+def l2_policy_string(P):
+    """Timing rule: inputs (or the per-step working set) larger than the GPU's 126 MB L2 -- a property of the workload."""
+    return ("inputs larger than L2" if 2 * P * W * H > 126e6 else "working set (pyramids+derivatives) larger than L2")
+
+
+def config_dict(P):
+    return {"workload": workload_string(P), "pairs_per_gpu": P, "features_per_pair": NFEAT, "window": WIN, "levels": MAXLVL + 1,
+            "l2_policy": l2_policy_string(P)}
+
+
+_REF = {}
+
+
+def _ref_worker_init(P, seed):
+    """One worker process = one host core running the reference's library call single-threaded on its share of the pairs."""
+    import cv2
+    cv2.setNumThreads(1)
+    lefts, rights, pts = make_pairs(P, seed)
+    _REF.update(lefts=lefts, rights=rights, pts=pts)
+
+
+def _ref_worker_track(idx):
+    from oracle import klt as oklt
+    n_ok = 0
+    for i in idx:
+        p1, m = oklt.track(oklt.lk_cv2, _REF["lefts"][i], _REF["rights"][i], _REF["pts"][i], WIN, MAXLVL, THRES_ERR)
+        n_ok += int(m.sum())
+    return n_ok
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the SAME step the GPU arm runs: FeatureTracker::track on P independent stereo
+    pairs (cv2.calcOpticalFlowPyrLK 4.13 -- the library call of feature_tracker.cpp:29 -- + the post-filter), two ways:
+    (a) one pair per host core (a pool of single-threaded processes: what BASELINE.md section 3 promises for the batched
+    config), (b) pair after pair with OpenCV's internal parallel_for on all threads.  value = the faster of the two."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lefts, rights, pts = make_pairs(1, 2002)
+    import multiprocessing as mp
+    P = args.pairs
     cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    # (a) process pool, created before this process touches cv2's thread pool
+    ctxmp = mp.get_context("spawn")
+    nproc = max(1, min(cores, P))
+    shares = [list(range(k, P, nproc)) for k in range(nproc)]
+    pool_val = pool_ms = None
+    try:
+        with ctxmp.Pool(nproc, initializer=_ref_worker_init, initargs=(P, 2002)) as pool:
+            for _ in range(max(1, min(args.warmup, 2))):
+                pool.map(_ref_worker_track, shares, chunksize=1)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pool.map(_ref_worker_track, shares, chunksize=1)
+            dt_pool = time.perf_counter() - t0
+        pool_val = args.steps * P * NFEAT / dt_pool
+        pool_ms = 1e3 * dt_pool / args.steps
+    except Exception as e:          # a box that cannot spawn processes still reports (b)
+        pool_err = repr(e)
+    # (b) OpenCV's own threading, pair after pair: a bounded sample of the step (8 pairs), scaled to P pairs
     import cv2
     from oracle import klt as oklt
+    lefts, rights, pts = make_pairs(min(P, 8), 2002)
     cv2.setNumThreads(cores)
-    for _ in range(max(args.warmup, 1)):
-        oklt.track(oklt.lk_cv2, lefts[0], rights[0], pts[0], WIN, MAXLVL, THRES_ERR)
+    nb = len(lefts)
+    for i in range(nb):
+        oklt.track(oklt.lk_cv2, lefts[i], rights[i], pts[i], WIN, MAXLVL, THRES_ERR)
+    reps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oklt.track(oklt.lk_cv2, lefts[0], rights[0], pts[0], WIN, MAXLVL, THRES_ERR)
-    dt = time.perf_counter() - t0
-    val = args.steps * NFEAT / dt
-    sample = (f"{args.steps} steps x 1 stereo pair x {NFEAT} features: cv2.calcOpticalFlowPyrLK 4.13 "
-              f"(+ track() post-filter), {cores} threads")
+    for _ in range(reps):
+        for i in range(nb):
+            oklt.track(oklt.lk_cv2, lefts[i], rights[i], pts[i], WIN, MAXLVL, THRES_ERR)
+    dt_thr = time.perf_counter() - t0
+    thr_val = reps * nb * NFEAT / dt_thr
+    if pool_val is not None and pool_val >= thr_val:
+        val, ms_step, how = pool_val, pool_ms, f"{nproc} single-threaded processes, one pair per core at a time"
+    else:
+        val, ms_step, how = thr_val, 1e3 * P * NFEAT / thr_val, f"pair after pair, OpenCV parallel_for on {cores} threads (sample of {nb} pairs scaled to {P})"
+    sample = (f"{args.steps} steps x {P} stereo pairs x {NFEAT} features: cv2.calcOpticalFlowPyrLK 4.13 + track() post-filter; "
+              f"pool of {nproc} processes: {pool_val and round(pool_val)} features/s, OpenCV-threaded ({cores} threads): {round(thr_val)} features/s; "
+              f"reported = the faster ({how})")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "features/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16 fixed-point + f32", "data": "synthetic",
-        "config": {"workload": "cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21; step = pyramids(both) + Scharr + LK",
-                   "reference_sample": "one stereo pair per step (bounded sample of the batched workload)",
-                   "features_per_pair": NFEAT, "window": WIN, "levels": MAXLVL + 1},
-        "cpu_baseline": {"value": val, "unit": "features/s", "cores": cores, "kind": "reference", "sample": sample},
+        "config": config_dict(P),
+        "cpu_baseline": {"value": val, "unit": "features/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "pool_value": pool_val, "opencv_threads_value": thr_val},
         "e2e": {"value": val, "unit": "features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -165,7 +235,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=128, help="independent stereo pairs per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
-    ap.add_argument("--skip-extras", action="store_true", help="skip pose-GN / single-frame side measurements")
+    ap.add_argument("--skip-extras", action="store_true", help="skip pose-GN / single-frame / sequence side measurements")
+    ap.add_argument("--sequences", type=int, default=64, help="config 5: independent stereo sequences, sharded over the ranks")
+    ap.add_argument("--seq-frames", type=int, default=100, help="config 5: frames per sequence")
+    ap.add_argument("--cfg3-frames", type=int, default=1000, help="config 3: frames of the single-sequence measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -183,6 +256,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_binding = bind_to_gpu_numa(local)      # before any pinned allocation (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -306,20 +380,50 @@ def main():
     h2d = 2 * P * W * H + P * n * 8 + P * n
     d2h = P * n * 8 + P * n
 
+    # ---------------------------------------------------------------- H2D-only bandwidth, all ranks copying at once
+    # (what bounds e2e at N > 1: every rank's pinned images cross the same host memory / PCIe root complex)
+    raw_d = torch.empty((2 * P, H, W), dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        raw_d.copy_(host_imgs, non_blocking=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(5):
+        raw_d.copy_(host_imgs, non_blocking=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbs_rank = 5 * host_imgs.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    if world > 1:
+        t = torch.tensor([h2d_gbs_rank], dtype=torch.float64, device=dev)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        h2d_gbs_all = [float(x.item()) for x in g]
+    else:
+        h2d_gbs_all = [h2d_gbs_rank]
+    del raw_d
+    # e2e cannot beat max(device time, image DMA time): the ceiling the measured H2D rate allows
+    e2e_ceiling = world * P * n / (max(ms_step, 2 * P * W * H / (min(h2d_gbs_all) * 1e9) * 1e3) * 1e-3)
+    numa = gpu_numa_info(local)
+
+    # ---------------------------------------------------------------- BASELINE config 5 at SEQUENCE level: 64 independent
+    # StereoVO sequences sharded 64 / N per rank (sharding.shard_range), no inter-GPU traffic
+    seqs = None
+    if not args.skip_extras:
+        seqs = sharded_sequences(torch, dist, dev, local, rank, world, synth, barrier, max_over_ranks, args.sequences, args.seq_frames)
+
     out = {
         "metric": METRIC, "value": value, "unit": "features/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int16 fixed-point + f32", "data": "synthetic",
-        "config": {"workload": f"cfg2 stereo KLT 1241x376, 2000 features, 4 levels, win 21; {P} independent pairs "
-                               f"per GPU per step (cfg5 batching); step = pyramids(both) + Scharr + LK",
-                   "pairs_per_gpu": P, "features_per_pair": n, "window": WIN, "levels": nlev,
-                   "l2_policy": "inputs larger than L2" if 2 * P * W * H > 126e6 else
-                                "working set (pyramids+derivatives) larger than L2",
-                   "tracked_ok": tracked},
+        "config": config_dict(P), "tracked_ok": tracked,
         "e2e": {"value": e2e_val, "unit": "features/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps": Ke, "api": "vo_ft_track_batch (host buffers)"},
+                "ms_per_step": e2e_ms, "steps": Ke, "api": "vo_ft_track_batch (host buffers)",
+                "h2d_only_gbs_per_rank": h2d_gbs_all, "h2d_only_gbs_aggregate": float(sum(h2d_gbs_all)),
+                "numa_binding": numa_binding, "ceiling_from_h2d": e2e_ceiling, "frac_of_ceiling": e2e_val / e2e_ceiling, "gpu_numa": numa,
+                "note": "ceiling = features / max(device-resident step time, image bytes / measured H2D rate with every rank copying)"},
+        "sequences": seqs,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_klt2<21,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_klt3<21>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_klt2 launch (64 pairs x 2000 features) from the
                      # committed `ncu --set full` capture profiles/r1_v4_klt_full_raw.csv: 241.60 MB + 6.78 MB
@@ -333,7 +437,7 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.skip_extras:
-        out.update(side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, capi))
+        out.update(side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, capi, args.cfg3_frames))
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1
         v_all, reps, dt = cpu_reference_rate(lefts[0], rights[0], pts0_h[0], cores, args.cpu_budget)
@@ -352,7 +456,162 @@ def main():
         dist.destroy_process_group()
 
 
-def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, capi):
+def gpu_numa_info(local):
+    """NUMA node / CPU affinity of this rank's GPU (sysfs), and this process's CPU affinity."""
+    info = {}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devn = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devn:02x}.0"
+        with open(path + "/numa_node") as f:
+            info["gpu_numa_node"] = int(f.read().strip())
+        with open(path + "/local_cpulist") as f:
+            info["gpu_local_cpulist"] = f.read().strip()
+    except Exception as e:
+        info["error"] = repr(e)[:80]
+    try:
+        info["process_cpus"] = len(os.sched_getaffinity(0))
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["host_numa_nodes"] = len(nodes)
+    except Exception:
+        pass
+    return info
+
+
+def bind_to_gpu_numa(local):
+    """Run this rank's threads (and first-touch its pinned buffers) on the CPUs local to its GPU, when the box has
+    more than one NUMA node.  Returns what was done."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        with open(path) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} CPUs local to GPU {local}"
+        return "GPU-local CPUs == all allowed CPUs (single NUMA node): nothing to bind"
+    except Exception as e:
+        return "not bound: " + repr(e)[:80]
+
+
+def sharded_sequences(torch, dist, dev, local, rank, world, synth, barrier, max_over_ranks, n_seq_total, n_frames):
+    """BASELINE config 5 for real: n_seq_total independent stereo sequences (full StereoVO::trackStereoImages drop-in: tracking,
+    pose GN, detection, new features every frame; reconstruction + local BA on keyframes), rank r runs
+    sharding.shard_range(n_seq_total, world, r), one StereoVO instance + host thread + CUDA stream per sequence, no data-path
+    collective.  The sequences replay 8 distinct renderings (seeds 5000..5007) round-robin -- 64 distinct 100-frame
+    renderings would be 6 GB of host images -- which changes nothing for the GPU (every instance does its own uploads and
+    keeps its own state).  frames/s = all frames of all ranks / max-over-ranks wall time between two barriers."""
+    import threading
+    from visual_odometry_ros_b200 import sharding, stereo_vo as svo
+    lo, hi = sharding.shard_range(n_seq_total, world, rank)
+    K4, Tlr = synth.kitti_K(), synth.kitti_T_lr()
+    n_render = min(8, n_seq_total)
+    rend = []
+    for i in range(n_render):
+        L, R, _ = synth.stereo_sequence(n_frames, W, H, K4, seed=5000 + i, device=str(dev))
+        rend.append((torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()))
+    mine = list(range(lo, hi))
+    vos = [svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=64, n_bins_v=32, device=local))
+           for _ in mine]
+    for vo, sidx in zip(vos, mine):              # first frame + first step outside the timed region (allocations, module load)
+        L, R = rend[sidx % n_render]
+        vo.trackStereoImages(L[0], R[0], 0.0)
+        vo.trackStereoImages(L[1], R[1], 0.1)
+    errors = []
+    start = threading.Barrier(len(vos) + 1, timeout=300)
+    kf_count = [0] * len(vos)
+
+    def run(j, vo, sidx):
+        try:
+            L, R = rend[sidx % n_render]
+            start.wait()
+            for k in range(2, n_frames):
+                vo.trackStereoImages(L[k], R[k], 0.1 * k)
+                kf_count[j] += vo.frame_info()["keyframe"]
+        except Exception as e:
+            errors.append(repr(e))
+    th = [threading.Thread(target=run, args=(j, vo, sidx), daemon=True) for j, (vo, sidx) in enumerate(zip(vos, mine))]
+    for t in th:
+        t.start()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    try:
+        start.wait()
+    except threading.BrokenBarrierError:
+        errors.append("start barrier broken")
+    for t in th:
+        t.join()
+    dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    for vo in vos:
+        vo.close()
+    frames_rank = len(vos) * (n_frames - 2)
+    if world > 1:
+        t = torch.tensor([float(frames_rank), float(sum(kf_count)), float(len(errors))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        frames_all, kf_all, nerr = int(t[0].item()), int(t[1].item()), int(t[2].item())
+    else:
+        frames_all, kf_all, nerr = frames_rank, sum(kf_count), len(errors)
+    res = {"sequences_total": n_seq_total, "sequences_per_rank": len(vos), "frames_each": n_frames - 2, "distinct_renderings": n_render,
+           "frames_per_s": frames_all / (dt_ms * 1e-3), "ms_per_frame_amortised": dt_ms / max(1, frames_all) * 1.0,
+           "keyframes": kf_all, "errors": nerr, "first_error": errors[:1],
+           "what": "config 5: independent StereoVO sequences sharded over the ranks (one instance + thread + stream each), host u8 images in, "
+                   "pose out, keyframes + local BA included; wall clock between barriers, max over ranks"}
+    if rank == 0 and world == 1:
+        res["cpu"] = cpu_sequence_pool(synth, n_frames=8)
+    return res
+
+
+def _cpu_seq_worker(arg):
+    seed, n_frames = arg
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import stereo_vo as osvo
+    from visual_odometry_ros_b200 import synth
+    K4, Tlr = synth.kitti_K(), synth.kitti_T_lr()
+    L, R, _ = synth.stereo_sequence(n_frames, W, H, K4, seed=seed, device="cpu")
+    ora = osvo.StereoVOOracle(W, H, K4, K4, Tlr, osvo.default_params(window_size=WIN, max_level=MAXLVL, n_bins_u=64, n_bins_v=32))
+    ora.track(L[0], R[0])
+    t0 = time.perf_counter()
+    for k in range(1, n_frames):
+        ora.track(L[k], R[k])
+    return (n_frames - 1), time.perf_counter() - t0
+
+
+def cpu_sequence_pool(synth, n_frames=8):
+    """The CPU side of config 5: the oracle composition of StereoVO::trackStereoImages (cv2 LK + C restatements), one
+    single-threaded process per host core, one sequence each; a bounded sample (n_frames frames per sequence)."""
+    import multiprocessing as mp
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    try:
+        t0 = time.perf_counter()
+        with mp.get_context("spawn").Pool(cores) as pool:
+            r = pool.map(_cpu_seq_worker, [(5000 + i, n_frames) for i in range(cores)], chunksize=1)
+        frames = sum(a for a, _ in r)
+        slowest = max(b for _, b in r)
+        return {"frames_per_s": frames / slowest, "processes": cores, "frames_each": n_frames - 1, "kind": "port (oracle composition, cv2 LK single-threaded per process)",
+                "wall_s_incl_rendering": time.perf_counter() - t0}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+
+
+def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, capi, cfg3_frames=1000):
     """pose-GN solves/s (batched) and single-frame ms (KLT temporal + KLT stereo + pose GN)."""
     from oracle import pose as opose
     res = {}
@@ -393,9 +652,41 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
         opose.pose_gn_stereo(X[creps % nprob], pl[creps % nprob], pr[creps % nprob], K4, K4, Tlr, 3.0, np.eye(4))
         creps += 1
     cpu_rate = creps / (time.perf_counter() - t0)
+    iters_total = float(it_d.double().sum().item())
+    peak_hbm, _ = load_peak()
+    pose_bytes = 28.0 * npts * iters_total            # 12 + 8 + 8 B per point per iteration
+    pose_flops = 260.0 * npts * iters_total           # ~260 FLOP per point per iteration (un-fused FP32)
+    fp32_peak_nofma = 148 * 128 * 1.965e9 / 1e12      # TFLOP/s of un-fused FP32 (the kernel is compiled -fmad=false)
     res["pose_gn"] = {"solves_per_s": nprob / (ms * 1e-3), "batch": nprob, "points": npts, "ms_per_batch": ms,
                       "mean_iters": float(it_d.float().mean().item()),
-                      "cpu_port_solves_per_s_1core": cpu_rate}
+                      "cpu_port_solves_per_s_1core": cpu_rate, "mode": "VO_POSE_FAST (FP64 tree sums)"}
+    res["roofline_pose"] = {"kernel": "k_pose_gn<128>", "bound": "hbm", "achieved": pose_bytes / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                            "frac": pose_bytes / (ms * 1e-3) / 1e9 / peak_hbm,
+                            "flops": {"achieved_tflops": pose_flops / (ms * 1e-3) / 1e12, "peak_tflops_fp32_unfused": fp32_peak_nofma,
+                                      "frac": pose_flops / (ms * 1e-3) / 1e12 / fp32_peak_nofma},
+                            "algorithmic_bytes_per_launch": pose_bytes, "note": "4096 problems re-read 28 B/point every GN iteration from L2 "
+                            "(the 57 MB batch fits the 126 MB L2); the kernel is bound by the per-iteration serial solve + FP32 row arithmetic, "
+                            "see the flops fraction"}
+    # the same batch in strict-order mode (sequential FP32 sums == the reference's arithmetic)
+    def solve_strict():
+        T_d.copy_(eye)
+        ctx.pose_gn_stereo_batch_d(nprob, off_d.data_ptr(), X_d.data_ptr(), pl_d.data_ptr(), pr_d.data_ptr(), K4, K4,
+                                   Tlr, 3.0, T_d.data_ptr(), mask_d.data_ptr(), ok_d.data_ptr(), it_d.data_ptr(), flags=capi.VO_POSE_STRICT)
+    solve()
+    torch.cuda.synchronize()
+    T_fast = T_d.clone()
+    for _ in range(2):
+        solve_strict()
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(reps):
+        solve_strict()
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms_s = a.elapsed_time(b) / reps
+    res["pose_gn_strict"] = {"solves_per_s": nprob / (ms_s * 1e-3), "ms_per_batch": ms_s, "mean_iters": float(it_d.float().mean().item()),
+                             "max_abs_dT_fast_vs_strict": float((T_fast - T_d).abs().max().item()),
+                             "mode": "VO_POSE_STRICT (sequential FP32 sums in point order: the reference's arithmetic, bit for bit)"}
     # ---- single frame: the device-resident stereo tracking step (S1, stereo_vo.cpp:475-670) through the host C ABI:
     #      H2D of the two new images + landmark state, prior, 2x trackWithPrior, trackWithScale, stereo pose GN,
     #      compactions, D2H of pose + survivors; wall clock incl. every copy and the one synchronisation.
@@ -428,7 +719,7 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                            "what": "vo_stereo_track_step (host buffers): 2 image uploads + prior + 2x trackWithPrior (2000 feat, "
                                    "4 levels, win 21) [+ trackWithScale] + stereo pose GN + compactions, wall clock incl. all "
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
-    res["sequence"] = sequence_measurement(torch, dev, synth)
+    res["sequence"] = sequence_measurement(torch, dev, synth, n_frames=cfg3_frames)
     res["mono_sequence"] = mono_sequence_measurement(torch, dev, synth)
     res["sequence_orb"] = sequence_measurement(torch, dev, synth, n_frames=60, n_cpu=6, detector="orb", with_concurrent=False)
     res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
@@ -509,7 +800,14 @@ def cfg4_measurement(ctx, synth):
     for _ in range(20):
         omisc.depth_filter_normal(x0, c0, x1, c1)
     df_cpu_ms = (time.perf_counter() - t0) * 1e3 / 20
-    return {"lba_ms": gpu_ms, "lba_cpu_port_ms_1core": cpu_ms, "keyframes": 10, "landmarks": int(p["n_points"]), "observations": int(p["n_obs"]),
+    peak_hbm, _ = load_peak()
+    n_obs, M, iters = int(p["n_obs"]), int(p["n_points"]), int(p["max_iter"])
+    lba_bytes = iters * (185.0 * n_obs + 96.0 * M + 144.0 * n_obs)       # build + per-landmark C,b + Schur re-read of B
+    roofline_lba = {"kernel": "k_lba_build + k_lba_reduce + k_lba_solve + k_lba_update_points (x iterations)", "bound": "hbm",
+                    "achieved": lba_bytes / (gpu_ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s", "frac": lba_bytes / (gpu_ms * 1e-3) / 1e9 / peak_hbm,
+                    "algorithmic_bytes_per_call": lba_bytes,
+                    "note": "whole vo_lba_solve call incl. H2D/D2H; 10 dependent LM iterations of ~15 MB each: latency-bound (serial 48x48 LDLT per iteration), not HBM-bound"}
+    return {"roofline_lba": roofline_lba, "lba_ms": gpu_ms, "lba_cpu_port_ms_1core": cpu_ms, "keyframes": 10, "landmarks": int(p["n_points"]), "observations": int(p["n_obs"]),
             "iterations": int(p["max_iter"]), "lba_final_avg_err_px": float(out[2][-1]), "lba_max_pose_diff_vs_cpu": float(np.abs(out[0] - poses_o).max()),
             "depth_filter_ms": df_ms, "depth_filter_cpu_port_ms_1core": df_cpu_ms, "seeds": n,
             "what": "vo_lba_solve / vo_depth_filter_normal with host buffers, wall clock incl. H2D/D2H and the sync"}

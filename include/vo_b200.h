@@ -431,6 +431,25 @@ typedef struct vo_lba_problem {
 VO_API int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *prob, double *poses_out, double *points_out,
                  double *avg_err_out, int *success);
 
+/* ------------------------------------------------------------------ oversize windows on several GPUs (NCCL over NVLink)
+ * BASELINE.json north_star / SURVEY 8(e): the LANDMARKS of one local-BA window are partitioned over the ranks (one process +
+ * one vo_ctx per GPU), the keyframe poses are replicated.  Every rank accumulates the Schur-complement reduced camera system
+ * of its own landmarks (what sparse_bundle_adjustment.cpp:456-515 accumulates over all of them); one
+ * ncclAllReduce(sum, float64) of (6 N_opt)(6 N_opt + 1) + 27 N_opt + 2 values per LM iteration, enqueued on the context's
+ * stream between the build and the dense solve (:517-536), completes it; the solve and the pose retraction run redundantly
+ * and identically on every rank, each rank back-substitutes its own landmarks.
+ *   vo_dist_unique_id : rank 0 creates the 128-byte NCCL id; the host program ships it to the other ranks (any transport).
+ *   vo_dist_init      : collective; ncclCommInitRank on the context's device.  libnccl.so.2 is loaded at run time.
+ *   vo_lba_solve_dist : collective; `local_part` = ALL frames / poses (identical on every rank) + this rank's landmarks and
+ *                       observations.  poses_out: the full pose set (identical on every rank); points_out: this rank's
+ *                       landmarks; avg_err_out: the GLOBAL per-iteration error. */
+#define VO_DIST_UNIQUE_ID_BYTES 128
+VO_API int vo_dist_unique_id(void *id_out);
+VO_API int vo_dist_init(vo_ctx *ctx, int rank, int world, const void *unique_id);
+VO_API int vo_dist_finalize(vo_ctx *ctx);
+VO_API int vo_lba_solve_dist(vo_ctx *ctx, const vo_lba_problem *local_part, double *poses_out, double *points_out,
+                      double *avg_err_out, int *success);
+
 #ifdef __cplusplus
 }
 #endif

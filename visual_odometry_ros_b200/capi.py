@@ -131,6 +131,9 @@ def lib():
     L.vo_pose_gn_mono_ex.argtypes = L.vo_pose_gn_mono.argtypes + [ctypes.c_int, ctypes.c_int, vp]
     L.vo_pose_gn_stereo_ex.argtypes = L.vo_pose_gn_stereo.argtypes + [ctypes.c_int, ctypes.c_int, vp]
     L.vo_pose_gn_stereo_batch_ex_d.argtypes = L.vo_pose_gn_stereo_batch_d.argtypes + [ctypes.c_int, ctypes.c_int, vp]
+    L.vo_dist_unique_id.argtypes = [vp]
+    L.vo_dist_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    L.vo_dist_finalize.argtypes = [vp]
     L.vo_set_pose_mode.argtypes = [vp, ctypes.c_int]
     L.vo_get_pose_mode.argtypes = [vp]
     L.vo_triangulate_dlt.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
@@ -179,6 +182,15 @@ def check(ctx_handle, rc):
         if ctx_handle:
             txt += ": " + L.vo_last_error(ctx_handle).decode()
         raise VoError(rc, txt)
+
+
+def dist_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host program ships it to the other ranks)."""
+    buf = (ctypes.c_char * 128)()
+    rc = lib().vo_dist_unique_id(buf)
+    if rc != 0:
+        raise VoError(rc, "vo_dist_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(buf)
 
 
 class Context:
@@ -517,7 +529,7 @@ class Context:
         return pt, m.astype(bool)
 
     # ---------------------------------------------------------------- local bundle adjustment
-    def lba_solve(self, p):
+    def lba_solve(self, p, dist=False):
         """SparseBundleAdjustmentSolver::solveForFiniteIterations on a flat problem dict
         (layout of synth.lba_problem / vo_lba_problem). Returns (poses, points, avg_err, success)."""
         keep = {}
@@ -544,8 +556,23 @@ class Context:
         points = np.zeros((max(s.n_points, 1), 3))
         avg = np.zeros(s.max_iter)
         ok = ctypes.c_int(0)
-        check(self.h, self.L.vo_lba_solve(self.h, ctypes.byref(s), _ptr(poses), _ptr(points), _ptr(avg), ctypes.byref(ok)))
+        fn = self.L.vo_lba_solve_dist if dist else self.L.vo_lba_solve
+        check(self.h, fn(self.h, ctypes.byref(s), _ptr(poses), _ptr(points), _ptr(avg), ctypes.byref(ok)))
         return poses, points[:s.n_points], avg, bool(ok.value)
+
+    # ---------------------------------------------------------------- landmark-sharded local BA over NCCL
+    def dist_init(self, rank, world, unique_id):
+        """Collective: ncclCommInitRank on this context's device. unique_id: the 128 bytes rank 0 got from dist_unique_id()."""
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(unique_id))
+        check(self.h, self.L.vo_dist_init(self.h, int(rank), int(world), buf))
+
+    def dist_finalize(self):
+        check(self.h, self.L.vo_dist_finalize(self.h))
+
+    def lba_solve_dist(self, p_local):
+        """Collective: p_local = all frames / poses + this rank's landmarks (sharding.split_lba_problem).
+        Returns (poses [all, identical on every rank], points [this rank's], avg_err [global], success)."""
+        return self.lba_solve(p_local, dist=True)
 
     # ---------------------------------------------------------------- stereo tracking step (S1)
     def stereo_track_step(self, slot_l0, slot_l1, slot_r1, img_l1, img_r1, pts_l0, pts_r0, Xw, tri, T_wp, dT_pc_prev,

@@ -123,6 +123,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (!ctx) return VO_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm) vo_dist_finalize(ctx);
     for (auto &S : ctx->slots) if (S.base) cudaFree(S.base);
     if (ctx->d_slots) cudaFree(ctx->d_slots);
     if (ctx->d_tmaps) cudaFree(ctx->d_tmaps);

@@ -486,34 +486,38 @@ __global__ void __launch_bounds__(256) k_lba_reduce(const LbaDev d)
 #pragma unroll
     for (int k = 1; k < LBA_RED_G; ++k) tot += __shfl_sync(0xffffffffu, acc, (lane % (32 / LBA_RED_G)) + k * (32 / LBA_RED_G));
     if (act && g == 0) d.red[e] = tot;
+    // observation count of this shard, summed over the ranks with everything else in the distributed variant
+    if (gid == 0) d.red[nS + nA + 1] = (double)d.n_obs;
 }
 
 // ------------------------------------------------------------------ k_lba_solve (one CTA)
-__global__ void __launch_bounds__(LBA_THREADS, 1)
-k_lba_solve(const LbaDev d, int iter)
-{
-    extern __shared__ double smem[];
-    const int n = d.n6, No = d.n_opt, ncol = n + 1;
-    double *S = smem;                    // [n][n+1] (padded row)
-    double *rhs = S + (size_t)n * (n + 1);
-    double *temp = rhs + n;
-    double *Aj = temp + n;               // [No][27]
-    __shared__ int s_tr[6 * LBA_MAX_OPT];
-    __shared__ int s_big;
-    __shared__ double s_err;
-    const int tid = threadIdx.x;
-#define SM(i, j) S[(size_t)(i) * (n + 1) + (j)]
-#define STAMP(k) do { if (d.dbg && tid == 0) d.dbg[k] = clock64(); } while (0)
-    STAMP(0);
+// Reduced camera system S = blkdiag(A damped) - BCinvBt (with the reference's mirror quirk), pivoted LDLT, solve, pose
+// retraction.  Round 1 factorised S in shared memory: 48 steps of {pivot search, swap, scale, trailing update}, four
+// block barriers and a shared-memory read-modify-write of the whole trailing triangle per step -- 98 k cycles per LM
+// iteration (VO_LBA_TRACE), the longest stage of the local BA.  Here the matrix lives in REGISTERS: the CTA is a 16 x 16
+// thread grid, thread (ty, tx) owns the B x B block of rows ty*B.. and columns tx*B.. of the FULL symmetric matrix
+// (B = 3 for n <= 48, i.e. the reference's window of 8 optimised keyframes; B = 6 up to n = 96).  Nothing is ever
+// swapped: diagonal pivoting only chooses the ORDER of elimination, so step k eliminates original index p_k in place --
+// the pivot column is broadcast through 16*B doubles of shared memory, every thread updates its own registers
+// (A(i,j) -= L(i,p) * (D_p L(j,p)), the same products as Eigen's unblocked LDLT), two block barriers per step.  The
+// pivot rule is Eigen's (largest remaining |diagonal|, FIRST POSITION on ties): a position -> index table mirrors the
+// row/column transpositions Eigen would have made, and every warp evaluates it redundantly so no barrier is needed to
+// publish the choice.  The triangular solves then run on one warp over the factor parked in shared memory, in original
+// index order (no permutation of the right-hand side).
+#define SOLVE_G 16
 
-    // fixed-order reduction of the tile partials
+// S, rhs, Aj in shared memory from the reduced tile sums (d.red), exactly as sparse_bundle_adjustment.cpp:456-531 leaves them
+__device__ __forceinline__ void lba_assemble(const LbaDev &d, double *S, const int ld, double *rhs, double *Aj, double *s_err, const int tid)
+{
+    const int n = d.n6, No = d.n_opt, ncol = n + 1;
+#define SM(i, j) S[(size_t)(i) * ld + (j)]
     for (int e = tid; e < n * ncol; e += LBA_THREADS) {
         const double acc = d.red[e];
         const int r = e / ncol, c = e - r * ncol;
         if (c == n) rhs[r] = acc; else SM(r, c) = acc;
     }
     for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) Aj[e] = d.red[n * ncol + e];
-    if (tid == 0) s_err = d.red[n * ncol + No * LBA_NA];
+    if (tid == 0) *s_err = d.red[n * ncol + No * LBA_NA];
     __syncthreads();
     // S <- blkdiag(A damped) - BCinvBt with the reference's mirror (upper blocks -> lower, diagonal
     // blocks transposed, sparse_bundle_adjustment.cpp:501-512); rhs <- a - BCinv_b
@@ -522,9 +526,7 @@ k_lba_solve(const LbaDev d, int iter)
         const int jb = r / 6, kb = c / 6;
         if (jb > kb) continue;                      // handle each upper-block entry once
         const double up = SM(r, c);                 // BCinvBt[jb][kb](r%6, c%6), untouched so far
-        if (jb < kb) {
-            SM(c, r) = -up;                         // lower block = transpose
-        }
+        if (jb < kb) SM(c, r) = -up;                // lower block = transpose
     }
     __syncthreads();
     for (int e = tid; e < n * n; e += LBA_THREADS) {
@@ -538,8 +540,7 @@ k_lba_solve(const LbaDev d, int iter)
         const int jb = e / 36, rr = (e % 36) / 6, cc = e % 6;
         if (rr > cc) continue;                      // one thread handles the (rr,cc)/(cc,rr) pair
         const int lo = rr, hi = cc;
-        // upper index of (lo,hi) in the 21-entry packing
-        const int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+        const int idx = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // upper index of (lo,hi) in the 21-entry packing
         double a_v = Aj[jb * LBA_NA + idx];
         if (lo == hi) a_v += d.lambda * a_v;        // damping A(k,k) += lambda*A(k,k)
         const double b_rc = SM(6 * jb + rr, 6 * jb + cc), b_cr = SM(6 * jb + cc, 6 * jb + rr);
@@ -548,20 +549,64 @@ k_lba_solve(const LbaDev d, int iter)
     }
     for (int r = tid; r < n; r += LBA_THREADS) rhs[r] = Aj[(r / 6) * LBA_NA + 21 + (r % 6)] - rhs[r];
     __syncthreads();
+#undef SM
+}
 
+template <int B>
+__global__ void __launch_bounds__(LBA_THREADS, 1)
+k_lba_solve(const LbaDev d, int iter)
+{
+    constexpr int NP = SOLVE_G * B;      // padded system size
+    constexpr int LD = NP + 1;           // shared-memory row pitch (odd: conflict-free column walks)
+    extern __shared__ double smem[];
+    const int n = d.n6, No = d.n_opt;
+    double *S = smem;                    // [NP][LD]: assembly, later the factor L
+    double *rhs = S + (size_t)NP * LD;   // [NP]
+    double *Aj = rhs + NP;               // [No][27]
+    __shared__ double s_diag[NP], s_col[NP], s_D[NP];
+    __shared__ int s_idx_at[NP];         // position -> original index (the transpositions Eigen would have applied)
+    __shared__ int s_piv[NP];            // step -> original index
+    __shared__ int s_step[NP];           // original index -> step
+    __shared__ double s_err;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ty = tid / SOLVE_G, tx = tid % SOLVE_G;
+#define SM(i, j) S[(size_t)(i) * LD + (j)]
+#define STAMP(k) do { if (d.dbg && tid == 0) d.dbg[k] = clock64(); } while (0)
+    STAMP(0);
+    lba_assemble(d, S, LD, rhs, Aj, &s_err, tid);
     STAMP(1);
-    // ---- pivoted LDLT (lower storage), pivoting as Eigen::LDLT::compute (largest remaining |diagonal|, first index on
-    // ties), right-looking: the products are Eigen's, L(i,j) * (D_j L(k,j)), subtracted one column at a time instead of
-    // as a pre-summed dot product, so every element update of a column is independent.  Per column: warp 0 finds the
-    // pivot with three integer redux.sync (non-negative doubles order like their bit patterns), all eight warps swap,
-    // scale and update the trailing triangle (warp w owns rows w, w+8, ...; lanes own columns).
+
+    // ---- registers <- the LOWER triangle (what Eigen::LDLT<.., Lower> reads), mirrored to a full symmetric matrix
+    double A[B][B];
+    unsigned rowdead = 0, coldead = 0;   // bit a: index eliminated or padding (>= n)
+#pragma unroll
+    for (int a = 0; a < B; ++a) {
+        const int i = ty * B + a;
+        if (i >= n) rowdead |= 1u << a;
+        const int jj = tx * B + a;
+        if (jj >= n) coldead |= 1u << a;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int j = tx * B + b;
+            A[a][b] = (i < n && j < n) ? (i >= j ? SM(i, j) : SM(j, i)) : 0.0;
+        }
+    }
+    if (tid < NP) { s_idx_at[tid] = tid; s_step[tid] = -1; s_D[tid] = 0.0; }
+    if (ty == tx) {
+#pragma unroll
+        for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
+    }
+    __syncthreads();
+
     for (int k = 0; k < n; ++k) {
-        if (tid < 32) {
+        // ---- pivot: largest |diagonal| among positions k .. n-1, first position on ties (every warp, redundantly)
+        int big_pos;
+        {
             double bv = -1.0;
-            int bi = k;
-            for (int i = k + tid; i < n; i += 32) {
-                const double v = fabs(SM(i, i));
-                if (v > bv) { bv = v; bi = i; }
+            int bp = k;
+            for (int pos = k + lane; pos < n; pos += 32) {
+                const double v = fabs(s_diag[s_idx_at[pos]]);
+                if (v > bv) { bv = v; bp = pos; }
             }
             const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
             const unsigned long long key = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
@@ -570,68 +615,87 @@ k_lba_solve(const LbaDev d, int iter)
             const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
             const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
             const bool win = has && hi == mhi && (unsigned)key == mlo;
-            bi = __reduce_min_sync(0xffffffffu, win ? bi : 0x7fffffff);
-            if (bi == 0x7fffffff) bi = k;
-            if (tid == 0) { s_big = bi; s_tr[k] = bi; }
+            big_pos = __reduce_min_sync(0xffffffffu, win ? bp : 0x7fffffff);
+            if (big_pos == 0x7fffffff) big_pos = k;
         }
-        __syncthreads();
-        const int big = s_big;
-        if (big != k) {
-            const int sr = n - big - 1;
-            for (int j = tid; j < k; j += LBA_THREADS) { const double t = SM(k, j); SM(k, j) = SM(big, j); SM(big, j) = t; }
-            for (int i = tid; i < sr; i += LBA_THREADS) { const double t = SM(big + 1 + i, k); SM(big + 1 + i, k) = SM(big + 1 + i, big); SM(big + 1 + i, big) = t; }
-            for (int i = k + 1 + tid; i < big; i += LBA_THREADS) { const double t = SM(i, k); SM(i, k) = SM(big, i); SM(big, i) = t; }
-            if (tid == 0) { const double t = SM(k, k); SM(k, k) = SM(big, big); SM(big, big) = t; }
-            __syncthreads();
+        const int p = s_idx_at[big_pos];
+        const int pb = p / B, pa = p - pb * B;
+        // ---- the owners of column p publish it
+        if (tx == pb) {
+#pragma unroll
+            for (int a = 0; a < B; ++a)
+#pragma unroll
+                for (int b = 0; b < B; ++b)
+                    if (b == pa) s_col[ty * B + a] = A[a][b];
         }
-        const int rs = n - k - 1;
-        const double akk = SM(k, k);
-        {   // L(:,k) = A(:,k) * (1 / D_k) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp),
-            // temp = D_k * L(:,k)
-            const bool scale = rs > 0 && fabs(akk) > 0.0;
-            const double rk = scale ? __drcp_rn(akk) : 0.0;
-            for (int i = tid; i < rs; i += LBA_THREADS) {
-                double l = SM(k + 1 + i, k);
-                if (scale) { l *= rk; SM(k + 1 + i, k) = l; }
-                temp[i] = akk * l;
+        __syncthreads();                     // (1) column visible; every warp has read the position table and the diagonal
+        if (tid == 0) {
+            const int q = s_idx_at[k];
+            s_idx_at[k] = p; s_idx_at[big_pos] = q;
+            s_piv[k] = p; s_step[p] = k; s_D[p] = s_col[p];
+        }
+        const double akk = s_col[p];
+        // L(:,p) = A(:,p) * (1 / D_p) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp), temp = D_p L(:,p)
+        const bool scale = (k < n - 1) && fabs(akk) > 0.0;
+        const double rk = scale ? __drcp_rn(akk) : 0.0;
+        double li[B], ti[B], lj[B], tj[B];
+#pragma unroll
+        for (int a = 0; a < B; ++a) {
+            double l = s_col[ty * B + a];
+            if (scale) l *= rk;
+            li[a] = l; ti[a] = akk * l;
+            double m = s_col[tx * B + a];
+            if (scale) m *= rk;
+            lj[a] = m; tj[a] = akk * m;
+        }
+        if (ty == pb) rowdead |= 1u << pa;
+        const unsigned colalive_before = ~coldead;
+        if (tx == pb) coldead |= 1u << pa;
+#pragma unroll
+        for (int a = 0; a < B; ++a) {
+            const int i = ty * B + a;
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int j = tx * B + b;
+                if (!((rowdead >> a) & 1u) && !((coldead >> b) & 1u))
+                    A[a][b] -= (i >= j) ? li[a] * tj[b] : lj[b] * ti[a];          // the trailing update, both triangles
+                else if (tx == pb && b == pa && !((rowdead >> a) & 1u) && ((colalive_before >> b) & 1u))
+                    A[a][b] = li[a];                                            // column p now holds L(:,p)
             }
         }
-        __syncthreads();
-        // trailing lower triangle: A(k+1+r, k+1+c) -= L(k+1+r, k) * temp[c] for c <= r
-        {
-            const int lane = tid & 31, wid = tid >> 5;
-            for (int r = wid; r < rs; r += LBA_THREADS / 32) {
-                const double l = SM(k + 1 + r, k);
-                for (int c = lane; c <= r; c += 32) SM(k + 1 + r, k + 1 + c) -= l * temp[c];
-            }
+        if (ty == tx) {
+#pragma unroll
+            for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
         }
-        __syncthreads();
+        __syncthreads();                     // (2) diagonal + position table updated; s_col may be overwritten
     }
-    if (tid < 32) {
-        // ---- solve: P b, L^-1, D^-1, L^-T, P^T  (column-oriented updates keep the row-wise order)
-        if (tid == 0) for (int k = 0; k < n; ++k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
-        __syncwarp();
-        for (int j = 0; j < n; ++j) {
-            const double yj = rhs[j];
-            for (int i = j + 1 + tid; i < n; i += 32) rhs[i] -= SM(i, j) * yj;
-            __syncwarp();
-        }
-    }
+    // ---- park the factor in shared memory (column p_k of L sits in column p_k of the matrix, rows eliminated later)
+#pragma unroll
+    for (int a = 0; a < B; ++a)
+#pragma unroll
+        for (int b = 0; b < B; ++b) SM(ty * B + a, tx * B + b) = A[a][b];
     __syncthreads();
     STAMP(2);
     const double tol = 1.0 / 1.7976931348623157e308;
-    for (int i = tid; i < n; i += LBA_THREADS) rhs[i] = fabs(SM(i, i)) > tol ? rhs[i] / SM(i, i) : 0.0;
-    __syncthreads();
-    // backward substitution L^T x = y, column-oriented: once x_i is final, every x_j (j < i) takes its update
-    // independently (one serial FP64 step per row instead of a dot-product chain), then P^T
     if (tid < 32) {
-        for (int i = n - 1; i > 0; --i) {
-            const double xi = rhs[i];
-            for (int j = tid; j < i; j += 32) rhs[j] -= SM(i, j) * xi;
+        // forward: for k ascending, y(p_k) is final; every index eliminated later takes its update
+        for (int k = 0; k < n; ++k) {
+            const int p = s_piv[k];
+            const double yk = rhs[p];
+            for (int i = tid; i < n; i += 32)
+                if (s_step[i] > k) rhs[i] -= SM(i, p) * yk;
             __syncwarp();
         }
-        if (tid == 0)
-            for (int k = n - 1; k >= 0; --k) if (s_tr[k] != k) { const double t = rhs[k]; rhs[k] = rhs[s_tr[k]]; rhs[s_tr[k]] = t; }
+        for (int i = tid; i < n; i += 32) rhs[i] = fabs(s_D[i]) > tol ? rhs[i] / s_D[i] : 0.0;
+        __syncwarp();
+        // backward: L^T x = y, column-oriented: once x(p_k) is final, every index eliminated EARLIER takes its update
+        for (int k = n - 1; k > 0; --k) {
+            const int p = s_piv[k];
+            const double xk = rhs[p];
+            for (int i = tid; i < n; i += 32)
+                if (s_step[i] < k) rhs[i] -= SM(p, i) * xk;
+            __syncwarp();
+        }
     }
     __syncthreads();
     STAMP(3);
@@ -647,10 +711,12 @@ k_lba_solve(const LbaDev d, int iter)
     }
     STAMP(4);
     if (tid == 0) {
-        d.avg_err[iter] = sqrt(s_err / (double)d.n_obs);
+        const double n_obs_all = d.red[n * (n + 1) + No * LBA_NA + 1];     // == d.n_obs on one GPU; the all-reduced count otherwise
+        d.avg_err[iter] = sqrt(s_err / n_obs_all);
         if (isnan(s_err)) atomicExch(d.nan_flag, 1);
     }
 #undef SM
+#undef STAMP
 }
 
 // final landmark update after the last iteration
@@ -687,8 +753,102 @@ static void inv_se3_host_d(const double *T, double *O)
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 
+// ------------------------------------------------------------------ NCCL (loaded at run time; only the distributed entry needs it)
+// Oversize windows (north_star / SURVEY 8e): the LANDMARKS are partitioned over the ranks, the keyframe poses are replicated.
+// Each rank builds the partial reduced camera system of its landmarks; ONE ncclAllReduce(sum, double) of
+// (6 N_opt)(6 N_opt + 1) + 27 N_opt + 2 values per LM iteration -- enqueued on the LBA stream right after k_lba_reduce, so it
+// rides NVLink between the build of this iteration and the redundant dense solve -- makes the system complete on every rank;
+// the solve, the pose retraction and the back-substitution of the rank's own landmarks stay local.
+#include <dlfcn.h>
+typedef struct ncclComm *vo_ncclComm_t;
+typedef struct { char internal[128]; } vo_ncclUniqueId;
+struct NcclApi {
+    int (*GetUniqueId)(vo_ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(vo_ncclComm_t *, int, vo_ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, vo_ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(vo_ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static const NcclApi &nccl_api()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);      // the copy torch already loaded, else the system one
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.GetUniqueId = (int (*)(vo_ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (int (*)(vo_ncclComm_t *, int, vo_ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+        a.AllReduce = (int (*)(const void *, void *, size_t, int, int, vo_ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        a.CommDestroy = (int (*)(vo_ncclComm_t))dlsym(h, "ncclCommDestroy");
+        a.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy;
+        return a;
+    }();
+    return api;
+}
+#define VO_NCCL_DOUBLE 8     /* ncclFloat64 */
+#define VO_NCCL_SUM 0        /* ncclSum */
+
+extern "C" int vo_dist_unique_id(void *id_out)
+{
+    if (!id_out || !nccl_api().ok) return VO_ERR_INVALID_ARG;
+    vo_ncclUniqueId id;
+    if (nccl_api().GetUniqueId(&id) != 0) return VO_ERR_CUDA;
+    memcpy(id_out, &id, sizeof(id));
+    return VO_OK;
+}
+
+extern "C" int vo_dist_init(vo_ctx *ctx, int rank, int world, const void *unique_id)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(unique_id && world >= 1 && rank >= 0 && rank < world, VO_ERR_INVALID_ARG, "vo_dist_init: bad rank / world / id");
+    VO_REQUIRE(nccl_api().ok, VO_ERR_CUDA, "libnccl.so.2 could not be loaded");
+    VO_REQUIRE(!ctx->nccl_comm, VO_ERR_INVALID_ARG, "vo_dist_init: communicator already initialised");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    vo_ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    vo_ncclComm_t comm = nullptr;
+    const int rc = nccl_api().CommInitRank(&comm, world, id, rank);
+    if (rc != 0) {
+        ctx->last_error = std::string("ncclCommInitRank: ") + (nccl_api().GetErrorString ? nccl_api().GetErrorString(rc) : "error");
+        return VO_ERR_CUDA;
+    }
+    ctx->nccl_comm = comm; ctx->dist_rank = rank; ctx->dist_world = world;
+    return VO_OK;
+}
+
+extern "C" int vo_dist_finalize(vo_ctx *ctx)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    if (ctx->nccl_comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api().CommDestroy((vo_ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr; ctx->dist_world = 1; ctx->dist_rank = 0;
+    }
+    return VO_OK;
+}
+
+static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out, double *avg_err_out, int *success,
+                          bool dist);
+
 extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out,
                             double *avg_err_out, int *success)
+{
+    return lba_solve_impl(ctx, p, poses_out, points_out, avg_err_out, success, false);
+}
+
+extern "C" int vo_lba_solve_dist(vo_ctx *ctx, const vo_lba_problem *local_part, double *poses_out, double *points_out,
+                                 double *avg_err_out, int *success)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(ctx->nccl_comm != nullptr, VO_ERR_INVALID_ARG, "vo_lba_solve_dist: call vo_dist_init first");
+    return lba_solve_impl(ctx, local_part, poses_out, points_out, avg_err_out, success, true);
+}
+
+static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out, double *avg_err_out, int *success,
+                          bool dist)
 {
     if (!ctx || !p) return VO_ERR_INVALID_ARG;
     VO_REQUIRE(p->n_frames > 0 && p->n_points >= 0 && p->n_obs >= 0 && p->max_iter >= 1, VO_ERR_INVALID_ARG, "bad sizes");
@@ -745,7 +905,9 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     VO_REQUIRE(TL >= LBA_WARPS, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
     const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
     const size_t smem_build = fixed + per_lm * TL;
-    const size_t smem_solve = ((size_t)n6 * (n6 + 1) + 2 * n6 + (size_t)No * LBA_NA) * 8;
+    const int solve_B = n6 <= 48 ? 3 : 6;      // k_lba_solve<B>: 16 x 16 threads own B x B register blocks
+    const int solve_NP = SOLVE_G * solve_B;
+    const size_t smem_solve = ((size_t)solve_NP * (solve_NP + 1) + solve_NP + (size_t)No * LBA_NA) * 8;
 
     // device scratch (one allocation, grow-only)
     size_t off = 0;
@@ -757,7 +919,8 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     const size_t o_bc = take((size_t)n_obs * 144), o_cb = take((size_t)M * 24);
     const size_t o_sp = take((size_t)n_tiles * n6 * (n6 + 1) * 8), o_ap = take((size_t)n_tiles * No * LBA_NA * 8);
     const size_t o_ep = take((size_t)n_tiles * 8), o_x = take((size_t)n6 * 8);
-    const size_t o_red = take(((size_t)n6 * (n6 + 1) + (size_t)No * LBA_NA + 1) * 8);
+    const size_t n_red = (size_t)n6 * (n6 + 1) + (size_t)No * LBA_NA + 2;      // reduced system + A blocks + error + observation count
+    const size_t o_red = take(n_red * 8);
     const size_t o_ae = take((size_t)p->max_iter * 8), o_nan = take(16), o_dbg = take(128);
     const size_t total = off;
     if (total > ctx->lba_bytes) {
@@ -808,11 +971,12 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
         static std::once_flag once;
         static cudaError_t attr_err = cudaSuccess;
         std::call_once(once, [&]() {
-            const size_t max_solve = ((size_t)(6 * LBA_MAX_OPT) * (6 * LBA_MAX_OPT + 1) + 2 * 6 * LBA_MAX_OPT + (size_t)LBA_MAX_OPT * LBA_NA) * 8;
+            const size_t max_solve = ((size_t)(SOLVE_G * 6) * (SOLVE_G * 6 + 1) + SOLVE_G * 6 + (size_t)LBA_MAX_OPT * LBA_NA) * 8;
             cudaError_t e = cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
             cudaFuncSetAttribute(k_lba_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_lba_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_solve<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_solve<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_update_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr_err = e;
         });
@@ -824,8 +988,14 @@ extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_
     for (int it = 0; it < p->max_iter; ++it) {
         k_lba_build<<<n_tiles, LBA_THREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
         k_lba_reduce<<<vo_div_up((n6 * (n6 + 1) + No * LBA_NA + 1) * LBA_RED_G, 256), 256, 0, ctx->stream>>>(d);
+        if (dist) {
+            // the one exchange step of the path: partial reduced systems of the ranks' landmark shards -> complete system everywhere
+            const int nrc = nccl_api().AllReduce(d.red, d.red, n_red, VO_NCCL_DOUBLE, VO_NCCL_SUM, (vo_ncclComm_t)ctx->nccl_comm, ctx->stream);
+            if (nrc != 0) { ctx->last_error = std::string("ncclAllReduce: ") + (nccl_api().GetErrorString ? nccl_api().GetErrorString(nrc) : "error"); return VO_ERR_CUDA; }
+        }
         if (trace) cudaEventRecord(evs[2 * it + 1], ctx->stream);
-        k_lba_solve<<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
+        if (solve_B == 3) k_lba_solve<3><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
+        else k_lba_solve<6><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
         if (trace) cudaEventRecord(evs[2 * it + 2], ctx->stream);
         ctx->launches += 3;
     }

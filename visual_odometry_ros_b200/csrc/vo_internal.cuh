@@ -92,6 +92,9 @@ struct vo_ctx {
     // LBA scratch
     void *d_lba = nullptr;
     size_t lba_bytes = 0;
+    // distributed local BA (vo_dist_init): NCCL communicator of the landmark-sharded solve
+    void *nccl_comm = nullptr;
+    int dist_rank = 0, dist_world = 1;
 };
 
 #define VO_CUDA(call)                                                                  \
