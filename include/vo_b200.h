@@ -397,6 +397,16 @@ VO_API int vo_depth_filter_student_t(vo_ctx *ctx, const double *x_prev, const do
                               double *x_max_inout, const double *x_curr, const double *cov_curr,
                               int n, double *x_upd, double *cov_upd);
 
+/* Device-resident forms of the two seed updates (all pointers are device pointers, asynchronous on the context's stream):
+ * the seed state stays in HBM between frames; x_upd_d / cov_upd_d may alias x_prev_d / cov_prev_d (in-place update). */
+VO_API int vo_depth_filter_normal_d(vo_ctx *ctx, const double *x_prev_d, const double *cov_prev_d,
+                             const double *x_curr_d, const double *cov_curr_d, int n, double *x_upd_d,
+                             double *cov_upd_d);
+VO_API int vo_depth_filter_student_t_d(vo_ctx *ctx, const double *x_prev_d, const double *cov_prev_d,
+                                double *a_inout_d, double *b_inout_d, double *x_min_inout_d,
+                                double *x_max_inout_d, const double *x_curr_d, const double *cov_curr_d,
+                                int n, double *x_upd_d, double *cov_upd_d);
+
 /* ------------------------------------------------------------------ compaction
  * Stable mask compaction == LandmarkTracking(src, mask) (landmark.cpp:194-231, 291-332):
  * index_out[k] = index of the k-th set mask entry; *n_out = number kept. */

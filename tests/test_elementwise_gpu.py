@@ -89,6 +89,38 @@ def test_depth_filter_student_t(gpu_ctx):
     assert np.array_equal(log_, loo) and np.array_equal(hig, hio)
 
 
+def test_depth_filter_device_resident(gpu_ctx):
+    """vo_depth_filter_normal_d / _student_t_d: seeds stay in HBM, 10 in-place updates, same results as the host-buffer entries."""
+    import torch
+    from oracle import misc
+    rng = np.random.default_rng(4006)
+    n = 20000
+    dev = torch.device("cuda:0")
+    x, cov = rng.uniform(0.02, 0.5, n), rng.uniform(1e-4, 1e-2, n)
+    xo, co = x.copy(), cov.copy()
+    ao, bo, loo, hio = np.full(n, 10.0), np.full(n, 10.0), np.full(n, 0.01), np.full(n, 1.0)
+    xs, cs = x.copy(), cov.copy()
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(cov).to(dev)
+    xt, ct = torch.from_numpy(x).to(dev), torch.from_numpy(cov).to(dev)
+    at, bt = torch.full((n,), 10.0, dtype=torch.float64, device=dev), torch.full((n,), 10.0, dtype=torch.float64, device=dev)
+    lot, hit = torch.full((n,), 0.01, dtype=torch.float64, device=dev), torch.full((n,), 1.0, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for it in range(10):
+        meas, mcov = x + rng.normal(0, 0.01, n), rng.uniform(1e-4, 1e-3, n)
+        md, mc = torch.from_numpy(meas).to(dev), torch.from_numpy(mcov).to(dev)
+        torch.cuda.synchronize()
+        gpu_ctx.depth_filter_normal_d(xd.data_ptr(), cd.data_ptr(), md.data_ptr(), mc.data_ptr(), n, xd.data_ptr(), cd.data_ptr())   # in place
+        gpu_ctx.depth_filter_student_t_d(xt.data_ptr(), ct.data_ptr(), at.data_ptr(), bt.data_ptr(), lot.data_ptr(), hit.data_ptr(),
+                                         md.data_ptr(), mc.data_ptr(), n, xt.data_ptr(), ct.data_ptr())
+        gpu_ctx.synchronize()
+        xs, cs = misc.depth_filter_normal(xs, cs, meas, mcov)
+        xo, co, ao, bo, loo, hio = misc.depth_filter_student_t(xo, co, ao, bo, loo, hio, meas, mcov)
+    assert np.array_equal(xd.cpu().numpy(), xs) and np.array_equal(cd.cpu().numpy(), cs)
+    for g, o in ((xt, xo), (ct, co), (at, ao), (bt, bo)):
+        assert np.allclose(g.cpu().numpy(), o, rtol=1e-11, atol=0)
+    assert np.array_equal(lot.cpu().numpy(), loo) and np.array_equal(hit.cpu().numpy(), hio)
+
+
 def test_calc_prior_bit_exact(gpu_ctx):
     from oracle import misc
     rng = np.random.default_rng(12)

@@ -38,7 +38,8 @@ eye = T_d.clone()
 mask_d = torch.zeros(nprob * npts, dtype=torch.uint8, device=dev)
 it_d = torch.zeros(nprob, dtype=torch.int32, device=dev)
 ok_d = torch.zeros(nprob, dtype=torch.int32, device=dev)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(device=dev)      # an explicit stream shared by torch and the context (handle 0 would mean "own stream")
+torch.cuda.set_stream(stream)
 ctx2 = capi.Context(device=0, max_w=64, max_h=64, n_slots=0, max_feat=64, stream=stream.cuda_stream)
 res_T = {}
 for name, fl in (("fast", capi.VO_POSE_FAST), ("strict", capi.VO_POSE_STRICT)):

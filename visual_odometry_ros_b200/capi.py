@@ -139,6 +139,8 @@ def lib():
     L.vo_triangulate_dlt.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     L.vo_depth_filter_normal.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.vo_depth_filter_student_t.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
+    L.vo_depth_filter_normal_d.argtypes = L.vo_depth_filter_normal.argtypes
+    L.vo_depth_filter_student_t_d.argtypes = L.vo_depth_filter_student_t.argtypes
     L.vo_ft_calc_prior.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp]
     L.vo_compact.argtypes = [vp, vp, ctypes.c_int, vp, c_int_p]
     L.vo_ft_track_with_scale.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]
@@ -527,6 +529,15 @@ class Context:
         m = np.ones(n, np.uint8) if mask is None else np.ascontiguousarray(mask).astype(np.uint8).copy()
         check(self.h, self.L.vo_ft_track_with_scale(self.h, slot0, slot1, _ptr(p0), _ptr(sc), n, _ptr(pt), _ptr(m)))
         return pt, m.astype(bool)
+
+    def depth_filter_normal_d(self, x_prev_d, cov_prev_d, x_curr_d, cov_curr_d, n, x_upd_d, cov_upd_d):
+        """Device-resident DepthFilter::updateNormalDistribution (device pointers as ints; asynchronous)."""
+        check(self.h, self.L.vo_depth_filter_normal_d(self.h, vp(x_prev_d), vp(cov_prev_d), vp(x_curr_d), vp(cov_curr_d), int(n),
+                                                      vp(x_upd_d), vp(cov_upd_d)))
+
+    def depth_filter_student_t_d(self, x_prev_d, cov_prev_d, a_d, b_d, xmin_d, xmax_d, x_curr_d, cov_curr_d, n, x_upd_d, cov_upd_d):
+        check(self.h, self.L.vo_depth_filter_student_t_d(self.h, vp(x_prev_d), vp(cov_prev_d), vp(a_d), vp(b_d), vp(xmin_d), vp(xmax_d),
+                                                         vp(x_curr_d), vp(cov_curr_d), int(n), vp(x_upd_d), vp(cov_upd_d)))
 
     # ---------------------------------------------------------------- local bundle adjustment
     def lba_solve(self, p, dist=False):

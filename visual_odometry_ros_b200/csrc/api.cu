@@ -91,19 +91,21 @@ extern "C" int vo_ctx_create(int device, int max_w, int max_h, int n_slots, int 
         img_bytes += align_up(pitch * rows, 256);
         der_bytes += align_up(pitch * rows * sizeof(short2), 256);
     }
+    // ONE allocation for all slots, uniform stride: the pyramid planes of level l of every slot are then one 3-D tensor
+    // (x, y, slot) for the TMA descriptors of the LK kernels (klt.cu)
     ctx->slots.resize(n_slots);
+    ctx->slot_stride = img_bytes + der_bytes;          // multiple of 256
+    if (n_slots > 0) {
+        if (cudaMalloc((void **)&ctx->slot_pool, ctx->slot_stride * (size_t)n_slots) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+        if (cudaMemsetAsync(ctx->slot_pool, 0, ctx->slot_stride * (size_t)n_slots, ctx->stream) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+    }
     for (int s = 0; s < n_slots; ++s) {
         Slot &S = ctx->slots[s];
-        S.bytes = img_bytes + der_bytes;
-        if (cudaMalloc((void **)&S.base, S.bytes) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
-        if (cudaMemsetAsync(S.base, 0, S.bytes, ctx->stream) != cudaSuccess) { vo_ctx_destroy(ctx); return VO_ERR_CUDA; }
+        S.bytes = ctx->slot_stride;
+        S.base = ctx->slot_pool + (size_t)s * ctx->slot_stride;
         memset(&S.desc, 0, sizeof(S.desc));
     }
     if (n_slots > 0 && cudaMalloc((void **)&ctx->d_slots, sizeof(SlotDesc) * n_slots) != cudaSuccess) {
-        vo_ctx_destroy(ctx);
-        return VO_ERR_CUDA;
-    }
-    if (n_slots > 0 && cudaMalloc((void **)&ctx->d_tmaps, sizeof(CUtensorMap) * (size_t)n_slots * VO_MAX_LEVELS * 3) != cudaSuccess) {
         vo_ctx_destroy(ctx);
         return VO_ERR_CUDA;
     }
@@ -124,9 +126,9 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl_comm) vo_dist_finalize(ctx);
-    for (auto &S : ctx->slots) if (S.base) cudaFree(S.base);
+    vo_klt_maps_free(ctx);
+    if (ctx->slot_pool) cudaFree(ctx->slot_pool);
     if (ctx->d_slots) cudaFree(ctx->d_slots);
-    if (ctx->d_tmaps) cudaFree(ctx->d_tmaps);
     if (ctx->raw_base) cudaFree(ctx->raw_base);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
@@ -207,7 +209,6 @@ static int slot_set_geometry(vo_ctx *ctx, int slot, int w, int h)
     }
     S.desc.raw = ctx->raw_base + (size_t)slot * ctx->raw_stride;
     S.w = w; S.h = h;
-    S.tmap_win = 0;              // plane addresses / sizes changed: the TMA descriptors are stale
     VO_CUDA(cudaMemcpyAsync(ctx->d_slots + slot, &S.desc, sizeof(SlotDesc), cudaMemcpyHostToDevice, ctx->stream));
     // the descriptor lives in pageable host memory inside the vector: make the copy complete
     // before anybody can move/modify it

@@ -36,21 +36,22 @@ __global__ void __launch_bounds__(128) k_triangulate(const TriArgs a)
 
 // ------------------------------------------------------------------------------ K-df
 __global__ void __launch_bounds__(256)
-k_df_normal(const double *__restrict__ xp, const double *__restrict__ cp, const double *__restrict__ xc,
-            const double *__restrict__ cc, int n, double *__restrict__ xu, double *__restrict__ cu)
+k_df_normal(const double *xp, const double *cp, const double *__restrict__ xc,
+            const double *__restrict__ cc, int n, double *xu, double *cu)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double inv_cov_sum = 1.0 / (cp[i] + cc[i]);
-    cu[i] = (cp[i] * cc[i]) * inv_cov_sum;
-    xu[i] = (xp[i] * cc[i] + xc[i] * cp[i]) * inv_cov_sum;
+    const double x0 = xp[i], c0 = cp[i], x1 = xc[i], c1 = cc[i];     // all reads first: xu / cu may alias xp / cp
+    const double inv_cov_sum = 1.0 / (c0 + c1);
+    cu[i] = (c0 * c1) * inv_cov_sum;
+    xu[i] = (x0 * c1 + x1 * c0) * inv_cov_sum;
 }
 
 __global__ void __launch_bounds__(256)
-k_df_student_t(const double *__restrict__ xp, const double *__restrict__ cp, double *__restrict__ a,
+k_df_student_t(const double *xp, const double *cp, double *__restrict__ a,
                double *__restrict__ b, double *__restrict__ xmin, double *__restrict__ xmax,
-               const double *__restrict__ xc, const double *__restrict__ cc, int n, double *__restrict__ xu,
-               double *__restrict__ cu)
+               const double *__restrict__ xc, const double *__restrict__ cc, int n, double *xu,
+               double *cu)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -251,6 +252,39 @@ extern "C" int vo_depth_filter_student_t(vo_ctx *ctx, const double *x_prev, cons
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(a_inout, h, N); memcpy(b_inout, h + N, N); memcpy(x_min_inout, h + 2 * N, N); memcpy(x_max_inout, h + 3 * N, N);
     memcpy(x_upd, h + 4 * N, N); memcpy(cov_upd, h + 5 * N, N);
+    return VO_OK;
+}
+
+// Device-resident forms: the seed arrays stay in HBM between updates (a 20 000-seed update through host buffers is a
+// 1 MB PCIe round trip around a 2 us kernel -- slower than one CPU core; resident, it is the kernel alone).
+extern "C" int vo_depth_filter_normal_d(vo_ctx *ctx, const double *x_prev_d, const double *cov_prev_d, const double *x_curr_d,
+                                        const double *cov_curr_d, int n, double *x_upd_d, double *cov_upd_d)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(x_prev_d && cov_prev_d && x_curr_d && cov_curr_d && x_upd_d && cov_upd_d, VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    k_df_normal<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(x_prev_d, cov_prev_d, x_curr_d, cov_curr_d, n, x_upd_d, cov_upd_d);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
+extern "C" int vo_depth_filter_student_t_d(vo_ctx *ctx, const double *x_prev_d, const double *cov_prev_d, double *a_inout_d,
+                                           double *b_inout_d, double *x_min_inout_d, double *x_max_inout_d, const double *x_curr_d,
+                                           const double *cov_curr_d, int n, double *x_upd_d, double *cov_upd_d)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(x_prev_d && cov_prev_d && a_inout_d && b_inout_d && x_min_inout_d && x_max_inout_d && x_curr_d && cov_curr_d && x_upd_d && cov_upd_d,
+               VO_ERR_INVALID_ARG, "null pointer");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    k_df_student_t<<<vo_div_up(n, 256), 256, 0, ctx->stream>>>(x_prev_d, cov_prev_d, a_inout_d, b_inout_d, x_min_inout_d, x_max_inout_d,
+                                                              x_curr_d, cov_curr_d, n, x_upd_d, cov_upd_d);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
     return VO_OK;
 }
 

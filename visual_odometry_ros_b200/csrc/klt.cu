@@ -18,6 +18,7 @@
 #include "klt_scale_device.cuh"
 
 #include <cfloat>
+#include <map>
 #include <cstdlib>
 
 #define W_BITS 14
@@ -27,14 +28,13 @@
 
 struct KltArgs {
     const SlotDesc *slots;
-    IdList s0, s1;
+    int sid0, sid1;                 // image slots of the pair (single-pair launches: the fused chains)
     const float2 *pts0;
     float2 *pts1;
     uint8_t *status;
     float *err;
     unsigned long long *counters;   // [2*VO_MAX_LEVELS] or null
     const uint8_t *skip_mask;       // nullable: features whose entry is 0 are not tracked (outputs untouched)
-    const CUtensorMap *tmaps;       // [n_slots][VO_MAX_LEVELS][3] (k_klt3 / k_track_chain)
     int n;
     int win;
     int top_level;      // effective maxLevel
@@ -43,6 +43,11 @@ struct KltArgs {
     float min_eig;
     double eps2;
     KltPost post;
+};
+// batched launches: up to VO_IDLIST_MAX pairs, slot ids by value (kept apart from KltArgs so that the fused chain kernel,
+// which carries three KltArgs and the TMA descriptors, stays below 4 KB of kernel parameters)
+struct KltBatchIds {
+    IdList s0, s1;
 };
 
 __device__ __forceinline__ long long warp_sum_exact(int v)
@@ -119,7 +124,7 @@ __device__ __forceinline__ void klt_epilogue(const KltArgs &a, size_t gi, const 
 
 template <int NPX>
 __global__ void __launch_bounds__(128)
-k_klt(const KltArgs a)
+k_klt(const KltArgs a, const KltBatchIds ids)
 {
     const int lane = threadIdx.x & 31;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -127,8 +132,8 @@ k_klt(const KltArgs a)
     if (f >= a.n) return;
     const size_t gi = (size_t)pair * a.n + f;
     if (a.skip_mask && !a.skip_mask[gi]) return;
-    const SlotDesc &S0 = a.slots[a.s0.id[pair]];
-    const SlotDesc &S1 = a.slots[a.s1.id[pair]];
+    const SlotDesc &S0 = a.slots[ids.s0.id[pair]];
+    const SlotDesc &S1 = a.slots[ids.s1.id[pair]];
     const int win = a.win;
     const int npix = win * win;
     const float halfWin = (float)(win - 1) * 0.5f;
@@ -285,11 +290,14 @@ k_klt(const KltArgs a)
 // v3 hands the staging to the TMA unit: three cp.async.bulk.tensor.2d boxes per (feature, level) -- template patch
 // (u8), Scharr patch (short2 as 32-bit elements), search region (u8) -- issued by one lane against per-(slot, level)
 // tensor maps, landing on two per-warp mbarriers:
-//   * the boxes start at the EXACT window origin (TMA takes element coordinates), so the template is word-aligned by
-//     construction and the staging needs no address arithmetic, no registers and no STS;
+//   * the staging needs no address arithmetic, no registers and no STS: three box coordinates per request;
 //   * the NEXT level's template / Scharr boxes are requested as soon as the current level's template registers are
 //     built, the current level's search region right at the level start: both land while the warp computes.
-// Box row pitches (48 B image rows, 28 / 36-element Scharr rows) are the dense TMA layout; they are chosen so that
+// A TMA box must start on a 16-byte boundary of its innermost dimension (measured on this B200 / driver 13.0 with
+// tools/probe/tma_probe3.cu: the programming guide's own example faults with "illegal instruction" at x = 65 int32
+// elements and runs at x = 64), so box origins are rounded DOWN to 16 pixels (u8 planes) / 4 elements (short2 plane)
+// and the window sits at byte offset ipx & 15 inside the staged rows -- the funnel-shift realignment of load_run absorbs it.
+// Box row pitches (48 / 80 B image rows, 28 / 36-element Scharr rows) are the dense TMA layout; they are chosen so that
 // r * pitch mod 32 banks has period 8, which keeps the row-segment reads of the iterations at most 2-way conflicted.
 // Each lane owns RPL horizontal runs of RL pixels; a run reads 3 words from each of 2 rows, realigns them with funnel
 // shifts and evaluates the fixed-point bilinear sample of a pixel with two dp2a (s16 weight pair x u8 pixel pair) --
@@ -304,22 +312,25 @@ template <int WIN> struct Klt3Cfg {
     static constexpr int NRUN = WIN * SEG;
     static constexpr int RPL = (NRUN + 31) / 32;                         // runs per lane
     static constexpr bool FULL = (WIN % SEG) == 0;                       // every run has RL pixels
+    static constexpr int MISS = SEG * RL - WIN;                          // pixels the LAST run of a row is short of RL
     static constexpr int NPX = RPL * RL;                                 // template registers per lane
-    // TMA boxes (dense rows in shared memory)
-    static constexpr int IBW = 48;                                       // template patch: bytes per row (12 words)
-    static constexpr int DBW = (SEG * RL + 1 <= 28) ? 28 : 36;           // Scharr patch: short2 elements per row
-    static constexpr int JBW = 48;                                       // search region: bytes per row
+    // TMA boxes (dense rows in shared memory); origins are 16-byte aligned, so a row holds up to 15 (u8) / 3 (short2) lead-in
+    // elements before the window
+    static constexpr int JBW = (W1 + MJ + 15 <= 48) ? 48 : 80;           // search region: bytes per row (12 / 20 words)
+    static constexpr int IBW = JBW;                                      // template patch: fetched with the search-region box
+    static constexpr int DBW = (SEG * RL + 4 <= 28) ? 28 : 36;           // Scharr patch: short2 elements per row
     static constexpr int JR = W1 + 2 * MJ;                               // search region rows
-    static constexpr int JMX = (JBW - W1) / 2;                           // horizontal margin left of the window
     static constexpr int IPW = IBW / 4, DPW = DBW, JPW = JBW / 4;        // pitches in 32-bit words
-    static constexpr int I_BYTES = W1 * IBW, D_BYTES = W1 * DBW * 4, J_BYTES = JR * JBW;
+    static constexpr int I_BYTES = JR * IBW;                             // the template patch is fetched with the search-region box
+    static constexpr int D_BYTES = W1 * DBW * 4, J_BYTES = JR * JBW;
     static constexpr int OFF_I = 0;
     static constexpr int OFF_D = (I_BYTES + 127) & ~127;
     static constexpr int OFF_J = OFF_D + ((D_BYTES + 127) & ~127);
     static constexpr int WARP_BYTES = OFF_J + ((J_BYTES + 16 + 127) & ~127);   // +16: load_run may touch one word past a row
     static constexpr int MINB = NPX <= 14 ? 5 : (NPX <= 24 ? 3 : 2);     // resident CTAs per SM the register budget is sized for
     static_assert(RL <= 8, "load_run covers at most 8 pixels");
-    static_assert(W1 <= JBW - 2 && SEG * RL + 1 <= DBW, "boxes too small for this window");
+    static_assert(W1 + MJ + 15 <= JBW && SEG * RL + 4 <= DBW && IBW == JBW, "boxes too small for this window");
+    static_assert(((15 + (SEG - 1) * RL) >> 2) + 3 <= IPW, "template run reads leave the staged row");
 };
 
 __device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c)
@@ -334,6 +345,15 @@ __device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c)
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+
+// TMA descriptors of one launch, passed BY VALUE as a __grid_constant__ kernel parameter (the canonical path: no
+// descriptor fetch from global memory, no proxy fence).  All slots of a context live in one allocation with a uniform
+// stride, so level l of every slot is ONE rank-3 tensor (x, y, slot): [l] image plane, box JBW x JR x 1 (search region; the
+// template patch uses the same box and ignores the extra rows), [l] Scharr plane, box DBW x W1 x 1.
+struct KltMaps {
+    CUtensorMap img[VO_MAX_LEVELS];
+    CUtensorMap der[VO_MAX_LEVELS];
+};
 
 // ---- TMA / mbarrier plumbing (one lane issues, the warp waits)
 struct WarpPipe {
@@ -363,10 +383,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t &phase)
     while (!mbar_try_wait(bar, phase)) { if (++spins > (1 << 20)) __trap(); }
     phase ^= 1u;
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // 8-bit sample stream of one run: E holds bytes e0.., O the same shifted by one byte.
@@ -411,7 +431,8 @@ __device__ __forceinline__ bool klt_tpl_origin(const float2 p0, const int level,
 // One (pair, feature) on one warp: every level, every iteration, the fused post-filter epilogue.
 // wbuf: this warp's 128-byte aligned staging area (Klt3Cfg<WIN>::WARP_BYTES); pp: its two mbarriers.
 template <int WIN>
-__device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, const int f, uint8_t *wbuf, WarpPipe &pp, const int lane)
+__device__ __forceinline__ void klt3_feature(const KltArgs &a, const KltMaps &maps, const int sid0, const int sid1, const int pair, const int f,
+                                             uint8_t *wbuf, WarpPipe &pp, const int lane)
 {
     using C = Klt3Cfg<WIN>;
     const size_t gi = (size_t)pair * a.n + f;
@@ -420,19 +441,16 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
     uint32_t *Dbuf = reinterpret_cast<uint32_t *>(wbuf + C::OFF_D);
     uint32_t *Jbuf = reinterpret_cast<uint32_t *>(wbuf + C::OFF_J);
     const uint32_t sI = smem_addr(Ibuf), sD = smem_addr(Dbuf), sJ = smem_addr(Jbuf);
-    const int sid0 = a.s0.id[pair], sid1 = a.s1.id[pair];
     const SlotDesc &S0 = a.slots[sid0];
     const SlotDesc &S1 = a.slots[sid1];
-    const CUtensorMap *tm0 = a.tmaps + (size_t)sid0 * (VO_MAX_LEVELS * 3);   // per level: {template box, Scharr box, search box}
-    const CUtensorMap *tm1 = a.tmaps + (size_t)sid1 * (VO_MAX_LEVELS * 3);
     const float halfWin = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     const float eps2_lo = (float)a.eps2 * 0.9999f, eps2_hi = (float)a.eps2 * 1.0001f;
 
     // run geometry of this lane (level independent). Idle slots alias an existing run; their
     // contributions are dropped per RUN (run_ok), never per pixel.
-    int run_row[C::RPL], run_x0[C::RPL];
-    bool run_ok[C::RPL], last_ok[C::RPL];
+    int run_row[C::RPL], run_x0[C::RPL], run_len[C::RPL];
+    bool run_ok[C::RPL];
 #pragma unroll
     for (int q = 0; q < C::RPL; ++q) {
         const int id = lane + 32 * q;
@@ -441,7 +459,7 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
         const int r = idm / C::SEG, sgm = idm - r * C::SEG;
         run_row[q] = r;
         run_x0[q] = sgm * C::RL;
-        last_ok[q] = C::FULL || (sgm * C::RL + C::RL <= WIN);     // does pixel RL-1 of this run exist?
+        run_len[q] = min(C::RL, WIN - sgm * C::RL);               // pixels of this run inside the window (RL - MISS for a row's last run)
     }
 
     const float2 p0 = a.pts0[gi];
@@ -455,8 +473,8 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
         const LevelDesc I = S0.lv[a.top_level];
         if (klt_tpl_origin(p0, a.top_level, halfWin, WIN, I.w, I.h, px_, py_, ix_, iy_) && lane == 0) {
             mbar_expect_tx(pp.bar_id, C::I_BYTES + C::D_BYTES);
-            tma_load_2d(sI, tm0 + a.top_level * 3 + 0, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
-            tma_load_2d(sD, tm0 + a.top_level * 3 + 1, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
+            tma_load_3d(sI, &maps.img[a.top_level], pp.bar_id, (ix_ & ~15) + VO_PAD, iy_ + VO_PAD, sid0);
+            tma_load_3d(sD, &maps.der[a.top_level], pp.bar_id, (ix_ & ~3) + VO_PAD, iy_ + VO_PAD, sid0);
         }
     }
 
@@ -483,15 +501,15 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
 
         // ---- request the search region around the start position (lands while the template is built)
         nextx = __fsub_rn(nextx, halfWin); nexty = __fsub_rn(nexty, halfWin);
-        int jx0, jy0;   // origin (pixel coords) of the staged search region
+        int jx0, jy0;   // origin (pixel coords) of the staged search region; jx0 is 16-aligned
         {
             int inx = __float2int_rd(nextx), iny = __float2int_rd(nexty);
             // clamp the staging origin so that it stays near the padded plane even for a wild start
             inx = max(-WIN, min(inx, J.w - 1)); iny = max(-WIN, min(iny, J.h - 1));
-            jx0 = inx - C::JMX; jy0 = iny - MJ;
+            jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
             if (lane == 0) {
                 mbar_expect_tx(pp.bar_j, C::J_BYTES);
-                tma_load_2d(sJ, tm1 + level * 3 + 2, pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD);
+                tma_load_3d(sJ, &maps.img[level], pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD, sid1);
             }
         }
         mbar_wait(pp.bar_id, pp.ph_id);        // template + Scharr boxes of this level (requested one level earlier)
@@ -502,13 +520,14 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
         int sA11 = 0, sA12 = 0, sA22 = 0;
         {
             const int wA = (iw00 & 0xffff) | (iw01 << 16), wB = (iw10 & 0xffff) | (iw11 << 16);
+            const int offI = ipx & 15, offD = ipx & 3;                    // the boxes start at ipx rounded down to 16 bytes
 #pragma unroll
             for (int q = 0; q < C::RPL; ++q) {
                 uint32_t EA[3], OA[3], EB[3], OB[3];
                 const int r = run_row[q];
-                load_run(Ibuf + r * C::IPW, run_x0[q], EA, OA);           // the box starts at the window origin
-                load_run(Ibuf + (r + 1) * C::IPW, run_x0[q], EB, OB);
-                const uint32_t *d0 = Dbuf + r * C::DPW + run_x0[q];
+                load_run(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
+                load_run(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
+                const uint32_t *d0 = Dbuf + r * C::DPW + offD + run_x0[q];
                 const uint32_t *d1 = d0 + C::DPW;
                 uint32_t da = d0[0], db = d1[0];
                 int a11 = 0, a12 = 0, a22 = 0;
@@ -520,7 +539,7 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
                               (int)(short)(db1 & 0xffff) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
                     int iy = (((int)da >> 16) * iw00 + ((int)da1 >> 16) * iw01 + ((int)db >> 16) * iw10 + ((int)db1 >> 16) * iw11 +
                               (1 << (W_BITS - 1))) >> W_BITS;
-                    if (!C::FULL && k == C::RL - 1 && !last_ok[q]) { ix = 0; iy = 0; }
+                    if (!C::FULL && k >= C::RL - C::MISS && k >= run_len[q]) { ix = 0; iy = 0; }
                     Cn[q * C::RL + k] = KLT2_RND - (iv << KLT2_SH);
                     Ix[q * C::RL + k] = ix; Iy[q * C::RL + k] = iy;
                     a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
@@ -536,8 +555,8 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
             const LevelDesc In = S0.lv[level - 1];
             if (klt_tpl_origin(p0, level - 1, halfWin, WIN, In.w, In.h, px_, py_, ix_, iy_) && lane == 0) {
                 mbar_expect_tx(pp.bar_id, C::I_BYTES + C::D_BYTES);
-                tma_load_2d(sI, tm0 + (level - 1) * 3 + 0, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
-                tma_load_2d(sD, tm0 + (level - 1) * 3 + 1, pp.bar_id, ix_ + VO_PAD, iy_ + VO_PAD);
+                tma_load_3d(sI, &maps.img[level - 1], pp.bar_id, (ix_ & ~15) + VO_PAD, iy_ + VO_PAD, sid0);
+                tma_load_3d(sD, &maps.der[level - 1], pp.bar_id, (ix_ & ~3) + VO_PAD, iy_ + VO_PAD, sid0);
             }
         }
         const float A11 = __fmul_rn(warp_sum_exact_f(sA11), FLT_SCALE);
@@ -569,10 +588,10 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
             int offx = inx - jx0, offy = iny - jy0;
             if (offx < 0 || offx + C::W1 > C::JBW || offy < 0 || offy + C::W1 > C::JR) {
                 __syncwarp();
-                jx0 = inx - C::JMX; jy0 = iny - MJ;
+                jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
                 if (lane == 0) {
                     mbar_expect_tx(pp.bar_j, C::J_BYTES);
-                    tma_load_2d(sJ, tm1 + level * 3 + 2, pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD);
+                    tma_load_3d(sJ, &maps.img[level], pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD, sid1);
                 }
                 mbar_wait(pp.bar_j, pp.ph_j);
                 offx = inx - jx0; offy = iny - jy0;
@@ -590,7 +609,7 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
 #pragma unroll
                 for (int k = 0; k < C::RL; ++k) {
                     const int diff = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, Cn[q * C::RL + k]) >> KLT2_SH;
-                    b1q += diff * Ix[q * C::RL + k];     // Ix = Iy = 0 on a non-existent last pixel
+                    b1q += diff * Ix[q * C::RL + k];     // Ix = Iy = 0 on the pixels a short run does not have
                     b2q += diff * Iy[q * C::RL + k];
                 }
                 sb1 += run_ok[q] ? b1q : 0; sb2 += run_ok[q] ? b2q : 0;
@@ -621,10 +640,10 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
                 int offx = inx - jx0, offy = iny - jy0;
                 if (offx < 0 || offx + C::W1 > C::JBW || offy < 0 || offy + C::W1 > C::JR) {
                     __syncwarp();
-                    jx0 = inx - C::JMX; jy0 = iny - MJ;
+                    jx0 = (inx - MJ) & ~15; jy0 = iny - MJ;
                     if (lane == 0) {
                         mbar_expect_tx(pp.bar_j, C::J_BYTES);
-                        tma_load_2d(sJ, tm1 + level * 3 + 2, pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD);
+                        tma_load_3d(sJ, &maps.img[level], pp.bar_j, jx0 + VO_PAD, jy0 + VO_PAD, sid1);
                     }
                     mbar_wait(pp.bar_j, pp.ph_j);
                     offx = inx - jx0; offy = iny - jy0;
@@ -642,7 +661,7 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const int pair, c
 #pragma unroll
                     for (int k = 0; k < C::RL; ++k) {
                         const int diff = KLT2_SAMPLE(k, EA, OA, EB, OB, wA, wB, Cn[q * C::RL + k]) >> KLT2_SH;
-                        sq += (!C::FULL && k == C::RL - 1 && !last_ok[q]) ? 0 : abs(diff);
+                        sq += (!C::FULL && k >= C::RL - C::MISS && k >= run_len[q]) ? 0 : abs(diff);
                     }
                     sabs += run_ok[q] ? sq : 0;
                 }
@@ -677,7 +696,7 @@ __device__ __forceinline__ uint8_t *klt3_warp_setup(uint8_t *smem_raw, unsigned 
 
 template <int WIN>
 __global__ void __launch_bounds__(32 * KLT2_WPB, Klt3Cfg<WIN>::MINB * 4 / KLT2_WPB)
-k_klt3(const KltArgs a)
+k_klt3(const KltArgs a, const KltBatchIds ids, const __grid_constant__ KltMaps maps)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * KLT2_WPB];
@@ -686,7 +705,7 @@ k_klt3(const KltArgs a)
     if (f >= a.n) return;
     WarpPipe pp;
     uint8_t *wbuf = klt3_warp_setup<WIN>(smem_raw, bars, wib, lane, pp);
-    klt3_feature<WIN>(a, blockIdx.y, f, wbuf, pp, lane);
+    klt3_feature<WIN>(a, maps, ids.s0.id[blockIdx.y], ids.s1.id[blockIdx.y], blockIdx.y, f, wbuf, pp, lane);
 }
 
 // Fused tracking chain of the stereo frame step (stereo_vo.cpp:533-571): trackWithPrior(l0 -> l1), trackWithScale,
@@ -699,7 +718,7 @@ k_klt3(const KltArgs a)
 #define VO_CHAIN_NEXT 4     // third LK pass (l1 -> r1)
 template <int WIN>
 __global__ void __launch_bounds__(32 * KLT2_WPB, (Klt3Cfg<WIN>::MINB > 4 ? 4 : Klt3Cfg<WIN>::MINB) * 4 / KLT2_WPB)
-k_track_chain(const KltArgs a1, const KltArgs a2, const KltScaleArgs sc, const KltArgs a3, const int stages)
+k_track_chain(const KltArgs a1, const KltArgs a2, const KltScaleArgs sc, const KltArgs a3, const int stages, const __grid_constant__ KltMaps maps)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * KLT2_WPB];
@@ -708,11 +727,11 @@ k_track_chain(const KltArgs a1, const KltArgs a2, const KltScaleArgs sc, const K
     if (f >= a1.n) return;
     WarpPipe pp;
     uint8_t *wbuf = klt3_warp_setup<WIN>(smem_raw, bars, wib, lane, pp);
-    klt3_feature<WIN>(a1, 0, f, wbuf, pp, lane);
+    klt3_feature<WIN>(a1, maps, a1.sid0, a1.sid1, 0, f, wbuf, pp, lane);
     __syncwarp();                          // lane 0's point / status / mask stores are visible to the whole warp
-    if (stages & VO_CHAIN_BACK) { klt3_feature<WIN>(a2, 0, f, wbuf, pp, lane); __syncwarp(); }
+    if (stages & VO_CHAIN_BACK) { klt3_feature<WIN>(a2, maps, a2.sid0, a2.sid1, 0, f, wbuf, pp, lane); __syncwarp(); }
     if (stages & VO_CHAIN_SCALE) { klt_scale_feature(sc, f, lane); __syncwarp(); }
-    if (stages & VO_CHAIN_NEXT) klt3_feature<WIN>(a3, 0, f, wbuf, pp, lane);
+    if (stages & VO_CHAIN_NEXT) klt3_feature<WIN>(a3, maps, a3.sid0, a3.sid1, 0, f, wbuf, pp, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -728,11 +747,11 @@ static Klt3Boxes klt3_boxes(int win)
 {
     const int seg = win > 24 ? 4 : (win > 16 ? 3 : 2), rl = (win + seg - 1) / seg;
     Klt3Boxes b;
-    b.w1 = win + 1; b.ibw = 48; b.dbw = (seg * rl + 1 <= 28) ? 28 : 36; b.jbw = 48; b.jr = win + 1 + 2 * MJ;
+    b.w1 = win + 1; b.jbw = (win + 1 + MJ + 15 <= 48) ? 48 : 80; b.ibw = b.jbw; b.dbw = (seg * rl + 4 <= 28) ? 28 : 36; b.jr = win + 1 + 2 * MJ;
     return b;
 }
-#define KLT3_CHECK_BOXES(W) static_assert(Klt3Cfg<W>::IBW == 48 && Klt3Cfg<W>::JBW == 48 && Klt3Cfg<W>::JR == W + 1 + 2 * MJ && \
-                                          Klt3Cfg<W>::DBW == ((((W > 24 ? 4 : (W > 16 ? 3 : 2)) * Klt3Cfg<W>::RL + 1) <= 28) ? 28 : 36), "klt3_boxes out of step");
+#define KLT3_CHECK_BOXES(W) static_assert(Klt3Cfg<W>::JBW == ((W + 1 + MJ + 15 <= 48) ? 48 : 80) && Klt3Cfg<W>::JR == W + 1 + 2 * MJ && \
+                                          Klt3Cfg<W>::DBW == ((((W > 24 ? 4 : (W > 16 ? 3 : 2)) * Klt3Cfg<W>::RL + 4) <= 28) ? 28 : 36), "klt3_boxes out of step");
 KLT3_FOR_EACH_WIN(KLT3_CHECK_BOXES)
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -749,68 +768,74 @@ static PFN_tmapEncodeTiled tmap_encoder()
     return fn;
 }
 
-// (Re)encode the TMA descriptors of these slots for window size `win` and put them on the device (stream-ordered before
-// the launch that follows).  Per (slot, level): [0] template box IBW x W1 (u8), [1] Scharr box DBW x W1 (short2 as 32-bit
-// elements), [2] search box JBW x JR (u8), all over the WHOLE padded plane (pitch x (h + 2 PAD)), so that any window
-// origin the kernel can produce is a valid (possibly partly out-of-bounds = zero-filled, never used) box coordinate.
-static int ensure_tmaps(vo_ctx *ctx, const int *slots, int n, int win)
+// TMA descriptor set for images of w x h in this context and window size `win`, encoded once and cached.  Per level:
+// image planes of ALL slots as one rank-3 u8 tensor {pitch, h + 2 PAD, n_slots} (strides pitch, slot stride), box JBW x JR x 1;
+// Scharr planes as a rank-3 tensor of 32-bit elements (short2), box DBW x W1 x 1.  The tensors cover the whole padded
+// planes, so any window origin the kernel can produce is a valid (possibly partly out-of-bounds = zero-filled, never
+// used) box coordinate.
+struct KltMapKey {
+    int w, h, win;
+    bool operator<(const KltMapKey &o) const { return w != o.w ? w < o.w : (h != o.h ? h < o.h : win < o.win); }
+};
+typedef std::map<KltMapKey, KltMaps> KltMapCache;
+
+void vo_klt_maps_free(vo_ctx *ctx)
 {
-    PFN_tmapEncodeTiled enc = nullptr;
+    delete static_cast<KltMapCache *>(ctx->klt_maps);
+    ctx->klt_maps = nullptr;
+}
+
+static int get_klt_maps(vo_ctx *ctx, int slot, int win, const KltMaps **out)
+{
+    const Slot &S = ctx->slots[slot];
+    if (!ctx->klt_maps) ctx->klt_maps = new KltMapCache();
+    KltMapCache &cache = *static_cast<KltMapCache *>(ctx->klt_maps);
+    const KltMapKey key{S.w, S.h, win};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = &it->second; return VO_OK; }
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    VO_REQUIRE(enc != nullptr, VO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const Klt3Boxes B = klt3_boxes(win);
-    bool copied = false;
-    for (int i = 0; i < n; ++i) {
-        Slot &S = ctx->slots[slots[i]];
-        if (S.tmap_win == win) continue;
-        if (!enc) {
-            enc = tmap_encoder();
-            VO_REQUIRE(enc != nullptr, VO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    KltMaps m;
+    memset(&m, 0, sizeof(m));
+    for (int l = 0; l < ctx->max_levels; ++l) {
+        const LevelDesc &L = S.desc.lv[l];
+        if (!L.img) continue;
+        // plane start of this level inside slot 0 (every slot of this geometry has the same layout at the same offsets)
+        uint8_t *img_plane0 = ctx->slot_pool + ((L.img - (size_t)VO_PAD * L.pitch - VO_PAD) - S.base);
+        uint8_t *der_plane0 = ctx->slot_pool + (reinterpret_cast<uint8_t *>(L.deriv - (size_t)VO_PAD * L.pitch - VO_PAD) - S.base);
+        const cuuint64_t rows = (cuuint64_t)L.h + 2 * VO_PAD;
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, rows, (cuuint64_t)ctx->n_slots};
+        const cuuint64_t str8[2] = {(cuuint64_t)L.pitch, (cuuint64_t)ctx->slot_stride};
+        const cuuint64_t str32[2] = {(cuuint64_t)L.pitch * 4, (cuuint64_t)ctx->slot_stride};
+        const cuuint32_t boxJ[3] = {(cuuint32_t)B.jbw, (cuuint32_t)B.jr, 1}, boxD[3] = {(cuuint32_t)B.dbw, (cuuint32_t)B.w1, 1};
+        const CUresult r0 = enc(&m.img[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, img_plane0, dims, str8, boxJ, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const CUresult r1 = enc(&m.der[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, der_plane0, dims, str32, boxD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS) {
+            ctx->last_error = "cuTensorMapEncodeTiled failed (level " + std::to_string(l) + ", codes " + std::to_string((int)r0) + " " +
+                              std::to_string((int)r1) + ")";
+            return VO_ERR_CUDA;
         }
-        CUtensorMap maps[VO_MAX_LEVELS * 3];
-        memset(maps, 0, sizeof(maps));
-        for (int l = 0; l < ctx->max_levels; ++l) {
-            const LevelDesc &L = S.desc.lv[l];
-            if (!L.img) continue;
-            const cuuint64_t rows = (cuuint64_t)L.h + 2 * VO_PAD;
-            const cuuint32_t estr[2] = {1, 1};
-            void *img_plane = L.img - (size_t)VO_PAD * L.pitch - VO_PAD;
-            void *der_plane = L.deriv - (size_t)VO_PAD * L.pitch - VO_PAD;
-            const cuuint64_t dim8[2] = {(cuuint64_t)L.pitch, rows}, str8[1] = {(cuuint64_t)L.pitch};
-            const cuuint64_t dim32[2] = {(cuuint64_t)L.pitch, rows}, str32[1] = {(cuuint64_t)L.pitch * 4};
-            const cuuint32_t boxI[2] = {(cuuint32_t)B.ibw, (cuuint32_t)B.w1}, boxD[2] = {(cuuint32_t)B.dbw, (cuuint32_t)B.w1};
-            const cuuint32_t boxJ[2] = {(cuuint32_t)B.jbw, (cuuint32_t)B.jr};
-            CUresult r0 = enc(&maps[l * 3 + 0], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img_plane, dim8, str8, boxI, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            CUresult r1 = enc(&maps[l * 3 + 1], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, der_plane, dim32, str32, boxD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            CUresult r2 = enc(&maps[l * 3 + 2], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img_plane, dim8, str8, boxJ, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-                ctx->last_error = "cuTensorMapEncodeTiled failed (level " + std::to_string(l) + ", codes " + std::to_string((int)r0) + " " +
-                                  std::to_string((int)r1) + " " + std::to_string((int)r2) + ")";
-                return VO_ERR_CUDA;
-            }
-        }
-        // pageable source: the runtime stages the bytes before returning, so `maps` may go out of scope
-        VO_CUDA(cudaMemcpyAsync(ctx->d_tmaps + (size_t)slots[i] * VO_MAX_LEVELS * 3, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
-        S.tmap_win = win;
-        copied = true;
     }
-    // other streams of this context (the batched entry point alternates between two) may use these descriptors next
-    if (copied) VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = &cache.emplace(key, m).first->second;
     return VO_OK;
 }
 
 template <int WIN>
-static cudaError_t launch_klt3(const KltArgs &a, dim3 grd, cudaStream_t st)
+static cudaError_t launch_klt3(const KltArgs &a, const KltBatchIds &ids, const KltMaps &maps, dim3 grd, cudaStream_t st)
 {
     grd.x = (grd.x * 4 + KLT2_WPB - 1) / KLT2_WPB;
-    k_klt3<WIN><<<grd, 32 * KLT2_WPB, KLT3_SMEM(WIN), st>>>(a);
+    k_klt3<WIN><<<grd, 32 * KLT2_WPB, KLT3_SMEM(WIN), st>>>(a, ids, maps);
     return cudaGetLastError();
 }
 template <int WIN>
-static cudaError_t launch_chain(const KltArgs &a1, const KltArgs &a2, const KltScaleArgs &sc, const KltArgs &a3, int stages, int n, cudaStream_t st)
+static cudaError_t launch_chain(const KltArgs &a1, const KltArgs &a2, const KltScaleArgs &sc, const KltArgs &a3, int stages, int n,
+                                const KltMaps &maps, cudaStream_t st)
 {
-    k_track_chain<WIN><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, KLT3_SMEM(WIN), st>>>(a1, a2, sc, a3, stages);
+    k_track_chain<WIN><<<vo_div_up(n, KLT2_WPB), 32 * KLT2_WPB, KLT3_SMEM(WIN), st>>>(a1, a2, sc, a3, stages, maps);
     return cudaGetLastError();
 }
 
@@ -836,10 +861,11 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
     if (rc) return rc;
     rc = vo_ensure_pyramids(ctx, slots1, n_pairs, eff + 1, 0);
     if (rc) return rc;
+    const KltMaps *maps = nullptr;
     if (klt3_window(win)) {
-        rc = ensure_tmaps(ctx, slots0, n_pairs, win);
-        if (rc) return rc;
-        rc = ensure_tmaps(ctx, slots1, n_pairs, win);
+        for (int i = 0; i < n_pairs; ++i)
+            VO_REQUIRE(ctx->slots[slots0[i]].w == A.w && ctx->slots[slots0[i]].h == A.h, VO_ERR_SIZE_MISMATCH, "batched pairs must share one image size");
+        rc = get_klt_maps(ctx, slots0[0], win, &maps);
         if (rc) return rc;
     }
 
@@ -847,9 +873,10 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
     for (int c0 = 0; c0 < n_pairs; c0 += VO_IDLIST_MAX) {
         const int nb = n_pairs - c0 < VO_IDLIST_MAX ? n_pairs - c0 : VO_IDLIST_MAX;
         KltArgs a;
+        KltBatchIds ids;
         a.slots = ctx->d_slots;
-        a.tmaps = ctx->d_tmaps;
-        for (int i = 0; i < nb; ++i) { a.s0.id[i] = slots0[c0 + i]; a.s1.id[i] = slots1[c0 + i]; }
+        for (int i = 0; i < nb; ++i) { ids.s0.id[i] = slots0[c0 + i]; ids.s1.id[i] = slots1[c0 + i]; }
+        a.sid0 = slots0[c0]; a.sid1 = slots1[c0];
         const size_t off = (size_t)c0 * n;
         a.pts0 = reinterpret_cast<const float2 *>(pts0_d) + off;
         a.pts1 = reinterpret_cast<float2 *>(pts1_d) + off;
@@ -873,18 +900,18 @@ int vo_klt_launch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1
         if (klt3_window(win)) {
             cudaError_t e = cudaErrorInvalidValue;
             switch (win) {
-#define KLT3_CASE(W) case W: e = launch_klt3<W>(a, grd, ctx->stream); break;
+#define KLT3_CASE(W) case W: e = launch_klt3<W>(a, ids, *maps, grd, ctx->stream); break;
                 KLT3_FOR_EACH_WIN(KLT3_CASE)
 #undef KLT3_CASE
             }
             if (e != cudaSuccess) { ctx->last_error = std::string("k_klt3: ") + cudaGetErrorString(e); return VO_ERR_CUDA; }
         }
-        else if (npx <= 6) k_klt<6><<<grd, 128, 0, ctx->stream>>>(a);
-        else if (npx <= 8) k_klt<8><<<grd, 128, 0, ctx->stream>>>(a);
-        else if (npx <= 10) k_klt<10><<<grd, 128, 0, ctx->stream>>>(a);
-        else if (npx <= 14) k_klt<14><<<grd, 128, 0, ctx->stream>>>(a);
-        else if (npx <= 20) k_klt<20><<<grd, 128, 0, ctx->stream>>>(a);
-        else k_klt<31><<<grd, 128, 0, ctx->stream>>>(a);
+        else if (npx <= 6) k_klt<6><<<grd, 128, 0, ctx->stream>>>(a, ids);
+        else if (npx <= 8) k_klt<8><<<grd, 128, 0, ctx->stream>>>(a, ids);
+        else if (npx <= 10) k_klt<10><<<grd, 128, 0, ctx->stream>>>(a, ids);
+        else if (npx <= 14) k_klt<14><<<grd, 128, 0, ctx->stream>>>(a, ids);
+        else if (npx <= 20) k_klt<20><<<grd, 128, 0, ctx->stream>>>(a, ids);
+        else k_klt<31><<<grd, 128, 0, ctx->stream>>>(a, ids);
         ctx->launches++;
     }
     VO_CUDA(cudaGetLastError());
@@ -897,8 +924,7 @@ static void fill_klt_args(vo_ctx *ctx, KltArgs &a, int s0, int s1, const float *
                           int win, int eff, int flags, const KltPost &post)
 {
     a.slots = ctx->d_slots;
-    a.tmaps = ctx->d_tmaps;
-    a.s0.id[0] = s0; a.s1.id[0] = s1;
+    a.sid0 = s0; a.sid1 = s1;
     a.pts0 = reinterpret_cast<const float2 *>(pts0_d); a.pts1 = reinterpret_cast<float2 *>(pts1_d);
     a.status = status_d; a.err = err_d; a.counters = nullptr;
     a.skip_mask = (post.skip_masked && post.mask) ? post.mask : nullptr;
@@ -909,9 +935,12 @@ static void fill_klt_args(vo_ctx *ctx, KltArgs &a, int s0, int s1, const float *
 static bool chain_unfused(int win) { return !klt3_window(win); }   // even / tiny windows: separate v1 launches
 static int launch_chain_win(vo_ctx *ctx, int win, const KltArgs &a1, const KltArgs &a2, const KltScaleArgs &sc, const KltArgs &a3, int stages, int n)
 {
+    const KltMaps *maps = nullptr;
+    int rc = get_klt_maps(ctx, a1.sid0, win, &maps);
+    if (rc) return rc;
     cudaError_t e = cudaErrorInvalidValue;
     switch (win) {
-#define KLT3_CASE(W) case W: e = launch_chain<W>(a1, a2, sc, a3, stages, n, ctx->stream); break;
+#define KLT3_CASE(W) case W: e = launch_chain<W>(a1, a2, sc, a3, stages, n, *maps, ctx->stream); break;
         KLT3_FOR_EACH_WIN(KLT3_CASE)
 #undef KLT3_CASE
     }
@@ -953,8 +982,6 @@ int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, 
     sc.slots = ctx->d_slots; sc.slot0 = slot_l0; sc.slot1 = slot_l1;
     sc.pts0 = reinterpret_cast<const float2 *>(pts_l0_d); sc.scale = scale_d;
     sc.pts_track = reinterpret_cast<float2 *>(pts_l1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
-    rc = ensure_tmaps(ctx, sl, 3, win);
-    if (rc) return rc;
     return launch_chain_win(ctx, win, a1, a1, sc, a3, (do_scale ? VO_CHAIN_SCALE : 0) | VO_CHAIN_NEXT, n);
 }
 
@@ -997,7 +1024,5 @@ int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0
     sc.slots = ctx->d_slots; sc.slot0 = slot0; sc.slot1 = slot1;
     sc.pts0 = reinterpret_cast<const float2 *>(pts0_d); sc.scale = scale_d;
     sc.pts_track = reinterpret_cast<float2 *>(pts1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
-    rc = ensure_tmaps(ctx, sl, 2, win);
-    if (rc) return rc;
     return launch_chain_win(ctx, win, a1, a2, sc, a1, VO_CHAIN_BACK | (scale_d ? VO_CHAIN_SCALE : 0), n);
 }

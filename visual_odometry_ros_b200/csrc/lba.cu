@@ -495,8 +495,12 @@ __global__ void __launch_bounds__(256) k_lba_reduce(const LbaDev d)
 // retraction.  Round 1 factorised S in shared memory: 48 steps of {pivot search, swap, scale, trailing update}, four
 // block barriers and a shared-memory read-modify-write of the whole trailing triangle per step -- 98 k cycles per LM
 // iteration (VO_LBA_TRACE), the longest stage of the local BA.  Here the matrix lives in REGISTERS: the CTA is a 16 x 16
-// thread grid, thread (ty, tx) owns the B x B block of rows ty*B.. and columns tx*B.. of the FULL symmetric matrix
-// (B = 3 for n <= 48, i.e. the reference's window of 8 optimised keyframes; B = 6 up to n = 96).  Nothing is ever
+// thread grid (8 x 8 for n <= 48, i.e. the reference's window of 8 optimised keyframes: two warps, 36 independent updates
+// per thread; 16 x 16 up to n = 96), thread (ty, tx) owns the 6 x 6 block of rows ty*6.. and columns tx*6.. of the FULL
+// symmetric matrix.  A first version with 3 x 3 blocks on 256 threads needed 367 warp-instructions per step and warp, most
+// of them predicate / select bookkeeping, on 2 warps per scheduler (profiles/r2_lba_solve_*): latency-bound, no faster than
+// the shared-memory version.  Now the column owners publish l = L(:,p) and t = D_p l with zeros for eliminated rows, so the
+// update of every element is an unconditional A -= u * v whose operands' roles are fixed per thread.  Nothing is ever
 // swapped: diagonal pivoting only chooses the ORDER of elimination, so step k eliminates original index p_k in place --
 // the pivot column is broadcast through 16*B doubles of shared memory, every thread updates its own registers
 // (A(i,j) -= L(i,p) * (D_p L(j,p)), the same products as Eigen's unblocked LDLT), two block barriers per step.  The
@@ -552,24 +556,25 @@ __device__ __forceinline__ void lba_assemble(const LbaDev &d, double *S, const i
 #undef SM
 }
 
-template <int B>
+template <int G, int B>      // G x G threads own B x B register blocks of the (G*B)-padded system
 __global__ void __launch_bounds__(LBA_THREADS, 1)
 k_lba_solve(const LbaDev d, int iter)
 {
-    constexpr int NP = SOLVE_G * B;      // padded system size
+    constexpr int NP = G * B;            // padded system size
     constexpr int LD = NP + 1;           // shared-memory row pitch (odd: conflict-free column walks)
     extern __shared__ double smem[];
     const int n = d.n6, No = d.n_opt;
-    double *S = smem;                    // [NP][LD]: assembly, later the factor L
+    double *S = smem;                    // [NP][LD]: assembly, then (column by column) the factor L
     double *rhs = S + (size_t)NP * LD;   // [NP]
     double *Aj = rhs + NP;               // [No][27]
-    __shared__ double s_diag[NP], s_col[NP], s_D[NP];
+    __shared__ double s_diag[NP], s_l[NP], s_t[NP], s_D[NP];
     __shared__ int s_idx_at[NP];         // position -> original index (the transpositions Eigen would have applied)
     __shared__ int s_piv[NP];            // step -> original index
     __shared__ int s_step[NP];           // original index -> step
     __shared__ double s_err;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int ty = tid / SOLVE_G, tx = tid % SOLVE_G;
+    const bool act = tid < G * G;        // threads of the factorisation grid (the others only keep the barriers company)
+    const int ty = tid / G, tx = tid % G;
 #define SM(i, j) S[(size_t)(i) * LD + (j)]
 #define STAMP(k) do { if (d.dbg && tid == 0) d.dbg[k] = clock64(); } while (0)
     STAMP(0);
@@ -578,103 +583,108 @@ k_lba_solve(const LbaDev d, int iter)
 
     // ---- registers <- the LOWER triangle (what Eigen::LDLT<.., Lower> reads), mirrored to a full symmetric matrix
     double A[B][B];
-    unsigned rowdead = 0, coldead = 0;   // bit a: index eliminated or padding (>= n)
-#pragma unroll
-    for (int a = 0; a < B; ++a) {
-        const int i = ty * B + a;
-        if (i >= n) rowdead |= 1u << a;
-        const int jj = tx * B + a;
-        if (jj >= n) coldead |= 1u << a;
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const int j = tx * B + b;
-            A[a][b] = (i < n && j < n) ? (i >= j ? SM(i, j) : SM(j, i)) : 0.0;
-        }
-    }
-    if (tid < NP) { s_idx_at[tid] = tid; s_step[tid] = -1; s_D[tid] = 0.0; }
-    if (ty == tx) {
-#pragma unroll
-        for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
-    }
-    __syncthreads();
-
-    for (int k = 0; k < n; ++k) {
-        // ---- pivot: largest |diagonal| among positions k .. n-1, first position on ties (every warp, redundantly)
-        int big_pos;
-        {
-            double bv = -1.0;
-            int bp = k;
-            for (int pos = k + lane; pos < n; pos += 32) {
-                const double v = fabs(s_diag[s_idx_at[pos]]);
-                if (v > bv) { bv = v; bp = pos; }
-            }
-            const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
-            const unsigned long long key = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
-            const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
-            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-            const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
-            const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-            const bool win = has && hi == mhi && (unsigned)key == mlo;
-            big_pos = __reduce_min_sync(0xffffffffu, win ? bp : 0x7fffffff);
-            if (big_pos == 0x7fffffff) big_pos = k;
-        }
-        const int p = s_idx_at[big_pos];
-        const int pb = p / B, pa = p - pb * B;
-        // ---- the owners of column p publish it
-        if (tx == pb) {
-#pragma unroll
-            for (int a = 0; a < B; ++a)
-#pragma unroll
-                for (int b = 0; b < B; ++b)
-                    if (b == pa) s_col[ty * B + a] = A[a][b];
-        }
-        __syncthreads();                     // (1) column visible; every warp has read the position table and the diagonal
-        if (tid == 0) {
-            const int q = s_idx_at[k];
-            s_idx_at[k] = p; s_idx_at[big_pos] = q;
-            s_piv[k] = p; s_step[p] = k; s_D[p] = s_col[p];
-        }
-        const double akk = s_col[p];
-        // L(:,p) = A(:,p) * (1 / D_p) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp), temp = D_p L(:,p)
-        const bool scale = (k < n - 1) && fabs(akk) > 0.0;
-        const double rk = scale ? __drcp_rn(akk) : 0.0;
-        double li[B], ti[B], lj[B], tj[B];
-#pragma unroll
-        for (int a = 0; a < B; ++a) {
-            double l = s_col[ty * B + a];
-            if (scale) l *= rk;
-            li[a] = l; ti[a] = akk * l;
-            double m = s_col[tx * B + a];
-            if (scale) m *= rk;
-            lj[a] = m; tj[a] = akk * m;
-        }
-        if (ty == pb) rowdead |= 1u << pa;
-        const unsigned colalive_before = ~coldead;
-        if (tx == pb) coldead |= 1u << pa;
+    unsigned rowdead = 0;                // bit a: row index eliminated or padding (>= n)
+    if (act) {
 #pragma unroll
         for (int a = 0; a < B; ++a) {
             const int i = ty * B + a;
+            if (i >= n) rowdead |= 1u << a;
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const int j = tx * B + b;
-                if (!((rowdead >> a) & 1u) && !((coldead >> b) & 1u))
-                    A[a][b] -= (i >= j) ? li[a] * tj[b] : lj[b] * ti[a];          // the trailing update, both triangles
-                else if (tx == pb && b == pa && !((rowdead >> a) & 1u) && ((colalive_before >> b) & 1u))
-                    A[a][b] = li[a];                                            // column p now holds L(:,p)
+                A[a][b] = (i < n && j < n) ? (i >= j ? SM(i, j) : SM(j, i)) : 0.0;
             }
         }
-        if (ty == tx) {
-#pragma unroll
-            for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
-        }
-        __syncthreads();                     // (2) diagonal + position table updated; s_col may be overwritten
     }
-    // ---- park the factor in shared memory (column p_k of L sits in column p_k of the matrix, rows eliminated later)
+    if (tid < NP) { s_idx_at[tid] = tid; s_step[tid] = -1; s_D[tid] = 0.0; }
+    __syncthreads();                     // every register copy is made before the factor overwrites S
+    if (act && ty == tx) {
 #pragma unroll
-    for (int a = 0; a < B; ++a)
-#pragma unroll
-        for (int b = 0; b < B; ++b) SM(ty * B + a, tx * B + b) = A[a][b];
+        for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
+    }
+    // Which of {l, t = D l} a thread multiplies is fixed by its block position: element (i, j) takes L(i,p) * (D_p L(j,p)) with
+    // i >= j (the lower-triangle product) and its mirror image otherwise; inside a diagonal block the split is a >= b.
+    const double *pUA = (ty >= tx) ? s_l : s_t, *pVA = (ty >= tx) ? s_t : s_l;      // elements with a >= b
+    const double *pUB = (ty > tx) ? s_l : s_t, *pVB = (ty > tx) ? s_t : s_l;        // elements with a <  b
     __syncthreads();
+
+    long long t_piv = 0, t_pub = 0, t_upd = 0, t_last = d.dbg ? clock64() : 0;      // VO_LBA_TRACE: where a step's cycles go
+#define PHASE(acc) do { if (d.dbg && tid == 0) { const long long t_now = clock64(); acc += t_now - t_last; t_last = t_now; } } while (0)
+    for (int k = 0; k < n; ++k) {
+        if (act) {
+            // ---- pivot: largest |diagonal| among positions k .. n-1, first position on ties (every active warp, redundantly)
+            int big_pos;
+            {
+                double bv = -1.0;
+                int bp = k;
+                for (int pos = k + lane; pos < n; pos += 32) {
+                    const double v = fabs(s_diag[s_idx_at[pos]]);
+                    if (v > bv) { bv = v; bp = pos; }
+                }
+                const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
+                const unsigned long long key = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
+                const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
+                const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
+                const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+                const bool win = has && hi == mhi && (unsigned)key == mlo;
+                big_pos = __reduce_min_sync(0xffffffffu, win ? bp : 0x7fffffff);
+                if (big_pos == 0x7fffffff) big_pos = k;
+            }
+            const int p = s_idx_at[big_pos];
+            const int pb = p / B, pa = p - pb * B;
+            // ---- the owners of column p publish L(:,p), D_p L(:,p) and park the factor column
+            if (tx == pb) {
+                const double akk = s_diag[p];
+                // L(:,p) = A(:,p) * (1 / D_p) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp)
+                const bool scale = (k < n - 1) && fabs(akk) > 0.0;
+                const double rk = scale ? __drcp_rn(akk) : 0.0;
+#pragma unroll
+                for (int a = 0; a < B; ++a) {
+                    const int i = ty * B + a;
+                    double c = A[a][0];
+#pragma unroll
+                    for (int b = 1; b < B; ++b) c = (b == pa) ? A[a][b] : c;
+                    const bool alive = !((rowdead >> a) & 1u) && i != p;
+                    const double l = scale ? c * rk : c;
+                    s_l[i] = alive ? l : 0.0;             // eliminated rows take no further update
+                    s_t[i] = alive ? akk * l : 0.0;
+                    if (alive) SM(i, p) = l;
+                }
+                if (ty == pb) s_D[p] = akk;
+            }
+            if (ty == pb) rowdead |= 1u << pa;    // every thread of that block row: it may own a later pivot column
+            if (tid == 0) s_piv[k] = p;
+            if (tid == 1 % (G * G)) s_step[p] = k;
+            PHASE(t_piv);
+            __syncthreads();                 // (1) column visible; every warp has read the position table and the diagonal
+            PHASE(t_pub);
+            if (tid == 0) {
+                const int q = s_idx_at[k];
+                s_idx_at[k] = p; s_idx_at[big_pos] = q;
+            }
+            double uA[B], vA[B], uB[B], vB[B];
+#pragma unroll
+            for (int a = 0; a < B; ++a) {
+                uA[a] = pUA[ty * B + a]; uB[a] = pUB[ty * B + a];
+                vA[a] = pVA[tx * B + a]; vB[a] = pVB[tx * B + a];
+            }
+#pragma unroll
+            for (int a = 0; a < B; ++a)
+#pragma unroll
+                for (int b = 0; b < B; ++b) A[a][b] -= (a >= b) ? uA[a] * vA[b] : uB[a] * vB[b];   // the trailing update, both triangles
+            if (ty == tx) {
+#pragma unroll
+                for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
+            }
+        } else {
+            __syncthreads();                 // (1)
+        }
+        __syncthreads();                     // (2) diagonal + position table updated; s_l / s_t may be overwritten
+        PHASE(t_upd);
+    }
+    if (d.dbg && tid == 0) { d.dbg[5] = t_piv; d.dbg[6] = t_pub; d.dbg[7] = t_upd; }
+#undef PHASE
     STAMP(2);
     const double tol = 1.0 / 1.7976931348623157e308;
     if (tid < 32) {
@@ -905,8 +915,8 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     VO_REQUIRE(TL >= LBA_WARPS, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
     const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
     const size_t smem_build = fixed + per_lm * TL;
-    const int solve_B = n6 <= 48 ? 3 : 6;      // k_lba_solve<B>: 16 x 16 threads own B x B register blocks
-    const int solve_NP = SOLVE_G * solve_B;
+    const int solve_G = n6 <= 48 ? 8 : 16;     // k_lba_solve<G, 6>: G x G threads own 6 x 6 register blocks
+    const int solve_NP = solve_G * 6;
     const size_t smem_solve = ((size_t)solve_NP * (solve_NP + 1) + solve_NP + (size_t)No * LBA_NA) * 8;
 
     // device scratch (one allocation, grow-only)
@@ -973,10 +983,10 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
         std::call_once(once, [&]() {
             const size_t max_solve = ((size_t)(SOLVE_G * 6) * (SOLVE_G * 6 + 1) + SOLVE_G * 6 + (size_t)LBA_MAX_OPT * LBA_NA) * 8;
             cudaError_t e = cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve<16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
             cudaFuncSetAttribute(k_lba_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_lba_solve<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_lba_solve<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_solve<8, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_solve<16, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_update_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr_err = e;
         });
@@ -994,8 +1004,8 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
             if (nrc != 0) { ctx->last_error = std::string("ncclAllReduce: ") + (nccl_api().GetErrorString ? nccl_api().GetErrorString(nrc) : "error"); return VO_ERR_CUDA; }
         }
         if (trace) cudaEventRecord(evs[2 * it + 1], ctx->stream);
-        if (solve_B == 3) k_lba_solve<3><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
-        else k_lba_solve<6><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
+        if (solve_G == 8) k_lba_solve<8, 6><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
+        else k_lba_solve<16, 6><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
         if (trace) cudaEventRecord(evs[2 * it + 2], ctx->stream);
         ctx->launches += 3;
     }
@@ -1012,7 +1022,8 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
         cudaMemcpy(st2, dv + o_dbg, 104, cudaMemcpyDeviceToHost);
         memcpy(st, st2, 40);
 
-        fprintf(stderr, "k_lba_solve cycles: assemble %lld, ldlt+fwd %lld, diag+backward %lld, retract %lld\n", st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3]);
+        fprintf(stderr, "k_lba_solve cycles: assemble %lld, ldlt %lld (pivot %lld, barrier-1 %lld, update+barrier-2 %lld), solves %lld, retract %lld\n",
+                st[1] - st[0], st[2] - st[1], st2[5], st2[6], st2[7], st[3] - st[2], st[4] - st[3]);
     }
     if (M > 0) { k_lba_update_points<<<vo_div_up(M, 256), 256, 0, ctx->stream>>>(d); ctx->launches++; }
     VO_CUDA(cudaGetLastError());

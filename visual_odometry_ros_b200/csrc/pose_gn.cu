@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include <cstring>
+#include <mutex>
 
 #define POSE_MAX_ITER 100
 #define NACC 28   // 21 (upper JtWJ) + 6 (mJtWr) + 1 (err)
@@ -547,29 +548,47 @@ k_pose_gn_cluster(const PoseArgs a)
 // chain latency (4 cycles per row) is the cost: about 16 us per iteration at N = 2000.  Chunks are double-buffered so
 // the producers stay ahead of the consumer.  Structurally zero entries contribute a*0 = +-0, which leaves an FP32 sum
 // unchanged, exactly like the `+= JtJ_tmp` of the zero-filled temporary in the reference.
-// Row record = 16 floats: [0..5] Jt, [6..11] w*Jt, [12] -(w*r), [13] e, [14] 1, [15] 0; its four 16-byte quads are
-// XOR-swizzled with (point & 3) so the producers' 128-bit stores of neighbouring points spread over the banks.
-#define STRICT_PTS 64                  // points per chunk = 2 producer warps x 32 lanes
-#define STRICT_THREADS 96              // warp 0 = consumer, warps 1..2 = producers
+// Shared-memory layout: rows are stored in BLOCKS of four (= one stereo point, two mono points), field-major: a block is
+// 16 fields x 16 bytes, field f = {f of row 0, row 1, row 2, row 3}; fields [0..5] Jt, [6..11] w*Jt, [12] -(w*r), [13] e,
+// [14] 1, [15] 0.  A consumer lane therefore fetches its two operands for FOUR rows with two 128-bit loads (the first
+// version used two 32-bit loads per row and was bound by the shared-memory instruction rate, not by the add chain:
+// profiles/r2_strict_*).  Blocks are 17 slots (272 bytes) apart, so the producers' 128-bit stores of eight neighbouring
+// points fall on eight different bank groups while the consumer's field offsets stay compile-time immediates.
+#define STRICT_PTS 128                 // points per chunk = 4 producer warps x 32 lanes
+#define STRICT_THREADS 160             // warp 0 = consumer, warps 1..4 = producers
+#define STRICT_BLK 68                  // floats per block of four rows (16 fields x 4 + one slot of padding)
+#define STRICT_SMEM(RPP) (2 * (STRICT_PTS / (4 / (RPP)) + 2) * STRICT_BLK * 4)     // two buffers, each padded by two blocks (prefetch overrun)
 
 template <int RPP>
 struct RecSink {
-    float *rec;      // first record of this lane's point
-    int swz;         // point & 3
+    float Jt_[RPP][6], wJ_[RPP][6], nwr_[RPP], e_[RPP];
     int k;           // next row
     template <int ZERO>
     __device__ __forceinline__ void row(const float *Jt, float w, float r, bool weighted, float e)
     {
-        float wJ[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) wJ[i] = weighted ? w * Jt[i] : Jt[i];
-        const float wr = weighted ? w * r : r;
-        float4 *q = reinterpret_cast<float4 *>(rec + k * 16);
-        q[0 ^ swz] = make_float4(Jt[0], Jt[1], Jt[2], Jt[3]);
-        q[1 ^ swz] = make_float4(Jt[4], Jt[5], wJ[0], wJ[1]);
-        q[2 ^ swz] = make_float4(wJ[2], wJ[3], wJ[4], wJ[5]);
-        q[3 ^ swz] = make_float4(-wr, e, 1.0f, 0.f);
+        for (int q = 0; q < RPP; ++q)
+            if (q == k) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { Jt_[q][i] = Jt[i]; wJ_[q][i] = weighted ? w * Jt[i] : Jt[i]; }
+                nwr_[q] = -(weighted ? w * r : r);
+                e_[q] = e;
+            }
         ++k;
+    }
+    // block: this point's block; half = which half of the block (mono)
+    __device__ __forceinline__ void store(float *block, int half) const
+    {
+#pragma unroll
+        for (int f = 0; f < 16; ++f) {
+            float v[RPP];
+#pragma unroll
+            for (int q = 0; q < RPP; ++q)
+                v[q] = f < 6 ? Jt_[q][f] : (f < 12 ? wJ_[q][f - 6] : (f == 12 ? nwr_[q] : (f == 13 ? e_[q] : (f == 14 ? 1.0f : 0.f))));
+            float *dst = block + 4 * f;
+            if (RPP == 4) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[RPP - 1]);
+            else *reinterpret_cast<float2 *>(dst + 2 * half) = make_float2(v[0], v[RPP - 1]);
+        }
     }
 };
 
@@ -577,7 +596,10 @@ template <int RPP>   // rows per point: 2 mono, 4 stereo
 __global__ void __launch_bounds__(STRICT_THREADS)
 k_pose_gn_strict(const PoseArgs a)
 {
-    __shared__ __align__(16) float s_rec[2][STRICT_PTS * RPP * 16];
+    constexpr int PPB = 4 / RPP;                                   // points per block of four rows
+    constexpr int BLOCKS = STRICT_PTS / PPB;                       // blocks per chunk
+    extern __shared__ __align__(16) float s_rec_dyn[];             // [2][(BLOCKS + 2) * STRICT_BLK]
+    float (*s_rec)[(BLOCKS + 2) * STRICT_BLK] = reinterpret_cast<float (*)[(BLOCKS + 2) * STRICT_BLK]>(s_rec_dyn);
     __shared__ double s_red[NACC];
     __shared__ float s_T10[16];
     __shared__ int s_stop;
@@ -604,9 +626,8 @@ k_pose_gn_strict(const PoseArgs a)
     }
     __syncthreads();
 
-    // consumer lane -> the two record words it multiplies: H(i,j) = sum (w*Jt[i]) * Jt[j]; g(i) = sum (-(w*r)) * Jt[i];
-    // err = sum e * 1
-    int wa = 14, wb = 14;
+    // consumer lane -> the two fields it multiplies: H(i,j) = sum (w*Jt[i]) * Jt[j]; g(i) = sum (-(w*r)) * Jt[i]; err = sum e * 1
+    int wa = 15, wb = 15;
     if (lane < 21) {
         int idx = 0;
         for (int i = 0; i < 6; ++i)
@@ -614,12 +635,6 @@ k_pose_gn_strict(const PoseArgs a)
                 if (idx == lane) { wa = 6 + i; wb = j; }
     } else if (lane < 27) { wa = 12; wb = lane - 21; }
     else if (lane == 27) { wa = 13; wb = 14; }
-    int offa[4], offb[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        offa[s] = ((((wa >> 2) ^ s) << 2) | (wa & 3));
-        offb[s] = ((((wb >> 2) ^ s) << 2) | (wb & 3));
-    }
 
     const int n_chunks = (n + STRICT_PTS - 1) / STRICT_PTS;
     int iter = 0;
@@ -631,36 +646,41 @@ k_pose_gn_strict(const PoseArgs a)
         for (int c = 0; c <= n_chunks; ++c) {
             if (wid > 0) {
                 if (c < n_chunks) {
-                    // producer: point (c*64 + p), p = lane of producer warp 1 / 2
+                    // producer: point (c * STRICT_PTS + p), p = lane of producer warp 1 .. 4
                     const int p = (wid - 1) * 32 + lane;
                     const int i = c * STRICT_PTS + p;
-                    float *rec = &s_rec[c & 1][p * RPP * 16];
+                    const int blk = p / PPB;
+                    float *block = &s_rec[c & 1][blk * STRICT_BLK];
                     if (i < n) {
-                        RecSink<RPP> sink{rec, p & 3, 0};
+                        RecSink<RPP> sink;
+                        sink.k = 0;
                         pose_point(a, X, pl, pr, mask, i, T10, sink);
-                    } else if (i < ((n + 3) & ~3)) {
-                        // pad the last group of four points with all-zero rows (+0 leaves every sum unchanged)
-                        float4 *q = reinterpret_cast<float4 *>(rec);
+                        sink.store(block, p % PPB);
+                    } else if (PPB == 2 && i == n && (n & 1)) {
+                        // mono, odd point count: the second half of the last block is all-zero rows (+0 leaves every sum unchanged)
 #pragma unroll
-                        for (int k = 0; k < RPP * 4; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int f = 0; f < 16; ++f) *reinterpret_cast<float2 *>(block + 4 * f + 2) = make_float2(0.f, 0.f);
                     }
                 }
             } else if (c > 0) {
-                // consumer: chunk c-1, groups of four points (= 4*RPP rows, swizzle pattern known at compile time)
+                // consumer: chunk c-1, one block (four rows) per step, software-pipelined two blocks deep: the adds of block b
+                // run while the products of block b+1 are formed and the operands of block b+2 are loaded.
                 const int cc = c - 1;
                 const int npts = min(STRICT_PTS, n - cc * STRICT_PTS);
-                const int groups = (npts + 3) >> 2;
-                const float *buf = s_rec[cc & 1];
-                for (int g = 0; g < groups; ++g) {
-                    const float *gb = buf + g * (4 * RPP * 16);
-                    float va[4 * RPP], vb[4 * RPP];
-#pragma unroll
-                    for (int r = 0; r < 4 * RPP; ++r) {
-                        va[r] = gb[r * 16 + offa[r / RPP]];
-                        vb[r] = gb[r * 16 + offb[r / RPP]];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 4 * RPP; ++r) acc = acc + va[r] * vb[r];
+                const int blocks = (npts + PPB - 1) / PPB;
+                // (blocks past the chunk's end are read -- the buffers are padded -- but their products are never added)
+                const float *qa = s_rec[cc & 1] + 4 * wa, *qb = s_rec[cc & 1] + 4 * wb;
+                float4 pa = *reinterpret_cast<const float4 *>(qa), pb = *reinterpret_cast<const float4 *>(qb);
+                float4 pr0 = make_float4(pa.x * pb.x, pa.y * pb.y, pa.z * pb.z, pa.w * pb.w);
+                float4 la = *reinterpret_cast<const float4 *>(qa + STRICT_BLK), lb = *reinterpret_cast<const float4 *>(qb + STRICT_BLK);
+                qa += 2 * STRICT_BLK; qb += 2 * STRICT_BLK;
+#pragma unroll 4
+                for (int b = 0; b < blocks; ++b) {
+                    const float4 na = *reinterpret_cast<const float4 *>(qa), nb = *reinterpret_cast<const float4 *>(qb);
+                    qa += STRICT_BLK; qb += STRICT_BLK;
+                    acc = acc + pr0.x; acc = acc + pr0.y; acc = acc + pr0.z; acc = acc + pr0.w;
+                    pr0 = make_float4(la.x * lb.x, la.y * lb.y, la.z * lb.z, la.w * lb.w);
+                    la = na; lb = nb;
                 }
             }
             __syncthreads();
@@ -716,8 +736,15 @@ int vo_pose_launch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_sin
     ctx->launches++;
     if (flags & VO_POSE_STRICT) {
         // sequential FP32 sums in point order: one CTA per problem whatever its size (the consumer chain is the cost)
-        if (mono) k_pose_gn_strict<2><<<n_prob, STRICT_THREADS, 0, ctx->stream>>>(a);
-        else k_pose_gn_strict<4><<<n_prob, STRICT_THREADS, 0, ctx->stream>>>(a);
+        {   // 32 / 64 KB of dynamic shared memory (double-buffered row records); the attribute is process-wide: set once
+            static std::once_flag once;
+            std::call_once(once, [] {
+                cudaFuncSetAttribute(k_pose_gn_strict<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2));
+                cudaFuncSetAttribute(k_pose_gn_strict<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4));
+            });
+        }
+        if (mono) k_pose_gn_strict<2><<<n_prob, STRICT_THREADS, STRICT_SMEM(2), ctx->stream>>>(a);
+        else k_pose_gn_strict<4><<<n_prob, STRICT_THREADS, STRICT_SMEM(4), ctx->stream>>>(a);
         VO_CUDA(cudaGetLastError());
         return VO_OK;
     }

@@ -545,8 +545,7 @@ int vo_ensure_pyramids(vo_ctx *ctx, const int *slot_ids, int n, int n_levels, in
     }
     if (todo.empty()) return VO_OK;
     // ---- fused path: every stale slot is built from its level-0 pixels in ONE launch per <= 64 images
-    static const bool no_fused = getenv("VO_PYR_UNFUSED") != nullptr;      // A/B switch for profiling
-    bool all_fresh = !no_fused && w >= VO_PAD + 2 && h >= VO_PAD + 2;
+    bool all_fresh = w >= VO_PAD + 2 && h >= VO_PAD + 2;
     for (int s : todo) all_fresh &= ctx->slots[s].levels_built <= 1 && ctx->slots[s].deriv_built == 0;
     if (all_fresh) {
         // fused levels: at most 4, and only levels at least VO_PAD + 2 px wide/high (single-bounce ring reflection)

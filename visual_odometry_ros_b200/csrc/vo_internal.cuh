@@ -45,7 +45,6 @@ struct Slot {
     int deriv_built = 0;      // derivative levels valid
     bool border0 = false;     // level-0 border filled
     bool raw_pending = false; // pixels sit in the raw staging area, not yet ingested into level 0
-    int tmap_win = 0;         // LK window size the slot's device tensor maps were encoded for (0 = none / stale)
 };
 
 struct vo_ctx {
@@ -59,7 +58,9 @@ struct vo_ctx {
     int max_w = 0, max_h = 0, n_slots = 0, max_feat = 0;
     std::vector<Slot> slots;
     SlotDesc *d_slots = nullptr;   // device mirror of all slot descriptors
-    CUtensorMap *d_tmaps = nullptr;   // [n_slots][VO_MAX_LEVELS][3] TMA descriptors of the pyramid planes (klt.cu)
+    uint8_t *slot_pool = nullptr;  // one allocation: slot s lives at slot_pool + s * slot_stride
+    size_t slot_stride = 0;
+    void *klt_maps = nullptr;      // cache of TMA descriptor sets keyed by (w, h, window) (klt.cu)
     uint8_t *raw_base = nullptr;   // n_slots x raw_stride bytes: contiguous upload staging
     size_t raw_stride = 0;
     int max_levels = 0;            // levels allocated per slot
@@ -123,6 +124,7 @@ int vo_slot_prepare(vo_ctx *ctx, int slot, int w, int h);
 int vo_ensure_pyramids(vo_ctx *ctx, const int *slots, int n, int n_levels, int with_deriv);
 
 // klt.cu
+void vo_klt_maps_free(vo_ctx *ctx);
 struct KltPost {           // fused FeatureTracker post-filter (feature_tracker.cpp:33-34 etc.)
     int mode;              // 0 none, 1 track, 2 with_prior, 3 bidir-forward (no mask), 4 bidir-backward
     float thres_err;
