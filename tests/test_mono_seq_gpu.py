@@ -138,7 +138,9 @@ def test_mono_vo_deterministic_and_yaml(seq, tmp_path):
                  "feature_extractor.n_bins_u: 32\nfeature_extractor.n_bins_v: 12\nmotion_estimator.thres_5p_error: 1.0\n"
                  "map_update.thres_parallax: 1.0\nkeyframe_update.thres_translation: 2.0\n")
     c = mvo.MonoVO(yaml_path=str(y))
-    d = _make(seed=0, detector="orb", thres_fastscore=20)      # the yaml constructor runs the reference's extractor (default FAST 20)
+    # the yaml constructor is the drop-in path: the reference's extractor (default FAST 20) and the reference's arithmetic
+    # in the pose-only GN (strict-order sums)
+    d = _make(seed=0, detector="orb", thres_fastscore=20, pose_strict=True)
     for k in range(5):
         c.trackImage(L[k], 0.1 * k)
         d.trackImage(L[k], 0.1 * k)

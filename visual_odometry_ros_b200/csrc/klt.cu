@@ -19,6 +19,7 @@
 
 #include <cfloat>
 #include <map>
+#include <mutex>
 #include <cstdlib>
 
 #define W_BITS 14
@@ -389,7 +390,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
                  ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-// 8-bit sample stream of one run: E holds bytes e0.., O the same shifted by one byte.
+// 8-bit sample stream of one run: E holds bytes e0.., O the same shifted by one byte.  A run of RL pixels needs bytes
+// 0 .. RL: with RL <= 7 the third word only feeds the funnel shift of E[1] and O[1] is a plain shift.
+template <int RL>
 __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_t E[3], uint32_t O[3])
 {
     const uint32_t *p = row + (byte0 >> 2);
@@ -397,10 +400,14 @@ __device__ __forceinline__ void load_run(const uint32_t *row, int byte0, uint32_
     const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
     E[0] = __funnelshift_r(w0, w1, sh);
     E[1] = __funnelshift_r(w1, w2, sh);
-    E[2] = w2 >> sh;
     O[0] = __funnelshift_r(E[0], E[1], 8);
-    O[1] = __funnelshift_r(E[1], E[2], 8);
-    O[2] = E[2] >> 8;
+    if (RL <= 7) {
+        E[2] = 0; O[1] = E[1] >> 8; O[2] = 0;
+    } else {
+        E[2] = w2 >> sh;
+        O[1] = __funnelshift_r(E[1], E[2], 8);
+        O[2] = E[2] >> 8;
+    }
 }
 
 // fixed-point bilinear sample of pixel k of a run, accumulated onto `acc`:
@@ -525,8 +532,8 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const KltMaps &ma
             for (int q = 0; q < C::RPL; ++q) {
                 uint32_t EA[3], OA[3], EB[3], OB[3];
                 const int r = run_row[q];
-                load_run(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
-                load_run(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
+                load_run<C::RL>(Ibuf + r * C::IPW, offI + run_x0[q], EA, OA);
+                load_run<C::RL>(Ibuf + (r + 1) * C::IPW, offI + run_x0[q], EB, OB);
                 const uint32_t *d0 = Dbuf + r * C::DPW + offD + run_x0[q];
                 const uint32_t *d1 = d0 + C::DPW;
                 uint32_t da = d0[0], db = d1[0];
@@ -575,7 +582,9 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const KltMaps &ma
             __syncwarp();
             continue;
         }
-        D = __fdiv_rn(1.f, D);
+        // b = sum * 2^-20 feeds only delta = (A12 b2 - A22 b1) * D: a power-of-two factor commutes with every rounding on the way
+        // (no under/overflow at these magnitudes), so it is folded into D once per level
+        D = __fmul_rn(__fdiv_rn(1.f, D), FLT_SCALE);
 
         float pdx = 0.f, pdy = 0.f;
         int j = 0;
@@ -603,8 +612,8 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const KltMaps &ma
             for (int q = 0; q < C::RPL; ++q) {
                 uint32_t EA[3], OA[3], EB[3], OB[3];
                 const uint32_t *rowA = Jbuf + (offy + run_row[q]) * C::JPW;
-                load_run(rowA, offx + run_x0[q], EA, OA);
-                load_run(rowA + C::JPW, offx + run_x0[q], EB, OB);
+                load_run<C::RL>(rowA, offx + run_x0[q], EA, OA);
+                load_run<C::RL>(rowA + C::JPW, offx + run_x0[q], EB, OB);
                 int b1q = 0, b2q = 0;
 #pragma unroll
                 for (int k = 0; k < C::RL; ++k) {
@@ -614,8 +623,8 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const KltMaps &ma
                 }
                 sb1 += run_ok[q] ? b1q : 0; sb2 += run_ok[q] ? b2q : 0;
             }
-            const float b1 = __fmul_rn(warp_sum_exact_f(sb1), FLT_SCALE);
-            const float b2 = __fmul_rn(warp_sum_exact_f(sb2), FLT_SCALE);
+            const float b1 = warp_sum_exact_f(sb1);        // x 2^20 (the scale lives in D)
+            const float b2 = warp_sum_exact_f(sb2);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nextx = __fadd_rn(nextx, dx); nexty = __fadd_rn(nexty, dy);
@@ -655,8 +664,8 @@ __device__ __forceinline__ void klt3_feature(const KltArgs &a, const KltMaps &ma
                 for (int q = 0; q < C::RPL; ++q) {
                     uint32_t EA[3], OA[3], EB[3], OB[3];
                     const uint32_t *rowA = Jbuf + (offy + run_row[q]) * C::JPW;
-                    load_run(rowA, offx + run_x0[q], EA, OA);
-                    load_run(rowA + C::JPW, offx + run_x0[q], EB, OB);
+                    load_run<C::RL>(rowA, offx + run_x0[q], EA, OA);
+                    load_run<C::RL>(rowA + C::JPW, offx + run_x0[q], EB, OB);
                     int sq = 0;
 #pragma unroll
                     for (int k = 0; k < C::RL; ++k) {

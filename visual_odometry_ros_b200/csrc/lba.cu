@@ -610,17 +610,39 @@ k_lba_solve(const LbaDev d, int iter)
 
     long long t_piv = 0, t_pub = 0, t_upd = 0, t_last = d.dbg ? clock64() : 0;      // VO_LBA_TRACE: where a step's cycles go
 #define PHASE(acc) do { if (d.dbg && tid == 0) { const long long t_now = clock64(); acc += t_now - t_last; t_last = t_now; } } while (0)
+    // Software pipeline over the steps: once the new DIAGONAL of step k is published (barrier 2) the pivot of step k+1 can be
+    // searched, so the rest of step k's trailing update (36 independent multiply-subtracts per thread) is issued between the
+    // search's shared-memory loads and its warp reductions -- it runs in the shadow of the search's latency.
+    double uA[B], vA[B], uB[B], vB[B];
+#pragma unroll
+    for (int a = 0; a < B; ++a) { uA[a] = 0.0; vA[a] = 0.0; uB[a] = 0.0; vB[a] = 0.0; }     // step -1: nothing to subtract
+    constexpr int NPS = (NP + 31) / 32;          // pivot-search positions per lane
     for (int k = 0; k < n; ++k) {
         if (act) {
-            // ---- pivot: largest |diagonal| among positions k .. n-1, first position on ties (every active warp, redundantly)
+            // ---- pivot of step k: largest |diagonal| among positions k .. n-1, first position on ties (every active warp,
+            // redundantly); loads first ...
+            double dv[NPS];
+#pragma unroll
+            for (int q = 0; q < NPS; ++q) {
+                const int pos = k + lane + 32 * q;
+                dv[q] = pos < n ? fabs(s_diag[s_idx_at[pos]]) : -1.0;
+            }
+            // ... the rest of step k-1's trailing update (everything but the diagonal entries of the diagonal blocks) ...
+#pragma unroll
+            for (int a = 0; a < B; ++a)
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const double prod = (a >= b) ? uA[a] * vA[b] : uB[a] * vB[b];
+                    if (a != b || ty != tx) A[a][b] -= prod;
+                }
+            // ... then the reductions
             int big_pos;
             {
                 double bv = -1.0;
                 int bp = k;
-                for (int pos = k + lane; pos < n; pos += 32) {
-                    const double v = fabs(s_diag[s_idx_at[pos]]);
-                    if (v > bv) { bv = v; bp = pos; }
-                }
+#pragma unroll
+                for (int q = 0; q < NPS; ++q)
+                    if (dv[q] > bv) { bv = dv[q]; bp = k + lane + 32 * q; }
                 const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
                 const unsigned long long key = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
                 const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
@@ -663,19 +685,15 @@ k_lba_solve(const LbaDev d, int iter)
                 const int q = s_idx_at[k];
                 s_idx_at[k] = p; s_idx_at[big_pos] = q;
             }
-            double uA[B], vA[B], uB[B], vB[B];
 #pragma unroll
             for (int a = 0; a < B; ++a) {
                 uA[a] = pUA[ty * B + a]; uB[a] = pUB[ty * B + a];
                 vA[a] = pVA[tx * B + a]; vB[a] = pVB[tx * B + a];
             }
-#pragma unroll
-            for (int a = 0; a < B; ++a)
-#pragma unroll
-                for (int b = 0; b < B; ++b) A[a][b] -= (a >= b) ? uA[a] * vA[b] : uB[a] * vB[b];   // the trailing update, both triangles
+            // the new diagonal first: it is all the next pivot search needs
             if (ty == tx) {
 #pragma unroll
-                for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
+                for (int a = 0; a < B; ++a) { A[a][a] -= uA[a] * vA[a]; s_diag[ty * B + a] = A[a][a]; }
             }
         } else {
             __syncthreads();                 // (1)
@@ -688,23 +706,56 @@ k_lba_solve(const LbaDev d, int iter)
     STAMP(2);
     const double tol = 1.0 / 1.7976931348623157e308;
     if (tid < 32) {
+        // The triangular solves on one warp with the right-hand side in REGISTERS (lane owns indices lane, lane + 32, ...): a
+        // step is one shuffle of the finished component plus one multiply-subtract per owned index; the factor entries and
+        // the pivot list are plain shared-memory loads off the dependent chain (the first version kept the right-hand side
+        // in shared memory: 400 cycles of load -> multiply -> store -> barrier per step, 38 k cycles per LM iteration).
+        constexpr int NPL = (NP + 31) / 32;
+        double r[NPL];
+        int st[NPL];
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int i = lane + 32 * q;
+            r[q] = i < n ? rhs[i] : 0.0;
+            st[q] = i < n ? s_step[i] : -1;
+        }
         // forward: for k ascending, y(p_k) is final; every index eliminated later takes its update
+#pragma unroll 4
         for (int k = 0; k < n; ++k) {
             const int p = s_piv[k];
-            const double yk = rhs[p];
-            for (int i = tid; i < n; i += 32)
-                if (s_step[i] > k) rhs[i] -= SM(i, p) * yk;
-            __syncwarp();
+            double v = r[0];
+#pragma unroll
+            for (int q = 1; q < NPL; ++q) v = (p >> 5) == q ? r[q] : v;
+            const double yk = __shfl_sync(0xffffffffu, v, p & 31);
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                const int i = lane + 32 * q;
+                if (st[q] > k) r[q] -= SM(i, p) * yk;
+            }
         }
-        for (int i = tid; i < n; i += 32) rhs[i] = fabs(s_D[i]) > tol ? rhs[i] / s_D[i] : 0.0;
-        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int i = lane + 32 * q;
+            if (i < n) { const double D = s_D[i]; r[q] = fabs(D) > tol ? r[q] / D : 0.0; }
+        }
         // backward: L^T x = y, column-oriented: once x(p_k) is final, every index eliminated EARLIER takes its update
+#pragma unroll 4
         for (int k = n - 1; k > 0; --k) {
             const int p = s_piv[k];
-            const double xk = rhs[p];
-            for (int i = tid; i < n; i += 32)
-                if (s_step[i] < k) rhs[i] -= SM(p, i) * xk;
-            __syncwarp();
+            double v = r[0];
+#pragma unroll
+            for (int q = 1; q < NPL; ++q) v = (p >> 5) == q ? r[q] : v;
+            const double xk = __shfl_sync(0xffffffffu, v, p & 31);
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                const int i = lane + 32 * q;
+                if (st[q] >= 0 && st[q] < k) r[q] -= SM(p, i) * xk;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int i = lane + 32 * q;
+            if (i < n) rhs[i] = r[q];
         }
     }
     __syncthreads();

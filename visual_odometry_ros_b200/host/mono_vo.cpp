@@ -51,6 +51,7 @@ MonoVO::MonoVO(std::string mode, std::string directory_intrinsic)
     p_.n_bins_v = (int)num("feature_extractor.n_bins_v", p_.n_bins_v);
     p_.detector = VO_DETECTOR_ORB;                                    // the reference's extractor
     p_.thres_fastscore = (int)num("feature_extractor.thres_fastscore", p_.thres_fastscore);   // initParams(..., int THRES_FAST, ...)
+    p_.pose_strict = (int)num("motion_estimator.pose_strict", 1);     // yaml construction = drop-in use: the reference's arithmetic
     p_.thres_5p_error = (float)num("motion_estimator.thres_5p_error", p_.thres_5p_error);
     p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
     p_.thres_overlap_ratio = (float)num("keyframe_update.thres_overlap_ratio", p_.thres_overlap_ratio);
@@ -65,6 +66,8 @@ void MonoVO::init()
     const int nb = std::max(1, p_.n_bins_u * p_.n_bins_v);
     const int rc = vo_ctx_create(p_.device, p_.width, p_.height, 2, std::max(4 * nb + 4096, 262144), nullptr, &ctx_);
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
+    const int rp = vo_set_pose_mode(ctx_, p_.pose_strict ? VO_POSE_STRICT : VO_POSE_FAST);
+    if (rp) fail(ctx_, rp);
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
     {   // landmark tables: room for 2^19 landmarks before the first reallocation (see StereoVO::init)

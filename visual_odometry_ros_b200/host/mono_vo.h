@@ -76,6 +76,9 @@ public:
         // D = k1 k2 p1 p2 k3 (camera.cpp:30-34).  The camera matrix is unchanged
         int do_undistortion = 0;
         float D[5] = {0, 0, 0, 0, 0};
+        // pose-only GN accumulation: 0 = VO_POSE_FAST (FP64 tree sums), 1 = VO_POSE_STRICT (sequential FP32 sums in point
+        // order: the reference's arithmetic bit for bit); yaml key motion_estimator.pose_strict (ours)
+        int pose_strict = 0;
     };
 
     MonoVO(std::string mode, std::string directory_intrinsic);     // mono_vo.cpp:11-55 (yaml via a minimal parser)

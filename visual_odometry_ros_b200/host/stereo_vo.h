@@ -71,6 +71,10 @@ public:
         // reference runs; the yaml constructor selects it with feature_extractor.thres_fastscore, stereo_vo.cpp:31-36)
         int detector = VO_DETECTOR_HARRIS_SCHARR;
         int thres_fastscore = 20;
+        // pose-only GN accumulation: 0 = VO_POSE_FAST (FP64 tree sums), 1 = VO_POSE_STRICT (sequential FP32 sums in point
+        // order: the reference's arithmetic bit for bit, about 0.2 ms more per frame at 2000 landmarks); yaml key
+        // motion_estimator.pose_strict (ours; the reference has no such key)
+        int pose_strict = 0;
     };
 
     StereoVO(std::string mode, std::string directory_intrinsic);   // stereo_vo.cpp:9-53 (yaml via a minimal parser)
