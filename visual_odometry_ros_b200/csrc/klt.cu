@@ -381,7 +381,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t phase)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t &phase)
 {
     int spins = 0;
-    while (!mbar_try_wait(bar, phase)) { if (++spins > (1 << 20)) __trap(); }
+    while (!mbar_try_wait(bar, phase)) { if (++spins > (1 << 24)) __trap(); }
     phase ^= 1u;
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2)

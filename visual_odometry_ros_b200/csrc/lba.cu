@@ -432,13 +432,51 @@ k_lba_build(const LbaDev d, int apply_update)
     const int ncol = n6 + 1;
     double *out = d.s_part + (size_t)blockIdx.x * n6 * ncol;
     const int K3 = 3 * TL;
-    for (int e = tid; e < n6 * ncol; e += LBA_THREADS) {
-        const int r = e / ncol, c = e - r * ncol;
-        double acc = 0.0;
-        if (c == n6 || (c / 6) >= (r / 6)) {   // upper block triangle + rhs column
-            for (int k = 0; k < K3; ++k) acc += P[(size_t)k * n6 + r] * Q[(size_t)k * ncol + c];
+    // Register-tiled: a work item is a 2 x 3 patch of one 6 x 6 block (jb <= kb: the upper block triangle) or a 6 x 1 slice
+    // of the right-hand-side column; per k it loads 2 + 3 (6 + 1) panel entries for 6 multiply-adds on six independent
+    // accumulators (the first version ran one dependent 3 TL-long dot product per entry, two loads per multiply-add:
+    // 41 % of the kernel's instructions, profiles/r2_lba_build_*).  Every entry is still summed over k in ascending order.
+    {
+        const int n_pairs = No * (No + 1) / 2;
+        const int n_items = n_pairs * 6 + No;
+        for (int e = tid; e < n6 * ncol; e += LBA_THREADS) {      // entries outside the upper block triangle: zero
+            const int r = e / ncol, c = e - r * ncol;
+            if (c != n6 && (c / 6) < (r / 6)) out[e] = 0.0;
         }
-        out[e] = acc;
+        for (int it = tid; it < n_items; it += LBA_THREADS) {
+            if (it < n_pairs * 6) {
+                const int pair = it / 6, sub = it - pair * 6;       // sub: 3 row pairs x 2 column triples
+                int jb = 0, rem = pair;
+                while (rem >= No - jb) { rem -= No - jb; ++jb; }
+                const int kb = jb + rem;
+                const int r0 = 6 * jb + 2 * (sub >> 1), c0 = 6 * kb + 3 * (sub & 1);
+                double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0;
+                const double *pp = P + r0, *qq = Q + c0;
+#pragma unroll 4
+                for (int k = 0; k < K3; ++k) {
+                    const double p0 = pp[0], p1 = pp[1], q0 = qq[0], q1 = qq[1], q2 = qq[2];
+                    a00 += p0 * q0; a01 += p0 * q1; a02 += p0 * q2;
+                    a10 += p1 * q0; a11 += p1 * q1; a12 += p1 * q2;
+                    pp += n6; qq += ncol;
+                }
+                double *o = out + (size_t)r0 * ncol + c0;
+                o[0] = a00; o[1] = a01; o[2] = a02;
+                o[ncol] = a10; o[ncol + 1] = a11; o[ncol + 2] = a12;
+            } else {
+                const int jb = it - n_pairs * 6;
+                double a[6] = {0, 0, 0, 0, 0, 0};
+                const double *pp = P + 6 * jb, *qq = Q + n6;
+#pragma unroll 4
+                for (int k = 0; k < K3; ++k) {
+                    const double q = qq[0];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) a[r] += pp[r] * q;
+                    pp += n6; qq += ncol;
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) out[(size_t)(6 * jb + r) * ncol + n6] = a[r];
+            }
+        }
     }
     for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) {
         double acc = 0.0;
