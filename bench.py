@@ -849,6 +849,7 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
     warm.close()
     vo = mk()
     ms, kf, nfeat = [], [], []
+    parts = {key: [] for key in ("step", "book", "recon", "lba_pack", "lba_solve", "stats", "total")}
     launches0 = vo.launch_count
     for k in range(n_frames):
         t0 = time.perf_counter()
@@ -857,6 +858,9 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
         fi = vo.frame_info()
         kf.append(fi["keyframe"])
         nfeat.append(fi["n_in"])
+        if fi["keyframe"] and k >= 2:
+            for key in parts:
+                parts[key].append(fi["ms_" + key])
     launches = vo.launch_count - launches0
     T_g = vo.pose()
     gt = np.linalg.inv(T_true[0]) @ T_true[n_frames - 1]
@@ -878,6 +882,7 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
             "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
             "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None,
             "ms_per_keyframe_median": float(np.median(ms[kf])) if kf.any() else None, "keyframes": int(kf.sum()),
+            "keyframe_breakdown_ms": {key: float(np.mean(v)) for key, v in parts.items() if v},
             "mean_tracked_features": float(np.mean(nfeat[2:])), "bins": [nbu, nbv], "gpu_launches": int(launches),
             "translation_drift_vs_ground_truth": drift,
             "cpu_ms_per_frame": float(np.mean(cms[2:])), "cpu_frames": n_cpu, "cpu_cores": os.cpu_count() or 1,

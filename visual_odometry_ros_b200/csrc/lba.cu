@@ -31,6 +31,8 @@
 
 #define LBA_WARPS 8
 #define LBA_THREADS (LBA_WARPS * 32)
+#define LBA_BWARPS 16           // k_lba_build: warps per tile (latency-bound per-landmark chains: more warps in flight)
+#define LBA_BTHREADS (LBA_BWARPS * 32)
 #define LBA_MAX_OPT 16
 #define LBA_NA 27            // 21 upper entries of Q^T W Q + 6 entries of Q^T W r
 
@@ -201,10 +203,10 @@ __device__ __forceinline__ double wsum(double v)
 // dynamic shared memory layout (doubles):
 //   P     [3*TL][n6]        P[3*il+m][6j+r] = BCinv[j][i](r, m)
 //   Q     [3*TL][n6+1]      Q[3*il+m][6k+c] = B[k][i](c, m) ; Q[3*il+m][n6] = b_i(m)
-//   Aacc  [LBA_WARPS][n_opt][27]
-//   Btmp  [LBA_WARPS][n_opt][18]
-//   errw  [LBA_WARPS]
-__global__ void __launch_bounds__(LBA_THREADS, 1)
+//   Aacc  [LBA_BWARPS][n_opt][27]
+//   Btmp  [LBA_BWARPS][n_opt][18]
+//   errw  [LBA_BWARPS]
+__global__ void __launch_bounds__(LBA_BTHREADS, 1)
 k_lba_build(const LbaDev d, int apply_update)
 {
     extern __shared__ double smem[];
@@ -212,11 +214,19 @@ k_lba_build(const LbaDev d, int apply_update)
     double *P = smem;
     double *Q = P + (size_t)3 * TL * n6;
     double *Aacc = Q + (size_t)3 * TL * (n6 + 1);
-    double *Btmp = Aacc + (size_t)LBA_WARPS * No * LBA_NA;
-    double *errw = Btmp + (size_t)LBA_WARPS * No * 18;
+    double *Btmp = Aacc + (size_t)LBA_BWARPS * No * LBA_NA;
+    double *errw = Btmp + (size_t)LBA_BWARPS * No * 18;
+    double *s_x = errw + LBA_BWARPS;                       // [n6]        the pose update of the previous iteration
+    double *s_T = s_x + n6;                                // [N][16]     keyframe poses
+    int *s_opt = reinterpret_cast<int *>(s_T + (size_t)16 * d.n_frames);   // [N]  frame -> optimisable index
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n_smem = (int)(errw + LBA_WARPS - smem);
-    for (int i = tid; i < n_smem; i += LBA_THREADS) smem[i] = 0.0;
+    const int n_smem = (int)(errw + LBA_BWARPS - smem);
+    for (int i = tid; i < n_smem; i += LBA_BTHREADS) smem[i] = 0.0;
+    // the per-frame tables every observation looks up: once per tile from global memory instead of a dependent L2 round trip
+    // (frame -> index -> pose) in each of a landmark's three passes
+    for (int i = tid; i < n6; i += LBA_BTHREADS) s_x[i] = apply_update ? d.x[i] : 0.0;
+    for (int i = tid; i < 16 * d.n_frames; i += LBA_BTHREADS) s_T[i] = d.poses[i];
+    for (int i = tid; i < d.n_frames; i += LBA_BTHREADS) s_opt[i] = d.opt_index[i];
     __syncthreads();
 
     const int tile_base = blockIdx.x * TL;
@@ -224,7 +234,7 @@ k_lba_build(const LbaDev d, int apply_update)
     double *myB = Btmp + (size_t)wid * No * 18;
     double err_w = 0.0;
 
-    for (int il = wid; il < TL; il += LBA_WARPS) {
+    for (int il = wid; il < TL; il += LBA_BWARPS) {
         const int i = tile_base + il;
         if (i >= d.n_points) break;
         const int o_beg = d.obs_ptr[i], o_end = d.obs_ptr[i + 1];
@@ -235,14 +245,14 @@ k_lba_build(const LbaDev d, int apply_update)
             double cb[3] = {0, 0, 0};
             for (int o = o_beg + lane; o < o_end; o += 32) {
                 if (d.obs_right[o]) continue;
-                const int j = d.opt_index[d.obs_frame[o]];
+                const int j = s_opt[d.obs_frame[o]];
                 if (j < 0) continue;
                 const double *BC = d.bcinv + (size_t)o * 18;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     double s = 0;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) s += BC[c * 3 + r] * d.x[6 * j + c];
+                    for (int c = 0; c < 6; ++c) s += BC[c * 3 + r] * s_x[6 * j + c];
                     cb[r] += s;
                 }
             }
@@ -265,8 +275,8 @@ k_lba_build(const LbaDev d, int apply_update)
             if (act) {
                 const int f = d.obs_frame[o];
                 right = d.obs_right[o];
-                j = d.opt_index[f];
-                const double *T = d.poses + 16 * f;
+                j = s_opt[f];
+                const double *T = s_T + 16 * f;
                 double R_jw[9], t_jw[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) { R_jw[r * 3] = T[r * 4]; R_jw[r * 3 + 1] = T[r * 4 + 1]; R_jw[r * 3 + 2] = T[r * 4 + 2]; t_jw[r] = T[r * 4 + 3]; }
@@ -397,7 +407,7 @@ k_lba_build(const LbaDev d, int apply_update)
         for (int o0 = o_beg; o0 < o_end; o0 += 32) {
             const int o = o0 + lane;
             if (o < o_end && !d.obs_right[o]) {
-                const int j = d.opt_index[d.obs_frame[o]];
+                const int j = s_opt[d.obs_frame[o]];
                 if (j >= 0) {
                     const double *Bj = myB + (size_t)j * 18;
                     double BC[18];
@@ -439,11 +449,11 @@ k_lba_build(const LbaDev d, int apply_update)
     {
         const int n_pairs = No * (No + 1) / 2;
         const int n_items = n_pairs * 6 + No;
-        for (int e = tid; e < n6 * ncol; e += LBA_THREADS) {      // entries outside the upper block triangle: zero
+        for (int e = tid; e < n6 * ncol; e += LBA_BTHREADS) {      // entries outside the upper block triangle: zero
             const int r = e / ncol, c = e - r * ncol;
             if (c != n6 && (c / 6) < (r / 6)) out[e] = 0.0;
         }
-        for (int it = tid; it < n_items; it += LBA_THREADS) {
+        for (int it = tid; it < n_items; it += LBA_BTHREADS) {
             if (it < n_pairs * 6) {
                 const int pair = it / 6, sub = it - pair * 6;       // sub: 3 row pairs x 2 column triples
                 int jb = 0, rem = pair;
@@ -478,14 +488,14 @@ k_lba_build(const LbaDev d, int apply_update)
             }
         }
     }
-    for (int e = tid; e < No * LBA_NA; e += LBA_THREADS) {
+    for (int e = tid; e < No * LBA_NA; e += LBA_BTHREADS) {
         double acc = 0.0;
-        for (int w = 0; w < LBA_WARPS; ++w) acc += Aacc[(size_t)w * No * LBA_NA + e];
+        for (int w = 0; w < LBA_BWARPS; ++w) acc += Aacc[(size_t)w * No * LBA_NA + e];
         d.a_part[(size_t)blockIdx.x * No * LBA_NA + e] = acc;
     }
     if (tid == 0) {
         double acc = 0.0;
-        for (int w = 0; w < LBA_WARPS; ++w) acc += errw[w];
+        for (int w = 0; w < LBA_BWARPS; ++w) acc += errw[w];
         d.err_part[blockIdx.x] = acc;
     }
 }
@@ -594,6 +604,38 @@ __device__ __forceinline__ void lba_assemble(const LbaDev &d, double *S, const i
 #undef SM
 }
 
+// One elimination step's column work with the pivot's in-block column PA known at compile time (register arrays cannot be
+// indexed dynamically; the caller switches on the warp-uniform value).  Owners of column p (tx == pb) publish
+// L(:,p) = A(:,p) * rk and D_p L(:,p), park the factor column, and retire the column; owners of row p (ty == pb) retire the
+// row.  Retired rows / columns are ZERO in the registers from then on (0 - 0 * t stays 0), so no liveness masks are needed.
+template <int B, int PA>
+__device__ __forceinline__ void ldlt_column_step(double (&A)[B][B], bool col_owner, bool row_owner, double rk, double akk,
+                                                 double *l_rows, double *t_rows, double *S_col, int LD)
+{
+    if (col_owner) {
+        double l[B], t[B];
+#pragma unroll
+        for (int a = 0; a < B; ++a) {
+            const double c = (a == PA && row_owner) ? 0.0 : A[a][PA];      // the pivot's own row takes no update
+            l[a] = c * rk;
+            t[a] = akk * l[a];
+            A[a][PA] = 0.0;
+        }
+        static_assert(B % 2 == 0, "vector stores below");
+#pragma unroll
+        for (int h = 0; h < B / 2; ++h) {
+            reinterpret_cast<double2 *>(l_rows)[h] = make_double2(l[2 * h], l[2 * h + 1]);
+            reinterpret_cast<double2 *>(t_rows)[h] = make_double2(t[2 * h], t[2 * h + 1]);
+        }
+#pragma unroll
+        for (int a = 0; a < B; ++a) S_col[(size_t)a * LD] = l[a];           // rows eliminated earlier store a zero nobody reads
+    }
+    if (row_owner) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) A[PA][b] = 0.0;
+    }
+}
+
 template <int G, int B>      // G x G threads own B x B register blocks of the (G*B)-padded system
 __global__ void __launch_bounds__(LBA_THREADS, 1)
 k_lba_solve(const LbaDev d, int iter)
@@ -605,13 +647,13 @@ k_lba_solve(const LbaDev d, int iter)
     double *S = smem;                    // [NP][LD]: assembly, then (column by column) the factor L
     double *rhs = S + (size_t)NP * LD;   // [NP]
     double *Aj = rhs + NP;               // [No][27]
-    __shared__ double s_diag[NP], s_l[NP], s_t[NP], s_D[NP];
-    __shared__ int s_idx_at[NP];         // position -> original index (the transpositions Eigen would have applied)
+    __shared__ __align__(16) double s_lt[4 * NP];      // L(:,p) and D_p L(:,p) of the current step, double-buffered by step parity: [l 0 | l 1 | t 0 | t 1]
+    __shared__ double s_D[NP];
     __shared__ int s_piv[NP];            // step -> original index
     __shared__ int s_step[NP];           // original index -> step
     __shared__ double s_err;
     const int tid = threadIdx.x, lane = tid & 31;
-    const bool act = tid < G * G;        // threads of the factorisation grid (the others only keep the barriers company)
+    const bool act = tid < G * G;        // threads of the factorisation grid (the other warps wait at the barrier behind the loop)
     const int ty = tid / G, tx = tid % G;
 #define SM(i, j) S[(size_t)(i) * LD + (j)]
 #define STAMP(k) do { if (d.dbg && tid == 0) d.dbg[k] = clock64(); } while (0)
@@ -621,126 +663,117 @@ k_lba_solve(const LbaDev d, int iter)
 
     // ---- registers <- the LOWER triangle (what Eigen::LDLT<.., Lower> reads), mirrored to a full symmetric matrix
     double A[B][B];
-    unsigned rowdead = 0;                // bit a: row index eliminated or padding (>= n)
+    // Every active warp also keeps, redundantly and in REGISTERS, the whole diagonal (lane owns the original indices lane,
+    // lane + 32, ...) and the POSITION each index would have after the transpositions Eigen applies (its tie rule is "first
+    // position"); -1 = eliminated or padding.  The pivot search then needs no shared memory and no second barrier.
+    constexpr int NPS = (NP + 31) / 32;
+    double dg[NPS];
+    int pos[NPS];
     if (act) {
 #pragma unroll
         for (int a = 0; a < B; ++a) {
             const int i = ty * B + a;
-            if (i >= n) rowdead |= 1u << a;
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const int j = tx * B + b;
                 A[a][b] = (i < n && j < n) ? (i >= j ? SM(i, j) : SM(j, i)) : 0.0;
             }
         }
-    }
-    if (tid < NP) { s_idx_at[tid] = tid; s_step[tid] = -1; s_D[tid] = 0.0; }
-    __syncthreads();                     // every register copy is made before the factor overwrites S
-    if (act && ty == tx) {
 #pragma unroll
-        for (int a = 0; a < B; ++a) s_diag[ty * B + a] = A[a][a];
+        for (int q = 0; q < NPS; ++q) {
+            const int i = lane + 32 * q;
+            dg[q] = i < n ? SM(i, i) : 0.0;
+            pos[q] = i < n ? i : -1;
+        }
     }
+    if (tid < NP) { s_step[tid] = -1; s_D[tid] = 0.0; }
     // Which of {l, t = D l} a thread multiplies is fixed by its block position: element (i, j) takes L(i,p) * (D_p L(j,p)) with
     // i >= j (the lower-triangle product) and its mirror image otherwise; inside a diagonal block the split is a >= b.
-    const double *pUA = (ty >= tx) ? s_l : s_t, *pVA = (ty >= tx) ? s_t : s_l;      // elements with a >= b
-    const double *pUB = (ty > tx) ? s_l : s_t, *pVB = (ty > tx) ? s_t : s_l;        // elements with a <  b
-    __syncthreads();
+    const int oUA = (ty >= tx) ? 0 : 2 * NP, oVA = (ty >= tx) ? 2 * NP : 0;         // l or t: offsets into s_lt relative to the step's l buffer
+    const int oUB = (ty > tx) ? 0 : 2 * NP, oVB = (ty > tx) ? 2 * NP : 0;
+    __syncthreads();                     // every register copy is made before the factor overwrites S
 
-    long long t_piv = 0, t_pub = 0, t_upd = 0, t_last = d.dbg ? clock64() : 0;      // VO_LBA_TRACE: where a step's cycles go
-#define PHASE(acc) do { if (d.dbg && tid == 0) { const long long t_now = clock64(); acc += t_now - t_last; t_last = t_now; } } while (0)
-    // Software pipeline over the steps: once the new DIAGONAL of step k is published (barrier 2) the pivot of step k+1 can be
-    // searched, so the rest of step k's trailing update (36 independent multiply-subtracts per thread) is issued between the
-    // search's shared-memory loads and its warp reductions -- it runs in the shadow of the search's latency.
-    double uA[B], vA[B], uB[B], vB[B];
-#pragma unroll
-    for (int a = 0; a < B; ++a) { uA[a] = 0.0; vA[a] = 0.0; uB[a] = 0.0; vB[a] = 0.0; }     // step -1: nothing to subtract
-    constexpr int NPS = (NP + 31) / 32;          // pivot-search positions per lane
-    for (int k = 0; k < n; ++k) {
-        if (act) {
-            // ---- pivot of step k: largest |diagonal| among positions k .. n-1, first position on ties (every active warp,
-            // redundantly); loads first ...
-            double dv[NPS];
-#pragma unroll
-            for (int q = 0; q < NPS; ++q) {
-                const int pos = k + lane + 32 * q;
-                dv[q] = pos < n ? fabs(s_diag[s_idx_at[pos]]) : -1.0;
-            }
-            // ... the rest of step k-1's trailing update (everything but the diagonal entries of the diagonal blocks) ...
-#pragma unroll
-            for (int a = 0; a < B; ++a)
-#pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    const double prod = (a >= b) ? uA[a] * vA[b] : uB[a] * vB[b];
-                    if (a != b || ty != tx) A[a][b] -= prod;
-                }
-            // ... then the reductions
+    // One barrier per step.  After the barrier of step k every thread holds L(:,p_k) and D L(:,p_k); the register diagonal is
+    // updated first (one fused multiply-subtract per owned index), the search for step k+1 runs on it, and the 36 independent
+    // fused multiply-subtracts of the trailing update are issued in the shadow of the search's reductions and of the pivot
+    // reciprocal.  (No clock stamps inside the loop: they pin the instruction order and undo exactly that overlap.)
+    if (act) {
+        for (int k = 0; k < n; ++k) {
+            // ---- pivot of step k: largest |diagonal| among the live indices, first POSITION on ties (every active warp).
+            // Keys are the bit patterns of |d| (monotonic for non-negative doubles); eliminated / padding / NaN entries and
+            // exact zeros carry key 0 and never win -- if nothing wins the pivot is the index at position k, as in Eigen.
             int big_pos;
             {
-                double bv = -1.0;
-                int bp = k;
+                unsigned long long bk = 0ull;
+                int bp = 0x7fffffff;
 #pragma unroll
-                for (int q = 0; q < NPS; ++q)
-                    if (dv[q] > bv) { bv = dv[q]; bp = k + lane + 32 * q; }
-                const bool has = bv >= 0.0;       // NaN and "no element" (-1) never win
-                const unsigned long long key = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
-                const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
+                for (int q = 0; q < NPS; ++q) {
+                    const double v = fabs(dg[q]);
+                    const unsigned long long key = (pos[q] >= 0 && v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;
+                    if (key > bk || (key == bk && key != 0ull && pos[q] < bp)) { bk = key; bp = pos[q]; }
+                }
+                const unsigned hi = (unsigned)(bk >> 32);
                 const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-                const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
+                const unsigned lo = (hi == mhi) ? (unsigned)bk : 0u;
                 const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-                const bool win = has && hi == mhi && (unsigned)key == mlo;
+                const bool win = bk != 0ull && hi == mhi && (unsigned)bk == mlo;
                 big_pos = __reduce_min_sync(0xffffffffu, win ? bp : 0x7fffffff);
                 if (big_pos == 0x7fffffff) big_pos = k;
             }
-            const int p = s_idx_at[big_pos];
+            int my_q = -1;
+#pragma unroll
+            for (int q = 0; q < NPS; ++q)
+                if (pos[q] == big_pos) my_q = q;
+            const int src = __ffs(__ballot_sync(0xffffffffu, my_q >= 0)) - 1;
+            double sel = dg[0];
+#pragma unroll
+            for (int q = 1; q < NPS; ++q) sel = (my_q == q) ? dg[q] : sel;
+            const int p = __shfl_sync(0xffffffffu, lane + 32 * (my_q > 0 ? my_q : 0), src);
+            const double akk = __shfl_sync(0xffffffffu, sel, src);
+            // the transposition: the pivot leaves the table, the index that sat at position k takes the pivot's old position
+#pragma unroll
+            for (int q = 0; q < NPS; ++q) {
+                if (lane == src && q == my_q) pos[q] = -1;
+                else if (pos[q] == k) pos[q] = big_pos;
+            }
             const int pb = p / B, pa = p - pb * B;
-            // ---- the owners of column p publish L(:,p), D_p L(:,p) and park the factor column
-            if (tx == pb) {
-                const double akk = s_diag[p];
-                // L(:,p) = A(:,p) * (1 / D_p) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp)
-                const bool scale = (k < n - 1) && fabs(akk) > 0.0;
-                const double rk = scale ? __drcp_rn(akk) : 0.0;
-#pragma unroll
-                for (int a = 0; a < B; ++a) {
-                    const int i = ty * B + a;
-                    double c = A[a][0];
-#pragma unroll
-                    for (int b = 1; b < B; ++b) c = (b == pa) ? A[a][b] : c;
-                    const bool alive = !((rowdead >> a) & 1u) && i != p;
-                    const double l = scale ? c * rk : c;
-                    s_l[i] = alive ? l : 0.0;             // eliminated rows take no further update
-                    s_t[i] = alive ? akk * l : 0.0;
-                    if (alive) SM(i, p) = l;
+            // L(:,p) = A(:,p) * (1 / D_p) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp); Eigen leaves
+            // the column unscaled at the last step and for an exactly zero pivot: factor 1
+            const double rk = ((k < n - 1) && fabs(akk) > 0.0) ? __drcp_rn(akk) : 1.0;
+            double *bl = s_lt + (k & 1) * NP, *bt = bl + 2 * NP;
+            {
+                const bool co = tx == pb, ro = ty == pb;
+                double *lr = bl + ty * B, *tr = bt + ty * B, *sc = &SM(ty * B, p);
+                switch (pa) {
+                case 0: ldlt_column_step<B, 0>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                case 1: ldlt_column_step<B, 1>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                case 2: ldlt_column_step<B, 2>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                case 3: ldlt_column_step<B, 3>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                case 4: ldlt_column_step<B, 4>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                default: ldlt_column_step<B, 5>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
                 }
-                if (ty == pb) s_D[p] = akk;
             }
-            if (ty == pb) rowdead |= 1u << pa;    // every thread of that block row: it may own a later pivot column
-            if (tid == 0) s_piv[k] = p;
-            if (tid == 1 % (G * G)) s_step[p] = k;
-            PHASE(t_piv);
-            __syncthreads();                 // (1) column visible; every warp has read the position table and the diagonal
-            PHASE(t_pub);
-            if (tid == 0) {
-                const int q = s_idx_at[k];
-                s_idx_at[k] = p; s_idx_at[big_pos] = q;
+            if (tid == 0) { s_piv[k] = p; s_step[p] = k; s_D[p] = akk; }
+            asm volatile("bar.sync 1, %0;" ::"n"(G * G) : "memory");    // column visible (the idle warps are not involved)
+            // ---- the diagonal first (all the next search needs), then the trailing update
+#pragma unroll
+            for (int q = 0; q < NPS; ++q) {
+                const int i = lane + 32 * q;
+                if (i < NP) dg[q] = __fma_rn(-bl[i], bt[i], dg[q]);
             }
+            double uA[B], vA[B], uB[B], vB[B];
 #pragma unroll
             for (int a = 0; a < B; ++a) {
-                uA[a] = pUA[ty * B + a]; uB[a] = pUB[ty * B + a];
-                vA[a] = pVA[tx * B + a]; vB[a] = pVB[tx * B + a];
+                uA[a] = bl[oUA + ty * B + a]; uB[a] = bl[oUB + ty * B + a];
+                vA[a] = bl[oVA + tx * B + a]; vB[a] = bl[oVB + tx * B + a];
             }
-            // the new diagonal first: it is all the next pivot search needs
-            if (ty == tx) {
 #pragma unroll
-                for (int a = 0; a < B; ++a) { A[a][a] -= uA[a] * vA[a]; s_diag[ty * B + a] = A[a][a]; }
-            }
-        } else {
-            __syncthreads();                 // (1)
+            for (int a = 0; a < B; ++a)
+#pragma unroll
+                for (int b = 0; b < B; ++b) A[a][b] = (a >= b) ? __fma_rn(-uA[a], vA[b], A[a][b]) : __fma_rn(-uB[a], vB[b], A[a][b]);
         }
-        __syncthreads();                     // (2) diagonal + position table updated; s_l / s_t may be overwritten
-        PHASE(t_upd);
     }
-    if (d.dbg && tid == 0) { d.dbg[5] = t_piv; d.dbg[6] = t_pub; d.dbg[7] = t_upd; }
-#undef PHASE
+    __syncthreads();
     STAMP(2);
     const double tol = 1.0 / 1.7976931348623157e308;
     if (tid < 32) {
@@ -988,20 +1021,19 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
 
     // tile size from the shared-memory budget
     const size_t budget = 200 * 1024;
-    const size_t fixed = ((size_t)LBA_WARPS * No * (LBA_NA + 18) + LBA_WARPS) * 8;
+    const size_t fixed = ((size_t)LBA_BWARPS * No * (LBA_NA + 18) + LBA_BWARPS + n6 + (size_t)16 * N) * 8 + (size_t)N * 4 + 8;
     const size_t per_lm = (size_t)3 * (2 * n6 + 1) * 8;
+    VO_REQUIRE(fixed + per_lm <= budget, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
     int TL = (int)((budget - fixed) / per_lm);
-    TL = TL / LBA_WARPS * LBA_WARPS;
     if (TL > 64) TL = 64;
     {   // fill the machine: about one tile per SM (a tile's warps walk their landmarks sequentially, so fewer
         // landmarks per tile is lower latency; more tiles only cost a longer k_lba_reduce)
         static int n_sm = 0;
         if (!n_sm) { cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device); if (n_sm <= 0) n_sm = 148; }
-        int want = vo_div_up(vo_div_up(M > 0 ? M : 1, n_sm), LBA_WARPS) * LBA_WARPS;
-        if (want < LBA_WARPS) want = LBA_WARPS;
+        const int want = vo_div_up(M > 0 ? M : 1, n_sm);
         if (want < TL) TL = want;
     }
-    VO_REQUIRE(TL >= LBA_WARPS, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
+    VO_REQUIRE(TL >= 1, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
     const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
     const size_t smem_build = fixed + per_lm * TL;
     const int solve_G = n6 <= 48 ? 8 : 16;     // k_lba_solve<G, 6>: G x G threads own 6 x 6 register blocks
@@ -1085,7 +1117,7 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     std::vector<cudaEvent_t> evs;
     if (trace) { evs.resize(2 * p->max_iter + 1); for (auto &e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], ctx->stream); }
     for (int it = 0; it < p->max_iter; ++it) {
-        k_lba_build<<<n_tiles, LBA_THREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
+        k_lba_build<<<n_tiles, LBA_BTHREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
         k_lba_reduce<<<vo_div_up((n6 * (n6 + 1) + No * LBA_NA + 1) * LBA_RED_G, 256), 256, 0, ctx->stream>>>(d);
         if (dist) {
             // the one exchange step of the path: partial reduced systems of the ranks' landmark shards -> complete system everywhere
@@ -1107,12 +1139,8 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
         }
         for (auto &e : evs) cudaEventDestroy(e);
         long long st[8];
-        long long st2[16];
-        cudaMemcpy(st2, dv + o_dbg, 104, cudaMemcpyDeviceToHost);
-        memcpy(st, st2, 40);
-
-        fprintf(stderr, "k_lba_solve cycles: assemble %lld, ldlt %lld (pivot %lld, barrier-1 %lld, update+barrier-2 %lld), solves %lld, retract %lld\n",
-                st[1] - st[0], st[2] - st[1], st2[5], st2[6], st2[7], st[3] - st[2], st[4] - st[3]);
+        cudaMemcpy(st, dv + o_dbg, 40, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "k_lba_solve cycles: assemble %lld, ldlt %lld, solves %lld, retract %lld\n", st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3]);
     }
     if (M > 0) { k_lba_update_points<<<vo_div_up(M, 256), 256, 0, ctx->stream>>>(d); ctx->launches++; }
     VO_CUDA(cudaGetLastError());

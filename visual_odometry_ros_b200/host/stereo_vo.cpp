@@ -97,7 +97,7 @@ void StereoVO::init()
         // otherwise move hundreds of thousands of per-landmark vectors inside a frame (a ~10 ms latency spike)
         const size_t cap = (size_t)1 << 19;
         lm_X_.reserve(cap * 3); lm_tri_.reserve(cap); lm_alive_.reserve(cap); lm_bundled_.reserve(cap); lm_last_frame_.reserve(cap);
-        lm_kf_obs_.reserve(cap); lm_kf_slots_.reserve(cap); lm_seen_stamp_.reserve(cap);
+        lm_slot_head_.reserve(cap); lm_seen_stamp_.reserve(cap); lm_lba_slot_.reserve(cap); kf_slot_pool_.reserve(cap);
     }
     memcpy(K_use_l_, p_.K_l, 16); memcpy(K_use_r_, p_.K_r, 16); memcpy(T_lr_use_, p_.T_lr, 64);
     if (p_.do_undistortion) {
@@ -129,8 +129,7 @@ int StereoVO::newLandmarks(int k, int frame_id)
     lm_X_.resize((size_t)(base + k) * 3, 0.f);
     lm_tri_.resize(base + k, 0); lm_alive_.resize(base + k, 1); lm_bundled_.resize(base + k, 0);
     lm_last_frame_.resize(base + k, frame_id);
-    lm_kf_obs_.resize(base + k);
-    lm_kf_slots_.resize(base + k);
+    lm_slot_head_.resize(base + k, -1);
     return base;
 }
 
@@ -157,16 +156,16 @@ void StereoVO::addKeyframe(const FrameRecPtr &f)
     all_keyframes_.push_back(f);
     if ((int)window_.size() == p_.n_max_keyframes_in_window) window_.pop_front();
     window_.push_back(f);
+    // The window keyframes keep their own (landmark id, left pixel, right pixel) arrays: the local-BA packing reads those
+    // (localBundleAdjustment), so no per-landmark observation list has to be maintained here.
     const size_t n = f->lm_ids.size();
-    for (size_t i = 0; i < n; ++i) {
-        auto &v = lm_kf_obs_[f->lm_ids[i]];
-        if (v.empty()) { v.reserve(8); lm_kf_slots_[f->lm_ids[i]].reserve(4); }      // one allocation instead of the 1-2-4-8 growth
-        v.push_back({f->id, 0, f->pts_l[2 * i], f->pts_l[2 * i + 1]});
-    }
-    for (size_t i = 0; i < n; ++i) lm_kf_obs_[f->lm_ids[i]].push_back({f->id, 1, f->pts_r[2 * i], f->pts_r[2 * i + 1]});
     const int kf_index = (int)all_keyframes_.size() - 1;
     f->kf_index = kf_index;
-    for (size_t i = 0; i < n; ++i) lm_kf_slots_[f->lm_ids[i]].push_back({kf_index, (int)i});
+    for (size_t i = 0; i < n; ++i) {
+        const int id = f->lm_ids[i];
+        kf_slot_pool_.push_back({kf_index, (int)i, lm_slot_head_[id]});
+        lm_slot_head_[id] = (int)kf_slot_pool_.size() - 1;
+    }
 }
 
 void StereoVO::reconstruct(FrameRec &f, int n_first)
@@ -194,24 +193,40 @@ void StereoVO::localBundleAdjustment()
     if ((int)window_.size() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return;
     const auto t_pack = Clock::now();
     const int nf = (int)window_.size();
-    // frame id -> window position (frame ids are dense and increasing: a flat table instead of the reference's
-    // unordered_map lookups per observation, sparse_ba_parameters.h:384)
-    const int id0 = window_.front()->id;
-    std::vector<int> fidx_tab((size_t)(window_.back()->id - id0 + 1), -1);
-    for (int k = 0; k < nf; ++k) fidx_tab[window_[k]->id - id0] = k;
-    auto fidx_of = [&](int kf_id) { const int r = kf_id - id0; return (r >= 0 && r < (int)fidx_tab.size()) ? fidx_tab[r] : -1; };
-    // 1) alive + triangulated landmarks of the window, first-seen order (the reference's unordered_set order is
-    //    address-hash dependent)
-    std::vector<int> &lmset = lba_lmset_;
-    lmset.clear();
+    // 1) alive + triangulated landmarks of the window in first-seen order (the reference's unordered_set order is
+    //    address-hash dependent) and their observation counts, straight from the window keyframes'
+    //    own arrays: every keyframe lists each of its landmarks once, with the left and the right pixel.
+    //    (The first version walked a per-landmark vector of observations: 0.30 ms of pointer chasing per keyframe, plus
+    //    0.15 ms per keyframe to maintain those vectors.)
+    std::vector<int> &lms = lba_lms_, &obs_ptr = lba_obs_ptr_, &cursor = lba_obs_cursor_, &obs_frame = lba_obs_frame_;
+    lms.clear(); obs_ptr.clear();
     {
         // stamp instead of a cleared flag array: no O(all landmarks) memset per keyframe
         lm_seen_stamp_.resize(lm_tri_.size(), 0);
+        lm_lba_slot_.resize(lm_tri_.size(), 0);
         const int stamp = ++seen_stamp_;
         for (const auto &fr : window_)
-            for (int id : fr->lm_ids)
-                if (lm_seen_stamp_[id] != stamp && lm_tri_[id] && lm_alive_[id]) { lm_seen_stamp_[id] = stamp; lmset.push_back(id); }
+            for (int id : fr->lm_ids) {
+                if (!lm_tri_[id] || !lm_alive_[id]) continue;
+                if (lm_seen_stamp_[id] != stamp) {
+                    lm_seen_stamp_[id] = stamp;
+                    lm_lba_slot_[id] = (int)lms.size();
+                    lms.push_back(id);
+                    obs_ptr.push_back(0);
+                }
+                obs_ptr[lm_lba_slot_[id]] += 2;          // left + right
+            }
     }
+    // THRES_MINIMUM_SEEN = 2 observations: a stereo keyframe contributes two, so every listed landmark qualifies
+    if (lms.empty()) return;
+    const int n_lm = (int)lms.size();
+    cursor.resize(n_lm);
+    {
+        int run = 0;
+        for (int j = 0; j < n_lm; ++j) { const int c = obs_ptr[j]; obs_ptr[j] = run; cursor[j] = run; run += c; }
+        obs_ptr.push_back(run);
+    }
+    const int n_obs = obs_ptr[n_lm];
     double Twj_ref[16], Tjw_ref[16];
     for (int i = 0; i < 12; ++i) Twj_ref[i] = window_[0]->Twc[i];
     Twj_ref[12] = Twj_ref[13] = Twj_ref[14] = 0; Twj_ref[15] = 1;
@@ -224,27 +239,31 @@ void StereoVO::localBundleAdjustment()
     Tjw_ref[15] = 1;
     const double pose_scale = 10.0, inv_scale = 1.0 / pose_scale;
     // packing buffers live in the object: a few MB that would otherwise be mmap'ed, page-faulted and unmapped per keyframe
-    std::vector<int> &lms = lba_lms_, &obs_ptr = lba_obs_ptr_, &obs_frame = lba_obs_frame_;
     std::vector<uint8_t> &obs_right = lba_obs_right_;
     std::vector<double> &points = lba_points_, &obs_px = lba_obs_px_;
-    lms.clear(); obs_ptr.assign(1, 0); obs_frame.clear(); obs_right.clear(); points.clear(); obs_px.clear();
-    for (int id : lmset) {
-        // one pass: append the window observations, roll back if the landmark has fewer than two (THRES_MINIMUM_SEEN)
-        const size_t o0 = obs_frame.size();
-        for (const KfObs &o : lm_kf_obs_[id]) {
-            const int fk = fidx_of(o.kf_id);
-            if (fk < 0) continue;
-            obs_frame.push_back(fk); obs_right.push_back(o.right);
-            obs_px.push_back(o.x); obs_px.push_back(o.y);
+    obs_frame.resize(n_obs); obs_right.resize(n_obs); obs_px.resize((size_t)2 * n_obs); points.resize((size_t)3 * n_lm);
+    // 2) observations: keyframes in chronological order, left then right -- the order Landmark::related_keyframes_ /
+    //    observations_on_keyframes_ have in the reference (landmark.cpp:105-124)
+    for (int k = 0; k < nf; ++k) {
+        const FrameRec &fr = *window_[k];
+        const size_t n = fr.lm_ids.size();
+        for (size_t i = 0; i < n; ++i) {
+            const int id = fr.lm_ids[i];
+            if (!lm_tri_[id] || !lm_alive_[id]) continue;
+            const int o = cursor[lm_lba_slot_[id]];
+            cursor[lm_lba_slot_[id]] = o + 2;
+            obs_frame[o] = k; obs_frame[o + 1] = k;
+            obs_right[o] = 0; obs_right[o + 1] = 1;
+            obs_px[2 * (size_t)o] = fr.pts_l[2 * i]; obs_px[2 * (size_t)o + 1] = fr.pts_l[2 * i + 1];
+            obs_px[2 * (size_t)o + 2] = fr.pts_r[2 * i]; obs_px[2 * (size_t)o + 3] = fr.pts_r[2 * i + 1];
         }
-        if (obs_frame.size() - o0 < 2) { obs_frame.resize(o0); obs_right.resize(o0); obs_px.resize(2 * o0); continue; }
+    }
+    for (int j = 0; j < n_lm; ++j) {
+        const int id = lms[j];
         const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
         for (int r = 0; r < 3; ++r)
-            points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
-        lms.push_back(id);
-        obs_ptr.push_back((int)obs_frame.size());
+            points[3 * (size_t)j + r] = (Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale;
     }
-    if (lms.empty()) return;
     std::vector<double> poses((size_t)nf * 16);
     for (int k = 0; k < nf; ++k) {
         double Tjw[16];
@@ -324,8 +343,10 @@ void StereoVO::pushStats(const FrameRec &f, bool keyframe)
                 for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)nk.lm_ids[i] * 3 + r];
             for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_keyframe[kf->kf_index].Twc);
             for (int id : dirty_)
-                for (const KfSlot &sl : lm_kf_slots_[id])
+                for (int e = lm_slot_head_[id]; e >= 0; e = kf_slot_pool_[e].next) {
+                    const KfSlot &sl = kf_slot_pool_[e];
                     for (int r = 0; r < 3; ++r) stat_.stats_keyframe[sl.kf_index].mappoints[sl.slot](r) = lm_X_[(size_t)id * 3 + r];
+                }
         }
         dirty_.clear();              // points that change on a non-keyframe (first-frame / initial reconstruction) wait for the next keyframe
     }

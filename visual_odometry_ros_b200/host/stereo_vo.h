@@ -104,7 +104,6 @@ public:
     bool statsConsistent() const;       // stats_keyframe equals the reference's full refresh (test hook)
 
 private:
-    struct KfObs { int kf_id; uint8_t right; float x, y; };
     struct FrameRec {
         int id = 0;
         int kf_index = -1;                  // position in all_keyframes_ / stats_keyframe
@@ -133,14 +132,16 @@ private:
     std::vector<float> lm_X_;
     std::vector<uint8_t> lm_tri_, lm_alive_, lm_bundled_;
     std::vector<int> lm_last_frame_;
-    std::vector<std::vector<KfObs>> lm_kf_obs_;
     // where a landmark's point sits in stats_keyframe[k].mappoints, and the landmarks whose point changed in this frame:
     // the per-keyframe refresh of the reference (all keyframes x all their points, every keyframe) becomes incremental
-    struct KfSlot { int kf_index, slot; };
-    std::vector<std::vector<KfSlot>> lm_kf_slots_;
+    // (a singly linked list per landmark in one flat pool: appending is two sequential stores and one head update instead of a
+    // push_back into one of half a million small vectors)
+    struct KfSlot { int kf_index, slot, next; };
+    std::vector<KfSlot> kf_slot_pool_;
+    std::vector<int> lm_slot_head_;          // landmark -> newest pool entry, -1 = none
     std::vector<int> dirty_;
     // local-BA packing scratch (kept across keyframes)
-    std::vector<int> lm_seen_stamp_, lba_lmset_, lba_lms_, lba_obs_ptr_, lba_obs_frame_;
+    std::vector<int> lm_seen_stamp_, lm_lba_slot_, lba_lms_, lba_obs_ptr_, lba_obs_cursor_, lba_obs_frame_;
     std::vector<uint8_t> lba_obs_right_;
     std::vector<double> lba_points_, lba_obs_px_, lba_poses_out_, lba_points_out_;
     int seen_stamp_ = 0;
