@@ -75,7 +75,8 @@ void MonoVO::init()
         lm_X_.reserve(cap * 3); lm_first_px_.reserve(cap * 2); lm_last_px_.reserve(cap * 2); lm_last_parallax_.reserve(cap);
         lm_tri_.reserve(cap); lm_alive_.reserve(cap); lm_bundled_.reserve(cap);
         lm_last_frame_.reserve(cap); lm_first_frame_.reserve(cap); lm_age_.reserve(cap);
-        lm_kf_obs_.reserve(cap); lm_kf_slots_.reserve(cap); lm_seen_stamp_.reserve(cap);
+        lm_kf_count_.reserve(cap); lm_kf_first_id_.reserve(cap); lm_kf_first_px_.reserve(2 * cap); lm_kf_last_px_.reserve(2 * cap);
+        lm_slot_head_.reserve(cap); lm_seen_stamp_.reserve(cap); lm_lba_slot_.reserve(cap); kf_slot_pool_.reserve(cap);
         frames_.reserve(1 << 16);
     }
     {   // allocate the five-point scratch and load its kernels now, not inside the initialisation frame
@@ -126,8 +127,8 @@ int MonoVO::newLandmarks(int k, const float *pts, const FrameRec &f)
     lm_first_px_.resize(n * 2); lm_last_px_.resize(n * 2);
     memcpy(&lm_first_px_[(size_t)base * 2], pts, (size_t)k * 8);
     memcpy(&lm_last_px_[(size_t)base * 2], pts, (size_t)k * 8);
-    lm_kf_obs_.resize(n);
-    lm_kf_slots_.resize(n);
+    lm_kf_count_.resize(n, 0); lm_kf_first_id_.resize(n, -1); lm_kf_first_px_.resize(n * 2, 0.f); lm_kf_last_px_.resize(n * 2, 0.f);
+    lm_slot_head_.resize(n, -1);
     return base;
 }
 
@@ -183,14 +184,19 @@ void MonoVO::addKeyframe(const FrameRecPtr &f)
     all_keyframes_.push_back(f);
     if ((int)window_.size() == p_.n_max_keyframes_in_window) window_.pop_front();
     window_.push_back(f);
-    for (int id : f->lm_ids) {
-        auto &v = lm_kf_obs_[id];
-        if (v.empty()) { v.reserve(4); lm_kf_slots_[id].reserve(4); }              // one allocation instead of the 1-2-4 growth
-        v.push_back({f->id, lm_last_px_[2 * (size_t)id], lm_last_px_[2 * (size_t)id + 1]});   // observations.back()
-    }
+    const size_t n = f->lm_ids.size();
     const int kf_index = (int)all_keyframes_.size() - 1;
     f->kf_index = kf_index;
-    for (size_t i = 0; i < f->lm_ids.size(); ++i) lm_kf_slots_[f->lm_ids[i]].push_back({kf_index, (int)i});
+    f->kf_px.resize(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+        const int id = f->lm_ids[i];
+        const float x = lm_last_px_[2 * (size_t)id], y = lm_last_px_[2 * (size_t)id + 1];     // observations.back()
+        f->kf_px[2 * i] = x; f->kf_px[2 * i + 1] = y;
+        if (lm_kf_count_[id]++ == 0) { lm_kf_first_id_[id] = f->id; lm_kf_first_px_[2 * (size_t)id] = x; lm_kf_first_px_[2 * (size_t)id + 1] = y; }
+        lm_kf_last_px_[2 * (size_t)id] = x; lm_kf_last_px_[2 * (size_t)id + 1] = y;
+        kf_slot_pool_.push_back({kf_index, (int)i, lm_slot_head_[id]});
+        lm_slot_head_[id] = (int)kf_slot_pool_.size() - 1;
+    }
 }
 
 // triangulateDLT of the candidates, one device call per distinct frame of the first point (T10 = T1w * Tw0)
@@ -259,10 +265,10 @@ int MonoVO::reconstructKeyframe(const FrameRec &f)
     std::vector<int> cand, f0;
     std::vector<float> pt0, pt1, X0, X1;
     for (int id : f.lm_ids)
-        if (lm_alive_[id] && !lm_tri_[id] && lm_last_parallax_[id] >= thr && lm_kf_obs_[id].size() > 2) {
-            const KfObs &a = lm_kf_obs_[id].front(), &b = lm_kf_obs_[id].back();
-            cand.push_back(id); f0.push_back(a.kf_id);
-            pt0.push_back(a.x); pt0.push_back(a.y); pt1.push_back(b.x); pt1.push_back(b.y);
+        if (lm_alive_[id] && !lm_tri_[id] && lm_last_parallax_[id] >= thr && lm_kf_count_[id] > 2) {
+            cand.push_back(id); f0.push_back(lm_kf_first_id_[id]);
+            pt0.push_back(lm_kf_first_px_[2 * (size_t)id]); pt0.push_back(lm_kf_first_px_[2 * (size_t)id + 1]);
+            pt1.push_back(lm_kf_last_px_[2 * (size_t)id]); pt1.push_back(lm_kf_last_px_[2 * (size_t)id + 1]);
         }
     if (cand.empty()) return 0;
     dltGroups(cand, pt0, pt1, f0, f, X0, X1);
@@ -292,20 +298,41 @@ void MonoVO::localBundleAdjustment()
     if ((int)window_.size() < NUM_MINIMUM_REQUIRED_KEYFRAMES) return;
     const auto t_pack = Clock::now();
     const int nf = (int)window_.size();
-    const int id0 = window_.front()->id;
-    std::vector<int> fidx_tab((size_t)(window_.back()->id - id0 + 1), -1);
-    for (int k = 0; k < nf; ++k) fidx_tab[window_[k]->id - id0] = k;
-    auto fidx_of = [&](int kf_id) { const int r = kf_id - id0; return (r >= 0 && r < (int)fidx_tab.size()) ? fidx_tab[r] : -1; };
-    std::vector<int> &lmset = lba_lmset_;
-    lmset.clear();
+    // 1) alive + triangulated landmarks of the window in first-seen order with their observation counts, straight from the
+    //    window keyframes' own arrays (every keyframe lists each of its landmarks once)
+    std::vector<int> &cand = lba_cand_, &cnt = lba_cnt_, &lms = lba_lms_, &obs_ptr = lba_obs_ptr_, &cursor = lba_obs_cursor_, &obs_frame = lba_obs_frame_;
+    cand.clear(); cnt.clear();
     {
         // stamp instead of a cleared flag array: no O(all landmarks) memset per keyframe
         lm_seen_stamp_.resize(lm_tri_.size(), 0);
+        lm_lba_slot_.resize(lm_tri_.size(), 0);
         const int stamp = ++seen_stamp_;
         for (const auto &fr : window_)
-            for (int id : fr->lm_ids)
-                if (lm_seen_stamp_[id] != stamp && lm_tri_[id] && lm_alive_[id]) { lm_seen_stamp_[id] = stamp; lmset.push_back(id); }
+            for (int id : fr->lm_ids) {
+                if (!lm_tri_[id] || !lm_alive_[id]) continue;
+                if (lm_seen_stamp_[id] != stamp) {
+                    lm_seen_stamp_[id] = stamp;
+                    lm_lba_slot_[id] = (int)cand.size();
+                    cand.push_back(id);
+                    cnt.push_back(0);
+                }
+                ++cnt[lm_lba_slot_[id]];
+            }
     }
+    // THRES_MINIMUM_SEEN: fewer than two window observations -> not a BA landmark
+    lms.clear(); obs_ptr.clear();
+    int n_obs = 0;
+    for (size_t j = 0; j < cand.size(); ++j) {
+        if (cnt[j] < 2) { lm_lba_slot_[cand[j]] = -1; continue; }
+        lm_lba_slot_[cand[j]] = (int)lms.size();
+        lms.push_back(cand[j]);
+        obs_ptr.push_back(n_obs);
+        n_obs += cnt[j];
+    }
+    if (lms.empty()) return;
+    const int n_lm = (int)lms.size();
+    obs_ptr.push_back(n_obs);
+    cursor.assign(obs_ptr.begin(), obs_ptr.begin() + n_lm);
     double Twj_ref[16], Tjw_ref[16];
     for (int i = 0; i < 12; ++i) Twj_ref[i] = window_[0]->Twc[i];
     Twj_ref[12] = Twj_ref[13] = Twj_ref[14] = 0; Twj_ref[15] = 1;
@@ -318,26 +345,28 @@ void MonoVO::localBundleAdjustment()
     Tjw_ref[15] = 1;
     const double pose_scale = 10.0, inv_scale = 1.0 / pose_scale;
     // packing buffers live in the object: a few MB that would otherwise be mmap'ed, page-faulted and unmapped per keyframe
-    std::vector<int> &lms = lba_lms_, &obs_ptr = lba_obs_ptr_, &obs_frame = lba_obs_frame_;
     std::vector<double> &points = lba_points_, &obs_px = lba_obs_px_;
-    lms.clear(); obs_ptr.assign(1, 0); obs_frame.clear(); points.clear(); obs_px.clear();
-    for (int id : lmset) {
-        // one pass: append the window observations, roll back if the landmark has fewer than two (THRES_MINIMUM_SEEN)
-        const size_t o0 = obs_frame.size();
-        for (const KfObs &o : lm_kf_obs_[id]) {
-            const int fk = fidx_of(o.kf_id);
-            if (fk < 0) continue;
-            obs_frame.push_back(fk);
-            obs_px.push_back(o.x); obs_px.push_back(o.y);
+    obs_frame.resize(n_obs); obs_px.resize((size_t)2 * n_obs); points.resize((size_t)3 * n_lm);
+    // 2) observations: keyframes in chronological order (landmark.cpp:105-124)
+    for (int k = 0; k < nf; ++k) {
+        const FrameRec &fr = *window_[k];
+        const size_t n = fr.lm_ids.size();
+        for (size_t i = 0; i < n; ++i) {
+            const int id = fr.lm_ids[i];
+            if (!lm_tri_[id] || !lm_alive_[id]) continue;
+            const int s = lm_lba_slot_[id];
+            if (s < 0) continue;
+            const int o = cursor[s]++;
+            obs_frame[o] = k;
+            obs_px[2 * (size_t)o] = fr.kf_px[2 * i]; obs_px[2 * (size_t)o + 1] = fr.kf_px[2 * i + 1];
         }
-        if (obs_frame.size() - o0 < 2) { obs_frame.resize(o0); obs_px.resize(2 * o0); continue; }
+    }
+    for (int j = 0; j < n_lm; ++j) {
+        const int id = lms[j];
         const double Xw[3] = {lm_X_[(size_t)id * 3], lm_X_[(size_t)id * 3 + 1], lm_X_[(size_t)id * 3 + 2]};
         for (int r = 0; r < 3; ++r)
-            points.push_back((Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale);
-        lms.push_back(id);
-        obs_ptr.push_back((int)obs_frame.size());
+            points[3 * (size_t)j + r] = (Tjw_ref[r * 4] * Xw[0] + Tjw_ref[r * 4 + 1] * Xw[1] + Tjw_ref[r * 4 + 2] * Xw[2] + Tjw_ref[r * 4 + 3]) * inv_scale;
     }
-    if (lms.empty()) return;
     std::vector<uint8_t> &obs_right = lba_obs_right_;
     obs_right.assign(obs_frame.size(), 0);
     std::vector<double> poses((size_t)nf * 16);
@@ -417,8 +446,10 @@ void MonoVO::pushStats(const FrameRec &f, bool keyframe)
                 for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)nk.lm_ids[i] * 3 + r];
             for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_keyframe[kf->kf_index].Twc);
             for (int id : dirty_)
-                for (const KfSlot &sl : lm_kf_slots_[id])
+                for (int e = lm_slot_head_[id]; e >= 0; e = kf_slot_pool_[e].next) {
+                    const KfSlot &sl = kf_slot_pool_[e];
                     for (int r = 0; r < 3; ++r) stat_.stats_keyframe[sl.kf_index].mappoints[sl.slot](r) = lm_X_[(size_t)id * 3 + r];
+                }
         }
         dirty_.clear();              // points that change on a non-keyframe (first-frame / initial reconstruction) wait for the next keyframe
     }

@@ -107,7 +107,6 @@ public:
     bool statsConsistent() const;       // stats_keyframe equals the reference's full refresh (test hook)
 
 private:
-    struct KfObs { int kf_id; float x, y; };
     struct FrameRec {
         int id = 0;
         int kf_index = -1;                  // position in all_keyframes_ / stats_keyframe
@@ -115,6 +114,7 @@ private:
         float Twc[16], Tcw[16], dT01[16], dT10[16];
         std::vector<float> pts;             // interleaved x, y (dropped once the frame is neither previous nor a keyframe)
         std::vector<int> lm_ids;
+        std::vector<float> kf_px;           // keyframes: the landmarks' observations.back() at the time the keyframe was added
     };
     using FrameRecPtr = std::shared_ptr<FrameRec>;
 
@@ -142,14 +142,19 @@ private:
     std::vector<float> lm_X_, lm_first_px_, lm_last_px_, lm_last_parallax_;
     std::vector<uint8_t> lm_tri_, lm_alive_, lm_bundled_;
     std::vector<int> lm_last_frame_, lm_first_frame_, lm_age_;
-    std::vector<std::vector<KfObs>> lm_kf_obs_;
+    // keyframe observations of a landmark: what the path reads is the first one, the last one and how many (mono_vo.cpp:1032-1050);
+    // the window's observations for the local BA come from the window keyframes' own arrays
+    std::vector<int> lm_kf_count_, lm_kf_first_id_;
+    std::vector<float> lm_kf_first_px_, lm_kf_last_px_;
     // where a landmark's point sits in stats_keyframe[k].mappoints, and the landmarks whose point changed in this frame:
     // the per-keyframe refresh of the reference (all keyframes x all their points, every keyframe) becomes incremental
-    struct KfSlot { int kf_index, slot; };
-    std::vector<std::vector<KfSlot>> lm_kf_slots_;
+    // (a singly linked list per landmark in one flat pool instead of one small vector per landmark)
+    struct KfSlot { int kf_index, slot, next; };
+    std::vector<KfSlot> kf_slot_pool_;
+    std::vector<int> lm_slot_head_;          // landmark -> newest pool entry, -1 = none
     std::vector<int> dirty_;
     // local-BA packing scratch (kept across keyframes)
-    std::vector<int> lm_seen_stamp_, lba_lmset_, lba_lms_, lba_obs_ptr_, lba_obs_frame_;
+    std::vector<int> lm_seen_stamp_, lm_lba_slot_, lba_cand_, lba_cnt_, lba_lms_, lba_obs_ptr_, lba_obs_cursor_, lba_obs_frame_;
     std::vector<uint8_t> lba_obs_right_;
     std::vector<double> lba_points_, lba_obs_px_, lba_poses_out_, lba_points_out_;
     int seen_stamp_ = 0;
