@@ -543,19 +543,26 @@ __global__ void __launch_bounds__(256) k_lba_reduce(const LbaDev d)
 // retraction.  Round 1 factorised S in shared memory: 48 steps of {pivot search, swap, scale, trailing update}, four
 // block barriers and a shared-memory read-modify-write of the whole trailing triangle per step -- 98 k cycles per LM
 // iteration (VO_LBA_TRACE), the longest stage of the local BA.  Here the matrix lives in REGISTERS: the CTA is a 16 x 16
-// thread grid (8 x 8 for n <= 48, i.e. the reference's window of 8 optimised keyframes: two warps, 36 independent updates
-// per thread; 16 x 16 up to n = 96), thread (ty, tx) owns the 6 x 6 block of rows ty*6.. and columns tx*6.. of the FULL
-// symmetric matrix.  A first version with 3 x 3 blocks on 256 threads needed 367 warp-instructions per step and warp, most
-// of them predicate / select bookkeeping, on 2 warps per scheduler (profiles/r2_lba_solve_*): latency-bound, no faster than
-// the shared-memory version.  Now the column owners publish l = L(:,p) and t = D_p l with zeros for eliminated rows, so the
-// update of every element is an unconditional A -= u * v whose operands' roles are fixed per thread.  Nothing is ever
-// swapped: diagonal pivoting only chooses the ORDER of elimination, so step k eliminates original index p_k in place --
-// the pivot column is broadcast through 16*B doubles of shared memory, every thread updates its own registers
-// (A(i,j) -= L(i,p) * (D_p L(j,p)), the same products as Eigen's unblocked LDLT), two block barriers per step.  The
-// pivot rule is Eigen's (largest remaining |diagonal|, FIRST POSITION on ties): a position -> index table mirrors the
-// row/column transpositions Eigen would have made, and every warp evaluates it redundantly so no barrier is needed to
-// publish the choice.  The triangular solves then run on one warp over the factor parked in shared memory, in original
-// index order (no permutation of the right-hand side).
+// thread grid, thread (ty, tx) owns the B x B block of rows ty*B.. and columns tx*B.. of the FULL symmetric matrix (B = 3
+// for n <= 48, i.e. the reference's window of 8 optimised keyframes; B = 6 up to n = 96).  Nothing is ever swapped:
+// diagonal pivoting only chooses the ORDER of elimination, so step k eliminates original index p_k in place.  A step:
+//   1. every warp holds the whole diagonal and a position table in registers (lane = index mod 32) and finds Eigen's pivot
+//      (largest remaining |diagonal|, FIRST POSITION on ties -- the table mirrors the transpositions Eigen would have made)
+//      with one redux on the leading 32 bits; only if two lanes tie there do the second redux and the position redux run.
+//      The lane-local candidate's reciprocal is computed in the shadow of the reduction and shuffled with the pivot.
+//   2. the owners of column p publish l = L(:,p) and t = D_p l (double-buffered by step parity) and park the factor column;
+//      the pivot's row and column are set to ZERO in the registers, so every later update is an unconditional
+//      A -= u * v with no liveness masks (the in-block column index is a warp-uniform switch: registers cannot be indexed).
+//   3. ONE named barrier, then every thread updates its own registers (A(i,j) -= L(i,p) * (D_p L(j,p)), the products of
+//      Eigen's unblocked LDLT, fused) and its copy of the diagonal.
+// History (VO_LBA_TRACE cycles of the factorisation at n = 48): shared-memory version 98 k; 6 x 6 register blocks on two
+// warps with a shared diagonal / position table and two barriers per step 72 k; register-resident search, one barrier 56 k;
+// zeroed retired rows instead of masks, fused updates 51 k; 3 x 3 blocks on eight warps + single-redux search 51 k.
+// What a step costs now (ablation with the pieces switched off, tools/probe notes in DESIGN.md): ~550 cycles of dependent
+// register / shuffle work (select, redux, ballot, shuffle, reciprocal, scale: ~7 cycles per dependent ALU operation with one
+// or two warps per scheduler), ~200 for the barrier, ~110 for the column switch, ~170 for the shared-memory round trip.
+// The triangular solves then run on one warp over the factor parked in shared memory, in original index order (no
+// permutation of the right-hand side).
 #define SOLVE_G 16
 
 // S, rhs, Aj in shared memory from the reduced tile sums (d.red), exactly as sparse_bundle_adjustment.cpp:456-531 leaves them
@@ -604,6 +611,19 @@ __device__ __forceinline__ void lba_assemble(const LbaDev &d, double *S, const i
 #undef SM
 }
 
+__device__ __forceinline__ unsigned redux_max_u32(unsigned v)
+{
+    unsigned r;
+    asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ int redux_min_s32(int v)
+{
+    int r;
+    asm volatile("redux.sync.min.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 // One elimination step's column work with the pivot's in-block column PA known at compile time (register arrays cannot be
 // indexed dynamically; the caller switches on the warp-uniform value).  Owners of column p (tx == pb) publish
 // L(:,p) = A(:,p) * rk and D_p L(:,p), park the factor column, and retire the column; owners of row p (ty == pb) retire the
@@ -621,11 +641,15 @@ __device__ __forceinline__ void ldlt_column_step(double (&A)[B][B], bool col_own
             t[a] = akk * l[a];
             A[a][PA] = 0.0;
         }
-        static_assert(B % 2 == 0, "vector stores below");
+        if constexpr (B % 2 == 0) {
 #pragma unroll
-        for (int h = 0; h < B / 2; ++h) {
-            reinterpret_cast<double2 *>(l_rows)[h] = make_double2(l[2 * h], l[2 * h + 1]);
-            reinterpret_cast<double2 *>(t_rows)[h] = make_double2(t[2 * h], t[2 * h + 1]);
+            for (int h = 0; h < B / 2; ++h) {
+                reinterpret_cast<double2 *>(l_rows)[h] = make_double2(l[2 * h], l[2 * h + 1]);
+                reinterpret_cast<double2 *>(t_rows)[h] = make_double2(t[2 * h], t[2 * h + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < B; ++a) { l_rows[a] = l[a]; t_rows[a] = t[a]; }
         }
 #pragma unroll
         for (int a = 0; a < B; ++a) S_col[(size_t)a * LD] = l[a];           // rows eliminated earlier store a zero nobody reads
@@ -702,44 +726,68 @@ k_lba_solve(const LbaDev d, int iter)
             // ---- pivot of step k: largest |diagonal| among the live indices, first POSITION on ties (every active warp).
             // Keys are the bit patterns of |d| (monotonic for non-negative doubles); eliminated / padding / NaN entries and
             // exact zeros carry key 0 and never win -- if nothing wins the pivot is the index at position k, as in Eigen.
-            int big_pos;
-            {
-                unsigned long long bk = 0ull;
-                int bp = 0x7fffffff;
+            // lane-local candidate (value key, position, which of the lane's entries) ...
+            unsigned long long bk = 0ull;
+            int bp = 0x7fffffff, bq = 0;
+            double bd = dg[0];
 #pragma unroll
-                for (int q = 0; q < NPS; ++q) {
-                    const double v = fabs(dg[q]);
-                    const unsigned long long key = (pos[q] >= 0 && v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;
-                    if (key > bk || (key == bk && key != 0ull && pos[q] < bp)) { bk = key; bp = pos[q]; }
-                }
-                const unsigned hi = (unsigned)(bk >> 32);
-                const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-                const unsigned lo = (hi == mhi) ? (unsigned)bk : 0u;
-                const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
-                const bool win = bk != 0ull && hi == mhi && (unsigned)bk == mlo;
-                big_pos = __reduce_min_sync(0xffffffffu, win ? bp : 0x7fffffff);
-                if (big_pos == 0x7fffffff) big_pos = k;
+            for (int q = 0; q < NPS; ++q) {
+                const double v = fabs(dg[q]);
+                const unsigned long long key = (pos[q] >= 0 && v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;
+                const bool take = key > bk || (key == bk && key != 0ull && pos[q] < bp);
+                bk = take ? key : bk;
+                bp = take ? pos[q] : bp;
+                bq = take ? q : bq;
+                bd = take ? dg[q] : bd;
             }
-            int my_q = -1;
+            // ... and its reciprocal, started now so that it runs in the shadow of the warp reductions: two Newton steps and a
+            // final correction on the hardware approximation (within one ulp of the quotient Eigen forms; no slow-path call)
+            double br;
+            {
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(br) : "d"(bd));
+                double e = __fma_rn(-bd, br, 1.0);
+                br = __fma_rn(br, e, br);
+                e = __fma_rn(-bd, br, 1.0);
+                br = __fma_rn(br, e, br);
+                e = __fma_rn(-bd, br, 1.0);
+                br = __fma_rn(br, e, br);
+            }
+            const unsigned hi = (unsigned)(bk >> 32);
+            const unsigned mhi = redux_max_u32(hi);
+            unsigned owners = __ballot_sync(0xffffffffu, bk != 0ull && hi == mhi);
+            if (__popc(owners) != 1) {
+                // rare: several lanes share the leading 32 bits, or nothing is comparable (all zero / NaN: Eigen keeps position k)
+                const unsigned lo = (bk != 0ull && hi == mhi) ? (unsigned)bk : 0u;
+                const unsigned mlo = redux_max_u32(lo);
+                const bool win = bk != 0ull && hi == mhi && (unsigned)bk == mlo;
+                int big = redux_min_s32(win ? bp : 0x7fffffff);
+                big = big == 0x7fffffff ? k : big;
+                int my_q = -1;
 #pragma unroll
-            for (int q = 0; q < NPS; ++q)
-                if (pos[q] == big_pos) my_q = q;
-            const int src = __ffs(__ballot_sync(0xffffffffu, my_q >= 0)) - 1;
-            double sel = dg[0];
+                for (int q = 0; q < NPS; ++q) my_q = (pos[q] == big) ? q : my_q;
+                owners = __ballot_sync(0xffffffffu, my_q >= 0);
+                if (my_q >= 0 && (my_q != bq || bp != big)) {          // the owner's entry is not its lane-local candidate
+                    bq = my_q; bp = big;
+                    bd = dg[0];
 #pragma unroll
-            for (int q = 1; q < NPS; ++q) sel = (my_q == q) ? dg[q] : sel;
-            const int p = __shfl_sync(0xffffffffu, lane + 32 * (my_q > 0 ? my_q : 0), src);
-            const double akk = __shfl_sync(0xffffffffu, sel, src);
+                    for (int q = 1; q < NPS; ++q) bd = (my_q == q) ? dg[q] : bd;
+                    br = 1.0 / bd;
+                }
+            }
+            const int src = __ffs(owners) - 1;
+            const int p = __shfl_sync(0xffffffffu, lane + 32 * bq, src);
+            const int big_pos = __shfl_sync(0xffffffffu, bp, src);
+            const double akk = __shfl_sync(0xffffffffu, bd, src);
+            const double rcp_akk = __shfl_sync(0xffffffffu, br, src);
             // the transposition: the pivot leaves the table, the index that sat at position k takes the pivot's old position
 #pragma unroll
             for (int q = 0; q < NPS; ++q) {
-                if (lane == src && q == my_q) pos[q] = -1;
-                else if (pos[q] == k) pos[q] = big_pos;
+                const int moved = (pos[q] == k) ? big_pos : pos[q];
+                pos[q] = (lane == src && q == bq) ? -1 : moved;
             }
             const int pb = p / B, pa = p - pb * B;
-            // L(:,p) = A(:,p) * (1 / D_p) (correctly rounded reciprocal; may differ from Eigen's quotient by one ulp); Eigen leaves
-            // the column unscaled at the last step and for an exactly zero pivot: factor 1
-            const double rk = ((k < n - 1) && fabs(akk) > 0.0) ? __drcp_rn(akk) : 1.0;
+            // L(:,p) = A(:,p) * (1 / D_p).  Eigen leaves the column unscaled at the last step and for an exactly zero pivot: factor 1
+            const double rk = ((k < n - 1) && fabs(akk) > 0.0) ? rcp_akk : 1.0;
             double *bl = s_lt + (k & 1) * NP, *bt = bl + 2 * NP;
             {
                 const bool co = tx == pb, ro = ty == pb;
@@ -748,9 +796,9 @@ k_lba_solve(const LbaDev d, int iter)
                 case 0: ldlt_column_step<B, 0>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
                 case 1: ldlt_column_step<B, 1>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
                 case 2: ldlt_column_step<B, 2>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
-                case 3: ldlt_column_step<B, 3>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
-                case 4: ldlt_column_step<B, 4>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
-                default: ldlt_column_step<B, 5>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                case 3: ldlt_column_step<B, (3 < B ? 3 : 0)>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                case 4: ldlt_column_step<B, (4 < B ? 4 : 0)>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
+                default: ldlt_column_step<B, (5 < B ? 5 : 0)>(A, co, ro, rk, akk, lr, tr, sc, LD); break;
                 }
             }
             if (tid == 0) { s_piv[k] = p; s_step[p] = k; s_D[p] = akk; }
@@ -1036,8 +1084,8 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     VO_REQUIRE(TL >= 1, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
     const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
     const size_t smem_build = fixed + per_lm * TL;
-    const int solve_G = n6 <= 48 ? 8 : 16;     // k_lba_solve<G, 6>: G x G threads own 6 x 6 register blocks
-    const int solve_NP = solve_G * 6;
+    const int solve_B = n6 <= 48 ? 3 : 6;      // k_lba_solve<16, B>: 16 x 16 threads own B x B register blocks
+    const int solve_NP = 16 * solve_B;
     const size_t smem_solve = ((size_t)solve_NP * (solve_NP + 1) + solve_NP + (size_t)No * LBA_NA) * 8;
 
     // device scratch (one allocation, grow-only)
@@ -1106,7 +1154,7 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
             cudaError_t e = cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve<16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
             cudaFuncSetAttribute(k_lba_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_lba_solve<8, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_solve<16, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_solve<16, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_update_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr_err = e;
@@ -1125,7 +1173,7 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
             if (nrc != 0) { ctx->last_error = std::string("ncclAllReduce: ") + (nccl_api().GetErrorString ? nccl_api().GetErrorString(nrc) : "error"); return VO_ERR_CUDA; }
         }
         if (trace) cudaEventRecord(evs[2 * it + 1], ctx->stream);
-        if (solve_G == 8) k_lba_solve<8, 6><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
+        if (solve_B == 3) k_lba_solve<16, 3><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
         else k_lba_solve<16, 6><<<1, LBA_THREADS, smem_solve, ctx->stream>>>(d, it);
         if (trace) cudaEventRecord(evs[2 * it + 2], ctx->stream);
         ctx->launches += 3;
