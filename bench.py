@@ -723,6 +723,7 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                                    "4 levels, win 21) [+ trackWithScale] + stereo pose GN + compactions, wall clock incl. all "
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
     res["sequence"] = sequence_measurement(torch, dev, synth, n_frames=cfg3_frames)
+    res["sequence_strict_pose"] = sequence_measurement(torch, dev, synth, n_frames=min(cfg3_frames, 300), n_cpu=0, with_concurrent=False, pose_strict=True)
     res["mono_sequence"] = mono_sequence_measurement(torch, dev, synth)
     res["sequence_orb"] = sequence_measurement(torch, dev, synth, n_frames=60, n_cpu=6, detector="orb", with_concurrent=False)
     res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
@@ -831,7 +832,7 @@ def cfg4_measurement(ctx, synth):
             "what": "vo_lba_solve / vo_depth_filter_normal with host buffers, wall clock incl. H2D/D2H and the sync"}
 
 
-def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="harris", with_concurrent=True):
+def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="harris", with_concurrent=True, pose_strict=False):
     """BASELINE config 3: the full stereo VO step over a synthetic KITTI-like sequence through the reference-API class
     (host images in, pose out; tracking + new features every frame, reconstruction + local BA on keyframes)."""
     from oracle import stereo_vo as osvo
@@ -842,7 +843,7 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
     Lp, Rp = torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()
     # warm-up instance: first use of every kernel (lazy module loading), first pinned / device allocations
     mk = lambda: svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv,
-                                                  detector=detector, thres_fastscore=20))
+                                                  detector=detector, thres_fastscore=20, pose_strict=pose_strict))
     warm = mk()
     for k in range(min(16, n_frames)):
         warm.trackStereoImages(Lp[k], Rp[k], 0.1 * k)
@@ -878,6 +879,8 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
         cms.append((time.perf_counter() - t0) * 1e3)
     conc = concurrent_sequences(svo, Lp, Rp, K4, Tlr, nbu, nbv) if with_concurrent else None
     return {"concurrent_sequences": conc, "detector": "K-det (Harris on the Scharr plane)" if detector == "harris" else "cv::ORB restated (the reference's extractor), FAST threshold 20",
+            "pose_mode": "strict (sequential FP32 sums, the reference's arithmetic bit for bit; what the yaml constructor selects)" if pose_strict
+                         else "fast (FP64 tree sums; the Parameters-struct default)",
             "frames": n_frames, "ms_per_frame_mean": float(ms.mean()), "ms_per_frame_median": float(np.median(ms)),
             "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
             "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None,
@@ -885,7 +888,7 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
             "keyframe_breakdown_ms": {key: float(np.mean(v)) for key, v in parts.items() if v},
             "mean_tracked_features": float(np.mean(nfeat[2:])), "bins": [nbu, nbv], "gpu_launches": int(launches),
             "translation_drift_vs_ground_truth": drift,
-            "cpu_ms_per_frame": float(np.mean(cms[2:])), "cpu_frames": n_cpu, "cpu_cores": os.cpu_count() or 1,
+            "cpu_ms_per_frame": float(np.mean(cms[2:])) if len(cms) > 2 else None, "cpu_frames": n_cpu, "cpu_cores": os.cpu_count() or 1,
             "what": "StereoVO::trackStereoImages drop-in (host u8 images in, pose out): fused frame step (pyramids, prior, 2x trackWithPrior, "
                     "trackWithScale, stereo pose GN, compactions, bucketed detection, bidirectional stereo match of new features) every "
                     "frame; reconstruction + 10-iteration local BA on keyframes; wall clock incl. all copies/syncs and the host "

@@ -204,24 +204,44 @@ __device__ __forceinline__ double wsum(double v)
 //   P     [3*TL][n6]        P[3*il+m][6j+r] = BCinv[j][i](r, m)
 //   Q     [3*TL][n6+1]      Q[3*il+m][6k+c] = B[k][i](c, m) ; Q[3*il+m][n6] = b_i(m)
 //   Aacc  [LBA_BWARPS][n_opt][27]
-//   Btmp  [LBA_BWARPS][n_opt][18]
+//   Btmp  [LBA_BWARPS][NG][n_opt][18]
 //   errw  [LBA_BWARPS]
+// A warp works on NG landmarks at a time, one per group of GS = 32 / NG lanes (lane of the group = observation).  The
+// per-landmark work is one long dependent chain (observation tables -> projection -> divisions -> group sums -> 3 x 3
+// LDLT inverse -> B Cinv); a landmark of the benchmark window has 5 observations on average, so a whole warp per landmark
+// left 27 lanes idle and every warp walked 3+ landmarks one after the other (issue slots 36 % busy, profiles/r2_lba_build_*).
+// With four groups the 16 warps of a tile hold 64 landmarks in flight: one round for a tile of the 7.5 k-landmark window.
+// Only the accumulation into the warp's A_j blocks is serialised over the groups (fixed order: deterministic sums).
+template <int GS>
+__device__ __forceinline__ double gsum(double v)
+{
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NG>
 __global__ void __launch_bounds__(LBA_BTHREADS, 1)
 k_lba_build(const LbaDev d, int apply_update)
 {
-    extern __shared__ double smem[];
+    constexpr int GS = 32 / NG;
+    extern __shared__ __align__(16) double smem[];
     const int n6 = d.n6, No = d.n_opt, TL = d.tile;
     double *P = smem;
     double *Q = P + (size_t)3 * TL * n6;
     double *Aacc = Q + (size_t)3 * TL * (n6 + 1);
     double *Btmp = Aacc + (size_t)LBA_BWARPS * No * LBA_NA;
-    double *errw = Btmp + (size_t)LBA_BWARPS * No * 18;
+    double *errw = Btmp + (size_t)LBA_BWARPS * NG * No * 18;
     double *s_x = errw + LBA_BWARPS;                       // [n6]        the pose update of the previous iteration
     double *s_T = s_x + n6;                                // [N][16]     keyframe poses
     int *s_opt = reinterpret_cast<int *>(s_T + (size_t)16 * d.n_frames);   // [N]  frame -> optimisable index
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_smem = (int)(errw + LBA_BWARPS - smem);
-    for (int i = tid; i < n_smem; i += LBA_BTHREADS) smem[i] = 0.0;
+    {   // zero fill, 16 bytes per store (the panels are dense: keyframes a landmark does not see stay zero)
+        double2 *z = reinterpret_cast<double2 *>(smem);
+        for (int i = tid; i < n_smem / 2; i += LBA_BTHREADS) z[i] = make_double2(0.0, 0.0);
+        if (tid == 0 && (n_smem & 1)) smem[n_smem - 1] = 0.0;
+    }
     // the per-frame tables every observation looks up: once per tile from global memory instead of a dependent L2 round trip
     // (frame -> index -> pose) in each of a landmark's three passes
     for (int i = tid; i < n6; i += LBA_BTHREADS) s_x[i] = apply_update ? d.x[i] : 0.0;
@@ -230,20 +250,25 @@ k_lba_build(const LbaDev d, int apply_update)
     __syncthreads();
 
     const int tile_base = blockIdx.x * TL;
+    const int grp = lane / GS, gl = lane % GS;
     double *myA = Aacc + (size_t)wid * No * LBA_NA;
-    double *myB = Btmp + (size_t)wid * No * 18;
+    double *myB = Btmp + ((size_t)wid * NG + grp) * No * 18;
     double err_w = 0.0;
 
-    for (int il = wid; il < TL; il += LBA_BWARPS) {
+    for (int il0 = wid * NG; il0 < TL; il0 += LBA_BWARPS * NG) {
+        if (tile_base + il0 >= d.n_points) break;                    // warp-uniform: every group is past the end
+        const int il = il0 + grp;
         const int i = tile_base + il;
-        if (i >= d.n_points) break;
-        const int o_beg = d.obs_ptr[i], o_end = d.obs_ptr[i + 1];
-        double Xi[3] = {d.points[3 * i], d.points[3 * i + 1], d.points[3 * i + 2]};
+        const bool valid = il < TL && i < d.n_points;                // this group has a landmark in this round
+        const int o_beg = valid ? d.obs_ptr[i] : 0, o_end = valid ? d.obs_ptr[i + 1] : 0;
+        const int n_chunks = __reduce_max_sync(0xffffffffu, (o_end - o_beg + GS - 1) / GS);      // warp-uniform trip count
+        double Xi[3] = {0.0, 0.0, 1.0};
+        if (valid) { Xi[0] = d.points[3 * i]; Xi[1] = d.points[3 * i + 1]; Xi[2] = d.points[3 * i + 2]; }
 
         // ---- apply the previous iteration's landmark update: X_i += Cinv_b_i - sum_j CinvBt[i][j] x_j
         if (apply_update) {
             double cb[3] = {0, 0, 0};
-            for (int o = o_beg + lane; o < o_end; o += 32) {
+            for (int o = o_beg + gl; o < o_end; o += GS) {
                 if (d.obs_right[o]) continue;
                 const int j = s_opt[d.obs_frame[o]];
                 if (j < 0) continue;
@@ -258,17 +283,17 @@ k_lba_build(const LbaDev d, int apply_update)
             }
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                cb[r] = wsum(cb[r]);
-                Xi[r] += d.cinv_b[3 * i + r] - cb[r];
+                cb[r] = gsum<GS>(cb[r]);
+                if (valid) Xi[r] += d.cinv_b[3 * i + r] - cb[r];
             }
             __syncwarp();
-            if (lane == 0) { d.points[3 * i] = Xi[0]; d.points[3 * i + 1] = Xi[1]; d.points[3 * i + 2] = Xi[2]; }
+            if (gl == 0 && valid) { d.points[3 * i] = Xi[0]; d.points[3 * i + 1] = Xi[1]; d.points[3 * i + 2] = Xi[2]; }
         }
 
         // ---- observations: lane per observation (chunks of 32)
         double Cs[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
-        for (int o0 = o_beg; o0 < o_end; o0 += 32) {
-            const int o = o0 + lane;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int o = o_beg + ch * GS + gl;
             const bool act = o < o_end;
             int j = -1, right = 0;
             double Rij[6], rij[2] = {0, 0}, weight = 1.0, Qm[12];
@@ -346,9 +371,10 @@ k_lba_build(const LbaDev d, int apply_update)
             // A_j / a_j: left-camera lanes first, then right-camera lanes -- within one pass a keyframe
             // occurs at most once per landmark, so the per-warp accumulators see no write conflict
             // and the summation order is fixed.
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                if (act && j >= 0 && right == pass) {
+#pragma unroll 1
+            for (int gp = 0; gp < 2 * NG; ++gp) {
+                const int pass = gp & 1;
+                if (grp == (gp >> 1) && act && j >= 0 && right == pass) {
                     double wa[12];
 #pragma unroll
                     for (int k = 0; k < 12; ++k) wa[k] = weight * Qm[k];
@@ -372,9 +398,9 @@ k_lba_build(const LbaDev d, int apply_update)
             }
             // B[j][i]: last writer (highest observation index) of each optimisable keyframe
             {
-                const int key = (act && j >= 0) ? j : -1 - lane;
-                const unsigned grp = __match_any_sync(0xffffffffu, key);
-                const bool last = act && j >= 0 && (lane == 31 - __clz(grp));
+                const int key = (act && j >= 0) ? grp * LBA_MAX_OPT + j : -1 - lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                const bool last = act && j >= 0 && (lane == 31 - __clz(peers));
                 if (last) {
                     double *Bj = myB + (size_t)j * 18;
 #pragma unroll
@@ -390,9 +416,9 @@ k_lba_build(const LbaDev d, int apply_update)
         {
             double c6[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) c6[k] = wsum(Cs[k]);
+            for (int k = 0; k < 6; ++k) c6[k] = gsum<GS>(Cs[k]);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) b[k] = wsum(bs[k]);
+            for (int k = 0; k < 3; ++k) b[k] = gsum<GS>(bs[k]);
             C[0] = c6[0]; C[1] = c6[1]; C[2] = c6[2]; C[3] = c6[1]; C[4] = c6[3]; C[5] = c6[4]; C[6] = c6[2]; C[7] = c6[4]; C[8] = c6[5];
         }
         C[0] += d.lambda * C[0]; C[4] += d.lambda * C[4]; C[8] += d.lambda * C[8];
@@ -401,12 +427,11 @@ k_lba_build(const LbaDev d, int apply_update)
         double cib[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) cib[r] = (Cinv[r * 3] * b[0] + Cinv[r * 3 + 1] * b[1]) + Cinv[r * 3 + 2] * b[2];
-        if (lane == 0) { d.cinv_b[3 * i] = cib[0]; d.cinv_b[3 * i + 1] = cib[1]; d.cinv_b[3 * i + 2] = cib[2]; }
-        if (lane < 3) Q[(size_t)(3 * il + lane) * (n6 + 1) + n6] = b[lane];
+        if (gl == 0 && valid) { d.cinv_b[3 * i] = cib[0]; d.cinv_b[3 * i + 1] = cib[1]; d.cinv_b[3 * i + 2] = cib[2]; }
+        if (gl < 3 && valid) Q[(size_t)(3 * il + gl) * (n6 + 1) + n6] = b[gl];
         // ---- BCinv for the left-camera observations of optimisable keyframes; stage P and Q
-        for (int o0 = o_beg; o0 < o_end; o0 += 32) {
-            const int o = o0 + lane;
-            if (o < o_end && !d.obs_right[o]) {
+        for (int o = o_beg + gl; o < o_end; o += GS) {
+            if (!d.obs_right[o]) {
                 const int j = s_opt[d.obs_frame[o]];
                 if (j >= 0) {
                     const double *Bj = myB + (size_t)j * 18;
@@ -431,7 +456,7 @@ k_lba_build(const LbaDev d, int apply_update)
         }
         __syncwarp();
         // clear the last-writer scratch for the next landmark of this warp
-        for (int k = lane; k < No * 18; k += 32) myB[k] = 0.0;
+        for (int k = gl; k < No * 18; k += GS) myB[k] = 0.0;
         __syncwarp();
     }
     err_w = wsum(err_w);
@@ -1067,21 +1092,32 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     }
     VO_CUDA(cudaSetDevice(ctx->device));
 
-    // tile size from the shared-memory budget
-    const size_t budget = 200 * 1024;
-    const size_t fixed = ((size_t)LBA_BWARPS * No * (LBA_NA + 18) + LBA_BWARPS + n6 + (size_t)16 * N) * 8 + (size_t)N * 4 + 8;
+    // Tile size and landmarks per warp.  About one tile per SM (more tiles only cost a longer k_lba_reduce); inside a tile
+    // the 16 warps take NG landmarks each per round, so NG is the smallest of {1, 2, 4} that covers the tile in one round --
+    // as far as the shared-memory budget allows (the last-writer scratch grows with NG, the panels with the tile).
+    const size_t budget = 227 * 1024;          // opt-in maximum of dynamic shared memory per CTA on sm_100
     const size_t per_lm = (size_t)3 * (2 * n6 + 1) * 8;
-    VO_REQUIRE(fixed + per_lm <= budget, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
-    int TL = (int)((budget - fixed) / per_lm);
-    if (TL > 64) TL = 64;
-    {   // fill the machine: about one tile per SM (a tile's warps walk their landmarks sequentially, so fewer
-        // landmarks per tile is lower latency; more tiles only cost a longer k_lba_reduce)
-        static int n_sm = 0;
-        if (!n_sm) { cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device); if (n_sm <= 0) n_sm = 148; }
-        const int want = vo_div_up(M > 0 ? M : 1, n_sm);
-        if (want < TL) TL = want;
+    auto fixed_of = [&](int ng) {
+        return ((size_t)LBA_BWARPS * No * LBA_NA + (size_t)LBA_BWARPS * ng * No * 18 + LBA_BWARPS + n6 + (size_t)16 * N) * 8 + (size_t)N * 4 + 8;
+    };
+    VO_REQUIRE(fixed_of(1) + per_lm <= budget, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
+    static int n_sm = 0;
+    if (!n_sm) { cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device); if (n_sm <= 0) n_sm = 148; }
+    int want = vo_div_up(M > 0 ? M : 1, n_sm);
+    if (want > 64) want = 64;
+    int NG = 1, TL = 1;
+    {
+        long best_rounds = -1;
+        for (int ng = 1; ng <= 4; ng *= 2) {
+            if (fixed_of(ng) + per_lm > budget) break;
+            int tl = (int)((budget - fixed_of(ng)) / per_lm);
+            if (tl > want) tl = want;
+            // cost model: waves of tiles over the SMs x rounds per tile (a round is one landmark latency)
+            const long rounds = (long)vo_div_up(vo_div_up(M > 0 ? M : 1, tl), n_sm) * vo_div_up(tl, LBA_BWARPS * ng);
+            if (best_rounds < 0 || rounds < best_rounds) { best_rounds = rounds; NG = ng; TL = tl; }
+        }
     }
-    VO_REQUIRE(TL >= 1, VO_ERR_INVALID_ARG, "window too large for the shared-memory tile");
+    const size_t fixed = fixed_of(NG);
     const int n_tiles = M > 0 ? vo_div_up(M, TL) : 1;
     const size_t smem_build = fixed + per_lm * TL;
     const int solve_B = n6 <= 48 ? 3 : 6;      // k_lba_solve<16, B>: 16 x 16 threads own B x B register blocks
@@ -1151,9 +1187,13 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
         static cudaError_t attr_err = cudaSuccess;
         std::call_once(once, [&]() {
             const size_t max_solve = ((size_t)(SOLVE_G * 6) * (SOLVE_G * 6 + 1) + SOLVE_G * 6 + (size_t)LBA_MAX_OPT * LBA_NA) * 8;
-            cudaError_t e = cudaFuncSetAttribute(k_lba_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            cudaError_t e = cudaFuncSetAttribute(k_lba_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_build<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_build<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lba_solve<16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_solve);
-            cudaFuncSetAttribute(k_lba_build, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_build<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_build<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_lba_build<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_solve<16, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_solve<16, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_lba_update_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1165,7 +1205,9 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     std::vector<cudaEvent_t> evs;
     if (trace) { evs.resize(2 * p->max_iter + 1); for (auto &e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], ctx->stream); }
     for (int it = 0; it < p->max_iter; ++it) {
-        k_lba_build<<<n_tiles, LBA_BTHREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
+        if (NG == 4) k_lba_build<4><<<n_tiles, LBA_BTHREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
+        else if (NG == 2) k_lba_build<2><<<n_tiles, LBA_BTHREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
+        else k_lba_build<1><<<n_tiles, LBA_BTHREADS, smem_build, ctx->stream>>>(d, it > 0 ? 1 : 0);
         k_lba_reduce<<<vo_div_up((n6 * (n6 + 1) + No * LBA_NA + 1) * LBA_RED_G, 256), 256, 0, ctx->stream>>>(d);
         if (dist) {
             // the one exchange step of the path: partial reduced systems of the ranks' landmark shards -> complete system everywhere
@@ -1183,7 +1225,7 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
         for (int it = 0; it < p->max_iter; ++it) {
             float a = 0, b = 0;
             cudaEventElapsedTime(&a, evs[2 * it], evs[2 * it + 1]); cudaEventElapsedTime(&b, evs[2 * it + 1], evs[2 * it + 2]);
-            fprintf(stderr, "lba it %d: build %.1f us, solve %.1f us (tiles %d, smem %zu / %zu)\n", it, a * 1e3f, b * 1e3f, n_tiles, smem_build, smem_solve);
+            fprintf(stderr, "lba it %d: build %.1f us, solve %.1f us (tiles %d x %d landmarks, %d per warp, smem %zu / %zu)\n", it, a * 1e3f, b * 1e3f, n_tiles, TL, NG, smem_build, smem_solve);
         }
         for (auto &e : evs) cudaEventDestroy(e);
         long long st[8];
