@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include <cstring>
+#include <chrono>
 #include <vector>
 
 #define LBA_WARPS 8
@@ -199,6 +200,12 @@ __device__ __forceinline__ double wsum(double v)
     return v;
 }
 
+// frame of observation o, clamped into the window: the host checks the range while the kernels already run
+__device__ __forceinline__ int lba_frame(const LbaDev &d, const int o)
+{
+    return min(max(d.obs_frame[o], 0), d.n_frames - 1);
+}
+
 // ------------------------------------------------------------------ k_lba_build
 // dynamic shared memory layout (doubles):
 //   P     [3*TL][n6]        P[3*il+m][6j+r] = BCinv[j][i](r, m)
@@ -270,7 +277,7 @@ k_lba_build(const LbaDev d, int apply_update)
             double cb[3] = {0, 0, 0};
             for (int o = o_beg + gl; o < o_end; o += GS) {
                 if (d.obs_right[o]) continue;
-                const int j = s_opt[d.obs_frame[o]];
+                const int j = s_opt[lba_frame(d, o)];
                 if (j < 0) continue;
                 const double *BC = d.bcinv + (size_t)o * 18;
 #pragma unroll
@@ -298,7 +305,7 @@ k_lba_build(const LbaDev d, int apply_update)
             int j = -1, right = 0;
             double Rij[6], rij[2] = {0, 0}, weight = 1.0, Qm[12];
             if (act) {
-                const int f = d.obs_frame[o];
+                const int f = lba_frame(d, o);
                 right = d.obs_right[o];
                 j = s_opt[f];
                 const double *T = s_T + 16 * f;
@@ -432,7 +439,7 @@ k_lba_build(const LbaDev d, int apply_update)
         // ---- BCinv for the left-camera observations of optimisable keyframes; stage P and Q
         for (int o = o_beg + gl; o < o_end; o += GS) {
             if (!d.obs_right[o]) {
-                const int j = s_opt[d.obs_frame[o]];
+                const int j = s_opt[lba_frame(d, o)];
                 if (j >= 0) {
                     const double *Bj = myB + (size_t)j * 18;
                     double BC[18];
@@ -932,7 +939,7 @@ __global__ void __launch_bounds__(256) k_lba_update_points(const LbaDev d)
     double cb[3] = {0, 0, 0};
     for (int o = d.obs_ptr[i]; o < d.obs_ptr[i + 1]; ++o) {
         if (d.obs_right[o]) continue;
-        const int j = d.opt_index[d.obs_frame[o]];
+        const int j = d.opt_index[lba_frame(d, o)];
         if (j < 0) continue;
         const double *BC = d.bcinv + (size_t)o * 18;
         for (int r = 0; r < 3; ++r) {
@@ -1052,6 +1059,32 @@ extern "C" int vo_lba_solve_dist(vo_ctx *ctx, const vo_lba_problem *local_part, 
     return lba_solve_impl(ctx, local_part, poses_out, points_out, avg_err_out, success, true);
 }
 
+// Deferred part of the problem validation (see lba_solve_impl): nullptr if the observation lists are well formed.
+static const char *lba_check_observations(const vo_lba_problem *p)
+{
+    const int N = p->n_frames, M = p->n_points;
+    for (int i = 0; i < M; ++i) {
+        int last_left_opt = -1;
+        unsigned seen_l = 0, seen_r = 0;
+        for (int o = p->obs_ptr[i]; o < p->obs_ptr[i + 1]; ++o) {
+            const int f = p->obs_frame[o];
+            if (f < 0 || f >= N) return "obs_frame out of range";
+            const int j = p->opt_index[f];
+            if (j < 0) continue;
+            unsigned &seen = p->obs_right[o] ? seen_r : seen_l;
+            if (seen & (1u << j)) return "duplicate (landmark, keyframe, camera) observation";
+            seen |= 1u << j;
+            if (!p->obs_right[o]) {
+                // the reference accumulates BCinvBt[j][k] for observation order jj <= kk and then mirrors
+                // the upper block triangle: only chronological (ascending opt index) lists are well defined
+                if (j <= last_left_opt) return "left observations must be in ascending keyframe order";
+                last_left_opt = j;
+            }
+        }
+    }
+    return nullptr;
+}
+
 static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out, double *avg_err_out, int *success,
                           bool dist)
 {
@@ -1061,6 +1094,10 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     VO_REQUIRE(p->poses && p->opt_index && p->points && p->obs_ptr && p->obs_frame && p->obs_right && p->obs_px && poses_out && points_out,
                VO_ERR_INVALID_ARG, "null pointer");
     const int N = p->n_frames, No = p->n_opt, M = p->n_points, n_obs = p->n_obs, n6 = 6 * No;
+    static const bool trace = getenv("VO_LBA_TRACE") != nullptr;
+    const auto h_t0 = std::chrono::steady_clock::now();
+    auto h_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h_t0).count(); };
+    double h_valid = 0, h_stage = 0, h_enq = 0;
     // host-side validation of the index structure (cheap, O(n_obs)); the kernels rely on it
     std::vector<int> opt_frame(No, -1);
     for (int f = 0; f < N; ++f) {
@@ -1070,26 +1107,12 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     }
     for (int j = 0; j < No; ++j) VO_REQUIRE(opt_frame[j] >= 0, VO_ERR_INVALID_ARG, "opt_index does not cover [0, n_opt)");
     VO_REQUIRE(p->obs_ptr[0] == 0 && p->obs_ptr[M] == n_obs, VO_ERR_SIZE_MISMATCH, "obs_ptr inconsistent with n_obs");
-    for (int i = 0; i < M; ++i) {
-        VO_REQUIRE(p->obs_ptr[i + 1] >= p->obs_ptr[i], VO_ERR_INVALID_ARG, "obs_ptr not monotone");
-        int last_left_opt = -1;
-        unsigned seen_l = 0, seen_r = 0;
-        for (int o = p->obs_ptr[i]; o < p->obs_ptr[i + 1]; ++o) {
-            const int f = p->obs_frame[o];
-            VO_REQUIRE(f >= 0 && f < N, VO_ERR_INVALID_ARG, "obs_frame out of range");
-            const int j = p->opt_index[f];
-            if (j < 0) continue;
-            unsigned &seen = p->obs_right[o] ? seen_r : seen_l;
-            VO_REQUIRE(!(seen & (1u << j)), VO_ERR_INVALID_ARG, "duplicate (landmark, keyframe, camera) observation");
-            seen |= 1u << j;
-            if (!p->obs_right[o]) {
-                // the reference accumulates BCinvBt[j][k] for observation order jj <= kk and then mirrors
-                // the upper block triangle: only chronological (ascending opt index) lists are well defined
-                VO_REQUIRE(j > last_left_opt, VO_ERR_INVALID_ARG, "left observations must be in ascending keyframe order");
-                last_left_opt = j;
-            }
-        }
-    }
+    for (int i = 0; i < M; ++i) VO_REQUIRE(p->obs_ptr[i + 1] >= p->obs_ptr[i], VO_ERR_INVALID_ARG, "obs_ptr not monotone");
+    // The O(n_obs) part of the validation (frame range, duplicates, chronological left observations: 2.4 ns per observation,
+    // 0.11 - 0.17 ms at the benchmark windows) runs AFTER the work is enqueued, while the GPU iterates; the kernels clamp
+    // the frame index they read, so a malformed list cannot make them touch memory they do not own, and a violation found
+    // here discards their output.
+    h_valid = h_ms();
     VO_CUDA(cudaSetDevice(ctx->device));
 
     // Tile size and landmarks per warp.  About one tile per SM (more tiles only cost a longer k_lba_reduce); inside a tile
@@ -1162,6 +1185,7 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     memcpy(h + o_of, p->obs_frame, (size_t)n_obs * 4);
     memcpy(h + o_or, p->obs_right, (size_t)n_obs);
     memcpy(h + o_px, p->obs_px, (size_t)n_obs * 16);
+    h_stage = h_ms();
     VO_CUDA(cudaMemcpyAsync(dv, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA(cudaMemsetAsync(dv + o_bc, 0, total - o_bc, ctx->stream));
 
@@ -1201,7 +1225,6 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
         });
         if (attr_err != cudaSuccess) { ctx->last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err); return VO_ERR_CUDA; }
     }
-    static const bool trace = getenv("VO_LBA_TRACE") != nullptr;
     std::vector<cudaEvent_t> evs;
     if (trace) { evs.resize(2 * p->max_iter + 1); for (auto &e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], ctx->stream); }
     for (int it = 0; it < p->max_iter; ++it) {
@@ -1243,7 +1266,11 @@ static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_ou
     if (M > 0) VO_CUDA(cudaMemcpyAsync(h + r_pts, dv + o_pts, (size_t)M * 24, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaMemcpyAsync(h + r_ae, dv + o_ae, (size_t)p->max_iter * 8, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(cudaMemcpyAsync(h + r_nan, dv + o_nan, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    h_enq = h_ms();
+    const char *bad = lba_check_observations(p);
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) { ctx->last_error = bad; return VO_ERR_INVALID_ARG; }
+    if (trace) fprintf(stderr, "vo_lba_solve host ms: validated at %.3f, staged at %.3f, enqueued at %.3f, results at %.3f\n", h_valid, h_stage, h_enq, h_ms());
     memcpy(poses_out, h + r_poses, (size_t)N * 128);
     if (M > 0) memcpy(points_out, h + r_pts, (size_t)M * 24);
     const double *ae = (const double *)(h + r_ae);
