@@ -129,6 +129,7 @@ int MonoVO::newLandmarks(int k, const float *pts, const FrameRec &f)
     memcpy(&lm_last_px_[(size_t)base * 2], pts, (size_t)k * 8);
     lm_kf_count_.resize(n, 0); lm_kf_first_id_.resize(n, -1); lm_kf_first_px_.resize(n * 2, 0.f); lm_kf_last_px_.resize(n * 2, 0.f);
     lm_slot_head_.resize(n, -1);
+    lm_first_kf_.resize(n, -1);
     return base;
 }
 
@@ -194,6 +195,7 @@ void MonoVO::addKeyframe(const FrameRecPtr &f)
         f->kf_px[2 * i] = x; f->kf_px[2 * i + 1] = y;
         if (lm_kf_count_[id]++ == 0) { lm_kf_first_id_[id] = f->id; lm_kf_first_px_[2 * (size_t)id] = x; lm_kf_first_px_[2 * (size_t)id + 1] = y; }
         lm_kf_last_px_[2 * (size_t)id] = x; lm_kf_last_px_[2 * (size_t)id + 1] = y;
+        if (lm_slot_head_[id] < 0) lm_first_kf_[id] = kf_index;
         kf_slot_pool_.push_back({kf_index, (int)i, lm_slot_head_[id]});
         lm_slot_head_[id] = (int)kf_slot_pool_.size() - 1;
     }
@@ -445,11 +447,30 @@ void MonoVO::pushStats(const FrameRec &f, bool keyframe)
             for (size_t i = 0; i < nk.lm_ids.size(); ++i)
                 for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)nk.lm_ids[i] * 3 + r];
             for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_keyframe[kf->kf_index].Twc);
-            for (int id : dirty_)
+            // changed points: the window keyframes by a sequential scan of their own landmark lists (one cache-friendly pass
+            // instead of a list walk per landmark), older keyframes -- only landmarks that outlived the window have any --
+            // through the per-landmark list
+            lm_dirty_stamp_.resize(lm_tri_.size(), 0);
+            const int stamp = ++dirty_stamp_;
+            for (int id : dirty_) lm_dirty_stamp_[id] = stamp;
+            const int front = window_.front()->kf_index;
+            for (const auto &kf : window_) {
+                PointVec &kmp = stat_.stats_keyframe[kf->kf_index].mappoints;
+                const size_t n_kf_lm = kf->lm_ids.size();
+                for (size_t i = 0; i < n_kf_lm; ++i) {
+                    const int id = kf->lm_ids[i];
+                    if (lm_dirty_stamp_[id] != stamp) continue;
+                    for (int r = 0; r < 3; ++r) kmp[i](r) = lm_X_[(size_t)id * 3 + r];
+                }
+            }
+            for (int id : dirty_) {
+                if (lm_first_kf_[id] < 0 || lm_first_kf_[id] >= front) continue;
                 for (int e = lm_slot_head_[id]; e >= 0; e = kf_slot_pool_[e].next) {
                     const KfSlot &sl = kf_slot_pool_[e];
+                    if (sl.kf_index >= front) continue;
                     for (int r = 0; r < 3; ++r) stat_.stats_keyframe[sl.kf_index].mappoints[sl.slot](r) = lm_X_[(size_t)id * 3 + r];
                 }
+            }
         }
         dirty_.clear();              // points that change on a non-keyframe (first-frame / initial reconstruction) wait for the next keyframe
     }

@@ -152,6 +152,9 @@ private:
     struct KfSlot { int kf_index, slot, next; };
     std::vector<KfSlot> kf_slot_pool_;
     std::vector<int> lm_slot_head_;          // landmark -> newest pool entry, -1 = none
+    std::vector<int> lm_first_kf_;           // landmark -> oldest keyframe (kf_index) that lists it, -1 = none
+    std::vector<int> lm_dirty_stamp_;        // scratch of the statistics refresh
+    int dirty_stamp_ = 0;
     std::vector<int> dirty_;
     // local-BA packing scratch (kept across keyframes)
     std::vector<int> lm_seen_stamp_, lm_lba_slot_, lba_cand_, lba_cnt_, lba_lms_, lba_obs_ptr_, lba_obs_cursor_, lba_obs_frame_;

@@ -130,6 +130,7 @@ int StereoVO::newLandmarks(int k, int frame_id)
     lm_tri_.resize(base + k, 0); lm_alive_.resize(base + k, 1); lm_bundled_.resize(base + k, 0);
     lm_last_frame_.resize(base + k, frame_id);
     lm_slot_head_.resize(base + k, -1);
+    lm_first_kf_.resize(base + k, -1);
     return base;
 }
 
@@ -163,6 +164,7 @@ void StereoVO::addKeyframe(const FrameRecPtr &f)
     f->kf_index = kf_index;
     for (size_t i = 0; i < n; ++i) {
         const int id = f->lm_ids[i];
+        if (lm_slot_head_[id] < 0) lm_first_kf_[id] = kf_index;
         kf_slot_pool_.push_back({kf_index, (int)i, lm_slot_head_[id]});
         lm_slot_head_[id] = (int)kf_slot_pool_.size() - 1;
     }
@@ -342,11 +344,30 @@ void StereoVO::pushStats(const FrameRec &f, bool keyframe)
             for (size_t i = 0; i < nk.lm_ids.size(); ++i)
                 for (int r = 0; r < 3; ++r) mp[i](r) = lm_X_[(size_t)nk.lm_ids[i] * 3 + r];
             for (const auto &kf : window_) rowmajor_to_pose(kf->Twc, stat_.stats_keyframe[kf->kf_index].Twc);
-            for (int id : dirty_)
+            // changed points: the window keyframes by a sequential scan of their own landmark lists (one cache-friendly pass
+            // instead of a list walk per landmark), older keyframes -- only landmarks that outlived the window have any --
+            // through the per-landmark list
+            lm_dirty_stamp_.resize(lm_tri_.size(), 0);
+            const int stamp = ++dirty_stamp_;
+            for (int id : dirty_) lm_dirty_stamp_[id] = stamp;
+            const int front = window_.front()->kf_index;
+            for (const auto &kf : window_) {
+                PointVec &kmp = stat_.stats_keyframe[kf->kf_index].mappoints;
+                const size_t n_kf_lm = kf->lm_ids.size();
+                for (size_t i = 0; i < n_kf_lm; ++i) {
+                    const int id = kf->lm_ids[i];
+                    if (lm_dirty_stamp_[id] != stamp) continue;
+                    for (int r = 0; r < 3; ++r) kmp[i](r) = lm_X_[(size_t)id * 3 + r];
+                }
+            }
+            for (int id : dirty_) {
+                if (lm_first_kf_[id] < 0 || lm_first_kf_[id] >= front) continue;
                 for (int e = lm_slot_head_[id]; e >= 0; e = kf_slot_pool_[e].next) {
                     const KfSlot &sl = kf_slot_pool_[e];
+                    if (sl.kf_index >= front) continue;
                     for (int r = 0; r < 3; ++r) stat_.stats_keyframe[sl.kf_index].mappoints[sl.slot](r) = lm_X_[(size_t)id * 3 + r];
                 }
+            }
         }
         dirty_.clear();              // points that change on a non-keyframe (first-frame / initial reconstruction) wait for the next keyframe
     }
