@@ -437,7 +437,11 @@ typedef struct vo_lba_problem {
     int max_iter;            /* 10 (motion_estimator.cpp:1226) */
 } vo_lba_problem;
 /* poses_out [n_frames][16], points_out [n_points][3]; avg_err_out[max_iter] per-iteration
- * sqrt(err/n_obs) (sparse_bundle_adjustment.cpp:606). *success = last avg_err <= 1 px. */
+ * sqrt(err/n_obs) (sparse_bundle_adjustment.cpp:606). *success = last avg_err <= 1 px.
+ * Argument checks: sizes, opt_index and obs_ptr are validated before anything is enqueued; the per-observation checks
+ * (obs_frame range, no duplicate (landmark, keyframe, camera), left observations in ascending keyframe order) run on
+ * the host while the GPU already iterates -- the kernels clamp the frame index they read -- and a violation returns
+ * VO_ERR_INVALID_ARG with the outputs untouched.  VO_ERR_NAN mirrors the reference's "Local BA NAN!" exception. */
 VO_API int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *prob, double *poses_out, double *points_out,
                  double *avg_err_out, int *success);
 
