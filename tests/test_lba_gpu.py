@@ -14,7 +14,9 @@ def _rot_angle(Ra, Rb):
 
 
 @pytest.mark.parametrize("n_points,n_kf,stereo,iters", [(200, 10, True, 10), (5000, 10, True, 10), (300, 6, False, 10),
-                                                          (64, 4, True, 3), (1, 3, True, 2)])
+                                                          (64, 4, True, 3), (1, 3, True, 2),
+                                                          # more than 8 optimised keyframes: the 6 x 6-block solve kernel, larger panels
+                                                          (1500, 14, True, 6), (6000, 18, True, 4), (400, 13, False, 5)])
 def test_lba_matches_oracle(gpu_ctx, n_points, n_kf, stereo, iters):
     from oracle import lba as olba
     p = synth.lba_problem(seed=4004 + n_points, n_kf=n_kf, n_points=n_points, stereo=stereo)
