@@ -723,7 +723,8 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                                    "4 levels, win 21) [+ trackWithScale] + stereo pose GN + compactions, wall clock incl. all "
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
     res["sequence"] = sequence_measurement(torch, dev, synth, n_frames=cfg3_frames)
-    res["sequence_strict_pose"] = sequence_measurement(torch, dev, synth, n_frames=min(cfg3_frames, 300), n_cpu=0, with_concurrent=False, pose_strict=True)
+    res["sequence_yaml_defaults"] = sequence_measurement(torch, dev, synth, n_frames=min(cfg3_frames, 300), n_cpu=0, with_concurrent=False,
+                                                           pose_strict=True, scale_faithful=True)
     res["mono_sequence"] = mono_sequence_measurement(torch, dev, synth)
     res["sequence_orb"] = sequence_measurement(torch, dev, synth, n_frames=60, n_cpu=6, detector="orb", with_concurrent=False)
     res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
@@ -832,7 +833,7 @@ def cfg4_measurement(ctx, synth):
             "what": "vo_lba_solve / vo_depth_filter_normal with host buffers, wall clock incl. H2D/D2H and the sync"}
 
 
-def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="harris", with_concurrent=True, pose_strict=False):
+def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="harris", with_concurrent=True, pose_strict=False, scale_faithful=False):
     """BASELINE config 3: the full stereo VO step over a synthetic KITTI-like sequence through the reference-API class
     (host images in, pose out; tracking + new features every frame, reconstruction + local BA on keyframes)."""
     from oracle import stereo_vo as osvo
@@ -843,7 +844,8 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
     Lp, Rp = torch.from_numpy(L).pin_memory().numpy(), torch.from_numpy(R).pin_memory().numpy()
     # warm-up instance: first use of every kernel (lazy module loading), first pinned / device allocations
     mk = lambda: svo.StereoVO(svo.make_parameters(W, H, K4, K4, Tlr, window_size=WIN, max_level=MAXLVL, n_bins_u=nbu, n_bins_v=nbv,
-                                                  detector=detector, thres_fastscore=20, pose_strict=pose_strict))
+                                                  detector=detector, thres_fastscore=20, pose_strict=pose_strict,
+                                                  scale_faithful_borders=scale_faithful))
     warm = mk()
     for k in range(min(16, n_frames)):
         warm.trackStereoImages(Lp[k], Rp[k], 0.1 * k)
@@ -881,6 +883,7 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
     return {"concurrent_sequences": conc, "detector": "K-det (Harris on the Scharr plane)" if detector == "harris" else "cv::ORB restated (the reference's extractor), FAST threshold 20",
             "pose_mode": "strict (sequential FP32 sums, the reference's arithmetic bit for bit; what the yaml constructor selects)" if pose_strict
                          else "fast (FP64 tree sums; the Parameters-struct default)",
+            "scale_border_mode": "reference-faithful stale sample buffers (yaml default)" if scale_faithful else "out-of-image samples masked (Parameters-struct default)",
             "frames": n_frames, "ms_per_frame_mean": float(ms.mean()), "ms_per_frame_median": float(np.median(ms)),
             "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
             "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None,

@@ -158,7 +158,14 @@ VO_API int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, const 
 VO_API int vo_ft_calc_prior(vo_ctx *ctx, const float *pts0, const float *Xw, int n, const float *Tw1,
                      const float *K4, float *pts1_prior);
 /* FeatureTracker::trackWithScale (feature_tracker.cpp:236-504). The float image and its
- * 3x3 Sobel derivatives (stereo_vo.cpp:551-552) are computed on device from slot0. */
+ * 3x3 Sobel derivatives (stereo_vo.cpp:551-552) are computed on device from slot0.
+ * Samples that leave the image: the reference keeps its per-sample buffers and masks across features and iterations
+ * (feature_tracker.cpp:324-333, image_processing.cpp:88-89), so such a sample reuses the value the previous feature /
+ * iteration left at that index.  vo_set_scale_mode(ctx, 1) reproduces exactly that (the affected features -- a few per
+ * frame -- are recomputed in a second pass against the buffer state their predecessors leave; every trackWithScale stage
+ * of the context, also inside the frame steps); mode 0 (default) masks those samples out, the intended semantics. */
+VO_API int vo_set_scale_mode(vo_ctx *ctx, int faithful_borders);
+VO_API int vo_get_scale_mode(const vo_ctx *ctx);
 VO_API int vo_ft_track_with_scale(vo_ctx *ctx, int slot0, int slot1, const float *pts0,
                            const float *scale_est, int n, float *pts_track_inout,
                            uint8_t *mask_inout);

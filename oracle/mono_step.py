@@ -73,7 +73,7 @@ def sampson(pts0, pts1, F):
 
 def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_prior, K4, win, max_level, thres_err, thres_bi,
                     thres_sampson, thres_poseba, use_bundled_only, n_bins_u=0, n_bins_v=0, det_edge=31, det_min_score=0,
-                    do_scale_refine=True, lk=oklt.lk_cv2, five_point=None, thres_5p=0.0, detect_fn=None):
+                    do_scale_refine=True, lk=oklt.lk_cv2, five_point=None, thres_5p=0.0, detect_fn=None, faithful_scale=False):
     h, w = I0.shape
     pts0 = np.asarray(pts0, f32).reshape(-1, 2)
     Xw = np.asarray(Xw, f32).reshape(-1, 3)
@@ -102,7 +102,7 @@ def mono_frame_step(I0, I1, pts0, Xw, triangulated, bundled, T_wc_prev, dT01_pri
     counts.append(len(idx))
     # K7 (:783)
     if do_scale_refine:
-        p1c, m = oklt.track_with_scale(I0, I1, p0c, sc, p1c)
+        p1c, m = oklt.track_with_scale(I0, I1, p0c, sc, p1c, faithful=faithful_scale)
         idx, p0c, p1c = idx[m], p0c[m], p1c[m]
     counts.append(len(idx))
     # selection (:799-827)

@@ -32,7 +32,7 @@ def _xform(T, X):
 
 
 def stereo_track_step(I0l, I1l, I1r, pts_l0, pts_r0, Xw, tri, T_wp, dT_prev, K_l, K_r, T_lr, win, max_level, thres_err,
-                      thres_poseba, do_scale_refine=True, sampson_y=660.0, lk=oklt.lk_cv2):
+                      thres_poseba, do_scale_refine=True, sampson_y=660.0, lk=oklt.lk_cv2, faithful_scale=False):
     h, w = I0l.shape
     pts_l0 = np.asarray(pts_l0, f32).reshape(-1, 2)
     pts_r0 = np.asarray(pts_r0, f32).reshape(-1, 2)
@@ -69,7 +69,7 @@ def stereo_track_step(I0l, I1l, I1r, pts_l0, pts_r0, Xw, tri, T_wp, dT_prev, K_l
     counts.append(len(idx))
     # [4-1] scale refinement
     if do_scale_refine:
-        l1, m = oklt.track_with_scale(I0l, I1l, l0, sc, l1)
+        l1, m = oklt.track_with_scale(I0l, I1l, l0, sc, l1, faithful=faithful_scale)
         idx, l0, l1, r1p = idx[m], l0[m], l1[m], r1p[m]
     counts.append(len(idx))
     # [5] l1 -> r1

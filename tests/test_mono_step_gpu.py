@@ -59,6 +59,24 @@ def test_mono_frame_step_matches_oracle(states, bundled_only):
         gf = ctx.mono_frame_step(0, 1, s["I1"], *args, want_counts=False, **kw)      # fused K4 + K7 chain
         for key in ("index", "pts1", "T_wc", "dT01", "dT10", "new_p1", "new_p0"):
             assert np.array_equal(gf[key], g[key]), (s["k"], key)
+        # trackWithScale with the reference's stale sample buffers (vo_set_scale_mode): fused chain + second pass against the
+        # sequential restatement in the same mode
+        try:
+            of = omono.mono_frame_step(s["I0"], s["I1"], *args, kw["win"], kw["max_level"], kw["thres_err"], kw["thres_bi"], kw["thres_sampson"],
+                                       kw["thres_poseba"], bundled_only, kw["n_bins_u"], kw["n_bins_v"], faithful_scale=True)
+            ctx.set_scale_mode(True)
+            try:
+                gff = ctx.mono_frame_step(0, 1, s["I1"], *args, want_counts=False, **kw)
+                gfu = ctx.mono_frame_step(0, 1, s["I1"], *args, **kw)
+            finally:
+                ctx.set_scale_mode(False)
+            assert np.array_equal(gff["index"], gfu["index"]) and np.array_equal(gff["pts1"], gfu["pts1"])
+            both_f = np.intersect1d(gff["index"], of["index"])
+            assert len(both_f) >= 0.995 * max(len(gff["index"]), len(of["index"]))
+            if np.array_equal(gff["index"], of["index"]):
+                assert np.mean(np.abs(gff["pts1"] - of["pts1"]).max(1) <= 0.01) >= 0.995
+        except RuntimeError:
+            pass
         inter = np.intersect1d(g["index"], o["index"])
         agree += len(inter); total += max(len(g["index"]), len(o["index"]))
         if np.array_equal(g["index"], o["index"]):

@@ -13,16 +13,23 @@ def _rot_angle(Ra, Rb):
     return float(np.arcsin(min(1.0, np.linalg.norm(dR - dR.T) / (2.0 * np.sqrt(2.0)))))
 
 
-@pytest.mark.parametrize("seed,n,refine", [(3003, 2000, True), (3004, 500, False), (3005, 40, True)])
-def test_stereo_track_step_matches_oracle(gpu_ctx, seed, n, refine):
+@pytest.mark.parametrize("seed,n,refine,faithful", [(3003, 2000, True, False), (3004, 500, False, False), (3005, 40, True, False),
+                                                    # trackWithScale with the reference's stale sample buffers (vo_set_scale_mode):
+                                                    # scale stage + second pass, then l1 -> r1 as a launch of its own
+                                                    (3003, 2000, True, True), (3006, 300, True, True)])
+def test_stereo_track_step_matches_oracle(gpu_ctx, seed, n, refine, faithful):
     from oracle import step as ostep
     s = synth.stereo_frame_pair(seed=seed, n=n)
     K, Tlr = synth.kitti_K(), synth.kitti_T_lr()
     o = ostep.stereo_track_step(s["L0"], s["L1"], s["R1"], s["pts_l0"], s["pts_r0"], s["Xw"], s["tri"], s["T_wp"], s["dT_pc_prev"],
-                                K, K, Tlr, 21, 3, 80.0, 3.0, do_scale_refine=refine)
+                                K, K, Tlr, 21, 3, 80.0, 3.0, do_scale_refine=refine, faithful_scale=faithful)
     gpu_ctx.upload_image(0, s["L0"])
-    g = gpu_ctx.stereo_track_step(0, 1, 2, s["L1"], s["R1"], s["pts_l0"], s["pts_r0"], s["Xw"], s["tri"], s["T_wp"], s["dT_pc_prev"],
-                                  K, K, Tlr, 21, 3, 80.0, 3.0, do_scale_refine=refine)
+    gpu_ctx.set_scale_mode(faithful)
+    try:
+        g = gpu_ctx.stereo_track_step(0, 1, 2, s["L1"], s["R1"], s["pts_l0"], s["pts_r0"], s["Xw"], s["tri"], s["T_wp"], s["dT_pc_prev"],
+                                      K, K, Tlr, 21, 3, 80.0, 3.0, do_scale_refine=refine)
+    finally:
+        gpu_ctx.set_scale_mode(False)
     print("counts gpu", g["counts"], "oracle", o["counts"])
     # feature indexing: survivors must be the same landmarks in the same order (>= 99.9 % agreement)
     both = np.intersect1d(g["index"], o["index"])

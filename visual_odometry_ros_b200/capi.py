@@ -135,6 +135,8 @@ def lib():
     L.vo_dist_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     L.vo_dist_finalize.argtypes = [vp]
     L.vo_set_pose_mode.argtypes = [vp, ctypes.c_int]
+    L.vo_set_scale_mode.argtypes = [vp, ctypes.c_int]
+    L.vo_get_scale_mode.argtypes = [vp]
     L.vo_get_pose_mode.argtypes = [vp]
     L.vo_triangulate_dlt.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     L.vo_depth_filter_normal.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
@@ -321,6 +323,10 @@ class Context:
     def ft_track_bidirection_with_prior(self, slot0, slot1, pts0, prior, win, lvl, thres_err, thres_bi, mask=None):
         return self._ft(self.L.vo_ft_track_bidirection_with_prior, slot0, slot1, pts0, win, lvl, thres_err,
                         [ctypes.c_float(thres_bi)], prior, mask)
+
+    def set_scale_mode(self, faithful_borders):
+        """trackWithScale samples outside the image: True = the reference's stale sample buffers reproduced, False = masked out."""
+        check(self.h, self.L.vo_set_scale_mode(self.h, int(bool(faithful_borders))))
 
     # ---------------------------------------------------------------- pose-only Gauss-Newton
     def set_pose_mode(self, flags):

@@ -134,6 +134,7 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     for (int i = 0; i < 4; ++i) if (ctx->d_f32[i]) cudaFree(ctx->d_f32[i]);
     if (ctx->d_lba) cudaFree(ctx->d_lba);
+    if (ctx->d_ks) cudaFree(ctx->d_ks);
     if (ctx->d_det) cudaFree(ctx->d_det);
     if (ctx->d_fp) cudaFree(ctx->d_fp);
     if (ctx->d_orb) cudaFree(ctx->d_orb);

@@ -991,6 +991,17 @@ int vo_track_chain_launch_d(vo_ctx *ctx, int slot_l0, int slot_l1, int slot_r1, 
     sc.slots = ctx->d_slots; sc.slot0 = slot_l0; sc.slot1 = slot_l1;
     sc.pts0 = reinterpret_cast<const float2 *>(pts_l0_d); sc.scale = scale_d;
     sc.pts_track = reinterpret_cast<float2 *>(pts_l1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
+    if (do_scale && ctx->scale_faithful) {
+        // reference-faithful trackWithScale borders: the second pass (k_klt_scale_fixup) must see every feature's scale stage
+        // before any feature goes on to l1 -> r1, so the third stage is a launch of its own in this mode
+        rc = vo_klt_scale_prepare(ctx, sc);
+        if (rc) return rc;
+        rc = launch_chain_win(ctx, win, a1, a1, sc, a3, VO_CHAIN_SCALE, n);
+        if (rc) return rc;
+        rc = vo_klt_scale_fixup_launch(ctx, sc);
+        if (rc) return rc;
+        return vo_klt_launch(ctx, 1, &slot_l1, &slot_r1, pts_l1_d, n, win, max_level, VO_KLT_USE_INITIAL_FLOW, pts_r1_d, nullptr, nullptr, nullptr, &post);
+    }
     return launch_chain_win(ctx, win, a1, a1, sc, a3, (do_scale ? VO_CHAIN_SCALE : 0) | VO_CHAIN_NEXT, n);
 }
 
@@ -1033,5 +1044,8 @@ int vo_bidir_chain_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0
     sc.slots = ctx->d_slots; sc.slot0 = slot0; sc.slot1 = slot1;
     sc.pts0 = reinterpret_cast<const float2 *>(pts0_d); sc.scale = scale_d;
     sc.pts_track = reinterpret_cast<float2 *>(pts1_d); sc.mask = mask_d; sc.nan_flag = nan_flag_d; sc.iters = nullptr; sc.n = n;
-    return launch_chain_win(ctx, win, a1, a2, sc, a1, VO_CHAIN_BACK | (scale_d ? VO_CHAIN_SCALE : 0), n);
+    if (scale_d) { rc = vo_klt_scale_prepare(ctx, sc); if (rc) return rc; }
+    rc = launch_chain_win(ctx, win, a1, a2, sc, a1, VO_CHAIN_BACK | (scale_d ? VO_CHAIN_SCALE : 0), n);
+    if (rc) return rc;
+    return scale_d ? vo_klt_scale_fixup_launch(ctx, sc) : VO_OK;        // the scale stage is the last one of this chain
 }

@@ -9,8 +9,11 @@
 // evaluated on the fly as exact small integers, so the sampled values are bit-identical to
 // the reference's.  Kept quirks: every sample uses the PATCH CENTRE's bilinear fractions and
 // (int)-truncated coordinates (Appendix B #9), fixed per-feature scale, stop rule evaluated
-// only for iter > 1, RMS-error <= 30 acceptance.  Out-of-image samples are masked out (the
-// intended semantics; the reference reuses stale buffer contents there -- see DESIGN.md).
+// only for iter > 1, RMS-error <= 30 acceptance.  Out-of-image samples: by default they are
+// masked out (the intended semantics).  The reference reuses stale buffer contents there, a
+// sequential dependence between features; vo_set_scale_mode(ctx, 1) reproduces that too
+// (k_klt_scale_fixup below: the few features with an out-of-image sample are recomputed against
+// the buffer state their predecessors would have left).
 // FP32 throughout like the reference, except that the 264-term sums are reduced in FP64
 // across the warp and rounded once (the reference adds them sequentially in FP32).
 // Compiled with -fmad=false.
@@ -27,6 +30,83 @@ __global__ void __launch_bounds__(128) k_klt_scale(const KltScaleArgs a)
     klt_scale_feature(a, f, lane);
 }
 
+// Reference-faithful border mode, second pass: one warp per feature that had an out-of-image sample in the parallel pass.
+// The reference's buffer state in front of feature f is fully determined by the nearest earlier feature q that was live,
+// entered its iteration loop and had every sample inside the image (it rewrote every buffer entry and every mask is true
+// from then on) -- or by the empty initial state if there is none.  The warp replays q and every live feature between q and
+// f against that state (normally q = f - 1 and nothing in between) and then computes f exactly as the reference would.
+// A chain that reaches back more than KS_LOOKBACK features without finding such a q keeps the intended-semantics result.
+#define KS_LOOKBACK 512
+__global__ void __launch_bounds__(128) k_klt_scale_fixup(const KltScaleArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= a.n) return;
+    const int fl = a.flags[f];
+    if ((fl & (KS_FLAG_PROCESSED | KS_FLAG_BORDER)) != (KS_FLAG_PROCESSED | KS_FLAG_BORDER)) return;
+    int q = -1;
+    bool gave_up = false;
+    for (int base = f - 1; base >= 0 && q < 0; base -= 32) {
+        if (f - base > KS_LOOKBACK) { gave_up = true; break; }
+        const int i = base - lane;
+        const bool reset = i >= 0 && (a.flags[i] & (KS_FLAG_PROCESSED | KS_FLAG_BORDER | KS_FLAG_RAN)) == (KS_FLAG_PROCESSED | KS_FLAG_RAN);
+        const unsigned m = __ballot_sync(0xffffffffu, reset);
+        if (m) q = base - (__ffs(m) - 1);
+    }
+    if (gave_up) return;
+    KsState st;
+    ks_state_clear(st);
+    bool ok, nan_hit;
+    float2 out;
+    for (int i = q < 0 ? 0 : q; i < f; ++i) {
+        if (!(a.flags[i] & KS_FLAG_PROCESSED)) continue;
+        klt_scale_feature_stale(a, i, lane, a.pre_pts[i], st, ok, out, nan_hit);
+    }
+    const float2 pt1 = a.pre_pts[f];
+    klt_scale_feature_stale(a, f, lane, pt1, st, ok, out, nan_hit);
+    if (lane == 0) {
+        if (nan_hit) atomicExch(a.nan_flag, 1);
+        a.mask[f] = ok ? 1 : 0;
+        a.pts_track[f] = ok ? out : pt1;          // a rejected feature keeps its input point (feature_tracker.cpp:489-500)
+    }
+}
+
+// grow-only scratch of the faithful mode: [flags n][pad][pre_pts n * 8]
+static int ks_scratch(vo_ctx *ctx, int n, uint8_t **flags, float2 **pre)
+{
+    const size_t need = ((size_t)n + 15) / 16 * 16 + (size_t)n * 8;
+    if (need > ctx->ks_bytes) {
+        VO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_ks) cudaFree(ctx->d_ks);
+        ctx->d_ks = nullptr; ctx->ks_bytes = 0;
+        size_t want = need * 2;
+        if (want < ((size_t)1 << 16)) want = (size_t)1 << 16;
+        VO_CUDA(cudaMalloc(&ctx->d_ks, want));
+        ctx->ks_bytes = want;
+    }
+    *flags = ctx->d_ks;
+    *pre = reinterpret_cast<float2 *>(ctx->d_ks + ((size_t)n + 15) / 16 * 16);
+    return VO_OK;
+}
+
+// faithful mode: fills the record pointers of a scale stage (also used by the fused chains in klt.cu)
+int vo_klt_scale_prepare(vo_ctx *ctx, KltScaleArgs &a)
+{
+    a.flags = nullptr; a.pre_pts = nullptr;
+    if (!ctx->scale_faithful) return VO_OK;
+    return ks_scratch(ctx, a.n, &a.flags, &a.pre_pts);
+}
+
+// faithful mode: the second pass over the records a scale stage left
+int vo_klt_scale_fixup_launch(vo_ctx *ctx, const KltScaleArgs &a)
+{
+    if (!a.flags) return VO_OK;
+    k_klt_scale_fixup<<<vo_div_up(a.n, 4), 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    return VO_OK;
+}
+
 int vo_klt_scale_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d, const float *scale_d, int n,
                           float *pts_track_d, uint8_t *mask_d, int *nan_flag_d)
 {
@@ -34,11 +114,22 @@ int vo_klt_scale_launch_d(vo_ctx *ctx, int slot0, int slot1, const float *pts0_d
     a.slots = ctx->d_slots; a.slot0 = slot0; a.slot1 = slot1;
     a.pts0 = (const float2 *)pts0_d; a.scale = scale_d;
     a.pts_track = (float2 *)pts_track_d; a.mask = mask_d; a.nan_flag = nan_flag_d; a.iters = nullptr; a.n = n;
+    int rc = vo_klt_scale_prepare(ctx, a);
+    if (rc) return rc;
     k_klt_scale<<<vo_div_up(n, 4), 128, 0, ctx->stream>>>(a);
     ctx->launches++;
     VO_CUDA(cudaGetLastError());
+    return vo_klt_scale_fixup_launch(ctx, a);
+}
+
+extern "C" int vo_set_scale_mode(vo_ctx *ctx, int faithful_borders)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    ctx->scale_faithful = faithful_borders ? 1 : 0;
     return VO_OK;
 }
+
+extern "C" int vo_get_scale_mode(const vo_ctx *ctx) { return ctx ? ctx->scale_faithful : VO_ERR_INVALID_ARG; }
 
 extern "C" int vo_ft_track_with_scale(vo_ctx *ctx, int slot0, int slot1, const float *pts0, const float *scale_est, int n,
                                       float *pts_track_inout, uint8_t *mask_inout)

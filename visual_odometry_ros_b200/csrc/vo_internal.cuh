@@ -70,6 +70,9 @@ struct vo_ctx {
     size_t stage_bytes = 0;
     long long launches = 0;
     int pose_flags = 0;            // VO_POSE_FAST / VO_POSE_STRICT (vo_set_pose_mode)
+    int scale_faithful = 0;        // trackWithScale: reproduce the reference's stale sample buffers (vo_set_scale_mode)
+    uint8_t *d_ks = nullptr;       // scratch of that mode (k_klt_scale_fixup)
+    size_t ks_bytes = 0;
     std::string last_error;
     // trackWithScale scratch (float image + Sobel derivatives), lazily allocated
     float *d_f32[4] = {nullptr, nullptr, nullptr, nullptr};

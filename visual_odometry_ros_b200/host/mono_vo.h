@@ -79,6 +79,9 @@ public:
         // pose-only GN accumulation: 0 = VO_POSE_FAST (FP64 tree sums), 1 = VO_POSE_STRICT (sequential FP32 sums in point
         // order: the reference's arithmetic bit for bit); yaml key motion_estimator.pose_strict (ours)
         int pose_strict = 0;
+        // trackWithScale samples outside the image: 1 = the reference's stale sample buffers reproduced (vo_set_scale_mode),
+        // 0 = masked out; yaml key feature_tracker.scale_faithful_borders (ours), 1 when constructed from yaml
+        int scale_faithful_borders = 0;
     };
 
     MonoVO(std::string mode, std::string directory_intrinsic);     // mono_vo.cpp:11-55 (yaml via a minimal parser)

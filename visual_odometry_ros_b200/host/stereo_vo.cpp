@@ -74,6 +74,7 @@ StereoVO::StereoVO(std::string mode, std::string directory_intrinsic)
     p_.detector = VO_DETECTOR_ORB;                                    // the reference's extractor
     p_.thres_fastscore = (int)num("feature_extractor.thres_fastscore", p_.thres_fastscore);   // initParams(..., int THRES_FAST, ...)
     p_.pose_strict = (int)num("motion_estimator.pose_strict", 1);     // yaml construction = drop-in use: the reference's arithmetic
+    p_.scale_faithful_borders = (int)num("feature_tracker.scale_faithful_borders", 1);
     p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
     p_.thres_alive_ratio = (float)num("keyframe_update.thres_alive_ratio", p_.thres_alive_ratio);
     p_.thres_trans = (float)num("keyframe_update.thres_trans", p_.thres_trans);
@@ -91,6 +92,8 @@ void StereoVO::init()
     if (rc != VO_OK) fail(nullptr, rc);          // VO_ERR_NO_DEVICE: there is no CPU fallback
     const int rp = vo_set_pose_mode(ctx_, p_.pose_strict ? VO_POSE_STRICT : VO_POSE_FAST);
     if (rp) fail(ctx_, rp);
+    const int rs = vo_set_scale_mode(ctx_, p_.scale_faithful_borders);
+    if (rs) fail(ctx_, rs);
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
     {   // landmark tables: room for 2^19 landmarks (several hundred frames) before the first reallocation, which would

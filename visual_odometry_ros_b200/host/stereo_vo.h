@@ -75,6 +75,9 @@ public:
         // order: the reference's arithmetic bit for bit, about 0.2 ms more per frame at 2000 landmarks); yaml key
         // motion_estimator.pose_strict (ours; the reference has no such key)
         int pose_strict = 0;
+        // trackWithScale samples outside the image: 1 = the reference's stale sample buffers reproduced (vo_set_scale_mode),
+        // 0 = masked out; yaml key feature_tracker.scale_faithful_borders (ours), 1 when constructed from yaml
+        int scale_faithful_borders = 0;
     };
 
     StereoVO(std::string mode, std::string directory_intrinsic);   // stereo_vo.cpp:9-53 (yaml via a minimal parser)

@@ -43,6 +43,8 @@ vo_ctx *shared_context(int min_w, int min_h)
     g_h = std::max(min_h, std::max(g_h, 1200));
     const int rc = vo_ctx_create(0, g_w, g_h, 5, 8192, nullptr, &g_ctx);      // slots 0-3: FeatureTracker, slot 4: FeatureExtractor
     if (rc != VO_OK) throw_status(nullptr, rc, nullptr);
+    // the shim stands in for the reference's classes: the reference's arithmetic, including trackWithScale's stale sample buffers
+    vo_set_scale_mode(g_ctx, 1);
     return g_ctx;
 }
 

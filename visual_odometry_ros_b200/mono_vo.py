@@ -22,7 +22,8 @@ class Parameters(ctypes.Structure):
                 ("do_scale_refine", ctypes.c_int), ("det_edge", ctypes.c_int), ("det_min_score", ctypes.c_longlong), ("device", ctypes.c_int),
                 ("n_hypotheses", ctypes.c_int), ("seed", ctypes.c_uint), ("collect_gate_counts", ctypes.c_int),
                 ("record_frame_mappoints", ctypes.c_int), ("detector", ctypes.c_int), ("thres_fastscore", ctypes.c_int),
-                ("do_undistortion", ctypes.c_int), ("D", ctypes.c_float * 5), ("pose_strict", ctypes.c_int)]
+                ("do_undistortion", ctypes.c_int), ("D", ctypes.c_float * 5), ("pose_strict", ctypes.c_int),
+                ("scale_faithful_borders", ctypes.c_int)]
 
 
 class FrameInfo(ctypes.Structure):
@@ -62,7 +63,7 @@ def make_parameters(w, h, K, *, window_size=21, max_level=6, thres_error=60.0, t
                     thres_parallax_deg=1.0, n_bins_u=30, n_bins_v=12, thres_5p_error=1.0, thres_poseba_error=5.0, thres_overlap_ratio=0.6,
                     thres_translation=4.0, thres_rotation_deg=10.0, n_max_keyframes_in_window=9, do_scale_refine=True, det_edge=31,
                     det_min_score=0, device=0, n_hypotheses=0, seed=0, collect_gate_counts=False, record_frame_mappoints=False,
-                    detector="harris", thres_fastscore=20, D=None, pose_strict=False):
+                    detector="harris", thres_fastscore=20, D=None, pose_strict=False, scale_faithful_borders=False):
     """Defaults = config/mono/kitti_00.yaml.  D = (k1, k2, p1, p2, k3) switches the on-device undistortion on."""
     p = Parameters()
     p.width, p.height = int(w), int(h)
@@ -78,6 +79,7 @@ def make_parameters(w, h, K, *, window_size=21, max_level=6, thres_error=60.0, t
     p.collect_gate_counts, p.record_frame_mappoints = int(bool(collect_gate_counts)), int(bool(record_frame_mappoints))
     p.detector, p.thres_fastscore = {"harris": 0, "orb": 1}[detector], int(thres_fastscore)
     p.pose_strict = int(bool(pose_strict))
+    p.scale_faithful_borders = int(bool(scale_faithful_borders))
     if D is not None:
         p.do_undistortion = 1
         p.D = (ctypes.c_float * 5)(*[float(v) for v in D])

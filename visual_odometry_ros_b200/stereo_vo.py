@@ -22,7 +22,8 @@ class Parameters(ctypes.Structure):
                 ("n_max_keyframes_in_window", ctypes.c_int), ("do_scale_refine", ctypes.c_int), ("det_edge", ctypes.c_int),
                 ("det_min_score", ctypes.c_longlong), ("device", ctypes.c_int), ("do_undistortion", ctypes.c_int),
                 ("D_l", ctypes.c_float * 5), ("D_r", ctypes.c_float * 5), ("collect_gate_counts", ctypes.c_int),
-                ("detector", ctypes.c_int), ("thres_fastscore", ctypes.c_int), ("pose_strict", ctypes.c_int)]
+                ("detector", ctypes.c_int), ("thres_fastscore", ctypes.c_int), ("pose_strict", ctypes.c_int),
+                ("scale_faithful_borders", ctypes.c_int)]
 
 
 class FrameInfo(ctypes.Structure):
@@ -61,7 +62,7 @@ def host_lib():
 def make_parameters(w, h, K_l, K_r, T_lr, *, window_size=21, max_level=3, thres_error=80.0, thres_bidirection=0.5, thres_sampson=60.0,
                     n_bins_u=64, n_bins_v=32, thres_poseba_error=3.0, thres_alive_ratio=0.6, thres_trans=10.0, thres_rotation_deg=15.0,
                     n_max_keyframes_in_window=9, do_scale_refine=True, det_edge=31, det_min_score=0, device=0, D_l=None, D_r=None, collect_gate_counts=False,
-                    detector="harris", thres_fastscore=20, pose_strict=False):
+                    detector="harris", thres_fastscore=20, pose_strict=False, scale_faithful_borders=False):
     p = Parameters()
     p.width, p.height = int(w), int(h)
     p.K_l = (ctypes.c_float * 4)(*[float(v) for v in K_l])
@@ -75,6 +76,7 @@ def make_parameters(w, h, K_l, K_r, T_lr, *, window_size=21, max_level=3, thres_
     p.collect_gate_counts = int(bool(collect_gate_counts))
     p.detector, p.thres_fastscore = {"harris": 0, "orb": 1}[detector], int(thres_fastscore)
     p.pose_strict = int(bool(pose_strict))
+    p.scale_faithful_borders = int(bool(scale_faithful_borders))
     if D_l is not None or D_r is not None:
         p.do_undistortion = 1
         p.D_l = (ctypes.c_float * 5)(*[float(v) for v in (D_l if D_l is not None else [0] * 5)])
