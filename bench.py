@@ -724,7 +724,9 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
                                    "copies and the single sync; cpu = the oracle composition (cv2 LK on all threads + C restatements)"}
     res["sequence"] = sequence_measurement(torch, dev, synth, n_frames=cfg3_frames)
     res["sequence_yaml_defaults"] = sequence_measurement(torch, dev, synth, n_frames=min(cfg3_frames, 300), n_cpu=0, with_concurrent=False,
-                                                           pose_strict=True, scale_faithful=True)
+                                                           pose_strict=True)
+    res["sequence_all_reference_quirks"] = sequence_measurement(torch, dev, synth, n_frames=min(cfg3_frames, 300), n_cpu=0, with_concurrent=False,
+                                                                 pose_strict=True, scale_faithful=True)
     res["mono_sequence"] = mono_sequence_measurement(torch, dev, synth)
     res["sequence_orb"] = sequence_measurement(torch, dev, synth, n_frames=60, n_cpu=6, detector="orb", with_concurrent=False)
     res["lba_depthfilter"] = cfg4_measurement(ctx, synth)
@@ -883,7 +885,7 @@ def sequence_measurement(torch, dev, synth, n_frames=120, n_cpu=12, detector="ha
     return {"concurrent_sequences": conc, "detector": "K-det (Harris on the Scharr plane)" if detector == "harris" else "cv::ORB restated (the reference's extractor), FAST threshold 20",
             "pose_mode": "strict (sequential FP32 sums, the reference's arithmetic bit for bit; what the yaml constructor selects)" if pose_strict
                          else "fast (FP64 tree sums; the Parameters-struct default)",
-            "scale_border_mode": "reference-faithful stale sample buffers (yaml default)" if scale_faithful else "out-of-image samples masked (Parameters-struct default)",
+            "scale_border_mode": "reference-faithful stale sample buffers (opt-in: feature_tracker.scale_faithful_borders)" if scale_faithful else "out-of-image samples masked (default)",
             "frames": n_frames, "ms_per_frame_mean": float(ms.mean()), "ms_per_frame_median": float(np.median(ms)),
             "ms_per_non_keyframe": float(ms[~kf].mean()) if (~kf).any() else None,
             "ms_per_keyframe": float(ms[kf].mean()) if kf.any() else None,

@@ -106,7 +106,7 @@ def test_stereo_vo_from_reference_yaml(frames, tmp_path):
     # the yaml constructor is the drop-in path: the reference's extractor (cv::ORB restated) at feature_extractor.thres_fastscore
     # and the reference's arithmetic in the pose-only GN (strict-order sums)
     ref = svo.StereoVO(svo.make_parameters(W, H, K, K, synth.kitti_T_lr(), max_level=6, n_bins_u=32, n_bins_v=12, thres_trans=2.0,
-                                           detector="orb", thres_fastscore=20, pose_strict=True, scale_faithful_borders=True))
+                                           detector="orb", thres_fastscore=20, pose_strict=True))
     for k in range(len(L)):
         vo.trackStereoImages(L[k], R[k], 0.1 * k)
         ref.trackStereoImages(L[k], R[k], 0.1 * k)

@@ -140,7 +140,7 @@ def test_mono_vo_deterministic_and_yaml(seq, tmp_path):
     c = mvo.MonoVO(yaml_path=str(y))
     # the yaml constructor is the drop-in path: the reference's extractor (default FAST 20) and the reference's arithmetic
     # in the pose-only GN (strict-order sums)
-    d = _make(seed=0, detector="orb", thres_fastscore=20, pose_strict=True, scale_faithful_borders=True)
+    d = _make(seed=0, detector="orb", thres_fastscore=20, pose_strict=True)
     for k in range(5):
         c.trackImage(L[k], 0.1 * k)
         d.trackImage(L[k], 0.1 * k)

@@ -30,44 +30,46 @@ __global__ void __launch_bounds__(128) k_klt_scale(const KltScaleArgs a)
     klt_scale_feature(a, f, lane);
 }
 
-// Reference-faithful border mode, second pass: one warp per feature that had an out-of-image sample in the parallel pass.
-// The reference's buffer state in front of feature f is fully determined by the nearest earlier feature q that was live,
-// entered its iteration loop and had every sample inside the image (it rewrote every buffer entry and every mask is true
-// from then on) -- or by the empty initial state if there is none.  The warp replays q and every live feature between q and
-// f against that state (normally q = f - 1 and nothing in between) and then computes f exactly as the reference would.
-// A chain that reaches back more than KS_LOOKBACK features without finding such a q keeps the intended-semantics result.
-#define KS_LOOKBACK 512
+// Reference-faithful border mode, second pass.  A live feature that entered its iteration loop with every sample inside the
+// image rewrites every entry of the reference's sample buffers (and every mask is true from then on): the buffer state
+// behind such a "reset" feature does not depend on anything before it.  All other live features -- a sample outside the
+// image, or rejected before the iterations -- read and/or carry stale entries; maximal runs of them between two reset
+// features are CHAINS that the reference processes strictly in order.  One warp per chain (the warp of its first feature):
+// it replays the reset feature in front of the chain, if any, against an empty state, then walks the chain, computing each
+// feature exactly as the reference would and storing the results of those whose samples left the image.  The work is
+// linear in the chain lengths; the latency is that of the longest chain (features along an image edge that are neighbours
+// in the list, e.g. a row of border bins, form chains of a few dozen).
 __global__ void __launch_bounds__(128) k_klt_scale_fixup(const KltScaleArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= a.n) return;
-    const int fl = a.flags[f];
-    if ((fl & (KS_FLAG_PROCESSED | KS_FLAG_BORDER)) != (KS_FLAG_PROCESSED | KS_FLAG_BORDER)) return;
-    int q = -1;
-    bool gave_up = false;
-    for (int base = f - 1; base >= 0 && q < 0; base -= 32) {
-        if (f - base > KS_LOOKBACK) { gave_up = true; break; }
+    auto live = [&](int i) { return (a.flags[i] & KS_FLAG_PROCESSED) != 0; };
+    auto reset = [&](int i) { return (a.flags[i] & (KS_FLAG_PROCESSED | KS_FLAG_BORDER | KS_FLAG_RAN)) == (KS_FLAG_PROCESSED | KS_FLAG_RAN); };
+    if (!live(f) || reset(f)) return;
+    // nearest live feature in front of f
+    int p = -1;
+    for (int base = f - 1; base >= 0 && p < 0; base -= 32) {
         const int i = base - lane;
-        const bool reset = i >= 0 && (a.flags[i] & (KS_FLAG_PROCESSED | KS_FLAG_BORDER | KS_FLAG_RAN)) == (KS_FLAG_PROCESSED | KS_FLAG_RAN);
-        const unsigned m = __ballot_sync(0xffffffffu, reset);
-        if (m) q = base - (__ffs(m) - 1);
+        const unsigned m = __ballot_sync(0xffffffffu, i >= 0 && live(i));
+        if (m) p = base - (__ffs(m) - 1);
     }
-    if (gave_up) return;
+    if (p >= 0 && !reset(p)) return;             // f is inside a chain; the chain's first feature owns it
     KsState st;
     ks_state_clear(st);
     bool ok, nan_hit;
     float2 out;
-    for (int i = q < 0 ? 0 : q; i < f; ++i) {
-        if (!(a.flags[i] & KS_FLAG_PROCESSED)) continue;
-        klt_scale_feature_stale(a, i, lane, a.pre_pts[i], st, ok, out, nan_hit);
-    }
-    const float2 pt1 = a.pre_pts[f];
-    klt_scale_feature_stale(a, f, lane, pt1, st, ok, out, nan_hit);
-    if (lane == 0) {
-        if (nan_hit) atomicExch(a.nan_flag, 1);
-        a.mask[f] = ok ? 1 : 0;
-        a.pts_track[f] = ok ? out : pt1;          // a rejected feature keeps its input point (feature_tracker.cpp:489-500)
+    if (p >= 0) klt_scale_feature_stale(a, p, lane, a.pre_pts[p], st, ok, out, nan_hit);
+    for (int i = f; i < a.n; ++i) {
+        if (!live(i)) continue;
+        if (reset(i)) break;
+        const float2 pt1 = a.pre_pts[i];
+        klt_scale_feature_stale(a, i, lane, pt1, st, ok, out, nan_hit);
+        if ((a.flags[i] & KS_FLAG_BORDER) && lane == 0) {
+            if (nan_hit) atomicExch(a.nan_flag, 1);
+            a.mask[i] = ok ? 1 : 0;
+            a.pts_track[i] = ok ? out : pt1;      // a rejected feature keeps its input point (feature_tracker.cpp:489-500)
+        }
     }
 }
 

@@ -52,7 +52,7 @@ MonoVO::MonoVO(std::string mode, std::string directory_intrinsic)
     p_.detector = VO_DETECTOR_ORB;                                    // the reference's extractor
     p_.thres_fastscore = (int)num("feature_extractor.thres_fastscore", p_.thres_fastscore);   // initParams(..., int THRES_FAST, ...)
     p_.pose_strict = (int)num("motion_estimator.pose_strict", 1);     // yaml construction = drop-in use: the reference's arithmetic
-    p_.scale_faithful_borders = (int)num("feature_tracker.scale_faithful_borders", 1);
+    p_.scale_faithful_borders = (int)num("feature_tracker.scale_faithful_borders", 0);
     p_.thres_5p_error = (float)num("motion_estimator.thres_5p_error", p_.thres_5p_error);
     p_.thres_poseba_error = (float)num("motion_estimator.thres_poseba_error", p_.thres_poseba_error);
     p_.thres_overlap_ratio = (float)num("keyframe_update.thres_overlap_ratio", p_.thres_overlap_ratio);

@@ -76,7 +76,8 @@ public:
         // motion_estimator.pose_strict (ours; the reference has no such key)
         int pose_strict = 0;
         // trackWithScale samples outside the image: 1 = the reference's stale sample buffers reproduced (vo_set_scale_mode),
-        // 0 = masked out; yaml key feature_tracker.scale_faithful_borders (ours), 1 when constructed from yaml
+        // 0 = masked out (default: the faithful mode serialises the features along an image edge, +0.1-0.4 ms per frame);
+        // yaml key feature_tracker.scale_faithful_borders (ours)
         int scale_faithful_borders = 0;
     };
 

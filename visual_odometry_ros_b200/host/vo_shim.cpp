@@ -33,6 +33,17 @@ std::recursive_mutex &shared_mutex()
     throw std::runtime_error(msg);
 }
 
+static int g_scale_faithful = 0;
+
+// FeatureTracker::trackWithScale: reproduce the reference's never-reset sample buffers for samples that leave the image
+// (vo_set_scale_mode; off by default: the affected features are then processed in list order, as in the reference)
+void set_scale_faithful_borders(bool on)
+{
+    std::lock_guard<std::recursive_mutex> lock(shared_mutex());
+    g_scale_faithful = on ? 1 : 0;
+    if (g_ctx) vo_set_scale_mode(g_ctx, g_scale_faithful);
+}
+
 vo_ctx *shared_context(int min_w, int min_h)
 {
     std::lock_guard<std::recursive_mutex> lock(shared_mutex());
@@ -43,8 +54,7 @@ vo_ctx *shared_context(int min_w, int min_h)
     g_h = std::max(min_h, std::max(g_h, 1200));
     const int rc = vo_ctx_create(0, g_w, g_h, 5, 8192, nullptr, &g_ctx);      // slots 0-3: FeatureTracker, slot 4: FeatureExtractor
     if (rc != VO_OK) throw_status(nullptr, rc, nullptr);
-    // the shim stands in for the reference's classes: the reference's arithmetic, including trackWithScale's stale sample buffers
-    vo_set_scale_mode(g_ctx, 1);
+    vo_set_scale_mode(g_ctx, g_scale_faithful);
     return g_ctx;
 }
 

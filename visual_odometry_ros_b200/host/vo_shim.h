@@ -18,6 +18,7 @@ namespace vo_b200 {
 // holds shared_mutex() for its duration (the shim may be called from several threads; calls are serialised).
 vo_ctx *shared_context(int min_w = 0, int min_h = 0);
 void release_shared_context();
+void set_scale_faithful_borders(bool on);   // trackWithScale: the reference's stale sample buffers (vo_set_scale_mode), default off
 std::recursive_mutex &shared_mutex();
 [[noreturn]] void throw_status(vo_ctx *ctx, int status, const char *reference_message);
 }  // namespace vo_b200
