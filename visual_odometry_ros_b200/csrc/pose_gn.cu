@@ -555,7 +555,9 @@ k_pose_gn_cluster(const PoseArgs a)
 // profiles/r2_strict_*).  Blocks are 17 slots (272 bytes) apart, so the producers' 128-bit stores of eight neighbouring
 // points fall on eight different bank groups while the consumer's field offsets stay compile-time immediates.
 #define STRICT_PTS 128                 // points per chunk = 4 producer warps x 32 lanes
-#define STRICT_THREADS 160             // warp 0 = consumer, warps 1..4 = producers
+// warp 0 = consumer, four producer warps.  THREADS = 160: producers are warps 1..4 (batched solves: more CTAs per SM);
+// THREADS = 192: producers are warps 1, 2, 3, 5 and warp 4 idles, so that the consumer has its scheduler (warp % 4) to itself --
+// one large problem is bound by the consumer's chain of dependent adds (N = 2000: 0.278 -> 0.263 ms; the batch loses 18 % with it)
 #define STRICT_BLK 68                  // floats per block of four rows (16 fields x 4 + one slot of padding)
 #define STRICT_SMEM(RPP) (2 * (STRICT_PTS / (4 / (RPP)) + 2) * STRICT_BLK * 4)     // two buffers, each padded by two blocks (prefetch overrun)
 
@@ -592,8 +594,8 @@ struct RecSink {
     }
 };
 
-template <int RPP>   // rows per point: 2 mono, 4 stereo
-__global__ void __launch_bounds__(STRICT_THREADS)
+template <int RPP, int THREADS>   // rows per point: 2 mono, 4 stereo
+__global__ void __launch_bounds__(THREADS)
 k_pose_gn_strict(const PoseArgs a)
 {
     constexpr int PPB = 4 / RPP;                                   // points per block of four rows
@@ -637,6 +639,7 @@ k_pose_gn_strict(const PoseArgs a)
     else if (lane == 27) { wa = 13; wb = 14; }
 
     const int n_chunks = (n + STRICT_PTS - 1) / STRICT_PTS;
+    const int pw = (wid >= 1 && wid <= 3) ? wid - 1 : (wid == (THREADS == 192 ? 5 : 4) ? 3 : -1);      // producer index, -1 = not a producer
     int iter = 0;
     for (; iter < a.max_iter; ++iter) {
         float T10[12];
@@ -644,10 +647,10 @@ k_pose_gn_strict(const PoseArgs a)
         for (int i = 0; i < 12; ++i) T10[i] = s_T10[i];
         float acc = 0.f;
         for (int c = 0; c <= n_chunks; ++c) {
-            if (wid > 0) {
+            if (pw >= 0) {
                 if (c < n_chunks) {
-                    // producer: point (c * STRICT_PTS + p), p = lane of producer warp 1 .. 4
-                    const int p = (wid - 1) * 32 + lane;
+                    // producer: point (c * STRICT_PTS + p), p = lane of producer 0 .. 3
+                    const int p = pw * 32 + lane;
                     const int i = c * STRICT_PTS + p;
                     const int blk = p / PPB;
                     float *block = &s_rec[c & 1][blk * STRICT_BLK];
@@ -662,7 +665,7 @@ k_pose_gn_strict(const PoseArgs a)
                         for (int f = 0; f < 16; ++f) *reinterpret_cast<float2 *>(block + 4 * f + 2) = make_float2(0.f, 0.f);
                     }
                 }
-            } else if (c > 0) {
+            } else if (wid == 0 && c > 0) {
                 // consumer: chunk c-1, one block (four rows) per step, software-pipelined two blocks deep: the adds of block b
                 // run while the products of block b+1 are formed and the operands of block b+2 are loaded.
                 const int cc = c - 1;
@@ -739,12 +742,19 @@ int vo_pose_launch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_sin
         {   // 32 / 64 KB of dynamic shared memory (double-buffered row records); the attribute is process-wide: set once
             static std::once_flag once;
             std::call_once(once, [] {
-                cudaFuncSetAttribute(k_pose_gn_strict<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2));
-                cudaFuncSetAttribute(k_pose_gn_strict<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4));
+                cudaFuncSetAttribute(k_pose_gn_strict<2, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2));
+                cudaFuncSetAttribute(k_pose_gn_strict<4, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4));
+                cudaFuncSetAttribute(k_pose_gn_strict<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2));
+                cudaFuncSetAttribute(k_pose_gn_strict<4, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4));
             });
         }
-        if (mono) k_pose_gn_strict<2><<<n_prob, STRICT_THREADS, STRICT_SMEM(2), ctx->stream>>>(a);
-        else k_pose_gn_strict<4><<<n_prob, STRICT_THREADS, STRICT_SMEM(4), ctx->stream>>>(a);
+        if (n_prob == 1) {
+            if (mono) k_pose_gn_strict<2, 192><<<1, 192, STRICT_SMEM(2), ctx->stream>>>(a);
+            else k_pose_gn_strict<4, 192><<<1, 192, STRICT_SMEM(4), ctx->stream>>>(a);
+        } else {
+            if (mono) k_pose_gn_strict<2, 160><<<n_prob, 160, STRICT_SMEM(2), ctx->stream>>>(a);
+            else k_pose_gn_strict<4, 160><<<n_prob, 160, STRICT_SMEM(4), ctx->stream>>>(a);
+        }
         VO_CUDA(cudaGetLastError());
         return VO_OK;
     }
