@@ -530,19 +530,26 @@ def sharded_sequences(torch, dist, dev, local, rank, world, synth, barrier, max_
         vo.trackStereoImages(L[0], R[0], 0.0)
         vo.trackStereoImages(L[1], R[1], 0.1)
     errors = []
-    start = threading.Barrier(len(vos) + 1, timeout=300)
+    # host threads: at most one per core this rank can count on (every trackStereoImages ends in a stream synchronize, which
+    # spins; 64 threads on 16 cores made this figure swing between 2000 and 3600 frames/s from run to run).  A thread owns
+    # several sequences and advances them frame by frame in turn.
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    n_threads = max(1, min(len(vos), max(2, cores // max(1, world))))
+    start = threading.Barrier(n_threads + 1, timeout=300)
     kf_count = [0] * len(vos)
 
-    def run(j, vo, sidx):
+    def run(t):
         try:
-            L, R = rend[sidx % n_render]
+            own = list(range(t, len(vos), n_threads))
             start.wait()
             for k in range(2, n_frames):
-                vo.trackStereoImages(L[k], R[k], 0.1 * k)
-                kf_count[j] += vo.frame_info()["keyframe"]
+                for j in own:
+                    L, R = rend[mine[j] % n_render]
+                    vos[j].trackStereoImages(L[k], R[k], 0.1 * k)
+                    kf_count[j] += vos[j].frame_info()["keyframe"]
         except Exception as e:
             errors.append(repr(e))
-    th = [threading.Thread(target=run, args=(j, vo, sidx), daemon=True) for j, (vo, sidx) in enumerate(zip(vos, mine))]
+    th = [threading.Thread(target=run, args=(t,), daemon=True) for t in range(n_threads)]
     for t in th:
         t.start()
     barrier()
@@ -567,9 +574,10 @@ def sharded_sequences(torch, dist, dev, local, rank, world, synth, barrier, max_
         frames_all, kf_all, nerr = frames_rank, sum(kf_count), len(errors)
     res = {"sequences_total": n_seq_total, "sequences_per_rank": len(vos), "frames_each": n_frames - 2, "distinct_renderings": n_render,
            "frames_per_s": frames_all / (dt_ms * 1e-3), "ms_per_frame_amortised": dt_ms / max(1, frames_all) * 1.0,
-           "keyframes": kf_all, "errors": nerr, "first_error": errors[:1],
-           "what": "config 5: independent StereoVO sequences sharded over the ranks (one instance + thread + stream each), host u8 images in, "
-                   "pose out, keyframes + local BA included; wall clock between barriers, max over ranks"}
+           "keyframes": kf_all, "errors": nerr, "first_error": errors[:1], "host_threads_per_rank": n_threads,
+           "what": "config 5: independent StereoVO sequences sharded over the ranks (one instance + stream each, one host thread per "
+                   "available core driving its share of the sequences frame by frame), host u8 images in, pose out, keyframes + local BA "
+                   "included; wall clock between barriers, max over ranks"}
     if rank == 0 and world == 1:
         res["cpu"] = cpu_sequence_pool(synth, rend[0], n_frames=8)
     return res
