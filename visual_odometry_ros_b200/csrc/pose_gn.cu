@@ -364,10 +364,32 @@ __device__ __forceinline__ void pose_solve(const PoseArgs &a, const double *red,
             }
 }
 
-// THREADS per problem: 128 for the batched small problems (4 resident CTAs per SM overlap the serial solve of one
+// Transposing butterfly over a warp: in, every lane's NACC partials; out (return value), on lane L < NACC the warp total of
+// accumulator L.  At every level a lane keeps one half of its values and hands the other half to its partner: 31 exchanges
+// instead of NACC x 5.
+__device__ __forceinline__ double warp_transpose_sum(const double *acc, const int lane)
+{
+    double v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < NACC ? acc[k] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            const double send = up ? v[k] : v[k + o];
+            const double keep = up ? v[k + o] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+// THREADS per problem: 128 for the batched small problems (5 resident CTAs per SM at 96 registers -- 8.76 -> 8.97 M solves/s against 4
+// CTAs at 126, 6 CTAs at 80 registers spill: 8.65 M -- overlap the serial solve of one
 // problem with the point loops of the others), 512 for one large problem (the frame step: 2000+ points, 4 per thread).
 template <int POSE_THREADS>
-__global__ void __launch_bounds__(POSE_THREADS)
+__global__ void __launch_bounds__(POSE_THREADS, POSE_THREADS == 128 ? 5 : 1)
 k_pose_gn(const PoseArgs a)
 {
     __shared__ double s_part[POSE_THREADS / 32][NACC];
@@ -408,12 +430,9 @@ k_pose_gn(const PoseArgs a)
 
         pose_points(a, X, pl, pr, mask, n, tid, POSE_THREADS, T10, acc);
         // warp-level then block-level reduction of the 28 FP64 partials
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-            double v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0) s_part[wid][k] = v;
+        {
+            const double tot = warp_transpose_sum(acc, lane);
+            if (lane < NACC) s_part[wid][lane] = tot;
         }
         __syncthreads();
         if (tid < NACC) {
@@ -486,12 +505,9 @@ k_pose_gn_cluster(const PoseArgs a)
 #pragma unroll
         for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
         pose_points(a, X, pl, pr, mask, n, rank * 256 + tid, POSE_CLUSTER * 256, T10, acc);
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-            double v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0) s_part[wid][k] = v;
+        {
+            const double tot = warp_transpose_sum(acc, lane);
+            if (lane < NACC) s_part[wid][lane] = tot;
         }
         __syncthreads();
         if (tid < NACC) {
