@@ -186,8 +186,9 @@ VO_API int vo_pose_gn_stereo(vo_ctx *ctx, const float *X, const float *pts_l1, c
                       float thres_reproj_outlier, float *T01_inout, uint8_t *mask_inlier,
                       int *success, int *iters_out);
 /* Accumulation mode of the pose-only GN (and of the frame steps that run it).
- * VO_POSE_FAST (default): per-point rows in the reference's FP32 operation order, JtWJ / mJtWr / err summed in FP64 by a
- *   fixed tree and rounded once.  More accurate than the reference's sums, but the reference's stop test
+ * VO_POSE_FAST (default): residuals, weights, Jacobian rows and inlier masks per point in the reference's FP32 operation
+ *   order; the row products of JtWJ / mJtWr are formed and summed in FP64 (fused multiply-add on the FP32 factors, fixed
+ *   reduction tree) and rounded once.  More accurate than the reference's sums, but the reference's stop test
  *   `delta_err < 1e-7` (motion_estimator.cpp:1044,1063) fires when ITS sequential FP32 error sum repeats bit for bit, so
  *   the stop iteration can differ by one or two and the poses then differ by the size of the last updates.
  * VO_POSE_STRICT: the 28 sums are accumulated sequentially in FP32 in point order, exactly like

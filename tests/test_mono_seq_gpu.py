@@ -49,7 +49,9 @@ def test_mono_vo_class_next_to_oracle(seq, detector):
         return True, r["R10"], r["t10"], r["mask"]
     ora = omvo.MonoVOOracle(W, H, K, omvo.default_params(n_bins_u=NB_U, n_bins_v=NB_V, max_level=3, kf_trans=2.0, detector=detector,
                                                          fast_threshold=15), five_point=fp_gpu)
-    vo = _make(detector=detector, thres_fastscore=15)
+    # strict pose arithmetic (the reference's sequential FP32 sums): the fast mode's FP64 sums make the mono GN stop one iteration
+    # apart from the restatement on some frames (4e-4 m on ~150 points), which is a property of that mode, not of this class
+    vo = _make(detector=detector, thres_fastscore=15, pose_strict=True)
     same_ids = n_kf = n_lba = 0
     in_step = True            # no borderline feature has flipped between the two LK implementations yet
     for k in range(len(L)):

@@ -230,19 +230,22 @@ __device__ void ldlt6_solve(float *m_in /*6x6 row-major sym*/, const float *b, f
 template <int ZERO>
 __device__ __forceinline__ void acc_row(double *acc, const float *Jt, float w, float r, bool weighted)
 {
-    float wJ[6];
+    // FP64 fused multiply-adds on the converted FP32 factors: 12 conversions + 26 DFMA per row.  (The first version rounded every
+    // product to FP32 as the reference does and added it in FP64 -- FMUL + F2F + DADD per entry, 40 % of the batched kernel's
+    // instructions, profiles/r2_pose_batch_*; this mode does not reproduce the reference's sums anyway, VO_POSE_STRICT does.)
+    double dJ[6], dW[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) wJ[i] = weighted ? w * Jt[i] : Jt[i];
+    for (int i = 0; i < 6; ++i) { dJ[i] = (double)Jt[i]; dW[i] = (double)(weighted ? w * Jt[i] : Jt[i]); }
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = i; j < 6; ++j, ++idx)
-            if (i != ZERO && j != ZERO) acc[idx] += (double)(wJ[i] * Jt[j]);
-    const float wr = weighted ? w * r : r;
+            if (i != ZERO && j != ZERO) acc[idx] = __fma_rn(dW[i], dJ[j], acc[idx]);
+    const double nwr = -(double)(weighted ? w * r : r);
 #pragma unroll
     for (int i = 0; i < 6; ++i)
-        if (i != ZERO) acc[21 + i] -= (double)(wr * Jt[i]);
+        if (i != ZERO) acc[21 + i] = __fma_rn(nwr, dJ[i], acc[21 + i]);
 }
 
 // Residuals / Jacobian rows of ONE point handed to a sink, one call per row in the reference's row order (per-point
