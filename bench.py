@@ -671,7 +671,7 @@ def side_measurements(ctx, torch, dev, stream, lefts, rights, pts0_h, synth, cap
     res["pose_gn"] = {"solves_per_s": nprob / (ms * 1e-3), "batch": nprob, "points": npts, "ms_per_batch": ms,
                       "mean_iters": float(it_d.float().mean().item()),
                       "cpu_port_solves_per_s_1core": cpu_rate, "mode": "VO_POSE_FAST (FP64 tree sums)"}
-    res["roofline_pose"] = {"kernel": "k_pose_gn<128>", "bound": "hbm", "achieved": pose_bytes / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+    res["roofline_pose"] = {"kernel": "k_pose_gn<32>", "bound": "hbm", "achieved": pose_bytes / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
                             "frac": pose_bytes / (ms * 1e-3) / 1e9 / peak_hbm,
                             "flops": {"achieved_tflops": pose_flops / (ms * 1e-3) / 1e12, "peak_tflops_fp32_unfused": fp32_peak_nofma,
                                       "frac": pose_flops / (ms * 1e-3) / 1e12 / fp32_peak_nofma},

@@ -388,11 +388,13 @@ __device__ __forceinline__ double warp_transpose_sum(const double *acc, const in
     return v[0];
 }
 
-// THREADS per problem: 128 for the batched small problems (5 resident CTAs per SM at 96 registers -- 8.76 -> 8.97 M solves/s against 4
-// CTAs at 126, 6 CTAs at 80 registers spill: 8.65 M -- overlap the serial solve of one
-// problem with the point loops of the others), 512 for one large problem (the frame step: 2000+ points, 4 per thread).
+// THREADS per problem: 32 for the batched small problems -- one warp per solve, up to 20 resident CTAs per SM at 96 registers,
+// whose point loops overlap the serial 6 x 6 solve that one thread of another CTA runs (measured on 4096 x 500 points:
+// 128 threads, 4 CTAs/SM at 126 registers 8.76 M solves/s; 5 CTAs at 96 registers 8.97 M; 6 CTAs at 80 registers spill: 8.65 M;
+// with the fused FP64 accumulation 10.9 M at 128 threads, 11.5 M at 64, 11.7 M at 32); 512 for one large problem (2000+
+// points, 4 per thread) when the cluster kernel below is not used.
 template <int POSE_THREADS>
-__global__ void __launch_bounds__(POSE_THREADS, POSE_THREADS == 128 ? 5 : 1)
+__global__ void __launch_bounds__(POSE_THREADS, POSE_THREADS == 32 ? 20 : 1)
 k_pose_gn(const PoseArgs a)
 {
     __shared__ double s_part[POSE_THREADS / 32][NACC];
@@ -783,7 +785,7 @@ int vo_pose_launch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_sin
         VO_CUDA(cudaGetLastError());
         return VO_OK;
     }
-    if (n_prob > 1) k_pose_gn<128><<<n_prob, 128, 0, ctx->stream>>>(a);
+    if (n_prob > 1) k_pose_gn<32><<<n_prob, 32, 0, ctx->stream>>>(a);
     else k_pose_gn<512><<<n_prob, 512, 0, ctx->stream>>>(a);
     VO_CUDA(cudaGetLastError());
     return VO_OK;
