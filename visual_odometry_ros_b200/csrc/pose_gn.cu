@@ -575,12 +575,14 @@ k_pose_gn_cluster(const PoseArgs a)
 // version used two 32-bit loads per row and was bound by the shared-memory instruction rate, not by the add chain:
 // profiles/r2_strict_*).  Blocks are 17 slots (272 bytes) apart, so the producers' 128-bit stores of eight neighbouring
 // points fall on eight different bank groups while the consumer's field offsets stay compile-time immediates.
-#define STRICT_PTS 128                 // points per chunk = 4 producer warps x 32 lanes
-// warp 0 = consumer, four producer warps.  THREADS = 160: producers are warps 1..4 (batched solves: more CTAs per SM);
-// THREADS = 192: producers are warps 1, 2, 3, 5 and warp 4 idles, so that the consumer has its scheduler (warp % 4) to itself --
-// one large problem is bound by the consumer's chain of dependent adds (N = 2000: 0.278 -> 0.263 ms; the batch loses 18 % with it)
+#define STRICT_PTS_OF(THREADS) ((THREADS) == 64 ? 32 : ((THREADS) == 96 ? 64 : 128))      // points per chunk = producer warps x 32 lanes
+// warp 0 = consumer; producers: THREADS = 192 (one large problem): warps 1, 2, 3, 5, and warp 4 idles, so that the consumer has its
+// scheduler (warp % 4) to itself -- the solve is bound by the consumer's chain of dependent adds (N = 2000: 0.278 -> 0.265 ms);
+// THREADS = 64 (batched solves): ONE producer warp and chunks of 32 points, 18 KB of shared memory instead of 70 KB, so
+// seven CTAs fit an SM instead of three (4096 x 500 points: 4.67 -> 6.08 M solves/s; two producers per consumer: 5.66 M;
+// capping the registers at 96 for ten CTAs: 6.00 M).
 #define STRICT_BLK 68                  // floats per block of four rows (16 fields x 4 + one slot of padding)
-#define STRICT_SMEM(RPP) (2 * (STRICT_PTS / (4 / (RPP)) + 2) * STRICT_BLK * 4)     // two buffers, each padded by two blocks (prefetch overrun)
+#define STRICT_SMEM(RPP, THREADS) (2 * (STRICT_PTS_OF(THREADS) / (4 / (RPP)) + 2) * STRICT_BLK * 4)     // two buffers, each padded by two blocks (prefetch overrun)
 
 template <int RPP>
 struct RecSink {
@@ -620,6 +622,7 @@ __global__ void __launch_bounds__(THREADS)
 k_pose_gn_strict(const PoseArgs a)
 {
     constexpr int PPB = 4 / RPP;                                   // points per block of four rows
+    constexpr int STRICT_PTS = STRICT_PTS_OF(THREADS);
     constexpr int BLOCKS = STRICT_PTS / PPB;                       // blocks per chunk
     extern __shared__ __align__(16) float s_rec_dyn[];             // [2][(BLOCKS + 2) * STRICT_BLK]
     float (*s_rec)[(BLOCKS + 2) * STRICT_BLK] = reinterpret_cast<float (*)[(BLOCKS + 2) * STRICT_BLK]>(s_rec_dyn);
@@ -660,7 +663,8 @@ k_pose_gn_strict(const PoseArgs a)
     else if (lane == 27) { wa = 13; wb = 14; }
 
     const int n_chunks = (n + STRICT_PTS - 1) / STRICT_PTS;
-    const int pw = (wid >= 1 && wid <= 3) ? wid - 1 : (wid == (THREADS == 192 ? 5 : 4) ? 3 : -1);      // producer index, -1 = not a producer
+    const int pw = THREADS <= 96 ? (wid >= 1 ? wid - 1 : -1)
+                                 : ((wid >= 1 && wid <= 3) ? wid - 1 : (wid == (THREADS == 192 ? 5 : 4) ? 3 : -1));      // producer index, -1 = not a producer
     int iter = 0;
     for (; iter < a.max_iter; ++iter) {
         float T10[12];
@@ -763,18 +767,18 @@ int vo_pose_launch_ex_d(vo_ctx *ctx, int n_prob, const int *offsets_d, int n_sin
         {   // 32 / 64 KB of dynamic shared memory (double-buffered row records); the attribute is process-wide: set once
             static std::once_flag once;
             std::call_once(once, [] {
-                cudaFuncSetAttribute(k_pose_gn_strict<2, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2));
-                cudaFuncSetAttribute(k_pose_gn_strict<4, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4));
-                cudaFuncSetAttribute(k_pose_gn_strict<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2));
-                cudaFuncSetAttribute(k_pose_gn_strict<4, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4));
+                cudaFuncSetAttribute(k_pose_gn_strict<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2, 64));
+                cudaFuncSetAttribute(k_pose_gn_strict<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4, 64));
+                cudaFuncSetAttribute(k_pose_gn_strict<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(2, 192));
+                cudaFuncSetAttribute(k_pose_gn_strict<4, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRICT_SMEM(4, 192));
             });
         }
         if (n_prob == 1) {
-            if (mono) k_pose_gn_strict<2, 192><<<1, 192, STRICT_SMEM(2), ctx->stream>>>(a);
-            else k_pose_gn_strict<4, 192><<<1, 192, STRICT_SMEM(4), ctx->stream>>>(a);
+            if (mono) k_pose_gn_strict<2, 192><<<1, 192, STRICT_SMEM(2, 192), ctx->stream>>>(a);
+            else k_pose_gn_strict<4, 192><<<1, 192, STRICT_SMEM(4, 192), ctx->stream>>>(a);
         } else {
-            if (mono) k_pose_gn_strict<2, 160><<<n_prob, 160, STRICT_SMEM(2), ctx->stream>>>(a);
-            else k_pose_gn_strict<4, 160><<<n_prob, 160, STRICT_SMEM(4), ctx->stream>>>(a);
+            if (mono) k_pose_gn_strict<2, 64><<<n_prob, 64, STRICT_SMEM(2, 64), ctx->stream>>>(a);
+            else k_pose_gn_strict<4, 64><<<n_prob, 64, STRICT_SMEM(4, 64), ctx->stream>>>(a);
         }
         VO_CUDA(cudaGetLastError());
         return VO_OK;
