@@ -141,8 +141,8 @@ extern "C" int vo_ctx_destroy(vo_ctx *ctx)
     if (ctx->d_rect) cudaFree(ctx->d_rect);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
-    for (int i = 0; i < 2; ++i) if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
+    for (int i = 0; i < 3; ++i) if (ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); }
+    for (int i = 0; i < 4; ++i) if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VO_OK;
@@ -505,10 +505,12 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     // kernels of chunk c (compute stream). Slots of different chunks are disjoint, so the only
     // dependency is "chunk c's kernels wait for chunk c's upload" (one event per chunk).
     if (!ctx->copy_stream) VO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    // chunk sizes ramp up (8, 16, then CH pairs) so the pipeline fills after a short first DMA
-    constexpr int CH = 32;
+    // Uniform chunks of 16 pairs round-robin over FOUR compute streams (measured on 128 KITTI-size pairs: the round-1 ramp
+    // 8, 16, 32 ... on two streams 3.69 ms; 16-pair chunks on 2 / 3 / 4 streams 3.58 / 3.49 / 3.47 ms; 8-pair chunks on four
+    // streams 3.43 - 3.56 ms; against 3.0 - 3.1 ms for the same call with the images already resident).
+    constexpr int CH = 16, NS = 4, SZ0 = 16;
     std::vector<int> chunk_begin;
-    for (int c0 = 0, sz = 8; c0 < n_pairs; ) {
+    for (int c0 = 0, sz = SZ0; c0 < n_pairs; ) {
         chunk_begin.push_back(c0);
         c0 += sz < CH ? sz : CH;
         sz *= 2;
@@ -540,18 +542,18 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
     KltPost post{};
     post.mode = with_prior ? 2 : 1;
     post.thres_err = thres_err;
-    // Chunks alternate between two compute streams so that the tail wave of chunk c's LK kernel overlaps the
-    // pyramid / head of chunk c+1 (chunks touch disjoint slots and disjoint ranges of the point arrays).
-    if (!ctx->stream2) VO_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    if (!ctx->ev_aux[0]) for (int i = 0; i < 2; ++i) VO_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux[i], cudaEventDisableTiming));
+    // Chunks go round-robin over the compute streams so that the tail wave of chunk c's LK kernel overlaps the pyramids /
+    // heads of the next chunks (chunks touch disjoint slots and disjoint ranges of the point arrays).
+    for (int i = 0; i < 3; ++i) if (!ctx->side[i]) VO_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+    if (!ctx->ev_aux[0]) for (int i = 0; i < 4; ++i) VO_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux[i], cudaEventDisableTiming));
     cudaStream_t main_stream = ctx->stream;
     VO_CUDA(cudaEventRecord(ctx->ev_aux[0], main_stream));          // the point / mask uploads above
-    VO_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_aux[0], 0));
+    for (int i = 0; i < 3; ++i) VO_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_aux[0], 0));
     // error exits: nothing may stay queued on the side streams (vo_stage_reserve / the next call only order against ctx->stream)
     auto drain = [&](int code) {
         ctx->stream = main_stream;
         cudaStreamSynchronize(ctx->copy_stream);
-        cudaStreamSynchronize(ctx->stream2);
+        for (int i = 0; i < 3; ++i) cudaStreamSynchronize(ctx->side[i]);
         cudaStreamSynchronize(main_stream);
         return code;
     };
@@ -562,7 +564,7 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
         if (rc) return drain(rc);
         rc = upload_many(ctx, nc, slots1 + c0, imgs1 ? imgs1 + c0 : nullptr, w, h, step, up);
         if (rc) return drain(rc);
-        cudaStream_t cs = (!chained && (c & 1)) ? ctx->stream2 : main_stream;
+        cudaStream_t cs = (!chained && (c % NS)) ? ctx->side[c % NS - 1] : main_stream;
         if (!chained) {
             if (cudaEventRecord(ctx->events[c], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(cs, ctx->events[c], 0) != cudaSuccess) {
                 ctx->last_error = "vo_ft_track_batch: event record / wait failed";
@@ -578,7 +580,10 @@ extern "C" int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, co
         ctx->stream = main_stream;
         if (rc) return drain(rc);
     }
-    if (cudaEventRecord(ctx->ev_aux[1], ctx->stream2) != cudaSuccess || cudaStreamWaitEvent(main_stream, ctx->ev_aux[1], 0) != cudaSuccess) {
+    bool join_ok = true;
+    for (int i = 0; i < 3; ++i)
+        join_ok = join_ok && cudaEventRecord(ctx->ev_aux[1 + i], ctx->side[i]) == cudaSuccess && cudaStreamWaitEvent(main_stream, ctx->ev_aux[1 + i], 0) == cudaSuccess;
+    if (!join_ok) {
         ctx->last_error = "vo_ft_track_batch: joining the second compute stream failed";
         return drain(VO_ERR_CUDA);
     }

@@ -52,8 +52,8 @@ struct vo_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;      // image DMA overlapped with compute in the batched entry points
-    cudaStream_t stream2 = nullptr;          // second compute stream of the batched entry points (chunk overlap)
-    cudaEvent_t ev_aux[2] = {nullptr, nullptr};
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // extra compute streams of the batched entry points (chunk overlap)
+    cudaEvent_t ev_aux[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;
     int max_w = 0, max_h = 0, n_slots = 0, max_feat = 0;
     std::vector<Slot> slots;
