@@ -479,7 +479,7 @@ k_pose_gn_cluster(const PoseArgs a)
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     __shared__ double s_part[8][NACC];
-    __shared__ double s_cta[POSE_CLUSTER][NACC];      // used on rank 0: one row per CTA, written remotely
+    __shared__ double s_cta[2][POSE_CLUSTER][NACC];   // [iteration parity][source CTA]: every CTA receives every CTA's partials
     __shared__ float s_T10[16];
     __shared__ int s_stop;
     __shared__ float s_err_prev;
@@ -499,8 +499,11 @@ k_pose_gn_cluster(const PoseArgs a)
         s_stop = 0;
         s_err_prev = 1e10f;
     }
+    // only rank 0 records the per-iteration trace; the solve itself runs on every CTA (identical inputs in identical order
+    // give identical bits), which replaces the pose broadcast and the second cluster barrier of an iteration
+    PoseArgs a_solve = a;
+    if (rank != 0) a_solve.trace = nullptr;
     cluster.sync();
-    double *cta_row_on_rank0 = cluster.map_shared_rank(&s_cta[0][0], 0) + rank * NACC;
     int iter = 0;
     for (; iter < a.max_iter; ++iter) {
         float T10[12];
@@ -519,29 +522,28 @@ k_pose_gn_cluster(const PoseArgs a)
             double v = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) v += s_part[w][tid];
-            cta_row_on_rank0[tid] = v;
+            s_part[0][tid] = v;                      // column tid is read and written by this thread only
+        }
+        __syncthreads();
+        // all-gather through distributed shared memory: this CTA's 28 sums into row `rank` of every CTA's table
+        if (tid < NACC * POSE_CLUSTER) {
+            const int r = tid / NACC, k = tid - r * NACC;
+            *(cluster.map_shared_rank(&s_cta[iter & 1][0][0], r) + rank * NACC + k) = s_part[0][k];
         }
         cluster.sync();
-        if (rank == 0) {
-            if (tid < NACC) {
-                double v = 0.0;
+        if (tid < NACC) {
+            double v = 0.0;
 #pragma unroll
-                for (int r = 0; r < POSE_CLUSTER; ++r) v += s_cta[r][tid];
-                s_part[0][tid] = v;
-            }
-            __syncthreads();
-            if (tid == 0) pose_solve(a, &s_part[0][0], n, s_T10, &s_err_prev, &s_stop, 0, iter);
-            __syncthreads();
-            // broadcast the new pose (16 floats) and the stop flag to the other CTAs
-            if (tid < 17 * (POSE_CLUSTER - 1)) {
-                const int r = 1 + tid / 17, k = tid % 17;
-                if (k < 16) *(cluster.map_shared_rank(&s_T10[0], r) + k) = s_T10[k];
-                else *cluster.map_shared_rank(&s_stop, r) = s_stop;
-            }
+            for (int r = 0; r < POSE_CLUSTER; ++r) v += s_cta[iter & 1][r][tid];
+            s_part[1][tid] = v;
         }
-        cluster.sync();
+        __syncthreads();
+        if (tid == 0) pose_solve(a_solve, &s_part[1][0], n, s_T10, &s_err_prev, &s_stop, 0, iter);
+        __syncthreads();
         if (s_stop) { ++iter; break; }
     }
+    // nobody may leave while a peer can still write into its shared memory
+    cluster.sync();
     if (rank == 0 && tid == 0) {
         float nrm2 = 0.f;
         for (int i = 0; i < 16; ++i) nrm2 += s_T10[i] * s_T10[i];
