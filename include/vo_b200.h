@@ -147,7 +147,7 @@ VO_API int vo_ft_track_bidirection_with_prior(vo_ctx *ctx, int slot0, int slot1,
  * pinned memory makes the copies asynchronous; a NULL entry keeps the slot's current image),
  * pts0 / pts_track / mask_inout are [n_pairs][n].  One H2D per image, batched kernels, one
  * D2H of the results, one synchronisation. with_prior != 0 selects trackWithPrior.
- * Pairs whose slots are all distinct are pipelined in chunks (image DMA on a copy stream, chunks alternating between two
+ * Pairs whose slots are all distinct are pipelined in chunks (image DMA on a copy stream, chunks round-robin over four
  * compute streams).  A batch that reuses a slot across pairs (e.g. a chain slots1[i] == slots0[i+1] with imgs0[i+1] == NULL)
  * is detected and processed strictly in order on the context's stream: same results, no overlap. */
 VO_API int vo_ft_track_batch(vo_ctx *ctx, int n_pairs, const int *slots0, const int *slots1,
