@@ -392,6 +392,11 @@ VO_API int vo_inliers_1point_histogram(vo_ctx *ctx, const float *pts0, const flo
  * mapping::triangulateDLT (core/util/triangulate_3d.cpp:5-130). K0/K1: fx,fy,cx,cy. */
 VO_API int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const float *R10,
                        const float *t10, const float *K0_4, const float *K1_4, float *X0, float *X1);
+/* The same for points that do not share one relative pose: group[i] in [0, n_groups) selects R10s[group[i]] (9 floats,
+ * row-major) / t10s[group[i]] (3 floats).  MonoVO's reconstructions (mono_vo.cpp:660-687, :1032-1076) call triangulateDLT
+ * once per landmark with the pose of the frame of its first observation; this entry does the keyframe's batch in one launch. */
+VO_API int vo_triangulate_dlt_grouped(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const int *group, int n_groups,
+                               const float *R10s, const float *t10s, const float *K0_4, const float *K1_4, float *X0, float *X1);
 
 /* ------------------------------------------------------------------ depth filter
  * DepthFilter::updateNormalDistribution (standalone/depth_filter/depth_filter.cpp:3-13). */

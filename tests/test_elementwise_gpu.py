@@ -147,3 +147,33 @@ def test_compact_indexing_bit_exact(gpu_ctx, n):
     o = misc.compact(mask)
     assert np.array_equal(g, o)
     assert np.array_equal(g, np.flatnonzero(mask))
+
+
+def test_triangulate_dlt_grouped_equals_per_group_calls(gpu_ctx):
+    """vo_triangulate_dlt_grouped (one relative pose per group of points, one launch) == vo_triangulate_dlt per group, bit for
+    bit, == the oracle; out-of-range group indices are refused."""
+    from oracle import misc
+    from visual_odometry_ros_b200 import capi
+    rng = np.random.default_rng(77)
+    n, G = 900, 5
+    X, p0, p1, _, _, K = _stereo_obs(rng, n, 0.2)
+    Rs, ts = [], []
+    for g in range(G):
+        w = rng.normal(0, 0.02, 3)
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        Rs.append((np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx).astype(np.float32))
+        ts.append(np.array([-0.5 - 0.1 * g, 0.01 * g, 0.02 * g], np.float32))
+    group = rng.integers(0, G, n).astype(np.int32)
+    X0, X1 = gpu_ctx.triangulate_dlt_grouped(p0, p1, group, np.stack(Rs), np.stack(ts), K, K)
+    for g in range(G):
+        sel = group == g
+        a0, a1 = gpu_ctx.triangulate_dlt(p0[sel], p1[sel], Rs[g], ts[g], K, K)
+        o0, o1 = misc.triangulate_dlt(p0[sel], p1[sel], Rs[g], ts[g], K, K)
+        assert np.array_equal(X0[sel], a0) and np.array_equal(X1[sel], a1)
+        assert np.array_equal(X0[sel], o0) and np.array_equal(X1[sel], o1)
+    bad = group.copy()
+    bad[3] = G
+    with pytest.raises(capi.VoError):
+        gpu_ctx.triangulate_dlt_grouped(p0, p1, bad, np.stack(Rs), np.stack(ts), K, K)

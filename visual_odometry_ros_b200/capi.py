@@ -139,6 +139,7 @@ def lib():
     L.vo_get_scale_mode.argtypes = [vp]
     L.vo_get_pose_mode.argtypes = [vp]
     L.vo_triangulate_dlt.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    L.vo_triangulate_dlt_grouped.argtypes = [vp, vp, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     L.vo_depth_filter_normal.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.vo_depth_filter_student_t.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp, vp]
     L.vo_depth_filter_normal_d.argtypes = L.vo_depth_filter_normal.argtypes
@@ -417,6 +418,22 @@ class Context:
         X1 = np.zeros((n, 3), np.float32)
         check(self.h, self.L.vo_triangulate_dlt(self.h, _ptr(p0), _ptr(p1), n, _ptr(R), _ptr(t), _ptr(K0), _ptr(K1),
                                                 _ptr(X0), _ptr(X1)))
+        return X0, X1
+
+    def triangulate_dlt_grouped(self, pts0, pts1, group, R10s, t10s, K0, K1=None):
+        """triangulateDLT with one relative pose per group of points -> (X0, X1)."""
+        p0 = np.ascontiguousarray(pts0, np.float32).reshape(-1, 2)
+        p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        g = np.ascontiguousarray(group, np.int32)
+        n = len(p0)
+        Rs = np.ascontiguousarray(R10s, np.float32).reshape(-1, 9)
+        ts = np.ascontiguousarray(t10s, np.float32).reshape(-1, 3)
+        K0 = np.ascontiguousarray(K0, np.float32)
+        K1 = K0 if K1 is None else np.ascontiguousarray(K1, np.float32)
+        X0 = np.zeros((n, 3), np.float32)
+        X1 = np.zeros((n, 3), np.float32)
+        check(self.h, self.L.vo_triangulate_dlt_grouped(self.h, _ptr(p0), _ptr(p1), n, _ptr(g), len(Rs), _ptr(Rs), _ptr(ts), _ptr(K0),
+                                                        _ptr(K1), _ptr(X0), _ptr(X1)))
         return X0, X1
 
     def epipolar_distance(self, pts0, pts1, K4=None, R10=None, t10=None, F10=None, symmetric=False):

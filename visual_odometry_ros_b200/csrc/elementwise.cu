@@ -34,6 +34,33 @@ __global__ void __launch_bounds__(128) k_triangulate(const TriArgs a)
     for (int r = 0; r < 3; ++r) { a.X0[3 * i + r] = X0[r]; a.X1[3 * i + r] = X1[r]; }
 }
 
+// the same with one relative pose per GROUP of points (MonoVO's keyframe reconstruction pairs every landmark with the frame
+// of its first observation: a handful of distinct frames per keyframe, one launch instead of one call per frame)
+struct TriGroupArgs {
+    const float2 *p0, *p1;
+    const int *group;          // [n]
+    const float *Rt;           // [n_groups][12]: R10 row-major (9), t10 (3)
+    float *X0, *X1;
+    int n;
+    float K0[4], K1[4];
+};
+
+__global__ void __launch_bounds__(128) k_triangulate_grouped(const TriGroupArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float *rt = a.Rt + 12 * a.group[i];
+    float R10[9], t10[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R10[k] = rt[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t10[k] = rt[9 + k];
+    float X0[3], X1[3];
+    tri_point(a.p0[i], a.p1[i], R10, t10, a.K0, a.K1, X0, X1);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { a.X0[3 * i + r] = X0[r]; a.X1[3 * i + r] = X1[r]; }
+}
+
 // ------------------------------------------------------------------------------ K-df
 __global__ void __launch_bounds__(256)
 k_df_normal(const double *xp, const double *cp, const double *__restrict__ xc,
@@ -196,6 +223,40 @@ extern "C" int vo_triangulate_dlt(vo_ctx *ctx, const float *pts0, const float *p
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(X0, h + oX0, (size_t)n * 12);
     memcpy(X1, h + oX1, (size_t)n * 12);
+    return VO_OK;
+}
+
+extern "C" int vo_triangulate_dlt_grouped(vo_ctx *ctx, const float *pts0, const float *pts1, int n, const int *group, int n_groups,
+                                          const float *R10s, const float *t10s, const float *K0_4, const float *K1_4, float *X0, float *X1)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_REQUIRE(n >= 0 && n_groups >= 0, VO_ERR_INVALID_ARG, "negative size");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(pts0 && pts1 && group && R10s && t10s && K0_4 && K1_4 && X0 && X1 && n_groups > 0, VO_ERR_INVALID_ARG, "null pointer");
+    for (int i = 0; i < n; ++i) VO_REQUIRE(group[i] >= 0 && group[i] < n_groups, VO_ERR_INVALID_ARG, "group index out of range");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)n;
+    const size_t o0 = 0, o1 = N * 8, oG = N * 16, oRt = oG + (N * 4 + 15) / 16 * 16, in_bytes = oRt + (size_t)n_groups * 48;
+    const size_t oX0 = (in_bytes + 15) / 16 * 16, oX1 = oX0 + N * 12, total = oX1 + N * 12;
+    int rc = vo_stage_reserve(ctx, total);
+    if (rc) return rc;
+    uint8_t *h = ctx->h_stage, *d = ctx->d_stage;
+    memcpy(h + o0, pts0, N * 8);
+    memcpy(h + o1, pts1, N * 8);
+    memcpy(h + oG, group, N * 4);
+    for (int g = 0; g < n_groups; ++g) { memcpy(h + oRt + (size_t)g * 48, R10s + 9 * g, 36); memcpy(h + oRt + (size_t)g * 48 + 36, t10s + 3 * g, 12); }
+    VO_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TriGroupArgs a;
+    a.p0 = (const float2 *)(d + o0); a.p1 = (const float2 *)(d + o1); a.group = (const int *)(d + oG); a.Rt = (const float *)(d + oRt);
+    a.X0 = (float *)(d + oX0); a.X1 = (float *)(d + oX1); a.n = n;
+    memcpy(a.K0, K0_4, 16); memcpy(a.K1, K1_4, 16);
+    k_triangulate_grouped<<<vo_div_up(n, 128), 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    VO_CUDA(cudaGetLastError());
+    VO_CUDA(cudaMemcpyAsync(h + oX0, d + oX0, N * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(X0, h + oX0, N * 12);
+    memcpy(X1, h + oX1, N * 12);
     return VO_OK;
 }
 

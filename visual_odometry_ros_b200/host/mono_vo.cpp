@@ -213,23 +213,20 @@ int MonoVO::dltGroups(const std::vector<int> &cand, const std::vector<float> &pt
     std::vector<int> groups(f0);
     std::sort(groups.begin(), groups.end());
     groups.erase(std::unique(groups.begin(), groups.end()), groups.end());
-    std::vector<float> a, b, xa, xb;
-    std::vector<int> sel;
-    for (int g : groups) {
-        sel.clear(); a.clear(); b.clear();
-        for (size_t j = 0; j < n; ++j)
-            if (f0[j] == g) { sel.push_back((int)j); a.push_back(pt0[2 * j]); a.push_back(pt0[2 * j + 1]); b.push_back(pt1[2 * j]); b.push_back(pt1[2 * j + 1]); }
-        float T10[16], R10[9], t10[3];
-        mul4_f(f1.Tcw, frames_[g]->Twc, T10);
-        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R10[r * 3 + c] = T10[r * 4 + c]; t10[r] = T10[r * 4 + 3]; }
-        xa.resize(sel.size() * 3); xb.resize(sel.size() * 3);
-        const int rc = vo_triangulate_dlt(ctx_, a.data(), b.data(), (int)sel.size(), R10, t10, p_.K, p_.K, xa.data(), xb.data());
-        if (rc) fail(ctx_, rc);
-        for (size_t q = 0; q < sel.size(); ++q) {
-            memcpy(&X0[(size_t)sel[q] * 3], &xa[q * 3], 12);
-            memcpy(&X1[(size_t)sel[q] * 3], &xb[q * 3], 12);
-        }
+    // one device call for the whole batch: the relative pose T10 = T1w * Tw0 of every distinct first-observation frame, and per
+    // point the index of its group (the first version made one call -- upload, launch, download, sync -- per distinct frame:
+    // 0.3 ms per keyframe)
+    std::vector<float> R10s(groups.size() * 9), t10s(groups.size() * 3);
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        float T10[16];
+        mul4_f(f1.Tcw, frames_[groups[gi]]->Twc, T10);
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R10s[gi * 9 + r * 3 + c] = T10[r * 4 + c]; t10s[gi * 3 + r] = T10[r * 4 + 3]; }
     }
+    std::vector<int> gidx(n);
+    for (size_t j = 0; j < n; ++j) gidx[j] = (int)(std::lower_bound(groups.begin(), groups.end(), f0[j]) - groups.begin());
+    const int rc = vo_triangulate_dlt_grouped(ctx_, pt0.data(), pt1.data(), (int)n, gidx.data(), (int)groups.size(), R10s.data(), t10s.data(),
+                                              p_.K, p_.K, X0.data(), X1.data());
+    if (rc) fail(ctx_, rc);
     return (int)groups.size();
 }
 
