@@ -355,7 +355,7 @@ void MonoVO::localBundleAdjustment()
         const size_t n = fr.lm_ids.size();
         for (size_t i = 0; i < n; ++i) {
             const int id = fr.lm_ids[i];
-            if (!lm_tri_[id] || !lm_alive_[id]) continue;
+            if (lm_seen_stamp_[id] != seen_stamp_) continue;          // stamped in pass 1 <=> triangulated and alive
             const int s = lm_lba_slot_[id];
             if (s < 0) continue;
             const int o = cursor[s]++;

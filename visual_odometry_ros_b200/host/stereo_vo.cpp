@@ -254,7 +254,7 @@ void StereoVO::localBundleAdjustment()
         const size_t n = fr.lm_ids.size();
         for (size_t i = 0; i < n; ++i) {
             const int id = fr.lm_ids[i];
-            if (!lm_tri_[id] || !lm_alive_[id]) continue;
+            if (lm_seen_stamp_[id] != seen_stamp_) continue;          // stamped in pass 1 <=> triangulated and alive
             const int o = cursor[lm_lba_slot_[id]];
             cursor[lm_lba_slot_[id]] = o + 2;
             obs_frame[o] = k; obs_frame[o + 1] = k;
