@@ -457,6 +457,9 @@ typedef struct vo_lba_problem {
  * VO_ERR_INVALID_ARG with the outputs untouched.  VO_ERR_NAN mirrors the reference's "Local BA NAN!" exception. */
 VO_API int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *prob, double *poses_out, double *points_out,
                  double *avg_err_out, int *success);
+/* Device scratch of the local BA ahead of time (grow-only; vo_lba_solve sizes it on demand otherwise, which costs the first
+ * keyframe with a local BA a cudaMalloc of 32 MB: ~1 ms).  StereoVO / MonoVO call it in their constructors. */
+VO_API int vo_lba_reserve(vo_ctx *ctx, size_t bytes);
 
 /* ------------------------------------------------------------------ oversize windows on several GPUs (NCCL over NVLink)
  * BASELINE.json north_star / SURVEY 8(e): the LANDMARKS of one local-BA window are partitioned over the ranks (one process +

@@ -1045,6 +1045,50 @@ extern "C" int vo_dist_finalize(vo_ctx *ctx)
 static int lba_solve_impl(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out, double *avg_err_out, int *success,
                           bool dist);
 
+extern "C" int vo_lba_reserve(vo_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return VO_ERR_INVALID_ARG;
+    VO_CUDA(cudaSetDevice(ctx->device));
+    if (bytes <= ctx->lba_bytes) return VO_OK;
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_lba) cudaFree(ctx->d_lba);
+    ctx->d_lba = nullptr; ctx->lba_bytes = 0;
+    VO_CUDA(cudaMalloc(&ctx->d_lba, bytes));
+    ctx->lba_bytes = bytes;
+    // one tiny well-posed window through the whole path: function attributes, first launches of the three kernels and the
+    // staging buffers are then out of the way before the first real keyframe (it was 0.9 ms slower than the next ones)
+    {
+        const int N = 3, M = 8;
+        double poses[N * 16], pts[M * 3], px[M * N * 2], poses_o[N * 16], pts_o[M * 3], avg[2];
+        int opt_index[N] = {-1, -1, 0}, obs_ptr[M + 1], obs_frame[M * N];
+        uint8_t obs_right[M * N];
+        for (int f = 0; f < N; ++f)
+            for (int k = 0; k < 16; ++k) poses[f * 16 + k] = (k % 5 == 0) ? 1.0 : (k == 3 ? -0.1 * f : 0.0);     // T_jw: camera f sits at x = 0.1 f
+        for (int i = 0; i < M; ++i) {
+            pts[3 * i] = 0.2 * (i % 3) - 0.2; pts[3 * i + 1] = 0.15 * (i / 3) - 0.15; pts[3 * i + 2] = 1.0 + 0.1 * i;
+            obs_ptr[i] = i * N;
+            for (int f = 0; f < N; ++f) {
+                const int o = i * N + f;
+                obs_frame[o] = f; obs_right[o] = 0;
+                px[2 * o] = 700.0 * (pts[3 * i] - 0.1 * f) / pts[3 * i + 2] + 600.0 + 0.3 * ((i + f) % 3 - 1);
+                px[2 * o + 1] = 700.0 * pts[3 * i + 1] / pts[3 * i + 2] + 180.0;
+            }
+        }
+        obs_ptr[M] = M * N;
+        vo_lba_problem w;
+        memset(&w, 0, sizeof(w));
+        w.n_frames = N; w.n_opt = 1; w.n_points = M; w.n_obs = M * N;
+        w.poses = poses; w.opt_index = opt_index; w.points = pts; w.obs_ptr = obs_ptr; w.obs_frame = obs_frame; w.obs_right = obs_right; w.obs_px = px;
+        w.K_l[0] = w.K_r[0] = 700; w.K_l[1] = w.K_r[1] = 700; w.K_l[2] = w.K_r[2] = 600; w.K_l[3] = w.K_r[3] = 180;
+        for (int k = 0; k < 16; ++k) w.T_lr[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        w.is_stereo = 0; w.huber = 0.5; w.lambda = 1e-5; w.max_iter = 2;
+        int ok = 0;
+        const int rc = lba_solve_impl(ctx, &w, poses_o, pts_o, avg, &ok, false);
+        if (rc != VO_OK && rc != VO_ERR_NAN) return rc;       // the warm-up's numbers do not matter, a CUDA failure does
+    }
+    return VO_OK;
+}
+
 extern "C" int vo_lba_solve(vo_ctx *ctx, const vo_lba_problem *p, double *poses_out, double *points_out,
                             double *avg_err_out, int *success)
 {

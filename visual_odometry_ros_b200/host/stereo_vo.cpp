@@ -94,6 +94,8 @@ void StereoVO::init()
     if (rp) fail(ctx_, rp);
     const int rs = vo_set_scale_mode(ctx_, p_.scale_faithful_borders);
     if (rs) fail(ctx_, rs);
+    const int rl = vo_lba_reserve(ctx_, (size_t)32 << 20);       // the first local BA then allocates nothing inside the frame loop
+    if (rl) fail(ctx_, rl);
     const int rd = vo_set_detector(ctx_, p_.detector, p_.thres_fastscore);
     if (rd) fail(ctx_, rd);
     {   // landmark tables: room for 2^19 landmarks (several hundred frames) before the first reallocation, which would
