@@ -442,8 +442,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_klt3<21>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_klt3 launch (64 pairs x 2000 features) from the
-                     # committed `ncu --set full` capture profiles/r2_v1_klt3_full_raw.csv: 243.25 MB + 9.60 MB
-                     "traffic": 252.9e6 if klt_launches_per_step * 64 == P else None, "traffic_source": "profiles/r2_v1_klt3_full_raw.csv",
+                     # committed `ncu --set full` capture profiles/r2_v2_klt3_full_raw.csv (final round-2 binary): 243.22 MB + 5.24 MB
+                     "traffic": 248.5e6 if klt_launches_per_step * 64 == P else None, "traffic_source": "profiles/r2_v2_klt3_full_raw.csv",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": klt_bytes_per_step / klt_launches_per_step,
                      "launch_ms": klt_ms / klt_launches_per_step, "launches_per_step": klt_launches_per_step,
